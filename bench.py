@@ -1,0 +1,383 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the CuSMC hot path on B200 (contract: see the task brief).
+
+Workload (BASELINE.json configs[1]): batched MVN log-density, d = 16, N = 2^20 points per step,
+shared covariance, fp64.  A "step" is one pass of the density kernel over one batch; batches
+rotate through a pool larger than L2 so no step re-reads cached input.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); points are sharded across ranks with no
+data-path collective (weak scaling: every rank evaluates its own 2^20-point batches).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+N_POINTS = 1 << 20
+DIM = 16
+BYTES_PER_EVAL = 8 * DIM + 8          # read the point, write the result
+POOL_BATCHES = 8                      # 8 x 128 MiB = 1 GiB of resident input > 126 MB L2
+METRIC = "mvn_logpdf_evals_per_sec"
+UNIT = "evals/s"
+
+
+def workload_inputs():
+    """Synthetic inputs of SURVEY.md section 8d (C2)."""
+    A = np.random.default_rng(1235).standard_normal((DIM, DIM))
+    sigma = A @ A.T / DIM + np.eye(DIM)
+    mu = np.random.default_rng(1236).standard_normal(DIM)
+    return mu, sigma
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+
+    def start(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                       "--format=csv,noheader,nounits", "-lms", "50"],
+                                      stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.12)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().strip().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arms (the oracle is test infrastructure; bench.py may time it as the reported CPU baseline)
+# ------------------------------------------------------------------------------------------------
+def cpu_faithful_evals_per_sec(n_sample, repeats=1):
+    """The reference's own CPU arithmetic for this path: per-point determinant() + inverse() (LU)
+    and the left-to-right quadratic form (src/statistics.cc.cpp:171-180 called per particle,
+    src/mcmc.cpp:193-215), OpenMP over points on all host cores."""
+    from oracle_lib import oracle
+    orc = oracle()
+    mu, sigma = workload_inputs()
+    x = np.random.default_rng(1234).standard_normal((n_sample, DIM))
+    orc.pdf_batch("mvn", x[:4096], mu, sigma, faithful=True)      # warm the thread pool
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.pdf_batch("mvn", x, mu, sigma, faithful=True)
+        best = min(best, time.perf_counter() - t0)
+    return n_sample / best, orc.num_threads(), best
+
+
+def cpu_hoisted_evals_per_sec(n_sample):
+    from oracle_lib import oracle
+    orc = oracle()
+    mu, sigma = workload_inputs()
+    x = np.random.default_rng(1234).standard_normal((n_sample, DIM))
+    orc.pdf_batch("mvn", x[:4096], mu, sigma, log=True)
+    t0 = time.perf_counter()
+    orc.pdf_batch("mvn", x, mu, sigma, log=True)
+    return n_sample / (time.perf_counter() - t0)
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (restated oracle, faithful
+    mode; the reference itself needs R + Rcpp + Eigen and cannot be built in this image)."""
+    if rank != 0:
+        return
+    n_sample = 1 << 17
+    times = []
+    from oracle_lib import oracle
+    orc = oracle()
+    mu, sigma = workload_inputs()
+    x = np.random.default_rng(1234).standard_normal((n_sample, DIM))
+    for s in range(args.warmup + args.steps):
+        t0 = time.perf_counter()
+        orc.pdf_batch("mvn", x, mu, sigma, faithful=True)
+        dt = time.perf_counter() - t0
+        if s >= args.warmup:
+            times.append(dt)
+    total = sum(times)
+    value = n_sample * len(times) / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "batched MVN pdf d=16 shared covariance fp64 (BASELINE configs[1])",
+                   "points_per_step": n_sample, "dim": DIM,
+                   "note": "CPU restatement of the reference (oracle, faithful per-point LU), bounded sample"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+                         "sample": "%d points per step, faithful mode" % n_sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# secondary workloads (reported inside the same JSON line; they do not affect `value`)
+# ------------------------------------------------------------------------------------------------
+def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
+    out = {}
+    I2 = np.eye(2)
+    try:
+        # C4: bootstrap PF on data_raw/y_t.csv, 1M particles, systematic resampling every step
+        Y = np.loadtxt(os.path.join(ROOT, "tests", "golden", "y_t.csv"), delimiter=",", skiprows=1).T
+        T = 101 if quick else 1000
+        N = 1000000
+        pf = ctx.filter(N=N, Y=Y[:, :T], m0=np.zeros(2), C0=I2, F=I2, G=I2, V=0.1 * I2, W=0.1 * I2,
+                        resampler="systematic", seed=1, summary=False)
+        pf.run()
+        ctx.synchronize()
+        l0 = ctx.launch_count
+        pf.run()
+        ms = pf.last_ms
+        launches = ctx.launch_count - l0
+        pf.close()
+        rate = N * (T - 1) / (ms * 1e-3)
+        out["pf_c4_particle_steps_per_sec"] = {
+            "value": rate, "N": N, "d": 2, "T": T, "ms_per_step": ms / (T - 1), "resampler": "systematic",
+            "noise": "philox in-kernel", "bytes_per_particle_step": 64,
+            "roofline_frac": rate * 64 / (hbm_gbs * 1e9), "launches_per_step": launches / T}
+    except Exception as e:   # a secondary failure must not hide the headline
+        out["pf_c4_particle_steps_per_sec"] = {"error": repr(e)}
+    try:
+        # C5 per-GPU shard: d = 8, 8 Mi particles, synthetic state-space model
+        d, N, T = 8, 8 << 20, (11 if quick else 41)
+        I = np.eye(d)
+        Y = np.random.default_rng(5000).standard_normal((d, T))
+        pf = ctx.filter(N=N, Y=Y, m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=I, W=I, resampler="systematic",
+                        seed=2, summary=False)
+        pf.run()
+        pf.run()
+        ms = pf.last_ms
+        pf.close()
+        rate = N * (T - 1) / (ms * 1e-3)
+        out["pf_c5_shard_particle_steps_per_sec"] = {
+            "value": rate, "N": N, "d": d, "T": T, "ms_per_step": ms / (T - 1), "resampler": "systematic",
+            "noise": "philox in-kernel", "bytes_per_particle_step": 160,
+            "roofline_frac": rate * 160 / (hbm_gbs * 1e9)}
+    except Exception as e:
+        out["pf_c5_shard_particle_steps_per_sec"] = {"error": repr(e)}
+    try:
+        # C3: 65 536 independent MH chains, MVT target d = 32, per-chain covariance
+        Cn, d, steps = 65536, 32, (50 if quick else 200)
+        g = torch.Generator(device="cuda").manual_seed(2000)
+        A = torch.randn((Cn, d, d), dtype=torch.float64, device="cuda", generator=g)
+        S = A @ A.transpose(1, 2) / d + torch.eye(d, dtype=torch.float64, device="cuda")
+        L = torch.linalg.cholesky(S)
+        Lcm = L.transpose(1, 2).contiguous()
+        del A, S
+        mu = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+        x = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+        nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+        ctx.use_torch_stream()
+        ctx.mh_chains_dev("mvt", mu, Lcm, x, 5, 0.3, nu=5.0, seed=3, n_accept=nacc)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=4, n_accept=nacc)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        rate = Cn * steps / (ms * 1e-3)
+        out["mh_c3_chain_steps_per_sec"] = {
+            "value": rate, "chains": Cn, "d": d, "steps": steps, "ms": ms, "target": "mvt nu=5 per-chain L",
+            "noise": "philox in-kernel", "accept_rate": float(nacc.double().mean().item() / steps),
+            "flops_per_chain_step": 2 * d * (d + 1) + 4 * d,
+            "fp64_tflops": rate * (2 * d * (d + 1) + 4 * d) / 1e12}
+    except Exception as e:
+        out["mh_c3_chain_steps_per_sec"] = {"error": repr(e)}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--quick", action="store_true", help="shorter secondary workloads")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: cusmc_b200 has no CPU fallback"}))
+        return 1
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    import cusmc_b200
+    ctx = cusmc_b200.Context(local_rank)
+    ctx.use_torch_stream()
+    hbm_gbs, peak_src = measured_peaks()
+
+    mu, sigma = workload_inputs()
+    g = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    pool = [torch.randn((DIM, N_POINTS), dtype=torch.float64, device="cuda", generator=g) for _ in range(POOL_BATCHES)]
+    out = torch.empty(N_POINTS, dtype=torch.float64, device="cuda")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        ctx.logpdf_dev("mvn", pool[i % POOL_BATCHES], mu, sigma, out, log=True)
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.1)
+    l0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for i in range(args.steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - l0
+    clocks = sampler.stop()
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    value = world * N_POINTS * args.steps / (ms_max * 1e-3)
+    kernel_ms = ms / args.steps
+    achieved = BYTES_PER_EVAL * N_POINTS / (kernel_ms * 1e-3) / 1e9
+
+    # ---- end to end through the host-pointer C ABI: pinned host AoS in, host result out --------
+    e2e_steps = max(3, min(args.steps, 20))
+    host_x = [torch.randn((N_POINTS, DIM), dtype=torch.float64).pin_memory() for _ in range(2)]
+    host_out = torch.empty(N_POINTS, dtype=torch.float64).pin_memory()
+    lib = ctx.lib
+    mu_c = np.ascontiguousarray(mu)
+    sg_c = np.ascontiguousarray(sigma.T).ravel()
+
+    def e2e_step(i):
+        rc = lib.cusmc_logpdf(ctx.h, 0, 1, host_x[i % 2].data_ptr(), 1, N_POINTS, N_POINTS, DIM,
+                              mu_c.ctypes.data, sg_c.ctypes.data, 0.0, host_out.data_ptr())
+        if rc:
+            raise RuntimeError(lib.cusmc_last_error(ctx.h).decode())
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * N_POINTS * e2e_steps / float(te.item())
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "batched MVN log-density, d=16, N=2^20 points/step/GPU, shared covariance, "
+                               "fp64 (BASELINE configs[1]); SoA device-resident input",
+                   "points_per_step_per_gpu": N_POINTS, "dim": DIM,
+                   "l2_policy": "inputs rotate through a %d-batch pool (%.0f MiB) larger than the 126 MB L2"
+                                % (POOL_BATCHES, POOL_BATCHES * N_POINTS * DIM * 8 / 2 ** 20),
+                   "parallelism": "points sharded across ranks, no data-path collective"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
+                     "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                     "kernel": "density_soa_kernel<16,true,2>", "algorithmic_bytes_per_launch": BYTES_PER_EVAL * N_POINTS,
+                     "kernel_ms": kernel_ms},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
+                "d2h_bytes_per_step": N_POINTS * 8, "steps": e2e_steps,
+                "path": "cusmc_logpdf (host pointers, pinned AoS in, pinned result out)"},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if rank == 0:
+        try:
+            v, cores, secs = cpu_faithful_evals_per_sec(1 << 17)
+            line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                    "sample": "2^17 of the 2^20 points, faithful mode (per-point LU det+inverse "
+                                              "as src/mcmc.cpp:211-212), %.1f s" % secs,
+                                    "hoisted_value": cpu_hoisted_evals_per_sec(1 << 20)}
+        except Exception as e:
+            line["cpu_baseline"] = {"error": repr(e)}
+        if not args.no_secondary and world == 1:
+            line["secondary"] = secondary_benchmarks(ctx, torch, hbm_gbs, args.quick)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

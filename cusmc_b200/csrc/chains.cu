@@ -1,0 +1,298 @@
+// chains.cu -- per-chain / per-point covariance paths (BASELINE.json configs[2]):
+//
+//  * mh_chains_kernel: independent random-walk Metropolis-Hastings chains on an MVN / MVT
+//    target, one warp per chain.  Lane k keeps row k of the chain's Cholesky factor in
+//    registers for the whole run, so a step reads only its d normals (+ threshold) from HBM:
+//    proposal x' = x + s L z is a shuffle-broadcast mat-vec, whitening v = L^-1 (x' - mu) a
+//    column-oriented forward substitution, accept/reject a transcendental-free comparison.
+//  * perpoint_kernel: log-density with one covariance per point; each warp pulls its point's
+//    packed factor into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
+//    double buffered) and runs the same forward substitution.
+//
+// The density arithmetic restates src/statistics.cc.cpp:171-196,295-324 in whitened form; the
+// chains themselves have no counterpart in the reference -- the oracle
+// (orc_mh_chains) fixes the operation order these kernels reproduce bit for bit.
+#include "common.cuh"
+#include "density.cuh"
+#include "hostmath.h"
+
+#include "../../include/cusmc_detmath.h"
+#include "../../include/cusmc_philox.h"
+
+namespace {
+
+constexpr int kWarpsPerBlock = 4;
+
+// Forward substitution, column oriented.  On entry lane k holds r_k; row[j] = L[k][j] (0 for
+// j > k or outside d), rinv = 1 / L[k][k] (0 outside d).  Returns q = sum_k v_k^2 in every lane.
+template <int D>
+__device__ __forceinline__ double whiten_q(const double (&row)[D], double rinv, double r)
+{
+    double q = 0.0;
+#pragma unroll
+    for (int j = 0; j < D; ++j) {
+        const double vj = __shfl_sync(0xffffffffu, r * rinv, j);
+        q = fma(vj, vj, q);
+        r = fma(-row[j], vj, r);   // no-op for lanes k < j (row[j] == 0); lane j is done with r
+    }
+    return q;
+}
+
+struct ChainArgs {
+    const double *mu, *L, *z, *thr;
+    double *x, *sum_x, *sum_xx;
+    uint32_t *n_accept;
+    uint8_t *accept_bits;
+    int64_t C;
+    uint64_t seed;
+    double step_size, nu;
+    int d, steps, kind, shared;
+};
+
+template <int D, bool PHILOX>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+mh_chains_kernel(const ChainArgs a)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    if (c >= a.C) return;
+    const int d = a.d;
+    const bool live = lane < d;
+    const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
+    const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
+    double row[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) row[j] = (live && j <= lane) ? __ldg(Lc + (size_t)j * d + lane) : 0.0;
+    const double rinv = live ? 1.0 / __ldg(Lc + (size_t)lane * d + lane) : 0.0;
+    const double mu = live ? __ldg(mc + lane) : 0.0;
+    double x = live ? a.x[(size_t)c * d + lane] : 0.0;
+    double q = whiten_q<D>(row, rinv, x - mu);
+    const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
+    double sx = 0.0, sxx = 0.0;
+    uint32_t nacc = 0;
+
+    const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
+    double z_next = (zc && live) ? ld_stream(zc + lane) : 0.0;
+    for (int s = 0; s < a.steps; ++s) {
+        double z, thr;
+        if (PHILOX) {
+            double z0, z1;
+            cusmc_normal_pair(cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)s, (uint64_t)c, (uint32_t)(lane >> 1)), &z0, &z1);
+            z = live ? ((lane & 1) ? z1 : z0) : 0.0;
+            const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)s, (uint64_t)c, 0);
+            const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+            thr = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+        } else {
+            z = z_next;
+            if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + lane);   // prefetch
+            thr = __ldg(a.thr + (size_t)c * a.steps + s);
+        }
+        // proposal: x' = x + step * (L z), row k = sum_{j <= k} L[k][j] z_j, j ascending
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) acc = fma(row[j], __shfl_sync(0xffffffffu, z, j), acc);
+        const double xp = fma(a.step_size, acc, x);
+        const double qp = whiten_q<D>(row, rinv, xp - mu);
+        bool accept;
+        if (a.kind == CUSMC_MVT)
+            accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
+        else
+            accept = 0.5 * (qp - q) < thr;
+        if (accept) {
+            x = xp;
+            q = qp;
+            ++nacc;
+        }
+        sx += x;
+        sxx = fma(x, x, sxx);
+        if (a.accept_bits && lane == 0) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
+    }
+    if (live) {
+        a.x[(size_t)c * d + lane] = x;
+        if (a.sum_x) a.sum_x[(size_t)c * d + lane] = sx;
+        if (a.sum_xx) a.sum_xx[(size_t)c * d + lane] = sxx;
+    }
+    if (a.n_accept && lane == 0) a.n_accept[c] = nacc;
+}
+
+// ---- per-point covariance log-density -------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "bra WAIT_%=;\n\t"
+        "DONE_%=:\n\t}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// 1-D TMA: global -> shared bulk copy that completes on an mbarrier (SASS: UBLKCP).
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+struct PerPointArgs {
+    const double *x, *mu, *L;
+    double *out;
+    int64_t N;
+    int d, use_tma;
+};
+
+template <int D>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+perpoint_kernel(const PerPointArgs a, const Epilogue ep, const double lognorm_base)
+{
+    constexpr int kPacked = D * (D + 1) / 2;
+    __shared__ __align__(128) double s_L[kWarpsPerBlock][2][kPacked + (kPacked & 1)];
+    __shared__ __align__(8) uint64_t s_bar[kWarpsPerBlock][2];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int d = a.d;
+    const int packed = d * (d + 1) / 2;
+    const uint32_t bytes = (uint32_t)(packed * sizeof(double));
+    const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerBlock;
+    const int64_t w0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
+    const bool live = lane < d;
+
+    if (a.use_tma && lane == 0) {
+        mbar_init(&s_bar[wib][0], 1);
+        mbar_init(&s_bar[wib][1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+    auto issue = [&](int64_t pt, int buf) {
+        if (a.use_tma) {
+            if (lane == 0) {
+                mbar_expect_tx(&s_bar[wib][buf], bytes);
+                tma_load_1d(&s_L[wib][buf][0], a.L + (size_t)pt * packed, bytes, &s_bar[wib][buf]);
+            }
+        } else {
+            const double *src = a.L + (size_t)pt * packed;
+            for (int e = lane; e < packed; e += 32) s_L[wib][buf][e] = ld_stream(src + e);
+        }
+    };
+    if (w0 < a.N) issue(w0, 0);
+    uint32_t phase[2] = {0, 0};
+    int buf = 0;
+    for (int64_t pt = w0; pt < a.N; pt += n_warps, buf ^= 1) {
+        const int64_t nxt = pt + n_warps;
+        if (nxt < a.N) issue(nxt, buf ^ 1);          // prefetch the next factor
+        double r = live ? ld_stream(a.x + (size_t)pt * d + lane) - (a.mu ? ld_stream(a.mu + (size_t)pt * d + lane) : 0.0) : 0.0;
+        if (a.use_tma) {
+            mbar_wait(&s_bar[wib][buf], phase[buf]);
+            phase[buf] ^= 1;
+        } else {
+            __syncwarp();
+        }
+        double row[D];
+        const int off = lane * (lane + 1) / 2;
+#pragma unroll
+        for (int j = 0; j < D; ++j) row[j] = (live && j <= lane) ? s_L[wib][buf][off + j] : 0.0;
+        const double diag = live ? s_L[wib][buf][off + lane] : 1.0;
+        __syncwarp();                                 // everyone has read the buffer before it is refilled
+        const double rinv = live ? 1.0 / diag : 0.0;
+        const double q = whiten_q<D>(row, rinv, r);
+        // log det Sigma = 2 sum log L_kk
+        double ld = live ? log(diag) : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+        if (lane == 0) {
+            Epilogue e2 = ep;
+            e2.lognorm = lognorm_base - ld;           // lognorm_base excludes -1/2 log det
+            e2.scale = exp(e2.lognorm);
+            st_stream(a.out + pt, density_epilogue(e2, q));
+        }
+    }
+}
+
+}  // namespace
+
+extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps, double step_size,
+                                   double nu, int shared, const double *mu_dev, const double *L_dev,
+                                   double *x_dev, const double *z_dev, const double *thr_dev, uint64_t seed,
+                                   uint32_t *n_accept_dev, uint8_t *accept_bits_dev, double *sum_x_dev,
+                                   double *sum_xx_dev)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, C >= 0 && steps >= 0 && d >= 1, "bad sizes");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || kind == CUSMC_MVT, "unknown distribution");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || nu > 0.0, "mvt needs nu > 0");
+    CUSMC_REQUIRE(ctx, (z_dev == nullptr) == (thr_dev == nullptr), "z and thr must both be given or both NULL");
+    CUSMC_REQUIRE(ctx, C == 0 || (mu_dev && L_dev && x_dev), "NULL pointer");
+    if (d > 32) return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d = %d > 32", d);
+    if (C == 0) return CUSMC_OK;
+    ChainArgs a;
+    a.mu = mu_dev; a.L = L_dev; a.z = z_dev; a.thr = thr_dev;
+    a.x = x_dev; a.sum_x = sum_x_dev; a.sum_xx = sum_xx_dev;
+    a.n_accept = n_accept_dev; a.accept_bits = accept_bits_dev;
+    a.C = C; a.seed = seed; a.step_size = step_size; a.nu = nu;
+    a.d = d; a.steps = steps; a.kind = kind; a.shared = shared;
+    const unsigned grid = (unsigned)((C + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const bool philox = z_dev == nullptr;
+#define CUSMC_CHAIN_CASE(DD)                                                                         \
+    case DD:                                                                                         \
+        if (philox) mh_chains_kernel<DD, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);    \
+        else mh_chains_kernel<DD, false><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);          \
+        break;
+    switch (cusmc_pad_dim(d)) {
+        CUSMC_CHAIN_CASE(2)
+        CUSMC_CHAIN_CASE(4)
+        CUSMC_CHAIN_CASE(8)
+        CUSMC_CHAIN_CASE(16)
+        CUSMC_CHAIN_CASE(32)
+    }
+#undef CUSMC_CHAIN_CASE
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_logpdf_perpoint_dev(cusmc_ctx *ctx, int kind, int want_log, const double *x_dev,
+                                         const double *mu_dev, const double *L_dev, int64_t N, int d,
+                                         float nu, double *out_dev)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1, "bad sizes");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || kind == CUSMC_MVT, "unknown distribution");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || nu > 0.0f, "mvt needs nu > 0");
+    CUSMC_REQUIRE(ctx, N == 0 || (x_dev && L_dev && out_dev), "NULL pointer");
+    if (d > 32) return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d = %d > 32", d);
+    if (N == 0) return CUSMC_OK;
+    Epilogue ep{};
+    ep.kind = kind;
+    ep.want_log = want_log;
+    double base;   // log normalising constant without the -1/2 log det term
+    if (kind == CUSMC_MVN) {
+        base = hostmath::mvn_lognorm(0.0, d);
+    } else {
+        base = hostmath::mvt_lognorm(0.0, d, nu);
+        ep.half_nu_d = hostmath::mvt_half_nu_plus_d(nu, d);
+        ep.inv_nu = 1.0 / (double)nu;
+    }
+    PerPointArgs a;
+    a.x = x_dev; a.mu = mu_dev; a.L = L_dev; a.out = out_dev; a.N = N; a.d = d;
+    const size_t bytes = sizeof(double) * (size_t)d * (d + 1) / 2;
+    a.use_tma = (bytes % 16 == 0) && ((uintptr_t)L_dev % 16 == 0);
+    int64_t grid = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
+    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    if (grid > cap) grid = cap;
+    switch (cusmc_pad_dim(d)) {
+        case 2: perpoint_kernel<2><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
+        case 4: perpoint_kernel<4><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
+        case 8: perpoint_kernel<8><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
+        case 16: perpoint_kernel<16><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
+        default: perpoint_kernel<32><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
+    }
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}

@@ -1,0 +1,103 @@
+// common.cuh -- context object, error plumbing and launch helpers shared by every
+// translation unit of libcusmc_b200.so.  sm_100a only; no CPU fallback anywhere.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/cusmc_b200.h"
+
+#define CUSMC_NUM_SCRATCH 8
+
+struct cusmc_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t launches = 0;
+    double last_ms = 0.0;
+    std::string err;
+    // grow-only device scratch used by the host-pointer entry points
+    void *scratch[CUSMC_NUM_SCRATCH] = {};
+    size_t scratch_cap[CUSMC_NUM_SCRATCH] = {};
+    // pinned staging for small device->host reads (status words, stats)
+    void *pinned = nullptr;
+    size_t pinned_cap = 0;
+};
+
+inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    return code;
+}
+
+// The reference's CUDA_CALL (inst/include/support.cuh:9-20) prints and throws; here a
+// failed runtime call becomes a status code plus a message on the context.
+#define CUSMC_CUDA(ctx, call)                                                          \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess)                                                         \
+            return cusmc_fail((ctx), CUSMC_ERR_CUDA, "%s:%d: %s failed: %s", __FILE__,  \
+                              __LINE__, #call, cudaGetErrorString(e__));                \
+    } while (0)
+
+#define CUSMC_CHECK(expr)                 \
+    do {                                  \
+        int rc__ = (expr);                \
+        if (rc__ != CUSMC_OK) return rc__; \
+    } while (0)
+
+#define CUSMC_REQUIRE(ctx, cond, msg)                                             \
+    do {                                                                          \
+        if (!(cond)) return cusmc_fail((ctx), CUSMC_ERR_INVALID, "%s: %s", __func__, (msg)); \
+    } while (0)
+
+// Checked after every launch; counts the launch for bench.py's gpu_launches.
+#define CUSMC_LAUNCHED(ctx)                                                          \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess)                                                      \
+            return cusmc_fail((ctx), CUSMC_ERR_CUDA, "%s:%d: kernel launch failed: %s", \
+                              __FILE__, __LINE__, cudaGetErrorString(e__));          \
+        (ctx)->launches++;                                                           \
+    } while (0)
+
+int cusmc_scratch(cusmc_ctx *ctx, int slot, size_t bytes, void **out);
+int cusmc_pinned(cusmc_ctx *ctx, size_t bytes, void **out);
+
+// ---- device helpers ----------------------------------------------------------------
+// Streaming (read-once / write-once) accesses: keep them out of L1 and mark evict-first.
+__device__ __forceinline__ double ld_stream(const double *p) { return __ldcs(p); }
+__device__ __forceinline__ double2 ld_stream2(const double *p)
+{
+    return __ldcs(reinterpret_cast<const double2 *>(p));
+}
+__device__ __forceinline__ void st_stream(double *p, double v) { __stcs(p, v); }
+__device__ __forceinline__ void st_stream2(double *p, double2 v)
+{
+    __stcs(reinterpret_cast<double2 *>(p), v);
+}
+
+// Order-preserving map double <-> uint64 so atomicMax on integers gives the fp64 max
+// (deterministic: max is associative and commutative).
+__device__ __forceinline__ unsigned long long ordered_from_double(double v)
+{
+    unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double double_from_ordered(unsigned long long o)
+{
+    unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
+    return __longlong_as_double((long long)b);
+}

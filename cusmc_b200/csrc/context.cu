@@ -1,0 +1,107 @@
+// context.cu -- context lifetime, stream binding, grow-only scratch.
+//
+// Ownership model: the context owns device scratch, stream and
+// events; the caller owns host buffers.  The reference instead cudaMalloc/cudaFree-s
+// 8-10 buffers and calls cudaDeviceReset() on every time step
+// (src/mvn_dist.cu.cpp:231-240,305-314,788) -- none of that survives here.
+#include "common.cuh"
+
+#include <new>
+
+extern "C" int cusmc_version(void) { return CUSMC_VERSION; }
+
+extern "C" int cusmc_ctx_create(cusmc_ctx **out, int device)
+{
+    if (!out) return CUSMC_ERR_INVALID;
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) return CUSMC_ERR_CUDA;   // no CPU fallback, by design
+    if (device < 0 || device >= n_dev) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = new (std::nothrow) cusmc_ctx();
+    if (!ctx) return CUSMC_ERR_CUDA;
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess ||
+        cudaDeviceGetAttribute(&ctx->sm_count, cudaDevAttrMultiProcessorCount, device) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) {
+        delete ctx;
+        return CUSMC_ERR_CUDA;
+    }
+    ctx->stream = ctx->own_stream;
+    *out = ctx;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_ctx_destroy(cusmc_ctx *ctx)
+{
+    if (!ctx) return CUSMC_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < CUSMC_NUM_SCRATCH; ++s)
+        if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return CUSMC_OK;
+}
+
+extern "C" const char *cusmc_last_error(const cusmc_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : "cusmc: NULL context (no CUDA device, or creation failed)";
+}
+
+extern "C" int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_ctx_synchronize(cusmc_ctx *ctx)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return CUSMC_OK;
+}
+
+extern "C" uint64_t cusmc_ctx_launch_count(const cusmc_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" double cusmc_ctx_last_kernel_ms(const cusmc_ctx *ctx) { return ctx ? ctx->last_ms : 0.0; }
+
+int cusmc_scratch(cusmc_ctx *ctx, int slot, size_t bytes, void **out)
+{
+    if (slot < 0 || slot >= CUSMC_NUM_SCRATCH) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "bad scratch slot");
+    if (bytes > ctx->scratch_cap[slot]) {
+        CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+        if (ctx->scratch[slot]) {
+            CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            CUSMC_CUDA(ctx, cudaFree(ctx->scratch[slot]));
+            ctx->scratch[slot] = nullptr;
+            ctx->scratch_cap[slot] = 0;
+        }
+        const size_t cap = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        CUSMC_CUDA(ctx, cudaMalloc(&ctx->scratch[slot], cap));
+        ctx->scratch_cap[slot] = cap;
+    }
+    *out = ctx->scratch[slot];
+    return CUSMC_OK;
+}
+
+int cusmc_pinned(cusmc_ctx *ctx, size_t bytes, void **out)
+{
+    if (bytes > ctx->pinned_cap) {
+        if (ctx->pinned) {
+            CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            CUSMC_CUDA(ctx, cudaFreeHost(ctx->pinned));
+            ctx->pinned = nullptr;
+            ctx->pinned_cap = 0;
+        }
+        const size_t cap = bytes < 4096 ? 4096 : bytes;
+        CUSMC_CUDA(ctx, cudaMallocHost(&ctx->pinned, cap));
+        ctx->pinned_cap = cap;
+    }
+    *out = ctx->pinned;
+    return CUSMC_OK;
+}

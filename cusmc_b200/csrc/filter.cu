@@ -1,0 +1,946 @@
+// filter.cu -- the particle-filter step and the time loop.
+//
+// One fused kernel per step replaces the reference's eight (Gmu, sample, y_minus_Fmu,
+// Einv_alpha, pdf + RNG set-up kernels; src/mvn_dist.cu.cpp:33-172,455-668) and the host-side
+// ancestor gather / AoS flattening / H2D+D2H of the whole particle cloud every step
+// (src/mvn_dist.cu.cpp:194-205,231-251,300-302): a thread owns one child particle,
+//
+//     parent  = anc[i]
+//     x_new   = mu + G x_prev[:, parent] + noise_i          noise = Q xi | chi (.) (Q xi)
+//     lw[i]   = log pdf_V(y_t - F x_new)   (or the density, reference mode)
+//     max     = atomic max over lw (for the max-shifted normalisation)
+//
+// State is SoA and stays on the device for the whole run; G, Q and the whitened observation
+// operator ride in the kernel parameter bank.
+#include "density.cuh"
+#include "hostmath.h"
+#include "resample.cuh"
+
+#include "../../include/cusmc_detmath.h"
+#include "../../include/cusmc_philox.h"
+
+#include <cmath>
+#include <new>
+#include <vector>
+
+int cusmc_density_launch(cusmc_ctx *ctx, bool tri, int m, int d, const std::vector<double> &M_rowmajor,
+                         const double *shift, const double *off, const Epilogue &ep, const double *x,
+                         int layout, int64_t N, int64_t ld, double *out);
+int cusmc_build_whitening(cusmc_ctx *ctx, int kind, int want_log, int d, const double *sigma, float nu,
+                          std::vector<double> &W_rowmajor, Epilogue &ep);
+
+namespace {
+
+constexpr int kThreads = 256;
+
+template <int D>
+struct StepOp {
+    double G[D * D];   // row-major transition
+    double Q[D * D];   // row-major noise factor (already multiplied by noise_scale)
+    double M[D * D];   // row-major whitened observation operator  L_V^-1 F
+    double c[D];       // L_V^-1 y_t
+    double mu[D];      // additive location (m0 at t = 0, otherwise 0)
+};
+
+struct StepArgs {
+    double *x_new;
+    const double *x_prev;
+    const uint32_t *anc;
+    const double *xi;
+    const double *chi;
+    double *lw;
+    double *lw_max;              // optional
+    unsigned long long *zero_ptr; // optional: words to clear for the next scan
+    int64_t zero_n;
+    int64_t n_out, ld_new, ld_prev, ld_noise;
+    int64_t i0;                  // global index of child 0 (keys the counter-based draws)
+    int64_t parent_base;         // global index of x_prev column 0
+    uint64_t seed, step;
+    double const_weight;         // used when skip_weight
+    float nu;
+    int d, dy, kind, has_prev, skip_weight, rng_stream;
+};
+
+__device__ __forceinline__ void atomic_max_double(double *addr, double v)
+{
+    if (v != v) return;
+    if (v >= 0.0)
+        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+    else
+        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2): Marsaglia-Tsang with reproducible
+// log/exp (the reference's curand_gamma / curand_chi_square, src/mvt_dist.cu.cpp:20-61).
+__device__ __noinline__ double chi_factor(uint64_t seed, uint64_t step, uint64_t index, int k, float nu)
+{
+    const double a0 = 0.5 * (double)nu;
+    const double a = a0 < 1.0 ? a0 + 1.0 : a0;
+    const double dd = a - 1.0 / 3.0;
+    const double cc = 1.0 / sqrt(9.0 * dd);
+    double g = dd;
+    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
+        const uint32_t sub = ((uint32_t)k << 8) | attempt;
+        double z0, z1;
+        cusmc_normal_pair(cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub), &z0, &z1);
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub | 0x800000u);
+        const double t = fma(cc, z0, 1.0);
+        const double v = t * t * t;
+        if (v > 0.0) {
+            const double lu = cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+            if (lu < fma(0.5 * z0, z0, dd) - dd * v + dd * cusmc_det_log(v)) {
+                g = dd * v;
+                if (a0 < 1.0) {
+                    const double lb = cusmc_det_log(cusmc_u01_open0(r.v[2], r.v[3]));
+                    g = g * cusmc_det_exp(lb / a0);
+                }
+                break;
+            }
+        }
+    }
+    return sqrt((double)nu / (2.0 * g));
+}
+
+// MVT is a template flag so the MVN kernel carries neither the chi branch nor the call to the
+// (rejection-loop) chi-square sampler, whose calling convention alone costs ~30 registers.
+template <int D, bool PHILOX, bool MVT>
+__global__ void __launch_bounds__(kThreads, (D >= 32 ? 1 : (D >= 16 ? 2 : (D >= 8 ? 3 : 4))))
+pf_step_kernel(const __grid_constant__ StepOp<D> op, const Epilogue ep, const StepArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (a.zero_ptr && i < a.zero_n) a.zero_ptr[i] = 0ull;
+    const bool active = i < a.n_out;
+    double lw = -INFINITY;
+    if (active) {
+        double xp[D], z[D], xn[D];
+        int64_t parent = i;
+        if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
+#pragma unroll
+        for (int j = 0; j < D; ++j)
+            xp[j] = (a.has_prev && j < a.d) ? __ldg(a.x_prev + (int64_t)j * a.ld_prev + parent) : 0.0;
+        if (PHILOX) {
+#pragma unroll
+            for (int jp = 0; jp < D / 2; ++jp) {
+                double z0 = 0.0, z1 = 0.0;
+                if (2 * jp < a.d)
+                    cusmc_normal_pair(cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), (uint32_t)jp), &z0, &z1);
+                z[2 * jp] = z0;
+                z[2 * jp + 1] = (2 * jp + 1 < a.d) ? z1 : 0.0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j)
+                z[j] = (j < a.d) ? ld_stream(a.xi + (int64_t)j * a.ld_noise + i) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double g = op.mu[k];
+#pragma unroll
+            for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
+            double s = 0.0;
+#pragma unroll
+            for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
+            if (MVT && k < a.d) {
+                const double chi = a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i)
+                                         : chi_factor(a.seed, a.step, (uint64_t)(a.i0 + i), k, a.nu);
+                s = chi * s;
+            }
+            xn[k] = s + g;
+            if (k < a.d) st_stream(a.x_new + (int64_t)k * a.ld_new + i, xn[k]);
+        }
+        if (a.skip_weight) {
+            lw = a.const_weight;
+        } else {
+            double q = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double zk = op.c[k];
+#pragma unroll
+                for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
+                q = fma(zk, zk, q);
+            }
+            lw = density_epilogue(ep, q);
+        }
+        st_stream(a.lw + i, lw);
+    }
+    if (a.lw_max) {
+        double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __shared__ double sm[kThreads / 32];
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (threadIdx.x == 0) atomic_max_double(a.lw_max, m);
+        }
+    }
+}
+
+// ---- layout transposes through shared memory (coalesced on both sides) ----------------------
+__global__ void __launch_bounds__(kThreads)
+aos_to_soa_kernel(const double *__restrict__ aos, double *__restrict__ soa, int64_t N, int64_t ld, int d)
+{
+    extern __shared__ double tile[];
+    const int pitch = d | 1;
+    const int64_t base = (int64_t)blockIdx.x * kThreads;
+    const int npts = (int)((N - base) < kThreads ? (N - base) : kThreads);
+    const int n_el = npts * d;
+    for (int e = threadIdx.x; e < n_el; e += kThreads) {
+        const int row = e / d, col = e - row * d;
+        tile[row * pitch + col] = aos[base * d + e];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < npts)
+        for (int j = 0; j < d; ++j) soa[(int64_t)j * ld + base + threadIdx.x] = tile[threadIdx.x * pitch + j];
+}
+
+__global__ void __launch_bounds__(kThreads)
+soa_to_aos_kernel(const double *__restrict__ soa, double *__restrict__ aos, int64_t N, int64_t ld, int d)
+{
+    extern __shared__ double tile[];
+    const int pitch = d | 1;
+    const int64_t base = (int64_t)blockIdx.x * kThreads;
+    const int npts = (int)((N - base) < kThreads ? (N - base) : kThreads);
+    if ((int)threadIdx.x < npts)
+        for (int j = 0; j < d; ++j) tile[threadIdx.x * pitch + j] = soa[(int64_t)j * ld + base + threadIdx.x];
+    __syncthreads();
+    const int n_el = npts * d;
+    for (int e = threadIdx.x; e < n_el; e += kThreads) {
+        const int row = e / d, col = e - row * d;
+        aos[base * d + e] = tile[row * pitch + col];
+    }
+}
+
+// Weighted first moments and weight sums of one step: out[0] += sum w, out[1] += sum w^2,
+// out[2 + k] += sum w x_k, with w = exp(lw - max) (log mode) or the raw density.
+__global__ void __launch_bounds__(kThreads)
+moments_kernel(const double *__restrict__ x, const double *__restrict__ w, const double *__restrict__ wmax,
+               int is_log, int64_t N, int64_t ld, int d, double *__restrict__ out)
+{
+    __shared__ double sm[kThreads / 32];
+    const double m = (is_log && wmax) ? *wmax : 0.0;
+    double acc[2 + CUSMC_MAX_DIM];
+    for (int k = 0; k < 2 + d; ++k) acc[k] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
+        double wi = __ldg(w + i);
+        if (is_log) wi = exp(wi - m);
+        if (!(wi > 0.0) || wi == INFINITY) wi = 0.0;
+        acc[0] += wi;
+        acc[1] = fma(wi, wi, acc[1]);
+        for (int k = 0; k < d; ++k) acc[2 + k] = fma(wi, __ldg(x + (int64_t)k * ld + i), acc[2 + k]);
+    }
+    for (int k = 0; k < 2 + d; ++k) {
+        double v = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int q = 0; q < kThreads / 32; ++q) t += sm[q];
+            atomicAdd(out + k, t);
+        }
+        __syncthreads();
+    }
+}
+
+template <int D>
+void fill_step_op(StepOp<D> &op, int d, int dy, const double *G, const double *Q, double qscale,
+                  const std::vector<double> *M_rowmajor, const double *c, const double *mu)
+{
+    std::memset(&op, 0, sizeof(op));
+    for (int k = 0; k < d; ++k)
+        for (int j = 0; j < d; ++j) {
+            if (G) op.G[k * D + j] = G[(size_t)j * d + k];
+            if (Q) op.Q[k * D + j] = Q[(size_t)j * d + k] * qscale;
+        }
+    if (M_rowmajor)
+        for (int k = 0; k < dy; ++k)
+            for (int j = 0; j < d; ++j) op.M[k * D + j] = (*M_rowmajor)[(size_t)k * d + j];
+    for (int k = 0; k < dy; ++k) op.c[k] = c ? c[k] : 0.0;
+    for (int k = 0; k < d; ++k) op.mu[k] = mu ? mu[k] : 0.0;
+}
+
+template <int D>
+int launch_step_D(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
+                  const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
+                  const StepArgs &a, bool philox)
+{
+    StepOp<D> op;
+    fill_step_op<D>(op, d, dy, G, Q, qscale, M, c, mu);
+    int64_t n = a.n_out > a.zero_n ? a.n_out : a.zero_n;
+    const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
+    const bool mvt = a.kind == CUSMC_MVT;
+    if (philox && mvt)
+        pf_step_kernel<D, true, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    else if (philox)
+        pf_step_kernel<D, true, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    else if (mvt)
+        pf_step_kernel<D, false, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    else
+        pf_step_kernel<D, false, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+}  // namespace
+
+// G, Q column-major d x d host; M row-major dy x d; c dy.  Shared with sharded callers.
+int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
+                      const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
+                      const StepArgs &a, bool philox)
+{
+    const int dm = d > dy ? d : dy;
+    if (dm > CUSMC_MAX_DIM || d < 1)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "dimension %d not in 1..%d", dm, CUSMC_MAX_DIM);
+    if (a.n_out == 0 && a.zero_n == 0) return CUSMC_OK;
+    switch (cusmc_pad_dim(dm)) {
+        case 2: return launch_step_D<2>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
+        case 4: return launch_step_D<4>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
+        case 8: return launch_step_D<8>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
+        case 16: return launch_step_D<16>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
+        default: return launch_step_D<32>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
+    }
+}
+
+// Observation model set-up: M = L_V^-1 F (row-major dy x d), Winv = L_V^-1 (row-major), epilogue.
+static int build_observation(cusmc_ctx *ctx, int kind, int want_log, int d, int dy, const double *F,
+                             const double *V, float nu, std::vector<double> &M, std::vector<double> &Winv,
+                             Epilogue &ep)
+{
+    CUSMC_CHECK(cusmc_build_whitening(ctx, kind, want_log, dy, V, nu, Winv, ep));
+    M.assign((size_t)dy * d, 0.0);
+    for (int k = 0; k < dy; ++k)
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int i = 0; i <= k; ++i) s += Winv[(size_t)k * dy + i] * F[(size_t)j * dy + i];
+            M[(size_t)k * d + j] = s;
+        }
+    return CUSMC_OK;
+}
+
+static void whiten_observation(const std::vector<double> &Winv, int dy, const double *y, double *c)
+{
+    for (int k = 0; k < dy; ++k) {
+        double s = 0.0;
+        for (int i = 0; i <= k; ++i) s += Winv[(size_t)k * dy + i] * y[i];
+        c[k] = s;
+    }
+}
+
+// ---- extern "C": layout helpers -----------------------------------------------------------------
+extern "C" int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, double *soa_dev, int64_t N,
+                                    int64_t ld, int d)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && ld >= N, "bad sizes");
+    if (N == 0) return CUSMC_OK;
+    const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
+    CUSMC_REQUIRE(ctx, smem <= 48 * 1024, "d too large for the transpose tile");
+    aos_to_soa_kernel<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, smem, ctx->stream>>>(aos_dev, soa_dev, N, ld, d);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_soa_to_aos_dev(cusmc_ctx *ctx, const double *soa_dev, double *aos_dev, int64_t N,
+                                    int64_t ld, int d)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && ld >= N, "bad sizes");
+    if (N == 0) return CUSMC_OK;
+    const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
+    CUSMC_REQUIRE(ctx, smem <= 48 * 1024, "d too large for the transpose tile");
+    soa_to_aos_kernel<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, smem, ctx->stream>>>(soa_dev, aos_dev, N, ld, d);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+// ---- extern "C": fused propagate + reweight on device SoA state -----------------------------------
+extern "C" int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_log, double *x_new_dev,
+                                            const double *x_prev_dev, const uint32_t *a_dev, int64_t N,
+                                            int64_t ld, int d, int dy, const double *G, const double *Q,
+                                            const double *y, const double *F, const double *V, float nu,
+                                            const double *xi_dev, const double *chi_dev, uint64_t seed,
+                                            uint64_t step, double *lw_dev, double *lw_max_dev)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && dy >= 1 && ld >= N, "bad sizes");
+    CUSMC_REQUIRE(ctx, G && Q && y && F && V, "model matrix is NULL");
+    CUSMC_REQUIRE(ctx, N == 0 || (x_new_dev && x_prev_dev && lw_dev), "state pointer is NULL");
+    CUSMC_REQUIRE(ctx, x_new_dev != x_prev_dev, "x_new must not alias x_prev (children read arbitrary parents)");
+    std::vector<double> M, Winv;
+    Epilogue ep;
+    CUSMC_CHECK(build_observation(ctx, kind, want_log, d, dy, F, V, nu, M, Winv, ep));
+    double c[CUSMC_MAX_DIM];
+    whiten_observation(Winv, dy, y, c);
+    StepArgs a{};
+    a.x_new = x_new_dev;
+    a.x_prev = x_prev_dev;
+    a.anc = a_dev;
+    a.xi = xi_dev;
+    a.chi = chi_dev;
+    a.lw = lw_dev;
+    a.lw_max = lw_max_dev;
+    a.n_out = N;
+    a.ld_new = a.ld_prev = a.ld_noise = ld;
+    a.seed = seed;
+    a.step = step;
+    a.nu = nu;
+    a.d = d;
+    a.dy = dy;
+    a.kind = kind;
+    a.has_prev = 1;
+    a.rng_stream = CUSMC_STREAM_NORMAL;
+    return cusmc_launch_step(ctx, d, dy, G, Q, 1.0, &M, c, nullptr, ep, a, xi_dev == nullptr);
+}
+
+// ---- extern "C": drop-ins for the reference's pdf wrappers (host pointers, AoS) --------------------
+static int pdf_dropin(cusmc_ctx *ctx, int kind, double *w, const double *y, const double *x_aos, double norm,
+                      const double *E_inv, const double *F, int64_t N, int d, int dy, float df)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && dy >= 1, "bad sizes");
+    CUSMC_REQUIRE(ctx, y && E_inv && F && (N == 0 || (w && x_aos)), "NULL pointer");
+    if (d > CUSMC_MAX_DIM || dy > CUSMC_MAX_DIM)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d/dy > %d", CUSMC_MAX_DIM);
+    if (kind == CUSMC_MVT && !(df > 0.0f)) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "mvt needs df > 0");
+    if (N == 0) return CUSMC_OK;
+    // q = r^T P r with P = E_inv = Lp Lp^T  ->  q = |Lp^T r|^2,  r = y - F x
+    std::vector<double> Lp;
+    const int bad = hostmath::cholesky_lower(E_inv, dy, Lp);
+    if (bad) return cusmc_fail(ctx, CUSMC_ERR_NOT_SPD, "E_inv is not positive definite (pivot %d)", bad - 1);
+    std::vector<double> M((size_t)dy * d, 0.0);
+    double c[CUSMC_MAX_DIM];
+    for (int k = 0; k < dy; ++k) {
+        for (int j = 0; j < d; ++j) {
+            double s = 0.0;
+            for (int i = k; i < dy; ++i) s += Lp[(size_t)k * dy + i] * F[(size_t)j * dy + i];
+            M[(size_t)k * d + j] = s;
+        }
+        double s = 0.0;
+        for (int i = k; i < dy; ++i) s += Lp[(size_t)k * dy + i] * y[i];
+        c[k] = s;
+    }
+    Epilogue ep{};
+    ep.kind = kind;
+    ep.want_log = 0;
+    ep.scale = norm;
+    ep.lognorm = std::log(norm);
+    if (kind == CUSMC_MVT) {
+        ep.half_nu_d = hostmath::mvt_half_nu_plus_d(df, dy);
+        ep.inv_nu = 1.0 / (double)df;
+    }
+    void *xd = nullptr, *wd = nullptr;
+    CUSMC_CHECK(cusmc_scratch(ctx, 0, sizeof(double) * (size_t)N * d, &xd));
+    CUSMC_CHECK(cusmc_scratch(ctx, 1, sizeof(double) * (size_t)N, &wd));
+    CUSMC_CUDA(ctx, cudaMemcpyAsync(xd, x_aos, sizeof(double) * (size_t)N * d, cudaMemcpyHostToDevice, ctx->stream));
+    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CUSMC_CHECK(cusmc_density_launch(ctx, false, dy, d, M, nullptr, c, ep, (const double *)xd, CUSMC_AOS, N, N, (double *)wd));
+    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUSMC_CUDA(ctx, cudaMemcpyAsync(w, wd, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUSMC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_mvn_pdf(cusmc_ctx *ctx, double *w, const double *y, const double *x_aos, double norm,
+                             const double *E_inv, const double *F, int64_t N, int d, int dy)
+{
+    return pdf_dropin(ctx, CUSMC_MVN, w, y, x_aos, norm, E_inv, F, N, d, dy, 0.0f);
+}
+
+extern "C" int cusmc_mvt_pdf(cusmc_ctx *ctx, double *w, const double *y, const double *x_aos,
+                             const double *E_inv, const double *F, double norm, int64_t N, int d, int dy,
+                             float df)
+{
+    return pdf_dropin(ctx, CUSMC_MVT, w, y, x_aos, norm, E_inv, F, N, d, dy, df);
+}
+
+// ---- extern "C": drop-ins for the reference's sample wrappers (host pointers, AoS) -------------------
+static int sample_dropin(cusmc_ctx *ctx, int kind, double *x_new_aos, const double *x_prev_aos,
+                         const uint32_t *anc, const double *G, const double *mu, const double *Q,
+                         const double *xi, const double *chi, uint64_t seed, uint64_t step, int stream_id,
+                         int64_t N, int d, float df)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= CUSMC_MAX_DIM, "bad sizes");
+    CUSMC_REQUIRE(ctx, Q && (N == 0 || x_new_aos), "NULL pointer");
+    CUSMC_REQUIRE(ctx, !G || N == 0 || x_prev_aos, "x_prev is NULL");
+    if (kind == CUSMC_MVT && !(df > 0.0f)) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "mvt needs df > 0");
+    if (N == 0) return CUSMC_OK;
+    const size_t nd = sizeof(double) * (size_t)N * d;
+    void *stage = nullptr, *xprev = nullptr, *xnew = nullptr, *xis = nullptr, *chis = nullptr, *ad = nullptr, *lw = nullptr;
+    CUSMC_CHECK(cusmc_scratch(ctx, 0, nd, &stage));
+    CUSMC_CHECK(cusmc_scratch(ctx, 1, nd, &xprev));
+    CUSMC_CHECK(cusmc_scratch(ctx, 2, nd, &xnew));
+    CUSMC_CHECK(cusmc_scratch(ctx, 5, sizeof(double) * (size_t)N, &lw));
+    if (G) {
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(stage, x_prev_aos, nd, cudaMemcpyHostToDevice, ctx->stream));
+        CUSMC_CHECK(cusmc_aos_to_soa_dev(ctx, (const double *)stage, (double *)xprev, N, N, d));
+    }
+    if (xi) {
+        CUSMC_CHECK(cusmc_scratch(ctx, 3, nd, &xis));
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(stage, xi, nd, cudaMemcpyHostToDevice, ctx->stream));
+        CUSMC_CHECK(cusmc_aos_to_soa_dev(ctx, (const double *)stage, (double *)xis, N, N, d));
+    }
+    if (chi) {
+        CUSMC_CHECK(cusmc_scratch(ctx, 4, nd, &chis));
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(stage, chi, nd, cudaMemcpyHostToDevice, ctx->stream));
+        CUSMC_CHECK(cusmc_aos_to_soa_dev(ctx, (const double *)stage, (double *)chis, N, N, d));
+    }
+    if (anc) {
+        CUSMC_CHECK(cusmc_scratch(ctx, 6, sizeof(uint32_t) * (size_t)N + 64, &ad));
+        ad = (char *)ad + 64;   // the first 64 bytes of slot 6 hold reduction scalars elsewhere
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(ad, anc, sizeof(uint32_t) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    StepArgs a{};
+    a.x_new = (double *)xnew;
+    a.x_prev = (const double *)xprev;
+    a.anc = (const uint32_t *)ad;
+    a.xi = (const double *)xis;
+    a.chi = (const double *)chis;
+    a.lw = (double *)lw;
+    a.n_out = N;
+    a.ld_new = a.ld_prev = a.ld_noise = N;
+    a.seed = seed;
+    a.step = step;
+    a.nu = df;
+    a.d = d;
+    a.dy = d;
+    a.kind = kind;
+    a.has_prev = G ? 1 : 0;
+    a.skip_weight = 1;
+    a.rng_stream = stream_id;
+    Epilogue ep{};
+    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CUSMC_CHECK(cusmc_launch_step(ctx, d, d, G, Q, 1.0, nullptr, nullptr, mu, ep, a, xi == nullptr));
+    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CUSMC_CHECK(cusmc_soa_to_aos_dev(ctx, (const double *)xnew, (double *)stage, N, N, d));
+    CUSMC_CUDA(ctx, cudaMemcpyAsync(x_new_aos, stage, nd, cudaMemcpyDeviceToHost, ctx->stream));
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    float ms = 0.f;
+    CUSMC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    ctx->last_ms = ms;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_mvn_sample(cusmc_ctx *ctx, double *x_new_aos, const double *x_prev_aos, const uint32_t *a,
+                                const double *G, const double *Q, const double *xi, uint64_t seed,
+                                uint64_t step, int64_t N, int d)
+{
+    if (ctx && !G) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "cusmc_mvn_sample: G is NULL");
+    return sample_dropin(ctx, CUSMC_MVN, x_new_aos, x_prev_aos, a, G, nullptr, Q, xi, nullptr, seed, step,
+                         CUSMC_STREAM_NORMAL, N, d, 0.0f);
+}
+
+extern "C" int cusmc_mvn_sample_init(cusmc_ctx *ctx, double *x_aos, const double *mu, const double *Q,
+                                     const double *xi, uint64_t seed, int64_t N, int d)
+{
+    return sample_dropin(ctx, CUSMC_MVN, x_aos, nullptr, nullptr, nullptr, mu, Q, xi, nullptr, seed, 0,
+                         CUSMC_STREAM_INIT, N, d, 0.0f);
+}
+
+extern "C" int cusmc_mvt_sample(cusmc_ctx *ctx, double *x_new_aos, const double *x_prev_aos, const uint32_t *a,
+                                const double *G, const double *Q, const double *xi, const double *chi,
+                                uint64_t seed, uint64_t step, int64_t N, int d, float df)
+{
+    if (ctx && !G) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "cusmc_mvt_sample: G is NULL");
+    return sample_dropin(ctx, CUSMC_MVT, x_new_aos, x_prev_aos, a, G, nullptr, Q, xi, chi, seed, step,
+                         CUSMC_STREAM_NORMAL, N, d, df);
+}
+
+// ================================================================================================
+// The filter object: particle_filter() / initialize() / MCMC() of the reference
+// (src/particle_filter.cpp:6-39, src/mcmc.cpp:44-88,239-309) with device-resident state.
+// ================================================================================================
+struct StepSlot {            // one per time step, on the device (64 bytes)
+    double lw_max;           // max log-weight (log modes), -inf initialised
+    uint64_t sum_q, sum_q2, n_pos, pad;   // fixed-point sums (weights_sum_kernel)
+    double reserved[3];
+};
+
+struct cusmc_filter {
+    cusmc_ctx *ctx = nullptr;
+    cusmc_filter_config cfg{};
+    std::vector<double> Y, m0, C0, F, G, V, W;       // host copies (column-major)
+    std::vector<double> Qc0, Qw;                      // noise factors
+    std::vector<double> M, Winv;                      // observation operator
+    Epilogue ep{};
+    int is_log = 1;
+    int shift = 0;
+    double *x[2] = {nullptr, nullptr};
+    double *lw = nullptr;
+    uint32_t *anc = nullptr;
+    uint64_t *cdf = nullptr;
+    StepSlot *slots = nullptr;
+    double *moments = nullptr;        // T x (2 + d)
+    void *scan_state = nullptr;
+    double *hist_x = nullptr, *hist_w = nullptr;
+    uint32_t *hist_a = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    int cur = 0;
+    bool ran = false;
+};
+
+// Symmetric eigen factor Q = V sqrt(Lambda) (reference: eigenSolver, src/linear_algebra.cpp:10-23)
+// by cyclic Jacobi; any Q with Q Q^T = Sigma gives the same law, the eigen form is kept so the
+// noise a given xi produces matches the reference's convention up to eigenvector sign.
+static int eigen_factor(cusmc_ctx *ctx, const double *S, int d, std::vector<double> &Q)
+{
+    std::vector<double> A(S, S + (size_t)d * d), Vv((size_t)d * d, 0.0);
+    for (int i = 0; i < d; ++i) Vv[(size_t)i * d + i] = 1.0;
+    for (int sweep = 0; sweep < 100; ++sweep) {
+        double off = 0.0;
+        for (int p = 0; p < d; ++p)
+            for (int q = p + 1; q < d; ++q) off += A[(size_t)q * d + p] * A[(size_t)q * d + p];
+        if (off < 1e-300) break;
+        for (int p = 0; p < d; ++p)
+            for (int q = p + 1; q < d; ++q) {
+                const double apq = A[(size_t)q * d + p];
+                if (std::fabs(apq) < 1e-300) continue;
+                const double app = A[(size_t)p * d + p], aqq = A[(size_t)q * d + q];
+                const double theta = (aqq - app) / (2.0 * apq);
+                const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+                const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+                for (int k = 0; k < d; ++k) {
+                    const double akp = A[(size_t)p * d + k], akq = A[(size_t)q * d + k];
+                    A[(size_t)p * d + k] = cs * akp - sn * akq;
+                    A[(size_t)q * d + k] = sn * akp + cs * akq;
+                }
+                for (int k = 0; k < d; ++k) {
+                    const double apk = A[(size_t)k * d + p], aqk = A[(size_t)k * d + q];
+                    A[(size_t)k * d + p] = cs * apk - sn * aqk;
+                    A[(size_t)k * d + q] = sn * apk + cs * aqk;
+                }
+                for (int k = 0; k < d; ++k) {
+                    const double vkp = Vv[(size_t)p * d + k], vkq = Vv[(size_t)q * d + k];
+                    Vv[(size_t)p * d + k] = cs * vkp - sn * vkq;
+                    Vv[(size_t)q * d + k] = sn * vkp + cs * vkq;
+                }
+            }
+    }
+    Q.assign((size_t)d * d, 0.0);
+    for (int c = 0; c < d; ++c) {
+        const double lam = A[(size_t)c * d + c];
+        if (!(lam >= -1e-12)) return cusmc_fail(ctx, CUSMC_ERR_NOT_SPD, "covariance has a negative eigenvalue");
+        const double s = std::sqrt(lam > 0 ? lam : 0.0);
+        for (int r = 0; r < d; ++r) Q[(size_t)c * d + r] = Vv[(size_t)c * d + r] * s;
+    }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_destroy(cusmc_filter *f)
+{
+    if (!f) return CUSMC_OK;
+    cudaSetDevice(f->ctx->device);
+    cudaStreamSynchronize(f->ctx->stream);
+    cudaFree(f->x[0]);
+    cudaFree(f->x[1]);
+    cudaFree(f->lw);
+    cudaFree(f->anc);
+    cudaFree(f->cdf);
+    cudaFree(f->slots);
+    cudaFree(f->moments);
+    cudaFree(f->scan_state);
+    cudaFree(f->hist_x);
+    cudaFree(f->hist_w);
+    cudaFree(f->hist_a);
+    if (f->ev0) cudaEventDestroy(f->ev0);
+    if (f->ev1) cudaEventDestroy(f->ev1);
+    delete f;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_filter **out)
+{
+    if (!ctx || !out) return CUSMC_ERR_INVALID;
+    *out = nullptr;
+    CUSMC_REQUIRE(ctx, cfg != nullptr, "config is NULL");
+    CUSMC_REQUIRE(ctx, cfg->N >= 1 && cfg->N <= 0xFFFFFFFFll, "N must be in 1..2^32-1");
+    CUSMC_REQUIRE(ctx, cfg->d >= 1 && cfg->dy >= 1 && cfg->T >= 1, "d, dy, T must be positive");
+    CUSMC_REQUIRE(ctx, cfg->d <= CUSMC_MAX_DIM && cfg->dy <= CUSMC_MAX_DIM, "d/dy exceed CUSMC_MAX_DIM");
+    CUSMC_REQUIRE(ctx, cfg->Y && cfg->m0 && cfg->C0 && cfg->F && cfg->G && cfg->V && cfg->W, "model pointer is NULL");
+    CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->kind == CUSMC_MVT, "unknown distribution");
+    CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 2, "unknown resampler");
+    CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
+    cusmc_filter *f = new (std::nothrow) cusmc_filter();
+    if (!f) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "out of host memory");
+    f->ctx = ctx;
+    f->cfg = *cfg;
+    const int d = cfg->d, dy = cfg->dy, T = cfg->T;
+    const int64_t N = cfg->N;
+    f->Y.assign(cfg->Y, cfg->Y + (size_t)dy * T);
+    f->m0.assign(cfg->m0, cfg->m0 + d);
+    f->C0.assign(cfg->C0, cfg->C0 + (size_t)d * d);
+    f->F.assign(cfg->F, cfg->F + (size_t)dy * d);
+    f->G.assign(cfg->G, cfg->G + (size_t)d * d);
+    f->V.assign(cfg->V, cfg->V + (size_t)dy * dy);
+    f->W.assign(cfg->W, cfg->W + (size_t)d * d);
+    f->cfg.Y = f->Y.data();
+    f->cfg.m0 = f->m0.data();
+    f->cfg.C0 = f->C0.data();
+    f->cfg.F = f->F.data();
+    f->cfg.G = f->G.data();
+    f->cfg.V = f->V.data();
+    f->cfg.W = f->W.data();
+    if (f->cfg.noise_scale == 0.0) f->cfg.noise_scale = 1.0;
+    if (f->cfg.B <= 0) f->cfg.B = 10;   // the reference hard-codes B = 10 (src/mcmc.cpp:291)
+    // Reference mode (metropolis) keeps raw densities as weights like src/mcmc.cpp:212; the
+    // normalised resamplers work on log-weights.
+    f->is_log = cfg->resampler == CUSMC_RESAMPLE_METROPOLIS ? 0 : 1;
+    f->shift = cusmc_fixed_shift(N);
+    int rc = eigen_factor(ctx, f->C0.data(), d, f->Qc0);
+    if (rc == CUSMC_OK) rc = eigen_factor(ctx, f->W.data(), d, f->Qw);
+    if (rc == CUSMC_OK)
+        rc = build_observation(ctx, cfg->kind, f->is_log, d, dy, f->F.data(), f->V.data(), cfg->nu, f->M, f->Winv, f->ep);
+    if (rc != CUSMC_OK) {
+        delete f;
+        return rc;
+    }
+    cudaError_t e = cudaSetDevice(ctx->device);
+    auto alloc = [&](void **p, size_t bytes) {
+        if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8);
+    };
+    alloc((void **)&f->x[0], sizeof(double) * (size_t)N * d);
+    alloc((void **)&f->x[1], sizeof(double) * (size_t)N * d);
+    alloc((void **)&f->lw, sizeof(double) * (size_t)N);
+    alloc((void **)&f->anc, sizeof(uint32_t) * (size_t)N);
+    if (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL) alloc((void **)&f->cdf, sizeof(uint64_t) * (size_t)N);
+    alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
+    alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
+    alloc(&f->scan_state, cusmc_scan_state_bytes(N));
+    if (cfg->keep_history) {
+        alloc((void **)&f->hist_x, sizeof(double) * (size_t)T * N * d);
+        alloc((void **)&f->hist_w, sizeof(double) * (size_t)T * N);
+        alloc((void **)&f->hist_a, sizeof(uint32_t) * (size_t)T * N);
+    }
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
+    if (e != cudaSuccess) {
+        cusmc_fail(ctx, CUSMC_ERR_CUDA, "filter allocation failed: %s", cudaGetErrorString(e));
+        cusmc_filter_destroy(f);
+        return CUSMC_ERR_CUDA;
+    }
+    *out = f;
+    return CUSMC_OK;
+}
+
+__global__ void init_slots_kernel(StepSlot *slots, int T)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) {
+        StepSlot s;
+        s.lw_max = -INFINITY;
+        s.sum_q = s.sum_q2 = s.n_pos = s.pad = 0;
+        s.reserved[0] = s.reserved[1] = s.reserved[2] = 0.0;
+        slots[t] = s;
+    }
+}
+
+static uint64_t host_u0_bits(uint64_t seed, uint64_t step)
+{
+    const cusmc_u32x4 r = cusmc_rng(seed, 7 /* systematic offset */, step, 0, 0);
+    return ((uint64_t)r.v[0] << 32) | r.v[1];
+}
+
+extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    const int d = cfg.d, dy = cfg.dy, T = cfg.T;
+    const int64_t N = cfg.N;
+    cusmc_filter_draws none{};
+    if (!draws) draws = &none;
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+
+    init_slots_kernel<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
+    CUSMC_LAUNCHED(ctx);
+    CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
+    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, cusmc_scan_state_bytes(N), st));
+    const int64_t zero_words = (int64_t)(cusmc_scan_state_bytes(N) / 8);
+    const int mom_grid = (int)std::min<int64_t>((N + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
+
+    auto after_step = [&](int t) -> int {
+        // sums for normalisation / ESS (log modes), moments, history
+        if (f->is_log)
+            CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, N, f->shift, &f->slots[t].sum_q));
+        if (cfg.summary) {
+            moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, N, N, d,
+                                                          f->moments + (size_t)t * (2 + d));
+            CUSMC_LAUNCHED(ctx);
+        }
+        if (cfg.keep_history) {
+            CUSMC_CHECK(cusmc_soa_to_aos_dev(ctx, f->x[f->cur], f->hist_x + (size_t)t * N * d, N, N, d));
+            CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_w + (size_t)t * N, f->lw, sizeof(double) * (size_t)N,
+                                            cudaMemcpyDeviceToDevice, st));
+            if (t > 0)
+                CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_a + (size_t)t * N, f->anc, sizeof(uint32_t) * (size_t)N,
+                                                cudaMemcpyDeviceToDevice, st));
+        }
+        return CUSMC_OK;
+    };
+
+    // ---- t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N ----
+    f->cur = 0;
+    {
+        StepArgs a{};
+        a.x_new = f->x[0];
+        a.x_prev = f->x[1];
+        a.xi = draws->xi0_dev;
+        a.lw = f->lw;
+        a.lw_max = f->is_log ? &f->slots[0].lw_max : nullptr;
+        a.n_out = N;
+        a.ld_new = a.ld_prev = a.ld_noise = N;
+        a.seed = cfg.seed;
+        a.step = 0;
+        a.nu = cfg.nu;
+        a.d = d;
+        a.dy = dy;
+        a.kind = CUSMC_MVN;   // initial chi are 1 (see oracle: orc_filter_metropolis)
+        a.has_prev = 0;
+        a.skip_weight = 1;
+        a.const_weight = f->is_log ? 0.0 : 1.0 / (double)N;
+        a.rng_stream = CUSMC_STREAM_INIT;
+        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
+                                      f->m0.data(), f->ep, a, draws->xi0_dev == nullptr));
+    }
+    CUSMC_CHECK(after_step(0));
+
+    CUSMC_CUDA(ctx, cudaEventRecord(f->ev0, st));
+    for (int t = 1; t < T; ++t) {
+        const size_t off = (size_t)(t - 1);
+        // 1. ancestors (src/mcmc.cpp:295)
+        if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
+            const double *u = draws->u_dev ? draws->u_dev + off * N * cfg.B : nullptr;
+            const uint32_t *j = draws->j_dev ? draws->j_dev + off * N * cfg.B : nullptr;
+            CUSMC_CHECK(cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log, 0, N));
+        } else if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
+            const double u0 = draws->u0_host ? draws->u0_host[off]
+                                             : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+            CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
+                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, false, nullptr, f->anc,
+                                          0, 0, N, u0));
+        } else {
+            CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
+                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, false, f->cdf, nullptr,
+                                          0, 0, 0, 0.0));
+            const double *um = draws->um_dev ? draws->um_dev + off * N : nullptr;
+            CUSMC_CHECK(cusmc_launch_multinomial(ctx, f->cdf, N, &f->slots[t - 1].sum_q, um, cfg.seed, (uint64_t)t, 0, N, 0, f->anc));
+        }
+        // 2 + 3. propagate and reweight, fused (src/mcmc.cpp:298-307)
+        double c[CUSMC_MAX_DIM];
+        whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
+        StepArgs a{};
+        a.x_new = f->x[f->cur ^ 1];
+        a.x_prev = f->x[f->cur];
+        a.anc = f->anc;
+        a.xi = draws->xi_dev ? draws->xi_dev + off * N * d : nullptr;
+        a.chi = draws->chi_dev ? draws->chi_dev + off * N * d : nullptr;
+        a.lw = f->lw;
+        a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
+        a.zero_ptr = (unsigned long long *)f->scan_state;   // clear the scan state for the next step
+        a.zero_n = cfg.resampler == CUSMC_RESAMPLE_METROPOLIS ? 0 : zero_words;
+        a.n_out = N;
+        a.ld_new = a.ld_prev = a.ld_noise = N;
+        a.seed = cfg.seed;
+        a.step = (uint64_t)t;
+        a.nu = cfg.nu;
+        a.d = d;
+        a.dy = dy;
+        a.kind = cfg.kind;
+        a.has_prev = 1;
+        a.rng_stream = CUSMC_STREAM_NORMAL;
+        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
+                                      f->ep, a, a.xi == nullptr));
+        f->cur ^= 1;
+        CUSMC_CHECK(after_step(t));
+    }
+    CUSMC_CUDA(ctx, cudaEventRecord(f->ev1, st));
+    f->ran = true;
+    return CUSMC_OK;
+}
+
+extern "C" double cusmc_filter_last_ms(const cusmc_filter *f)
+{
+    if (!f || !f->ran) return 0.0;
+    cudaEventSynchronize(f->ev1);
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, f->ev0, f->ev1) != cudaSuccess) return 0.0;
+    return ms;
+}
+
+extern "C" int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *ess, double *loglik)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, f->ran, "filter has not run");
+    const int d = f->cfg.d, T = f->cfg.T;
+    std::vector<StepSlot> slots(T);
+    std::vector<double> mom((size_t)T * (2 + d));
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CUSMC_CUDA(ctx, cudaMemcpy(slots.data(), f->slots, sizeof(StepSlot) * T, cudaMemcpyDeviceToHost));
+    CUSMC_CUDA(ctx, cudaMemcpy(mom.data(), f->moments, sizeof(double) * mom.size(), cudaMemcpyDeviceToHost));
+    const double scale = std::ldexp(1.0, f->shift);
+    for (int t = 0; t < T; ++t) {
+        const double *m = &mom[(size_t)t * (2 + d)];
+        if (mean)
+            for (int k = 0; k < d; ++k) mean[(size_t)t * d + k] = f->cfg.summary ? m[2 + k] / m[0] : NAN;
+        if (f->is_log) {
+            const double sq = (double)slots[t].sum_q, sq2 = (double)slots[t].sum_q2;
+            if (ess) ess[t] = sq * sq / (sq2 * scale);
+            if (loglik) loglik[t] = slots[t].lw_max + std::log(sq / scale / (double)f->cfg.N);
+        } else {
+            if (ess) ess[t] = f->cfg.summary ? m[0] * m[0] / m[1] : NAN;
+            if (loglik) loglik[t] = f->cfg.summary ? std::log(m[0] / (double)f->cfg.N) : NAN;
+        }
+    }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history, "history was not kept");
+    const size_t TN = (size_t)f->cfg.T * f->cfg.N;
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (x_aos) CUSMC_CUDA(ctx, cudaMemcpy(x_aos, f->hist_x, sizeof(double) * TN * f->cfg.d, cudaMemcpyDeviceToHost));
+    if (w) CUSMC_CUDA(ctx, cudaMemcpy(w, f->hist_w, sizeof(double) * TN, cudaMemcpyDeviceToHost));
+    if (a) {
+        CUSMC_CUDA(ctx, cudaMemcpy(a, f->hist_a, sizeof(uint32_t) * TN, cudaMemcpyDeviceToHost));
+        for (int64_t i = 0; i < f->cfg.N; ++i) a[i] = (uint32_t)i;   // row t = 0: identity
+    }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa, double **lw, uint32_t **anc)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    if (x_soa) *x_soa = f->x[f->cur];
+    if (lw) *lw = f->lw;
+    if (anc) *anc = f->anc;
+    return CUSMC_OK;
+}
+
+// R-level run() (src/run.rcpp.cpp:58-126): weights [T][N], posterior_x [T][N][d].
+extern "C" int cusmc_run(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, cfg != nullptr, "config is NULL");
+    cusmc_filter_config c = *cfg;
+    c.keep_history = 1;
+    cusmc_filter *f = nullptr;
+    CUSMC_CHECK(cusmc_filter_create(ctx, &c, &f));
+    int rc = cusmc_filter_run(f, nullptr);
+    if (rc == CUSMC_OK) rc = cusmc_filter_get_history(f, posterior_x, weights, nullptr);
+    cusmc_filter_destroy(f);
+    return rc;
+}

@@ -1,0 +1,304 @@
+/*
+ * cusmc_b200.h -- C ABI of the B200-native CuSMC sampling hot path.
+ *
+ * This is the drop-in boundary: the five C++ wrappers the reference declares in
+ * inst/include/distributions/mvn_dist.hpp:19-54 (reached through the virtuals
+ * pdf_cu / sample_cu / sample_cu_init, inst/include/statistics.hpp:51-94) and the
+ * resampler seam resampler_f (inst/include/types.hpp:32) are replaced by the
+ * extern "C" entry points below.  Plain pointers and sizes only; no C++ or torch
+ * types cross this line.  INTEGRATION.md shows the Rcpp-side binding.
+ *
+ * Conventions
+ *   - All arithmetic is fp64; ancestor indices are uint32 (the reference's `unsigned`).
+ *   - Small matrices (Sigma, F, G, Q, ...) are HOST pointers, column-major with
+ *     leading dimension = rows, i.e. Eigen::MatrixXd::data().
+ *   - Particle arrays: CUSMC_AOS = x[i*d + k] (what the reference's wrappers
+ *     flatten VectorXd[N] into, src/mvn_dist.cu.cpp:202-205); CUSMC_SOA =
+ *     x[k*ld + i], the device-resident layout the kernels stream with 128-bit loads.
+ *   - Functions ending in _dev take DEVICE pointers for the particle-sized arrays
+ *     and enqueue on the context's stream without synchronising; the others take
+ *     HOST pointers, copy in and out, and return when the result is on the host.
+ *   - Every function returns an int status (0 = CUSMC_OK); the message of the last
+ *     failure is kept per context (cusmc_last_error).  Nothing throws or exits
+ *     across this ABI (the reference's CUDA_CALL/FATAL -> Rcpp::stop convention,
+ *     inst/include/support.cuh:9-32, is applied by the binding, not here).
+ *   - One context = one device = one caller thread at a time; no global mutable
+ *     state, contexts are independent.
+ *   - There is no CPU fallback: without a usable CUDA device every call fails.
+ */
+#ifndef CUSMC_B200_H
+#define CUSMC_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CUSMC_VERSION 100
+
+enum cusmc_status {
+    CUSMC_OK = 0,
+    CUSMC_ERR_INVALID = 1,      /* bad argument (NULL, size, unsupported d) */
+    CUSMC_ERR_CUDA = 2,         /* CUDA runtime / launch failure */
+    CUSMC_ERR_NOT_SPD = 3,      /* covariance not symmetric positive definite */
+    CUSMC_ERR_DEGENERATE = 4,   /* all weights zero / non-finite: nothing to resample from */
+    CUSMC_ERR_UNSUPPORTED = 5
+};
+
+enum cusmc_dist_kind { CUSMC_MVN = 0, CUSMC_MVT = 1 };   /* Distributions["mvn"|"mvt"], src/mcmc.cpp:53-58 */
+enum cusmc_layout { CUSMC_SOA = 0, CUSMC_AOS = 1 };
+enum cusmc_resampler {                                    /* Resamplers[...], src/mcmc.cpp:252-255 */
+    CUSMC_RESAMPLE_METROPOLIS = 0,   /* the reference's only resampler */
+    CUSMC_RESAMPLE_SYSTEMATIC = 1,
+    CUSMC_RESAMPLE_MULTINOMIAL = 2
+};
+
+#define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
+
+typedef struct cusmc_ctx cusmc_ctx;
+
+/* ---- context ---------------------------------------------------------------- */
+int cusmc_version(void);
+int cusmc_ctx_create(cusmc_ctx **ctx, int device);
+int cusmc_ctx_destroy(cusmc_ctx *ctx);
+const char *cusmc_last_error(const cusmc_ctx *ctx);
+/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
+int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream);
+int cusmc_ctx_synchronize(cusmc_ctx *ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t cusmc_ctx_launch_count(const cusmc_ctx *ctx);
+/* Device time in ms of the last host-pointer call's kernels (CUDA events on the stream). */
+double cusmc_ctx_last_kernel_ms(const cusmc_ctx *ctx);
+
+/* ---- a1/a2: batched density, shared covariance ------------------------------- */
+/*
+ * out[i] = pdf(x_i) or log pdf(x_i) of MVN(mu, Sigma) / MVT(mu, Sigma, nu) for N points.
+ * Replaces MultiVariateNormalDistribution::pdf (src/statistics.cc.cpp:171-196) and
+ * MultiVariateTStudentDistribution::pdf (:295-324) evaluated per particle; nu is a
+ * float and (nu + d) is a float sum, as in the reference (:302).
+ * mu may be NULL (zero mean).  Sigma is factored once on the host (Cholesky; the
+ * whitening operator W = L^-1 travels in the kernel's parameter bank).
+ */
+int cusmc_logpdf_dev(cusmc_ctx *ctx, int kind, int want_log,
+                     const double *x_dev, int layout, int64_t N, int64_t ld, int d,
+                     const double *mu, const double *sigma, float nu,
+                     double *out_dev);
+int cusmc_logpdf(cusmc_ctx *ctx, int kind, int want_log,
+                 const double *x_host, int layout, int64_t N, int64_t ld, int d,
+                 const double *mu, const double *sigma, float nu,
+                 double *out_host);
+
+/* Per-point covariance: L_dev holds N packed lower Cholesky factors, point-major,
+ * row-packed (L00, L10, L11, L20, ...; d(d+1)/2 doubles each); mu_dev is N x d AoS or NULL;
+ * x_dev is AoS N x d.  out[i] = log pdf (want_log) or pdf. */
+int cusmc_logpdf_perpoint_dev(cusmc_ctx *ctx, int kind, int want_log,
+                              const double *x_dev, const double *mu_dev, const double *L_dev,
+                              int64_t N, int d, float nu, double *out_dev);
+
+/* ---- drop-ins for the reference's L0 wrappers (host pointers) ------------------ */
+/*
+ * mvn_pdf_kernel_wrapper (inst/include/distributions/mvn_dist.hpp:19-26,
+ * src/mvn_dist.cu.cpp:671-808): w[i] = norm * exp(-1/2 r^T E_inv r), r = y - F x_i.
+ * x_aos is the flattened post_x_t[t]; E_inv is dy x dy, F is dy x d.
+ */
+int cusmc_mvn_pdf(cusmc_ctx *ctx, double *w, const double *y, const double *x_aos,
+                  double norm, const double *E_inv, const double *F,
+                  int64_t N, int d, int dy);
+/* mvt_pdf_kernel_wrapper (mvn_dist.hpp:38-46, src/mvt_dist.cu.cpp:573-697):
+ * w[i] = norm * (1 + q/df)^(-(df + dy)/2). */
+int cusmc_mvt_pdf(cusmc_ctx *ctx, double *w, const double *y, const double *x_aos,
+                  const double *E_inv, const double *F, double norm,
+                  int64_t N, int d, int dy, float df);
+/*
+ * mvn_sample_kernel_wrapper, propagate overload (mvn_dist.hpp:28-31,
+ * src/mvn_dist.cu.cpp:175-319): x_new[i] = G x_prev[a[i]] + Q xi_i.
+ * xi (N x d AoS standard normals) may be NULL: they are then drawn on the device
+ * from Philox4x32-10 keyed by (seed, step) -- see include/cusmc_philox.h.
+ * a may be NULL (identity).  x_new may alias nothing.
+ */
+int cusmc_mvn_sample(cusmc_ctx *ctx, double *x_new_aos, const double *x_prev_aos,
+                     const uint32_t *a, const double *G, const double *Q,
+                     const double *xi, uint64_t seed, uint64_t step,
+                     int64_t N, int d);
+/* init overload (mvn_dist.hpp:33-36, src/mvn_dist.cu.cpp:321-453): x[i] = mu + Q xi_i. */
+int cusmc_mvn_sample_init(cusmc_ctx *ctx, double *x_aos, const double *mu, const double *Q,
+                          const double *xi, uint64_t seed, int64_t N, int d);
+/* mvt_sample_kernel_wrapper (mvn_dist.hpp:48-54, src/mvt_dist.cu.cpp:225-354):
+ * x_new[i] = G x_prev[a[i]] + chi_i (.) (Q xi_i); chi = sqrt(df / chi2_df) per component
+ * (the reference's Q2 semantics).  chi/xi NULL -> drawn on the device. */
+int cusmc_mvt_sample(cusmc_ctx *ctx, double *x_new_aos, const double *x_prev_aos,
+                     const uint32_t *a, const double *G, const double *Q,
+                     const double *xi, const double *chi, uint64_t seed, uint64_t step,
+                     int64_t N, int d, float df);
+/*
+ * Sampler::metropolis_hastings / resampler_f (src/samplers.cpp:7-36,
+ * inst/include/types.hpp:32): for each i, k = i; B times: if (u <= w[j]/w[k]) k = j.
+ * u, j: N x B in the reference's consumption order (for i, for n), or both NULL to
+ * draw them on the device from Philox keyed by (seed, step).  a receives a_t[t*N + i].
+ */
+int cusmc_metropolis_hastings(cusmc_ctx *ctx, uint32_t *a, const double *w,
+                              const double *u, const uint32_t *j,
+                              uint64_t seed, uint64_t step, int64_t N, int B);
+
+/* ---- device-resident building blocks (SoA state) ------------------------------ */
+/* is_log = 0: the reference rule u <= w[j]/w[k];  1: w holds log-weights, u <= exp(lw[j]-lw[k])
+ * with the reproducible exp of cusmc_detmath.h (robust to the underflow of SURVEY.md Q8). */
+int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev,
+                                  const double *u_dev, const uint32_t *j_dev,
+                                  uint64_t seed, uint64_t step, int64_t N, int B, int is_log);
+/*
+ * Fused propagate + reweight (src/mcmc.cpp:90-160 + :162-237), SoA in and out:
+ *   x_new[:, i] = G x_prev[:, a[i]] + noise_i,   noise = Q xi (mvn) | chi (.) (Q xi) (mvt)
+ *   lw[i]       = log pdf_V(y - F x_new[:, i])   (want_log) or the density itself
+ * a_dev NULL = identity; xi_dev/chi_dev are SoA [d][ld] or NULL (Philox).
+ * lw_max_dev (optional, 1 double, must be initialised to -inf by the caller or
+ * by cusmc_weights_begin) receives max_i lw[i] via an ordered atomic.
+ */
+int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_log,
+                                 double *x_new_dev, const double *x_prev_dev,
+                                 const uint32_t *a_dev, int64_t N, int64_t ld, int d, int dy,
+                                 const double *G, const double *Q,
+                                 const double *y, const double *F, const double *V, float nu,
+                                 const double *xi_dev, const double *chi_dev,
+                                 uint64_t seed, uint64_t step,
+                                 double *lw_dev, double *lw_max_dev);
+
+/*
+ * Weight normalisation and resampling on the deterministic fixed-point image (DESIGN.md,
+ * include/cusmc_detmath.h):
+ *   wn_i = exp(lw_i - max)  (log weights, cusmc_det_exp)   or   w_i / max  (linear weights)
+ *   q_i  = (uint64) trunc(wn_i * 2^shift),  shift = 61 - ceil(log2(N_global))
+ * Sums and prefix sums of q are INTEGER, so they do not depend on the order blocks, tiles or
+ * ranks are combined in; a CPU can reproduce every ancestor bit for bit.
+ *
+ * cusmc_weights_max_dev : *max_dev = max_i w_i over finite entries (set to -inf first).
+ * cusmc_weights_sum_dev : stats_dev[0..2] = { sum q_i, sum trunc(wn_i^2 2^shift), #(q_i > 0) }
+ *                         (zeroed first).  log-sum-exp = max + log(stats[0] / 2^shift),
+ *                         ESS = stats[0]^2 / (stats[1] 2^shift).
+ * cusmc_weights_scan_dev: cdf_dev[i] = *cdf_offset_dev + inclusive prefix sum of q (single-pass
+ *                         decoupled look-back scan).  cdf_offset_dev may be NULL (0): it is the
+ *                         fixed-point mass held by lower-ranked shards.
+ * On several GPUs the caller all-reduces max (MAX) and stats (SUM) between these calls and
+ * passes the exclusive prefix of the per-rank sums as cdf_offset (cusmc_b200/sharded.py).
+ */
+int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev);
+int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, const double *max_dev,
+                          int64_t N, int64_t N_global, uint64_t *stats_dev);
+int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, const double *max_dev,
+                           int64_t N, int64_t N_global, const uint64_t *cdf_offset_dev,
+                           uint64_t *cdf_dev);
+
+/*
+ * Systematic resampling, offspring-scatter form, fused into the scan: with T = *total_dev the
+ * global fixed-point mass and r0 = min((uint64)(u0 * (double)T), T - 1), child slot i (global,
+ * 0 <= i < N_global) belongs to the parent j with  C_{j-1} * N_global <= i * T + r0 < C_j * N_global
+ * (C = global inclusive prefix; 128-bit integer compare).  Every local parent j writes
+ *   a_dev[i - out_lo] = j0 + j      for its children i inside [out_lo, out_lo + out_n).
+ * j0 = global index of w_dev[0].  One GPU: j0 = out_lo = 0, out_n = N_local = N_global.
+ */
+int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
+                                  const double *max_dev, int64_t N_local, int64_t N_global,
+                                  const uint64_t *total_dev, const uint64_t *cdf_offset_dev,
+                                  int64_t j0, int64_t out_lo, int64_t out_n, double u0,
+                                  uint32_t *a_dev);
+/* Multinomial: a_dev[t] = j0 + #{ j : cdf_j <= p },  p = min((uint64)(u * (double)T), T - 1), for
+ * children i0 .. i0 + n_out - 1; u = u_dev[t] or, if u_dev is NULL, the Philox draw keyed by
+ * (seed, step, i0 + t). */
+int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cdf_dev, int64_t N,
+                                   const uint64_t *total_dev, const double *u_dev,
+                                   uint64_t seed, uint64_t step, int64_t i0, int64_t n_out,
+                                   int64_t j0, uint32_t *a_dev);
+
+/* Host-pointer conveniences: full resampling of N weights (linear domain) -> ancestors. */
+int cusmc_resample_systematic(cusmc_ctx *ctx, const double *w, int64_t N, double u0, uint32_t *a);
+int cusmc_resample_multinomial(cusmc_ctx *ctx, const double *w, int64_t N, const double *u,
+                               uint32_t *a);
+/* lse = lw_max + log(sum exp(lw - lw_max)),  ess = (sum wn)^2 / sum wn^2. */
+int cusmc_normalize_ess(cusmc_ctx *ctx, const double *lw, int64_t N, double *lse, double *ess);
+
+/* ---- independent Metropolis-Hastings chains (configs[2]) ------------------------ */
+/*
+ * C random-walk MH chains on an MVN / MVT target with per-chain (shared = 0) or
+ * single (shared = 1) location mu and lower Cholesky factor L (column-major d x d,
+ * strict upper ignored).  Proposal x' = x + step_size * (L z).  Accept rule
+ * (transcendental-free so decisions are bit-reproducible on the host):
+ *   mvn: 0.5 (q' - q) < thr             thr = -log(u)
+ *   mvt: (1 + q'/nu) < thr (1 + q/nu)   thr = exp(2 (-log u) / (nu + d))
+ * z_dev [C][steps][d] and thr_dev [C][steps] pre-drawn, or both NULL: drawn in the
+ * kernel from Philox keyed by (seed, chain, step).  x_dev is AoS C x d, updated in place.
+ * n_accept_dev (C), accept_bits_dev (C x steps bytes), sum_x_dev / sum_xx_dev (C x d running
+ * sums over steps) are optional.
+ */
+int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps,
+                        double step_size, double nu, int shared,
+                        const double *mu_dev, const double *L_dev, double *x_dev,
+                        const double *z_dev, const double *thr_dev, uint64_t seed,
+                        uint32_t *n_accept_dev, uint8_t *accept_bits_dev,
+                        double *sum_x_dev, double *sum_xx_dev);
+
+/* ---- the filter (a7): particle_filter() / MCMC() -------------------------------- */
+/*
+ * Device-resident bootstrap particle filter for x_t = G x_{t-1} + w_t, y_t = F x_t + v_t
+ * (src/particle_filter.cpp:6-39, src/mcmc.cpp:44-88,239-309).  State stays on the
+ * device in SoA double buffers owned by the filter object; history is optional.
+ */
+typedef struct cusmc_filter cusmc_filter;
+
+typedef struct cusmc_filter_config {
+    int64_t N;            /* particles */
+    int d, dy, T;         /* state dim, observation dim, time steps (t = 0 .. T-1) */
+    int kind;             /* cusmc_dist_kind for both noises (as the reference does) */
+    int resampler;        /* cusmc_resampler */
+    int B;                /* Metropolis steps per particle (reference hard-codes 10, src/mcmc.cpp:291) */
+    float nu;             /* degrees of freedom (mvt) */
+    double noise_scale;   /* multiplies Q_c0 and Q_w: sqrt(3) reproduces the reference CPU
+                             build's CLT sampler moments, 1 the GPU build's */
+    uint64_t seed;        /* Philox key for device-drawn randomness */
+    const double *Y;      /* dy x T column-major observations (host) */
+    const double *m0, *C0, *F, *G, *V, *W;   /* host, column-major */
+    int keep_history;     /* 1: keep x (T x N x d), w (T x N), a (T x N) on the device */
+    int summary;          /* 1: per-step weighted posterior mean (one extra pass over the state) */
+} cusmc_filter_config;
+
+/* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):
+ *   xi0 [d][N] SoA; per step t = 1..T-1: xi [(T-1)][d][N], chi idem,
+ *   u [(T-1)][N][B], j [(T-1)][N][B] (metropolis), u0 [(T-1)] host doubles (systematic),
+ *   um [(T-1)][N] (multinomial). */
+typedef struct cusmc_filter_draws {
+    const double *xi0_dev, *xi_dev, *chi_dev, *u_dev;
+    const uint32_t *j_dev;
+    const double *u0_host;
+    const double *um_dev;
+} cusmc_filter_draws;
+
+int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_filter **out);
+int cusmc_filter_destroy(cusmc_filter *f);
+/* Runs t = 0 (initialize) then steps 1 .. T-1 on the stream; returns after enqueueing. */
+int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
+/* Per-step outputs copied to the host (any pointer may be NULL):
+ * mean [T][d] weighted posterior mean, ess [T], loglik [T] (log of the mean weight). */
+int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *ess, double *loglik);
+/* History (needs keep_history): x_aos [T][N][d], w [T][N] (densities or normalised
+ * weights), a [T][N]. */
+int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a);
+/* Device time of the last run's step loop (t = 1 .. T-1), ms, from CUDA events on the stream. */
+double cusmc_filter_last_ms(const cusmc_filter *f);
+/* Current device-resident state: x (SoA [d][N]), weights (N), ancestors of the last step (N). */
+int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa_dev, double **w_dev, uint32_t **a_dev);
+
+/* R-level run() (src/run.rcpp.cpp:58-126) on host pointers: allocates a filter, runs it,
+ * returns weights [T][N] and posterior_x [T][N][d] exactly as the reference shapes them. */
+int cusmc_run(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x);
+
+/* ---- layout helpers -------------------------------------------------------------- */
+int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, double *soa_dev,
+                         int64_t N, int64_t ld, int d);
+int cusmc_soa_to_aos_dev(cusmc_ctx *ctx, const double *soa_dev, double *aos_dev,
+                         int64_t N, int64_t ld, int d);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CUSMC_B200_H */

@@ -1,0 +1,189 @@
+/*
+ * cusmc_detmath.h -- deterministic elementary functions and the fixed-point weight image.
+ *
+ * Everything here is built from IEEE-754 basic operations (add, mul, fma, div, sqrt,
+ * conversions) in a FIXED order, so the same inputs give the same bits on the device
+ * (nvcc -fmad=false) and on any host compiler that does not contract floating point
+ * (gcc -ffp-contract=off).  That is what lets resampling decisions taken on the GPU be
+ * reproduced bit-for-bit on a CPU: libm's and CUDA's exp/log differ in the last ulp,
+ * these do not.  The CPU oracle carries an independent restatement (orc_det_exp,
+ * orc_det_log, orc_fixed_weights) that the tests compare against.
+ *
+ * There is no counterpart in the reference (it never normalises weights and works in the
+ * linear domain); semantics are defined here.
+ */
+#ifndef CUSMC_DETMATH_H
+#define CUSMC_DETMATH_H
+
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#if defined(__CUDACC__)
+#define CUSMC_HD __host__ __device__ __forceinline__
+#else
+#define CUSMC_HD static inline
+#endif
+
+CUSMC_HD double cusmc_bits_to_double(uint64_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __longlong_as_double((long long)b);
+#else
+    double d;
+    memcpy(&d, &b, 8);
+    return d;
+#endif
+}
+
+CUSMC_HD uint64_t cusmc_double_to_bits(double d)
+{
+#if defined(__CUDA_ARCH__)
+    return (uint64_t)__double_as_longlong(d);
+#else
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    return b;
+#endif
+}
+
+/* 2^e for -1022 <= e <= 1023 */
+CUSMC_HD double cusmc_pow2i(int e) { return cusmc_bits_to_double((uint64_t)(e + 1023) << 52); }
+
+/* exp(x): range reduction x = k ln2 + r with a two-term ln2, degree-13 Taylor polynomial
+ * in Horner/fma form, exact scaling by 2^k (gradual underflow handled in two steps). */
+CUSMC_HD double cusmc_det_exp(double x)
+{
+    if (x != x) return x;
+    if (x > 709.782712893384) return cusmc_bits_to_double(0x7FF0000000000000ull);
+    if (x < -745.2) return 0.0;
+    const double kf = rint(x * 1.4426950408889634074);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = 1.0 / 6227020800.0;
+    p = fma(p, r, 1.0 / 479001600.0);
+    p = fma(p, r, 1.0 / 39916800.0);
+    p = fma(p, r, 1.0 / 3628800.0);
+    p = fma(p, r, 1.0 / 362880.0);
+    p = fma(p, r, 1.0 / 40320.0);
+    p = fma(p, r, 1.0 / 5040.0);
+    p = fma(p, r, 1.0 / 720.0);
+    p = fma(p, r, 1.0 / 120.0);
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    const int k = (int)kf;
+    if (k >= -1021 && k <= 1023) return p * cusmc_pow2i(k);
+    if (k > 1023) return (p * cusmc_pow2i(k - 1)) * 2.0;
+    return (p * cusmc_pow2i(k + 1022)) * cusmc_pow2i(-1022);
+}
+
+/* log(x): x = m 2^e, m in [sqrt(1/2), sqrt 2), log m = 2 atanh(s), s = (m-1)/(m+1). */
+CUSMC_HD double cusmc_det_log(double x)
+{
+    if (x != x || x < 0.0) return cusmc_bits_to_double(0x7FF8000000000000ull);
+    if (x == 0.0) return cusmc_bits_to_double(0xFFF0000000000000ull);
+    uint64_t b = cusmc_double_to_bits(x);
+    if (b == 0x7FF0000000000000ull) return x;
+    int e = 0;
+    if ((b >> 52) == 0) {
+        x = x * 18014398509481984.0; /* 2^54, exact */
+        b = cusmc_double_to_bits(x);
+        e = -54;
+    }
+    e += (int)(b >> 52) - 1023;
+    double m = cusmc_bits_to_double((b & 0x000FFFFFFFFFFFFFull) | 0x3FF0000000000000ull);
+    if (m > 1.4142135623730951) {
+        m = m * 0.5;
+        e += 1;
+    }
+    const double f = m - 1.0;
+    const double s = f / (2.0 + f);
+    const double s2 = s * s;
+    double p = 1.0 / 23.0;
+    p = fma(p, s2, 1.0 / 21.0);
+    p = fma(p, s2, 1.0 / 19.0);
+    p = fma(p, s2, 1.0 / 17.0);
+    p = fma(p, s2, 1.0 / 15.0);
+    p = fma(p, s2, 1.0 / 13.0);
+    p = fma(p, s2, 1.0 / 11.0);
+    p = fma(p, s2, 1.0 / 9.0);
+    p = fma(p, s2, 1.0 / 7.0);
+    p = fma(p, s2, 1.0 / 5.0);
+    p = fma(p, s2, 1.0 / 3.0);
+    p = p * s2;
+    const double two_s = s + s;
+    const double lo = fma(two_s, p, (double)e * 1.90821492927058770002e-10);
+    return fma((double)e, 6.93147180369123816490e-01, two_s + lo);
+}
+
+/* sin(pi t), cos(pi t) for t in [0, 2): quadrant n = rint(2t), f = t - n/2 in [-1/4, 1/4]
+ * (exact), Taylor polynomials in x = pi f. */
+CUSMC_HD void cusmc_det_sincospi(double t, double *s_out, double *c_out)
+{
+    const double nf = rint(t + t);
+    const double f = fma(nf, -0.5, t);
+    const double x = fma(f, 3.141592653589793116, f * 1.2246467991473532e-16);
+    const double x2 = x * x;
+    double ps = -1.0 / 121645100408832000.0;          /* -1/19! */
+    ps = fma(ps, x2, 1.0 / 355687428096000.0);        /*  1/17! */
+    ps = fma(ps, x2, -1.0 / 1307674368000.0);         /* -1/15! */
+    ps = fma(ps, x2, 1.0 / 6227020800.0);             /*  1/13! */
+    ps = fma(ps, x2, -1.0 / 39916800.0);              /* -1/11! */
+    ps = fma(ps, x2, 1.0 / 362880.0);                 /*  1/9!  */
+    ps = fma(ps, x2, -1.0 / 5040.0);                  /* -1/7!  */
+    ps = fma(ps, x2, 1.0 / 120.0);                    /*  1/5!  */
+    ps = fma(ps, x2, -1.0 / 6.0);                     /* -1/3!  */
+    const double sn = fma(x * x2, ps, x);
+    double pc = 1.0 / 2432902008176640000.0;          /*  1/20! */
+    pc = fma(pc, x2, -1.0 / 6402373705728000.0);      /* -1/18! */
+    pc = fma(pc, x2, 1.0 / 20922789888000.0);         /*  1/16! */
+    pc = fma(pc, x2, -1.0 / 87178291200.0);           /* -1/14! */
+    pc = fma(pc, x2, 1.0 / 479001600.0);              /*  1/12! */
+    pc = fma(pc, x2, -1.0 / 3628800.0);               /* -1/10! */
+    pc = fma(pc, x2, 1.0 / 40320.0);                  /*  1/8!  */
+    pc = fma(pc, x2, -1.0 / 720.0);                   /* -1/6!  */
+    pc = fma(pc, x2, 1.0 / 24.0);                     /*  1/4!  */
+    pc = fma(pc, x2, -0.5);                           /* -1/2!  */
+    const double cs = fma(x2, pc, 1.0);
+    const int n = ((int)nf) & 3;
+    *s_out = (n == 0) ? sn : (n == 1) ? cs : (n == 2) ? -sn : -cs;
+    *c_out = (n == 0) ? cs : (n == 1) ? -sn : (n == 2) ? -cs : sn;
+}
+
+/* ---- fixed-point weight image ------------------------------------------------------------
+ * shift = 61 - ceil(log2(N_global)): N_global weights in [0, 2^shift] sum to at most 2^61, so
+ * a prefix sum fits 62 bits and the two top bits of a 64-bit word stay free for the
+ * decoupled look-back status flags. */
+CUSMC_HD int cusmc_fixed_shift(int64_t n_global)
+{
+    int b = 0;
+    while (((int64_t)1 << b) < n_global) ++b;
+    return 61 - b;
+}
+
+/* wn in [0, 1] -> trunc(wn * 2^shift); anything else (NaN, negative) -> 0. */
+CUSMC_HD uint64_t cusmc_fixed_from_unit(double wn, int shift)
+{
+    if (!(wn > 0.0)) return 0;
+    if (wn > 1.0) wn = 1.0;
+    return (uint64_t)(wn * cusmc_pow2i(shift));
+}
+
+/* Linear-domain weight w relative to wmax. */
+CUSMC_HD double cusmc_unit_from_linear(double w, double wmax)
+{
+    if (!(w > 0.0) || !(w <= wmax)) return 0.0;
+    return w / wmax;
+}
+
+/* Log-domain weight lw relative to lmax. */
+CUSMC_HD double cusmc_unit_from_log(double lw, double lmax)
+{
+    if (!(lw <= lmax)) return 0.0; /* NaN or above the max */
+    return cusmc_det_exp(lw - lmax);
+}
+
+#endif /* CUSMC_DETMATH_H */

@@ -1,0 +1,103 @@
+/*
+ * cusmc_philox.h -- counter-based randomness (Philox4x32-10, Salmon et al., SC'11) and the
+ * fixed (seed, stream, step, index) -> draw mapping the kernels use when the caller does not
+ * inject pre-drawn numbers.
+ *
+ * Replaces the reference's one-XORWOW-state-per-scalar scheme (curand_init per thread,
+ * src/mvn_dist.cu.cpp:15-31, src/mvt_dist.cu.cpp:63-82; 48 bytes of state per scalar, seeded
+ * from srand(time), not reproducible) with a stateless generator: integer arithmetic only, so
+ * a host can regenerate exactly the numbers a kernel consumed.  Normals come from Box-Muller
+ * on cusmc_detmath.h functions and are therefore bit-reproducible too.
+ *
+ * Counter layout:  ctr = { index_lo, index_hi, (uint32) step, stream | (sub << 8) }
+ *                  key = { seed_lo, seed_hi }
+ */
+#ifndef CUSMC_PHILOX_H
+#define CUSMC_PHILOX_H
+
+#include "cusmc_detmath.h"
+
+enum cusmc_rng_stream {
+    CUSMC_STREAM_METROPOLIS = 0, /* sub = n (0..B-1): out[0..1] -> u, out[2..3] -> j */
+    CUSMC_STREAM_NORMAL = 1,     /* sub = component pair k/2: two normals per call */
+    CUSMC_STREAM_CHI = 2,        /* sub = component k */
+    CUSMC_STREAM_MULTINOMIAL = 3,
+    CUSMC_STREAM_CHAIN_Z = 4,    /* index = chain, step = MH step, sub = component pair */
+    CUSMC_STREAM_CHAIN_U = 5,
+    CUSMC_STREAM_INIT = 6
+};
+
+typedef struct cusmc_u32x4 {
+    uint32_t v[4];
+} cusmc_u32x4;
+
+CUSMC_HD cusmc_u32x4 cusmc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                         uint32_t k0, uint32_t k1)
+{
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int round = 0; round < 10; ++round) {
+        const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        const uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        c1 = (uint32_t)p1;
+        c3 = (uint32_t)p0;
+        c0 = n0;
+        c2 = n2;
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    cusmc_u32x4 out;
+    out.v[0] = c0;
+    out.v[1] = c1;
+    out.v[2] = c2;
+    out.v[3] = c3;
+    return out;
+}
+
+CUSMC_HD cusmc_u32x4 cusmc_rng(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub)
+{
+    return cusmc_philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)step,
+                               (uint32_t)stream | (sub << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+/* 53-bit uniform in [0, 1). */
+CUSMC_HD double cusmc_u01(uint32_t hi, uint32_t lo)
+{
+    const uint64_t bits = (((uint64_t)hi << 32) | lo) >> 11;
+    return (double)bits * 1.1102230246251565e-16; /* 2^-53 */
+}
+
+/* 53-bit uniform in (0, 1] (safe argument for log). */
+CUSMC_HD double cusmc_u01_open0(uint32_t hi, uint32_t lo)
+{
+    const uint64_t bits = ((((uint64_t)hi << 32) | lo) >> 11) + 1;
+    return (double)bits * 1.1102230246251565e-16;
+}
+
+/* Uniform integer in [0, n): high word of a 64 x 64 -> 128 bit product (Lemire). */
+CUSMC_HD uint64_t cusmc_uint_below(uint32_t hi, uint32_t lo, uint64_t n)
+{
+    const uint64_t bits = ((uint64_t)hi << 32) | lo;
+#if defined(__CUDA_ARCH__)
+    return __umul64hi(bits, n);
+#else
+    return (uint64_t)(((unsigned __int128)bits * n) >> 64);
+#endif
+}
+
+/* Two independent standard normals from one Philox block (Box-Muller). */
+CUSMC_HD void cusmc_normal_pair(cusmc_u32x4 r, double *z0, double *z1)
+{
+    const double u1 = cusmc_u01_open0(r.v[0], r.v[1]);
+    const double u2 = cusmc_u01(r.v[2], r.v[3]);
+    const double rad = sqrt(-2.0 * cusmc_det_log(u1));
+    double s, c;
+    cusmc_det_sincospi(u2 + u2, &s, &c);
+    *z0 = rad * c;
+    *z1 = rad * s;
+}
+
+#endif /* CUSMC_PHILOX_H */

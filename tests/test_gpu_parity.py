@@ -1,0 +1,535 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle.
+
+Tolerances (BASELINE.json north_star): fp64 log-densities within 1e-10 relative; accept/reject
+decisions and ancestor indices bit-exact on identical inputs; posterior moments within a stated
+Monte Carlo tolerance.
+"""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+RTOL_LOGPDF = 1e-10
+
+
+def spd(rng, d):
+    A = rng.standard_normal((d, d))
+    return A @ A.T / d + np.eye(d)
+
+
+def relerr(got, want):
+    return np.max(np.abs(got - want) / np.maximum(np.abs(want), 1e-300))
+
+
+def torch_dev(a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+# ------------------------------------------------------------------------------------------------
+# a1 / a2: densities
+# ------------------------------------------------------------------------------------------------
+def test_reference_known_answers(ctx):
+    import cusmc_b200
+    ref = GOLDEN["reference"]
+    v = cusmc_b200.MVNPDF(ref["MVNPDF"]["x"], ref["MVNPDF"]["mu"], np.array(ref["MVNPDF"]["sigma"], float))
+    assert abs(v - ref["MVNPDF"]["value"]) < 5e-8          # 0.1591549, 7 significant digits
+    assert abs(v - 1 / (2 * math.pi)) < 1e-15
+    v = cusmc_b200.MVTPDF(ref["MVTPDF"]["x"], ref["MVTPDF"]["mu"], np.array(ref["MVTPDF"]["sigma"], float),
+                          ref["MVTPDF"]["nu"])
+    assert abs(v - ref["MVTPDF"]["value"]) < 5e-9          # 0.07799708
+    a = cusmc_b200.metropolis_hastings(ref["metropolis_hastings"]["w"], 2, 10)
+    assert a.dtype == np.float64 and a.tolist() == [0.0, 1.0]   # 0/0 = NaN never accepts
+
+
+def test_independent_golden_cases(ctx):
+    for c in GOLDEN["independent"]:
+        x = np.array(c["x"])
+        sigma = np.array(c["sigma"])
+        got = ctx.logpdf(c["kind"], x, c["mu"], sigma, nu=c["nu"], log=True)
+        assert relerr(got, np.array(c["logpdf"])) < RTOL_LOGPDF, (c["kind"], c["d"])
+        got = ctx.logpdf(c["kind"], x, c["mu"], sigma, nu=c["nu"], log=False)
+        assert relerr(got, np.array(c["pdf"])) < 1e-10, (c["kind"], c["d"])
+
+
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0), ("mvt", 0.7)])
+@pytest.mark.parametrize("d", [1, 2, 3, 5, 8, 11, 16, 24, 32])
+def test_logpdf_shared_vs_oracle(ctx, orc, kind, nu, d):
+    rng = np.random.default_rng(100 + d)
+    N = 3001                               # odd: exercises the scalar (VEC = 1) SoA path and tile tails
+    sigma, mu = spd(rng, d), rng.standard_normal(d)
+    x = rng.standard_normal((N, d)) * 2.0 + mu
+    want = orc.pdf_batch(kind, x, mu, sigma, nu, faithful=True, log=False)   # the reference's own form
+    want_log = orc.pdf_batch(kind, x, mu, sigma, nu, log=True)
+    got = ctx.logpdf(kind, x, mu, sigma, nu=nu, log=True)                    # AoS host entry point
+    assert relerr(got, want_log) < RTOL_LOGPDF
+    assert relerr(np.exp(got), want) < 1e-10
+    assert relerr(ctx.logpdf(kind, x, mu, sigma, nu=nu, log=False), want) < 1e-10
+    # SoA device entry point, both vector widths
+    import torch
+    for n in (N, N - 1):
+        xs = torch_dev(x[:n].T)
+        out = torch.empty(n, dtype=torch.float64, device="cuda")
+        ctx.logpdf_dev(kind, xs, mu, sigma, out, nu=nu, log=True)
+        ctx.synchronize()
+        assert relerr(out.cpu().numpy(), want_log[:n]) < RTOL_LOGPDF
+
+
+def test_logpdf_layouts_agree_bitwise(ctx):
+    import torch
+    rng = np.random.default_rng(5)
+    d, N = 16, 8192
+    sigma, mu = spd(rng, d), rng.standard_normal(d)
+    x = rng.standard_normal((N, d))
+    aos = ctx.logpdf("mvn", x, mu, sigma)
+    soa = ctx.logpdf("mvn", np.ascontiguousarray(x.T), mu, sigma, layout=0)
+    assert np.array_equal(aos, soa)        # same operation order in both kernels
+
+
+def test_logpdf_edge_cases(ctx, orc):
+    import cusmc_b200
+    rng = np.random.default_rng(6)
+    sigma = spd(rng, 4)
+    assert ctx.logpdf("mvn", np.zeros((0, 4)), None, sigma).shape == (0,)
+    x1 = rng.standard_normal((1, 4))
+    assert relerr(ctx.logpdf("mvn", x1, None, sigma), orc.pdf_batch("mvn", x1, None, sigma, log=True)) < 1e-12
+    with pytest.raises(cusmc_b200.CusmcError) as e:
+        ctx.logpdf("mvn", x1, None, -np.eye(4))
+    assert e.value.code == 3               # CUSMC_ERR_NOT_SPD, not NaNs
+    with pytest.raises(cusmc_b200.CusmcError):
+        ctx.logpdf("mvt", x1, None, sigma, nu=0.0)
+    with pytest.raises(cusmc_b200.CusmcError) as e:
+        ctx.logpdf("mvn", np.zeros((2, 33)), None, np.eye(33))
+    assert e.value.code == 5               # d > CUSMC_MAX_DIM
+    with pytest.raises(ValueError):
+        ctx.logpdf("normal", x1, None, sigma)
+    # far tail: log-density stays finite where the reference's density underflows to 0 (Q8)
+    far = np.full((2, 4), 60.0)
+    assert np.all(np.isfinite(ctx.logpdf("mvn", far, None, sigma)))
+    assert np.all(ctx.logpdf("mvn", far, None, sigma, log=False) == 0.0)
+
+
+def test_logpdf_full_size_properties(ctx, orc):
+    """BASELINE config: N = 2^20 points, d = 16, shared covariance.  Size-independent checks:
+    translation invariance, a checksum against the oracle on a strided sample, agreement of the
+    SoA and AoS kernels."""
+    import torch
+    rng = np.random.default_rng(1234)
+    N, d = 1 << 20, 16
+    sigma, mu = spd(rng, d), rng.standard_normal(d)
+    x = rng.standard_normal((N, d))
+    xs = torch_dev(x.T)
+    out = torch.empty(N, dtype=torch.float64, device="cuda")
+    ctx.logpdf_dev("mvn", xs, mu, sigma, out)
+    ctx.synchronize()
+    got = out.cpu().numpy()
+    idx = np.arange(0, N, 997)
+    want = orc.pdf_batch("mvn", x[idx], mu, sigma, log=True)
+    assert relerr(got[idx], want) < RTOL_LOGPDF
+    shift = rng.standard_normal(d)
+    out2 = torch.empty_like(out)
+    ctx.logpdf_dev("mvn", xs + torch_dev(shift)[:, None], mu + shift, sigma, out2)
+    ctx.synchronize()
+    assert relerr(out2.cpu().numpy(), got) < 1e-9
+    xa = torch_dev(x)
+    out3 = torch.empty_like(out)
+    ctx.logpdf_dev("mvn", xa, mu, sigma, out3, layout=1)
+    ctx.synchronize()
+    assert np.array_equal(out3.cpu().numpy(), got)
+
+
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 4.0)])
+@pytest.mark.parametrize("d", [2, 3, 8, 32])
+def test_logpdf_perpoint(ctx, orc, kind, nu, d):
+    import torch
+    rng = np.random.default_rng(40 + d)
+    N = 777
+    sig = np.stack([spd(rng, d) for _ in range(N)])
+    mu = rng.standard_normal((N, d))
+    x = mu + rng.standard_normal((N, d))
+    Ls = np.linalg.cholesky(sig)
+    tril = np.tril_indices(d)
+    packed = np.ascontiguousarray(Ls[:, tril[0], tril[1]])       # row-packed lower factors
+    out = torch.empty(N, dtype=torch.float64, device="cuda")
+    ctx.logpdf_perpoint_dev(kind, torch_dev(x), torch_dev(mu), torch_dev(packed), out, nu=nu, log=True)
+    ctx.synchronize()
+    want = orc.pdf_batch_perpoint(kind, x, mu, sig, nu, log=True)
+    assert relerr(out.cpu().numpy(), want) < RTOL_LOGPDF
+
+
+# ------------------------------------------------------------------------------------------------
+# drop-ins for the reference wrappers
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("d,dy", [(2, 2), (4, 2), (3, 5), (8, 8)])
+def test_pdf_wrappers_vs_reweight(ctx, orc, d, dy):
+    rng = np.random.default_rng(d * 10 + dy)
+    N = 2500
+    F = rng.standard_normal((dy, d))
+    V = spd(rng, dy)
+    y = rng.standard_normal(dy)
+    x = rng.standard_normal((N, d))
+    Vinv = orc.inverse(V)
+    got = ctx.mvn_pdf(y, x, orc.mvn_norm(V), Vinv, F)
+    want = orc.reweight("mvn", y, x, F, V, faithful=True)        # src/mcmc.cpp:193-215 as written
+    assert relerr(got, want) < 1e-10
+    got = ctx.mvt_pdf(y, x, Vinv, F, orc.mvt_norm(V, 3.5), 3.5)
+    want = orc.reweight("mvt", y, x, F, V, nu=3.5, faithful=True)
+    assert relerr(got, want) < 1e-10
+
+
+@pytest.mark.parametrize("d", [2, 5, 8])
+def test_sample_wrappers(ctx, orc, d):
+    rng = np.random.default_rng(70 + d)
+    N = 1500
+    G, Q = rng.standard_normal((d, d)), rng.standard_normal((d, d))
+    xp, xi = rng.standard_normal((N, d)), rng.standard_normal((N, d))
+    chi = np.sqrt(4.0 / rng.chisquare(4.0, (N, d)))
+    a = rng.integers(0, N, N, dtype=np.uint32)
+    got = ctx.mvn_sample(xp, a, G, Q, xi=xi)
+    assert np.allclose(got, orc.propagate("mvn", xp, a, G, None, Q, xi), rtol=1e-13, atol=1e-13)
+    want_det, _ = orc.step_det("mvn", xp, a, G, Q, np.zeros(d), np.eye(d), np.eye(d), xi)
+    assert np.array_equal(got, want_det)                         # production order: bit for bit
+    got = ctx.mvt_sample(xp, a, G, Q, 4.0, xi=xi, chi=chi)
+    assert np.allclose(got, orc.propagate("mvt", xp, a, G, None, Q, xi, chi), rtol=1e-13, atol=1e-13)
+    mu = rng.standard_normal(d)
+    got = ctx.mvn_sample_init(mu, Q, N, xi=xi)
+    assert np.allclose(got, orc.propagate("mvn", None, None, None, mu, Q, xi), rtol=1e-13, atol=1e-13)
+    # device-drawn noise is the Philox stream the oracle mirrors
+    got = ctx.mvn_sample(xp, a, G, Q, seed=99, step=3)
+    xi_dev = orc.rng_fill_normals(99, 1, 3, 0, N, d)
+    want_det, _ = orc.step_det("mvn", xp, a, G, Q, np.zeros(d), np.eye(d), np.eye(d), xi_dev)
+    assert np.array_equal(got, want_det)
+    # chi-square factors drawn on the device: right law (E[chi^-2] = 1, i.e. chi2/nu has mean 1)
+    got = ctx.mvt_sample(np.zeros((20000, 1)), None, np.zeros((1, 1)), np.ones((1, 1)), 6.0, xi=np.ones((20000, 1)), seed=5)
+    inv = 1.0 / got[:, 0] ** 2
+    assert abs(inv.mean() - 1.0) < 0.02 and abs(inv.var() - 2.0 / 6.0) < 0.03
+
+
+# ------------------------------------------------------------------------------------------------
+# a4: Metropolis resampler
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("N,B", [(1, 3), (2, 10), (1000, 10), (65537, 7)])
+def test_metropolis_bit_exact(ctx, orc, N, B):
+    rng = np.random.default_rng(N + B)
+    w = rng.random(N) ** 4
+    w[rng.random(N) < 0.1] = 0.0                                # zero weights: 0/0, x/0 branches
+    u, j = rng.random((N, B)), rng.integers(0, N, (N, B), dtype=np.uint32)
+    assert np.array_equal(ctx.metropolis_hastings(w, B, u=u, j=j), orc.metropolis_hastings(w, u, j))
+
+
+def test_metropolis_invariants(ctx, orc):
+    rng = np.random.default_rng(3)
+    N, B = 512, 10
+    u, j = rng.random((N, B)) * 0.999 + 0.001, rng.integers(0, N, (N, B), dtype=np.uint32)
+    assert np.array_equal(ctx.metropolis_hastings(np.ones(N), B, u=u, j=j), j[:, -1])   # constant w
+    m = 17
+    onehot = np.zeros(N)
+    onehot[m] = 1.0
+    a = ctx.metropolis_hastings(onehot, B, u=u, j=j)
+    hit = (j == m).any(axis=1)
+    assert np.array_equal(a[hit], np.full(hit.sum(), m))
+    others = ~hit
+    others[m] = False
+    # particles that never draw m keep k = i ... unless k = i has weight 0 and j has weight 0: 0/0 rejects
+    assert np.array_equal(a[others], np.arange(N, dtype=np.uint32)[others])
+    assert np.array_equal(ctx.metropolis_hastings(np.zeros(2), 10), [0, 1])
+
+
+def test_metropolis_philox_mirror(ctx, orc):
+    N, B = 300, 10
+    w = np.random.default_rng(8).random(N)
+    u, j = orc.rng_metropolis(1234, 5, N, B)
+    assert np.array_equal(ctx.metropolis_hastings(w, B, seed=1234, step=5), orc.metropolis_hastings(w, u, j))
+
+
+# ------------------------------------------------------------------------------------------------
+# a11: normalisation, ESS, systematic / multinomial resampling
+# ------------------------------------------------------------------------------------------------
+def _weight_cases(rng, N):
+    yield "uniform", np.ones(N)
+    yield "random", rng.random(N)
+    yield "heavy", rng.random(N) ** 20
+    w = np.zeros(N)
+    w[N // 3] = 1.0
+    yield "onehot", w
+    w = rng.random(N)
+    w[rng.random(N) < 0.9] = 0.0
+    w[-1] = 0.5
+    yield "sparse", w
+    yield "tiny", rng.random(N) * 1e-300
+    w = rng.random(N)
+    w[0] = np.nan
+    w[1] = -1.0
+    yield "nan_neg", w
+
+
+@pytest.mark.parametrize("N", [1, 2, 255, 2048, 2049, 10000, 300001])
+def test_systematic_bit_exact(ctx, orc, N):
+    rng = np.random.default_rng(N)
+    for name, w in _weight_cases(rng, N):
+        for u0 in (0.0, 0.37, 0.999999999):
+            want, rc = orc.resample_systematic(w, u0)
+            assert rc == 0
+            got = ctx.resample_systematic(w, u0)
+            assert np.array_equal(got, want), (name, N, u0)
+
+
+def test_systematic_properties_large(ctx):
+    rng = np.random.default_rng(11)
+    N = (1 << 22) + 12345                   # many tiles: look-back windows beyond 32 tiles
+    w = rng.random(N) ** 3
+    a = ctx.resample_systematic(w, 0.5).astype(np.int64)
+    assert np.all(np.diff(a) >= 0)          # sorted
+    counts = np.bincount(a, minlength=N)
+    expect = N * w / w.sum()
+    assert counts.sum() == N
+    assert np.all(np.abs(counts - expect) < 1.0 + 1e-6)   # systematic: floor or ceil of N w / sum w
+
+
+def test_resample_degenerate_is_an_error(ctx):
+    import cusmc_b200
+    with pytest.raises(cusmc_b200.CusmcError) as e:
+        ctx.resample_systematic(np.zeros(100), 0.3)
+    assert e.value.code == 4
+    with pytest.raises(cusmc_b200.CusmcError):
+        ctx.resample_multinomial(np.full(10, np.nan), np.full(10, 0.5))
+    with pytest.raises(cusmc_b200.CusmcError):
+        ctx.resample_systematic(np.ones(4), 1.0)      # u0 outside [0, 1)
+
+
+@pytest.mark.parametrize("N", [1, 100, 5000, 200003])
+def test_multinomial_bit_exact(ctx, orc, N):
+    rng = np.random.default_rng(N + 1)
+    for name, w in _weight_cases(rng, N):
+        u = rng.random(N)
+        u[0] = 0.0
+        want, rc = orc.resample_multinomial(w, u)
+        assert np.array_equal(ctx.resample_multinomial(w, u), want), (name, N)
+
+
+def test_normalize_ess(ctx, orc):
+    rng = np.random.default_rng(21)
+    for N in (1, 1000, 100000):
+        lw = rng.standard_normal(N) * 30 - 700.0     # the linear domain would underflow here
+        lse, ess = ctx.normalize_ess(lw)
+        lse0, ess0, _ = orc.logsumexp_ess(lw)
+        assert abs(lse - lse0) < 1e-9 * abs(lse0)
+        assert abs(ess - ess0) < 1e-6 * ess0 + 1e-9
+    lse, ess = ctx.normalize_ess(np.array([-np.inf, 0.0, -np.inf]))
+    assert abs(lse) < 1e-12 and abs(ess - 1.0) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# fused propagate + reweight, and the whole filter
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0)])
+@pytest.mark.parametrize("d,dy", [(2, 2), (8, 8), (5, 3), (16, 16)])
+def test_propagate_reweight_dev(ctx, orc, kind, nu, d, dy):
+    import torch
+    rng = np.random.default_rng(d + dy)
+    N = 4099
+    G, Q, F, V = rng.standard_normal((d, d)) * 0.5, rng.standard_normal((d, d)) * 0.3, rng.standard_normal((dy, d)), spd(rng, dy)
+    y = rng.standard_normal(dy)
+    xp, xi = rng.standard_normal((N, d)), rng.standard_normal((N, d))
+    chi = np.sqrt(nu / rng.chisquare(nu, (N, d))) if kind == "mvt" else None
+    a = rng.integers(0, N, N, dtype=np.uint32)
+    x_new = torch.empty((d, N), dtype=torch.float64, device="cuda")
+    lw = torch.empty(N, dtype=torch.float64, device="cuda")
+    mx = torch.full((1,), -np.inf, dtype=torch.float64, device="cuda")
+    ctx.propagate_reweight_dev(kind, x_new, torch_dev(xp.T), torch_dev(a), G, Q, y, F, V, lw, nu=nu,
+                               xi=torch_dev(xi.T), chi=None if chi is None else torch_dev(chi.T), lw_max=mx)
+    ctx.synchronize()
+    want_x, want_lw = orc.step_det(kind, xp, a, G, Q, y, F, V, xi, nu=nu, chi=chi)
+    assert np.array_equal(x_new.cpu().numpy().T, want_x)
+    if kind == "mvn":
+        assert np.array_equal(lw.cpu().numpy(), want_lw)
+    else:
+        assert relerr(lw.cpu().numpy(), want_lw) < 1e-12
+    assert mx.item() == lw.max().item()
+    # and against the reference-form arithmetic (LU inverse, left-to-right quadratic form)
+    ref_x = orc.propagate(kind, xp, a, G, None, Q, xi, chi)
+    ref_lw = orc.reweight(kind, y, ref_x, F, V, nu=nu, log=True)
+    assert relerr(lw.cpu().numpy(), ref_lw) < RTOL_LOGPDF
+
+
+def _model(d, rng=None):
+    I = np.eye(d)
+    return dict(m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=0.5 * I, W=0.3 * I)
+
+
+def _eig_factor(S):
+    lam, vec = np.linalg.eigh(S)
+    return vec * np.sqrt(lam)
+
+
+@pytest.mark.parametrize("resampler", ["systematic", "multinomial", "metropolis"])
+@pytest.mark.parametrize("d", [2, 8])
+def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d):
+    """Same pre-drawn normals / uniforms on both sides: ancestors and particle states must agree
+    bit for bit at every step; log-weights too (MVN), ESS and log-likelihood to rounding."""
+    rng = np.random.default_rng(500 + d)
+    N, T, B = 3000, 12, 10
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((T - 1, N, d))
+    u, j = rng.random((T - 1, N, B)), rng.integers(0, N, (T - 1, N, B), dtype=np.uint32)
+    u0, um = rng.random(T - 1), rng.random((T - 1, N))
+    pf = ctx.filter(N=N, Y=Y, resampler=resampler, B=B, keep_history=True, **md)
+    pf.run(xi0=torch_dev(xi0.T), xi=torch_dev(xi.transpose(0, 2, 1)), u=torch_dev(u), j=torch_dev(j),
+           u0=u0, um=torch_dev(um))
+    h, s = pf.history(), pf.summary()
+    pf.close()
+    # the library uses an eigen factor of C0 / W; for scalar covariances it is sqrt(c) I up to
+    # sign conventions of the Jacobi sweep (none applied to a diagonal matrix)
+    ref = orc.filter_det("mvn", resampler, Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, B=B, xi0=xi0, xi=xi, u=u, j=j, u0=u0, um=um)
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+    if resampler == "metropolis":
+        assert relerr(h["w"], ref["w"]) < 1e-13       # densities: CUDA exp vs libm exp
+    else:
+        assert np.array_equal(h["w"], ref["w"])
+        assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+        assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
+    wn = np.exp(h["w"] - h["w"].max(axis=1, keepdims=True)) if resampler != "metropolis" else h["w"]
+    mean = (wn[:, :, None] * h["x"]).sum(1) / wn.sum(1)[:, None]
+    assert np.allclose(s["mean"], mean, rtol=1e-10, atol=1e-12)
+
+
+@pytest.mark.parametrize("resampler", ["systematic", "metropolis"])
+def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
+    rng = np.random.default_rng(77)
+    d, N, T = 2, 2048, 8
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=N, Y=Y, resampler=resampler, seed=4242, keep_history=True, **md)
+    h = pf.run().history()
+    pf.close()
+    ref = orc.filter_det("mvn", resampler, Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, seed=4242)
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+
+
+def kalman_means(Y, m0, C0, F, G, V, W):
+    m, P = m0.copy(), C0.copy()
+    out = [m.copy()]
+    for t in range(1, Y.shape[1]):
+        m, P = G @ m, G @ P @ G.T + W
+        S = F @ P @ F.T + V
+        K = P @ F.T @ np.linalg.inv(S)
+        m = m + K @ (Y[:, t] - F @ m)
+        P = P - K @ F @ P
+        out.append(m.copy())
+    return np.array(out), P
+
+
+@pytest.mark.parametrize("resampler", ["systematic", "multinomial", "metropolis"])
+def test_filter_posterior_moments_vs_kalman(ctx, resampler):
+    """Linear-Gaussian model on the reference's data series: the exact filtering mean is the Kalman
+    mean.  Monte Carlo tolerance: 6 sigma / sqrt(ESS) per component (ESS ~ N/3 here), plus the
+    O(1/B)-type bias of the Metropolis resampler (B = 30)."""
+    Y = np.loadtxt(os.path.join(HERE, "golden", "y_t.csv"), delimiter=",", skiprows=1).T[:, :60]
+    I = np.eye(2)
+    md = dict(m0=np.zeros(2), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
+    N = 200000
+    pf = ctx.filter(N=N, Y=Y, resampler=resampler, B=30, seed=9, **md)
+    s = pf.run().summary()
+    pf.close()
+    km, P = kalman_means(Y, **md)
+    sd = math.sqrt(P[0, 0])
+    tol = 6 * sd / math.sqrt(N / 4) + (0.02 if resampler == "metropolis" else 0.0)
+    assert np.max(np.abs(s["mean"][1:] - km[1:])) < tol
+    if resampler != "metropolis":
+        assert np.all(s["ess"][1:] > N / 10) and np.all(s["ess"] <= N * (1 + 1e-9))
+
+
+def test_run_r_api(ctx):
+    import cusmc_b200
+    Y = np.loadtxt(os.path.join(HERE, "golden", "y_t.csv"), delimiter=",", skiprows=1).T
+    I = np.eye(2)
+    out = cusmc_b200.run(1000, 2, 25, Y, np.zeros(2), I, I, I, 0.1 * I, 0.1 * I, 0.0, "metropolis", "mvn")
+    assert out["weights"].shape == (25, 1000) and out["posterior_x"].shape == (25, 1000, 2)
+    assert np.allclose(out["weights"][0], 1.0 / 1000)           # w_0 = 1/N (src/mcmc.cpp:85)
+    assert np.all(out["weights"][1:] >= 0) and np.all(np.isfinite(out["posterior_x"]))
+    out = cusmc_b200.run(500, 2, 10, Y, np.zeros(2), I, I, I, 0.1 * I, 0.1 * I, 4.0, "metropolis", "mvt")
+    assert np.all(np.isfinite(out["posterior_x"]))
+    with pytest.raises(ValueError):
+        cusmc_b200.run(10, 2, 5, Y, np.zeros(2), I, I, I, I, I, 0.0, "gibbs", "mvn")
+    d1 = cusmc_b200.MVN(np.zeros(2), I, seed=1)
+    d2 = cusmc_b200.MVT(np.zeros(3), np.eye(3), 3.0, seed=1)
+    assert d1.shape == (2,) and d2.shape == (3,) and np.all(np.isfinite(d1)) and np.all(np.isfinite(d2))
+
+
+# ------------------------------------------------------------------------------------------------
+# independent MH chains
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0)])
+@pytest.mark.parametrize("d,shared", [(2, False), (8, True), (32, False), (17, False)])
+def test_mh_chains_bit_exact(ctx, orc, kind, nu, d, shared):
+    import torch
+    rng = np.random.default_rng(900 + d)
+    Cn, steps, step = 257, 40, 0.3
+    if shared:
+        L, mu = np.linalg.cholesky(spd(rng, d)), rng.standard_normal(d)
+        Ldev, mudev = torch_dev(L.T), torch_dev(mu)              # column-major
+    else:
+        L = np.stack([np.linalg.cholesky(spd(rng, d)) for _ in range(Cn)])
+        mu = rng.standard_normal((Cn, d))
+        Ldev, mudev = torch_dev(L.transpose(0, 2, 1)), torch_dev(mu)
+    x0 = rng.standard_normal((Cn, d))
+    z = rng.standard_normal((Cn, steps, d))
+    e = -np.log(rng.random((Cn, steps)))
+    thr = e if kind == "mvn" else np.exp(2 * e / (nu + d))
+    want_x, want_n, want_bits = orc.mh_chains(kind, mu, L, x0, z, thr, step, nu=nu, shared=shared)
+    x = torch_dev(x0)
+    nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+    bits = torch.zeros((Cn, steps), dtype=torch.uint8, device="cuda")
+    ctx.mh_chains_dev(kind, mudev, Ldev, x, steps, step, nu=nu, shared=shared, z=torch_dev(z), thr=torch_dev(thr),
+                      n_accept=nacc, accept_bits=bits)
+    ctx.synchronize()
+    assert np.array_equal(bits.cpu().numpy(), want_bits)          # accept / reject decisions
+    assert np.array_equal(nacc.cpu().numpy().astype(np.uint32), want_n)
+    assert np.array_equal(x.cpu().numpy(), want_x)
+    assert 0.05 < want_bits.mean() < 0.99
+
+
+def test_mh_chains_device_rng_moments(ctx):
+    """Philox-driven chains on an MVN target: time-averaged first and second moments of many chains
+    against the target's, 5 sigma Monte Carlo tolerance with the chain autocorrelation folded in."""
+    import torch
+    rng = np.random.default_rng(31)
+    d, Cn, steps = 4, 4096, 2000
+    S = spd(rng, d)
+    L, mu = np.linalg.cholesky(S), rng.standard_normal(d)
+    x = torch_dev(np.tile(mu, (Cn, 1)))
+    sx = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+    sxx = torch.zeros_like(sx)
+    nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+    ctx.mh_chains_dev("mvn", torch_dev(mu), torch_dev(L.T), x, steps, 1.0, shared=True, seed=77, n_accept=nacc,
+                      sum_x=sx, sum_xx=sxx)
+    ctx.synchronize()
+    mean = sx.cpu().numpy().mean(0) / steps
+    var = sxx.cpu().numpy().mean(0) / steps - mean ** 2
+    acc = nacc.cpu().numpy().mean() / steps
+    assert 0.1 < acc < 0.6
+    tol = 5 * np.sqrt(np.diag(S) * 40.0 / (Cn * steps))           # integrated autocorrelation <~ 40
+    assert np.all(np.abs(mean - mu) < tol + 0.01)
+    assert np.all(np.abs(var / np.diag(S) - 1.0) < 0.05)
+
+
+def test_layout_helpers(ctx):
+    import torch
+    x = torch.randn((1000, 7), dtype=torch.float64, device="cuda")
+    s = torch.empty((7, 1000), dtype=torch.float64, device="cuda")
+    b = torch.empty_like(x)
+    ctx.aos_to_soa_dev(x, s)
+    ctx.soa_to_aos_dev(s, b)
+    ctx.synchronize()
+    assert torch.equal(s, x.T.contiguous()) and torch.equal(b, x)
