@@ -56,8 +56,30 @@ def _colmajor(M):
 
 
 def _hp(a):
-    """Host pointer of a numpy array (None -> NULL)."""
+    """Host pointer of a numpy array the CALLER keeps alive (None -> NULL)."""
     return None if a is None else a.ctypes.data
+
+
+class _Args:
+    """Keeps converted temporaries alive for the duration of one C call: taking .ctypes.data of
+    an unnamed temporary would leave a dangling pointer by the time the call executes."""
+
+    def __init__(self):
+        self.keep = []
+
+    def mat(self, M):
+        if M is None:
+            return None
+        a = _colmajor(M)
+        self.keep.append(a)
+        return a.ctypes.data
+
+    def vec(self, v, dtype=np.float64):
+        if v is None:
+            return None
+        a = np.ascontiguousarray(v, dtype=dtype)
+        self.keep.append(a)
+        return a.ctypes.data
 
 
 def _dp(t):
@@ -104,7 +126,9 @@ class Context:
         """stream: a raw cudaStream_t integer, a torch.cuda.Stream, or None (context's own)."""
         ptr = None
         if stream is not None:
-            ptr = getattr(stream, "cuda_stream", stream)
+            # torch's default stream has handle 0, which the C ABI reads as "the context's own
+            # stream": address the legacy default stream by its explicit handle cudaStreamLegacy.
+            ptr = getattr(stream, "cuda_stream", stream) or 1
         self._check(self.lib.cusmc_ctx_set_stream(self.h, ptr))
 
     def use_torch_stream(self):
@@ -165,8 +189,9 @@ class Context:
         F = np.asarray(F, dtype=np.float64)
         dy = F.shape[0]
         w = np.empty(N)
-        self._check(self.lib.cusmc_mvn_pdf(self.h, _hp(w), _hp(_f64(y)), _hp(x), float(norm),
-                                           _hp(_colmajor(E_inv)), _hp(_colmajor(F)), N, d, dy))
+        A = _Args()
+        self._check(self.lib.cusmc_mvn_pdf(self.h, _hp(w), A.vec(y), _hp(x), float(norm),
+                                           A.mat(E_inv), A.mat(F), N, d, dy))
         return w
 
     def mvt_pdf(self, y, x_aos, E_inv, F, norm, df):
@@ -175,8 +200,9 @@ class Context:
         F = np.asarray(F, dtype=np.float64)
         dy = F.shape[0]
         w = np.empty(N)
-        self._check(self.lib.cusmc_mvt_pdf(self.h, _hp(w), _hp(_f64(y)), _hp(x), _hp(_colmajor(E_inv)),
-                                           _hp(_colmajor(F)), float(norm), N, d, dy, float(df)))
+        A = _Args()
+        self._check(self.lib.cusmc_mvt_pdf(self.h, _hp(w), A.vec(y), _hp(x), A.mat(E_inv),
+                                           A.mat(F), float(norm), N, d, dy, float(df)))
         return w
 
     def mvn_sample(self, x_prev_aos, a, G, Q, xi=None, seed=0, step=0):
@@ -185,8 +211,9 @@ class Context:
         out = np.empty((N, d))
         a_ = None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
         xi_ = None if xi is None else _f64(xi)
-        self._check(self.lib.cusmc_mvn_sample(self.h, _hp(out), _hp(xp), _hp(a_), _hp(_colmajor(G)),
-                                              _hp(_colmajor(Q)), _hp(xi_), int(seed), int(step), N, d))
+        A = _Args()
+        self._check(self.lib.cusmc_mvn_sample(self.h, _hp(out), _hp(xp), _hp(a_), A.mat(G),
+                                              A.mat(Q), _hp(xi_), int(seed), int(step), N, d))
         return out
 
     def mvn_sample_init(self, mu, Q, N, xi=None, seed=0):
@@ -194,7 +221,8 @@ class Context:
         d = mu.size
         out = np.empty((N, d))
         xi_ = None if xi is None else _f64(xi)
-        self._check(self.lib.cusmc_mvn_sample_init(self.h, _hp(out), _hp(mu), _hp(_colmajor(Q)),
+        A = _Args()
+        self._check(self.lib.cusmc_mvn_sample_init(self.h, _hp(out), _hp(mu), A.mat(Q),
                                                    _hp(xi_), int(seed), N, d))
         return out
 
@@ -205,8 +233,9 @@ class Context:
         a_ = None if a is None else np.ascontiguousarray(a, dtype=np.uint32)
         xi_ = None if xi is None else _f64(xi)
         chi_ = None if chi is None else _f64(chi)
-        self._check(self.lib.cusmc_mvt_sample(self.h, _hp(out), _hp(xp), _hp(a_), _hp(_colmajor(G)),
-                                              _hp(_colmajor(Q)), _hp(xi_), _hp(chi_), int(seed),
+        A = _Args()
+        self._check(self.lib.cusmc_mvt_sample(self.h, _hp(out), _hp(xp), _hp(a_), A.mat(G),
+                                              A.mat(Q), _hp(xi_), _hp(chi_), int(seed),
                                               int(step), N, d, float(df)))
         return out
 
@@ -282,9 +311,10 @@ class Context:
         N = ld if N is None else N
         F = np.asarray(F, dtype=np.float64)
         dy = F.shape[0]
+        A = _Args()
         self._check(self.lib.cusmc_propagate_reweight_dev(
             self.h, _kind(dist), int(log), _dp(x_new), _dp(x_prev), _dp(a), N, ld, d, dy,
-            _hp(_colmajor(G)), _hp(_colmajor(Q)), _hp(_f64(y)), _hp(_colmajor(F)), _hp(_colmajor(V)),
+            A.mat(G), A.mat(Q), A.vec(y), A.mat(F), A.mat(V),
             float(nu), _dp(xi), _dp(chi), int(seed), int(step), _dp(lw), _dp(lw_max)))
 
     def mh_chains_dev(self, dist, mu, L, x, steps, step_size, nu=0.0, shared=False, z=None, thr=None,

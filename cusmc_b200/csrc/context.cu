@@ -56,6 +56,8 @@ extern "C" const char *cusmc_last_error(const cusmc_ctx *ctx)
 extern "C" int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
+    // NULL selects the context's own stream; the legacy default stream is addressed by its
+    // explicit handle cudaStreamLegacy (0x1), which is what bindings pass for "stream 0".
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     return CUSMC_OK;
 }

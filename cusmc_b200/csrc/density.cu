@@ -116,6 +116,14 @@ int launch_density(cusmc_ctx *ctx, const AffineOp<D, TRI> &op, const Epilogue &e
         const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
         const int64_t grid = (N + kThreads - 1) / kThreads;
         const int vec_ok = (d % 2 == 0) && ((uintptr_t)x % 16 == 0);
+        if (smem > 48 * 1024) {   // d > 23: the tile needs the opt-in shared-memory carve-out
+            static bool raised = false;   // per instantiation
+            if (!raised) {
+                CUSMC_CUDA(ctx, cudaFuncSetAttribute(density_aos_kernel<D, TRI>,
+                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+                raised = true;
+            }
+        }
         density_aos_kernel<D, TRI><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
             op, ep, x, N, d, vec_ok, out);
     }

@@ -336,10 +336,11 @@ extern "C" int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, doubl
                                     int64_t ld, int d)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
-    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && ld >= N, "bad sizes");
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= 96 && ld >= N, "bad sizes (d must be in 1..96)");
     if (N == 0) return CUSMC_OK;
     const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
-    CUSMC_REQUIRE(ctx, smem <= 48 * 1024, "d too large for the transpose tile");
+    if (smem > 48 * 1024)
+        CUSMC_CUDA(ctx, cudaFuncSetAttribute(aos_to_soa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     aos_to_soa_kernel<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, smem, ctx->stream>>>(aos_dev, soa_dev, N, ld, d);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
@@ -349,10 +350,11 @@ extern "C" int cusmc_soa_to_aos_dev(cusmc_ctx *ctx, const double *soa_dev, doubl
                                     int64_t ld, int d)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
-    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && ld >= N, "bad sizes");
+    CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= 96 && ld >= N, "bad sizes (d must be in 1..96)");
     if (N == 0) return CUSMC_OK;
     const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
-    CUSMC_REQUIRE(ctx, smem <= 48 * 1024, "d too large for the transpose tile");
+    if (smem > 48 * 1024)
+        CUSMC_CUDA(ctx, cudaFuncSetAttribute(soa_to_aos_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     soa_to_aos_kernel<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, smem, ctx->stream>>>(soa_dev, aos_dev, N, ld, d);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;

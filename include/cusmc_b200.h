@@ -64,7 +64,8 @@ int cusmc_version(void);
 int cusmc_ctx_create(cusmc_ctx **ctx, int device);
 int cusmc_ctx_destroy(cusmc_ctx *ctx);
 const char *cusmc_last_error(const cusmc_ctx *ctx);
-/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own. */
+/* Use an existing cudaStream_t (e.g. torch's current stream); NULL = the context's own
+ * non-blocking stream.  To run on the legacy default stream pass cudaStreamLegacy (0x1). */
 int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream);
 int cusmc_ctx_synchronize(cusmc_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */

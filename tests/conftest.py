@@ -26,5 +26,6 @@ def ctx():
         pytest.skip("no CUDA device")
     import cusmc_b200
     c = cusmc_b200.Context(0)
+    c.use_torch_stream()      # one stream for torch's fills/copies and the library's kernels
     yield c
     c.close()
