@@ -1,0 +1,273 @@
+"""CPU tests: pin the oracle against the reference's known answers, the committed golden vectors
+and textbook invariants.  No GPU needed."""
+import json
+import math
+import os
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+GOLDEN = json.load(open(os.path.join(HERE, "golden", "golden.json")))
+
+
+def spd(rng, d):
+    A = rng.standard_normal((d, d))
+    return A @ A.T / d + np.eye(d)
+
+
+# ---- the reference's own known answers ----------------------------------
+def test_reference_known_answers(orc):
+    ref = GOLDEN["reference"]
+    v = orc.MVNPDF(ref["MVNPDF"]["x"], ref["MVNPDF"]["mu"], np.array(ref["MVNPDF"]["sigma"], float))
+    assert round(v, 7) == ref["MVNPDF"]["value"]                  # CuSMC/CuSMC.tex:104
+    v = orc.MVTPDF(ref["MVTPDF"]["x"], ref["MVTPDF"]["mu"], np.array(ref["MVTPDF"]["sigma"], float), 3.0)
+    assert round(v, 8) == ref["MVTPDF"]["value"]                  # CuSMC/CuSMC.tex:141
+    rng = np.random.default_rng(0)
+    u, j = rng.random((2, 10)), rng.integers(0, 2, (2, 10), dtype=np.uint32)
+    assert orc.metropolis_hastings([0.0, 0.0], u, j).tolist() == [0, 1]   # man/metropolis_hastings.Rd:22-27
+
+
+def test_independent_golden_vectors(orc):
+    worst = 0.0
+    for c in GOLDEN["independent"]:
+        x, sigma = np.array(c["x"]), np.array(c["sigma"])
+        for faithful in (False, True):
+            pdf = orc.pdf_batch(c["kind"], x, c["mu"], sigma, c["nu"], faithful=faithful)
+            worst = max(worst, np.max(np.abs(pdf - c["pdf"]) / np.abs(c["pdf"])))
+        lg = orc.pdf_batch(c["kind"], x, c["mu"], sigma, c["nu"], log=True)
+        worst = max(worst, np.max(np.abs(lg - c["logpdf"]) / np.abs(c["logpdf"])))
+        # the single-vector R helpers agree with the batch form
+        one = orc.MVNPDF(x[0], c["mu"], sigma) if c["kind"] == "mvn" else orc.MVTPDF(x[0], c["mu"], sigma, c["nu"])
+        assert abs(one - c["pdf"][0]) <= 1e-12 * c["pdf"][0]
+    assert worst < 1e-12
+
+
+def test_philox_known_answers(orc):
+    for k in GOLDEN["philox4x32_10"]:
+        assert orc.philox4x32(k["ctr"], k["key"]).tolist() == k["out"]
+
+
+def test_data_fixture():
+    y = np.loadtxt(os.path.join(HERE, "golden", "y_t.csv"), delimiter=",", skiprows=1)
+    assert y.shape == (1000, 2) and y[0].tolist() == [0.0, 0.0]      # data_raw/y_t.csv:2
+    assert y[:, 1].max() == 0.0 and -2.61 < y[:, 0].min() < -2.59
+
+
+# ---- dense helpers --------------------------------------------------------------------------------
+@pytest.mark.parametrize("d", [1, 2, 5, 16, 32])
+def test_lu_det_inverse_cholesky(orc, d):
+    rng = np.random.default_rng(d)
+    A = rng.standard_normal((d, d)) + 3 * np.eye(d)
+    assert abs(orc.determinant(A) - np.linalg.det(A)) <= 1e-10 * abs(np.linalg.det(A))
+    assert np.allclose(orc.inverse(A) @ A, np.eye(d), atol=1e-10)
+    S = spd(rng, d)
+    L = orc.cholesky_lower(S)
+    assert np.allclose(L @ L.T, S, atol=1e-12) and np.allclose(L, np.tril(L))
+    assert np.allclose(orc.tri_inverse_lower(L) @ L, np.eye(d), atol=1e-12)
+    with pytest.raises(np.linalg.LinAlgError):
+        orc.cholesky_lower(-np.eye(d))
+
+
+def test_mvt_float_nu_semantics(orc):
+    """nu is a float and nu + n is a float sum: nu = 0.1 is not a double 0.1."""
+    S = np.eye(3)
+    x = np.array([0.3, -0.2, 0.5])
+    nu32 = float(np.float32(0.1))
+    q = float(x @ x)
+    nun = float(np.float32(0.1) + np.float32(3))
+    want = ((math.pi * nu32) ** -1.5) * math.gamma(0.5 * nun) / math.gamma(0.5 * nu32) * (1 + q / nu32) ** (-0.5 * nun)
+    assert abs(orc.MVTPDF(x, np.zeros(3), S, 0.1) - want) <= 1e-13 * want
+    wrong = ((math.pi * 0.1) ** -1.5) * math.gamma(1.55) / math.gamma(0.05) * (1 + q / 0.1) ** (-1.55)
+    assert abs(orc.MVTPDF(x, np.zeros(3), S, 0.1) - wrong) > 1e-9 * wrong
+
+
+# ---- Metropolis resampler invariants ---------------------------------------
+def test_metropolis_invariants(orc):
+    rng = np.random.default_rng(1)
+    N, B = 200, 10
+    u = rng.random((N, B)) * 0.99 + 0.005
+    j = rng.integers(0, N, (N, B), dtype=np.uint32)
+    assert np.array_equal(orc.metropolis_hastings(np.ones(N), u, j), j[:, -1])   # constant w: last j drawn
+    m = 7
+    w = np.zeros(N)
+    w[m] = 1.0
+    a = orc.metropolis_hastings(w, u, j)
+    hit = (j == m).any(axis=1)
+    hit[m] = True
+    assert np.all(a[hit] == m) and np.array_equal(a[~hit], np.arange(N)[~hit])
+    assert np.array_equal(orc.metropolis_hastings(rng.random(N), u[:, :0], j[:, :0]), np.arange(N))   # B = 0
+
+
+# ---- deterministic math -----------------------------------------------------------------------------
+def test_det_exp_log_accuracy(orc):
+    x = np.concatenate([np.linspace(-700, 0, 20001), np.linspace(0, 700, 2001)])
+    rel = np.abs(orc.det_exp(x) - np.exp(x)) / np.exp(x)
+    assert rel.max() < 4e-16 * 4                      # a few ulp
+    assert orc.det_exp([0.0])[0] == 1.0 and orc.det_exp([-800.0])[0] == 0.0 and np.isinf(orc.det_exp([710.0])[0])
+    sub = orc.det_exp([-740.0])[0]                    # subnormal result
+    assert 0 < sub < 1e-320 and abs(sub - math.exp(-740.0)) <= 5e-324 * 4
+    y = np.concatenate([np.logspace(-307, 307, 20001), np.linspace(0.5, 2.0, 5001), [5e-324, 1e-310]])
+    err = np.abs(orc.det_log(y) - np.log(y))
+    assert np.all(err <= 4e-16 * np.maximum(np.abs(np.log(y)), 1.0))
+    assert orc.det_log([1.0])[0] == 0.0 and np.isneginf(orc.det_log([0.0])[0]) and np.isnan(orc.det_log([-1.0])[0])
+    for t in np.linspace(0, 1.9999, 2001):
+        s, c = orc.det_sincospi(t)
+        assert abs(s - math.sin(math.pi * t)) < 2e-15 and abs(c - math.cos(math.pi * t)) < 2e-15   # pi*t itself rounds
+
+
+def test_counter_based_normals(orc):
+    z = orc.rng_fill_normals(123, 1, 7, 0, 200000, 3)
+    assert abs(z.mean()) < 0.01 and abs(z.var() - 1) < 0.01
+    assert abs(np.corrcoef(z[:, 0], z[:, 1])[0, 1]) < 0.01
+    assert np.array_equal(z[1000:1010], orc.rng_fill_normals(123, 1, 7, 1000, 10, 3))   # keyed by global index
+    assert not np.array_equal(z[:10], orc.rng_fill_normals(123, 1, 8, 0, 10, 3))
+    u, j = orc.rng_metropolis(5, 2, 64, 10)
+    assert np.all((u >= 0) & (u < 1)) and np.all(j < 64)
+
+
+# ---- fixed-point normalisation / resampling ---------------------------------------------------------
+def test_fixed_point_weights(orc):
+    assert orc.fixed_shift(1) == 61 and orc.fixed_shift(2) == 60 and orc.fixed_shift(3) == 59
+    assert orc.fixed_shift(1 << 20) == 41 and orc.fixed_shift((1 << 20) + 1) == 40
+    w = np.array([1.0, 0.5, 0.0, -1.0, np.nan, 0.25, np.inf])
+    q, tot = orc.fixed_weights(w, 1.0, 10)
+    assert q.tolist() == [1024, 512, 0, 0, 0, 256, 0] and tot == 1792
+
+
+@pytest.mark.parametrize("N", [1, 2, 3, 17, 1000, 65536])
+def test_systematic_matches_textbook(orc, N):
+    """Against the floating-point textbook algorithm: equal except where a boundary falls within
+    fixed-point resolution (none for these sizes), sorted, counts = floor/ceil of N w / sum w."""
+    rng = np.random.default_rng(N)
+    w = rng.random(N) + 1e-3
+    u0 = rng.random()
+    a, rc = orc.resample_systematic(w, u0)
+    assert rc == 0
+    cdf = np.cumsum(w / w.sum())
+    cdf[-1] = 1.0
+    tb = np.searchsorted(cdf, (np.arange(N) + u0) / N, side="right")
+    assert np.mean(a == tb) > 0.999
+    assert np.all(np.diff(a.astype(np.int64)) >= 0)
+    cnt = np.bincount(a, minlength=N)
+    assert cnt.sum() == N and np.all(np.abs(cnt - N * w / w.sum()) < 1 + 1e-6)
+
+
+def test_systematic_degenerate(orc):
+    a, rc = orc.resample_systematic(np.zeros(5), 0.5)
+    assert rc == 1 and a.tolist() == [0, 1, 2, 3, 4]
+    w = np.zeros(100)
+    w[42] = 3.0
+    a, rc = orc.resample_systematic(w, 0.9)
+    assert rc == 0 and np.all(a == 42)
+
+
+def test_multinomial_matches_textbook(orc):
+    rng = np.random.default_rng(3)
+    N = 5000
+    w, u = rng.random(N), rng.random(N)
+    a, rc = orc.resample_multinomial(w, u)
+    tb = np.searchsorted(np.cumsum(w / w.sum()), u, side="right")
+    assert rc == 0 and np.mean(a == np.minimum(tb, N - 1)) > 0.999
+    freq = np.bincount(a, minlength=N) / N
+    assert abs(freq @ np.arange(N) - (w / w.sum()) @ np.arange(N)) < 5 * N / math.sqrt(N)
+
+
+def test_logsumexp_ess(orc):
+    lw = np.log(np.array([1.0, 2.0, 3.0, 4.0])) - 1000.0
+    lse, ess, m = orc.logsumexp_ess(lw)
+    assert abs(lse - (math.log(10.0) - 1000.0)) < 1e-12 and abs(ess - 100.0 / 30.0) < 1e-12
+    assert m == lw.max()
+
+
+# ---- propagate / reweight / filter --------------------------------------------------------------------
+def test_propagate_reweight_reference_form(orc):
+    rng = np.random.default_rng(4)
+    N, d, dy = 300, 3, 2
+    G, Q, F, V = rng.standard_normal((d, d)), rng.standard_normal((d, d)), rng.standard_normal((dy, d)), spd(rng, dy)
+    xp, xi, y = rng.standard_normal((N, d)), rng.standard_normal((N, d)), rng.standard_normal(dy)
+    a = rng.integers(0, N, N, dtype=np.uint32)
+    x = orc.propagate("mvn", xp, a, G, None, Q, xi)
+    assert np.allclose(x, xp[a] @ G.T + xi @ Q.T, atol=1e-13)
+    chi = rng.random((N, d)) + 0.5
+    xt = orc.propagate("mvt", xp, a, G, None, Q, xi, chi)
+    assert np.allclose(xt, xp[a] @ G.T + chi * (xi @ Q.T), atol=1e-13)                   # Q2: chi per component
+    from scipy import stats
+    w = orc.reweight("mvn", y, x, F, V, faithful=True)
+    assert np.allclose(w, stats.multivariate_normal(mean=np.zeros(dy), cov=V).pdf(y - x @ F.T), rtol=1e-11)
+    wt = orc.reweight("mvt", y, x, F, V, nu=4.0)
+    assert np.allclose(wt, stats.multivariate_t(loc=np.zeros(dy), shape=V, df=4.0).pdf(y - x @ F.T), rtol=1e-11)
+    # production-order restatement agrees with the reference form to rounding
+    xd, lwd = orc.step_det("mvn", xp, a, G, Q, y, F, V, xi)
+    assert np.allclose(xd, x, rtol=1e-13, atol=1e-13)
+    assert np.allclose(lwd, np.log(w), rtol=1e-11)
+    assert orc.quadform_fma(np.eye(3), np.array([1.0, 2.0, 3.0]), np.array([1.0, 1.0, 1.0]), tri=True) == 0 + 1 + 4
+
+
+def kalman_means(Y, m0, C0, F, G, V, W):
+    m, P = m0.copy(), C0.copy()
+    out = [m.copy()]
+    for t in range(1, Y.shape[1]):
+        m, P = G @ m, G @ P @ G.T + W
+        K = P @ F.T @ np.linalg.inv(F @ P @ F.T + V)
+        m = m + K @ (Y[:, t] - F @ m)
+        P = P - K @ F @ P
+        out.append(m.copy())
+    return np.array(out), P
+
+
+@pytest.mark.parametrize("resampler", ["metropolis", "systematic", "multinomial"])
+def test_filter_tracks_kalman(orc, resampler):
+    """configs[0] in small: the reference model on y_t.csv, against the exact Kalman mean."""
+    Y = np.loadtxt(os.path.join(HERE, "golden", "y_t.csv"), delimiter=",", skiprows=1).T[:, :40]
+    I = np.eye(2)
+    md = dict(m0=np.zeros(2), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
+    N = 20000
+    s10 = math.sqrt(0.1)
+    r = orc.filter_det("mvn", resampler, Y, md["m0"], I, I, I, md["V"], s10 * I, N, seed=3, B=30)
+    w = r["w"] if resampler == "metropolis" else np.exp(r["w"] - r["w"].max(axis=1, keepdims=True))
+    mean = (w[:, :, None] * r["x"]).sum(1) / w.sum(1)[:, None]
+    km, P = kalman_means(Y, **md)
+    assert np.max(np.abs(mean[8:] - km[8:])) < 6 * math.sqrt(P[0, 0]) / math.sqrt(N / 4) + 0.02
+    if resampler != "metropolis":
+        assert np.all(r["ess"][8:] > N / 10)
+
+
+def test_filter_reference_loop_equals_det_loop(orc):
+    """orc_filter_metropolis (reference-form arithmetic) and orc_filter_det (production order) are two
+    statements of src/mcmc.cpp:292-308: same ancestors, states equal to rounding."""
+    rng = np.random.default_rng(8)
+    N, d, T, B = 400, 2, 10, 10
+    I = np.eye(d)
+    Y = rng.standard_normal((d, T))
+    xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((T - 1, N, d))
+    u, j = rng.random((T - 1, N, B)), rng.integers(0, N, (T - 1, N, B), dtype=np.uint32)
+    G, Qw, V = 0.9 * I, 0.6 * I, 0.5 * I
+    r1 = orc.filter_metropolis("mvn", Y, np.zeros(d), I, I, G, V, Qw, 0.0, xi0, u, j, xi)
+    r2 = orc.filter_det("mvn", "metropolis", Y, np.zeros(d), I, I, G, V, Qw, N, B=B, xi0=xi0, xi=xi, u=u, j=j)
+    assert np.array_equal(r1["a"][1:], r2["a"][1:])
+    assert np.allclose(r1["x"], r2["x"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(r1["w"], r2["w"], rtol=1e-11)
+
+
+# ---- MH chains ------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 6.0)])
+def test_mh_chains_oracle_targets_the_right_law(orc, kind, nu):
+    rng = np.random.default_rng(12)
+    d, Cn, steps = 3, 400, 1500
+    S = spd(rng, d)
+    L, mu = np.linalg.cholesky(S), rng.standard_normal(d)
+    x0 = mu + rng.standard_normal((Cn, d)) @ L.T
+    z = rng.standard_normal((Cn, steps, d))
+    e = -np.log(rng.random((Cn, steps)))
+    thr = e if kind == "mvn" else np.exp(2 * e / (nu + d))
+    xf, nacc, bits = orc.mh_chains(kind, mu, L, x0, z, thr, 1.0, nu=nu, shared=True)
+    assert 0.15 < bits.mean() < 0.7 and np.array_equal(bits.sum(1), nacc)
+    cov = S if kind == "mvn" else S * nu / (nu - 2)
+    assert np.all(np.abs(xf.mean(0) - mu) < 5 * np.sqrt(np.diag(cov) / Cn))
+    assert np.all(np.abs(np.var(xf, axis=0) / np.diag(cov) - 1) < 0.45)
+    # a step with thr = 0 never accepts (mvn: 0.5 (q' - q) < 0 only if q' < q -> still possible), so
+    # use thr = -inf for "never" and +inf for "always"
+    xa, na, _ = orc.mh_chains(kind, mu, L, x0, z[:, :5], np.full((Cn, 5), np.inf), 1.0, nu=nu, shared=True)
+    xn, nn, _ = orc.mh_chains(kind, mu, L, x0, z[:, :5], np.full((Cn, 5), -np.inf), 1.0, nu=nu, shared=True)
+    assert np.all(na == 5) and np.all(nn == 0) and np.array_equal(xn, x0)
