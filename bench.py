@@ -221,7 +221,9 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
         Lcm = L.transpose(1, 2).contiguous()
         del A, S
         mu = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
-        x = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+        # start in the typical set (x0 = L z): at d = 32 a chain started AT the mode cannot leave it
+        x = (L @ torch.randn((Cn, d, 1), dtype=torch.float64, device="cuda", generator=g)).squeeze(-1).contiguous()
+        del L
         nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
         ctx.use_torch_stream()
         ctx.mh_chains_dev("mvt", mu, Lcm, x, 5, 0.3, nu=5.0, seed=3, n_accept=nacc)

@@ -76,9 +76,11 @@ mh_chains_kernel(const ChainArgs a)
     for (int s = 0; s < a.steps; ++s) {
         double z, thr;
         if (PHILOX) {
-            double z0, z1;
-            cusmc_normal_pair(cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)s, (uint64_t)c, (uint32_t)(lane >> 1)), &z0, &z1);
-            z = live ? ((lane & 1) ? z1 : z0) : 0.0;
+            // lanes 4m .. 4m+3 share one Philox block; each keeps the Box-Muller pair it needs
+            const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)s, (uint64_t)c, (uint32_t)(lane >> 2));
+            float z0, z1;
+            cusmc_box_muller_f32((lane & 2) ? rz.v[2] : rz.v[0], (lane & 2) ? rz.v[3] : rz.v[1], &z0, &z1);
+            z = live ? (double)((lane & 1) ? z1 : z0) : 0.0;
             const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)s, (uint64_t)c, 0);
             const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
             thr = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;

@@ -59,6 +59,12 @@ struct StepArgs {
     double const_weight;         // used when skip_weight
     float nu;
     int d, dy, kind, has_prev, skip_weight, rng_stream;
+    // sharded runs (sharded != 0): child i0 + i goes to slot (child - own_lo) of x_new / lw when it
+    // falls in [own_lo, own_lo + own_n), otherwise to the side buffer [(d + 1)][ld_side] (rows
+    // 0..d-1 state, row d weight) in child order, to be shipped to the owning rank.
+    int64_t own_lo, own_n, n_own_children, ld_side;
+    double *side;
+    int sharded;
 };
 
 __device__ __forceinline__ void atomic_max_double(double *addr, double v)
@@ -115,17 +121,33 @@ pf_step_kernel(const __grid_constant__ StepOp<D> op, const Epilogue ep, const St
         double xp[D], z[D], xn[D];
         int64_t parent = i;
         if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
+        double *dst_x = a.x_new + i, *dst_lw = a.lw + i;
+        int64_t dst_ld = a.ld_new;
+        if (a.sharded) {
+            const int64_t child = a.i0 + i;
+            if (child >= a.own_lo && child < a.own_lo + a.own_n) {
+                dst_x = a.x_new + (child - a.own_lo);
+                dst_lw = a.lw + (child - a.own_lo);
+            } else {
+                const int64_t sidx = child < a.own_lo ? i : i - a.n_own_children;
+                dst_x = a.side + sidx;
+                dst_lw = a.side + (int64_t)a.d * a.ld_side + sidx;
+                dst_ld = a.ld_side;
+            }
+        }
 #pragma unroll
         for (int j = 0; j < D; ++j)
             xp[j] = (a.has_prev && j < a.d) ? __ldg(a.x_prev + (int64_t)j * a.ld_prev + parent) : 0.0;
         if (PHILOX) {
+            // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
 #pragma unroll
-            for (int jp = 0; jp < D / 2; ++jp) {
-                double z0 = 0.0, z1 = 0.0;
-                if (2 * jp < a.d)
-                    cusmc_normal_pair(cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), (uint32_t)jp), &z0, &z1);
-                z[2 * jp] = z0;
-                z[2 * jp + 1] = (2 * jp + 1 < a.d) ? z1 : 0.0;
+            for (int jq = 0; jq < (D + 3) / 4; ++jq) {
+                double zq[4] = {0.0, 0.0, 0.0, 0.0};
+                if (4 * jq < a.d)
+                    cusmc_normal4(cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), (uint32_t)jq), zq);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * jq + e < D) z[4 * jq + e] = (4 * jq + e < a.d) ? zq[e] : 0.0;
             }
         } else {
 #pragma unroll
@@ -146,7 +168,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D> op, const Epilogue ep, const St
                 s = chi * s;
             }
             xn[k] = s + g;
-            if (k < a.d) st_stream(a.x_new + (int64_t)k * a.ld_new + i, xn[k]);
+            if (k < a.d) st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
         }
         if (a.skip_weight) {
             lw = a.const_weight;
@@ -161,7 +183,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D> op, const Epilogue ep, const St
             }
             lw = density_epilogue(ep, q);
         }
-        st_stream(a.lw + i, lw);
+        st_stream(dst_lw, lw);
     }
     if (a.lw_max) {
         double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
@@ -554,6 +576,65 @@ extern "C" int cusmc_mvt_sample(cusmc_ctx *ctx, double *x_new_aos, const double 
     if (ctx && !G) return cusmc_fail(ctx, CUSMC_ERR_INVALID, "cusmc_mvt_sample: G is NULL");
     return sample_dropin(ctx, CUSMC_MVT, x_new_aos, x_prev_aos, a, G, nullptr, Q, xi, chi, seed, step,
                          CUSMC_STREAM_NORMAL, N, d, df);
+}
+
+// ---- extern "C": one sharded step (child form), see cusmc_b200/sharded.py ---------------------------
+extern "C" int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log, double *x_own_dev,
+                                          double *lw_own_dev, int64_t ld_own, int64_t own_lo, int64_t own_n,
+                                          double *side_dev, int64_t ld_side, const double *x_prev_dev,
+                                          int64_t ld_prev, int64_t parent_base, const uint32_t *a_dev,
+                                          int64_t child_lo, int64_t n_children, int d, int dy,
+                                          const double *mu, const double *G, const double *Q, const double *y,
+                                          const double *F, const double *V, float nu, double const_weight,
+                                          uint64_t seed, uint64_t step, int rng_stream, double *lw_max_dev)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(ctx, n_children >= 0 && d >= 1 && dy >= 1 && own_n >= 0, "bad sizes");
+    CUSMC_REQUIRE(ctx, Q != nullptr, "Q is NULL");
+    CUSMC_REQUIRE(ctx, !G || x_prev_dev, "G given without parents");
+    CUSMC_REQUIRE(ctx, !V || (y && F), "V given without y / F");
+    if (n_children == 0) return CUSMC_OK;
+    const int64_t lo = child_lo > own_lo ? child_lo : own_lo;
+    const int64_t hi = (child_lo + n_children) < (own_lo + own_n) ? (child_lo + n_children) : (own_lo + own_n);
+    const int64_t n_own = hi > lo ? hi - lo : 0;
+    CUSMC_REQUIRE(ctx, n_own == n_children || side_dev, "children fall outside the own range but side is NULL");
+    CUSMC_REQUIRE(ctx, n_own == n_children || ld_side >= n_children - n_own, "side buffer too small");
+    CUSMC_REQUIRE(ctx, n_own == 0 || (x_own_dev && lw_own_dev && ld_own >= own_n), "own buffers missing");
+    std::vector<double> M, Winv;
+    Epilogue ep{};
+    double c[CUSMC_MAX_DIM] = {0};
+    if (V) {
+        CUSMC_CHECK(build_observation(ctx, kind, want_log, d, dy, F, V, nu, M, Winv, ep));
+        whiten_observation(Winv, dy, y, c);
+    }
+    StepArgs a{};
+    a.x_new = x_own_dev;
+    a.lw = lw_own_dev;
+    a.ld_new = ld_own;
+    a.x_prev = x_prev_dev;
+    a.ld_prev = ld_prev;
+    a.parent_base = parent_base;
+    a.anc = a_dev;
+    a.lw_max = lw_max_dev;
+    a.n_out = n_children;
+    a.i0 = child_lo;
+    a.seed = seed;
+    a.step = step;
+    a.nu = nu;
+    a.d = d;
+    a.dy = dy;
+    a.kind = kind;
+    a.has_prev = G ? 1 : 0;
+    a.skip_weight = V ? 0 : 1;
+    a.const_weight = const_weight;
+    a.rng_stream = rng_stream;
+    a.sharded = 1;
+    a.own_lo = own_lo;
+    a.own_n = own_n;
+    a.n_own_children = n_own;
+    a.side = side_dev;
+    a.ld_side = ld_side;
+    return cusmc_launch_step(ctx, d, dy, G, Q, 1.0, V ? &M : nullptr, c, mu, ep, a, true);
 }
 
 // ================================================================================================

@@ -150,8 +150,18 @@ constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (
 __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
                                                     double ng_over_t, double r0_over_t)
 {
+    // p = (C*Ng - r0) / T; the answer is ceil(p) for p > 0.  est is within 2^-19 of p (C, Ng/T and
+    // r0/T each carry one rounding and p <= 2^32), so whenever est sits safely inside an open unit
+    // interval the answer is floor(est) + 1 and no 128-bit arithmetic is needed.  Only boundaries
+    // within 1e-4 of an integer (2e-4 of all cases) take the exact path below.
+    const double est = fma((double)C, ng_over_t, -r0_over_t);
+    const double fl = floor(est);
+    const double frac = est - fl;
+    if (est > 1e-4 && frac > 1e-4 && frac < 1.0 - 1e-4) {
+        const uint64_t kf = (uint64_t)fl + 1;
+        return kf > Ng ? Ng : kf;
+    }
     const uint64_t rhs_lo = C * Ng, rhs_hi = __umul64hi(C, Ng);
-    double est = fma((double)C, ng_over_t, -r0_over_t);
     uint64_t k = est <= 0.0 ? 0 : (est >= (double)Ng ? Ng : (uint64_t)est);
     // lhs(k) = k*T + r0 as 128 bit
     auto lhs_less = [&](uint64_t kk) {
@@ -290,6 +300,7 @@ scan_resample_kernel(const ScanArgs p)
         ng_over_t = (double)p.N_global / (double)T;
         r0_over_t = (double)r0 / (double)T;
     }
+    uint64_t carry_k = 0;   // k2 of lane 31 in the previous round
 #pragma unroll
     for (int r = 0; r < kScanItems / 2; ++r) {
         const int64_t idx = wbase + r * 64 + lane * 2;
@@ -308,14 +319,16 @@ scan_resample_kernel(const ScanArgs p)
             }
         }
         if (p.anc_out) {
-            // children of particle idx   : [k0, k1),  of idx+1 : [k1, k2)
-            uint64_t k0 = 0, k1 = 0, k2 = 0;
-            const bool any = (q[2 * r] | q[2 * r + 1]) != 0;
-            if (any) {
-                k0 = offspring_below(c_before, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t);
-                k1 = q[2 * r] ? offspring_below(c0, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t) : k0;
-                k2 = q[2 * r + 1] ? offspring_below(c1, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t) : k1;
-            }
+            // children of particle idx : [k0, k1),  of idx+1 : [k1, k2).  The count is a pure
+            // function of the CDF value, so k0 is the left neighbour's k2: two evaluations per
+            // pair, plus one per warp for the first pair of the warp's chunk.
+            const uint64_t k1 = offspring_below(c0, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t);
+            const uint64_t k2 = offspring_below(c1, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t);
+            uint64_t k0 = __shfl_up_sync(0xffffffffu, k2, 1);
+            if (lane == 0)
+                k0 = (r == 0) ? offspring_below(c_before, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t)
+                              : carry_k;
+            carry_k = __shfl_sync(0xffffffffu, k2, 31);
             const uint64_t lo_lim = (uint64_t)p.out_lo, hi_lim = (uint64_t)(p.out_lo + p.out_n);
 #pragma unroll
             for (int h = 0; h < 2; ++h) {

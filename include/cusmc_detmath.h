@@ -153,6 +153,79 @@ CUSMC_HD void cusmc_det_sincospi(double t, double *s_out, double *c_out)
     *c_out = (n == 0) ? cs : (n == 1) ? -sn : (n == 2) ? -cs : sn;
 }
 
+
+/* ---- single-precision twins (FFMA + exact bit manipulation only) ---------------------------------
+ * Used by the in-kernel normal generator: its draws need 24-bit, not 53-bit, resolution, and on
+ * the device the fp64 versions above cost ~7x more issue slots (fp64 divide / sqrt / 64-bit
+ * int->double conversions expand into long instruction sequences). */
+CUSMC_HD float cusmc_bits_to_float(uint32_t b)
+{
+#if defined(__CUDA_ARCH__)
+    return __uint_as_float(b);
+#else
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+#endif
+}
+
+CUSMC_HD uint32_t cusmc_float_to_bits(float f)
+{
+#if defined(__CUDA_ARCH__)
+    return __float_as_uint(f);
+#else
+    uint32_t b;
+    memcpy(&b, &f, 4);
+    return b;
+#endif
+}
+
+/* log(x) for normal positive floats: x = m 2^e, m in [sqrt(1/2), sqrt 2), log m = f + f^2 P(f),
+ * f = m - 1, P a degree-7 least-squares fit (max abs error 3.9e-8). */
+CUSMC_HD float cusmc_det_logf(float x)
+{
+    const uint32_t b = cusmc_float_to_bits(x);
+    int e = (int)(b >> 23) - 127;
+    float m = cusmc_bits_to_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) {
+        m = m * 0.5f;
+        e += 1;
+    }
+    const float f = m - 1.0f;
+    float p = 0.09004202485084534f;
+    p = fmaf(p, f, -0.14257794618606567f);
+    p = fmaf(p, f, 0.14806459844112396f);
+    p = fmaf(p, f, -0.16575047373771667f);
+    p = fmaf(p, f, 0.19973105192184448f);
+    p = fmaf(p, f, -0.25001609325408936f);
+    p = fmaf(p, f, 0.33333659172058105f);
+    p = fmaf(p, f, -0.4999999403953552f);
+    const float r = fmaf(p * f, f, f);
+    return fmaf((float)e, 0.693147182464599609375f, r);
+}
+
+/* sin(pi t), cos(pi t) for t in [0, 2), t a multiple of 2^-23. */
+CUSMC_HD void cusmc_det_sincospif(float t, float *s_out, float *c_out)
+{
+    const float nf = rintf(t + t);
+    const float f = fmaf(nf, -0.5f, t);                 /* exact, in [-1/4, 1/4] */
+    const float x = f * 3.14159274101257324f;
+    const float x2 = x * x;
+    float ps = 2.75573192e-6f;                          /*  1/9! */
+    ps = fmaf(ps, x2, -1.98412698e-4f);                 /* -1/7! */
+    ps = fmaf(ps, x2, 8.33333377e-3f);                  /*  1/5! */
+    ps = fmaf(ps, x2, -1.66666672e-1f);                 /* -1/3! */
+    const float sn = fmaf(x * x2, ps, x);
+    float pc = 2.48015876e-5f;                          /*  1/8! */
+    pc = fmaf(pc, x2, -1.38888892e-3f);                 /* -1/6! */
+    pc = fmaf(pc, x2, 4.16666679e-2f);                  /*  1/4! */
+    pc = fmaf(pc, x2, -0.5f);
+    const float cs = fmaf(x2, pc, 1.0f);
+    const int n = ((int)nf) & 3;
+    *s_out = (n == 0) ? sn : (n == 1) ? cs : (n == 2) ? -sn : -cs;
+    *c_out = (n == 0) ? cs : (n == 1) ? -sn : (n == 2) ? -cs : sn;
+}
+
 /* ---- fixed-point weight image ------------------------------------------------------------
  * shift = 61 - ceil(log2(N_global)): N_global weights in [0, 2^shift] sum to at most 2^61, so
  * a prefix sum fits 62 bits and the two top bits of a 64-bit word stay free for the

@@ -19,10 +19,10 @@
 
 enum cusmc_rng_stream {
     CUSMC_STREAM_METROPOLIS = 0, /* sub = n (0..B-1): out[0..1] -> u, out[2..3] -> j */
-    CUSMC_STREAM_NORMAL = 1,     /* sub = component pair k/2: two normals per call */
+    CUSMC_STREAM_NORMAL = 1,     /* sub = component quad k/4: four normals per call */
     CUSMC_STREAM_CHI = 2,        /* sub = component k */
     CUSMC_STREAM_MULTINOMIAL = 3,
-    CUSMC_STREAM_CHAIN_Z = 4,    /* index = chain, step = MH step, sub = component pair */
+    CUSMC_STREAM_CHAIN_Z = 4,    /* index = chain, step = MH step, sub = component quad */
     CUSMC_STREAM_CHAIN_U = 5,
     CUSMC_STREAM_INIT = 6
 };
@@ -88,7 +88,9 @@ CUSMC_HD uint64_t cusmc_uint_below(uint32_t hi, uint32_t lo, uint64_t n)
 #endif
 }
 
-/* Two independent standard normals from one Philox block (Box-Muller). */
+/* Two independent standard normals from one Philox block, double-precision Box-Muller (53-bit
+ * uniforms, fp64 log / sincos).  Kept for the chi-square sampler and for callers that want
+ * full-resolution draws; the step kernels use cusmc_normal4 below. */
 CUSMC_HD void cusmc_normal_pair(cusmc_u32x4 r, double *z0, double *z1)
 {
     const double u1 = cusmc_u01_open0(r.v[0], r.v[1]);
@@ -98,6 +100,34 @@ CUSMC_HD void cusmc_normal_pair(cusmc_u32x4 r, double *z0, double *z1)
     cusmc_det_sincospi(u2 + u2, &s, &c);
     *z0 = rad * c;
     *z1 = rad * s;
+}
+
+
+/* Single-precision Box-Muller on two 32-bit words: the kernels' default normal generator.
+ * u1 = (a + 1/2) 2^-32 in (0, 1] (the tail keeps its full 2^-32 resolution: small a are exact
+ * floats), angle = (b >> 8) 2^-23 half-turns.  Deterministic: FFMA, IEEE sqrt, bit operations.
+ * The draws carry 24 significant bits and reach 6.7 sigma; every operation ON the state stays fp64. */
+CUSMC_HD void cusmc_box_muller_f32(uint32_t a, uint32_t b, float *z0, float *z1)
+{
+    float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.16415321826934814e-10f);
+    if (u1 > 1.0f) u1 = 1.0f;
+    const float rad = sqrtf(-2.0f * cusmc_det_logf(u1));
+    float s, c;
+    cusmc_det_sincospif((float)(b >> 8) * 1.1920928955078125e-7f, &s, &c);
+    *z0 = rad * c;
+    *z1 = rad * s;
+}
+
+/* Four standard normals (as doubles) from one Philox block. */
+CUSMC_HD void cusmc_normal4(cusmc_u32x4 r, double z[4])
+{
+    float a0, a1, b0, b1;
+    cusmc_box_muller_f32(r.v[0], r.v[1], &a0, &a1);
+    cusmc_box_muller_f32(r.v[2], r.v[3], &b0, &b1);
+    z[0] = (double)a0;
+    z[1] = (double)a1;
+    z[2] = (double)b0;
+    z[3] = (double)b1;
 }
 
 #endif /* CUSMC_PHILOX_H */

@@ -908,15 +908,77 @@ void orc_rng_metropolis(uint64_t seed, uint64_t step, uint64_t index, uint32_t n
     *j = (uint32_t)(((unsigned __int128)bits * N) >> 64);
 }
 
+/* Single-precision deterministic log / sincospi / Box-Muller: mirror of the kernels' default
+ * normal generator (include/cusmc_detmath.h, cusmc_philox.h). */
+static float bits_to_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
+static uint32_t float_to_bits(float f) { uint32_t b; memcpy(&b, &f, 4); return b; }
+
+float orc_det_logf(float x)
+{
+    uint32_t b = float_to_bits(x);
+    int e = (int)(b >> 23) - 127;
+    float m = bits_to_float((b & 0x007FFFFFu) | 0x3F800000u);
+    if (m > 1.41421354f) { m = m * 0.5f; e += 1; }
+    float f = m - 1.0f;
+    static const float P[8] = { 0.09004202485084534f, -0.14257794618606567f, 0.14806459844112396f,
+        -0.16575047373771667f, 0.19973105192184448f, -0.25001609325408936f, 0.33333659172058105f,
+        -0.4999999403953552f };
+    float p = P[0];
+    for (int i = 1; i < 8; ++i) p = fmaf(p, f, P[i]);
+    float r = fmaf(p * f, f, f);
+    return fmaf((float)e, 0.693147182464599609375f, r);
+}
+
+void orc_det_sincospif(float t, float *s_out, float *c_out)
+{
+    float nf = rintf(t + t);
+    float f = fmaf(nf, -0.5f, t);
+    float x = f * 3.14159274101257324f;
+    float x2 = x * x;
+    float ps = 2.75573192e-6f;
+    ps = fmaf(ps, x2, -1.98412698e-4f);
+    ps = fmaf(ps, x2, 8.33333377e-3f);
+    ps = fmaf(ps, x2, -1.66666672e-1f);
+    float sn = fmaf(x * x2, ps, x);
+    float pc = 2.48015876e-5f;
+    pc = fmaf(pc, x2, -1.38888892e-3f);
+    pc = fmaf(pc, x2, 4.16666679e-2f);
+    pc = fmaf(pc, x2, -0.5f);
+    float cs = fmaf(x2, pc, 1.0f);
+    int n = ((int)nf) & 3;
+    *s_out = n == 0 ? sn : n == 1 ? cs : n == 2 ? -sn : -cs;
+    *c_out = n == 0 ? cs : n == 1 ? -sn : n == 2 ? -cs : sn;
+}
+
+static void box_muller_f32(uint32_t a, uint32_t b, float *z0, float *z1)
+{
+    float u1 = fmaf((float)a, 2.3283064365386963e-10f, 1.16415321826934814e-10f);
+    if (u1 > 1.0f) u1 = 1.0f;
+    float rad = sqrtf(-2.0f * orc_det_logf(u1));
+    float s, c;
+    orc_det_sincospif((float)(b >> 8) * 1.1920928955078125e-7f, &s, &c);
+    *z0 = rad * c;
+    *z1 = rad * s;
+}
+
+void orc_rng_normal4(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub, double z[4])
+{
+    uint32_t r[4];
+    float a0, a1, b0, b1;
+    rng_block(seed, stream, step, index, sub, r);
+    box_muller_f32(r[0], r[1], &a0, &a1);
+    box_muller_f32(r[2], r[3], &b0, &b1);
+    z[0] = a0; z[1] = a1; z[2] = b0; z[3] = b1;
+}
+
 void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, int64_t N, int d, double *xi)
 {
 #pragma omp parallel for schedule(static)
     for (int64_t i = 0; i < N; ++i)
-        for (int jp = 0; 2 * jp < d; ++jp) {
-            double z[2];
-            orc_rng_normal_pair(seed, stream, step, (uint64_t)(i0 + i), (uint32_t)jp, z);
-            xi[(size_t)i * d + 2 * jp] = z[0];
-            if (2 * jp + 1 < d) xi[(size_t)i * d + 2 * jp + 1] = z[1];
+        for (int jq = 0; 4 * jq < d; ++jq) {
+            double z[4];
+            orc_rng_normal4(seed, stream, step, (uint64_t)(i0 + i), (uint32_t)jq, z);
+            for (int e = 0; e < 4 && 4 * jq + e < d; ++e) xi[(size_t)i * d + 4 * jq + e] = z[e];
         }
 }
 

@@ -187,6 +187,10 @@ void orc_step_det(int dist, int want_log, double *x_new, double *lw, const doubl
 /* Counter-based draws, mirror of include/cusmc_philox.h. */
 void orc_det_sincospi(double t, double *s, double *c);
 void orc_rng_normal_pair(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub, double z[2]);
+/* The kernels' default generator: four single-precision Box-Muller normals per Philox block. */
+float orc_det_logf(float x);
+void orc_det_sincospif(float t, float *s, float *c);
+void orc_rng_normal4(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub, double z[4]);
 double orc_rng_u01(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub);
 void orc_rng_metropolis(uint64_t seed, uint64_t step, uint64_t index, uint32_t n, uint64_t N,
                         double *u, uint32_t *j);

@@ -451,7 +451,9 @@ def test_filter_posterior_moments_vs_kalman(ctx, resampler):
     if resampler == "metropolis":
         assert np.max(np.abs(s["mean"][5:] - km[5:])) < 6 * sd / math.sqrt(N / 4) + 0.02
     else:
-        tol = 6 * sd / np.sqrt(s["ess"][1:, None])
+        # multinomial resampling adds its own O(1/N) variance every step on top of the weight
+        # degeneracy the ESS measures: twice the allowance
+        tol = (12 if resampler == "multinomial" else 6) * sd / np.sqrt(s["ess"][1:, None])
         assert np.all(np.abs(s["mean"][1:] - km[1:]) < tol)
         assert np.all(s["ess"][5:] > N / 10) and np.all(s["ess"] <= N * (1 + 1e-9))
 
