@@ -288,8 +288,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    prep = ctx.prepare_density("mvn", mu, sigma, log=True)
+
     def step(i):
-        ctx.logpdf_dev("mvn", pool[i % POOL_BATCHES], mu, sigma, out, log=True)
+        ctx.logpdf_prepared_dev(prep, pool[i % POOL_BATCHES], out)
 
     for i in range(args.warmup):
         step(i)
@@ -355,7 +357,7 @@ def main():
                    "parallelism": "points sharded across ranks, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
-                     "kernel": "density_soa_kernel<16,true,2>", "algorithmic_bytes_per_launch": BYTES_PER_EVAL * N_POINTS,
+                     "kernel": "density_soa_kernel<16,true,1,true>", "algorithmic_bytes_per_launch": BYTES_PER_EVAL * N_POINTS,
                      "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
                 "d2h_bytes_per_step": N_POINTS * 8, "steps": e2e_steps,

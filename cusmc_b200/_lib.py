@@ -69,9 +69,10 @@ PROTOTYPES = {
     "cusmc_pf_step_children_dev": (ci, [vp, ci, ci, vp, vp, i64, i64, i64, vp, i64, vp, i64, i64, vp, i64, i64,
                                         ci, ci, vp, vp, vp, vp, vp, vp, flt, dbl, u64, u64, ci, vp]),
     "cusmc_weights_max_dev": (ci, [vp, vp, i64, vp]),
-    "cusmc_weights_sum_dev": (ci, [vp, vp, ci, vp, i64, i64, vp]),
-    "cusmc_weights_scan_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp]),
-    "cusmc_resample_systematic_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp, i64, i64, i64, dbl, vp]),
+    "cusmc_tile_prefix_words": (i64, [i64]),
+    "cusmc_weights_sum_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp]),
+    "cusmc_weights_scan_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp, vp]),
+    "cusmc_resample_systematic_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp, vp, i64, i64, i64, dbl, vp]),
     "cusmc_resample_multinomial_dev": (ci, [vp, vp, i64, vp, vp, u64, u64, i64, i64, i64, vp]),
     "cusmc_resample_systematic": (ci, [vp, vp, i64, dbl, vp]),
     "cusmc_resample_multinomial": (ci, [vp, vp, i64, vp, vp]),

@@ -175,6 +175,26 @@ class Context:
                                               d_, _hp(mu_), _hp(sg), float(nu), _dp(out)))
         return out
 
+    def prepare_density(self, dist, mu, sigma, nu=0.0, log=True):
+        """The distribution object of the reference (built once by the Distributions factory,
+        src/mcmc.cpp:53-58, then asked for pdf() many times): converts mu / sigma once; use with
+        ``logpdf_prepared_dev`` when batches are small enough for per-call conversions to show."""
+        return PreparedDensity(dist, mu, sigma, nu, log)
+
+    def logpdf_prepared_dev(self, prep, x, out, layout=SOA, N=None, ld=None):
+        """x: torch CUDA tensor, (d, ld) for SOA or (N, d) for AOS; out: (N,)."""
+        if layout == SOA:
+            ld_ = x.shape[1] if ld is None else ld
+            N_ = ld_ if N is None else N
+        else:
+            N_ = x.shape[0] if N is None else N
+            ld_ = N_
+        rc = self.lib.cusmc_logpdf_dev(self.h, prep.kind, prep.log, x.data_ptr(), layout, N_, ld_, prep.d,
+                                       prep.mu_p, prep.sigma_p, prep.nu, out.data_ptr())
+        if rc != _lib.OK:
+            self._check(rc)
+        return out
+
     def logpdf_perpoint_dev(self, dist, x, mu, L_packed, out, nu=0.0, log=True):
         N, d = x.shape
         self._check(self.lib.cusmc_logpdf_perpoint_dev(self.h, _kind(dist), int(log), _dp(x), _dp(mu),
@@ -279,23 +299,29 @@ class Context:
         self._check(self.lib.cusmc_weights_max_dev(self.h, _dp(w), w.numel() if N is None else N,
                                                    _dp(max_out)))
 
-    def weights_sum_dev(self, w, is_log, max_dev, N_global, stats, N=None):
+    def tile_prefix_words(self, N):
+        return int(self.lib.cusmc_tile_prefix_words(int(N)))
+
+    def weights_sum_dev(self, w, is_log, max_dev, N_global, stats, N=None, tile_prefix=None):
+        """stats: 4 uint64 words (torch int64).  tile_prefix: int64 tensor of tile_prefix_words(N)
+        words with word 0 zero, or None (context scratch)."""
         self._check(self.lib.cusmc_weights_sum_dev(self.h, _dp(w), int(is_log), _dp(max_dev),
                                                    w.numel() if N is None else N, int(N_global),
-                                                   _dp(stats)))
+                                                   _dp(stats), _dp(tile_prefix)))
 
-    def weights_scan_dev(self, w, is_log, max_dev, N_global, cdf, cdf_offset=None, N=None):
+    def weights_scan_dev(self, w, is_log, max_dev, N_global, cdf, cdf_offset=None, N=None,
+                         tile_prefix=None):
         self._check(self.lib.cusmc_weights_scan_dev(self.h, _dp(w), int(is_log), _dp(max_dev),
                                                     w.numel() if N is None else N, int(N_global),
-                                                    _dp(cdf_offset), _dp(cdf)))
+                                                    _dp(cdf_offset), _dp(tile_prefix), _dp(cdf)))
 
     def resample_systematic_dev(self, w, is_log, max_dev, N_global, total, a, u0, cdf_offset=None,
-                                j0=0, out_lo=0, out_n=None, N=None):
+                                j0=0, out_lo=0, out_n=None, N=None, tile_prefix=None):
         N = w.numel() if N is None else N
         out_n = a.numel() if out_n is None else out_n
         self._check(self.lib.cusmc_resample_systematic_dev(
             self.h, _dp(w), int(is_log), _dp(max_dev), N, int(N_global), _dp(total), _dp(cdf_offset),
-            int(j0), int(out_lo), int(out_n), float(u0), _dp(a)))
+            _dp(tile_prefix), int(j0), int(out_lo), int(out_n), float(u0), _dp(a)))
 
     def resample_multinomial_dev(self, cdf, total, a, u=None, seed=0, step=0, i0=0, j0=0, N=None,
                                  n_out=None):
@@ -337,6 +363,22 @@ class Context:
     # ---- the filter --------------------------------------------------------------------------
     def filter(self, **kw):
         return ParticleFilter(self, **kw)
+
+
+class PreparedDensity:
+    """(kind, mu, sigma, nu) converted to the C ABI's layout once (see Context.prepare_density)."""
+
+    def __init__(self, dist, mu, sigma, nu=0.0, log=True):
+        self.kind = _kind(dist)
+        self.log = int(log)
+        self.nu = float(nu)
+        self._sigma = _colmajor(sigma)
+        self.d = int(round(math.sqrt(self._sigma.size)))
+        self._mu = None if mu is None else _f64(mu)
+        if self._mu is not None and self._mu.size != self.d:
+            raise ValueError("mu has %d entries, sigma is %d x %d" % (self._mu.size, self.d, self.d))
+        self.mu_p = _hp(self._mu)
+        self.sigma_p = _hp(self._sigma)
 
 
 class ParticleFilter:

@@ -14,6 +14,8 @@
 
 #define CUSMC_NUM_SCRATCH 8
 
+struct cusmc_density_cache;   // density.cu: last factored (kind, mu, Sigma, nu)
+
 struct cusmc_ctx {
     int device = 0;
     int sm_count = 148;
@@ -29,7 +31,13 @@ struct cusmc_ctx {
     // pinned staging for small device->host reads (status words, stats)
     void *pinned = nullptr;
     size_t pinned_cap = 0;
+    // set-up algebra of the last density call (Cholesky, L^-1, log norm): a caller that evaluates
+    // batch after batch under one distribution -- the reference builds its distribution object once
+    // and calls pdf() many times, src/mcmc.cpp:53-58 -- pays for it once, not per 25 us kernel
+    cusmc_density_cache *dcache = nullptr;
 };
+
+void cusmc_density_cache_free(cusmc_ctx *ctx);
 
 inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
 {

@@ -41,6 +41,7 @@ extern "C" int cusmc_ctx_destroy(cusmc_ctx *ctx)
     for (int s = 0; s < CUSMC_NUM_SCRATCH; ++s)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    cusmc_density_cache_free(ctx);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);

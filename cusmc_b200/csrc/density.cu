@@ -8,6 +8,7 @@
 #include "density.cuh"
 #include "hostmath.h"
 
+#include <new>
 #include <vector>
 
 namespace {
@@ -15,13 +16,16 @@ namespace {
 constexpr int kThreads = 256;
 
 // ---- SoA: x[j*ld + i].  VEC = 2 -> 128-bit loads, a thread owns points 2u and 2u+1. ----
-// One unit per thread and no grid-stride loop ON PURPOSE: with a loop, LICM hoists the whole
-// operator out of it into registers (170+ regs, spills).  Straight-line code lets ptxas feed
-// each DFMA its coefficient from the constant bank through a uniform register (LDCU -> UR).
-// The kernel is HBM-bound with 16 independent 128-bit loads in flight per thread, so the
-// hardware block scheduler balances the tail; wave quantisation does not show.
-template <int D, bool TRI, int VEC>
-__global__ void __launch_bounds__(kThreads, (D >= 16 ? 3 : 4))
+// One unit per thread and no grid-stride loop ON PURPOSE: with a loop (grid-stride or a
+// persistent TMA/mbarrier ring -- both tried, profiles/micro/density_variants.cu) LICM hoists the
+// whole operator out of it into registers (96-170 regs, spills).  Straight-line code lets ptxas
+// feed each DFMA its coefficient from the constant bank through a uniform register
+// (LDCU -> UR).  Shapes were picked on the B200 with that microbenchmark: at d = 16 one point
+// per thread at 56 registers (4 blocks/SM) reaches the read-only streaming ceiling of a
+// 142 MB pass (0.91 of the measured copy bandwidth); two points per thread pay off for d <= 8
+// where a point is only a few loads.  EXACT (d == D) drops every j < d predicate.
+template <int D, bool TRI, int VEC, bool EXACT>
+__global__ void __launch_bounds__(kThreads, (D >= 32 ? 2 : 4))
 density_soa_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue ep,
                    const double *__restrict__ x, int64_t n_units, int64_t ld, int d,
                    double *__restrict__ out)
@@ -33,7 +37,7 @@ density_soa_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue e
         double ra[D], rb[D];
 #pragma unroll
         for (int j = 0; j < D; ++j) {
-            if (j < d) {
+            if (EXACT || j < d) {
                 const double2 v = ld_stream2(x + (int64_t)j * ld + i);
                 ra[j] = v.x - op.shift[j];
                 rb[j] = v.y - op.shift[j];
@@ -50,7 +54,7 @@ density_soa_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue e
         double r[D];
 #pragma unroll
         for (int j = 0; j < D; ++j)
-            r[j] = (j < d) ? ld_stream(x + (int64_t)j * ld + u) - op.shift[j] : 0.0;
+            r[j] = (EXACT || j < d) ? ld_stream(x + (int64_t)j * ld + u) - op.shift[j] : 0.0;
         st_stream(out + u, density_epilogue(ep, affine_quadform<D, TRI>(op, r)));
     }
 }
@@ -99,19 +103,24 @@ int launch_density(cusmc_ctx *ctx, const AffineOp<D, TRI> &op, const Epilogue &e
 {
     if (N == 0) return CUSMC_OK;
     if (layout == CUSMC_SOA) {
-        const bool vec2 = D <= 16 && (N % 2 == 0) && (ld % 2 == 0) &&
+        const bool exact = d == D;
+        const bool vec2 = D <= 8 && (N % 2 == 0) && (ld % 2 == 0) &&
                           ((uintptr_t)x % 16 == 0) && ((uintptr_t)out % 16 == 0);
-        if constexpr (D <= 16) if (vec2) {
+        if constexpr (D <= 8) if (vec2) {
             const int64_t units = N / 2;
-            const int64_t grid = (units + kThreads - 1) / kThreads;
-            density_soa_kernel<D, TRI, 2><<<(unsigned)grid, kThreads, 0, ctx->stream>>>(
-                op, ep, x, units, ld, d, out);
+            const unsigned grid = (unsigned)((units + kThreads - 1) / kThreads);
+            if (exact)
+                density_soa_kernel<D, TRI, 2, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
+            else
+                density_soa_kernel<D, TRI, 2, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
             CUSMC_LAUNCHED(ctx);
             return CUSMC_OK;
         }
-        const int64_t grid = (N + kThreads - 1) / kThreads;
-        density_soa_kernel<D, TRI, 1><<<(unsigned)grid, kThreads, 0, ctx->stream>>>(
-            op, ep, x, N, ld, d, out);
+        const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
+        if (exact)
+            density_soa_kernel<D, TRI, 1, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, N, ld, d, out);
+        else
+            density_soa_kernel<D, TRI, 1, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, N, ld, d, out);
     } else {
         const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
         const int64_t grid = (N + kThreads - 1) / kThreads;
@@ -210,6 +219,44 @@ int cusmc_build_whitening(cusmc_ctx *ctx, int kind, int want_log, int d, const d
     return CUSMC_OK;
 }
 
+struct cusmc_density_cache {
+    int kind = -1, want_log = -1, d = 0;
+    float nu = 0.f;
+    std::vector<double> sigma, W;
+    Epilogue ep{};
+};
+
+void cusmc_density_cache_free(cusmc_ctx *ctx)
+{
+    delete ctx->dcache;
+    ctx->dcache = nullptr;
+}
+
+// cusmc_build_whitening through the context's one-entry cache (keyed on every input bit).
+static int cached_whitening(cusmc_ctx *ctx, int kind, int want_log, int d, const double *sigma, float nu,
+                            const std::vector<double> **W, Epilogue *ep)
+{
+    if (!ctx->dcache) ctx->dcache = new (std::nothrow) cusmc_density_cache();
+    cusmc_density_cache *c = ctx->dcache;
+    if (!c) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "out of host memory");
+    const size_t n = (size_t)d * d;
+    const bool hit = c->kind == kind && c->want_log == want_log && c->d == d &&
+                     std::memcmp(&c->nu, &nu, sizeof nu) == 0 && c->sigma.size() == n &&
+                     std::memcmp(c->sigma.data(), sigma, n * sizeof(double)) == 0;
+    if (!hit) {
+        c->kind = -1;   // stays invalid if the factorisation fails
+        CUSMC_CHECK(cusmc_build_whitening(ctx, kind, want_log, d, sigma, nu, c->W, c->ep));
+        c->sigma.assign(sigma, sigma + n);
+        c->kind = kind;
+        c->want_log = want_log;
+        c->d = d;
+        c->nu = nu;
+    }
+    *W = &c->W;
+    *ep = c->ep;
+    return CUSMC_OK;
+}
+
 extern "C" int cusmc_logpdf_dev(cusmc_ctx *ctx, int kind, int want_log, const double *x_dev,
                                 int layout, int64_t N, int64_t ld, int d, const double *mu,
                                 const double *sigma, float nu, double *out_dev)
@@ -222,10 +269,10 @@ extern "C" int cusmc_logpdf_dev(cusmc_ctx *ctx, int kind, int want_log, const do
     CUSMC_REQUIRE(ctx, layout == CUSMC_AOS || ld >= N, "ld < N");
     if (d > CUSMC_MAX_DIM)
         return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d = %d > %d", d, CUSMC_MAX_DIM);
-    std::vector<double> W;
+    const std::vector<double> *W = nullptr;
     Epilogue ep;
-    CUSMC_CHECK(cusmc_build_whitening(ctx, kind, want_log, d, sigma, nu, W, ep));
-    return cusmc_density_launch(ctx, true, d, d, W, mu, nullptr, ep, x_dev, layout, N, ld, out_dev);
+    CUSMC_CHECK(cached_whitening(ctx, kind, want_log, d, sigma, nu, &W, &ep));
+    return cusmc_density_launch(ctx, true, d, d, *W, mu, nullptr, ep, x_dev, layout, N, ld, out_dev);
 }
 
 extern "C" int cusmc_logpdf(cusmc_ctx *ctx, int kind, int want_log, const double *x_host,

@@ -14,6 +14,7 @@
 // operator ride in the kernel parameter bank.
 #include "density.cuh"
 #include "hostmath.h"
+#include "pf_step.cuh"
 #include "resample.cuh"
 
 #include "../../include/cusmc_detmath.h"
@@ -32,174 +33,6 @@ int cusmc_build_whitening(cusmc_ctx *ctx, int kind, int want_log, int d, const d
 namespace {
 
 constexpr int kThreads = 256;
-
-template <int D>
-struct StepOp {
-    double G[D * D];   // row-major transition
-    double Q[D * D];   // row-major noise factor (already multiplied by noise_scale)
-    double M[D * D];   // row-major whitened observation operator  L_V^-1 F
-    double c[D];       // L_V^-1 y_t
-    double mu[D];      // additive location (m0 at t = 0, otherwise 0)
-};
-
-struct StepArgs {
-    double *x_new;
-    const double *x_prev;
-    const uint32_t *anc;
-    const double *xi;
-    const double *chi;
-    double *lw;
-    double *lw_max;              // optional
-    unsigned long long *zero_ptr; // optional: words to clear for the next scan
-    int64_t zero_n;
-    int64_t n_out, ld_new, ld_prev, ld_noise;
-    int64_t i0;                  // global index of child 0 (keys the counter-based draws)
-    int64_t parent_base;         // global index of x_prev column 0
-    uint64_t seed, step;
-    double const_weight;         // used when skip_weight
-    float nu;
-    int d, dy, kind, has_prev, skip_weight, rng_stream;
-    // sharded runs (sharded != 0): child i0 + i goes to slot (child - own_lo) of x_new / lw when it
-    // falls in [own_lo, own_lo + own_n), otherwise to the side buffer [(d + 1)][ld_side] (rows
-    // 0..d-1 state, row d weight) in child order, to be shipped to the owning rank.
-    int64_t own_lo, own_n, n_own_children, ld_side;
-    double *side;
-    int sharded;
-};
-
-__device__ __forceinline__ void atomic_max_double(double *addr, double v)
-{
-    if (v != v) return;
-    if (v >= 0.0)
-        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
-    else
-        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
-}
-
-// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2): Marsaglia-Tsang with reproducible
-// log/exp (the reference's curand_gamma / curand_chi_square, src/mvt_dist.cu.cpp:20-61).
-__device__ __noinline__ double chi_factor(uint64_t seed, uint64_t step, uint64_t index, int k, float nu)
-{
-    const double a0 = 0.5 * (double)nu;
-    const double a = a0 < 1.0 ? a0 + 1.0 : a0;
-    const double dd = a - 1.0 / 3.0;
-    const double cc = 1.0 / sqrt(9.0 * dd);
-    double g = dd;
-    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
-        const uint32_t sub = ((uint32_t)k << 8) | attempt;
-        double z0, z1;
-        cusmc_normal_pair(cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub), &z0, &z1);
-        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub | 0x800000u);
-        const double t = fma(cc, z0, 1.0);
-        const double v = t * t * t;
-        if (v > 0.0) {
-            const double lu = cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
-            if (lu < fma(0.5 * z0, z0, dd) - dd * v + dd * cusmc_det_log(v)) {
-                g = dd * v;
-                if (a0 < 1.0) {
-                    const double lb = cusmc_det_log(cusmc_u01_open0(r.v[2], r.v[3]));
-                    g = g * cusmc_det_exp(lb / a0);
-                }
-                break;
-            }
-        }
-    }
-    return sqrt((double)nu / (2.0 * g));
-}
-
-// MVT is a template flag so the MVN kernel carries neither the chi branch nor the call to the
-// (rejection-loop) chi-square sampler, whose calling convention alone costs ~30 registers.
-template <int D, bool PHILOX, bool MVT>
-__global__ void __launch_bounds__(kThreads, (D >= 32 ? 1 : (D >= 16 ? 2 : (D >= 8 ? 3 : 4))))
-pf_step_kernel(const __grid_constant__ StepOp<D> op, const Epilogue ep, const StepArgs a)
-{
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (a.zero_ptr && i < a.zero_n) a.zero_ptr[i] = 0ull;
-    const bool active = i < a.n_out;
-    double lw = -INFINITY;
-    if (active) {
-        double xp[D], z[D], xn[D];
-        int64_t parent = i;
-        if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
-        double *dst_x = a.x_new + i, *dst_lw = a.lw + i;
-        int64_t dst_ld = a.ld_new;
-        if (a.sharded) {
-            const int64_t child = a.i0 + i;
-            if (child >= a.own_lo && child < a.own_lo + a.own_n) {
-                dst_x = a.x_new + (child - a.own_lo);
-                dst_lw = a.lw + (child - a.own_lo);
-            } else {
-                const int64_t sidx = child < a.own_lo ? i : i - a.n_own_children;
-                dst_x = a.side + sidx;
-                dst_lw = a.side + (int64_t)a.d * a.ld_side + sidx;
-                dst_ld = a.ld_side;
-            }
-        }
-#pragma unroll
-        for (int j = 0; j < D; ++j)
-            xp[j] = (a.has_prev && j < a.d) ? __ldg(a.x_prev + (int64_t)j * a.ld_prev + parent) : 0.0;
-        if (PHILOX) {
-            // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
-#pragma unroll
-            for (int jq = 0; jq < (D + 3) / 4; ++jq) {
-                double zq[4] = {0.0, 0.0, 0.0, 0.0};
-                if (4 * jq < a.d)
-                    cusmc_normal4(cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), (uint32_t)jq), zq);
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-                    if (4 * jq + e < D) z[4 * jq + e] = (4 * jq + e < a.d) ? zq[e] : 0.0;
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < D; ++j)
-                z[j] = (j < a.d) ? ld_stream(a.xi + (int64_t)j * a.ld_noise + i) : 0.0;
-        }
-#pragma unroll
-        for (int k = 0; k < D; ++k) {
-            double g = op.mu[k];
-#pragma unroll
-            for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
-            double s = 0.0;
-#pragma unroll
-            for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
-            if (MVT && k < a.d) {
-                const double chi = a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i)
-                                         : chi_factor(a.seed, a.step, (uint64_t)(a.i0 + i), k, a.nu);
-                s = chi * s;
-            }
-            xn[k] = s + g;
-            if (k < a.d) st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
-        }
-        if (a.skip_weight) {
-            lw = a.const_weight;
-        } else {
-            double q = 0.0;
-#pragma unroll
-            for (int k = 0; k < D; ++k) {
-                double zk = op.c[k];
-#pragma unroll
-                for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
-                q = fma(zk, zk, q);
-            }
-            lw = density_epilogue(ep, q);
-        }
-        st_stream(dst_lw, lw);
-    }
-    if (a.lw_max) {
-        double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-        __shared__ double sm[kThreads / 32];
-        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-            if (threadIdx.x == 0) atomic_max_double(a.lw_max, m);
-        }
-    }
-}
 
 // ---- layout transposes through shared memory (coalesced on both sides) ----------------------
 __global__ void __launch_bounds__(kThreads)
@@ -269,64 +102,7 @@ moments_kernel(const double *__restrict__ x, const double *__restrict__ w, const
     }
 }
 
-template <int D>
-void fill_step_op(StepOp<D> &op, int d, int dy, const double *G, const double *Q, double qscale,
-                  const std::vector<double> *M_rowmajor, const double *c, const double *mu)
-{
-    std::memset(&op, 0, sizeof(op));
-    for (int k = 0; k < d; ++k)
-        for (int j = 0; j < d; ++j) {
-            if (G) op.G[k * D + j] = G[(size_t)j * d + k];
-            if (Q) op.Q[k * D + j] = Q[(size_t)j * d + k] * qscale;
-        }
-    if (M_rowmajor)
-        for (int k = 0; k < dy; ++k)
-            for (int j = 0; j < d; ++j) op.M[k * D + j] = (*M_rowmajor)[(size_t)k * d + j];
-    for (int k = 0; k < dy; ++k) op.c[k] = c ? c[k] : 0.0;
-    for (int k = 0; k < d; ++k) op.mu[k] = mu ? mu[k] : 0.0;
-}
-
-template <int D>
-int launch_step_D(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
-                  const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
-                  const StepArgs &a, bool philox)
-{
-    StepOp<D> op;
-    fill_step_op<D>(op, d, dy, G, Q, qscale, M, c, mu);
-    int64_t n = a.n_out > a.zero_n ? a.n_out : a.zero_n;
-    const unsigned grid = (unsigned)((n + kThreads - 1) / kThreads);
-    const bool mvt = a.kind == CUSMC_MVT;
-    if (philox && mvt)
-        pf_step_kernel<D, true, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
-    else if (philox)
-        pf_step_kernel<D, true, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
-    else if (mvt)
-        pf_step_kernel<D, false, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
-    else
-        pf_step_kernel<D, false, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
-    CUSMC_LAUNCHED(ctx);
-    return CUSMC_OK;
-}
-
 }  // namespace
-
-// G, Q column-major d x d host; M row-major dy x d; c dy.  Shared with sharded callers.
-int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
-                      const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
-                      const StepArgs &a, bool philox)
-{
-    const int dm = d > dy ? d : dy;
-    if (dm > CUSMC_MAX_DIM || d < 1)
-        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "dimension %d not in 1..%d", dm, CUSMC_MAX_DIM);
-    if (a.n_out == 0 && a.zero_n == 0) return CUSMC_OK;
-    switch (cusmc_pad_dim(dm)) {
-        case 2: return launch_step_D<2>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
-        case 4: return launch_step_D<4>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
-        case 8: return launch_step_D<8>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
-        case 16: return launch_step_D<16>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
-        default: return launch_step_D<32>(ctx, d, dy, G, Q, qscale, M, c, mu, ep, a, philox);
-    }
-}
 
 // Observation model set-up: M = L_V^-1 F (row-major dy x d), Winv = L_V^-1 (row-major), epilogue.
 static int build_observation(cusmc_ctx *ctx, int kind, int want_log, int d, int dy, const double *F,
@@ -848,13 +624,13 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
     CUSMC_LAUNCHED(ctx);
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, cusmc_scan_state_bytes(N), st));
-    const int64_t zero_words = (int64_t)(cusmc_scan_state_bytes(N) / 8);
     const int mom_grid = (int)std::min<int64_t>((N + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
 
     auto after_step = [&](int t) -> int {
         // sums for normalisation / ESS (log modes), moments, history
         if (f->is_log)
-            CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, N, f->shift, &f->slots[t].sum_q));
+            CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, N, f->shift, &f->slots[t].sum_q,
+                                                 f->scan_state));
         if (cfg.summary) {
             moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, N, N, d,
                                                           f->moments + (size_t)t * (2 + d));
@@ -909,11 +685,11 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
             const double u0 = draws->u0_host ? draws->u0_host[off]
                                              : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
             CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
-                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, false, nullptr, f->anc,
+                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, nullptr, f->anc,
                                           0, 0, N, u0));
         } else {
             CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
-                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, false, f->cdf, nullptr,
+                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, f->cdf, nullptr,
                                           0, 0, 0, 0.0));
             const double *um = draws->um_dev ? draws->um_dev + off * N : nullptr;
             CUSMC_CHECK(cusmc_launch_multinomial(ctx, f->cdf, N, &f->slots[t - 1].sum_q, um, cfg.seed, (uint64_t)t, 0, N, 0, f->anc));
@@ -929,8 +705,6 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
         a.chi = draws->chi_dev ? draws->chi_dev + off * N * d : nullptr;
         a.lw = f->lw;
         a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
-        a.zero_ptr = (unsigned long long *)f->scan_state;   // clear the scan state for the next step
-        a.zero_n = cfg.resampler == CUSMC_RESAMPLE_METROPOLIS ? 0 : zero_words;
         a.n_out = N;
         a.ld_new = a.ld_prev = a.ld_noise = N;
         a.seed = cfg.seed;

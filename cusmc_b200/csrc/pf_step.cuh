@@ -1,0 +1,37 @@
+// pf_step.cuh -- arguments of the fused propagate + reweight kernel (pf_step.cu), shared with the
+// host loops in filter.cu.
+#pragma once
+
+#include "density.cuh"
+
+#include <vector>
+
+struct StepArgs {
+    double *x_new;
+    const double *x_prev;
+    const uint32_t *anc;
+    const double *xi;
+    const double *chi;
+    double *lw;
+    double *lw_max;              // optional
+    int64_t n_out, ld_new, ld_prev, ld_noise;
+    int64_t i0;                  // global index of child 0 (keys the counter-based draws)
+    int64_t parent_base;         // global index of x_prev column 0
+    uint64_t seed, step;
+    double const_weight;         // used when skip_weight
+    float nu;
+    int d, dy, kind, has_prev, skip_weight, rng_stream;
+    // sharded runs (sharded != 0): child i0 + i goes to slot (child - own_lo) of x_new / lw when it
+    // falls in [own_lo, own_lo + own_n), otherwise to the side buffer [(d + 1)][ld_side] (rows
+    // 0..d-1 state, row d weight) in child order, to be shipped to the owning rank.
+    int64_t own_lo, own_n, n_own_children, ld_side;
+    double *side;
+    int sharded;
+};
+
+// G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no
+// weights); c dy; mu d (NULL = 0).  Picks the EXACT (d == dy == padded D) and DIAG (G, Q, M all
+// diagonal) specialisations itself.
+int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
+                      const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
+                      const StepArgs &a, bool philox);

@@ -1,0 +1,269 @@
+// pf_step_impl.cuh -- the particle-filter step kernel (included by pf_step_mvn.cu / pf_step_mvt.cu,
+// one translation unit per noise family so the 60 instantiations compile in parallel).
+//
+// One fused kernel per step replaces the reference's eight (Gmu, sample, y_minus_Fmu,
+// Einv_alpha, pdf + RNG set-up kernels; src/mvn_dist.cu.cpp:33-172,455-668) and the host-side
+// ancestor gather / AoS flattening / H2D+D2H of the whole particle cloud every step
+// (src/mvn_dist.cu.cpp:194-205,231-251,300-302): a thread owns one child particle,
+//
+//     parent  = anc[i]
+//     x_new   = mu + G x_prev[:, parent] + noise_i          noise = Q xi | chi (.) (Q xi)
+//     lw[i]   = log pdf_V(y_t - F x_new)   (or the density, reference mode)
+//     max     = atomic max over lw (for the max-shifted normalisation)
+//
+// State is SoA and stays on the device for the whole run; G, Q and the whitened observation
+// operator ride in the kernel parameter bank.
+//
+// The kernel is ISSUE-bound, not HBM-bound (ncu r01: 975-1080 warp instructions per particle at
+// d = 8, issue slots 84 % busy): the counter-based normals cost ~50 instructions each, the three
+// dense d x d products 3 d^2 DFMA.  Two compile-time specialisations cut what can be cut:
+//   EXACT : d == dy == D, every `k < d` predicate folds away;
+//   DIAG  : G, Q and M = L_V^-1 F are all diagonal (random-walk / AR(1) models observed
+//           component-wise -- both filter configurations of BASELINE.json), the products shrink
+//           from 3 d^2 to 3 d DFMA.  Skipping the zero terms does not change a single bit:
+//           fma(0, x, acc) == acc for finite x.
+#pragma once
+
+#include "pf_step.cuh"
+
+#include "../../include/cusmc_detmath.h"
+#include "../../include/cusmc_philox.h"
+
+namespace pfstep {
+
+constexpr int kThreads = 256;
+
+template <int D, bool DIAG>
+struct StepOp {
+    static constexpr int NM = DIAG ? D : D * D;
+    double G[NM];      // row-major transition (DIAG: the diagonal)
+    double Q[NM];      // row-major noise factor (already multiplied by noise_scale)
+    double M[NM];      // row-major whitened observation operator  L_V^-1 F
+    double c[D];       // L_V^-1 y_t
+    double mu[D];      // additive location (m0 at t = 0, otherwise 0)
+};
+
+__device__ __forceinline__ void atomic_max_double(double *addr, double v)
+{
+    if (v != v) return;
+    if (v >= 0.0)
+        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+    else
+        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2): Marsaglia-Tsang with reproducible
+// log/exp (the reference's curand_gamma / curand_chi_square, src/mvt_dist.cu.cpp:20-61).
+static __device__ __noinline__ double chi_factor(uint64_t seed, uint64_t step, uint64_t index, int k, float nu)
+{
+    const double a0 = 0.5 * (double)nu;
+    const double a = a0 < 1.0 ? a0 + 1.0 : a0;
+    const double dd = a - 1.0 / 3.0;
+    const double cc = 1.0 / sqrt(9.0 * dd);
+    double g = dd;
+    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
+        const uint32_t sub = ((uint32_t)k << 8) | attempt;
+        double z0, z1;
+        cusmc_normal_pair(cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub), &z0, &z1);
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub | 0x800000u);
+        const double t = fma(cc, z0, 1.0);
+        const double v = t * t * t;
+        if (v > 0.0) {
+            const double lu = cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+            if (lu < fma(0.5 * z0, z0, dd) - dd * v + dd * cusmc_det_log(v)) {
+                g = dd * v;
+                if (a0 < 1.0) {
+                    const double lb = cusmc_det_log(cusmc_u01_open0(r.v[2], r.v[3]));
+                    g = g * cusmc_det_exp(lb / a0);
+                }
+                break;
+            }
+        }
+    }
+    return sqrt((double)nu / (2.0 * g));
+}
+
+constexpr int min_blocks(int D, bool diag) { return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? 3 : 4)); }
+
+// MVT is a template flag so the MVN kernel carries neither the chi branch nor the call to the
+// (rejection-loop) chi-square sampler, whose calling convention alone costs ~30 registers.
+template <int D, bool PHILOX, bool MVT, bool EXACT, bool DIAG>
+__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG))
+pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const StepArgs a)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    const bool active = i < a.n_out;
+    const int d = EXACT ? D : a.d;
+    double lw = -INFINITY;
+    if (active) {
+        double xp[D], z[D], xn[D];
+        int64_t parent = i;
+        if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
+        double *dst_x = a.x_new + i, *dst_lw = a.lw + i;
+        int64_t dst_ld = a.ld_new;
+        if (a.sharded) {
+            const int64_t child = a.i0 + i;
+            if (child >= a.own_lo && child < a.own_lo + a.own_n) {
+                dst_x = a.x_new + (child - a.own_lo);
+                dst_lw = a.lw + (child - a.own_lo);
+            } else {
+                const int64_t sidx = child < a.own_lo ? i : i - a.n_own_children;
+                dst_x = a.side + sidx;
+                dst_lw = a.side + (int64_t)a.d * a.ld_side + sidx;
+                dst_ld = a.ld_side;
+            }
+        }
+        if (a.has_prev) {
+            const double *src = a.x_prev + parent;
+#pragma unroll
+            for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) xp[j] = 0.0;
+        }
+        if (PHILOX) {
+            // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
+            const uint64_t idx = (uint64_t)(a.i0 + i);
+#pragma unroll
+            for (int jq = 0; jq < (D + 3) / 4; ++jq) {
+                double zq[4] = {0.0, 0.0, 0.0, 0.0};
+                if (EXACT || 4 * jq < d) cusmc_normal4(cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq), zq);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                    if (4 * jq + e < D) z[4 * jq + e] = (EXACT || 4 * jq + e < d) ? zq[e] : 0.0;
+            }
+        } else {
+            const double *src = a.xi + i;
+#pragma unroll
+            for (int j = 0; j < D; ++j) z[j] = (EXACT || j < d) ? ld_stream(src + (int64_t)j * a.ld_noise) : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            double g = op.mu[k], s = 0.0;
+            if constexpr (DIAG) {
+                g = fma(op.G[k], xp[k], g);
+                s = fma(op.Q[k], z[k], s);
+            } else {
+#pragma unroll
+                for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
+#pragma unroll
+                for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
+            }
+            if (MVT && (EXACT || k < d)) {
+                const double chi = a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i)
+                                         : chi_factor(a.seed, a.step, (uint64_t)(a.i0 + i), k, a.nu);
+                s = chi * s;
+            }
+            xn[k] = s + g;
+            if (EXACT || k < d) st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
+        }
+        if (a.skip_weight) {
+            lw = a.const_weight;
+        } else {
+            double q = 0.0;
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                double zk = op.c[k];
+                if constexpr (DIAG) {
+                    zk = fma(-op.M[k], xn[k], zk);
+                } else {
+#pragma unroll
+                    for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
+                }
+                q = fma(zk, zk, q);
+            }
+            lw = density_epilogue(ep, q);
+        }
+        st_stream(dst_lw, lw);
+    }
+    if (a.lw_max) {
+        double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        __shared__ double sm[kThreads / 32];
+        if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY;
+#pragma unroll
+            for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (threadIdx.x == 0) atomic_max_double(a.lw_max, m);
+        }
+    }
+}
+
+// Host-side view of the model matrices of one step (all optional, column-major like Eigen).
+struct StepModel {
+    int d, dy;
+    const double *G, *Q;
+    double qscale;
+    const std::vector<double> *M;   // row-major dy x d
+    const double *c, *mu;
+};
+
+template <int D, bool DIAG>
+void fill_step_op(StepOp<D, DIAG> &op, const StepModel &m)
+{
+    std::memset(&op, 0, sizeof(op));
+    const int d = m.d, dy = m.dy;
+    if constexpr (DIAG) {
+        for (int k = 0; k < d; ++k) {
+            if (m.G) op.G[k] = m.G[(size_t)k * d + k];
+            if (m.Q) op.Q[k] = m.Q[(size_t)k * d + k] * m.qscale;
+            if (m.M) op.M[k] = (*m.M)[(size_t)k * d + k];
+        }
+    } else {
+        for (int k = 0; k < d; ++k)
+            for (int j = 0; j < d; ++j) {
+                if (m.G) op.G[k * D + j] = m.G[(size_t)j * d + k];
+                if (m.Q) op.Q[k * D + j] = m.Q[(size_t)j * d + k] * m.qscale;
+            }
+        if (m.M)
+            for (int k = 0; k < dy; ++k)
+                for (int j = 0; j < d; ++j) op.M[k * D + j] = (*m.M)[(size_t)k * d + j];
+    }
+    for (int k = 0; k < dy; ++k) op.c[k] = m.c ? m.c[k] : 0.0;
+    for (int k = 0; k < d; ++k) op.mu[k] = m.mu ? m.mu[k] : 0.0;
+}
+
+template <int D, bool MVT, bool EXACT, bool DIAG>
+int launch_one(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const StepArgs &a, bool philox)
+{
+    StepOp<D, DIAG> op;
+    fill_step_op<D, DIAG>(op, m);
+    const unsigned grid = (unsigned)((a.n_out + kThreads - 1) / kThreads);
+    if (philox)
+        pf_step_kernel<D, true, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    else
+        pf_step_kernel<D, false, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+template <bool MVT>
+int launch_family(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const StepArgs &a, bool philox,
+                  bool exact, bool diag)
+{
+    const int dm = m.d > m.dy ? m.d : m.dy;
+#define CUSMC_STEP_CASE(DD)                                                                          \
+    case DD:                                                                                         \
+        if (exact && diag) return launch_one<DD, MVT, true, true>(ctx, m, ep, a, philox);            \
+        if (exact) return launch_one<DD, MVT, true, false>(ctx, m, ep, a, philox);                   \
+        return launch_one<DD, MVT, false, false>(ctx, m, ep, a, philox);
+    switch (cusmc_pad_dim(dm)) {
+        CUSMC_STEP_CASE(2)
+        CUSMC_STEP_CASE(4)
+        CUSMC_STEP_CASE(8)
+        CUSMC_STEP_CASE(16)
+        CUSMC_STEP_CASE(32)
+    }
+#undef CUSMC_STEP_CASE
+    return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "unreachable");
+}
+
+int launch_mvn(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const StepArgs &a, bool philox,
+               bool exact, bool diag);
+int launch_mvt(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const StepArgs &a, bool philox,
+               bool exact, bool diag);
+
+}  // namespace pfstep

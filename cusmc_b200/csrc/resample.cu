@@ -102,51 +102,116 @@ __device__ __forceinline__ double unit_weight(double w, double wmax, int is_log)
     return is_log ? cusmc_unit_from_log(w, wmax) : cusmc_unit_from_linear(w, wmax);
 }
 
-// stats[0] += sum q, stats[1] += sum q2, stats[2] += #positive.  Integer atomics: the totals
-// do not depend on the order the blocks arrive in.
-__global__ void __launch_bounds__(kThreads)
-weights_sum_kernel(const double *__restrict__ w, int is_log, const double *__restrict__ wmax_p,
-                   int64_t N, int shift, unsigned long long *__restrict__ stats)
+// ------------------------------------------------------------------------------------------
+// Normalisation sums and the tile prefixes of the fixed-point weight image.
+//
+// A tile is kTile = 2048 consecutive weights; thread t of the block owns the 8 consecutive weights
+// 8t .. 8t+7 (four 128-bit loads).  Tile state, uint64 words:
+//     [0]      arrival counter -- zero when a launch starts, reset to zero by its last block
+//     [1 + b]  sum of tile b, turned IN PLACE into the exclusive prefix over tiles by the last
+//              block to finish (one block scanning N/2048 integers: ~1 us at N = 8 Mi).
+// Because the per-tile totals are known before the resampling pass starts, that pass needs no
+// decoupled look-back (no spinning, no tile ordering, no state to clear between steps): its tiles
+// are independent.  Integer sums: every order of arrival gives the same bits.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileItems = 8;
+constexpr int kTile = kThreads * kTileItems;    // 2048 weights per tile
+
+__device__ __forceinline__ void load_tile_items(const double *__restrict__ w, int64_t base, int64_t N,
+                                                double (&v)[kTileItems])
 {
+    if (base + kTileItems <= N && (((uintptr_t)(w + base)) & 15) == 0) {
+#pragma unroll
+        for (int r = 0; r < kTileItems / 2; ++r) {
+            const double2 t = __ldg(reinterpret_cast<const double2 *>(w + base) + r);
+            v[2 * r] = t.x;
+            v[2 * r + 1] = t.y;
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) v[r] = base + r < N ? __ldg(w + base + r) : -INFINITY;
+    }
+}
+
+// Block-wide sum of one uint64 per thread; every thread gets the total.
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long t = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) t += sm[k];
+    __syncthreads();
+    return t;
+}
+
+__global__ void __launch_bounds__(kThreads)
+weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict__ wmax_p, int64_t N,
+             int shift, unsigned long long *__restrict__ stats, unsigned long long *__restrict__ tile_state)
+{
+    __shared__ unsigned long long sm[kThreads / 32];
+    __shared__ int s_last;
     const double wmax = *wmax_p;
+    const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
+    double v[kTileItems];
+    load_tile_items(w, base, N, v);
     unsigned long long s1 = 0, s2 = 0, np = 0;
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < N; i += (int64_t)gridDim.x * kThreads) {
-        const double wn = unit_weight(__ldg(w + i), wmax, is_log);
+#pragma unroll
+    for (int r = 0; r < kTileItems; ++r) {
+        const double wn = unit_weight(v[r], wmax, is_log);   // -inf padding -> 0
         const uint64_t q = cusmc_fixed_from_unit(wn, shift);
         s1 += q;
         s2 += cusmc_fixed_from_unit(wn * wn, shift);
         np += q > 0;
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-        s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-        np += __shfl_xor_sync(0xffffffffu, np, o);
+    s1 = block_sum_u64(s1, sm);
+    if (stats) {
+        s2 = block_sum_u64(s2, sm);
+        np = block_sum_u64(np, sm);
+        if (threadIdx.x == 0) {
+            atomicAdd(stats + 0, s1);
+            atomicAdd(stats + 1, s2);
+            atomicAdd(stats + 2, np);
+        }
     }
-    __shared__ unsigned long long sm[3][kThreads / 32];
-    if ((threadIdx.x & 31) == 0) {
-        sm[0][threadIdx.x >> 5] = s1;
-        sm[1][threadIdx.x >> 5] = s2;
-        sm[2][threadIdx.x >> 5] = np;
+    if (threadIdx.x == 0) {
+        tile_state[1 + blockIdx.x] = s1;
+        __threadfence();
+        s_last = atomicAdd(tile_state, 1ull) == (unsigned long long)gridDim.x - 1;
     }
     __syncthreads();
-    if (threadIdx.x < 3) {
-        unsigned long long t = 0;
-        for (int k = 0; k < kThreads / 32; ++k) t += sm[threadIdx.x][k];
-        atomicAdd(stats + threadIdx.x, t);
+    if (!s_last) return;
+    // last block: exclusive scan of the tile sums, in place
+    __threadfence();
+    const int n = (int)gridDim.x;
+    const int per = (n + kThreads - 1) / kThreads;
+    const int lo = threadIdx.x * per, hi = min(lo + per, n);
+    unsigned long long mine = 0;
+    for (int k = lo; k < hi; ++k) mine += __ldcg(tile_state + 1 + k);
+    // block exclusive scan of `mine`
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    unsigned long long off = inc - mine;
+    for (int k = 0; k < warp; ++k) off += sm[k];
+    for (int k = lo; k < hi; ++k) {
+        const unsigned long long t = __ldcg(tile_state + 1 + k);
+        tile_state[1 + k] = off;
+        off += t;
+    }
+    if (threadIdx.x == 0) tile_state[0] = 0;
 }
 
-// ------------------------------------------------------------------------------------------
-// Single-pass inclusive scan (decoupled look-back) of the fixed-point weights, with the
-// systematic offspring scatter fused in.
-// ------------------------------------------------------------------------------------------
-constexpr int kScanItems = 8;                       // per thread: 4 rounds of one 128-bit load
-constexpr int kScanTile = kThreads * kScanItems;    // 2048 weights per tile
-constexpr uint64_t kFlagAgg = 1ull << 62, kFlagPrefix = 2ull << 62, kValMask = (1ull << 62) - 1;
-
 // #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
-// Floating-point estimate, then an exact 128-bit correction.
+// Floating-point estimate, then (rarely) an exact 128-bit correction.
 __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
                                                     double ng_over_t, double r0_over_t)
 {
@@ -180,8 +245,7 @@ struct ScanArgs {
     const double *wmax;
     const unsigned long long *total;       // global fixed-point mass (device)
     const unsigned long long *cdf_offset;  // mass on lower shards, or NULL
-    unsigned long long *desc;              // tile descriptors, zeroed before the launch
-    unsigned int *ticket;                  // zeroed before the launch
+    const unsigned long long *tile_state;  // weigh_kernel's output: [1 + b] = exclusive prefix of tile b
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
     int64_t N, N_global, j0, out_lo, out_n;
@@ -189,169 +253,86 @@ struct ScanArgs {
     int shift, is_log;
 };
 
+// Inclusive CDF of the fixed-point weights and, fused in, the systematic offspring scatter:
+// parent j owns the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.
 __global__ void __launch_bounds__(kThreads)
 scan_resample_kernel(const ScanArgs p)
 {
-    __shared__ unsigned int s_tile;
     __shared__ unsigned long long s_warp[kThreads / 32];
-    __shared__ unsigned long long s_prefix;
-    if (threadIdx.x == 0) s_tile = atomicAdd(p.ticket, 1u);
-    __syncthreads();
-    const int64_t tile = s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double wmax = *p.wmax;
-
-    // each warp owns 256 consecutive weights; round r: lane loads weights 64 r + 2 lane, +1
-    const int64_t wbase = tile * kScanTile + (int64_t)warp * (kScanItems * 32);
-    uint64_t q[kScanItems];
+    const int64_t base_idx = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
+    double v[kTileItems];
+    load_tile_items(p.w, base_idx, p.N, v);
+    uint64_t c[kTileItems];   // inclusive prefix within the thread
+    uint64_t run = 0;
 #pragma unroll
-    for (int r = 0; r < kScanItems / 2; ++r) {
-        const int64_t idx = wbase + r * 64 + lane * 2;
-        double w0 = 0.0, w1 = 0.0;
-        bool have0 = idx < p.N, have1 = idx + 1 < p.N;
-        if (have1 && (((uintptr_t)(p.w + idx)) & 15) == 0) {
-            const double2 v = __ldg(reinterpret_cast<const double2 *>(p.w + idx));
-            w0 = v.x;
-            w1 = v.y;
-        } else {
-            if (have0) w0 = __ldg(p.w + idx);
-            if (have1) w1 = __ldg(p.w + idx + 1);
-        }
-        q[2 * r] = have0 ? cusmc_fixed_from_unit(unit_weight(w0, wmax, p.is_log), p.shift) : 0;
-        q[2 * r + 1] = have1 ? cusmc_fixed_from_unit(unit_weight(w1, wmax, p.is_log), p.shift) : 0;
+    for (int r = 0; r < kTileItems; ++r) {
+        run += cusmc_fixed_from_unit(unit_weight(v[r], wmax, p.is_log), p.shift);
+        c[r] = run;
     }
-
-    // warp-level inclusive scan, round after round
-    uint64_t excl[kScanItems / 2];   // exclusive prefix of each pair within the warp
-    uint64_t running = 0;
+    uint64_t inc = run;
 #pragma unroll
-    for (int r = 0; r < kScanItems / 2; ++r) {
-        const uint64_t s = q[2 * r] + q[2 * r + 1];
-        uint64_t inc = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint64_t n = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += n;
-        }
-        excl[r] = running + inc - s;
-        running += __shfl_sync(0xffffffffu, inc, 31);
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
     }
-    if (lane == 0) s_warp[warp] = running;
+    if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint64_t warp_off = 0, aggregate = 0;
+    uint64_t before = inc - run + p.tile_state[1 + blockIdx.x] + (p.cdf_offset ? *p.cdf_offset : 0ull);
 #pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) {
-        const uint64_t v = s_warp[k];
-        if (k < warp) warp_off += v;
-        aggregate += v;
-    }
+    for (int k = 0; k < kThreads / 32; ++k)
+        if (k < warp) before += s_warp[k];
 
-    // decoupled look-back by warp 0
-    if (warp == 0) {
-        uint64_t exclusive = 0;
-        if (tile == 0) {
-            exclusive = p.cdf_offset ? *p.cdf_offset : 0;
+    if (p.cdf_out) {
+        if (base_idx + kTileItems <= p.N && (((uintptr_t)(p.cdf_out + base_idx)) & 15) == 0) {
+#pragma unroll
+            for (int r = 0; r < kTileItems / 2; ++r) {
+                ulonglong2 t;
+                t.x = before + c[2 * r];
+                t.y = before + c[2 * r + 1];
+                reinterpret_cast<ulonglong2 *>(p.cdf_out + base_idx)[r] = t;
+            }
         } else {
-            if (lane == 0) {
-                __threadfence();
-                atomicExch(p.desc + tile, kFlagAgg | aggregate);
-            }
-            int64_t look = tile - 1;
-            while (true) {
-                const int64_t mine = look - lane;
-                unsigned long long d = kFlagPrefix;   // lanes before tile 0 contribute nothing
-                if (mine >= 0) {
-                    do {
-                        d = *reinterpret_cast<volatile unsigned long long *>(p.desc + mine);
-                    } while ((d >> 62) == 0);
-                }
-                const unsigned has_prefix = __ballot_sync(0xffffffffu, (d >> 62) == 2);
-                const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;
-                uint64_t v = (lane <= first && mine >= 0) ? (d & kValMask) : 0;
-                if (mine < 0) v = 0;
 #pragma unroll
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-                exclusive += v;
-                if (has_prefix) {
-                    // tile 0's published prefix already contains cdf_offset; if the window ran
-                    // past tile 0 the offset came with it.
-                    break;
-                }
-                look -= 32;
-            }
-        }
-        if (lane == 0) {
-            __threadfence();
-            atomicExch(p.desc + tile, kFlagPrefix | (exclusive + aggregate));
-            s_prefix = exclusive;
+            for (int r = 0; r < kTileItems; ++r)
+                if (base_idx + r < p.N) p.cdf_out[base_idx + r] = before + c[r];
         }
     }
-    __syncthreads();
-    const uint64_t base = s_prefix + warp_off;
-
-    // outputs
-    uint64_t T = 0, r0 = 0;
-    double ng_over_t = 0.0, r0_over_t = 0.0;
-    if (p.anc_out) {
-        T = *p.total;
-        if (T == 0) return;                           // degenerate: host reports it
-        r0 = (uint64_t)(p.u0 * (double)T);
-        if (r0 > T - 1) r0 = T - 1;
-        ng_over_t = (double)p.N_global / (double)T;
-        r0_over_t = (double)r0 / (double)T;
-    }
-    uint64_t carry_k = 0;   // k2 of lane 31 in the previous round
+    if (!p.anc_out) return;
+    const uint64_t T = *p.total;
+    if (T == 0) return;                               // degenerate: the host reports it
+    uint64_t r0 = (uint64_t)(p.u0 * (double)T);
+    if (r0 > T - 1) r0 = T - 1;
+    const double ng_over_t = (double)p.N_global / (double)T;
+    const double r0_over_t = (double)r0 / (double)T;
+    const uint64_t Ng = (uint64_t)p.N_global;
+    const uint64_t lo_lim = (uint64_t)p.out_lo, hi_lim = (uint64_t)(p.out_lo + p.out_n);
+    // the offspring count is a pure function of the CDF value: a weight of zero repeats its
+    // left neighbour's count and costs nothing
+    uint64_t k_prev = offspring_below(before, Ng, T, r0, ng_over_t, r0_over_t);
+    uint64_t c_prev = 0;
 #pragma unroll
-    for (int r = 0; r < kScanItems / 2; ++r) {
-        const int64_t idx = wbase + r * 64 + lane * 2;
-        const uint64_t c_before = base + excl[r];
-        const uint64_t c0 = c_before + q[2 * r];
-        const uint64_t c1 = c0 + q[2 * r + 1];
-        if (p.cdf_out) {
-            if (idx + 1 < p.N && (((uintptr_t)(p.cdf_out + idx)) & 15) == 0) {
-                ulonglong2 v;
-                v.x = c0;
-                v.y = c1;
-                *reinterpret_cast<ulonglong2 *>(p.cdf_out + idx) = v;
-            } else {
-                if (idx < p.N) p.cdf_out[idx] = c0;
-                if (idx + 1 < p.N) p.cdf_out[idx + 1] = c1;
-            }
+    for (int r = 0; r < kTileItems; ++r) {
+        const uint64_t k_here = c[r] != c_prev ? offspring_below(before + c[r], Ng, T, r0, ng_over_t, r0_over_t) : k_prev;
+        uint64_t a = k_prev < lo_lim ? lo_lim : k_prev;
+        const uint64_t b = k_here > hi_lim ? hi_lim : k_here;
+        const uint32_t parent = (uint32_t)(p.j0 + base_idx + r);
+        // small families: the owning thread writes them; large ones: the whole warp helps
+        const bool big = b > a && b - a > 8;
+        if (!big)
+            for (; a < b; ++a) p.anc_out[a - lo_lim] = parent;
+        unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        while (bigmask) {
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
+            const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
+            const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+            for (uint64_t i = sa + lane; i < sb; i += 32) p.anc_out[i - lo_lim] = sp;
         }
-        if (p.anc_out) {
-            // children of particle idx : [k0, k1),  of idx+1 : [k1, k2).  The count is a pure
-            // function of the CDF value, so k0 is the left neighbour's k2: two evaluations per
-            // pair, plus one per warp for the first pair of the warp's chunk.
-            const uint64_t k1 = offspring_below(c0, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t);
-            const uint64_t k2 = offspring_below(c1, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t);
-            uint64_t k0 = __shfl_up_sync(0xffffffffu, k2, 1);
-            if (lane == 0)
-                k0 = (r == 0) ? offspring_below(c_before, (uint64_t)p.N_global, T, r0, ng_over_t, r0_over_t)
-                              : carry_k;
-            carry_k = __shfl_sync(0xffffffffu, k2, 31);
-            const uint64_t lo_lim = (uint64_t)p.out_lo, hi_lim = (uint64_t)(p.out_lo + p.out_n);
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                uint64_t a = h ? k1 : k0, b = h ? k2 : k1;
-                if (a < lo_lim) a = lo_lim;
-                if (b > hi_lim) b = hi_lim;
-                const uint32_t parent = (uint32_t)(p.j0 + idx + h);
-                uint64_t cnt = b > a ? b - a : 0;
-                // small families: the owning thread writes them; large ones: the whole warp helps
-                const bool big = cnt > 8;
-                if (!big)
-                    for (uint64_t i = a; i < b; ++i) p.anc_out[i - lo_lim] = parent;
-                unsigned bigmask = __ballot_sync(0xffffffffu, big);
-                while (bigmask) {
-                    const int src = __ffs(bigmask) - 1;
-                    bigmask &= bigmask - 1;
-                    const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
-                    const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
-                    const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
-                    for (uint64_t i = sa + lane; i < sb; i += 32) p.anc_out[i - lo_lim] = sp;
-                }
-            }
-        }
+        k_prev = k_here;
+        c_prev = c[r];
     }
 }
 
@@ -425,39 +406,40 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
     return CUSMC_OK;
 }
 
+// tile_state: cusmc_scan_state_bytes(N) bytes, word 0 zero (see weigh_kernel).  stats_dev may be
+// NULL (tile prefixes only).
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev)
+                             int64_t N, int shift, uint64_t *stats_dev, void *tile_state)
 {
     if (N == 0) return CUSMC_OK;
-    weights_sum_kernel<<<grid_for(ctx, N, kThreads * 4), kThreads, 0, ctx->stream>>>(
-        w, is_log, max_dev, N, shift, (unsigned long long *)stats_dev);
+    const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
+    weigh_kernel<<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
+                                                      (unsigned long long *)stats_dev,
+                                                      (unsigned long long *)tile_state);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
 
 size_t cusmc_scan_state_bytes(int64_t N)
 {
-    const int64_t tiles = (N + kScanTile - 1) / kScanTile;
+    const int64_t tiles = (N + kTile - 1) / kTile;
     return sizeof(unsigned long long) * (size_t)(tiles + 2);
 }
 
-// state: [ticket (8 bytes)] [descriptors ...]; must be zero when the kernel starts.
+// tile_state must hold the exclusive tile prefixes of exactly these weights (same w, max, N).
 int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev, int64_t N,
                       int64_t N_global, int shift, const uint64_t *total_dev,
-                      const uint64_t *cdf_offset_dev, void *state_dev, bool zero_state,
+                      const uint64_t *cdf_offset_dev, const void *tile_state,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0)
 {
     if (N == 0) return CUSMC_OK;
-    if (zero_state)
-        CUSMC_CUDA(ctx, cudaMemsetAsync(state_dev, 0, cusmc_scan_state_bytes(N), ctx->stream));
     ScanArgs p;
     p.w = w;
     p.wmax = max_dev;
     p.total = (const unsigned long long *)total_dev;
     p.cdf_offset = (const unsigned long long *)cdf_offset_dev;
-    p.ticket = (unsigned int *)state_dev;
-    p.desc = (unsigned long long *)state_dev + 1;
+    p.tile_state = (const unsigned long long *)tile_state;
     p.cdf_out = (unsigned long long *)cdf_out;
     p.anc_out = anc_out;
     p.N = N;
@@ -468,7 +450,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double 
     p.u0 = u0;
     p.shift = shift;
     p.is_log = is_log;
-    const unsigned tiles = (unsigned)((N + kScanTile - 1) / kScanTile);
+    const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
     scan_resample_kernel<<<tiles, kThreads, 0, ctx->stream>>>(p);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
@@ -511,45 +493,85 @@ extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_
     return cusmc_launch_weights_max(ctx, w_dev, N, max_dev);
 }
 
+// Tile-prefix storage for the building-block entry points: the caller's buffer
+// (cusmc_tile_prefix_words(N) words, word 0 zero before first use) or context scratch.
+static int tile_state_for(cusmc_ctx *ctx, int64_t N, uint64_t *user, void **out)
+{
+    if (user) {
+        *out = user;
+        return CUSMC_OK;
+    }
+    CUSMC_CHECK(cusmc_scratch(ctx, 7, cusmc_scan_state_bytes(N), out));
+    CUSMC_CUDA(ctx, cudaMemsetAsync(*out, 0, sizeof(uint64_t), ctx->stream));
+    return CUSMC_OK;
+}
+
+extern "C" int64_t cusmc_tile_prefix_words(int64_t N)
+{
+    return N < 0 ? 0 : (int64_t)(cusmc_scan_state_bytes(N) / sizeof(uint64_t));
+}
+
 extern "C" int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
                                      const double *max_dev, int64_t N, int64_t N_global,
-                                     uint64_t *stats_dev)
+                                     uint64_t *stats_dev, uint64_t *tile_prefix_dev)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(ctx, stats_dev && max_dev && (N == 0 || w_dev), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N && N_global >= 1, "N_global < N");
     CUSMC_CUDA(ctx, cudaMemsetAsync(stats_dev, 0, 4 * sizeof(uint64_t), ctx->stream));
-    return cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), stats_dev);
+    if (N == 0) return CUSMC_OK;
+    void *state = nullptr;
+    CUSMC_CHECK(tile_state_for(ctx, N, tile_prefix_dev, &state));
+    return cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), stats_dev, state);
+}
+
+// Tile prefixes for a scan: the caller's (from cusmc_weights_sum_dev on the same weights) or a
+// fresh reduction into context scratch.
+static int scan_prefixes(cusmc_ctx *ctx, const double *w_dev, int is_log, const double *max_dev, int64_t N,
+                         int64_t N_global, const uint64_t *tile_prefix_dev, const void **state)
+{
+    if (tile_prefix_dev) {
+        *state = tile_prefix_dev;
+        return CUSMC_OK;
+    }
+    void *mine = nullptr;
+    CUSMC_CHECK(tile_state_for(ctx, N, nullptr, &mine));
+    CUSMC_CHECK(cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), nullptr, mine));
+    *state = mine;
+    return CUSMC_OK;
 }
 
 extern "C" int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
                                       const double *max_dev, int64_t N, int64_t N_global,
-                                      const uint64_t *cdf_offset_dev, uint64_t *cdf_dev)
+                                      const uint64_t *cdf_offset_dev, const uint64_t *tile_prefix_dev,
+                                      uint64_t *cdf_dev)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(ctx, max_dev && (N == 0 || (w_dev && cdf_dev)), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N && N_global >= 1, "N_global < N");
-    void *state = nullptr;
-    CUSMC_CHECK(cusmc_scratch(ctx, 7, cusmc_scan_state_bytes(N), &state));
+    if (N == 0) return CUSMC_OK;
+    const void *state = nullptr;
+    CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N, N_global, tile_prefix_dev, &state));
     return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N, N_global, cusmc_fixed_shift(N_global),
-                             nullptr, cdf_offset_dev, state, true, cdf_dev, nullptr, 0, 0, 0, 0.0);
+                             nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0);
 }
 
 extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
                                              const double *max_dev, int64_t N_local, int64_t N_global,
                                              const uint64_t *total_dev, const uint64_t *cdf_offset_dev,
-                                             int64_t j0, int64_t out_lo, int64_t out_n, double u0,
-                                             uint32_t *a_dev)
+                                             const uint64_t *tile_prefix_dev, int64_t j0, int64_t out_lo,
+                                             int64_t out_n, double u0, uint32_t *a_dev)
 {
     if (!ctx) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(ctx, max_dev && total_dev && (N_local == 0 || w_dev) && (out_n == 0 || a_dev), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N_local && N_global >= 1, "N_global < N_local");
     CUSMC_REQUIRE(ctx, N_global <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
     CUSMC_REQUIRE(ctx, u0 >= 0.0 && u0 < 1.0, "u0 must lie in [0, 1)");
-    void *state = nullptr;
-    CUSMC_CHECK(cusmc_scratch(ctx, 7, cusmc_scan_state_bytes(N_local), &state));
+    if (N_local == 0) return CUSMC_OK;
+    const void *state = nullptr;
+    CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N_local, N_global, tile_prefix_dev, &state));
     return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N_local, N_global, cusmc_fixed_shift(N_global),
-                             total_dev, cdf_offset_dev, state, true, nullptr, a_dev, j0, out_lo, out_n, u0);
+                             total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo, out_n, u0);
 }
 
 extern "C" int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cdf_dev, int64_t N,
@@ -584,7 +606,7 @@ int upload_and_reduce(cusmc_ctx *ctx, const double *w, int64_t N, int is_log, Ho
     hw.stats_dev = (uint64_t *)small + 1;
     CUSMC_CUDA(ctx, cudaMemcpyAsync(wd, w, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
     CUSMC_CHECK(cusmc_weights_max_dev(ctx, hw.w_dev, N, hw.max_dev));
-    CUSMC_CHECK(cusmc_weights_sum_dev(ctx, hw.w_dev, is_log, hw.max_dev, N, N, hw.stats_dev));
+    CUSMC_CHECK(cusmc_weights_sum_dev(ctx, hw.w_dev, is_log, hw.max_dev, N, N, hw.stats_dev, nullptr));
     CUSMC_CUDA(ctx, cudaMemcpyAsync(pin, small, 40, cudaMemcpyDeviceToHost, ctx->stream));
     CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     std::memcpy(max_host, pin, 8);
@@ -640,8 +662,9 @@ extern "C" int cusmc_resample_systematic(cusmc_ctx *ctx, const double *w, int64_
     }
     void *ad = nullptr;
     CUSMC_CHECK(cusmc_scratch(ctx, 1, sizeof(uint32_t) * (size_t)N, &ad));
-    CUSMC_CHECK(cusmc_resample_systematic_dev(ctx, hw.w_dev, 0, hw.max_dev, N, N, hw.stats_dev, nullptr, 0, 0,
-                                              N, u0, (uint32_t *)ad));
+    // the reduction above left this weight vector's tile prefixes in scratch slot 7
+    CUSMC_CHECK(cusmc_resample_systematic_dev(ctx, hw.w_dev, 0, hw.max_dev, N, N, hw.stats_dev, nullptr,
+                                              (const uint64_t *)ctx->scratch[7], 0, 0, N, u0, (uint32_t *)ad));
     CUSMC_CUDA(ctx, cudaMemcpyAsync(a, ad, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));
     CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return CUSMC_OK;
@@ -666,7 +689,8 @@ extern "C" int cusmc_resample_multinomial(cusmc_ctx *ctx, const double *w, int64
     CUSMC_CHECK(cusmc_scratch(ctx, 2, sizeof(uint64_t) * (size_t)N, &cd));
     CUSMC_CHECK(cusmc_scratch(ctx, 3, sizeof(double) * (size_t)N, &ud));
     CUSMC_CUDA(ctx, cudaMemcpyAsync(ud, u, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, ctx->stream));
-    CUSMC_CHECK(cusmc_weights_scan_dev(ctx, hw.w_dev, 0, hw.max_dev, N, N, nullptr, (uint64_t *)cd));
+    CUSMC_CHECK(cusmc_weights_scan_dev(ctx, hw.w_dev, 0, hw.max_dev, N, N, nullptr,
+                                       (const uint64_t *)ctx->scratch[7], (uint64_t *)cd));
     CUSMC_CHECK(cusmc_resample_multinomial_dev(ctx, (const uint64_t *)cd, N, hw.stats_dev, (const double *)ud,
                                                0, 0, 0, N, 0, (uint32_t *)ad));
     CUSMC_CUDA(ctx, cudaMemcpyAsync(a, ad, sizeof(uint32_t) * (size_t)N, cudaMemcpyDeviceToHost, ctx->stream));

@@ -196,20 +196,30 @@ int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log, double *x
  *
  * cusmc_weights_max_dev : *max_dev = max_i w_i over finite entries (set to -inf first).
  * cusmc_weights_sum_dev : stats_dev[0..2] = { sum q_i, sum trunc(wn_i^2 2^shift), #(q_i > 0) }
- *                         (zeroed first).  log-sum-exp = max + log(stats[0] / 2^shift),
- *                         ESS = stats[0]^2 / (stats[1] 2^shift).
- * cusmc_weights_scan_dev: cdf_dev[i] = *cdf_offset_dev + inclusive prefix sum of q (single-pass
- *                         decoupled look-back scan).  cdf_offset_dev may be NULL (0): it is the
+ *                         (4 words, zeroed first).  log-sum-exp = max + log(stats[0] / 2^shift),
+ *                         ESS = stats[0]^2 / (stats[1] 2^shift).  The same pass leaves the exclusive
+ *                         prefix of the per-tile sums (tile = 2048 weights) in tile_prefix_dev:
+ *                         cusmc_tile_prefix_words(N) uint64 words whose word 0 is zero before the
+ *                         first use (the kernel resets it); NULL = context scratch.
+ * cusmc_weights_scan_dev: cdf_dev[i] = *cdf_offset_dev + inclusive prefix sum of q.  Because the
+ *                         total must be known before a single child can be assigned, the sum pass
+ *                         above is mandatory anyway and hands the scan its tile prefixes: tiles are
+ *                         independent, nothing spins (a decoupled look-back would add a serial
+ *                         dependency for information that is already in memory).  tile_prefix_dev:
+ *                         what cusmc_weights_sum_dev left for the SAME (w, max, N, N_global), or
+ *                         NULL to recompute it here.  cdf_offset_dev may be NULL (0): it is the
  *                         fixed-point mass held by lower-ranked shards.
  * On several GPUs the caller all-reduces max (MAX) and stats (SUM) between these calls and
  * passes the exclusive prefix of the per-rank sums as cdf_offset (cusmc_b200/sharded.py).
  */
+int64_t cusmc_tile_prefix_words(int64_t N);
 int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev);
 int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, const double *max_dev,
-                          int64_t N, int64_t N_global, uint64_t *stats_dev);
+                          int64_t N, int64_t N_global, uint64_t *stats_dev,
+                          uint64_t *tile_prefix_dev);
 int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, const double *max_dev,
                            int64_t N, int64_t N_global, const uint64_t *cdf_offset_dev,
-                           uint64_t *cdf_dev);
+                           const uint64_t *tile_prefix_dev, uint64_t *cdf_dev);
 
 /*
  * Systematic resampling, offspring-scatter form, fused into the scan: with T = *total_dev the
@@ -218,12 +228,13 @@ int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, cons
  * (C = global inclusive prefix; 128-bit integer compare).  Every local parent j writes
  *   a_dev[i - out_lo] = j0 + j      for its children i inside [out_lo, out_lo + out_n).
  * j0 = global index of w_dev[0].  One GPU: j0 = out_lo = 0, out_n = N_local = N_global.
+ * tile_prefix_dev as for cusmc_weights_scan_dev.
  */
 int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
                                   const double *max_dev, int64_t N_local, int64_t N_global,
                                   const uint64_t *total_dev, const uint64_t *cdf_offset_dev,
-                                  int64_t j0, int64_t out_lo, int64_t out_n, double u0,
-                                  uint32_t *a_dev);
+                                  const uint64_t *tile_prefix_dev, int64_t j0, int64_t out_lo,
+                                  int64_t out_n, double u0, uint32_t *a_dev);
 /* Multinomial: a_dev[t] = j0 + #{ j : cdf_j <= p },  p = min((uint64)(u * (double)T), T - 1), for
  * children i0 .. i0 + n_out - 1; u = u_dev[t] or, if u_dev is NULL, the Philox draw keyed by
  * (seed, step, i0 + t). */
