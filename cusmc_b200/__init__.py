@@ -9,7 +9,9 @@ from ._lib import (AOS, SOA, CusmcError, LIB_PATH, MVN as KIND_MVN, MVT as KIND_
 from .api import (Context, MVN, MVNPDF, MVT, MVTPDF, ParticleFilter, default_context,  # noqa: F401
                   metropolis_hastings, run)
 
+from .sharded import ShardPlan, ShardedParticleFilter  # noqa: F401,E402
+
 load()   # a missing or incomplete libcusmc_b200.so is an import error, never a silent fallback
 
 __all__ = ["Context", "ParticleFilter", "MVN", "MVNPDF", "MVT", "MVTPDF", "metropolis_hastings", "run",
-           "CusmcError", "AOS", "SOA"]
+           "CusmcError", "AOS", "SOA", "ShardPlan", "ShardedParticleFilter"]

@@ -26,6 +26,8 @@ MVN, MVT = 0, 1
 SOA, AOS = 0, 1
 RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1, 2
 MAX_DIM = 32
+MAX_PEERS = 8
+IPC_HANDLE_BYTES = 64
 
 
 class FilterConfig(C.Structure):
@@ -33,7 +35,7 @@ class FilterConfig(C.Structure):
         ("N", i64), ("d", ci), ("dy", ci), ("T", ci), ("kind", ci), ("resampler", ci), ("B", ci),
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
-        ("keep_history", ci), ("summary", ci),
+        ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci),
     ]
 
 
@@ -82,6 +84,15 @@ PROTOTYPES = {
     "cusmc_filter_create": (ci, [vp, C.POINTER(FilterConfig), C.POINTER(vp)]),
     "cusmc_filter_destroy": (ci, [vp]),
     "cusmc_filter_run": (ci, [vp, C.POINTER(FilterDraws)]),
+    "cusmc_filter_begin": (ci, [vp, C.POINTER(FilterDraws)]),
+    "cusmc_filter_weigh": (ci, [vp, ci]),
+    "cusmc_filter_resample": (ci, [vp, ci]),
+    "cusmc_filter_propagate": (ci, [vp, ci]),
+    "cusmc_filter_mark": (ci, [vp, ci]),
+    "cusmc_filter_slot_dev": (ci, [vp, ci, C.POINTER(vp)]),
+    "cusmc_filter_moments_dev": (ci, [vp, C.POINTER(vp)]),
+    "cusmc_filter_ipc_export": (ci, [vp, vp]),
+    "cusmc_filter_ipc_attach": (ci, [vp, vp]),
     "cusmc_filter_get_summary": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_get_history": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_last_ms": (dbl, [vp]),

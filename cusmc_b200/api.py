@@ -385,13 +385,15 @@ class ParticleFilter:
     """particle_filter() of the reference (src/particle_filter.cpp:6-39) with device-resident state."""
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
-                 df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True):
+                 df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1):
         self.ctx = ctx
         Y = np.asarray(Y, dtype=np.float64)
         F = np.asarray(F, dtype=np.float64)
         self.dy, self.T = Y.shape
         self.d = np.asarray(G).shape[0]
         self.N = int(N)
+        per = -(-self.N // max(1, int(world)))
+        self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
         self._keep = [_colmajor(Y), _f64(m0), _colmajor(C0), _colmajor(F), _colmajor(G), _colmajor(V),
                       _colmajor(W)]
         cfg = FilterConfig()
@@ -405,6 +407,7 @@ class ParticleFilter:
         (cfg.Y, cfg.m0, cfg.C0, cfg.F, cfg.G, cfg.V, cfg.W) = [a.ctypes.data for a in self._keep]
         cfg.keep_history = int(keep_history)
         cfg.summary = int(summary)
+        cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
         self.keep_history = bool(keep_history)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
@@ -424,14 +427,18 @@ class ParticleFilter:
     def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None):
         """Injected draws are torch CUDA tensors (see cusmc_filter_draws), u0 a host array; any
         omitted stream of randomness is drawn on the device from Philox."""
+        dr = self._make_draws(xi0, xi, chi, u, j, u0, um)
+        self.ctx._check(self.ctx.lib.cusmc_filter_run(self.h, C.byref(dr)))
+        return self
+
+    def _make_draws(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None):
         dr = FilterDraws()
         dr.xi0_dev, dr.xi_dev, dr.chi_dev = _dp(xi0), _dp(xi), _dp(chi)
         dr.u_dev, dr.j_dev, dr.um_dev = _dp(u), _dp(j), _dp(um)
         self._u0 = None if u0 is None else _f64(u0)
         dr.u0_host = _hp(self._u0)
         self._draws = (xi0, xi, chi, u, j, um)   # keep alive until the stream has consumed them
-        self.ctx._check(self.ctx.lib.cusmc_filter_run(self.h, C.byref(dr)))
-        return self
+        return dr
 
     @property
     def last_ms(self):
@@ -445,9 +452,10 @@ class ParticleFilter:
         return dict(mean=mean, ess=ess, loglik=ll)
 
     def history(self):
-        x = np.empty((self.T, self.N, self.d))
-        w = np.empty((self.T, self.N))
-        a = np.empty((self.T, self.N), dtype=np.uint32)
+        n = self.n_local            # a sharded filter returns its own shard
+        x = np.empty((self.T, n, self.d))
+        w = np.empty((self.T, n))
+        a = np.empty((self.T, n), dtype=np.uint32)
         self.ctx._check(self.ctx.lib.cusmc_filter_get_history(self.h, _hp(x), _hp(w), _hp(a)))
         return dict(x=x, w=w, a=a)
 

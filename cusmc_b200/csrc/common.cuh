@@ -14,6 +14,14 @@
 
 #define CUSMC_NUM_SCRATCH 8
 
+// One peer-mapped pointer per rank of a sharded run (rank r owns global slots
+// r * per_rank .. ), see cusmc_ipc_open.
+struct CusmcPeers {
+    void *ptr[CUSMC_MAX_PEERS];
+    int64_t per_rank;
+    int world;
+};
+
 struct cusmc_density_cache;   // density.cu: last factored (kind, mu, Sigma, nu)
 
 struct cusmc_ctx {

@@ -20,6 +20,7 @@
 #include "../../include/cusmc_detmath.h"
 #include "../../include/cusmc_philox.h"
 
+#include <algorithm>
 #include <cmath>
 #include <new>
 #include <vector>
@@ -417,21 +418,28 @@ extern "C" int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log
 // The filter object: particle_filter() / initialize() / MCMC() of the reference
 // (src/particle_filter.cpp:6-39, src/mcmc.cpp:44-88,239-309) with device-resident state.
 // ================================================================================================
-struct StepSlot {            // one per time step, on the device (64 bytes)
-    double lw_max;           // max log-weight (log modes), -inf initialised
-    uint64_t sum_q, sum_q2, n_pos, pad;   // fixed-point sums (weights_sum_kernel)
+struct StepSlot {            // one per time step, on the device (64 bytes = 8 words)
+    double lw_max;           // [0] max log-weight (log modes), -inf initialised
+    uint64_t sum_q, sum_q2, n_pos;   // [1..3] fixed-point sums (weigh_kernel); global after the exchange
+    uint64_t cdf_offset;     // [4] fixed-point mass held by lower-ranked shards (0 on one GPU)
     double reserved[3];
 };
 
 struct cusmc_filter {
     cusmc_ctx *ctx = nullptr;
     cusmc_filter_config cfg{};
+    cusmc_filter_draws draws{};
     std::vector<double> Y, m0, C0, F, G, V, W;       // host copies (column-major)
     std::vector<double> Qc0, Qw;                      // noise factors
     std::vector<double> M, Winv;                      // observation operator
     Epilogue ep{};
     int is_log = 1;
     int shift = 0;
+    // sharding: this rank owns the global slots lo .. lo + n - 1; every rank allocates `per` columns
+    int world = 1, rank = 0;
+    int64_t per = 0, lo = 0, n = 0;
+    bool attached = false;
+    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{};
     double *x[2] = {nullptr, nullptr};
     double *lw = nullptr;
     uint32_t *anc = nullptr;
@@ -444,6 +452,7 @@ struct cusmc_filter {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     int cur = 0;
+    int next_t = -1;                  // phase bookkeeping: the step cusmc_filter_propagate expects
     bool ran = false;
 };
 
@@ -494,11 +503,22 @@ static int eigen_factor(cusmc_ctx *ctx, const double *S, int d, std::vector<doub
     return CUSMC_OK;
 }
 
+static void detach_peers(cusmc_filter *f)
+{
+    if (!f->attached) return;
+    CusmcPeers *tabs[4] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw};
+    for (CusmcPeers *t : tabs)
+        for (int r = 0; r < f->world; ++r)
+            if (r != f->rank && t->ptr[r]) cudaIpcCloseMemHandle(t->ptr[r]);
+    f->attached = false;
+}
+
 extern "C" int cusmc_filter_destroy(cusmc_filter *f)
 {
     if (!f) return CUSMC_OK;
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
+    detach_peers(f);
     cudaFree(f->x[0]);
     cudaFree(f->x[1]);
     cudaFree(f->lw);
@@ -528,12 +548,22 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->kind == CUSMC_MVT, "unknown distribution");
     CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 2, "unknown resampler");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
+    const int world = cfg->world <= 1 ? 1 : cfg->world;
+    CUSMC_REQUIRE(ctx, world <= CUSMC_MAX_PEERS, "world exceeds CUSMC_MAX_PEERS");
+    CUSMC_REQUIRE(ctx, world == 1 || (cfg->rank >= 0 && cfg->rank < world), "rank outside 0..world-1");
+    if (world > 1 && cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "the multinomial resampler is single-GPU only");
     cusmc_filter *f = new (std::nothrow) cusmc_filter();
     if (!f) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "out of host memory");
     f->ctx = ctx;
     f->cfg = *cfg;
     const int d = cfg->d, dy = cfg->dy, T = cfg->T;
     const int64_t N = cfg->N;
+    f->world = world;
+    f->rank = world == 1 ? 0 : cfg->rank;
+    f->per = (N + world - 1) / world;
+    f->lo = (int64_t)f->rank * f->per;
+    f->n = std::max<int64_t>(0, std::min<int64_t>(f->per, N - f->lo));
     f->Y.assign(cfg->Y, cfg->Y + (size_t)dy * T);
     f->m0.assign(cfg->m0, cfg->m0 + d);
     f->C0.assign(cfg->C0, cfg->C0 + (size_t)d * d);
@@ -566,18 +596,19 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     auto alloc = [&](void **p, size_t bytes) {
         if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8);
     };
-    alloc((void **)&f->x[0], sizeof(double) * (size_t)N * d);
-    alloc((void **)&f->x[1], sizeof(double) * (size_t)N * d);
-    alloc((void **)&f->lw, sizeof(double) * (size_t)N);
-    alloc((void **)&f->anc, sizeof(uint32_t) * (size_t)N);
-    if (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL) alloc((void **)&f->cdf, sizeof(uint64_t) * (size_t)N);
+    const size_t P = (size_t)f->per;          // columns allocated on every rank
+    alloc((void **)&f->x[0], sizeof(double) * P * d);
+    alloc((void **)&f->x[1], sizeof(double) * P * d);
+    alloc((void **)&f->lw, sizeof(double) * P);
+    alloc((void **)&f->anc, sizeof(uint32_t) * P);
+    if (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL) alloc((void **)&f->cdf, sizeof(uint64_t) * P);
     alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
     alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
-    alloc(&f->scan_state, cusmc_scan_state_bytes(N));
+    alloc(&f->scan_state, cusmc_scan_state_bytes(f->per));
     if (cfg->keep_history) {
-        alloc((void **)&f->hist_x, sizeof(double) * (size_t)T * N * d);
-        alloc((void **)&f->hist_w, sizeof(double) * (size_t)T * N);
-        alloc((void **)&f->hist_a, sizeof(uint32_t) * (size_t)T * N);
+        alloc((void **)&f->hist_x, sizeof(double) * (size_t)T * P * d);
+        alloc((void **)&f->hist_w, sizeof(double) * (size_t)T * P);
+        alloc((void **)&f->hist_a, sizeof(uint32_t) * (size_t)T * P);
     }
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
@@ -590,13 +621,82 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     return CUSMC_OK;
 }
 
+// ---- sharded runs: peer mapping of the state ---------------------------------------------------
+// Exported buffers, in this order: x[0], x[1], ancestors, weights.
+enum { kIpcBuffers = 4 };
+
+extern "C" int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, handles != nullptr, "handles is NULL");
+    static_assert(sizeof(cudaIpcMemHandle_t) == CUSMC_IPC_HANDLE_BYTES, "IPC handle size");
+    void *bufs[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw};
+    for (int b = 0; b < kIpcBuffers; ++b) {
+        cudaIpcMemHandle_t h;
+        CUSMC_CUDA(ctx, cudaIpcGetMemHandle(&h, bufs[b]));
+        std::memcpy(handles + (size_t)b * CUSMC_IPC_HANDLE_BYTES, &h, sizeof h);
+    }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all_handles)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, all_handles != nullptr, "handles is NULL");
+    CUSMC_REQUIRE(ctx, !f->attached, "peers are already attached");
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw};
+    void *mine[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw};
+    for (int b = 0; b < kIpcBuffers; ++b) {
+        *tabs[b] = CusmcPeers{};
+        tabs[b]->per_rank = f->per;
+        tabs[b]->world = f->world;
+    }
+    f->attached = true;   // so a failure below closes what was opened
+    for (int r = 0; r < f->world; ++r)
+        for (int b = 0; b < kIpcBuffers; ++b) {
+            if (r == f->rank) {
+                tabs[b]->ptr[r] = mine[b];
+                continue;
+            }
+            cudaIpcMemHandle_t h;
+            std::memcpy(&h, all_handles + ((size_t)r * kIpcBuffers + b) * CUSMC_IPC_HANDLE_BYTES, sizeof h);
+            cudaError_t e = cudaIpcOpenMemHandle(&tabs[b]->ptr[r], h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) {
+                tabs[b]->ptr[r] = nullptr;
+                detach_peers(f);
+                return cusmc_fail(ctx, CUSMC_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d, buffer %d): %s", r, b,
+                                  cudaGetErrorString(e));
+            }
+        }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, slot_dev && t >= 0 && t < f->cfg.T, "bad step");
+    *slot_dev = f->slots + t;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_moments_dev(cusmc_filter *f, double **moments_dev)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, moments_dev != nullptr, "NULL pointer");
+    *moments_dev = f->moments;
+    return CUSMC_OK;
+}
+
 __global__ void init_slots_kernel(StepSlot *slots, int T)
 {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < T) {
         StepSlot s;
         s.lw_max = -INFINITY;
-        s.sum_q = s.sum_q2 = s.n_pos = s.pad = 0;
+        s.sum_q = s.sum_q2 = s.n_pos = s.cdf_offset = 0;
         s.reserved[0] = s.reserved[1] = s.reserved[2] = 0.0;
         slots[t] = s;
     }
@@ -608,121 +708,184 @@ static uint64_t host_u0_bits(uint64_t seed, uint64_t step)
     return ((uint64_t)r.v[0] << 32) | r.v[1];
 }
 
-extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws)
+// ---- the step, phase by phase ------------------------------------------------------------------
+// One GPU: cusmc_filter_run chains them.  Sharded: the binding (cusmc_b200/sharded.py) puts the
+// scalar exchanges between them -- MAX of slot[t].lw_max after propagate, the per-rank sums after
+// weigh, a barrier after resample (ancestors land in peers' memory).
+
+extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws)
 {
     if (!f) return CUSMC_ERR_INVALID;
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     const int d = cfg.d, dy = cfg.dy, T = cfg.T;
-    const int64_t N = cfg.N;
-    cusmc_filter_draws none{};
-    if (!draws) draws = &none;
+    CUSMC_REQUIRE(ctx, f->world == 1 || f->attached, "sharded filter: attach the peers first");
+    f->draws = draws ? *draws : cusmc_filter_draws{};
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-
     init_slots_kernel<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
     CUSMC_LAUNCHED(ctx);
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
-    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, cusmc_scan_state_bytes(N), st));
-    const int mom_grid = (int)std::min<int64_t>((N + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
-
-    auto after_step = [&](int t) -> int {
-        // sums for normalisation / ESS (log modes), moments, history
-        if (f->is_log)
-            CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, N, f->shift, &f->slots[t].sum_q,
-                                                 f->scan_state));
-        if (cfg.summary) {
-            moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, N, N, d,
-                                                          f->moments + (size_t)t * (2 + d));
-            CUSMC_LAUNCHED(ctx);
-        }
-        if (cfg.keep_history) {
-            CUSMC_CHECK(cusmc_soa_to_aos_dev(ctx, f->x[f->cur], f->hist_x + (size_t)t * N * d, N, N, d));
-            CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_w + (size_t)t * N, f->lw, sizeof(double) * (size_t)N,
-                                            cudaMemcpyDeviceToDevice, st));
-            if (t > 0)
-                CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_a + (size_t)t * N, f->anc, sizeof(uint32_t) * (size_t)N,
-                                                cudaMemcpyDeviceToDevice, st));
-        }
-        return CUSMC_OK;
-    };
-
-    // ---- t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N ----
+    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, cusmc_scan_state_bytes(f->per), st));
+    // t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N
     f->cur = 0;
-    {
-        StepArgs a{};
-        a.x_new = f->x[0];
-        a.x_prev = f->x[1];
-        a.xi = draws->xi0_dev;
-        a.lw = f->lw;
-        a.lw_max = f->is_log ? &f->slots[0].lw_max : nullptr;
-        a.n_out = N;
-        a.ld_new = a.ld_prev = a.ld_noise = N;
-        a.seed = cfg.seed;
-        a.step = 0;
-        a.nu = cfg.nu;
-        a.d = d;
-        a.dy = dy;
-        a.kind = CUSMC_MVN;   // initial chi are 1 (see oracle: orc_filter_metropolis)
-        a.has_prev = 0;
-        a.skip_weight = 1;
-        a.const_weight = f->is_log ? 0.0 : 1.0 / (double)N;
-        a.rng_stream = CUSMC_STREAM_INIT;
-        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
-                                      f->m0.data(), f->ep, a, draws->xi0_dev == nullptr));
-    }
-    CUSMC_CHECK(after_step(0));
-
-    CUSMC_CUDA(ctx, cudaEventRecord(f->ev0, st));
-    for (int t = 1; t < T; ++t) {
-        const size_t off = (size_t)(t - 1);
-        // 1. ancestors (src/mcmc.cpp:295)
-        if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
-            const double *u = draws->u_dev ? draws->u_dev + off * N * cfg.B : nullptr;
-            const uint32_t *j = draws->j_dev ? draws->j_dev + off * N * cfg.B : nullptr;
-            CUSMC_CHECK(cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log, 0, N));
-        } else if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
-            const double u0 = draws->u0_host ? draws->u0_host[off]
-                                             : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
-            CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
-                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, nullptr, f->anc,
-                                          0, 0, N, u0));
-        } else {
-            CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &f->slots[t - 1].lw_max, N, N, f->shift,
-                                          &f->slots[t - 1].sum_q, nullptr, f->scan_state, f->cdf, nullptr,
-                                          0, 0, 0, 0.0));
-            const double *um = draws->um_dev ? draws->um_dev + off * N : nullptr;
-            CUSMC_CHECK(cusmc_launch_multinomial(ctx, f->cdf, N, &f->slots[t - 1].sum_q, um, cfg.seed, (uint64_t)t, 0, N, 0, f->anc));
-        }
-        // 2 + 3. propagate and reweight, fused (src/mcmc.cpp:298-307)
-        double c[CUSMC_MAX_DIM];
-        whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
-        StepArgs a{};
-        a.x_new = f->x[f->cur ^ 1];
-        a.x_prev = f->x[f->cur];
-        a.anc = f->anc;
-        a.xi = draws->xi_dev ? draws->xi_dev + off * N * d : nullptr;
-        a.chi = draws->chi_dev ? draws->chi_dev + off * N * d : nullptr;
-        a.lw = f->lw;
-        a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
-        a.n_out = N;
-        a.ld_new = a.ld_prev = a.ld_noise = N;
-        a.seed = cfg.seed;
-        a.step = (uint64_t)t;
-        a.nu = cfg.nu;
-        a.d = d;
-        a.dy = dy;
-        a.kind = cfg.kind;
-        a.has_prev = 1;
-        a.rng_stream = CUSMC_STREAM_NORMAL;
-        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
-                                      f->ep, a, a.xi == nullptr));
-        f->cur ^= 1;
-        CUSMC_CHECK(after_step(t));
-    }
-    CUSMC_CUDA(ctx, cudaEventRecord(f->ev1, st));
-    f->ran = true;
+    StepArgs a{};
+    a.x_new = f->x[0];
+    a.x_prev = f->x[1];
+    a.xi = f->draws.xi0_dev;
+    a.lw = f->lw;
+    a.lw_max = f->is_log ? &f->slots[0].lw_max : nullptr;
+    a.n_out = f->n;
+    a.ld_new = a.ld_prev = f->per;
+    a.ld_noise = f->n;
+    a.i0 = f->lo;
+    a.seed = cfg.seed;
+    a.step = 0;
+    a.nu = cfg.nu;
+    a.d = d;
+    a.dy = dy;
+    a.kind = CUSMC_MVN;   // initial chi are 1 (see oracle: orc_filter_metropolis)
+    a.has_prev = 0;
+    a.skip_weight = 1;
+    a.const_weight = f->is_log ? 0.0 : 1.0 / (double)cfg.N;
+    a.rng_stream = CUSMC_STREAM_INIT;
+    CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
+                                  f->m0.data(), f->ep, a, f->draws.xi0_dev == nullptr));
+    f->next_t = 1;
+    f->ran = false;
     return CUSMC_OK;
+}
+
+// After step t's weights exist and slot[t].lw_max holds the GLOBAL max: fixed-point sums and tile
+// prefixes (log modes), posterior moments, history.
+extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    CUSMC_REQUIRE(ctx, t >= 0 && t < cfg.T && f->next_t == t + 1, "weigh(t) follows begin / propagate(t)");
+    const int d = cfg.d;
+    const int64_t n = f->n, P = f->per;
+    cudaStream_t st = ctx->stream;
+    if (f->is_log)
+        CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
+                                             f->scan_state));
+    if (cfg.summary && n > 0) {
+        const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
+        moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
+                                                      f->moments + (size_t)t * (2 + d));
+        CUSMC_LAUNCHED(ctx);
+    }
+    if (cfg.keep_history && n > 0) {
+        CUSMC_CHECK(cusmc_soa_to_aos_dev(ctx, f->x[f->cur], f->hist_x + (size_t)t * n * d, n, P, d));
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_w + (size_t)t * n, f->lw, sizeof(double) * (size_t)n,
+                                        cudaMemcpyDeviceToDevice, st));
+        if (t > 0)
+            CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_a + (size_t)t * n, f->anc, sizeof(uint32_t) * (size_t)n,
+                                            cudaMemcpyDeviceToDevice, st));
+    }
+    return CUSMC_OK;
+}
+
+// Ancestors of step t (src/mcmc.cpp:295) from the weights of step t - 1.  Sharded systematic runs
+// need slot[t-1].sum_q = the GLOBAL mass and slot[t-1].cdf_offset = the mass on lower ranks.
+extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    CUSMC_REQUIRE(ctx, t >= 1 && t < cfg.T && f->next_t == t, "resample(t) follows weigh(t - 1)");
+    const cusmc_filter_draws &dr = f->draws;
+    const int64_t n = f->n, N = cfg.N;
+    const size_t off = (size_t)(t - 1);
+    const bool sharded = f->world > 1;
+    if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
+        const double *u = dr.u_dev ? dr.u_dev + off * n * cfg.B : nullptr;
+        const uint32_t *j = dr.j_dev ? dr.j_dev + off * n * cfg.B : nullptr;
+        return cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log,
+                                       f->lo, n, sharded ? &f->peer_lw : nullptr);
+    }
+    StepSlot *prev = &f->slots[t - 1];
+    if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
+        const double u0 = dr.u0_host ? dr.u0_host[off]
+                                     : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+        return cusmc_launch_scan(ctx, f->lw, 1, &prev->lw_max, n, N, f->shift, &prev->sum_q,
+                                 sharded ? &prev->cdf_offset : nullptr, f->scan_state, nullptr, f->anc, f->lo,
+                                 0, N, u0, sharded ? &f->peer_anc : nullptr);
+    }
+    CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &prev->lw_max, n, N, f->shift, &prev->sum_q, nullptr,
+                                  f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0, nullptr));
+    const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
+    return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc);
+}
+
+// Propagate and reweight, fused (src/mcmc.cpp:298-307).  Sharded: every rank's ancestors of step t
+// and state of step t - 1 must be complete (barrier after resample).
+extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    CUSMC_REQUIRE(ctx, t >= 1 && t < cfg.T && f->next_t == t, "propagate(t) follows resample(t)");
+    const cusmc_filter_draws &dr = f->draws;
+    const int d = cfg.d, dy = cfg.dy;
+    const int64_t n = f->n;
+    const size_t off = (size_t)(t - 1);
+    double c[CUSMC_MAX_DIM];
+    whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
+    StepArgs a{};
+    a.x_new = f->x[f->cur ^ 1];
+    a.x_prev = f->x[f->cur];
+    a.anc = f->anc;
+    a.xi = dr.xi_dev ? dr.xi_dev + off * n * d : nullptr;
+    a.chi = dr.chi_dev ? dr.chi_dev + off * n * d : nullptr;
+    a.lw = f->lw;
+    a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
+    a.n_out = n;
+    a.ld_new = a.ld_prev = f->per;
+    a.ld_noise = n;
+    a.i0 = f->lo;
+    a.seed = cfg.seed;
+    a.step = (uint64_t)t;
+    a.nu = cfg.nu;
+    a.d = d;
+    a.dy = dy;
+    a.kind = cfg.kind;
+    a.has_prev = 1;
+    a.rng_stream = CUSMC_STREAM_NORMAL;
+    if (f->world > 1) {
+        a.world = f->world;
+        a.per_rank = (uint32_t)f->per;
+        for (int r = 0; r < f->world; ++r) a.x_prev_peer[r] = (const double *)f->peer_x[f->cur].ptr[r];
+    }
+    CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
+                                  f->ep, a, a.xi == nullptr));
+    f->cur ^= 1;
+    f->next_t = t + 1;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_mark(cusmc_filter *f, int which)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_CUDA(f->ctx, cudaEventRecord(which ? f->ev1 : f->ev0, f->ctx->stream));
+    if (which) f->ran = true;
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, f->world == 1, "a sharded filter is driven phase by phase (cusmc_b200/sharded.py)");
+    CUSMC_CHECK(cusmc_filter_begin(f, draws));
+    CUSMC_CHECK(cusmc_filter_weigh(f, 0));
+    CUSMC_CHECK(cusmc_filter_mark(f, 0));
+    for (int t = 1; t < f->cfg.T; ++t) {
+        CUSMC_CHECK(cusmc_filter_resample(f, t));
+        CUSMC_CHECK(cusmc_filter_propagate(f, t));
+        CUSMC_CHECK(cusmc_filter_weigh(f, t));
+    }
+    return cusmc_filter_mark(f, 1);
 }
 
 extern "C" double cusmc_filter_last_ms(const cusmc_filter *f)
@@ -767,13 +930,13 @@ extern "C" int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *
     if (!f) return CUSMC_ERR_INVALID;
     cusmc_ctx *ctx = f->ctx;
     CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history, "history was not kept");
-    const size_t TN = (size_t)f->cfg.T * f->cfg.N;
+    const size_t TN = (size_t)f->cfg.T * (size_t)f->n;   // this rank's shard
     CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (x_aos) CUSMC_CUDA(ctx, cudaMemcpy(x_aos, f->hist_x, sizeof(double) * TN * f->cfg.d, cudaMemcpyDeviceToHost));
     if (w) CUSMC_CUDA(ctx, cudaMemcpy(w, f->hist_w, sizeof(double) * TN, cudaMemcpyDeviceToHost));
     if (a) {
         CUSMC_CUDA(ctx, cudaMemcpy(a, f->hist_a, sizeof(uint32_t) * TN, cudaMemcpyDeviceToHost));
-        for (int64_t i = 0; i < f->cfg.N; ++i) a[i] = (uint32_t)i;   // row t = 0: identity
+        for (int64_t i = 0; i < f->n; ++i) a[i] = (uint32_t)(f->lo + i);   // row t = 0: identity
     }
     return CUSMC_OK;
 }

@@ -27,6 +27,12 @@ struct StepArgs {
     int64_t own_lo, own_n, n_own_children, ld_side;
     double *side;
     int sharded;
+    // peer form (world > 1): anc holds GLOBAL parent ids, parent g lives on rank g / per_rank at
+    // column g % per_rank of that rank's state buffer (leading dimension ld_prev on every rank),
+    // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.
+    const double *x_prev_peer[CUSMC_MAX_PEERS];
+    uint32_t per_rank;
+    int world;
 };
 
 // G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no

@@ -115,6 +115,10 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         }
         if (a.has_prev) {
             const double *src = a.x_prev + parent;
+            if (a.world > 1) {
+                const uint32_t g = (uint32_t)parent, r = g / a.per_rank;
+                src = a.x_prev_peer[r] + (g - r * a.per_rank);
+            }
 #pragma unroll
             for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
         } else {

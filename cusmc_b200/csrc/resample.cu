@@ -21,9 +21,26 @@ constexpr int kThreads = 256;
 // ------------------------------------------------------------------------------------------
 // Metropolis ancestor resampler
 // ------------------------------------------------------------------------------------------
-template <bool PREDRAWN>
+// Sharded runs: the weight vector is the concatenation of every rank's shard (per_rank slots
+// each), read through peer-mapped pointers over NVLink.
+struct PeerWeights {
+    const double *w[CUSMC_MAX_PEERS];
+    uint32_t per_rank;
+};
+
+template <bool PEERS>
+__device__ __forceinline__ double weight_at(const double *__restrict__ w, const PeerWeights &pw, uint32_t idx)
+{
+    if (PEERS) {
+        const uint32_t r = idx / pw.per_rank;
+        return __ldg(pw.w[r] + (idx - r * pw.per_rank));
+    }
+    return __ldg(w + idx);
+}
+
+template <bool PREDRAWN, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
-metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w,
+metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const PeerWeights pw,
                   const double *__restrict__ u, const uint32_t *__restrict__ j, uint64_t seed,
                   uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out)
 {
@@ -31,7 +48,7 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w,
     if (t >= n_out) return;
     const int64_t i = i0 + t;              // global particle index (i0 = 0 on one GPU)
     uint32_t k = (uint32_t)i;
-    double wk = __ldg(w + i);
+    double wk = weight_at<PEERS>(w, pw, (uint32_t)i);
     for (int n = 0; n < B; ++n) {
         double un;
         uint32_t jn;
@@ -43,7 +60,7 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w,
             un = cusmc_u01(r.v[0], r.v[1]);
             jn = (uint32_t)cusmc_uint_below(r.v[2], r.v[3], (uint64_t)N);
         }
-        const double wj = __ldg(w + jn);
+        const double wj = weight_at<PEERS>(w, pw, jn);
         // linear: u <= w_j / w_k (0/0 = NaN rejects, x/0 = inf accepts, as on the CPU);
         // log   : u <= exp(lw_j - lw_k) with the reproducible exp.
         const double ratio = is_log ? cusmc_det_exp(wj - wk) : wj / wk;
@@ -248,6 +265,8 @@ struct ScanArgs {
     const unsigned long long *tile_state;  // weigh_kernel's output: [1 + b] = exclusive prefix of tile b
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
+    uint32_t *anc_peer[CUSMC_MAX_PEERS];   // PEERS: rank r's ancestor array (child slots r*per_rank ..)
+    uint32_t per_rank;
     int64_t N, N_global, j0, out_lo, out_n;
     double u0;
     int shift, is_log;
@@ -255,6 +274,20 @@ struct ScanArgs {
 
 // Inclusive CDF of the fixed-point weights and, fused in, the systematic offspring scatter:
 // parent j owns the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.
+// PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
+// owning rank's ancestor array through its peer-mapped pointer (4 bytes per child over NVLink).
+template <bool PEERS>
+__device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint64_t child, uint64_t lo_lim, uint32_t parent)
+{
+    if (PEERS) {
+        const uint32_t c = (uint32_t)child, r = c / p.per_rank;
+        p.anc_peer[r][c - r * p.per_rank] = parent;
+    } else {
+        p.anc_out[child - lo_lim] = parent;
+    }
+}
+
+template <bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 scan_resample_kernel(const ScanArgs p)
 {
@@ -299,7 +332,7 @@ scan_resample_kernel(const ScanArgs p)
                 if (base_idx + r < p.N) p.cdf_out[base_idx + r] = before + c[r];
         }
     }
-    if (!p.anc_out) return;
+    if (!PEERS && !p.anc_out) return;
     const uint64_t T = *p.total;
     if (T == 0) return;                               // degenerate: the host reports it
     uint64_t r0 = (uint64_t)(p.u0 * (double)T);
@@ -321,7 +354,7 @@ scan_resample_kernel(const ScanArgs p)
         // small families: the owning thread writes them; large ones: the whole warp helps
         const bool big = b > a && b - a > 8;
         if (!big)
-            for (; a < b; ++a) p.anc_out[a - lo_lim] = parent;
+            for (; a < b; ++a) put_ancestor<PEERS>(p, a, lo_lim, parent);
         unsigned bigmask = __ballot_sync(0xffffffffu, big);
         while (bigmask) {
             const int src = __ffs(bigmask) - 1;
@@ -329,7 +362,7 @@ scan_resample_kernel(const ScanArgs p)
             const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
             const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
             const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
-            for (uint64_t i = sa + lane; i < sb; i += 32) p.anc_out[i - lo_lim] = sp;
+            for (uint64_t i = sa + lane; i < sb; i += 32) put_ancestor<PEERS>(p, i, lo_lim, sp);
         }
         k_prev = k_here;
         c_prev = c[r];
@@ -386,14 +419,22 @@ int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n)
 
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out)
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers)
 {
     if (n_out == 0) return CUSMC_OK;
     const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
-    if (u)
-        metropolis_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(a, w, u, j, seed, step, N, B, is_log, i0, n_out);
+    PeerWeights pw{};
+    if (peers) {
+        for (int r = 0; r < peers->world; ++r) pw.w[r] = (const double *)peers->ptr[r];
+        pw.per_rank = (uint32_t)peers->per_rank;
+        if (u)
+            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+        else
+            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+    } else if (u)
+        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
     else
-        metropolis_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(a, w, u, j, seed, step, N, B, is_log, i0, n_out);
+        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -431,10 +472,10 @@ int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double 
                       int64_t N_global, int shift, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *tile_state,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
-                      int64_t out_n, double u0)
+                      int64_t out_n, double u0, const CusmcPeers *peers)
 {
     if (N == 0) return CUSMC_OK;
-    ScanArgs p;
+    ScanArgs p{};
     p.w = w;
     p.wmax = max_dev;
     p.total = (const unsigned long long *)total_dev;
@@ -451,7 +492,15 @@ int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double 
     p.shift = shift;
     p.is_log = is_log;
     const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
-    scan_resample_kernel<<<tiles, kThreads, 0, ctx->stream>>>(p);
+    if (peers) {
+        for (int r = 0; r < peers->world; ++r) p.anc_peer[r] = (uint32_t *)peers->ptr[r];
+        p.per_rank = (uint32_t)peers->per_rank;
+        p.out_lo = 0;
+        p.out_n = N_global;
+        scan_resample_kernel<true><<<tiles, kThreads, 0, ctx->stream>>>(p);
+    } else {
+        scan_resample_kernel<false><<<tiles, kThreads, 0, ctx->stream>>>(p);
+    }
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -482,7 +531,7 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
     CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
     CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
-    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N);
+    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr);
 }
 
 extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev)
@@ -553,7 +602,7 @@ extern "C" int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int i
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N, N_global, tile_prefix_dev, &state));
     return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N, N_global, cusmc_fixed_shift(N_global),
-                             nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0);
+                             nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0, nullptr);
 }
 
 extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
@@ -571,7 +620,7 @@ extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N_local, N_global, tile_prefix_dev, &state));
     return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N_local, N_global, cusmc_fixed_shift(N_global),
-                             total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo, out_n, u0);
+                             total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo, out_n, u0, nullptr);
 }
 
 extern "C" int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cdf_dev, int64_t N,

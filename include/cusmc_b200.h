@@ -56,6 +56,8 @@ enum cusmc_resampler {                                    /* Resamplers[...], sr
 };
 
 #define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
+#define CUSMC_MAX_PEERS 8           /* ranks (GPUs of one NVLink domain) of a sharded filter */
+#define CUSMC_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
 
 typedef struct cusmc_ctx cusmc_ctx;
 
@@ -292,6 +294,9 @@ typedef struct cusmc_filter_config {
     const double *m0, *C0, *F, *G, *V, *W;   /* host, column-major */
     int keep_history;     /* 1: keep x (T x N x d), w (T x N), a (T x N) on the device */
     int summary;          /* 1: per-step weighted posterior mean (one extra pass over the state) */
+    /* Sharded runs (one process per GPU): N is the GLOBAL particle count; rank r of `world` owns the
+     * global slots r*per .. min((r+1)*per, N) - 1, per = ceil(N / world).  world <= 1: one GPU. */
+    int rank, world;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):
@@ -309,6 +314,40 @@ int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_fi
 int cusmc_filter_destroy(cusmc_filter *f);
 /* Runs t = 0 (initialize) then steps 1 .. T-1 on the stream; returns after enqueueing. */
 int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
+/*
+ * The same run, phase by phase -- what cusmc_filter_run chains on one GPU:
+ *     begin;  weigh(0);  for t = 1 .. T-1:  resample(t);  propagate(t);  weigh(t)
+ * A sharded filter (cfg.world > 1) is driven through these by the binding, which puts the scalar
+ * exchanges between the phases (cusmc_b200/sharded.py; NCCL on the slot words below):
+ *     after begin / propagate(t) : all-reduce MAX of slot[t] word 0 (the log-weight max)
+ *     after weigh(t)             : all-gather of slot[t] words 1..3 (this rank's fixed-point sums);
+ *                                  then words 1..3 := sums over ranks, word 4 := sum of word 1 over
+ *                                  lower ranks (this rank's offset in the global CDF)
+ *     after resample(t)          : barrier -- parents wrote their children's ancestor entries
+ *                                  straight into the owning rank's array (peer stores over NVLink);
+ *                                  propagate(t) then gathers parent states from the owning rank's
+ *                                  state buffer (peer loads).  Ancestors are GLOBAL indices and the
+ *                                  noise is keyed by the global slot, so a sharded run reproduces the
+ *                                  single-GPU run bit for bit.
+ * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset; 3 spare }.
+ * Injected draws of a sharded run are this rank's shard (leading dimension = its particle count).
+ */
+int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws);
+int cusmc_filter_weigh(cusmc_filter *f, int t);
+int cusmc_filter_resample(cusmc_filter *f, int t);
+int cusmc_filter_propagate(cusmc_filter *f, int t);
+/* Records the start (which = 0) / end (1) event cusmc_filter_last_ms measures between. */
+int cusmc_filter_mark(cusmc_filter *f, int which);
+int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev);
+/* Per-step moment sums [T][2 + d] = { sum w, sum w^2, sum w x_k } of this rank's shard (device);
+ * a sharded run all-reduces them (SUM) before cusmc_filter_get_summary. */
+int cusmc_filter_moments_dev(cusmc_filter *f, double **moments_dev);
+/* Peer mapping: export this rank's 4 buffers (state x 2, ancestors, weights) as
+ * 4 x CUSMC_IPC_HANDLE_BYTES bytes; after an all-gather of those, attach maps every other
+ * rank's buffers (cudaIpcOpenMemHandle; all_handles = world x 4 x 64 bytes, rank-major). */
+int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles);
+int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all_handles);
+
 /* Per-step outputs copied to the host (any pointer may be NULL):
  * mean [T][d] weighted posterior mean, ess [T], loglik [T] (log of the mean weight). */
 int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *ess, double *loglik);
