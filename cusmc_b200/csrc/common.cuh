@@ -117,3 +117,15 @@ __device__ __forceinline__ double double_from_ordered(unsigned long long o)
     unsigned long long b = (o & 0x8000000000000000ull) ? (o & 0x7FFFFFFFFFFFFFFFull) : ~o;
     return __longlong_as_double((long long)b);
 }
+
+// Warp-wide maximum of finite-or--inf doubles (callers map NaN / +inf to -inf first): two
+// REDUX.MAX on the halves of the order-preserving integer image instead of five rounds of
+// 64-bit shuffles + compares.  Every lane gets the result.
+__device__ __forceinline__ double warp_max_double(double v)
+{
+    const unsigned long long o = ordered_from_double(v);
+    const unsigned hi = (unsigned)(o >> 32), lo = (unsigned)o;
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    return double_from_ordered(((unsigned long long)mhi << 32) | mlo);
+}

@@ -182,15 +182,12 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
     }
     if (a.lw_max) {
         double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        m = warp_max_double(m);
         __shared__ double sm[kThreads / 32];
         if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
         __syncthreads();
         if (threadIdx.x < 32) {
-            m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY;
-#pragma unroll
-            for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+            m = warp_max_double(threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY);
             if (threadIdx.x == 0) atomic_max_double(a.lw_max, m);
         }
     }

@@ -101,15 +101,12 @@ weights_max_kernel(const double *__restrict__ w, int64_t N, double *__restrict__
         const double v = __ldg(w + i);
         if (v > m && v < INFINITY) m = v;   // NaN and +inf never become the reference weight
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    m = warp_max_double(m);
     __shared__ double sm[kThreads / 32];
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
     __syncthreads();
     if (threadIdx.x < 32) {
-        m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY;
-#pragma unroll
-        for (int o = 4; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+        m = warp_max_double(threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : -INFINITY);
         if (threadIdx.x == 0) atomic_max_double(out, m);
     }
 }

@@ -50,34 +50,60 @@ CUSMC_HD uint64_t cusmc_double_to_bits(double d)
 /* 2^e for -1022 <= e <= 1023 */
 CUSMC_HD double cusmc_pow2i(int e) { return cusmc_bits_to_double((uint64_t)(e + 1023) << 52); }
 
-/* exp(x): range reduction x = k ln2 + r with a two-term ln2, degree-13 Taylor polynomial
- * in Horner/fma form, exact scaling by 2^k (gradual underflow handled in two steps). */
+/* Taylor coefficients 1/13! .. 1/0! of exp.  On the device they sit in constant memory so each
+ * DFMA of the Horner chain takes its coefficient as a constant-bank operand (no register or
+ * uniform-register moves); on the host they are the same correctly rounded quotients. */
+#define CUSMC_EXP_COEFS                                                                          \
+    { 1.0 / 6227020800.0, 1.0 / 479001600.0, 1.0 / 39916800.0, 1.0 / 3628800.0, 1.0 / 362880.0,  \
+      1.0 / 40320.0, 1.0 / 5040.0, 1.0 / 720.0, 1.0 / 120.0, 1.0 / 24.0, 1.0 / 6.0, 0.5, 1.0, 1.0 }
+#if defined(__CUDACC__)
+static __constant__ double cusmc_exp_coef_dev[14] = CUSMC_EXP_COEFS;
+#endif
+static const double cusmc_exp_coef_host[14] = CUSMC_EXP_COEFS;
+#if defined(__CUDA_ARCH__)
+#define CUSMC_EXP_C(i) cusmc_exp_coef_dev[i]
+#else
+#define CUSMC_EXP_C(i) cusmc_exp_coef_host[i]
+#endif
+
+/* The reduced exponential: x = k ln2 + r with a two-term ln2, degree-13 Taylor polynomial in
+ * Horner/fma form.  Returns p = exp(r) and k. */
+CUSMC_HD double cusmc_det_exp_core(double x, int *k_out)
+{
+    const double kf = rint(x * 1.4426950408889634074);
+    double r = fma(kf, -6.93147180369123816490e-01, x);
+    r = fma(kf, -1.90821492927058770002e-10, r);
+    double p = CUSMC_EXP_C(0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int i = 1; i < 14; ++i) p = fma(p, r, CUSMC_EXP_C(i));
+    *k_out = (int)kf;
+    return p;
+}
+
+/* exp(x) with exact scaling by 2^k (gradual underflow handled in two steps). */
 CUSMC_HD double cusmc_det_exp(double x)
 {
     if (x != x) return x;
     if (x > 709.782712893384) return cusmc_bits_to_double(0x7FF0000000000000ull);
     if (x < -745.2) return 0.0;
-    const double kf = rint(x * 1.4426950408889634074);
-    double r = fma(kf, -6.93147180369123816490e-01, x);
-    r = fma(kf, -1.90821492927058770002e-10, r);
-    double p = 1.0 / 6227020800.0;
-    p = fma(p, r, 1.0 / 479001600.0);
-    p = fma(p, r, 1.0 / 39916800.0);
-    p = fma(p, r, 1.0 / 3628800.0);
-    p = fma(p, r, 1.0 / 362880.0);
-    p = fma(p, r, 1.0 / 40320.0);
-    p = fma(p, r, 1.0 / 5040.0);
-    p = fma(p, r, 1.0 / 720.0);
-    p = fma(p, r, 1.0 / 120.0);
-    p = fma(p, r, 1.0 / 24.0);
-    p = fma(p, r, 1.0 / 6.0);
-    p = fma(p, r, 0.5);
-    p = fma(p, r, 1.0);
-    p = fma(p, r, 1.0);
-    const int k = (int)kf;
+    int k;
+    const double p = cusmc_det_exp_core(x, &k);
     if (k >= -1021 && k <= 1023) return p * cusmc_pow2i(k);
     if (k > 1023) return (p * cusmc_pow2i(k - 1)) * 2.0;
     return (p * cusmc_pow2i(k + 1022)) * cusmc_pow2i(-1022);
+}
+
+/* exp(x) for the weight image: x <= 0, and anything below 2^-62 may be flushed to zero (it
+ * truncates to q = 0 for every shift <= 61).  Bit-identical to cusmc_det_exp on [-43.5, 0];
+ * NaN, -inf and x < -43.5 give 0.  One compare, one scale: the hot form. */
+CUSMC_HD double cusmc_det_exp_unit(double x)
+{
+    if (!(x >= -43.5)) return 0.0;
+    int k;
+    const double p = cusmc_det_exp_core(x, &k);
+    return p * cusmc_pow2i(k);
 }
 
 /* log(x): x = m 2^e, m in [sqrt(1/2), sqrt 2), log m = 2 atanh(s), s = (m-1)/(m+1). */
@@ -221,9 +247,13 @@ CUSMC_HD void cusmc_det_sincospif(float t, float *s_out, float *c_out)
     pc = fmaf(pc, x2, 4.16666679e-2f);                  /*  1/4! */
     pc = fmaf(pc, x2, -0.5f);
     const float cs = fmaf(x2, pc, 1.0f);
-    const int n = ((int)nf) & 3;
-    *s_out = (n == 0) ? sn : (n == 1) ? cs : (n == 2) ? -sn : -cs;
-    *c_out = (n == 0) ? cs : (n == 1) ? -sn : (n == 2) ? -cs : sn;
+    /* quadrant n: (s, c) = (sn, cs), (cs, -sn), (-sn, -cs), (-cs, sn) -- a swap on odd n and two
+     * sign flips, written on the bit patterns so it compiles to selects and XORs (no branches) */
+    const uint32_t n = (uint32_t)(int)nf;
+    const uint32_t sb = cusmc_float_to_bits((n & 1u) ? cs : sn);
+    const uint32_t cb = cusmc_float_to_bits((n & 1u) ? sn : cs);
+    *s_out = cusmc_bits_to_float(sb ^ ((n & 2u) << 30));
+    *c_out = cusmc_bits_to_float(cb ^ (((n + 1u) & 2u) << 30));
 }
 
 /* ---- fixed-point weight image ------------------------------------------------------------
@@ -256,7 +286,7 @@ CUSMC_HD double cusmc_unit_from_linear(double w, double wmax)
 CUSMC_HD double cusmc_unit_from_log(double lw, double lmax)
 {
     if (!(lw <= lmax)) return 0.0; /* NaN or above the max */
-    return cusmc_det_exp(lw - lmax);
+    return cusmc_det_exp_unit(lw - lmax);
 }
 
 #endif /* CUSMC_DETMATH_H */

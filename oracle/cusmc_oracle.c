@@ -22,6 +22,15 @@
 
 #define A_(M, r, c, ld) ((M)[(size_t)(c) * (size_t)(ld) + (size_t)(r)])
 
+void orc_set_num_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

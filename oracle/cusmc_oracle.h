@@ -209,6 +209,7 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
 
 /* Threads the batched functions will use (OpenMP), for bench reporting. */
 int orc_num_threads(void);
+void orc_set_num_threads(int n);   /* launchers such as torchrun export OMP_NUM_THREADS=1 */
 
 #ifdef __cplusplus
 }

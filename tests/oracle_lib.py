@@ -409,6 +409,13 @@ class Oracle:
     def num_threads(self):
         return self.lib.orc_num_threads()
 
+    def use_all_cores(self):
+        """torchrun exports OMP_NUM_THREADS=1; a CPU baseline is timed on every host core."""
+        import os
+        n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.lib.orc_set_num_threads(int(n))
+        return self.num_threads()
+
 
 _ORACLE = None
 
