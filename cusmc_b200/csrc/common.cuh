@@ -30,6 +30,9 @@ struct cusmc_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // second lane of the pipelined host-pointer calls (created on first use)
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_aux = nullptr;
     uint64_t launches = 0;
     double last_ms = 0.0;
     std::string err;
@@ -91,6 +94,7 @@ inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
 
 int cusmc_scratch(cusmc_ctx *ctx, int slot, size_t bytes, void **out);
 int cusmc_pinned(cusmc_ctx *ctx, size_t bytes, void **out);
+int cusmc_aux_stream(cusmc_ctx *ctx);
 
 // ---- device helpers ----------------------------------------------------------------
 // Streaming (read-once / write-once) accesses: keep them out of L1 and mark evict-first.

@@ -42,6 +42,8 @@ extern "C" int cusmc_ctx_destroy(cusmc_ctx *ctx)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     cusmc_density_cache_free(ctx);
+    if (ctx->ev_aux) cudaEventDestroy(ctx->ev_aux);
+    if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -89,6 +91,15 @@ int cusmc_scratch(cusmc_ctx *ctx, int slot, size_t bytes, void **out)
         ctx->scratch_cap[slot] = cap;
     }
     *out = ctx->scratch[slot];
+    return CUSMC_OK;
+}
+
+int cusmc_aux_stream(cusmc_ctx *ctx)
+{
+    if (ctx->aux_stream) return CUSMC_OK;
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    CUSMC_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+    CUSMC_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     return CUSMC_OK;
 }
 

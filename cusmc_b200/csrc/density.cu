@@ -8,6 +8,7 @@
 #include "density.cuh"
 #include "hostmath.h"
 
+#include <algorithm>
 #include <new>
 #include <vector>
 
@@ -275,6 +276,11 @@ extern "C" int cusmc_logpdf_dev(cusmc_ctx *ctx, int kind, int want_log, const do
     return cusmc_density_launch(ctx, true, d, d, *W, mu, nullptr, ep, x_dev, layout, N, ld, out_dev);
 }
 
+// Host-pointer entry point.  The call is PCIe-bound (8d bytes in, 8 out per point, a kernel that
+// needs ~1 % of the copy time), so it is pipelined: the batch is cut into chunks that alternate
+// between two streams, and a chunk's kernel and device->host copy run under the next chunk's
+// host->device copy (the two directions use different copy engines).  With pinned host buffers
+// the call takes the time of the host->device copy alone.
 extern "C" int cusmc_logpdf(cusmc_ctx *ctx, int kind, int want_log, const double *x_host,
                             int layout, int64_t N, int64_t ld, int d, const double *mu,
                             const double *sigma, float nu, double *out_host)
@@ -286,20 +292,49 @@ extern "C" int cusmc_logpdf(cusmc_ctx *ctx, int kind, int want_log, const double
     if (N == 0) return CUSMC_OK;
     if (layout == CUSMC_AOS) ld = N;
     CUSMC_REQUIRE(ctx, ld >= N, "ld < N");
-    const size_t in_bytes = sizeof(double) * (layout == CUSMC_AOS ? (size_t)N * d : (size_t)ld * d);
+    constexpr int64_t kChunk = 1 << 17;                      // points per chunk (16 MiB at d = 16)
+    const int64_t n_chunks = (N + kChunk - 1) / kChunk;
+    const int64_t cpts = n_chunks > 1 ? kChunk : N;          // device columns per buffer
     void *xd = nullptr, *od = nullptr;
-    CUSMC_CHECK(cusmc_scratch(ctx, 0, in_bytes, &xd));
-    CUSMC_CHECK(cusmc_scratch(ctx, 1, sizeof(double) * (size_t)N, &od));
-    CUSMC_CUDA(ctx, cudaMemcpyAsync(xd, x_host, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
-    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    CUSMC_CHECK(cusmc_logpdf_dev(ctx, kind, want_log, (const double *)xd, layout, N, ld, d, mu, sigma,
-                                 nu, (double *)od));
-    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
-    CUSMC_CUDA(ctx, cudaMemcpyAsync(out_host, od, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost,
-                                    ctx->stream));
-    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CUSMC_CHECK(cusmc_scratch(ctx, 0, sizeof(double) * (size_t)cpts * d * 2, &xd));
+    CUSMC_CHECK(cusmc_scratch(ctx, 1, sizeof(double) * (size_t)cpts * 2, &od));
+    CUSMC_CHECK(cusmc_aux_stream(ctx));
+    cudaStream_t main_stream = ctx->stream, lanes[2] = {ctx->stream, ctx->aux_stream};
+    CUSMC_CUDA(ctx, cudaEventRecord(ctx->ev0, main_stream));
+    if (n_chunks > 1) CUSMC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev0, 0));
+    int rc = CUSMC_OK;
+    for (int64_t c = 0; c < n_chunks && rc == CUSMC_OK; ++c) {
+        const int lane = (int)(c & 1);
+        const int64_t i0 = c * kChunk, n = std::min<int64_t>(kChunk, N - i0);
+        double *xb = (double *)xd + (size_t)lane * cpts * d, *ob = (double *)od + (size_t)lane * cpts;
+        cudaStream_t st = lanes[lane];
+        cudaError_t e;
+        if (layout == CUSMC_AOS)
+            e = cudaMemcpyAsync(xb, x_host + (size_t)i0 * d, sizeof(double) * (size_t)n * d, cudaMemcpyHostToDevice, st);
+        else
+            e = cudaMemcpy2DAsync(xb, sizeof(double) * (size_t)cpts, x_host + i0, sizeof(double) * (size_t)ld,
+                                  sizeof(double) * (size_t)n, (size_t)d, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess) {
+            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "host->device copy failed: %s", cudaGetErrorString(e));
+            break;
+        }
+        ctx->stream = st;                                      // launch this chunk on its lane
+        rc = cusmc_logpdf_dev(ctx, kind, want_log, xb, layout, n, cpts, d, mu, sigma, nu, ob);
+        ctx->stream = main_stream;
+        if (rc != CUSMC_OK) break;
+        e = cudaMemcpyAsync(out_host + i0, ob, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, st);
+        if (e != cudaSuccess) rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "device->host copy failed: %s", cudaGetErrorString(e));
+    }
+    if (n_chunks > 1) {                                        // join the second lane
+        cudaEventRecord(ctx->ev_aux, ctx->aux_stream);
+        cudaStreamWaitEvent(main_stream, ctx->ev_aux, 0);
+    }
+    cudaEventRecord(ctx->ev1, main_stream);
+    cudaError_t e = cudaStreamSynchronize(main_stream);
+    if (rc != CUSMC_OK) return rc;
+    if (e != cudaSuccess) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_logpdf: %s", cudaGetErrorString(e));
     float ms = 0.f;
     CUSMC_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    ctx->last_ms = ms;
+    ctx->last_ms = ms;   // whole pipelined call: copies and kernels overlap
     return CUSMC_OK;
 }

@@ -72,7 +72,8 @@ int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream);
 int cusmc_ctx_synchronize(cusmc_ctx *ctx);
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 uint64_t cusmc_ctx_launch_count(const cusmc_ctx *ctx);
-/* Device time in ms of the last host-pointer call's kernels (CUDA events on the stream). */
+/* Device time in ms of the last host-pointer call between its first and last enqueued operation
+ * (CUDA events on the stream; cusmc_logpdf pipelines copies and kernels, so this is the whole call). */
 double cusmc_ctx_last_kernel_ms(const cusmc_ctx *ctx);
 
 /* ---- a1/a2: batched density, shared covariance ------------------------------- */

@@ -115,6 +115,21 @@ def test_logpdf_edge_cases(ctx, orc):
     assert np.all(ctx.logpdf("mvn", far, None, sigma, log=False) == 0.0)
 
 
+@pytest.mark.parametrize("N", [(1 << 17) + 1, 3 * (1 << 17) + 777])
+def test_logpdf_host_call_is_chunk_invariant(ctx, orc, N):
+    """cusmc_logpdf pipelines 2^17-point chunks over two streams: ragged last chunk, both layouts,
+    every point against the oracle and AoS == SoA bit for bit."""
+    rng = np.random.default_rng(N)
+    d = 5
+    sigma, mu = spd(rng, d), rng.standard_normal(d)
+    x = rng.standard_normal((N, d))
+    got_aos = ctx.logpdf("mvt", x, mu, sigma, nu=4.0)
+    got_soa = ctx.logpdf("mvt", np.ascontiguousarray(x.T), mu, sigma, nu=4.0, layout=0)
+    assert np.array_equal(got_aos, got_soa)
+    want = orc.pdf_batch("mvt", x, mu, sigma, nu=4.0, log=True)
+    assert relerr(got_aos, want) < 1e-10
+
+
 def test_logpdf_full_size_properties(ctx, orc):
     """BASELINE config: N = 2^20 points, d = 16, shared covariance.  Size-independent checks:
     translation invariance, a checksum against the oracle on a strided sample, agreement of the
