@@ -726,7 +726,7 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     init_slots_kernel<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
     CUSMC_LAUNCHED(ctx);
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
-    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, cusmc_scan_state_bytes(f->per), st));
+    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, sizeof(uint64_t), st));   // the arrival counter
     // t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N
     f->cur = 0;
     StepArgs a{};
@@ -769,7 +769,7 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
     cudaStream_t st = ctx->stream;
     if (f->is_log)
         CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
-                                             f->scan_state));
+                                             f->scan_state, cfg.summary != 0));
     if (cfg.summary && n > 0) {
         const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
         moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
@@ -809,12 +809,11 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
         const double u0 = dr.u0_host ? dr.u0_host[off]
                                      : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
-        return cusmc_launch_scan(ctx, f->lw, 1, &prev->lw_max, n, N, f->shift, &prev->sum_q,
-                                 sharded ? &prev->cdf_offset : nullptr, f->scan_state, nullptr, f->anc, f->lo,
-                                 0, N, u0, sharded ? &f->peer_anc : nullptr);
+        return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
+                                 nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr);
     }
-    CUSMC_CHECK(cusmc_launch_scan(ctx, f->lw, 1, &prev->lw_max, n, N, f->shift, &prev->sum_q, nullptr,
-                                  f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0, nullptr));
+    CUSMC_CHECK(cusmc_launch_scan(ctx, n, N, &prev->sum_q, nullptr, f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0,
+                                  nullptr));
     const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
     return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc);
 }

@@ -117,19 +117,27 @@ __device__ __forceinline__ double unit_weight(double w, double wmax, int is_log)
 }
 
 // ------------------------------------------------------------------------------------------
-// Normalisation sums and the tile prefixes of the fixed-point weight image.
+// The weight image: normalisation sums, tile prefixes and tile-local CDF of the fixed-point weights.
 //
 // A tile is kTile = 2048 consecutive weights; thread t of the block owns the 8 consecutive weights
-// 8t .. 8t+7 (four 128-bit loads).  Tile state, uint64 words:
-//     [0]      arrival counter -- zero when a launch starts, reset to zero by its last block
-//     [1 + b]  sum of tile b, turned IN PLACE into the exclusive prefix over tiles by the last
-//              block to finish (one block scanning N/2048 integers: ~1 us at N = 8 Mi).
-// Because the per-tile totals are known before the resampling pass starts, that pass needs no
-// decoupled look-back (no spinning, no tile ordering, no state to clear between steps): its tiles
-// are independent.  Integer sums: every order of arrival gives the same bits.
+// 8t .. 8t+7 (four 128-bit loads).  Workspace layout, uint64 words (cusmc_scan_state_bytes):
+//     [0]            arrival counter -- zero when a launch starts, reset to zero by its last block
+//     [1 + b]        sum of tile b, turned IN PLACE into the exclusive prefix over tiles by the last
+//                    block to finish (one block scanning N/2048 integers: ~1 us at N = 8 Mi)
+//     [H + i]        inclusive prefix of weight i INSIDE its tile (H = header words, even)
+// exp() is evaluated once per weight, here.  The resampling pass that follows needs neither the
+// weights nor a scan of its own: global CDF_i = offset + prefix[tile(i)] + local_i, one thread per
+// particle, tiles independent -- no decoupled look-back, no spinning, no state to clear between
+// steps.  Integer sums: every order of arrival gives the same bits.
 // ------------------------------------------------------------------------------------------
 constexpr int kTileItems = 8;
 constexpr int kTile = kThreads * kTileItems;    // 2048 weights per tile
+
+__host__ __device__ inline int64_t image_header_words(int64_t N)
+{
+    const int64_t tiles = (N + kTile - 1) / kTile;
+    return (tiles + 2 + 1) & ~(int64_t)1;       // counter + tiles + 1 spare, rounded to 16 bytes
+}
 
 __device__ __forceinline__ void load_tile_items(const double *__restrict__ w, int64_t base, int64_t N,
                                                 double (&v)[kTileItems])
@@ -152,48 +160,81 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
     if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = v;
     __syncthreads();
     unsigned long long t = 0;
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) t += sm[k];
-    __syncthreads();
     return t;
 }
 
+// FULL: also sum of squares and positive count (ESS); otherwise only what resampling needs.
+template <bool FULL>
 __global__ void __launch_bounds__(kThreads)
 weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict__ wmax_p, int64_t N,
-             int shift, unsigned long long *__restrict__ stats, unsigned long long *__restrict__ tile_state)
+             int shift, unsigned long long *__restrict__ stats, unsigned long long *__restrict__ image)
 {
     __shared__ unsigned long long sm[kThreads / 32];
     __shared__ int s_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double wmax = *wmax_p;
     const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
     double v[kTileItems];
     load_tile_items(w, base, N, v);
-    unsigned long long s1 = 0, s2 = 0, np = 0;
+    unsigned long long c[kTileItems];   // inclusive prefix within the thread
+    unsigned long long run = 0, s2 = 0, np = 0;
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
         const double wn = unit_weight(v[r], wmax, is_log);   // -inf padding -> 0
         const uint64_t q = cusmc_fixed_from_unit(wn, shift);
-        s1 += q;
-        s2 += cusmc_fixed_from_unit(wn * wn, shift);
-        np += q > 0;
-    }
-    s1 = block_sum_u64(s1, sm);
-    if (stats) {
-        s2 = block_sum_u64(s2, sm);
-        np = block_sum_u64(np, sm);
-        if (threadIdx.x == 0) {
-            atomicAdd(stats + 0, s1);
-            atomicAdd(stats + 1, s2);
-            atomicAdd(stats + 2, np);
+        run += q;
+        c[r] = run;
+        if (FULL) {
+            s2 += cusmc_fixed_from_unit(wn * wn, shift);
+            np += q > 0;
         }
     }
+    // block-wide exclusive prefix of the thread totals
+    unsigned long long inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sm[warp] = inc;
+    __syncthreads();
+    unsigned long long before = inc - run, tile_total = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        const unsigned long long t = sm[k];
+        if (k < warp) before += t;
+        tile_total += t;
+    }
+    // tile-local inclusive CDF (the workspace is padded to whole tiles: no bounds checks)
+    unsigned long long *local = image + image_header_words(N) + base;
+#pragma unroll
+    for (int r = 0; r < kTileItems / 2; ++r) {
+        ulonglong2 t;
+        t.x = before + c[2 * r];
+        t.y = before + c[2 * r + 1];
+        reinterpret_cast<ulonglong2 *>(local)[r] = t;
+    }
+    if (FULL) {
+        s2 = block_sum_u64(s2, sm);
+        np = block_sum_u64(np, sm);
+    }
     if (threadIdx.x == 0) {
-        tile_state[1 + blockIdx.x] = s1;
+        if (stats) {
+            atomicAdd(stats + 0, tile_total);
+            if (FULL) {
+                atomicAdd(stats + 1, s2);
+                atomicAdd(stats + 2, np);
+            }
+        }
+        image[1 + blockIdx.x] = tile_total;
         __threadfence();
-        s_last = atomicAdd(tile_state, 1ull) == (unsigned long long)gridDim.x - 1;
+        s_last = atomicAdd(image, 1ull) == (unsigned long long)gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
@@ -203,25 +244,24 @@ weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict_
     const int per = (n + kThreads - 1) / kThreads;
     const int lo = threadIdx.x * per, hi = min(lo + per, n);
     unsigned long long mine = 0;
-    for (int k = lo; k < hi; ++k) mine += __ldcg(tile_state + 1 + k);
-    // block exclusive scan of `mine`
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    unsigned long long inc = mine;
+    for (int k = lo; k < hi; ++k) mine += __ldcg(image + 1 + k);
+    inc = mine;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
+    __syncthreads();
     if (lane == 31) sm[warp] = inc;
     __syncthreads();
     unsigned long long off = inc - mine;
     for (int k = 0; k < warp; ++k) off += sm[k];
     for (int k = lo; k < hi; ++k) {
-        const unsigned long long t = __ldcg(tile_state + 1 + k);
-        tile_state[1 + k] = off;
+        const unsigned long long t = __ldcg(image + 1 + k);
+        image[1 + k] = off;
         off += t;
     }
-    if (threadIdx.x == 0) tile_state[0] = 0;
+    if (threadIdx.x == 0) image[0] = 0;
 }
 
 // #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
@@ -255,22 +295,17 @@ __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uin
 }
 
 struct ScanArgs {
-    const double *w;
-    const double *wmax;
     const unsigned long long *total;       // global fixed-point mass (device)
     const unsigned long long *cdf_offset;  // mass on lower shards, or NULL
-    const unsigned long long *tile_state;  // weigh_kernel's output: [1 + b] = exclusive prefix of tile b
+    const unsigned long long *image;       // weigh_kernel's workspace
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
     uint32_t *anc_peer[CUSMC_MAX_PEERS];   // PEERS: rank r's ancestor array (child slots r*per_rank ..)
     uint32_t per_rank;
     int64_t N, N_global, j0, out_lo, out_n;
     double u0;
-    int shift, is_log;
 };
 
-// Inclusive CDF of the fixed-point weights and, fused in, the systematic offspring scatter:
-// parent j owns the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.
 // PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
 // owning rank's ancestor array through its peer-mapped pointer (4 bytes per child over NVLink).
 template <bool PEERS>
@@ -284,51 +319,20 @@ __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint64_t child, 
     }
 }
 
+// Global CDF from the weight image and, fused in, the systematic offspring scatter: parent j owns
+// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  One thread per parent.
 template <bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 scan_resample_kernel(const ScanArgs p)
 {
-    __shared__ unsigned long long s_warp[kThreads / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double wmax = *p.wmax;
-    const int64_t base_idx = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
-    double v[kTileItems];
-    load_tile_items(p.w, base_idx, p.N, v);
-    uint64_t c[kTileItems];   // inclusive prefix within the thread
-    uint64_t run = 0;
-#pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
-        run += cusmc_fixed_from_unit(unit_weight(v[r], wmax, p.is_log), p.shift);
-        c[r] = run;
-    }
-    uint64_t inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint64_t t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
-    }
-    if (lane == 31) s_warp[warp] = inc;
-    __syncthreads();
-    uint64_t before = inc - run + p.tile_state[1 + blockIdx.x] + (p.cdf_offset ? *p.cdf_offset : 0ull);
-#pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k)
-        if (k < warp) before += s_warp[k];
-
-    if (p.cdf_out) {
-        if (base_idx + kTileItems <= p.N && (((uintptr_t)(p.cdf_out + base_idx)) & 15) == 0) {
-#pragma unroll
-            for (int r = 0; r < kTileItems / 2; ++r) {
-                ulonglong2 t;
-                t.x = before + c[2 * r];
-                t.y = before + c[2 * r + 1];
-                reinterpret_cast<ulonglong2 *>(p.cdf_out + base_idx)[r] = t;
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < kTileItems; ++r)
-                if (base_idx + r < p.N) p.cdf_out[base_idx + r] = before + c[r];
-        }
-    }
+    __shared__ unsigned long long s_k[kThreads];
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;      // local parent
+    const bool active = i < p.N;
+    const int64_t tile = ((int64_t)blockIdx.x * kThreads) / kTile;       // a block lies inside one tile
+    const unsigned long long *local = p.image + image_header_words(p.N);
+    const uint64_t base = p.image[1 + tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
+    const uint64_t C = base + (active ? __ldg(local + i) : 0ull);
+    if (p.cdf_out && active) p.cdf_out[i] = C;
     if (!PEERS && !p.anc_out) return;
     const uint64_t T = *p.total;
     if (T == 0) return;                               // degenerate: the host reports it
@@ -337,32 +341,36 @@ scan_resample_kernel(const ScanArgs p)
     const double ng_over_t = (double)p.N_global / (double)T;
     const double r0_over_t = (double)r0 / (double)T;
     const uint64_t Ng = (uint64_t)p.N_global;
+    // the offspring count is a pure function of the CDF value; the left neighbour's count comes
+    // through shared memory, the block's first thread evaluates its own
+    const uint64_t k_here = active ? offspring_below(C, Ng, T, r0, ng_over_t, r0_over_t) : 0;
+    s_k[threadIdx.x] = k_here;
+    __syncthreads();
+    uint64_t k_prev = 0;
+    if (threadIdx.x > 0) {
+        k_prev = s_k[threadIdx.x - 1];
+    } else if (active) {
+        const uint64_t Cprev = base + ((i % kTile) ? __ldg(local + i - 1) : 0ull);
+        k_prev = offspring_below(Cprev, Ng, T, r0, ng_over_t, r0_over_t);
+    }
     const uint64_t lo_lim = (uint64_t)p.out_lo, hi_lim = (uint64_t)(p.out_lo + p.out_n);
-    // the offspring count is a pure function of the CDF value: a weight of zero repeats its
-    // left neighbour's count and costs nothing
-    uint64_t k_prev = offspring_below(before, Ng, T, r0, ng_over_t, r0_over_t);
-    uint64_t c_prev = 0;
-#pragma unroll
-    for (int r = 0; r < kTileItems; ++r) {
-        const uint64_t k_here = c[r] != c_prev ? offspring_below(before + c[r], Ng, T, r0, ng_over_t, r0_over_t) : k_prev;
-        uint64_t a = k_prev < lo_lim ? lo_lim : k_prev;
-        const uint64_t b = k_here > hi_lim ? hi_lim : k_here;
-        const uint32_t parent = (uint32_t)(p.j0 + base_idx + r);
-        // small families: the owning thread writes them; large ones: the whole warp helps
-        const bool big = b > a && b - a > 8;
-        if (!big)
-            for (; a < b; ++a) put_ancestor<PEERS>(p, a, lo_lim, parent);
-        unsigned bigmask = __ballot_sync(0xffffffffu, big);
-        while (bigmask) {
-            const int src = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
-            const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
-            const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
-            for (uint64_t i = sa + lane; i < sb; i += 32) put_ancestor<PEERS>(p, i, lo_lim, sp);
-        }
-        k_prev = k_here;
-        c_prev = c[r];
+    // threads past the end own the empty range and stay to help with large families
+    uint64_t a = !active ? 0 : (k_prev < lo_lim ? lo_lim : k_prev);
+    const uint64_t b = !active ? 0 : (k_here > hi_lim ? hi_lim : k_here);
+    const uint32_t parent = (uint32_t)(p.j0 + i);
+    // small families: the owning thread writes them; large ones: the whole warp helps
+    const bool big = b > a && b - a > 8;
+    if (!big)
+        for (; a < b; ++a) put_ancestor<PEERS>(p, a, lo_lim, parent);
+    unsigned bigmask = __ballot_sync(0xffffffffu, big);
+    const int lane = threadIdx.x & 31;
+    while (bigmask) {
+        const int src = __ffs(bigmask) - 1;
+        bigmask &= bigmask - 1;
+        const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
+        const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
+        const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+        for (uint64_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, lo_lim, sp);
     }
 }
 
@@ -444,16 +452,21 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
     return CUSMC_OK;
 }
 
-// tile_state: cusmc_scan_state_bytes(N) bytes, word 0 zero (see weigh_kernel).  stats_dev may be
-// NULL (tile prefixes only).
+// image: cusmc_scan_state_bytes(N) bytes, word 0 zero (see weigh_kernel).  stats_dev may be NULL
+// (image only); full_stats adds the sum of squares and the positive count (ESS).
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *tile_state)
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats)
 {
     if (N == 0) return CUSMC_OK;
     const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
-    weigh_kernel<<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
-                                                      (unsigned long long *)stats_dev,
-                                                      (unsigned long long *)tile_state);
+    if (full_stats && stats_dev)
+        weigh_kernel<true><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
+                                                                (unsigned long long *)stats_dev,
+                                                                (unsigned long long *)image);
+    else
+        weigh_kernel<false><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
+                                                                 (unsigned long long *)stats_dev,
+                                                                 (unsigned long long *)image);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -461,23 +474,20 @@ int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const 
 size_t cusmc_scan_state_bytes(int64_t N)
 {
     const int64_t tiles = (N + kTile - 1) / kTile;
-    return sizeof(unsigned long long) * (size_t)(tiles + 2);
+    return sizeof(unsigned long long) * (size_t)(image_header_words(N) + tiles * kTile);
 }
 
-// tile_state must hold the exclusive tile prefixes of exactly these weights (same w, max, N).
-int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev, int64_t N,
-                      int64_t N_global, int shift, const uint64_t *total_dev,
-                      const uint64_t *cdf_offset_dev, const void *tile_state,
+// image must hold the weight image of exactly these weights (same w, max, N, shift).
+int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
+                      const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers)
 {
     if (N == 0) return CUSMC_OK;
     ScanArgs p{};
-    p.w = w;
-    p.wmax = max_dev;
     p.total = (const unsigned long long *)total_dev;
     p.cdf_offset = (const unsigned long long *)cdf_offset_dev;
-    p.tile_state = (const unsigned long long *)tile_state;
+    p.image = (const unsigned long long *)image;
     p.cdf_out = (unsigned long long *)cdf_out;
     p.anc_out = anc_out;
     p.N = N;
@@ -486,17 +496,15 @@ int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double 
     p.out_lo = out_lo;
     p.out_n = out_n;
     p.u0 = u0;
-    p.shift = shift;
-    p.is_log = is_log;
-    const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
+    const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
     if (peers) {
         for (int r = 0; r < peers->world; ++r) p.anc_peer[r] = (uint32_t *)peers->ptr[r];
         p.per_rank = (uint32_t)peers->per_rank;
         p.out_lo = 0;
         p.out_n = N_global;
-        scan_resample_kernel<true><<<tiles, kThreads, 0, ctx->stream>>>(p);
+        scan_resample_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
     } else {
-        scan_resample_kernel<false><<<tiles, kThreads, 0, ctx->stream>>>(p);
+        scan_resample_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(p);
     }
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
@@ -568,7 +576,7 @@ extern "C" int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is
     if (N == 0) return CUSMC_OK;
     void *state = nullptr;
     CUSMC_CHECK(tile_state_for(ctx, N, tile_prefix_dev, &state));
-    return cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), stats_dev, state);
+    return cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), stats_dev, state, true);
 }
 
 // Tile prefixes for a scan: the caller's (from cusmc_weights_sum_dev on the same weights) or a
@@ -582,7 +590,7 @@ static int scan_prefixes(cusmc_ctx *ctx, const double *w_dev, int is_log, const 
     }
     void *mine = nullptr;
     CUSMC_CHECK(tile_state_for(ctx, N, nullptr, &mine));
-    CUSMC_CHECK(cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), nullptr, mine));
+    CUSMC_CHECK(cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), nullptr, mine, false));
     *state = mine;
     return CUSMC_OK;
 }
@@ -598,8 +606,8 @@ extern "C" int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int i
     if (N == 0) return CUSMC_OK;
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N, N_global, tile_prefix_dev, &state));
-    return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N, N_global, cusmc_fixed_shift(N_global),
-                             nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0, nullptr);
+    return cusmc_launch_scan(ctx, N, N_global, nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0,
+                             nullptr);
 }
 
 extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
@@ -616,8 +624,8 @@ extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev
     if (N_local == 0) return CUSMC_OK;
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N_local, N_global, tile_prefix_dev, &state));
-    return cusmc_launch_scan(ctx, w_dev, is_log, max_dev, N_local, N_global, cusmc_fixed_shift(N_global),
-                             total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo, out_n, u0, nullptr);
+    return cusmc_launch_scan(ctx, N_local, N_global, total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo,
+                             out_n, u0, nullptr);
 }
 
 extern "C" int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cdf_dev, int64_t N,

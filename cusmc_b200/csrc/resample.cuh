@@ -8,14 +8,13 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
                             int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers);
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
-// tile_state: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the exclusive
-// tile prefixes the scan consumes.  stats_dev may be NULL.
+// image: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the weight image
+// (exclusive tile prefixes + tile-local CDF) the resampling pass consumes.  stats_dev may be NULL.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *tile_state);
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats);
 size_t cusmc_scan_state_bytes(int64_t N);
-int cusmc_launch_scan(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev, int64_t N,
-                      int64_t N_global, int shift, const uint64_t *total_dev,
-                      const uint64_t *cdf_offset_dev, const void *tile_state,
+int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
+                      const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers);
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,

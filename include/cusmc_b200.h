@@ -200,17 +200,20 @@ int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log, double *x
  * cusmc_weights_max_dev : *max_dev = max_i w_i over finite entries (set to -inf first).
  * cusmc_weights_sum_dev : stats_dev[0..2] = { sum q_i, sum trunc(wn_i^2 2^shift), #(q_i > 0) }
  *                         (4 words, zeroed first).  log-sum-exp = max + log(stats[0] / 2^shift),
- *                         ESS = stats[0]^2 / (stats[1] 2^shift).  The same pass leaves the exclusive
- *                         prefix of the per-tile sums (tile = 2048 weights) in tile_prefix_dev:
- *                         cusmc_tile_prefix_words(N) uint64 words whose word 0 is zero before the
- *                         first use (the kernel resets it); NULL = context scratch.
+ *                         ESS = stats[0]^2 / (stats[1] 2^shift).  The same pass leaves the WEIGHT
+ *                         IMAGE in tile_prefix_dev: the exclusive prefix of the per-tile sums
+ *                         (tile = 2048 weights) and every weight's inclusive prefix inside its
+ *                         tile -- cusmc_tile_prefix_words(N) uint64 words, 16-byte aligned, word 0
+ *                         zero before the first use (the kernel resets it); NULL = context scratch.
+ *                         exp() is evaluated once per weight, here.
  * cusmc_weights_scan_dev: cdf_dev[i] = *cdf_offset_dev + inclusive prefix sum of q.  Because the
  *                         total must be known before a single child can be assigned, the sum pass
- *                         above is mandatory anyway and hands the scan its tile prefixes: tiles are
+ *                         above is mandatory anyway and hands this pass everything it needs:
+ *                         CDF_i = offset + prefix[tile(i)] + local_i, one thread per weight, tiles
  *                         independent, nothing spins (a decoupled look-back would add a serial
  *                         dependency for information that is already in memory).  tile_prefix_dev:
  *                         what cusmc_weights_sum_dev left for the SAME (w, max, N, N_global), or
- *                         NULL to recompute it here.  cdf_offset_dev may be NULL (0): it is the
+ *                         NULL to compute it here.  cdf_offset_dev may be NULL (0): it is the
  *                         fixed-point mass held by lower-ranked shards.
  * On several GPUs the caller all-reduces max (MAX) and stats (SUM) between these calls and
  * passes the exclusive prefix of the per-rank sums as cdf_offset (cusmc_b200/sharded.py).
