@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcusmc_b200.so")
+# CUSMC_B200_LIB: another build of the same library (kernel-variant experiments under profiles/)
+LIB_PATH = os.environ.get("CUSMC_B200_LIB") or os.path.join(_HERE, "libcusmc_b200.so")
 
 c_double_p = C.POINTER(C.c_double)
 c_u32_p = C.POINTER(C.c_uint32)

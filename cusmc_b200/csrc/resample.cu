@@ -121,22 +121,29 @@ __device__ __forceinline__ double unit_weight(double w, double wmax, int is_log)
 //
 // A tile is kTile = 2048 consecutive weights; thread t of the block owns the 8 consecutive weights
 // 8t .. 8t+7 (four 128-bit loads).  Workspace layout, uint64 words (cusmc_scan_state_bytes):
-//     [0]            arrival counter -- zero when a launch starts, reset to zero by its last block
-//     [1 + b]        sum of tile b, turned IN PLACE into the exclusive prefix over tiles by the last
-//                    block to finish (one block scanning N/2048 integers: ~1 us at N = 8 Mi)
-//     [H + i]        inclusive prefix of weight i INSIDE its tile (H = header words, even)
+//     [0]                 reserved
+//     [1 + b]             sum of tile b, turned IN PLACE into the exclusive prefix over tiles by
+//                         tile_scan_kernel (one block; ~2 us at N = 8 Mi)
+//     [1 + tiles + b]     sum of squared weights of tile b   } FULL only (ESS); reduced by
+//     [1 + 2 tiles + b]   positive weights in tile b         } tile_scan_kernel
+//     [H + i]             inclusive prefix of weight i INSIDE its tile (H = header words, even)
 // exp() is evaluated once per weight, here.  The resampling pass that follows needs neither the
 // weights nor a scan of its own: global CDF_i = offset + prefix[tile(i)] + local_i, one thread per
-// particle, tiles independent -- no decoupled look-back, no spinning, no state to clear between
-// steps.  Integer sums: every order of arrival gives the same bits.
+// particle, tiles independent -- no decoupled look-back, no spinning, no atomics, no state to clear
+// between steps.  (A first version had every block atomicAdd its sums into one word and the last
+// block to arrive scan the tile sums: 2 same-address atomics per tile cost 18 us at N = 8 Mi.)
+// Integer sums: every order gives the same bits.
 // ------------------------------------------------------------------------------------------
-constexpr int kTileItems = 8;
+#ifndef CUSMC_TILE_ITEMS
+#define CUSMC_TILE_ITEMS 8
+#endif
+constexpr int kTileItems = CUSMC_TILE_ITEMS;
 constexpr int kTile = kThreads * kTileItems;    // 2048 weights per tile
 
+__host__ __device__ inline int64_t image_tiles(int64_t N) { return (N + kTile - 1) / kTile; }
 __host__ __device__ inline int64_t image_header_words(int64_t N)
 {
-    const int64_t tiles = (N + kTile - 1) / kTile;
-    return (tiles + 2 + 1) & ~(int64_t)1;       // counter + tiles + 1 spare, rounded to 16 bytes
+    return (1 + 3 * image_tiles(N) + 1) & ~(int64_t)1;       // rounded up to 16 bytes
 }
 
 __device__ __forceinline__ void load_tile_items(const double *__restrict__ w, int64_t base, int64_t N,
@@ -173,10 +180,9 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 template <bool FULL>
 __global__ void __launch_bounds__(kThreads)
 weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict__ wmax_p, int64_t N,
-             int shift, unsigned long long *__restrict__ stats, unsigned long long *__restrict__ image)
+             int shift, unsigned long long *__restrict__ image)
 {
     __shared__ unsigned long long sm[kThreads / 32];
-    __shared__ int s_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double wmax = *wmax_p;
     const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
@@ -225,43 +231,81 @@ weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict_
         np = block_sum_u64(np, sm);
     }
     if (threadIdx.x == 0) {
-        if (stats) {
-            atomicAdd(stats + 0, tile_total);
-            if (FULL) {
-                atomicAdd(stats + 1, s2);
-                atomicAdd(stats + 2, np);
-            }
-        }
+        const int64_t tiles = gridDim.x;
         image[1 + blockIdx.x] = tile_total;
-        __threadfence();
-        s_last = atomicAdd(image, 1ull) == (unsigned long long)gridDim.x - 1;
+        if (FULL) {
+            image[1 + tiles + blockIdx.x] = s2;
+            image[1 + 2 * tiles + blockIdx.x] = np;
+        }
     }
-    __syncthreads();
-    if (!s_last) return;
-    // last block: exclusive scan of the tile sums, in place
-    __threadfence();
-    const int n = (int)gridDim.x;
-    const int per = (n + kThreads - 1) / kThreads;
-    const int lo = threadIdx.x * per, hi = min(lo + per, n);
-    unsigned long long mine = 0;
-    for (int k = lo; k < hi; ++k) mine += __ldcg(image + 1 + k);
-    inc = mine;
+}
+
+// One block: exclusive prefix of the tile sums, in place, and the totals
+// stats[0..2] = { sum q, sum q2, #positive } (plain stores: nothing to zero beforehand).
+constexpr int kScanThreads = 1024;
+__global__ void __launch_bounds__(kScanThreads)
+tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned long long *__restrict__ stats,
+                 int full)
+{
+    __shared__ unsigned long long sm[kScanThreads / 32];
+    __shared__ unsigned long long s_chunk;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long carry = 0, s2 = 0, np = 0;
+    for (int64_t base = 0; base < tiles; base += kScanThreads) {
+        const int64_t idx = base + threadIdx.x;
+        const unsigned long long v = idx < tiles ? image[1 + idx] : 0ull;
+        if (full && idx < tiles) {
+            s2 += image[1 + tiles + idx];
+            np += image[1 + 2 * tiles + idx];
+        }
+        unsigned long long inc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += t;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) sm[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {                       // exclusive scan of the 32 warp totals
+            const unsigned long long w = sm[lane];
+            unsigned long long wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= o) wi += t;
+            }
+            sm[lane] = wi - w;
+            if (lane == 31) s_chunk = wi;
+        }
+        __syncthreads();
+        if (idx < tiles) image[1 + idx] = carry + sm[warp] + inc - v;
+        carry += s_chunk;
+        __syncthreads();
     }
-    __syncthreads();
-    if (lane == 31) sm[warp] = inc;
-    __syncthreads();
-    unsigned long long off = inc - mine;
-    for (int k = 0; k < warp; ++k) off += sm[k];
-    for (int k = lo; k < hi; ++k) {
-        const unsigned long long t = __ldcg(image + 1 + k);
-        image[1 + k] = off;
-        off += t;
+    if (!stats) return;
+    if (full) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+            np += __shfl_xor_sync(0xffffffffu, np, o);
+        }
+        __shared__ unsigned long long sm2[kScanThreads / 32];
+        if (lane == 0) {
+            sm[warp] = s2;
+            sm2[warp] = np;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            s2 = np = 0;
+            for (int k = 0; k < kScanThreads / 32; ++k) {
+                s2 += sm[k];
+                np += sm2[k];
+            }
+            stats[1] = s2;
+            stats[2] = np;
+        }
     }
-    if (threadIdx.x == 0) image[0] = 0;
+    if (threadIdx.x == 0) stats[0] = carry;
 }
 
 // #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
@@ -334,12 +378,23 @@ scan_resample_kernel(const ScanArgs p)
     const uint64_t C = base + (active ? __ldg(local + i) : 0ull);
     if (p.cdf_out && active) p.cdf_out[i] = C;
     if (!PEERS && !p.anc_out) return;
-    const uint64_t T = *p.total;
+    // the per-launch constants (two fp64 divisions, 64-bit conversions) once per block, not per thread
+    __shared__ uint64_t s_T, s_r0;
+    __shared__ double s_ng_over_t, s_r0_over_t;
+    if (threadIdx.x == 0) {
+        const uint64_t Tt = *p.total;
+        uint64_t rr = (uint64_t)(p.u0 * (double)Tt);
+        if (Tt && rr > Tt - 1) rr = Tt - 1;
+        s_T = Tt;
+        s_r0 = rr;
+        s_ng_over_t = (double)p.N_global / (double)Tt;
+        s_r0_over_t = (double)rr / (double)Tt;
+    }
+    __syncthreads();
+    const uint64_t T = s_T;
     if (T == 0) return;                               // degenerate: the host reports it
-    uint64_t r0 = (uint64_t)(p.u0 * (double)T);
-    if (r0 > T - 1) r0 = T - 1;
-    const double ng_over_t = (double)p.N_global / (double)T;
-    const double r0_over_t = (double)r0 / (double)T;
+    const uint64_t r0 = s_r0;
+    const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
     const uint64_t Ng = (uint64_t)p.N_global;
     // the offspring count is a pure function of the CDF value; the left neighbour's count comes
     // through shared memory, the block's first thread evaluates its own
@@ -452,29 +507,31 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
     return CUSMC_OK;
 }
 
-// image: cusmc_scan_state_bytes(N) bytes, word 0 zero (see weigh_kernel).  stats_dev may be NULL
-// (image only); full_stats adds the sum of squares and the positive count (ESS).
+// image: cusmc_scan_state_bytes(N) bytes (see weigh_kernel).  stats_dev may be NULL (image only);
+// full_stats adds the sum of squares and the positive count (ESS).  Two launches: the tiles, then
+// one block that turns the tile sums into prefixes and totals.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
                              int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats)
 {
     if (N == 0) return CUSMC_OK;
-    const unsigned tiles = (unsigned)((N + kTile - 1) / kTile);
-    if (full_stats && stats_dev)
+    const unsigned tiles = (unsigned)image_tiles(N);
+    const bool full = full_stats && stats_dev;
+    if (full)
         weigh_kernel<true><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
-                                                                (unsigned long long *)stats_dev,
                                                                 (unsigned long long *)image);
     else
         weigh_kernel<false><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
-                                                                 (unsigned long long *)stats_dev,
                                                                  (unsigned long long *)image);
+    CUSMC_LAUNCHED(ctx);
+    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>((unsigned long long *)image, (int64_t)tiles,
+                                                          (unsigned long long *)stats_dev, full ? 1 : 0);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
 
 size_t cusmc_scan_state_bytes(int64_t N)
 {
-    const int64_t tiles = (N + kTile - 1) / kTile;
-    return sizeof(unsigned long long) * (size_t)(image_header_words(N) + tiles * kTile);
+    return sizeof(unsigned long long) * (size_t)(image_header_words(N) + image_tiles(N) * kTile);
 }
 
 // image must hold the weight image of exactly these weights (same w, max, N, shift).
@@ -555,9 +612,7 @@ static int tile_state_for(cusmc_ctx *ctx, int64_t N, uint64_t *user, void **out)
         *out = user;
         return CUSMC_OK;
     }
-    CUSMC_CHECK(cusmc_scratch(ctx, 7, cusmc_scan_state_bytes(N), out));
-    CUSMC_CUDA(ctx, cudaMemsetAsync(*out, 0, sizeof(uint64_t), ctx->stream));
-    return CUSMC_OK;
+    return cusmc_scratch(ctx, 7, cusmc_scan_state_bytes(N), out);
 }
 
 extern "C" int64_t cusmc_tile_prefix_words(int64_t N)
@@ -572,8 +627,10 @@ extern "C" int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is
     if (!ctx) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(ctx, stats_dev && max_dev && (N == 0 || w_dev), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N && N_global >= 1, "N_global < N");
-    CUSMC_CUDA(ctx, cudaMemsetAsync(stats_dev, 0, 4 * sizeof(uint64_t), ctx->stream));
-    if (N == 0) return CUSMC_OK;
+    if (N == 0) {
+        CUSMC_CUDA(ctx, cudaMemsetAsync(stats_dev, 0, 3 * sizeof(uint64_t), ctx->stream));
+        return CUSMC_OK;
+    }
     void *state = nullptr;
     CUSMC_CHECK(tile_state_for(ctx, N, tile_prefix_dev, &state));
     return cusmc_launch_weights_sum(ctx, w_dev, is_log, max_dev, N, cusmc_fixed_shift(N_global), stats_dev, state, true);
