@@ -111,11 +111,6 @@ weights_max_kernel(const double *__restrict__ w, int64_t N, double *__restrict__
     }
 }
 
-__device__ __forceinline__ double unit_weight(double w, double wmax, int is_log)
-{
-    return is_log ? cusmc_unit_from_log(w, wmax) : cusmc_unit_from_linear(w, wmax);
-}
-
 // ------------------------------------------------------------------------------------------
 // The weight image: normalisation sums, tile prefixes and tile-local CDF of the fixed-point weights.
 //
@@ -177,9 +172,9 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 
 // FULL: also sum of squares and positive count (ESS); otherwise only what resampling needs.
-template <bool FULL>
+template <bool FULL, bool LOG>
 __global__ void __launch_bounds__(kThreads)
-weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict__ wmax_p, int64_t N,
+weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, int64_t N,
              int shift, unsigned long long *__restrict__ image)
 {
     __shared__ unsigned long long sm[kThreads / 32];
@@ -192,7 +187,8 @@ weigh_kernel(const double *__restrict__ w, int is_log, const double *__restrict_
     unsigned long long run = 0, s2 = 0, np = 0;
 #pragma unroll
     for (int r = 0; r < kTileItems; ++r) {
-        const double wn = unit_weight(v[r], wmax, is_log);   // -inf padding -> 0
+        // -inf padding -> 0
+        const double wn = LOG ? cusmc_unit_from_log(v[r], wmax) : cusmc_unit_from_linear(v[r], wmax);
         const uint64_t q = cusmc_fixed_from_unit(wn, shift);
         run += q;
         c[r] = run;
@@ -341,46 +337,47 @@ __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uin
 struct ScanArgs {
     const unsigned long long *total;       // global fixed-point mass (device)
     const unsigned long long *cdf_offset;  // mass on lower shards, or NULL
-    const unsigned long long *image;       // weigh_kernel's workspace
+    const unsigned long long *tile_prefix; // weight image: exclusive prefix of tile b at [b]
+    const unsigned long long *local;       // weight image: inclusive prefix of weight i inside its tile
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
     uint32_t *anc_peer[CUSMC_MAX_PEERS];   // PEERS: rank r's ancestor array (child slots r*per_rank ..)
     uint32_t per_rank;
-    int64_t N, N_global, j0, out_lo, out_n;
+    uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
 };
 
 // PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
 // owning rank's ancestor array through its peer-mapped pointer (4 bytes per child over NVLink).
 template <bool PEERS>
-__device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint64_t child, uint64_t lo_lim, uint32_t parent)
+__device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, uint32_t parent)
 {
     if (PEERS) {
-        const uint32_t c = (uint32_t)child, r = c / p.per_rank;
-        p.anc_peer[r][c - r * p.per_rank] = parent;
+        const uint32_t r = child / p.per_rank;
+        p.anc_peer[r][child - r * p.per_rank] = parent;
     } else {
-        p.anc_out[child - lo_lim] = parent;
+        p.anc_out[child - p.out_lo] = parent;
     }
 }
 
 // Global CDF from the weight image and, fused in, the systematic offspring scatter: parent j owns
-// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  One thread per parent.
+// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  One thread per parent;
+// indices and offspring counts are 32-bit throughout (N_global < 2^32).
 template <bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 scan_resample_kernel(const ScanArgs p)
 {
-    __shared__ unsigned long long s_k[kThreads];
-    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;      // local parent
+    __shared__ uint32_t s_k[kThreads];
+    __shared__ uint64_t s_T, s_r0;
+    __shared__ double s_ng_over_t, s_r0_over_t;
+    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;               // local parent
     const bool active = i < p.N;
-    const int64_t tile = ((int64_t)blockIdx.x * kThreads) / kTile;       // a block lies inside one tile
-    const unsigned long long *local = p.image + image_header_words(p.N);
-    const uint64_t base = p.image[1 + tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
-    const uint64_t C = base + (active ? __ldg(local + i) : 0ull);
+    const uint32_t tile = (blockIdx.x * kThreads) / kTile;                // a block lies inside one tile
+    const uint64_t base = p.tile_prefix[tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
+    const uint64_t C = base + (active ? __ldg(p.local + i) : 0ull);
     if (p.cdf_out && active) p.cdf_out[i] = C;
     if (!PEERS && !p.anc_out) return;
     // the per-launch constants (two fp64 divisions, 64-bit conversions) once per block, not per thread
-    __shared__ uint64_t s_T, s_r0;
-    __shared__ double s_ng_over_t, s_r0_over_t;
     if (threadIdx.x == 0) {
         const uint64_t Tt = *p.total;
         uint64_t rr = (uint64_t)(p.u0 * (double)Tt);
@@ -395,37 +392,39 @@ scan_resample_kernel(const ScanArgs p)
     if (T == 0) return;                               // degenerate: the host reports it
     const uint64_t r0 = s_r0;
     const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
-    const uint64_t Ng = (uint64_t)p.N_global;
+    const uint64_t Ng = p.N_global;
     // the offspring count is a pure function of the CDF value; the left neighbour's count comes
     // through shared memory, the block's first thread evaluates its own
-    const uint64_t k_here = active ? offspring_below(C, Ng, T, r0, ng_over_t, r0_over_t) : 0;
+    const uint32_t k_here = active ? (uint32_t)offspring_below(C, Ng, T, r0, ng_over_t, r0_over_t) : 0u;
     s_k[threadIdx.x] = k_here;
     __syncthreads();
-    uint64_t k_prev = 0;
+    uint32_t k_prev = 0;
     if (threadIdx.x > 0) {
         k_prev = s_k[threadIdx.x - 1];
     } else if (active) {
-        const uint64_t Cprev = base + ((i % kTile) ? __ldg(local + i - 1) : 0ull);
-        k_prev = offspring_below(Cprev, Ng, T, r0, ng_over_t, r0_over_t);
+        const uint64_t Cprev = base + ((i % kTile) ? __ldg(p.local + i - 1) : 0ull);
+        k_prev = (uint32_t)offspring_below(Cprev, Ng, T, r0, ng_over_t, r0_over_t);
     }
-    const uint64_t lo_lim = (uint64_t)p.out_lo, hi_lim = (uint64_t)(p.out_lo + p.out_n);
     // threads past the end own the empty range and stay to help with large families
-    uint64_t a = !active ? 0 : (k_prev < lo_lim ? lo_lim : k_prev);
-    const uint64_t b = !active ? 0 : (k_here > hi_lim ? hi_lim : k_here);
-    const uint32_t parent = (uint32_t)(p.j0 + i);
+    uint32_t a = active ? max(k_prev, p.out_lo) : 0u;
+    const uint32_t b = active ? min(k_here, p.out_hi) : 0u;
+    const uint32_t parent = p.j0 + i;
     // small families: the owning thread writes them; large ones: the whole warp helps
     const bool big = b > a && b - a > 8;
-    if (!big)
-        for (; a < b; ++a) put_ancestor<PEERS>(p, a, lo_lim, parent);
+    if (!big) {
+#pragma unroll 1
+        for (; a < b; ++a) put_ancestor<PEERS>(p, a, parent);
+    }
     unsigned bigmask = __ballot_sync(0xffffffffu, big);
-    const int lane = threadIdx.x & 31;
+    const uint32_t lane = threadIdx.x & 31;
     while (bigmask) {
         const int src = __ffs(bigmask) - 1;
         bigmask &= bigmask - 1;
-        const uint64_t sa = __shfl_sync(0xffffffffu, a, src);
-        const uint64_t sb = __shfl_sync(0xffffffffu, b, src);
+        const uint32_t sa = __shfl_sync(0xffffffffu, a, src);
+        const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
         const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
-        for (uint64_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, lo_lim, sp);
+#pragma unroll 1
+        for (uint32_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, sp);
     }
 }
 
@@ -516,12 +515,15 @@ int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const 
     if (N == 0) return CUSMC_OK;
     const unsigned tiles = (unsigned)image_tiles(N);
     const bool full = full_stats && stats_dev;
-    if (full)
-        weigh_kernel<true><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
-                                                                (unsigned long long *)image);
+    unsigned long long *img = (unsigned long long *)image;
+    if (full && is_log)
+        weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+    else if (full)
+        weigh_kernel<true, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+    else if (is_log)
+        weigh_kernel<false, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     else
-        weigh_kernel<false><<<tiles, kThreads, 0, ctx->stream>>>(w, is_log, max_dev, N, shift,
-                                                                 (unsigned long long *)image);
+        weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     CUSMC_LAUNCHED(ctx);
     tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>((unsigned long long *)image, (int64_t)tiles,
                                                           (unsigned long long *)stats_dev, full ? 1 : 0);
@@ -541,24 +543,27 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
                       int64_t out_n, double u0, const CusmcPeers *peers)
 {
     if (N == 0) return CUSMC_OK;
+    if (N_global > 0xFFFFFFFFll || out_lo < 0 || out_lo + out_n > N_global)
+        return cusmc_fail(ctx, CUSMC_ERR_INVALID, "resampling range outside 0..N_global (< 2^32)");
     ScanArgs p{};
     p.total = (const unsigned long long *)total_dev;
     p.cdf_offset = (const unsigned long long *)cdf_offset_dev;
-    p.image = (const unsigned long long *)image;
+    p.tile_prefix = (const unsigned long long *)image + 1;
+    p.local = (const unsigned long long *)image + image_header_words(N);
     p.cdf_out = (unsigned long long *)cdf_out;
     p.anc_out = anc_out;
-    p.N = N;
-    p.N_global = N_global;
-    p.j0 = j0;
-    p.out_lo = out_lo;
-    p.out_n = out_n;
+    p.N = (uint32_t)N;
+    p.N_global = (uint32_t)N_global;
+    p.j0 = (uint32_t)j0;
+    p.out_lo = (uint32_t)out_lo;
+    p.out_hi = (uint32_t)(out_lo + out_n);
     p.u0 = u0;
     const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
     if (peers) {
         for (int r = 0; r < peers->world; ++r) p.anc_peer[r] = (uint32_t *)peers->ptr[r];
         p.per_rank = (uint32_t)peers->per_rank;
         p.out_lo = 0;
-        p.out_n = N_global;
+        p.out_hi = (uint32_t)N_global;
         scan_resample_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
     } else {
         scan_resample_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(p);

@@ -100,10 +100,13 @@ CUSMC_HD double cusmc_det_exp(double x)
  * NaN, -inf and x < -43.5 give 0.  One compare, one scale: the hot form. */
 CUSMC_HD double cusmc_det_exp_unit(double x)
 {
-    if (!(x >= -43.5)) return 0.0;
+    /* branch-free on purpose: a thread that owns several weights gets its exp chains interleaved
+     * and the polynomial coefficients shared between them */
+    const int ok = x >= -43.5;
     int k;
-    const double p = cusmc_det_exp_core(x, &k);
-    return p * cusmc_pow2i(k);
+    const double p = cusmc_det_exp_core(ok ? x : 0.0, &k);
+    const double v = p * cusmc_pow2i(k);
+    return ok ? v : 0.0;
 }
 
 /* log(x): x = m 2^e, m in [sqrt(1/2), sqrt 2), log m = 2 atanh(s), s = (m-1)/(m+1). */
@@ -270,9 +273,8 @@ CUSMC_HD int cusmc_fixed_shift(int64_t n_global)
 /* wn in [0, 1] -> trunc(wn * 2^shift); anything else (NaN, negative) -> 0. */
 CUSMC_HD uint64_t cusmc_fixed_from_unit(double wn, int shift)
 {
-    if (!(wn > 0.0)) return 0;
-    if (wn > 1.0) wn = 1.0;
-    return (uint64_t)(wn * cusmc_pow2i(shift));
+    const double c = (wn > 0.0) ? (wn > 1.0 ? 1.0 : wn) : 0.0;   /* select form: no branches */
+    return (uint64_t)(c * cusmc_pow2i(shift));
 }
 
 /* Linear-domain weight w relative to wmax. */
@@ -285,8 +287,8 @@ CUSMC_HD double cusmc_unit_from_linear(double w, double wmax)
 /* Log-domain weight lw relative to lmax. */
 CUSMC_HD double cusmc_unit_from_log(double lw, double lmax)
 {
-    if (!(lw <= lmax)) return 0.0; /* NaN or above the max */
-    return cusmc_det_exp_unit(lw - lmax);
+    const double v = cusmc_det_exp_unit(lw - lmax);
+    return (lw <= lmax) ? v : 0.0; /* NaN or above the max -> 0 */
 }
 
 #endif /* CUSMC_DETMATH_H */
