@@ -259,23 +259,30 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         Y = np.random.default_rng(5000).standard_normal((d, T))
         pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, I, I,
                                               resampler="systematic", seed=2, summary=False)
-        pf.run()
-        torch.cuda.synchronize()
-        dist.barrier()
-        pf.run()
-        torch.cuda.synchronize()
-        t = torch.tensor([pf.last_ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-        ess = pf.summary()["ess"]
+        res = {}
+        for exchange in ("p2p", "nccl"):
+            pf.run(exchange=exchange)
+            torch.cuda.synchronize()
+            dist.barrier()
+            pf.run(exchange=exchange)
+            torch.cuda.synchronize()
+            t = torch.tensor([pf.last_ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res[exchange] = float(t.item())
+        status = pf.exchange_status()
         pf.close()
+        ms = res["p2p"]
         rate = N * (T - 1) / (ms * 1e-3)
         out["pf_c5_sharded_particle_steps_per_sec"] = {
             "value": rate, "N_global": N, "n_gpus": world, "d": d, "T": T, "ms_per_step": ms / (T - 1),
             "resampler": "systematic", "noise": "philox in-kernel", "bytes_per_particle_step": 160,
-            "roofline_frac_per_gpu": rate / world * 160 / (hbm_gbs * 1e9), "ess_last": float(ess[-1]),
-            "exchange": "NCCL all-reduce(max) + all-gather(sums) + barrier per step; ancestors by peer "
-                        "stores, parent states by peer loads (CUDA IPC over NVLink)"}
+            "roofline_frac_per_gpu": rate / world * 160 / (hbm_gbs * 1e9),
+            "exchange": "p2p: per-step max / sums / barrier through peer-memory mailboxes (one-warp kernels, "
+                        "CUDA IPC over NVLink), whole run enqueued by the library; ancestors by peer stores, "
+                        "parent states by peer loads",
+            "exchange_status": status,
+            "ms_per_step_nccl_exchange": res["nccl"] / (T - 1),
+            "value_nccl_exchange": N * (T - 1) / (res["nccl"] * 1e-3)}
     except Exception as e:
         out["pf_c5_sharded_particle_steps_per_sec"] = {"error": repr(e)}
     return out

@@ -29,6 +29,7 @@ RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1, 2
 MAX_DIM = 32
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
+FILTER_IPC_BUFFERS = 5
 
 
 class FilterConfig(C.Structure):
@@ -94,6 +95,8 @@ PROTOTYPES = {
     "cusmc_filter_moments_dev": (ci, [vp, C.POINTER(vp)]),
     "cusmc_filter_ipc_export": (ci, [vp, vp]),
     "cusmc_filter_ipc_attach": (ci, [vp, vp]),
+    "cusmc_filter_run_sharded": (ci, [vp, C.POINTER(FilterDraws)]),
+    "cusmc_filter_exchange_status": (ci, [vp, C.POINTER(u64)]),
     "cusmc_filter_get_summary": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_get_history": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_last_ms": (dbl, [vp]),

@@ -22,6 +22,30 @@ struct CusmcPeers {
     int world;
 };
 
+// n / d for any 32-bit n by multiply-high and shifts (Granlund-Montgomery round-up form): slot ->
+// owning rank on every peer access, without a hardware-emulated division per particle.
+struct FastDiv {
+    uint32_t d, M, s1, s2;
+};
+inline FastDiv make_fast_div(uint32_t d)
+{
+    uint32_t l = 0;
+    while (((uint64_t)1 << l) < d) ++l;
+    FastDiv f;
+    f.d = d;
+    f.M = (uint32_t)((((uint64_t)1 << 32) * (((uint64_t)1 << l) - d)) / d + 1);
+    f.s1 = l < 1 ? l : 1;
+    f.s2 = l > 0 ? l - 1 : 0;
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f)
+{
+    const uint32_t t = __umulhi(f.M, n);
+    return (t + ((n - t) >> f.s1)) >> f.s2;
+}
+#endif
+
 struct cusmc_density_cache;   // density.cu: last factored (kind, mu, Sigma, nu)
 
 struct cusmc_ctx {

@@ -14,6 +14,7 @@
 // operator ride in the kernel parameter bank.
 #include "density.cuh"
 #include "hostmath.h"
+#include "mailbox.cuh"
 #include "pf_step.cuh"
 #include "resample.cuh"
 
@@ -439,7 +440,11 @@ struct cusmc_filter {
     int world = 1, rank = 0;
     int64_t per = 0, lo = 0, n = 0;
     bool attached = false;
-    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{};
+    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
+    unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
+    unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
+    unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
+    bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
     double *x[2] = {nullptr, nullptr};
     double *lw = nullptr;
     uint32_t *anc = nullptr;
@@ -455,6 +460,21 @@ struct cusmc_filter {
     int next_t = -1;                  // phase bookkeeping: the step cusmc_filter_propagate expects
     bool ran = false;
 };
+
+// Scalar exchanges of a sharded run ride inside the kernels (mailbox.cuh) when `fused` is set.
+static MailArgs filter_mail(const cusmc_filter *f)
+{
+    MailArgs m{};
+    if (f->world > 1 && f->fused) {
+        for (int r = 0; r < f->world; ++r) m.peer[r] = (unsigned long long *)f->peer_mail.ptr[r];
+        m.err = f->mail_err;
+        m.epoch = f->epoch;
+        m.rank = f->rank;
+        m.world = f->world;
+    }
+    return m;
+}
+
 
 // Symmetric eigen factor Q = V sqrt(Lambda) (reference: eigenSolver, src/linear_algebra.cpp:10-23)
 // by cyclic Jacobi; any Q with Q Q^T = Sigma gives the same law, the eigen form is kept so the
@@ -506,7 +526,7 @@ static int eigen_factor(cusmc_ctx *ctx, const double *S, int d, std::vector<doub
 static void detach_peers(cusmc_filter *f)
 {
     if (!f->attached) return;
-    CusmcPeers *tabs[4] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw};
+    CusmcPeers *tabs[5] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail};
     for (CusmcPeers *t : tabs)
         for (int r = 0; r < f->world; ++r)
             if (r != f->rank && t->ptr[r]) cudaIpcCloseMemHandle(t->ptr[r]);
@@ -527,6 +547,8 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     cudaFree(f->slots);
     cudaFree(f->moments);
     cudaFree(f->scan_state);
+    cudaFree(f->mail);
+    cudaFree(f->mail_err);
     cudaFree(f->hist_x);
     cudaFree(f->hist_w);
     cudaFree(f->hist_a);
@@ -605,6 +627,13 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
     alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
     alloc(&f->scan_state, cusmc_scan_state_bytes(f->per));
+    if (world > 1) {
+        const size_t mail_bytes = sizeof(unsigned long long) * 4 * 3 * (size_t)world * (size_t)T;
+        alloc((void **)&f->mail, mail_bytes);
+        alloc((void **)&f->mail_err, 8);
+        if (e == cudaSuccess) e = cudaMemset(f->mail, 0, mail_bytes);
+        if (e == cudaSuccess) e = cudaMemset(f->mail_err, 0, 8);
+    }
     if (cfg->keep_history) {
         alloc((void **)&f->hist_x, sizeof(double) * (size_t)T * P * d);
         alloc((void **)&f->hist_w, sizeof(double) * (size_t)T * P);
@@ -622,8 +651,8 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
 }
 
 // ---- sharded runs: peer mapping of the state ---------------------------------------------------
-// Exported buffers, in this order: x[0], x[1], ancestors, weights.
-enum { kIpcBuffers = 4 };
+// Exported buffers, in this order: x[0], x[1], ancestors, weights, mailbox.
+enum { kIpcBuffers = CUSMC_FILTER_IPC_BUFFERS };
 
 extern "C" int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles)
 {
@@ -631,7 +660,8 @@ extern "C" int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles)
     cusmc_ctx *ctx = f->ctx;
     CUSMC_REQUIRE(ctx, handles != nullptr, "handles is NULL");
     static_assert(sizeof(cudaIpcMemHandle_t) == CUSMC_IPC_HANDLE_BYTES, "IPC handle size");
-    void *bufs[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw};
+    CUSMC_REQUIRE(ctx, f->world > 1, "not a sharded filter");
+    void *bufs[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail};
     for (int b = 0; b < kIpcBuffers; ++b) {
         cudaIpcMemHandle_t h;
         CUSMC_CUDA(ctx, cudaIpcGetMemHandle(&h, bufs[b]));
@@ -647,8 +677,9 @@ extern "C" int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all
     CUSMC_REQUIRE(ctx, all_handles != nullptr, "handles is NULL");
     CUSMC_REQUIRE(ctx, !f->attached, "peers are already attached");
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
-    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw};
-    void *mine[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw};
+    CUSMC_REQUIRE(ctx, f->world > 1, "not a sharded filter");
+    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail};
+    void *mine[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail};
     for (int b = 0; b < kIpcBuffers; ++b) {
         *tabs[b] = CusmcPeers{};
         tabs[b]->per_rank = f->per;
@@ -767,9 +798,10 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
     const int d = cfg.d;
     const int64_t n = f->n, P = f->per;
     cudaStream_t st = ctx->stream;
+    const MailArgs mail = filter_mail(f);
     if (f->is_log)
         CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
-                                             f->scan_state, cfg.summary != 0));
+                                             f->scan_state, cfg.summary != 0, &mail, t));
     if (cfg.summary && n > 0) {
         const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
         moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
@@ -802,8 +834,11 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
         const double *u = dr.u_dev ? dr.u_dev + off * n * cfg.B : nullptr;
         const uint32_t *j = dr.j_dev ? dr.j_dev + off * n * cfg.B : nullptr;
+        const MailArgs mail = filter_mail(f);
+        // fused gate: every rank's weights of step t - 1 are complete before anyone reads them
         return cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log,
-                                       f->lo, n, sharded ? &f->peer_lw : nullptr);
+                                       f->lo, n, sharded ? &f->peer_lw : nullptr, &mail,
+                                       mail_cell(t, kCellMax, f->world));
     }
     StepSlot *prev = &f->slots[t - 1];
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
@@ -854,8 +889,11 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     a.rng_stream = CUSMC_STREAM_NORMAL;
     if (f->world > 1) {
         a.world = f->world;
-        a.per_rank = (uint32_t)f->per;
+        a.per_rank = make_fast_div((uint32_t)f->per);
         for (int r = 0; r < f->world; ++r) a.x_prev_peer[r] = (const double *)f->peer_x[f->cur].ptr[r];
+        // fused barrier: every rank's ancestors (peer stores) have landed before anyone gathers
+        a.mail = filter_mail(f);
+        a.mail_cell0 = mail_cell(t, kCellBarrier, f->world);
     }
     CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
                                   f->ep, a, a.xi == nullptr));
@@ -869,6 +907,43 @@ extern "C" int cusmc_filter_mark(cusmc_filter *f, int which)
     if (!f) return CUSMC_ERR_INVALID;
     CUSMC_CUDA(f->ctx, cudaEventRecord(which ? f->ev1 : f->ev0, f->ctx->stream));
     if (which) f->ran = true;
+    return CUSMC_OK;
+}
+
+// ---- the sharded run ------------------------------------------------------------------------------
+// The whole sharded run enqueued from C++: the phases of cusmc_filter_run; the per-step max, sums
+// and barrier travel through the peer-memory mailboxes INSIDE weigh / tile-scan / propagate
+// (metropolis: inside the resampler), so a step launches the same four kernels as on one GPU.
+// Every rank calls it the same number of times (the epoch must agree); returns after enqueueing.
+extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, f->world > 1 && f->attached, "needs a sharded filter with attached peers");
+    ++f->epoch;
+    f->fused = true;
+    int rc = cudaMemsetAsync(f->mail_err, 0, 8, f->ctx->stream) == cudaSuccess ? CUSMC_OK : CUSMC_ERR_CUDA;
+    if (rc == CUSMC_OK) rc = cusmc_filter_begin(f, draws);
+    if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, 0);
+    if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 0);
+    for (int t = 1; t < f->cfg.T && rc == CUSMC_OK; ++t) {
+        rc = cusmc_filter_resample(f, t);
+        if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
+        if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, t);
+    }
+    if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 1);
+    f->fused = false;
+    return rc;
+}
+
+// Non-zero if a spin-wait of the last sharded run timed out (a peer never arrived).
+extern "C" int cusmc_filter_exchange_status(cusmc_filter *f, uint64_t *status)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, status != nullptr, "NULL pointer");
+    *status = 0;
+    if (!f->mail_err) return CUSMC_OK;
+    CUSMC_CUDA(f->ctx, cudaStreamSynchronize(f->ctx->stream));
+    CUSMC_CUDA(f->ctx, cudaMemcpy(status, f->mail_err, 8, cudaMemcpyDeviceToHost));
     return CUSMC_OK;
 }
 

@@ -3,6 +3,7 @@
 #pragma once
 
 #include "density.cuh"
+#include "mailbox.cuh"
 
 #include <vector>
 
@@ -31,8 +32,10 @@ struct StepArgs {
     // column g % per_rank of that rank's state buffer (leading dimension ld_prev on every rank),
     // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.
     const double *x_prev_peer[CUSMC_MAX_PEERS];
-    uint32_t per_rank;
+    FastDiv per_rank;
     int world;
+    MailArgs mail;               // mail.world > 1: gate on the ranks' barrier flags before reading peers
+    size_t mail_cell0;
 };
 
 // G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no

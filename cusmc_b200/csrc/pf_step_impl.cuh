@@ -95,6 +95,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
     const bool active = i < a.n_out;
     const int d = EXACT ? D : a.d;
     double lw = -INFINITY;
+    mail_gate(a.mail, a.mail_cell0);          // sharded runs only (no-op otherwise)
     if (active) {
         double xp[D], z[D], xn[D];
         int64_t parent = i;
@@ -116,8 +117,8 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         if (a.has_prev) {
             const double *src = a.x_prev + parent;
             if (a.world > 1) {
-                const uint32_t g = (uint32_t)parent, r = g / a.per_rank;
-                src = a.x_prev_peer[r] + (g - r * a.per_rank);
+                const uint32_t g = (uint32_t)parent, r = fast_div(g, a.per_rank);
+                src = a.x_prev_peer[r] + (g - r * a.per_rank.d);
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
@@ -232,7 +233,7 @@ int launch_one(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const Ste
 {
     StepOp<D, DIAG> op;
     fill_step_op<D, DIAG>(op, m);
-    const unsigned grid = (unsigned)((a.n_out + kThreads - 1) / kThreads);
+    const unsigned grid = a.n_out > 0 ? (unsigned)((a.n_out + kThreads - 1) / kThreads) : 1u;
     if (philox)
         pf_step_kernel<D, true, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
     else

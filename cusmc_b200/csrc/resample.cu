@@ -25,15 +25,15 @@ constexpr int kThreads = 256;
 // each), read through peer-mapped pointers over NVLink.
 struct PeerWeights {
     const double *w[CUSMC_MAX_PEERS];
-    uint32_t per_rank;
+    FastDiv per_rank;
 };
 
 template <bool PEERS>
 __device__ __forceinline__ double weight_at(const double *__restrict__ w, const PeerWeights &pw, uint32_t idx)
 {
     if (PEERS) {
-        const uint32_t r = idx / pw.per_rank;
-        return __ldg(pw.w[r] + (idx - r * pw.per_rank));
+        const uint32_t r = fast_div(idx, pw.per_rank);
+        return __ldg(pw.w[r] + (idx - r * pw.per_rank.d));
     }
     return __ldg(w + idx);
 }
@@ -42,8 +42,10 @@ template <bool PREDRAWN, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const PeerWeights pw,
                   const double *__restrict__ u, const uint32_t *__restrict__ j, uint64_t seed,
-                  uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out)
+                  uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out,
+                  const MailArgs mail, size_t mail_cell0)
 {
+    if (PEERS) mail_gate(mail, mail_cell0);   // every rank's weights are complete (fused barrier)
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= n_out) return;
     const int64_t i = i0 + t;              // global particle index (i0 = 0 on one GPU)
@@ -174,12 +176,34 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 // FULL: also sum of squares and positive count (ESS); otherwise only what resampling needs.
 template <bool FULL, bool LOG>
 __global__ void __launch_bounds__(kThreads)
-weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, int64_t N,
-             int shift, unsigned long long *__restrict__ image)
+weigh_kernel(const double *__restrict__ w, double *__restrict__ wmax_p, int64_t N,
+             int shift, unsigned long long *__restrict__ image, const MailArgs mail, size_t cell_max)
 {
     __shared__ unsigned long long sm[kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double wmax = *wmax_p;
+    double wmax;
+    if (mail.world > 1) {
+        // fused all-reduce(MAX) over the ranks: block 0 publishes this rank's max, every block
+        // takes the maximum of what the ranks published
+        __shared__ double s_max;
+        if (warp == 0) {
+            if (blockIdx.x == 0)
+                mail_publish(mail, cell_max, lane, (unsigned long long)__double_as_longlong(*wmax_p), 0, 0);
+            unsigned long long b0, b1, b2;
+            mail_wait(mail, cell_max, lane, b0, b1, b2);
+            double m = lane < mail.world ? __longlong_as_double((long long)b0) : -INFINITY;
+            if (!(m == m)) m = -INFINITY;
+            m = warp_max_double(m);
+            if (lane == 0) {
+                s_max = m;
+                if (blockIdx.x == 0) *wmax_p = m;      // the slot now holds the GLOBAL max
+            }
+        }
+        __syncthreads();
+        wmax = s_max;
+    } else {
+        wmax = *wmax_p;
+    }
     const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
     double v[kTileItems];
     load_tile_items(w, base, N, v);
@@ -241,7 +265,7 @@ weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, in
 constexpr int kScanThreads = 1024;
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned long long *__restrict__ stats,
-                 int full)
+                 int full, const MailArgs mail, size_t cell_sums)
 {
     __shared__ unsigned long long sm[kScanThreads / 32];
     __shared__ unsigned long long s_chunk;
@@ -279,6 +303,7 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
         __syncthreads();
     }
     if (!stats) return;
+    __shared__ unsigned long long s_tot[3];
     if (full) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -297,11 +322,37 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
                 s2 += sm[k];
                 np += sm2[k];
             }
-            stats[1] = s2;
-            stats[2] = np;
         }
     }
-    if (threadIdx.x == 0) stats[0] = carry;
+    if (threadIdx.x == 0) {
+        s_tot[0] = carry;
+        s_tot[1] = full ? s2 : 0ull;
+        s_tot[2] = full ? np : 0ull;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    unsigned long long w0 = s_tot[0], w1 = s_tot[1], w2 = s_tot[2], below = 0;
+    if (mail.world > 1) {
+        // fused all-gather of the per-rank sums: totals over ranks, and the mass on lower ranks
+        mail_publish(mail, cell_sums, lane, w0, w1, w2);
+        mail_wait(mail, cell_sums, lane, w0, w1, w2);
+        below = lane < mail.rank ? w0 : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            w0 += __shfl_xor_sync(0xffffffffu, w0, o);
+            w1 += __shfl_xor_sync(0xffffffffu, w1, o);
+            w2 += __shfl_xor_sync(0xffffffffu, w2, o);
+            below += __shfl_xor_sync(0xffffffffu, below, o);
+        }
+    }
+    if (lane == 0) {
+        stats[0] = w0;
+        if (full) {
+            stats[1] = w1;
+            stats[2] = w2;
+        }
+        if (mail.world > 1) stats[3] = below;      // StepSlot::cdf_offset
+    }
 }
 
 // #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
@@ -342,7 +393,7 @@ struct ScanArgs {
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
     uint32_t *anc_peer[CUSMC_MAX_PEERS];   // PEERS: rank r's ancestor array (child slots r*per_rank ..)
-    uint32_t per_rank;
+    FastDiv per_rank;
     uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
 };
@@ -353,8 +404,8 @@ template <bool PEERS>
 __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, uint32_t parent)
 {
     if (PEERS) {
-        const uint32_t r = child / p.per_rank;
-        p.anc_peer[r][child - r * p.per_rank] = parent;
+        const uint32_t r = fast_div(child, p.per_rank);
+        p.anc_peer[r][child - r * p.per_rank.d] = parent;
     } else {
         p.anc_out[child - p.out_lo] = parent;
     }
@@ -478,22 +529,28 @@ int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n)
 
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers)
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers,
+                            const MailArgs *mail_p, size_t cell0)
 {
-    if (n_out == 0) return CUSMC_OK;
-    const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
+    MailArgs mail{};
+    if (mail_p) mail = *mail_p;
+    unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
+    if (n_out == 0) {
+        if (mail.world <= 1) return CUSMC_OK;
+        grid = 1;                                  // an empty shard still takes part in the barrier
+    }
     PeerWeights pw{};
     if (peers) {
         for (int r = 0; r < peers->world; ++r) pw.w[r] = (const double *)peers->ptr[r];
-        pw.per_rank = (uint32_t)peers->per_rank;
+        pw.per_rank = make_fast_div((uint32_t)peers->per_rank);
         if (u)
-            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
         else
-            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
     } else if (u)
-        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
     else
-        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -510,23 +567,30 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
 // full_stats adds the sum of squares and the positive count (ESS).  Two launches: the tiles, then
 // one block that turns the tile sums into prefixes and totals.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats)
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
+                             const MailArgs *mail_p, int t)
 {
-    if (N == 0) return CUSMC_OK;
-    const unsigned tiles = (unsigned)image_tiles(N);
+    MailArgs mail{};
+    if (mail_p) mail = *mail_p;
+    const bool exchange = mail.world > 1;
+    if (N == 0 && !exchange) return CUSMC_OK;
+    // an empty shard still publishes (max = -inf, sums = 0): one block over zero weights
+    const unsigned tiles = N == 0 ? 1u : (unsigned)image_tiles(N);
     const bool full = full_stats && stats_dev;
+    const size_t cmax = mail_cell(t, kCellMax, mail.world), csum = mail_cell(t, kCellSums, mail.world);
     unsigned long long *img = (unsigned long long *)image;
+    double *mx = const_cast<double *>(max_dev);     // written only by the fused exchange (filter slots)
     if (full && is_log)
-        weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+        weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
     else if (full)
-        weigh_kernel<true, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+        weigh_kernel<true, false><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
     else if (is_log)
-        weigh_kernel<false, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+        weigh_kernel<false, true><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
     else
-        weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
+        weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
     CUSMC_LAUNCHED(ctx);
-    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>((unsigned long long *)image, (int64_t)tiles,
-                                                          (unsigned long long *)stats_dev, full ? 1 : 0);
+    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(img, (int64_t)tiles, (unsigned long long *)stats_dev,
+                                                          full ? 1 : 0, mail, csum);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -561,7 +625,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
     if (peers) {
         for (int r = 0; r < peers->world; ++r) p.anc_peer[r] = (uint32_t *)peers->ptr[r];
-        p.per_rank = (uint32_t)peers->per_rank;
+        p.per_rank = make_fast_div((uint32_t)peers->per_rank);
         p.out_lo = 0;
         p.out_hi = (uint32_t)N_global;
         scan_resample_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
@@ -598,7 +662,7 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
     CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
     CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
-    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr);
+    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr, nullptr, 0);
 }
 
 extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev)

@@ -2,16 +2,19 @@
 #pragma once
 
 #include "common.cuh"
+#include "mailbox.cuh"
 
 int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n);
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers);
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers,
+                            const MailArgs *mail = nullptr, size_t mail_cell0 = 0);
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
 // image: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the weight image
 // (exclusive tile prefixes + tile-local CDF) the resampling pass consumes.  stats_dev may be NULL.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats);
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
+                             const MailArgs *mail = nullptr, int t = 0);
 size_t cusmc_scan_state_bytes(int64_t N);
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,

@@ -147,7 +147,7 @@ class ShardedParticleFilter:
         lib, h = ctx.lib, self.pf.h
         if self.world > 1:
             # one-off: exchange the IPC handles of (x[0], x[1], ancestors, weights) and map the peers'
-            mine = (C.c_ubyte * (4 * _lib.IPC_HANDLE_BYTES))()
+            mine = (C.c_ubyte * (_lib.FILTER_IPC_BUFFERS * _lib.IPC_HANDLE_BYTES))()
             ctx._check(lib.cusmc_filter_ipc_export(h, mine))
             gathered = [None] * self.world
             dist.all_gather_object(gathered, bytes(mine), group=group)
@@ -186,12 +186,23 @@ class ShardedParticleFilter:
         if self.world > 1 and self.is_log:
             exchange_sums(self.slots_i64[t], self.rank, self.world, self._scratch, self.group)
 
-    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None):
+    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, exchange="p2p"):
         """Injected draws (optional) are this rank's shard; omitted ones come from Philox keyed by
-        the global slot.  Returns self; everything is enqueued on the stream."""
+        the global slot.  Returns self; everything is enqueued on the stream.
+
+        exchange="p2p" (default): the library enqueues the whole run and the per-step scalars
+        travel through peer-memory mailboxes (cusmc_filter_run_sharded) -- no collective and no
+        Python inside the time loop.  exchange="nccl": the same phases driven from here with
+        torch.distributed collectives in between (the reference formulation of the exchange)."""
         import torch.distributed as dist
         lib, h, ck = self.ctx.lib, self.pf.h, self.ctx._check
         dr = self.pf._make_draws(xi0=xi0, xi=xi, chi=chi, u=u, j=j, u0=u0, um=None)
+        if exchange not in ("p2p", "nccl"):
+            raise ValueError("exchange must be 'p2p' or 'nccl'")
+        if exchange == "p2p" and self.world > 1:
+            ck(lib.cusmc_filter_run_sharded(h, C.byref(dr)))
+            self._finish_moments()
+            return self
         ck(lib.cusmc_filter_begin(h, C.byref(dr)))
         self._after_weights(0)
         ck(lib.cusmc_filter_mark(h, 0))
@@ -202,6 +213,17 @@ class ShardedParticleFilter:
             ck(lib.cusmc_filter_propagate(h, t))
             self._after_weights(t)
         ck(lib.cusmc_filter_mark(h, 1))
+        self._finish_moments()
+        return self
+
+    def exchange_status(self):
+        """0, or which bounded spin-wait of the last p2p run timed out (results are then void)."""
+        st = C.c_uint64(0)
+        self.ctx._check(self.ctx.lib.cusmc_filter_exchange_status(self.pf.h, C.byref(st)))
+        return int(st.value)
+
+    def _finish_moments(self):
+        import torch.distributed as dist
         if self.world > 1 and self.summary_on:
             if _staged(self.moments, self.group):
                 hm = self.moments.cpu()

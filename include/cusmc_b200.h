@@ -58,6 +58,7 @@ enum cusmc_resampler {                                    /* Resamplers[...], sr
 #define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
 #define CUSMC_MAX_PEERS 8           /* ranks (GPUs of one NVLink domain) of a sharded filter */
 #define CUSMC_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
+#define CUSMC_FILTER_IPC_BUFFERS 5   /* state x 2, ancestors, weights, mailbox */
 
 typedef struct cusmc_ctx cusmc_ctx;
 
@@ -346,11 +347,20 @@ int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev);
 /* Per-step moment sums [T][2 + d] = { sum w, sum w^2, sum w x_k } of this rank's shard (device);
  * a sharded run all-reduces them (SUM) before cusmc_filter_get_summary. */
 int cusmc_filter_moments_dev(cusmc_filter *f, double **moments_dev);
-/* Peer mapping: export this rank's 4 buffers (state x 2, ancestors, weights) as
- * 4 x CUSMC_IPC_HANDLE_BYTES bytes; after an all-gather of those, attach maps every other
- * rank's buffers (cudaIpcOpenMemHandle; all_handles = world x 4 x 64 bytes, rank-major). */
+/* Peer mapping: export this rank's CUSMC_FILTER_IPC_BUFFERS buffers (state x 2, ancestors, weights,
+ * mailbox) as that many x CUSMC_IPC_HANDLE_BYTES bytes; after an all-gather of those, attach maps
+ * every other rank's buffers (cudaIpcOpenMemHandle; all_handles is rank-major). */
 int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles);
 int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all_handles);
+/*
+ * The whole sharded run enqueued by the library: the phases above, with the three scalar exchanges
+ * done by a one-warp kernel over PEER MEMORY (each rank stores its scalars and a flag into every
+ * peer's mailbox and spins, bounded, on its own) -- no collective library and no host round trip
+ * inside the time loop.  Every rank calls it collectively.  cusmc_filter_exchange_status returns
+ * non-zero if a bounded spin timed out (a peer never arrived); the run's results are then void.
+ */
+int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws);
+int cusmc_filter_exchange_status(cusmc_filter *f, uint64_t *status);
 
 /* Per-step outputs copied to the host (any pointer may be NULL):
  * mean [T][d] weighted posterior mean, ess [T], loglik [T] (log of the mean weight). */

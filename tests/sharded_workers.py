@@ -100,11 +100,11 @@ def gpu_filter_worker(rank, world, port, backend, devices, cfg, out_dir):
     pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, 0.5 * I, 0.3 * I,
                                           resampler=cfg["resampler"], distribution=cfg.get("dist", "mvn"),
                                           df=cfg.get("df", 0.0), seed=cfg["seed"], summary=True)
-    pf.run()
+    pf.run(exchange=cfg.get("exchange", "p2p"))
     x, w, a = pf.local_state()
     s = pf.summary()
     np.savez(os.path.join(out_dir, "rank%d.npz" % rank), x=x, w=w, a=a, mean=s["mean"], ess=s["ess"],
-             loglik=s["loglik"], lo=pf.plan.lo, n=pf.plan.n)
+             loglik=s["loglik"], lo=pf.plan.lo, n=pf.plan.n, status=pf.exchange_status())
     pf.close()
     ctx.close()
     dist.destroy_process_group()

@@ -49,14 +49,18 @@ def run_single(ctx, cfg):
     return h, s
 
 
+@pytest.mark.timeout(600)
+@pytest.mark.parametrize("exchange", ["p2p", "nccl"])
 @pytest.mark.parametrize("resampler,world,N,d", [
     ("systematic", 2, 6000, 2),
     ("systematic", 2, 5001, 8),      # ragged: the last rank owns one slot fewer
     ("systematic", 3, 4097, 4),
     ("metropolis", 2, 4096, 2),
 ])
-def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d):
-    cfg = dict(d=d, T=9, N=N, resampler=resampler, seed=2024, yseed=31)
+def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d, exchange):
+    """exchange = p2p: scalars through peer-memory mailboxes, whole run enqueued by the library;
+    nccl: the same phases with torch.distributed collectives in between."""
+    cfg = dict(d=d, T=9, N=N, resampler=resampler, seed=2024, yseed=31, exchange=exchange)
     h, s = run_single(ctx, cfg)
     parts = run_sharded(tmp_path, world, cfg)
     x = np.concatenate([p["x"] for p in parts], axis=1)           # [d][N]
@@ -65,6 +69,7 @@ def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d
     assert np.array_equal(a, h["a"][-1])
     assert np.array_equal(x.T, h["x"][-1])
     assert np.array_equal(w, h["w"][-1])
+    assert all(int(p["status"]) == 0 for p in parts)      # no spin-wait timed out
     for p in parts:          # every rank reports the GLOBAL summary
         if resampler != "metropolis":
             assert np.allclose(p["ess"], s["ess"], rtol=1e-12)
@@ -72,6 +77,7 @@ def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d
         assert np.allclose(p["mean"], s["mean"], rtol=1e-9, atol=1e-12)
 
 
+@pytest.mark.timeout(600)
 def test_sharded_mvt_noise(ctx, tmp_path):
     cfg = dict(d=4, T=6, N=3000, resampler="systematic", seed=7, yseed=32, dist="mvt", df=5.0)
     h, _ = run_single(ctx, cfg)
