@@ -17,7 +17,10 @@
 // One peer-mapped pointer per rank of a sharded run (rank r owns global slots
 // r * per_rank .. ), see cusmc_ipc_open.
 struct CusmcPeers {
-    void *ptr[CUSMC_MAX_PEERS];
+    void *ptr[CUSMC_MAX_PEERS];   // host copy (lifetime management)
+    void **table_dev;             // the same world pointers in DEVICE memory: kernels index this with a
+                                  // load -- indexing a kernel-parameter array by a runtime value would
+                                  // make every thread copy the whole parameter block to local memory
     int64_t per_rank;
     int world;
 };

@@ -443,6 +443,7 @@ struct cusmc_filter {
     CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
     unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
     unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
+    void **peer_tables = nullptr;             // device: [5 buffers][CUSMC_MAX_PEERS] peer pointers
     unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
     bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
     double *x[2] = {nullptr, nullptr};
@@ -466,7 +467,7 @@ static MailArgs filter_mail(const cusmc_filter *f)
 {
     MailArgs m{};
     if (f->world > 1 && f->fused) {
-        for (int r = 0; r < f->world; ++r) m.peer[r] = (unsigned long long *)f->peer_mail.ptr[r];
+        m.peer = (unsigned long long *const *)f->peer_mail.table_dev;
         m.err = f->mail_err;
         m.epoch = f->epoch;
         m.rank = f->rank;
@@ -474,7 +475,6 @@ static MailArgs filter_mail(const cusmc_filter *f)
     }
     return m;
 }
-
 
 // Symmetric eigen factor Q = V sqrt(Lambda) (reference: eigenSolver, src/linear_algebra.cpp:10-23)
 // by cyclic Jacobi; any Q with Q Q^T = Sigma gives the same law, the eigen form is kept so the
@@ -549,6 +549,7 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     cudaFree(f->scan_state);
     cudaFree(f->mail);
     cudaFree(f->mail_err);
+    cudaFree(f->peer_tables);
     cudaFree(f->hist_x);
     cudaFree(f->hist_w);
     cudaFree(f->hist_a);
@@ -702,6 +703,13 @@ extern "C" int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all
                                   cudaGetErrorString(e));
             }
         }
+    // the pointer tables the kernels index live in device memory
+    void *host_tab[kIpcBuffers][CUSMC_MAX_PEERS] = {};
+    for (int b = 0; b < kIpcBuffers; ++b)
+        for (int r = 0; r < f->world; ++r) host_tab[b][r] = tabs[b]->ptr[r];
+    if (!f->peer_tables) CUSMC_CUDA(ctx, cudaMalloc((void **)&f->peer_tables, sizeof host_tab));
+    CUSMC_CUDA(ctx, cudaMemcpy(f->peer_tables, host_tab, sizeof host_tab, cudaMemcpyHostToDevice));
+    for (int b = 0; b < kIpcBuffers; ++b) tabs[b]->table_dev = f->peer_tables + (size_t)b * CUSMC_MAX_PEERS;
     return CUSMC_OK;
 }
 
@@ -834,11 +842,8 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
         const double *u = dr.u_dev ? dr.u_dev + off * n * cfg.B : nullptr;
         const uint32_t *j = dr.j_dev ? dr.j_dev + off * n * cfg.B : nullptr;
-        const MailArgs mail = filter_mail(f);
-        // fused gate: every rank's weights of step t - 1 are complete before anyone reads them
         return cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log,
-                                       f->lo, n, sharded ? &f->peer_lw : nullptr, &mail,
-                                       mail_cell(t, kCellMax, f->world));
+                                       f->lo, n, sharded ? &f->peer_lw : nullptr);
     }
     StepSlot *prev = &f->slots[t - 1];
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
@@ -890,10 +895,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     if (f->world > 1) {
         a.world = f->world;
         a.per_rank = make_fast_div((uint32_t)f->per);
-        for (int r = 0; r < f->world; ++r) a.x_prev_peer[r] = (const double *)f->peer_x[f->cur].ptr[r];
-        // fused barrier: every rank's ancestors (peer stores) have landed before anyone gathers
-        a.mail = filter_mail(f);
-        a.mail_cell0 = mail_cell(t, kCellBarrier, f->world);
+        a.x_prev_peer = (const double *const *)f->peer_x[f->cur].table_dev;
     }
     CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
                                   f->ep, a, a.xi == nullptr));
@@ -911,24 +913,60 @@ extern "C" int cusmc_filter_mark(cusmc_filter *f, int which)
 }
 
 // ---- the sharded run ------------------------------------------------------------------------------
-// The whole sharded run enqueued from C++: the phases of cusmc_filter_run; the per-step max, sums
-// and barrier travel through the peer-memory mailboxes INSIDE weigh / tile-scan / propagate
-// (metropolis: inside the resampler), so a step launches the same four kernels as on one GPU.
-// Every rank calls it the same number of times (the epoch must agree); returns after enqueueing.
+// One-warp exchange kernels (mailbox.cuh): all-reduce(MAX) of the step's log-weight max, or a plain
+// barrier.  (The third exchange, the sums, rides in the tail of tile_scan_kernel.)
+template <bool MAX>
+__global__ void __launch_bounds__(32) exchange_kernel(const MailArgs m, size_t cell0, StepSlot *slot)
+{
+    const int lane = threadIdx.x;
+    mail_publish(m, cell0, lane, MAX ? (unsigned long long)__double_as_longlong(slot->lw_max) : 0ull, 0, 0);
+    unsigned long long w0, w1, w2;
+    mail_wait(m, cell0, lane, w0, w1, w2);
+    if (MAX) {
+        double v = lane < m.world ? __longlong_as_double((long long)w0) : -INFINITY;
+        if (!(v == v)) v = -INFINITY;
+        v = warp_max_double(v);
+        if (lane == 0) slot->lw_max = v;       // the slot now holds the GLOBAL max
+    }
+}
+
+static int launch_exchange(cusmc_filter *f, bool max, int cell, int t)
+{
+    cusmc_ctx *ctx = f->ctx;
+    const MailArgs m = filter_mail(f);
+    const size_t cell0 = mail_cell(t, cell, f->world);
+    if (max) exchange_kernel<true><<<1, 32, 0, ctx->stream>>>(m, cell0, f->slots + t);
+    else exchange_kernel<false><<<1, 32, 0, ctx->stream>>>(m, cell0, f->slots + t);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+// The whole sharded run enqueued from C++: the phases of cusmc_filter_run with the per-step max,
+// sums and barrier travelling through the peer-memory mailboxes.  Every rank calls it the same
+// number of times (the epoch must agree); returns after enqueueing.
 extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws)
 {
     if (!f) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(f->ctx, f->world > 1 && f->attached, "needs a sharded filter with attached peers");
+    const bool is_log = f->is_log != 0;
     ++f->epoch;
     f->fused = true;
+    auto after_weights = [&](int t) -> int {
+        // slot[t] holds this rank's max: make it global (metropolis: just a barrier, peers read
+        // these weights next); weigh then exchanges the sums inside its tile-scan kernel
+        CUSMC_CHECK(launch_exchange(f, is_log, kCellMax, t));
+        return cusmc_filter_weigh(f, t);
+    };
     int rc = cudaMemsetAsync(f->mail_err, 0, 8, f->ctx->stream) == cudaSuccess ? CUSMC_OK : CUSMC_ERR_CUDA;
     if (rc == CUSMC_OK) rc = cusmc_filter_begin(f, draws);
-    if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, 0);
+    if (rc == CUSMC_OK) rc = after_weights(0);
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 0);
     for (int t = 1; t < f->cfg.T && rc == CUSMC_OK; ++t) {
         rc = cusmc_filter_resample(f, t);
+        // ancestors went into the peers' arrays: after this barrier everyone's stores have landed
+        if (rc == CUSMC_OK) rc = launch_exchange(f, false, kCellBarrier, t);
         if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
-        if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, t);
+        if (rc == CUSMC_OK) rc = after_weights(t);
     }
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 1);
     f->fused = false;

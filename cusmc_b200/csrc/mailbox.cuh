@@ -4,10 +4,11 @@
 // that its peers map with CUDA IPC.  Publishing = lane r of one warp stores this rank's payload
 // into entry [cell][rank] of rank r's mailbox (a peer store over NVLink), fences at system scope,
 // then stores the flag; waiting = lane r spins on entry [cell][r] of the rank's OWN mailbox (local
-// memory the peers write).  The exchanges are FUSED into the compute kernels on either side of
-// them -- block 0 publishes in its prologue / epilogue, every block that needs the result gates on
-// the flags -- so a sharded step launches exactly the kernels a single-GPU step does: no collective
-// library, no extra launches, no host round trip.
+// memory the peers write).  No collective library and no host round trip inside the time loop.
+// The sums exchange is fused into the tail of the (single-block) tile-scan kernel; the max exchange
+// and the barrier are one-warp kernels.  (Gating every block of the big kernels on the flags was
+// tried: an extra dependent L2 round trip + system fence per block cost 100 us per step at 32 Ki
+// blocks.)
 //
 // Flags carry the run epoch, so a mailbox is never cleared.  Spins are bounded (2 s): on a timeout
 // the error word is set and the kernel goes on (results void) instead of hanging the GPU.
@@ -18,7 +19,7 @@
 enum { kCellMax = 0, kCellSums = 1, kCellBarrier = 2, kMailCells = 3 };
 
 struct MailArgs {
-    unsigned long long *peer[CUSMC_MAX_PEERS];   // every rank's mailbox (own one included)
+    unsigned long long *const *peer;              // device table: every rank's mailbox (own one included)
     unsigned long long *err;
     unsigned long long epoch;
     int rank, world;                              // world <= 1: no exchange
@@ -76,17 +77,4 @@ __device__ __forceinline__ void mail_wait(const MailArgs &m, size_t cell0, int l
     }
 }
 
-// Barrier fused into a kernel prologue: block 0 announces "everything this rank enqueued before
-// this kernel is complete" (stream order guarantees it), every block waits for all ranks' flags.
-// Call from all threads of the block; ends with __syncthreads().
-__device__ __forceinline__ void mail_gate(const MailArgs &m, size_t cell0)
-{
-    if (m.world <= 1) return;
-    if (threadIdx.x < 32) {
-        if (blockIdx.x == 0) mail_publish(m, cell0, threadIdx.x, 0, 0, 0);
-        unsigned long long a, b, c;
-        mail_wait(m, cell0, threadIdx.x, a, b, c);
-    }
-    __syncthreads();
-}
 #endif

@@ -3,7 +3,6 @@
 #pragma once
 
 #include "density.cuh"
-#include "mailbox.cuh"
 
 #include <vector>
 
@@ -31,11 +30,9 @@ struct StepArgs {
     // peer form (world > 1): anc holds GLOBAL parent ids, parent g lives on rank g / per_rank at
     // column g % per_rank of that rank's state buffer (leading dimension ld_prev on every rank),
     // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.
-    const double *x_prev_peer[CUSMC_MAX_PEERS];
+    const double *const *x_prev_peer;   // device table of the ranks' state buffers
     FastDiv per_rank;
     int world;
-    MailArgs mail;               // mail.world > 1: gate on the ranks' barrier flags before reading peers
-    size_t mail_cell0;
 };
 
 // G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no

@@ -95,7 +95,6 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
     const bool active = i < a.n_out;
     const int d = EXACT ? D : a.d;
     double lw = -INFINITY;
-    mail_gate(a.mail, a.mail_cell0);          // sharded runs only (no-op otherwise)
     if (active) {
         double xp[D], z[D], xn[D];
         int64_t parent = i;
@@ -118,7 +117,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             const double *src = a.x_prev + parent;
             if (a.world > 1) {
                 const uint32_t g = (uint32_t)parent, r = fast_div(g, a.per_rank);
-                src = a.x_prev_peer[r] + (g - r * a.per_rank.d);
+                src = a.x_prev_peer[r] + (g - r * a.per_rank.d);   // table in device memory
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
@@ -233,7 +232,7 @@ int launch_one(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const Ste
 {
     StepOp<D, DIAG> op;
     fill_step_op<D, DIAG>(op, m);
-    const unsigned grid = a.n_out > 0 ? (unsigned)((a.n_out + kThreads - 1) / kThreads) : 1u;
+    const unsigned grid = (unsigned)((a.n_out + kThreads - 1) / kThreads);
     if (philox)
         pf_step_kernel<D, true, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
     else

@@ -25,7 +25,7 @@ int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const doub
     const int dm = d > dy ? d : dy;
     if (dm > CUSMC_MAX_DIM || d < 1)
         return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "dimension %d not in 1..%d", dm, CUSMC_MAX_DIM);
-    if (a.n_out == 0 && a.mail.world <= 1) return CUSMC_OK;   // an empty shard still joins the barrier
+    if (a.n_out == 0) return CUSMC_OK;
     const bool exact = d == dy && d == cusmc_pad_dim(dm);
     bool diag = exact && is_diag_colmajor(G, d) && is_diag_colmajor(Q, d);
     if (diag && M)

@@ -24,7 +24,7 @@ constexpr int kThreads = 256;
 // Sharded runs: the weight vector is the concatenation of every rank's shard (per_rank slots
 // each), read through peer-mapped pointers over NVLink.
 struct PeerWeights {
-    const double *w[CUSMC_MAX_PEERS];
+    const double *const *w;      // device table of the ranks' weight arrays
     FastDiv per_rank;
 };
 
@@ -42,10 +42,8 @@ template <bool PREDRAWN, bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const PeerWeights pw,
                   const double *__restrict__ u, const uint32_t *__restrict__ j, uint64_t seed,
-                  uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out,
-                  const MailArgs mail, size_t mail_cell0)
+                  uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out)
 {
-    if (PEERS) mail_gate(mail, mail_cell0);   // every rank's weights are complete (fused barrier)
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= n_out) return;
     const int64_t i = i0 + t;              // global particle index (i0 = 0 on one GPU)
@@ -176,34 +174,12 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 // FULL: also sum of squares and positive count (ESS); otherwise only what resampling needs.
 template <bool FULL, bool LOG>
 __global__ void __launch_bounds__(kThreads)
-weigh_kernel(const double *__restrict__ w, double *__restrict__ wmax_p, int64_t N,
-             int shift, unsigned long long *__restrict__ image, const MailArgs mail, size_t cell_max)
+weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, int64_t N,
+             int shift, unsigned long long *__restrict__ image)
 {
     __shared__ unsigned long long sm[kThreads / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    double wmax;
-    if (mail.world > 1) {
-        // fused all-reduce(MAX) over the ranks: block 0 publishes this rank's max, every block
-        // takes the maximum of what the ranks published
-        __shared__ double s_max;
-        if (warp == 0) {
-            if (blockIdx.x == 0)
-                mail_publish(mail, cell_max, lane, (unsigned long long)__double_as_longlong(*wmax_p), 0, 0);
-            unsigned long long b0, b1, b2;
-            mail_wait(mail, cell_max, lane, b0, b1, b2);
-            double m = lane < mail.world ? __longlong_as_double((long long)b0) : -INFINITY;
-            if (!(m == m)) m = -INFINITY;
-            m = warp_max_double(m);
-            if (lane == 0) {
-                s_max = m;
-                if (blockIdx.x == 0) *wmax_p = m;      // the slot now holds the GLOBAL max
-            }
-        }
-        __syncthreads();
-        wmax = s_max;
-    } else {
-        wmax = *wmax_p;
-    }
+    const double wmax = *wmax_p;
     const int64_t base = (int64_t)blockIdx.x * kTile + (int64_t)threadIdx.x * kTileItems;
     double v[kTileItems];
     load_tile_items(w, base, N, v);
@@ -392,7 +368,7 @@ struct ScanArgs {
     const unsigned long long *local;       // weight image: inclusive prefix of weight i inside its tile
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
-    uint32_t *anc_peer[CUSMC_MAX_PEERS];   // PEERS: rank r's ancestor array (child slots r*per_rank ..)
+    uint32_t *const *anc_peer;             // PEERS: device table, rank r's ancestor array (child slots r*per_rank ..)
     FastDiv per_rank;
     uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
@@ -529,28 +505,22 @@ int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n)
 
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers,
-                            const MailArgs *mail_p, size_t cell0)
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers)
 {
-    MailArgs mail{};
-    if (mail_p) mail = *mail_p;
-    unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
-    if (n_out == 0) {
-        if (mail.world <= 1) return CUSMC_OK;
-        grid = 1;                                  // an empty shard still takes part in the barrier
-    }
+    if (n_out == 0) return CUSMC_OK;
+    const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
     PeerWeights pw{};
     if (peers) {
-        for (int r = 0; r < peers->world; ++r) pw.w[r] = (const double *)peers->ptr[r];
+        pw.w = (const double *const *)peers->table_dev;
         pw.per_rank = make_fast_div((uint32_t)peers->per_rank);
         if (u)
-            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
+            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
         else
-            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
+            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
     } else if (u)
-        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
+        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
     else
-        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out, mail, cell0);
+        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -577,17 +547,16 @@ int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const 
     // an empty shard still publishes (max = -inf, sums = 0): one block over zero weights
     const unsigned tiles = N == 0 ? 1u : (unsigned)image_tiles(N);
     const bool full = full_stats && stats_dev;
-    const size_t cmax = mail_cell(t, kCellMax, mail.world), csum = mail_cell(t, kCellSums, mail.world);
+    const size_t csum = mail_cell(t, kCellSums, mail.world);
     unsigned long long *img = (unsigned long long *)image;
-    double *mx = const_cast<double *>(max_dev);     // written only by the fused exchange (filter slots)
     if (full && is_log)
-        weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
+        weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     else if (full)
-        weigh_kernel<true, false><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
+        weigh_kernel<true, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     else if (is_log)
-        weigh_kernel<false, true><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
+        weigh_kernel<false, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     else
-        weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, mx, N, shift, img, mail, cmax);
+        weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     CUSMC_LAUNCHED(ctx);
     tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(img, (int64_t)tiles, (unsigned long long *)stats_dev,
                                                           full ? 1 : 0, mail, csum);
@@ -624,7 +593,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.u0 = u0;
     const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
     if (peers) {
-        for (int r = 0; r < peers->world; ++r) p.anc_peer[r] = (uint32_t *)peers->ptr[r];
+        p.anc_peer = (uint32_t *const *)peers->table_dev;
         p.per_rank = make_fast_div((uint32_t)peers->per_rank);
         p.out_lo = 0;
         p.out_hi = (uint32_t)N_global;
@@ -662,7 +631,7 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
     CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
     CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
-    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr, nullptr, 0);
+    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr);
 }
 
 extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev)
