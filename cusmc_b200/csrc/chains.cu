@@ -73,17 +73,41 @@ mh_chains_kernel(const ChainArgs a)
 
     const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
     double z_next = (zc && live) ? ld_stream(zc + lane) : 0.0;
+    // In-kernel randomness is generated in batches so that no Philox block is computed twice and
+    // none of its output is thrown away; the (seed, chain, step, component) -> draw mapping is the
+    // one of cusmc_philox.h, unchanged:
+    //  * thresholds: every 32 steps lane l computes the threshold of step s + l (one Philox block,
+    //    one log, one exp per lane per 32 steps instead of per step), broadcast per step;
+    //  * normals: lanes 4m .. 4m+3 share the block (step, m).  Every 4 steps lane 4m+k computes the
+    //    block of step s + k -- four normals, one for each lane of its quad -- and a 4 x 4 exchange
+    //    inside the quad hands every lane its own normal of steps s .. s + 3.
+    double thr_batch = 0.0;
+    float zq[4] = {0.f, 0.f, 0.f, 0.f};    // zq[r]: this lane's normal of step s0 + ((lane & 3) ^ r)
     for (int s = 0; s < a.steps; ++s) {
         double z, thr;
         if (PHILOX) {
-            // lanes 4m .. 4m+3 share one Philox block; each keeps the Box-Muller pair it needs
-            const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)s, (uint64_t)c, (uint32_t)(lane >> 2));
-            float z0, z1;
-            cusmc_box_muller_f32((lane & 2) ? rz.v[2] : rz.v[0], (lane & 2) ? rz.v[3] : rz.v[1], &z0, &z1);
-            z = live ? (double)((lane & 1) ? z1 : z0) : 0.0;
-            const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)s, (uint64_t)c, 0);
-            const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
-            thr = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+            if ((s & 31) == 0) {
+                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + lane), (uint64_t)c, 0);
+                const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+                thr_batch = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+            }
+            thr = __shfl_sync(0xffffffffu, thr_batch, s & 31);
+            if ((s & 3) == 0) {
+                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (lane & 3)), (uint64_t)c,
+                                                 (uint32_t)(lane >> 2));
+                float n[4];
+                cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+                cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int pick = (lane & 3) ^ r;        // the normal owed to lane ^ r
+                    const float v = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
+                    zq[r] = __shfl_xor_sync(0xffffffffu, v, r);
+                }
+            }
+            const int r = (lane & 3) ^ (s & 3);
+            const float zf = r == 0 ? zq[0] : r == 1 ? zq[1] : r == 2 ? zq[2] : zq[3];
+            z = live ? (double)zf : 0.0;
         } else {
             z = z_next;
             if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + lane);   // prefetch

@@ -523,6 +523,36 @@ def test_mh_chains_bit_exact(ctx, orc, kind, nu, d, shared):
     assert 0.05 < want_bits.mean() < 0.99
 
 
+@pytest.mark.parametrize("kind,nu,d", [("mvn", 0.0, 8), ("mvt", 5.0, 32), ("mvt", 3.0, 5)])
+def test_mh_chains_device_rng_matches_oracle_mirror(ctx, orc, kind, nu, d):
+    """Device-drawn chains: the kernel batches its Philox blocks (thresholds per 32 steps, normals per
+    4 steps and quad of lanes) but must consume exactly the (seed, chain, step, component) -> draw
+    mapping of cusmc_philox.h.  The oracle regenerates those draws on the host and runs the chains
+    with them: accept bits and final states agree bit for bit."""
+    import torch
+    rng = np.random.default_rng(4100 + d)
+    Cn, steps, step, seed = 48, 70, 0.3, 991
+    L = np.stack([np.linalg.cholesky(spd(rng, d)) for _ in range(Cn)])
+    mu = rng.standard_normal((Cn, d))
+    x0 = rng.standard_normal((Cn, d))
+    z = np.stack([orc.rng_fill_normals(seed, 4, s, 0, Cn, d) for s in range(steps)], axis=1)   # CHAIN_Z
+    thr = np.empty((Cn, steps))
+    for c in range(Cn):
+        for s in range(steps):
+            e = -float(orc.det_log(orc.rng_u01(seed, 5, s, c) + 2.0 ** -53)[0])             # CHAIN_U, (0, 1]
+            thr[c, s] = e if kind == "mvn" else float(orc.det_exp((e + e) / (nu + d))[0])
+    want_x, want_n, want_bits = orc.mh_chains(kind, mu, L, x0, z, thr, step, nu=nu, shared=False)
+    x = torch_dev(x0)
+    nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+    bits = torch.zeros((Cn, steps), dtype=torch.uint8, device="cuda")
+    ctx.mh_chains_dev(kind, torch_dev(mu), torch_dev(L.transpose(0, 2, 1)), x, steps, step, nu=nu, seed=seed,
+                      n_accept=nacc, accept_bits=bits)
+    ctx.synchronize()
+    assert np.array_equal(bits.cpu().numpy(), want_bits)
+    assert np.array_equal(x.cpu().numpy(), want_x)
+    assert 0.05 < want_bits.mean() < 0.99
+
+
 def test_mh_chains_device_rng_moments(ctx):
     """Philox-driven chains on an MVN target: time-averaged first and second moments of many chains
     against the target's, 5 sigma Monte Carlo tolerance with the chain autocorrelation folded in."""
