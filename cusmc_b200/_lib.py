@@ -70,8 +70,6 @@ PROTOTYPES = {
     "cusmc_metropolis_hastings_dev": (ci, [vp, vp, vp, vp, vp, u64, u64, i64, ci, ci]),
     "cusmc_propagate_reweight_dev": (ci, [vp, ci, ci, vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp,
                                           vp, flt, vp, vp, u64, u64, vp, vp]),
-    "cusmc_pf_step_children_dev": (ci, [vp, ci, ci, vp, vp, i64, i64, i64, vp, i64, vp, i64, i64, vp, i64, i64,
-                                        ci, ci, vp, vp, vp, vp, vp, vp, flt, dbl, u64, u64, ci, vp]),
     "cusmc_weights_max_dev": (ci, [vp, vp, i64, vp]),
     "cusmc_tile_prefix_words": (i64, [i64]),
     "cusmc_weights_sum_dev": (ci, [vp, vp, ci, vp, i64, i64, vp, vp]),

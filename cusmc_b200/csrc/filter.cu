@@ -356,65 +356,6 @@ extern "C" int cusmc_mvt_sample(cusmc_ctx *ctx, double *x_new_aos, const double 
                          CUSMC_STREAM_NORMAL, N, d, df);
 }
 
-// ---- extern "C": one sharded step (child form), see cusmc_b200/sharded.py ---------------------------
-extern "C" int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log, double *x_own_dev,
-                                          double *lw_own_dev, int64_t ld_own, int64_t own_lo, int64_t own_n,
-                                          double *side_dev, int64_t ld_side, const double *x_prev_dev,
-                                          int64_t ld_prev, int64_t parent_base, const uint32_t *a_dev,
-                                          int64_t child_lo, int64_t n_children, int d, int dy,
-                                          const double *mu, const double *G, const double *Q, const double *y,
-                                          const double *F, const double *V, float nu, double const_weight,
-                                          uint64_t seed, uint64_t step, int rng_stream, double *lw_max_dev)
-{
-    if (!ctx) return CUSMC_ERR_INVALID;
-    CUSMC_REQUIRE(ctx, n_children >= 0 && d >= 1 && dy >= 1 && own_n >= 0, "bad sizes");
-    CUSMC_REQUIRE(ctx, Q != nullptr, "Q is NULL");
-    CUSMC_REQUIRE(ctx, !G || x_prev_dev, "G given without parents");
-    CUSMC_REQUIRE(ctx, !V || (y && F), "V given without y / F");
-    if (n_children == 0) return CUSMC_OK;
-    const int64_t lo = child_lo > own_lo ? child_lo : own_lo;
-    const int64_t hi = (child_lo + n_children) < (own_lo + own_n) ? (child_lo + n_children) : (own_lo + own_n);
-    const int64_t n_own = hi > lo ? hi - lo : 0;
-    CUSMC_REQUIRE(ctx, n_own == n_children || side_dev, "children fall outside the own range but side is NULL");
-    CUSMC_REQUIRE(ctx, n_own == n_children || ld_side >= n_children - n_own, "side buffer too small");
-    CUSMC_REQUIRE(ctx, n_own == 0 || (x_own_dev && lw_own_dev && ld_own >= own_n), "own buffers missing");
-    std::vector<double> M, Winv;
-    Epilogue ep{};
-    double c[CUSMC_MAX_DIM] = {0};
-    if (V) {
-        CUSMC_CHECK(build_observation(ctx, kind, want_log, d, dy, F, V, nu, M, Winv, ep));
-        whiten_observation(Winv, dy, y, c);
-    }
-    StepArgs a{};
-    a.x_new = x_own_dev;
-    a.lw = lw_own_dev;
-    a.ld_new = ld_own;
-    a.x_prev = x_prev_dev;
-    a.ld_prev = ld_prev;
-    a.parent_base = parent_base;
-    a.anc = a_dev;
-    a.lw_max = lw_max_dev;
-    a.n_out = n_children;
-    a.i0 = child_lo;
-    a.seed = seed;
-    a.step = step;
-    a.nu = nu;
-    a.d = d;
-    a.dy = dy;
-    a.kind = kind;
-    a.has_prev = G ? 1 : 0;
-    a.skip_weight = V ? 0 : 1;
-    a.const_weight = const_weight;
-    a.rng_stream = rng_stream;
-    a.sharded = 1;
-    a.own_lo = own_lo;
-    a.own_n = own_n;
-    a.n_own_children = n_own;
-    a.side = side_dev;
-    a.ld_side = ld_side;
-    return cusmc_launch_step(ctx, d, dy, G, Q, 1.0, V ? &M : nullptr, c, mu, ep, a, true);
-}
-
 // ================================================================================================
 // The filter object: particle_filter() / initialize() / MCMC() of the reference
 // (src/particle_filter.cpp:6-39, src/mcmc.cpp:44-88,239-309) with device-resident state.

@@ -21,12 +21,6 @@ struct StepArgs {
     double const_weight;         // used when skip_weight
     float nu;
     int d, dy, kind, has_prev, skip_weight, rng_stream;
-    // sharded runs (sharded != 0): child i0 + i goes to slot (child - own_lo) of x_new / lw when it
-    // falls in [own_lo, own_lo + own_n), otherwise to the side buffer [(d + 1)][ld_side] (rows
-    // 0..d-1 state, row d weight) in child order, to be shipped to the owning rank.
-    int64_t own_lo, own_n, n_own_children, ld_side;
-    double *side;
-    int sharded;
     // peer form (world > 1): anc holds GLOBAL parent ids, parent g lives on rank g / per_rank at
     // column g % per_rank of that rank's state buffer (leading dimension ld_prev on every rank),
     // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.

@@ -97,22 +97,16 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
     double lw = -INFINITY;
     if (active) {
         double xp[D], z[D], xn[D];
+        // Order matters for latency: the ancestor load is issued first, the first Philox block
+        // (pure integer work) runs while it is in flight, then the parent gather goes out and the
+        // Box-Muller transforms and the remaining blocks run under ITS latency.
         int64_t parent = i;
         if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
         double *dst_x = a.x_new + i, *dst_lw = a.lw + i;
-        int64_t dst_ld = a.ld_new;
-        if (a.sharded) {
-            const int64_t child = a.i0 + i;
-            if (child >= a.own_lo && child < a.own_lo + a.own_n) {
-                dst_x = a.x_new + (child - a.own_lo);
-                dst_lw = a.lw + (child - a.own_lo);
-            } else {
-                const int64_t sidx = child < a.own_lo ? i : i - a.n_own_children;
-                dst_x = a.side + sidx;
-                dst_lw = a.side + (int64_t)a.d * a.ld_side + sidx;
-                dst_ld = a.ld_side;
-            }
-        }
+        const int64_t dst_ld = a.ld_new;
+        const uint64_t idx = (uint64_t)(a.i0 + i);
+        cusmc_u32x4 r0;
+        if (PHILOX) r0 = cusmc_rng(a.seed, a.rng_stream, a.step, idx, 0u);
         if (a.has_prev) {
             const double *src = a.x_prev + parent;
             if (a.world > 1) {
@@ -127,11 +121,11 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         }
         if (PHILOX) {
             // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
-            const uint64_t idx = (uint64_t)(a.i0 + i);
 #pragma unroll
             for (int jq = 0; jq < (D + 3) / 4; ++jq) {
                 double zq[4] = {0.0, 0.0, 0.0, 0.0};
-                if (EXACT || 4 * jq < d) cusmc_normal4(cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq), zq);
+                if (EXACT || 4 * jq < d)
+                    cusmc_normal4(jq == 0 ? r0 : cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq), zq);
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
                     if (4 * jq + e < D) z[4 * jq + e] = (EXACT || 4 * jq + e < d) ? zq[e] : 0.0;

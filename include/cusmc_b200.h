@@ -171,26 +171,6 @@ int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_log,
                                  double *lw_dev, double *lw_max_dev);
 
 /*
- * One step of a SHARDED filter, child form: this rank owns parents x_prev_dev (global indices
- * parent_base ..) and computes the children child_lo .. child_lo + n_children - 1 that the global
- * systematic resampling assigned to them (a_dev: global parent ids from
- * cusmc_resample_systematic_dev).  A child whose global slot lies in the rank's own slot range
- * [own_lo, own_lo + own_n) is written to x_own_dev / lw_own_dev at (slot - own_lo); the others go,
- * in child order, to side_dev [(d + 1)][ld_side] (rows 0..d-1 state, row d weight) for the caller
- * to ship to the owning rank.  Noise is Philox keyed by the GLOBAL child slot, so any sharding
- * gives the same particles.  G = NULL: no parent term (initialisation, x = mu + Q z);
- * V = NULL: weights are not computed (every weight = const_weight).
- */
-int cusmc_pf_step_children_dev(cusmc_ctx *ctx, int kind, int want_log, double *x_own_dev,
-                               double *lw_own_dev, int64_t ld_own, int64_t own_lo, int64_t own_n,
-                               double *side_dev, int64_t ld_side, const double *x_prev_dev,
-                               int64_t ld_prev, int64_t parent_base, const uint32_t *a_dev,
-                               int64_t child_lo, int64_t n_children, int d, int dy,
-                               const double *mu, const double *G, const double *Q, const double *y,
-                               const double *F, const double *V, float nu, double const_weight,
-                               uint64_t seed, uint64_t step, int rng_stream, double *lw_max_dev);
-
-/*
  * Weight normalisation and resampling on the deterministic fixed-point image (DESIGN.md,
  * include/cusmc_detmath.h):
  *   wn_i = exp(lw_i - max)  (log weights, cusmc_det_exp)   or   w_i / max  (linear weights)
