@@ -41,6 +41,14 @@ def workload_inputs():
     return mu, sigma
 
 
+def ncu_traffic():
+    """DRAM bytes per launch of the headline kernel from the committed ncu --set full capture."""
+    try:
+        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["traffic_bytes_per_launch"])
+    except Exception:
+        return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -399,7 +407,7 @@ def main():
                                 % (POOL_BATCHES, POOL_BATCHES * N_POINTS * DIM * 8 / 2 ** 20),
                    "parallelism": "points sharded across ranks, no data-path collective"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
-                     "frac": achieved / hbm_gbs, "traffic": None, "peak_source": peak_src,
+                     "frac": achieved / hbm_gbs, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel": "density_soa_kernel<16,true,1,true>", "algorithmic_bytes_per_launch": BYTES_PER_EVAL * N_POINTS,
                      "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
