@@ -37,7 +37,7 @@ class FilterConfig(C.Structure):
         ("N", i64), ("d", ci), ("dy", ci), ("T", ci), ("kind", ci), ("resampler", ci), ("B", ci),
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
-        ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci),
+        ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci),
     ]
 
 

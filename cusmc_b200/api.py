@@ -385,13 +385,15 @@ class ParticleFilter:
     """particle_filter() of the reference (src/particle_filter.cpp:6-39) with device-resident state."""
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
-                 df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1):
+                 df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
+                 persistent=False):
         self.ctx = ctx
         Y = np.asarray(Y, dtype=np.float64)
         F = np.asarray(F, dtype=np.float64)
         self.dy, self.T = Y.shape
         self.d = np.asarray(G).shape[0]
         self.N = int(N)
+        self._world = int(world)
         per = -(-self.N // max(1, int(world)))
         self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
         self._keep = [_colmajor(Y), _f64(m0), _colmajor(C0), _colmajor(F), _colmajor(G), _colmajor(V),
@@ -408,6 +410,7 @@ class ParticleFilter:
         cfg.keep_history = int(keep_history)
         cfg.summary = int(summary)
         cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
+        cfg.persistent = 1 if persistent else 0       # opt-in: one cooperative kernel per run when eligible
         self.keep_history = bool(keep_history)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
@@ -450,6 +453,22 @@ class ParticleFilter:
         ll = np.empty(self.T)
         self.ctx._check(self.ctx.lib.cusmc_filter_get_summary(self.h, _hp(mean), _hp(ess), _hp(ll)))
         return dict(mean=mean, ess=ess, loglik=ll)
+
+    def state(self):
+        """Current device-resident state copied to the host: x (d, n) SoA, weights (n,) (log-weights
+        for the normalised resamplers, densities for "metropolis"), ancestors of the last step (n,)."""
+        import torch
+        from .sharded import _device_view
+        px, pw, pa = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx._check(self.ctx.lib.cusmc_filter_state_dev(self.h, C.byref(px), C.byref(pw), C.byref(pa)))
+        self.ctx.synchronize()
+        torch.cuda.synchronize()
+        n, dev = self.n_local, self.ctx.device
+        per = self.N if self.n_local == self.N else -(-self.N // max(1, self._world))
+        x = _device_view(px.value, (self.d, per), "<f8", dev)[:, :n].cpu().numpy()
+        w = _device_view(pw.value, (per,), "<f8", dev)[:n].cpu().numpy()
+        a = _device_view(pa.value, (per,), "<i4", dev)[:n].cpu().numpy().view(np.uint32)
+        return x, w, a
 
     def history(self):
         n = self.n_local            # a sharded filter returns its own shard

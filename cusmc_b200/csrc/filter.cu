@@ -14,6 +14,7 @@
 // operator ride in the kernel parameter bank.
 #include "density.cuh"
 #include "hostmath.h"
+#include "filter_types.cuh"
 #include "mailbox.cuh"
 #include "pf_step.cuh"
 #include "resample.cuh"
@@ -360,49 +361,6 @@ extern "C" int cusmc_mvt_sample(cusmc_ctx *ctx, double *x_new_aos, const double 
 // The filter object: particle_filter() / initialize() / MCMC() of the reference
 // (src/particle_filter.cpp:6-39, src/mcmc.cpp:44-88,239-309) with device-resident state.
 // ================================================================================================
-struct StepSlot {            // one per time step, on the device (64 bytes = 8 words)
-    double lw_max;           // [0] max log-weight (log modes), -inf initialised
-    uint64_t sum_q, sum_q2, n_pos;   // [1..3] fixed-point sums (weigh_kernel); global after the exchange
-    uint64_t cdf_offset;     // [4] fixed-point mass held by lower-ranked shards (0 on one GPU)
-    double reserved[3];
-};
-
-struct cusmc_filter {
-    cusmc_ctx *ctx = nullptr;
-    cusmc_filter_config cfg{};
-    cusmc_filter_draws draws{};
-    std::vector<double> Y, m0, C0, F, G, V, W;       // host copies (column-major)
-    std::vector<double> Qc0, Qw;                      // noise factors
-    std::vector<double> M, Winv;                      // observation operator
-    Epilogue ep{};
-    int is_log = 1;
-    int shift = 0;
-    // sharding: this rank owns the global slots lo .. lo + n - 1; every rank allocates `per` columns
-    int world = 1, rank = 0;
-    int64_t per = 0, lo = 0, n = 0;
-    bool attached = false;
-    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
-    unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
-    unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
-    void **peer_tables = nullptr;             // device: [5 buffers][CUSMC_MAX_PEERS] peer pointers
-    unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
-    bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
-    double *x[2] = {nullptr, nullptr};
-    double *lw = nullptr;
-    uint32_t *anc = nullptr;
-    uint64_t *cdf = nullptr;
-    StepSlot *slots = nullptr;
-    double *moments = nullptr;        // T x (2 + d)
-    void *scan_state = nullptr;
-    double *hist_x = nullptr, *hist_w = nullptr;
-    uint32_t *hist_a = nullptr;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    double last_ms = 0.0;
-    int cur = 0;
-    int next_t = -1;                  // phase bookkeeping: the step cusmc_filter_propagate expects
-    bool ran = false;
-};
-
 // Scalar exchanges of a sharded run ride inside the kernels (mailbox.cuh) when `fused` is set.
 static MailArgs filter_mail(const cusmc_filter *f)
 {
@@ -488,6 +446,7 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     cudaFree(f->slots);
     cudaFree(f->moments);
     cudaFree(f->scan_state);
+    cudaFree(f->persist);
     cudaFree(f->mail);
     cudaFree(f->mail_err);
     cudaFree(f->peer_tables);
@@ -930,6 +889,10 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
 {
     if (!f) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(f->ctx, f->world == 1, "a sharded filter is driven phase by phase (cusmc_b200/sharded.py)");
+    if (cusmc_filter_persistent_eligible(f, draws)) {
+        const int rc = cusmc_filter_run_persistent(f, draws);
+        if (rc != CUSMC_ERR_UNSUPPORTED) return rc;      // unsupported after all (occupancy): fall through
+    }
     CUSMC_CHECK(cusmc_filter_begin(f, draws));
     CUSMC_CHECK(cusmc_filter_weigh(f, 0));
     CUSMC_CHECK(cusmc_filter_mark(f, 0));

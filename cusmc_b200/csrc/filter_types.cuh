@@ -1,0 +1,58 @@
+// filter_types.cuh -- the filter object and its per-step device record, shared by the host loop
+// (filter.cu) and the persistent whole-run kernel (pf_persist.cu).
+#pragma once
+
+#include "density.cuh"
+
+#include <vector>
+
+struct StepSlot {            // one per time step, on the device (64 bytes = 8 words)
+    double lw_max;           // [0] max log-weight (log modes), -inf initialised
+    uint64_t sum_q, sum_q2, n_pos;   // [1..3] fixed-point sums (weigh_kernel); global after the exchange
+    uint64_t cdf_offset;     // [4] fixed-point mass held by lower-ranked shards (0 on one GPU)
+    double reserved[3];
+};
+
+struct cusmc_filter {
+    cusmc_ctx *ctx = nullptr;
+    cusmc_filter_config cfg{};
+    cusmc_filter_draws draws{};
+    std::vector<double> Y, m0, C0, F, G, V, W;       // host copies (column-major)
+    std::vector<double> Qc0, Qw;                      // noise factors
+    std::vector<double> M, Winv;                      // observation operator
+    Epilogue ep{};
+    int is_log = 1;
+    int shift = 0;
+    // sharding: this rank owns the global slots lo .. lo + n - 1; every rank allocates `per` columns
+    int world = 1, rank = 0;
+    int64_t per = 0, lo = 0, n = 0;
+    bool attached = false;
+    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
+    unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
+    unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
+    void **peer_tables = nullptr;             // device: [5 buffers][CUSMC_MAX_PEERS] peer pointers
+    unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
+    bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
+    double *x[2] = {nullptr, nullptr};
+    double *lw = nullptr;
+    uint32_t *anc = nullptr;
+    uint64_t *cdf = nullptr;
+    StepSlot *slots = nullptr;
+    double *moments = nullptr;        // T x (2 + d)
+    void *scan_state = nullptr;
+    void *persist = nullptr;          // scratch of the persistent-kernel run (pf_persist.cu)
+    size_t persist_bytes = 0;
+    double *hist_x = nullptr, *hist_w = nullptr;
+    uint32_t *hist_a = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0;
+    int cur = 0;
+    int next_t = -1;                  // phase bookkeeping: the step cusmc_filter_propagate expects
+    bool ran = false;
+};
+
+
+// pf_persist.cu: the whole run as ONE cooperative kernel when the configuration allows it
+// (returns CUSMC_ERR_UNSUPPORTED otherwise, without side effects).
+int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws);
+bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_draws *draws);

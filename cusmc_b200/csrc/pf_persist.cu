@@ -1,0 +1,508 @@
+// pf_persist.cu -- the whole filter run as ONE cooperative kernel, for particle clouds that live in L2.
+//
+// At 10^6 particles (BASELINE configs[3]: the bootstrap filter on data_raw/y_t.csv) a step touches
+// 44 MB that never leave the 126 MB L2, and the four-launch step of filter.cu is bound by the
+// latency of its dependent ~9 us kernels.  A step has three grid-wide dependencies
+//     max of the log-weights  ->  total fixed-point mass  ->  ancestors scattered to the children
+// and here they are three grid barriers inside a persistent kernel instead of kernel boundaries:
+// one block per tile of 4096 particles, sixteen consecutive particles per thread (two resident
+// blocks of 256 threads per SM at <= 128 registers), and everything a thread's particles carry from
+// one phase to the next (log-weights, tile-local CDF) stays in registers -- neither the
+// log-weights nor the weight image are ever re-read from memory.
+//
+//   scatter(t) :  C_j = prefix(tile sums of t-1) + c_j  ->  children [k(C_{j-1}), k(C_j)) get ancestor j
+//   ---- grid barrier ----
+//   propagate(t): x_t[i] = G x_{t-1}[a_i] + Q z_i,  lw_i = log p(y_t | x_t[i]),  atomic max
+//   ---- grid barrier ----
+//   weigh(t)   :  q_i = fixed(exp(lw_i - max)), c_i = tile-local inclusive prefix, tile sum
+//   ---- grid barrier ----
+//
+// The arithmetic is the four-launch path's, operation for operation (same helpers, same Philox
+// counters): a persistent run reproduces it bit for bit (tests/test_gpu_parity.py).
+// Same semantics as cusmc_filter_run (src/mcmc.cpp:239-309 of the reference) restricted to:
+// one GPU, systematic resampling, Normal noise, d == dy in {2, 4}, device-drawn noise, no history,
+// no per-step moments, N <= one tile per resident block.
+#include "filter_types.cuh"
+#include "pf_step_impl.cuh"
+#include "resample.cuh"
+
+#include "../../include/cusmc_detmath.h"
+#include "../../include/cusmc_philox.h"
+
+#include <cooperative_groups.h>
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kItems = 16;                      // consecutive particles per thread
+constexpr int kHalf = 8;                        // propagated in two halves (register budget)
+constexpr int kPTile = kThreads * kItems;       // particles per block
+
+struct PersistArgs {
+    double *x[2];                   // SoA [d][ld] double buffer
+    double *lw;                     // [N] log-weights (kept for cusmc_filter_state_dev)
+    uint32_t *anc;                  // [N]
+    StepSlot *slots;                // [T]
+    unsigned long long *tile_sums;  // [2][gridDim.x]
+    const double *obs;              // [T][D]: L_V^-1 y_t
+    const double *u0;               // [T]: systematic offsets (entry t used by step t)
+    uint64_t seed;
+    int64_t ld;
+    uint32_t N;
+    int T, shift;
+};
+
+__device__ __forceinline__ void atomic_max_double_p(double *addr, double v)
+{
+    if (v != v) return;
+    if (v >= 0.0)
+        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+    else
+        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
+// x = mu + G xp + Q z and the whitened residual norm, in pf_step_kernel's operation order.
+template <int D, bool DIAG>
+__device__ __forceinline__ void propagate_one(const pfstep::StepOp<D, DIAG> &op, const double (&c)[D], const double (&xp)[D],
+                                              const double (&z)[D], double (&xn)[D], double &q)
+{
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double g = op.mu[k], s = 0.0;
+        if constexpr (DIAG) {
+            g = fma(op.G[k], xp[k], g);
+            s = fma(op.Q[k], z[k], s);
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
+#pragma unroll
+            for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
+        }
+        xn[k] = s + g;
+    }
+    q = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double zk = c[k];
+        if constexpr (DIAG) {
+            zk = fma(-op.M[k], xn[k], zk);
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
+        }
+        q = fma(zk, zk, q);
+    }
+}
+
+template <int D>
+__device__ __forceinline__ void draw_normals(uint64_t seed, int stream, uint64_t step, uint64_t idx, double (&z)[D])
+{
+#pragma unroll
+    for (int jq = 0; jq < (D + 3) / 4; ++jq) {
+        double zq[4];
+        cusmc_normal4(cusmc_rng(seed, stream, step, idx, (uint32_t)jq), zq);
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+            if (4 * jq + e < D) z[4 * jq + e] = zq[e];
+    }
+}
+
+// Block-wide sums of two uint64 per thread (every thread gets both totals).
+__device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long long &b, unsigned long long *sm)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        a += __shfl_xor_sync(0xffffffffu, a, o);
+        b += __shfl_xor_sync(0xffffffffu, b, o);
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+        sm[threadIdx.x >> 5] = a;
+        sm[8 + (threadIdx.x >> 5)] = b;
+    }
+    __syncthreads();
+    a = b = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        a += sm[k];
+        b += sm[8 + k];
+    }
+}
+
+template <int D, bool DIAG>
+__global__ void __launch_bounds__(kThreads, 2)
+pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
+                     const __grid_constant__ pfstep::StepOp<D, DIAG> op, const Epilogue ep, const PersistArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    __shared__ unsigned long long s_u64[16];
+    __shared__ double s_dbl[kThreads / 32];
+    __shared__ uint32_t s_k[kThreads];
+    __shared__ unsigned long long s_T, s_r0;
+    __shared__ double s_ng_over_t, s_r0_over_t;
+
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t base = blockIdx.x * kPTile + tid * kItems;      // my 16 consecutive particles
+    const bool full = base + kItems <= a.N;                        // vector path (ld, N even: checked by the host)
+    double lw[kItems];
+    unsigned long long c[kItems];                                  // tile-local inclusive CDF of my particles
+    int cur = 0;
+
+    // block max of the eight log-weights -> atomic max into the step's slot
+    auto publish_max = [&](int t) {
+        double m = -INFINITY;
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            const double v = lw[r];
+            if (v == v && v < INFINITY && v > m) m = v;
+        }
+        m = warp_max_double(m);
+        if (lane == 0) s_dbl[warp] = m;
+        __syncthreads();
+        if (tid < 32) {
+            m = warp_max_double(tid < kThreads / 32 ? s_dbl[tid] : -INFINITY);
+            if (tid == 0) atomic_max_double_p(&a.slots[t].lw_max, m);
+        }
+    };
+
+    // weigh(t): fixed-point weights against the global max, tile-local CDF in registers, tile sum
+    auto weigh = [&](int t) {
+        const double wmax = __ldcg(&a.slots[t].lw_max);
+        unsigned long long run = 0;
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) {
+            run += cusmc_fixed_from_unit(cusmc_unit_from_log(lw[r], wmax), a.shift);
+            c[r] = run;
+        }
+        unsigned long long inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
+        }
+        __syncthreads();
+        if (lane == 31) s_u64[warp] = inc;
+        __syncthreads();
+        unsigned long long before = inc - run, tile_total = 0;
+#pragma unroll
+        for (int k = 0; k < kThreads / 32; ++k) {
+            const unsigned long long v = s_u64[k];
+            if (k < (int)warp) before += v;
+            tile_total += v;
+        }
+#pragma unroll
+        for (int r = 0; r < kItems; ++r) c[r] += before;
+        if (tid == 0) a.tile_sums[(size_t)(t & 1) * gridDim.x + blockIdx.x] = tile_total;
+    };
+
+    // eight consecutive particles of one half, component by component (128-bit stores)
+    auto store_half = [&](double *xbuf, const double (&xs)[D][kHalf], int h) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            double *dst = xbuf + (int64_t)j * a.ld + base + h;
+            if (full) {
+#pragma unroll
+                for (int r = 0; r < kHalf; r += 2) st_stream2(dst + r, make_double2(xs[j][r], xs[j][r + 1]));
+            } else {
+#pragma unroll
+                for (int r = 0; r < kHalf; ++r)
+                    if (base + h + r < a.N) dst[r] = xs[j][r];
+            }
+        }
+    };
+    auto store_lw = [&]() {
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < kItems; r += 2) st_stream2(a.lw + base + r, make_double2(lw[r], lw[r + 1]));
+        } else {
+#pragma unroll
+            for (int r = 0; r < kItems; ++r)
+                if (base + r < a.N) a.lw[base + r] = lw[r];
+        }
+    };
+
+    // ---- t = 0: x_0 = m0 + Q_c0 z, constant log-weight 0 (src/mcmc.cpp:63-85) -----------------
+    {
+        const double zero_c[D] = {};
+#pragma unroll
+        for (int h = 0; h < kItems; h += kHalf) {
+            double xs[D][kHalf];
+#pragma unroll
+            for (int r = 0; r < kHalf; ++r) {
+                const uint32_t i = base + h + r;
+                double xp[D], z[D], xn[D], q;
+#pragma unroll
+                for (int j = 0; j < D; ++j) xp[j] = 0.0;
+                draw_normals<D>(a.seed, CUSMC_STREAM_INIT, 0, (uint64_t)i, z);
+                propagate_one<D, DIAG>(op_init, zero_c, xp, z, xn, q);
+#pragma unroll
+                for (int j = 0; j < D; ++j) xs[j][r] = xn[j];
+                lw[h + r] = i < a.N ? 0.0 : -INFINITY;
+            }
+            store_half(a.x[0], xs, h);
+        }
+        store_lw();
+        publish_max(0);
+    }
+    grid.sync();
+    weigh(0);
+    grid.sync();
+
+    for (int t = 1; t < a.T; ++t) {
+        // ---- scatter(t): ancestors of step t from the weight image of step t - 1 ----------------
+        {
+            const unsigned long long *ts = a.tile_sums + (size_t)((t - 1) & 1) * gridDim.x;
+            unsigned long long pre = 0, tot = 0;
+            for (uint32_t b = tid; b < gridDim.x; b += kThreads) {
+                const unsigned long long v = __ldcg(ts + b);
+                tot += v;
+                if (b < blockIdx.x) pre += v;
+            }
+            block_sum2(pre, tot, s_u64);
+            if (tid == 0) {
+                if (blockIdx.x == 0) a.slots[t - 1].sum_q = tot;
+                uint64_t rr = (uint64_t)(__ldg(a.u0 + t) * (double)tot);
+                if (tot && rr > tot - 1) rr = tot - 1;
+                s_T = tot;
+                s_r0 = rr;
+                s_ng_over_t = (double)a.N / (double)tot;
+                s_r0_over_t = (double)rr / (double)tot;
+            }
+            __syncthreads();
+            const uint64_t T = s_T;
+            if (T != 0) {                                   // T == 0: degenerate weights, ancestors stay
+                const uint64_t r0 = s_r0, Ng = a.N;
+                const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
+                uint32_t k[kItems];
+                unsigned long long c_prev = ~0ull;
+                uint32_t k_last = 0;
+#pragma unroll
+                for (int r = 0; r < kItems; ++r) {
+                    // the count is a pure function of the CDF value: zero weights repeat it for free
+                    k[r] = c[r] != c_prev ? (uint32_t)offspring_below(pre + c[r], Ng, T, r0, ng_over_t, r0_over_t) : k_last;
+                    c_prev = c[r];
+                    k_last = k[r];
+                }
+                s_k[tid] = k[kItems - 1];
+                __syncthreads();
+                uint32_t k_prev = tid ? s_k[tid - 1] : (uint32_t)offspring_below(pre, Ng, T, r0, ng_over_t, r0_over_t);
+#pragma unroll
+                for (int r = 0; r < kItems; ++r) {
+                    uint32_t lo = k_prev;
+                    const uint32_t hi = k[r];
+                    const uint32_t parent = base + r;
+                    const bool big = hi > lo && hi - lo > 8;
+                    if (!big) {
+#pragma unroll 1
+                        for (; lo < hi; ++lo) a.anc[lo] = parent;
+                    }
+                    unsigned bigmask = __ballot_sync(0xffffffffu, big);
+                    while (bigmask) {
+                        const int src = __ffs(bigmask) - 1;
+                        bigmask &= bigmask - 1;
+                        const uint32_t sa = __shfl_sync(0xffffffffu, lo, src);
+                        const uint32_t sb = __shfl_sync(0xffffffffu, hi, src);
+                        const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+#pragma unroll 1
+                        for (uint32_t ch = sa + lane; ch < sb; ch += 32) a.anc[ch] = sp;
+                    }
+                    k_prev = hi;
+                }
+            }
+        }
+        grid.sync();
+
+        // ---- propagate(t) + reweight(t) (src/mcmc.cpp:298-307), max of the log-weights ----------
+        {
+            double cobs[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) cobs[j] = __ldg(a.obs + (size_t)t * D + j);
+            const double *xprev = a.x[cur];
+            double *xnew = a.x[cur ^ 1];
+#pragma unroll
+            for (int h = 0; h < kItems; h += kHalf) {
+                uint32_t par[kHalf];
+                if (full) {
+                    const uint4 p0 = __ldcg(reinterpret_cast<const uint4 *>(a.anc + base + h));
+                    const uint4 p1 = __ldcg(reinterpret_cast<const uint4 *>(a.anc + base + h) + 1);
+                    par[0] = p0.x; par[1] = p0.y; par[2] = p0.z; par[3] = p0.w;
+                    par[4] = p1.x; par[5] = p1.y; par[6] = p1.z; par[7] = p1.w;
+                } else {
+#pragma unroll
+                    for (int r = 0; r < kHalf; ++r) par[r] = base + h + r < a.N ? __ldcg(a.anc + base + h + r) : 0u;
+                }
+                double xs[D][kHalf];
+#pragma unroll
+                for (int r = 0; r < kHalf; ++r) {
+                    const uint32_t i = base + h + r;
+                    double xp[D], z[D], xn[D], q;
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xp[j] = __ldcg(xprev + (int64_t)j * a.ld + par[r]);
+                    draw_normals<D>(a.seed, CUSMC_STREAM_NORMAL, (uint64_t)t, (uint64_t)i, z);
+                    propagate_one<D, DIAG>(op, cobs, xp, z, xn, q);
+#pragma unroll
+                    for (int j = 0; j < D; ++j) xs[j][r] = xn[j];
+                    lw[h + r] = i < a.N ? density_epilogue(ep, q) : -INFINITY;
+                }
+                store_half(xnew, xs, h);
+            }
+            store_lw();
+            publish_max(t);
+            cur ^= 1;
+        }
+        grid.sync();
+
+        // ---- weigh(t) ---------------------------------------------------------------------------
+        weigh(t);
+        grid.sync();
+    }
+    // total mass of the last step (log-likelihood of the summary)
+    if (blockIdx.x == 0) {
+        const unsigned long long *ts = a.tile_sums + (size_t)((a.T - 1) & 1) * gridDim.x;
+        unsigned long long pre = 0, tot = 0;
+        for (uint32_t b = tid; b < gridDim.x; b += kThreads) tot += __ldcg(ts + b);
+        block_sum2(pre, tot, s_u64);
+        if (tid == 0) a.slots[a.T - 1].sum_q = tot;
+    }
+}
+
+__global__ void persist_init_slots(StepSlot *slots, int T)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < T) {
+        StepSlot s{};
+        s.lw_max = -INFINITY;
+        slots[t] = s;
+    }
+}
+
+template <int D, bool DIAG>
+int launch_persistent(cusmc_filter *f, const PersistArgs &args, unsigned grid, bool probe_only)
+{
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    auto kernel = pf_persistent_kernel<D, DIAG>;
+    int per_sm = 0;
+    CUSMC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    if ((int64_t)per_sm * ctx->sm_count < (int64_t)grid)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "persistent run: %u tiles exceed the %d resident blocks", grid,
+                          per_sm * ctx->sm_count);
+    if (probe_only) return CUSMC_OK;
+    pfstep::StepOp<D, DIAG> op0, op;
+    const pfstep::StepModel m0{cfg.d, cfg.dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr, f->m0.data()};
+    const pfstep::StepModel m1{cfg.d, cfg.dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, nullptr, nullptr};
+    pfstep::fill_step_op<D, DIAG>(op0, m0);
+    pfstep::fill_step_op<D, DIAG>(op, m1);
+    Epilogue ep = f->ep;
+    PersistArgs a = args;
+    void *params[] = {&op0, &op, &ep, &a};
+    CUSMC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kThreads), params, 0, ctx->stream));
+    ctx->launches++;
+    return CUSMC_OK;
+}
+
+bool is_diag_cm(const double *A, int d)
+{
+    for (int c = 0; c < d; ++c)
+        for (int r = 0; r < d; ++r)
+            if (r != c && A[(size_t)c * d + r] != 0.0) return false;
+    return true;
+}
+
+uint64_t u0_bits(uint64_t seed, uint64_t step)
+{
+    const cusmc_u32x4 r = cusmc_rng(seed, 7 /* systematic offset */, step, 0, 0);
+    return ((uint64_t)r.v[0] << 32) | r.v[1];
+}
+
+}  // namespace
+
+bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_draws *draws)
+{
+    const cusmc_filter_config &cfg = f->cfg;
+    if (cfg.persistent <= 0 || f->world != 1) return false;
+    if (cfg.resampler != CUSMC_RESAMPLE_SYSTEMATIC || cfg.kind != CUSMC_MVN) return false;
+    if (cfg.keep_history || cfg.summary) return false;
+    if (cfg.d != cfg.dy || (cfg.d != 2 && cfg.d != 4)) return false;
+    if (cfg.N % 2 != 0 || cfg.T < 2) return false;
+    if (draws && (draws->xi0_dev || draws->xi_dev || draws->chi_dev || draws->u_dev || draws->j_dev || draws->um_dev))
+        return false;
+    const int64_t tiles = (cfg.N + kPTile - 1) / kPTile;
+    return tiles <= (int64_t)f->ctx->sm_count * 2;    // refined by the occupancy query at launch
+}
+
+int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws)
+{
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    if (!cusmc_filter_persistent_eligible(f, draws))
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "configuration not covered by the persistent kernel");
+    const int d = cfg.d, T = cfg.T;
+    const unsigned grid = (unsigned)((cfg.N + kPTile - 1) / kPTile);
+    bool diag = is_diag_cm(f->G.data(), d) && is_diag_cm(f->Qw.data(), d) && is_diag_cm(f->Qc0.data(), d);
+    for (int k = 0; k < d && diag; ++k)
+        for (int j = 0; j < d; ++j)
+            if (j != k && f->M[(size_t)k * d + j] != 0.0) diag = false;
+    PersistArgs a{};
+    // resident-block check before anything is enqueued (so the caller can still fall back)
+    int rc;
+    if (d == 2) rc = diag ? launch_persistent<2, true>(f, a, grid, true) : launch_persistent<2, false>(f, a, grid, true);
+    else rc = diag ? launch_persistent<4, true>(f, a, grid, true) : launch_persistent<4, false>(f, a, grid, true);
+    if (rc != CUSMC_OK) return rc;
+
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    // per-run scratch: tile sums [2][grid], whitened observations [T][d], systematic offsets [T]
+    const size_t n_sum = 2 * (size_t)grid, n_obs = (size_t)T * d, n_u0 = (size_t)T;
+    const size_t bytes = 8 * (n_sum + n_obs + n_u0);
+    if (bytes > f->persist_bytes) {
+        CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
+        cudaFree(f->persist);
+        f->persist = nullptr;
+        f->persist_bytes = 0;
+        CUSMC_CUDA(ctx, cudaMalloc(&f->persist, bytes));
+        f->persist_bytes = bytes;
+    }
+    std::vector<double> host(n_obs + n_u0, 0.0);
+    for (int t = 0; t < T; ++t) {
+        for (int k = 0; k < d; ++k) {     // L_V^-1 y_t, as whiten_observation in filter.cu
+            double s = 0.0;
+            for (int i = 0; i <= k; ++i) s += f->Winv[(size_t)k * d + i] * f->Y[(size_t)t * d + i];
+            host[(size_t)t * d + k] = s;
+        }
+        if (t >= 1)
+            host[n_obs + t] = (draws && draws->u0_host) ? draws->u0_host[t - 1]
+                                                        : (double)(u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+    }
+    unsigned long long *sums = (unsigned long long *)f->persist;
+    double *obs = (double *)(sums + n_sum), *u0 = obs + n_obs;
+    // the host vector dies with this call: a synchronous copy (pageable memory) is what we want
+    CUSMC_CUDA(ctx, cudaMemcpyAsync(obs, host.data(), 8 * host.size(), cudaMemcpyHostToDevice, st));
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
+    persist_init_slots<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
+    CUSMC_LAUNCHED(ctx);
+    a.x[0] = f->x[0];
+    a.x[1] = f->x[1];
+    a.lw = f->lw;
+    a.anc = f->anc;
+    a.slots = f->slots;
+    a.tile_sums = sums;
+    a.obs = obs;
+    a.u0 = u0;
+    a.seed = cfg.seed;
+    a.ld = f->per;
+    a.N = (uint32_t)cfg.N;
+    a.T = T;
+    a.shift = f->shift;
+    CUSMC_CUDA(ctx, cudaEventRecord(f->ev0, st));
+    if (d == 2) rc = diag ? launch_persistent<2, true>(f, a, grid, false) : launch_persistent<2, false>(f, a, grid, false);
+    else rc = diag ? launch_persistent<4, true>(f, a, grid, false) : launch_persistent<4, false>(f, a, grid, false);
+    if (rc != CUSMC_OK) return rc;
+    CUSMC_CUDA(ctx, cudaEventRecord(f->ev1, st));
+    f->cur = (T - 1) & 1;
+    f->next_t = T;
+    f->ran = true;
+    return CUSMC_OK;
+}

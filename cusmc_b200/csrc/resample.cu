@@ -129,12 +129,6 @@ weights_max_kernel(const double *__restrict__ w, int64_t N, double *__restrict__
 // block to arrive scan the tile sums: 2 same-address atomics per tile cost 18 us at N = 8 Mi.)
 // Integer sums: every order gives the same bits.
 // ------------------------------------------------------------------------------------------
-#ifndef CUSMC_TILE_ITEMS
-#define CUSMC_TILE_ITEMS 8
-#endif
-constexpr int kTileItems = CUSMC_TILE_ITEMS;
-constexpr int kTile = kThreads * kTileItems;    // 2048 weights per tile
-
 __host__ __device__ inline int64_t image_tiles(int64_t N) { return (N + kTile - 1) / kTile; }
 __host__ __device__ inline int64_t image_header_words(int64_t N)
 {
@@ -329,36 +323,6 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
         }
         if (mail.world > 1) stats[3] = below;      // StepSlot::cdf_offset
     }
-}
-
-// #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
-// Floating-point estimate, then (rarely) an exact 128-bit correction.
-__device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
-                                                    double ng_over_t, double r0_over_t)
-{
-    // p = (C*Ng - r0) / T; the answer is ceil(p) for p > 0.  est is within 2^-19 of p (C, Ng/T and
-    // r0/T each carry one rounding and p <= 2^32), so whenever est sits safely inside an open unit
-    // interval the answer is floor(est) + 1 and no 128-bit arithmetic is needed.  Only boundaries
-    // within 1e-4 of an integer (2e-4 of all cases) take the exact path below.
-    const double est = fma((double)C, ng_over_t, -r0_over_t);
-    const double fl = floor(est);
-    const double frac = est - fl;
-    if (est > 1e-4 && frac > 1e-4 && frac < 1.0 - 1e-4) {
-        const uint64_t kf = (uint64_t)fl + 1;
-        return kf > Ng ? Ng : kf;
-    }
-    const uint64_t rhs_lo = C * Ng, rhs_hi = __umul64hi(C, Ng);
-    uint64_t k = est <= 0.0 ? 0 : (est >= (double)Ng ? Ng : (uint64_t)est);
-    // lhs(k) = k*T + r0 as 128 bit
-    auto lhs_less = [&](uint64_t kk) {
-        uint64_t lo = kk * T, hi = __umul64hi(kk, T);
-        const uint64_t lo2 = lo + r0;
-        hi += lo2 < lo;
-        return hi < rhs_hi || (hi == rhs_hi && lo2 < rhs_lo);
-    };
-    while (k < Ng && lhs_less(k)) ++k;
-    while (k > 0 && !lhs_less(k - 1)) --k;
-    return k;
 }
 
 struct ScanArgs {

@@ -22,3 +22,45 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
                              int64_t n_out, int64_t j0, uint32_t *a);
+
+// ---- shared with the persistent filter kernel (pf_persist.cu) -------------------------------------
+constexpr int kResampleThreads = 256;
+#ifndef CUSMC_TILE_ITEMS
+#define CUSMC_TILE_ITEMS 8
+#endif
+constexpr int kTileItems = CUSMC_TILE_ITEMS;
+constexpr int kTile = kResampleThreads * kTileItems;    // 2048 weights per tile
+
+
+#ifdef __CUDACC__
+// #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
+// Floating-point estimate, then (rarely) an exact 128-bit correction.
+__device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
+                                                    double ng_over_t, double r0_over_t)
+{
+    // p = (C*Ng - r0) / T; the answer is ceil(p) for p > 0.  est is within 2^-19 of p (C, Ng/T and
+    // r0/T each carry one rounding and p <= 2^32), so whenever est sits safely inside an open unit
+    // interval the answer is floor(est) + 1 and no 128-bit arithmetic is needed.  Only boundaries
+    // within 1e-4 of an integer (2e-4 of all cases) take the exact path below.
+    const double est = fma((double)C, ng_over_t, -r0_over_t);
+    const double fl = floor(est);
+    const double frac = est - fl;
+    if (est > 1e-4 && frac > 1e-4 && frac < 1.0 - 1e-4) {
+        const uint64_t kf = (uint64_t)fl + 1;
+        return kf > Ng ? Ng : kf;
+    }
+    const uint64_t rhs_lo = C * Ng, rhs_hi = __umul64hi(C, Ng);
+    uint64_t k = est <= 0.0 ? 0 : (est >= (double)Ng ? Ng : (uint64_t)est);
+    // lhs(k) = k*T + r0 as 128 bit
+    auto lhs_less = [&](uint64_t kk) {
+        uint64_t lo = kk * T, hi = __umul64hi(kk, T);
+        const uint64_t lo2 = lo + r0;
+        hi += lo2 < lo;
+        return hi < rhs_hi || (hi == rhs_hi && lo2 < rhs_lo);
+    };
+    while (k < Ng && lhs_less(k)) ++k;
+    while (k > 0 && !lhs_less(k - 1)) --k;
+    return k;
+}
+
+#endif

@@ -282,6 +282,15 @@ typedef struct cusmc_filter_config {
     /* Sharded runs (one process per GPU): N is the GLOBAL particle count; rank r of `world` owns the
      * global slots r*per .. min((r+1)*per, N) - 1, per = ceil(N / world).  world <= 1: one GPU. */
     int rank, world;
+    /* 1: cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (three grid
+     * barriers per step instead of four launches; log-weights and the weight image stay in registers)
+     * when the configuration allows it: one GPU, systematic resampling, Normal noise, d == dy in
+     * {2, 4}, device-drawn noise, no history, no summary, N even and small enough for one 4096-particle
+     * tile per resident block (1.2 M particles on a B200); otherwise, and with 0 (default), the
+     * four-launch step.  Results are bit-identical.  Opt-in because it is not yet faster: at 3.3
+     * resident warps per scheduler the r01 kernel is latency-bound (43 vs 35 us per 10^6-particle
+     * step, profiles/r01i_persist_summary.md). */
+    int persistent;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):

@@ -433,6 +433,38 @@ def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
     assert np.array_equal(h["x"], ref["x"])
 
 
+@pytest.mark.parametrize("d,diag,N", [(2, True, 20000), (2, False, 8192), (4, True, 12346), (4, False, 4100),
+                                      (2, True, 300000)])
+def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
+    """cusmc_filter_run as ONE cooperative kernel (pf_persist.cu) against the four-launch path:
+    final particles, log-weights and ancestors bit for bit, and the per-step log-likelihood."""
+    rng = np.random.default_rng(31 * d + N)
+    T = 14
+    I = np.eye(d)
+    if diag:
+        md = dict(m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=0.5 * I, W=0.3 * I)
+    else:
+        A = rng.standard_normal((d, d)) * 0.2
+        md = dict(m0=rng.standard_normal(d), C0=spd(rng, d), F=I + A, G=0.8 * I + A.T, V=spd(rng, d), W=spd(rng, d))
+    Y = rng.standard_normal((d, T))
+    out = []
+    for persistent in (True, False):
+        pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=99, summary=False, persistent=persistent, **md)
+        l0 = ctx.launch_count
+        pf.run()
+        x, w, a = pf.state()
+        launches = ctx.launch_count - l0
+        out.append((x, w, a, pf.summary()["loglik"], launches))
+        pf.close()
+    (xp, wp, ap, lp, np_), (xf, wf, af, lf, nf) = out
+    assert np_ == 2 and nf == 4 * (T - 1) + 4          # the persistent run really took the one-kernel path
+    assert np.array_equal(ap, af)
+    assert np.array_equal(xp, xf)
+    assert np.array_equal(wp, wf)
+    assert np.array_equal(lp, lf)
+    assert len(np.unique(ap)) > 10 and np.all(np.diff(ap.astype(np.int64)) >= 0)
+
+
 def kalman_means(Y, m0, C0, F, G, V, W):
     m, P = m0.copy(), C0.copy()
     out = [m.copy()]
