@@ -5,10 +5,11 @@
 // latency of its dependent ~9 us kernels.  A step has three grid-wide dependencies
 //     max of the log-weights  ->  total fixed-point mass  ->  ancestors scattered to the children
 // and here they are three grid barriers inside a persistent kernel instead of kernel boundaries:
-// one block per tile of 4096 particles, sixteen consecutive particles per thread (two resident
-// blocks of 256 threads per SM at <= 128 registers), and everything a thread's particles carry from
-// one phase to the next (log-weights, tile-local CDF) stays in registers -- neither the
-// log-weights nor the weight image are ever re-read from memory.
+// one block of 512 threads per tile of 4096 particles, three blocks per SM, and everything a tile
+// carries from one phase to the next (log-weights, tile-local CDF) stays in shared memory --
+// neither the log-weights nor the weight image are ever re-read from global memory.  (A first
+// version kept them in registers, 16 particles per thread: 3.3 resident warps per scheduler,
+// latency-bound, slower than the four launches.)
 //
 //   scatter(t) :  C_j = prefix(tile sums of t-1) + c_j  ->  children [k(C_{j-1}), k(C_j)) get ancestor j
 //   ---- grid barrier ----
@@ -35,10 +36,14 @@ namespace cg = cooperative_groups;
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kItems = 16;                      // consecutive particles per thread
-constexpr int kHalf = 8;                        // propagated in two halves (register budget)
-constexpr int kPTile = kThreads * kItems;       // particles per block
+constexpr int kThreads = 512;
+constexpr int kItems = 8;                       // particles per thread
+constexpr int kPTile = kThreads * kItems;       // 4096 particles per block
+constexpr int kBlocksPerSM = 3;                 // 3 x 64 KB of shared memory, 1536 threads, <= 42 registers
+// shared-memory index of tile offset j: one pad word per 8, so both the striped (j = r*512 + tid)
+// and the blocked (j = 8*tid + r) access patterns stay (almost) conflict-free
+__device__ __forceinline__ int pad(int j) { return j + (j >> 3); }
+constexpr int kPadded = kPTile + kPTile / 8;
 
 struct PersistArgs {
     double *x[2];                   // SoA [d][ld] double buffer
@@ -112,6 +117,7 @@ __device__ __forceinline__ void draw_normals(uint64_t seed, int stream, uint64_t
 // Block-wide sums of two uint64 per thread (every thread gets both totals).
 __device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long long &b, unsigned long long *sm)
 {
+    constexpr int kWarps = kThreads / 32;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         a += __shfl_xor_sync(0xffffffffu, a, o);
@@ -120,44 +126,74 @@ __device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long 
     __syncthreads();
     if ((threadIdx.x & 31) == 0) {
         sm[threadIdx.x >> 5] = a;
-        sm[8 + (threadIdx.x >> 5)] = b;
+        sm[kWarps + (threadIdx.x >> 5)] = b;
     }
     __syncthreads();
     a = b = 0;
 #pragma unroll
-    for (int k = 0; k < kThreads / 32; ++k) {
+    for (int k = 0; k < kWarps; ++k) {
         a += sm[k];
-        b += sm[8 + k];
+        b += sm[kWarps + k];
     }
 }
 
+// Phase mappings of a block's 4096-particle tile:
+//   propagate : STRIPED, particle tile + r*512 + tid (round r) -- every global access of a warp is one
+//               contiguous line, one particle in flight per thread at a time (small register footprint,
+//               12 resident warps per scheduler hide the gather latency);
+//   weigh / scatter : BLOCKED, particles tile + 8*tid .. +7 -- the tile-local CDF is a thread-local
+//               running sum plus one block scan.
+// The log-weights and the CDF cross between the two mappings, and between phases, through shared
+// memory (2 x 36 KB per block): neither is ever re-read from global memory.
 template <int D, bool DIAG>
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                      const __grid_constant__ pfstep::StepOp<D, DIAG> op, const Epilogue ep, const PersistArgs a)
 {
     cg::grid_group grid = cg::this_grid();
-    __shared__ unsigned long long s_u64[16];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *s_lw = reinterpret_cast<double *>(smem_raw);                               // [kPadded]
+    unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw) + kPadded;   // [kPadded]
+    __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
     __shared__ double s_dbl[kThreads / 32];
     __shared__ uint32_t s_k[kThreads];
     __shared__ unsigned long long s_T, s_r0;
     __shared__ double s_ng_over_t, s_r0_over_t;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t base = blockIdx.x * kPTile + tid * kItems;      // my 16 consecutive particles
-    const bool full = base + kItems <= a.N;                        // vector path (ld, N even: checked by the host)
-    double lw[kItems];
-    unsigned long long c[kItems];                                  // tile-local inclusive CDF of my particles
+    const uint32_t tile0 = blockIdx.x * kPTile;
     int cur = 0;
 
-    // block max of the eight log-weights -> atomic max into the step's slot
-    auto publish_max = [&](int t) {
-        double m = -INFINITY;
+    // one particle: gather (t > 0), noise, propagate, reweight; striped round r
+    auto particle = [&](const pfstep::StepOp<D, DIAG> &o, const double (&cobs)[D], int t, int r, double &m) {
+        const int j = r * kThreads + (int)tid;
+        const uint32_t i = tile0 + (uint32_t)j;
+        double lw = -INFINITY;
+        if (i < a.N) {
+            double xp[D], z[D], xn[D], q;
+            if (t > 0) {
+                const uint32_t par = __ldcg(a.anc + i);
+                const double *src = a.x[cur] + par;
 #pragma unroll
-        for (int r = 0; r < kItems; ++r) {
-            const double v = lw[r];
-            if (v == v && v < INFINITY && v > m) m = v;
+                for (int k = 0; k < D; ++k) xp[k] = __ldcg(src + (int64_t)k * a.ld);
+            } else {
+#pragma unroll
+                for (int k = 0; k < D; ++k) xp[k] = 0.0;
+            }
+            draw_normals<D>(a.seed, t > 0 ? CUSMC_STREAM_NORMAL : CUSMC_STREAM_INIT, (uint64_t)t, (uint64_t)i, z);
+            propagate_one<D, DIAG>(o, cobs, xp, z, xn, q);
+            double *dst = a.x[t > 0 ? cur ^ 1 : 0] + i;
+#pragma unroll
+            for (int k = 0; k < D; ++k) st_stream(dst + (int64_t)k * a.ld, xn[k]);
+            lw = t > 0 ? density_epilogue(ep, q) : 0.0;
+            st_stream(a.lw + i, lw);
+            if (lw == lw && lw < INFINITY && lw > m) m = lw;
         }
+        s_lw[pad(j)] = lw;
+    };
+
+    // block max -> atomic max into the step's slot
+    auto publish_max = [&](int t, double m) {
         m = warp_max_double(m);
         if (lane == 0) s_dbl[warp] = m;
         __syncthreads();
@@ -167,13 +203,13 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         }
     };
 
-    // weigh(t): fixed-point weights against the global max, tile-local CDF in registers, tile sum
+    // weigh(t): fixed-point weights against the global max, tile-local CDF into shared memory, tile sum
     auto weigh = [&](int t) {
         const double wmax = __ldcg(&a.slots[t].lw_max);
-        unsigned long long run = 0;
+        unsigned long long c[kItems], run = 0;
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
-            run += cusmc_fixed_from_unit(cusmc_unit_from_log(lw[r], wmax), a.shift);
+            run += cusmc_fixed_from_unit(cusmc_unit_from_log(s_lw[pad(kItems * (int)tid + r)], wmax), a.shift);
             c[r] = run;
         }
         unsigned long long inc = run;
@@ -193,58 +229,17 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             tile_total += v;
         }
 #pragma unroll
-        for (int r = 0; r < kItems; ++r) c[r] += before;
+        for (int r = 0; r < kItems; ++r) s_c[pad(kItems * (int)tid + r)] = before + c[r];
         if (tid == 0) a.tile_sums[(size_t)(t & 1) * gridDim.x + blockIdx.x] = tile_total;
-    };
-
-    // eight consecutive particles of one half, component by component (128-bit stores)
-    auto store_half = [&](double *xbuf, const double (&xs)[D][kHalf], int h) {
-#pragma unroll
-        for (int j = 0; j < D; ++j) {
-            double *dst = xbuf + (int64_t)j * a.ld + base + h;
-            if (full) {
-#pragma unroll
-                for (int r = 0; r < kHalf; r += 2) st_stream2(dst + r, make_double2(xs[j][r], xs[j][r + 1]));
-            } else {
-#pragma unroll
-                for (int r = 0; r < kHalf; ++r)
-                    if (base + h + r < a.N) dst[r] = xs[j][r];
-            }
-        }
-    };
-    auto store_lw = [&]() {
-        if (full) {
-#pragma unroll
-            for (int r = 0; r < kItems; r += 2) st_stream2(a.lw + base + r, make_double2(lw[r], lw[r + 1]));
-        } else {
-#pragma unroll
-            for (int r = 0; r < kItems; ++r)
-                if (base + r < a.N) a.lw[base + r] = lw[r];
-        }
     };
 
     // ---- t = 0: x_0 = m0 + Q_c0 z, constant log-weight 0 (src/mcmc.cpp:63-85) -----------------
     {
         const double zero_c[D] = {};
-#pragma unroll
-        for (int h = 0; h < kItems; h += kHalf) {
-            double xs[D][kHalf];
-#pragma unroll
-            for (int r = 0; r < kHalf; ++r) {
-                const uint32_t i = base + h + r;
-                double xp[D], z[D], xn[D], q;
-#pragma unroll
-                for (int j = 0; j < D; ++j) xp[j] = 0.0;
-                draw_normals<D>(a.seed, CUSMC_STREAM_INIT, 0, (uint64_t)i, z);
-                propagate_one<D, DIAG>(op_init, zero_c, xp, z, xn, q);
-#pragma unroll
-                for (int j = 0; j < D; ++j) xs[j][r] = xn[j];
-                lw[h + r] = i < a.N ? 0.0 : -INFINITY;
-            }
-            store_half(a.x[0], xs, h);
-        }
-        store_lw();
-        publish_max(0);
+        double m = -INFINITY;
+#pragma unroll 1
+        for (int r = 0; r < kItems; ++r) particle(op_init, zero_c, 0, r, m);
+        publish_max(0, m);
     }
     grid.sync();
     weigh(0);
@@ -281,8 +276,9 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
 #pragma unroll
                 for (int r = 0; r < kItems; ++r) {
                     // the count is a pure function of the CDF value: zero weights repeat it for free
-                    k[r] = c[r] != c_prev ? (uint32_t)offspring_below(pre + c[r], Ng, T, r0, ng_over_t, r0_over_t) : k_last;
-                    c_prev = c[r];
+                    const unsigned long long cr = s_c[pad(kItems * (int)tid + r)];
+                    k[r] = cr != c_prev ? (uint32_t)offspring_below(pre + cr, Ng, T, r0, ng_over_t, r0_over_t) : k_last;
+                    c_prev = cr;
                     k_last = k[r];
                 }
                 s_k[tid] = k[kItems - 1];
@@ -292,7 +288,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                 for (int r = 0; r < kItems; ++r) {
                     uint32_t lo = k_prev;
                     const uint32_t hi = k[r];
-                    const uint32_t parent = base + r;
+                    const uint32_t parent = tile0 + kItems * tid + r;
                     const bool big = hi > lo && hi - lo > 8;
                     if (!big) {
 #pragma unroll 1
@@ -318,38 +314,11 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         {
             double cobs[D];
 #pragma unroll
-            for (int j = 0; j < D; ++j) cobs[j] = __ldg(a.obs + (size_t)t * D + j);
-            const double *xprev = a.x[cur];
-            double *xnew = a.x[cur ^ 1];
-#pragma unroll
-            for (int h = 0; h < kItems; h += kHalf) {
-                uint32_t par[kHalf];
-                if (full) {
-                    const uint4 p0 = __ldcg(reinterpret_cast<const uint4 *>(a.anc + base + h));
-                    const uint4 p1 = __ldcg(reinterpret_cast<const uint4 *>(a.anc + base + h) + 1);
-                    par[0] = p0.x; par[1] = p0.y; par[2] = p0.z; par[3] = p0.w;
-                    par[4] = p1.x; par[5] = p1.y; par[6] = p1.z; par[7] = p1.w;
-                } else {
-#pragma unroll
-                    for (int r = 0; r < kHalf; ++r) par[r] = base + h + r < a.N ? __ldcg(a.anc + base + h + r) : 0u;
-                }
-                double xs[D][kHalf];
-#pragma unroll
-                for (int r = 0; r < kHalf; ++r) {
-                    const uint32_t i = base + h + r;
-                    double xp[D], z[D], xn[D], q;
-#pragma unroll
-                    for (int j = 0; j < D; ++j) xp[j] = __ldcg(xprev + (int64_t)j * a.ld + par[r]);
-                    draw_normals<D>(a.seed, CUSMC_STREAM_NORMAL, (uint64_t)t, (uint64_t)i, z);
-                    propagate_one<D, DIAG>(op, cobs, xp, z, xn, q);
-#pragma unroll
-                    for (int j = 0; j < D; ++j) xs[j][r] = xn[j];
-                    lw[h + r] = i < a.N ? density_epilogue(ep, q) : -INFINITY;
-                }
-                store_half(xnew, xs, h);
-            }
-            store_lw();
-            publish_max(t);
+            for (int k = 0; k < D; ++k) cobs[k] = __ldg(a.obs + (size_t)t * D + k);
+            double m = -INFINITY;
+#pragma unroll 2
+            for (int r = 0; r < kItems; ++r) particle(op, cobs, t, r, m);
+            publish_max(t, m);
             cur ^= 1;
         }
         grid.sync();
@@ -384,8 +353,10 @@ int launch_persistent(cusmc_filter *f, const PersistArgs &args, unsigned grid, b
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     auto kernel = pf_persistent_kernel<D, DIAG>;
+    constexpr size_t kSmem = 2 * sizeof(double) * (size_t)kPadded;     // log-weights + CDF of one tile
+    CUSMC_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     int per_sm = 0;
-    CUSMC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, 0));
+    CUSMC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, kSmem));
     if ((int64_t)per_sm * ctx->sm_count < (int64_t)grid)
         return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "persistent run: %u tiles exceed the %d resident blocks", grid,
                           per_sm * ctx->sm_count);
@@ -398,7 +369,7 @@ int launch_persistent(cusmc_filter *f, const PersistArgs &args, unsigned grid, b
     Epilogue ep = f->ep;
     PersistArgs a = args;
     void *params[] = {&op0, &op, &ep, &a};
-    CUSMC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kThreads), params, 0, ctx->stream));
+    CUSMC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kThreads), params, kSmem, ctx->stream));
     ctx->launches++;
     return CUSMC_OK;
 }
@@ -426,11 +397,11 @@ bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_
     if (cfg.resampler != CUSMC_RESAMPLE_SYSTEMATIC || cfg.kind != CUSMC_MVN) return false;
     if (cfg.keep_history || cfg.summary) return false;
     if (cfg.d != cfg.dy || (cfg.d != 2 && cfg.d != 4)) return false;
-    if (cfg.N % 2 != 0 || cfg.T < 2) return false;
+    if (cfg.T < 2) return false;
     if (draws && (draws->xi0_dev || draws->xi_dev || draws->chi_dev || draws->u_dev || draws->j_dev || draws->um_dev))
         return false;
     const int64_t tiles = (cfg.N + kPTile - 1) / kPTile;
-    return tiles <= (int64_t)f->ctx->sm_count * 2;    // refined by the occupancy query at launch
+    return tiles <= (int64_t)f->ctx->sm_count * kBlocksPerSM;    // refined by the occupancy query at launch
 }
 
 int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws)
