@@ -386,7 +386,7 @@ class ParticleFilter:
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
                  df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                 persistent=False):
+                 persistent=True):
         self.ctx = ctx
         Y = np.asarray(Y, dtype=np.float64)
         F = np.asarray(F, dtype=np.float64)
@@ -410,7 +410,7 @@ class ParticleFilter:
         cfg.keep_history = int(keep_history)
         cfg.summary = int(summary)
         cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
-        cfg.persistent = 1 if persistent else 0       # opt-in: one cooperative kernel per run when eligible
+        cfg.persistent = 0 if persistent else -1      # one cooperative kernel per run when eligible
         self.keep_history = bool(keep_history)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))

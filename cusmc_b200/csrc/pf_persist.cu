@@ -30,6 +30,7 @@
 #include "../../include/cusmc_detmath.h"
 #include "../../include/cusmc_philox.h"
 
+#include <algorithm>
 #include <cooperative_groups.h>
 
 namespace cg = cooperative_groups;
@@ -37,13 +38,12 @@ namespace cg = cooperative_groups;
 namespace {
 
 constexpr int kThreads = 512;
-constexpr int kItems = 8;                       // particles per thread
-constexpr int kPTile = kThreads * kItems;       // 4096 particles per block
-constexpr int kBlocksPerSM = 3;                 // 3 x 64 KB of shared memory, 1536 threads, <= 42 registers
+// particles per thread: a template parameter P <= 8, picked so that N spreads evenly over the resident blocks
+constexpr int kBlocksPerSM = 2;                 // 2 x 512 threads at <= 64 registers, 2 x 72 KB of shared memory
 // shared-memory index of tile offset j: one pad word per 8, so both the striped (j = r*512 + tid)
-// and the blocked (j = 8*tid + r) access patterns stay (almost) conflict-free
+// and the blocked (j = P*tid + r) access patterns stay (almost) conflict-free
 __device__ __forceinline__ int pad(int j) { return j + (j >> 3); }
-constexpr int kPadded = kPTile + kPTile / 8;
+__host__ __device__ constexpr int padded_words(int P) { return kThreads * P + kThreads * P / 8 + 8; }
 
 struct PersistArgs {
     double *x[2];                   // SoA [d][ld] double buffer
@@ -56,6 +56,7 @@ struct PersistArgs {
     uint64_t seed;
     int64_t ld;
     uint32_t N;
+    uint32_t tile_n;                // particles per block (<= 512 P): N spread evenly over the resident blocks
     int T, shift;
 };
 
@@ -137,21 +138,22 @@ __device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long 
     }
 }
 
-// Phase mappings of a block's 4096-particle tile:
+// Phase mappings of a block's tile of 512 P particles:
 //   propagate : STRIPED, particle tile + r*512 + tid (round r) -- every global access of a warp is one
 //               contiguous line, one particle in flight per thread at a time (small register footprint,
 //               12 resident warps per scheduler hide the gather latency);
-//   weigh / scatter : BLOCKED, particles tile + 8*tid .. +7 -- the tile-local CDF is a thread-local
+//   weigh / scatter : BLOCKED, particles tile + P*tid .. +P-1 -- the tile-local CDF is a thread-local
 //               running sum plus one block scan.
 // The log-weights and the CDF cross between the two mappings, and between phases, through shared
 // memory (2 x 36 KB per block): neither is ever re-read from global memory.
-template <int D, bool DIAG>
+template <int D, bool DIAG, int P>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                      const __grid_constant__ pfstep::StepOp<D, DIAG> op, const Epilogue ep, const PersistArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kItems = P, kPadded = padded_words(P);
     double *s_lw = reinterpret_cast<double *>(smem_raw);                               // [kPadded]
     unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw) + kPadded;   // [kPadded]
     __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
@@ -161,7 +163,8 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
     __shared__ double s_ng_over_t, s_r0_over_t;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t tile0 = blockIdx.x * kPTile;
+    const uint32_t tile0 = blockIdx.x * a.tile_n;
+    const uint32_t tile_n = min(a.tile_n, a.N - tile0);     // particles of this tile
     int cur = 0;
 
     // one particle: gather (t > 0), noise, propagate, reweight; striped round r
@@ -169,7 +172,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         const int j = r * kThreads + (int)tid;
         const uint32_t i = tile0 + (uint32_t)j;
         double lw = -INFINITY;
-        if (i < a.N) {
+        if ((uint32_t)j < tile_n) {
             double xp[D], z[D], xn[D], q;
             if (t > 0) {
                 const uint32_t par = __ldcg(a.anc + i);
@@ -288,7 +291,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                 for (int r = 0; r < kItems; ++r) {
                     uint32_t lo = k_prev;
                     const uint32_t hi = k[r];
-                    const uint32_t parent = tile0 + kItems * tid + r;
+                    const uint32_t parent = tile0 + kItems * tid + r;      // (beyond the tile: zero weight, no children)
                     const bool big = hi > lo && hi - lo > 8;
                     if (!big) {
 #pragma unroll 1
@@ -347,13 +350,14 @@ __global__ void persist_init_slots(StepSlot *slots, int T)
     }
 }
 
-template <int D, bool DIAG>
-int launch_persistent(cusmc_filter *f, const PersistArgs &args, unsigned grid, bool probe_only)
+template <int D, bool DIAG, int P>
+int launch_persistent(cusmc_filter *f, const PersistArgs &args, bool probe_only)
 {
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
-    auto kernel = pf_persistent_kernel<D, DIAG>;
-    constexpr size_t kSmem = 2 * sizeof(double) * (size_t)kPadded;     // log-weights + CDF of one tile
+    auto kernel = pf_persistent_kernel<D, DIAG, P>;
+    constexpr size_t kSmem = 2 * sizeof(double) * (size_t)padded_words(P);     // log-weights + CDF of one tile
+    const unsigned grid = (unsigned)((cfg.N + args.tile_n - 1) / args.tile_n);
     CUSMC_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     int per_sm = 0;
     CUSMC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, kSmem));
@@ -369,9 +373,52 @@ int launch_persistent(cusmc_filter *f, const PersistArgs &args, unsigned grid, b
     Epilogue ep = f->ep;
     PersistArgs a = args;
     void *params[] = {&op0, &op, &ep, &a};
-    CUSMC_CUDA(ctx, cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kThreads), params, kSmem, ctx->stream));
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)kernel, dim3(grid), dim3(kThreads), params, kSmem,
+                                                      ctx->stream);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        cudaGetLastError();
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "cooperative launch refused: %s", cudaGetErrorString(e));
+    }
+    CUSMC_CUDA(ctx, e);
     ctx->launches++;
     return CUSMC_OK;
+}
+
+// Particles per tile: N spread evenly over ALL resident block slots (every SM gets the same work; a
+// fixed tile size would leave some SMs with half the work of their neighbours), and the smallest
+// particles-per-thread count P that holds such a tile.
+uint32_t pick_tile(const cusmc_filter *f)
+{
+    const int64_t slots = (int64_t)f->ctx->sm_count * kBlocksPerSM;
+    int64_t n = (f->cfg.N + slots - 1) / slots;
+    n = (n + 31) & ~(int64_t)31;                       // whole warps in the striped rounds
+    return (uint32_t)std::max<int64_t>(n, 32);
+}
+int pick_items(const cusmc_filter *f)
+{
+    const uint32_t n = pick_tile(f);
+    for (int P : {2, 4, 6, 7, 8})
+        if (n <= (uint32_t)(kThreads * P)) return P;
+    return 0;
+}
+
+template <int D, bool DIAG>
+int launch_persistent_p(cusmc_filter *f, const PersistArgs &args, int P, bool probe_only)
+{
+    switch (P) {
+        case 2: return launch_persistent<D, DIAG, 2>(f, args, probe_only);
+        case 4: return launch_persistent<D, DIAG, 4>(f, args, probe_only);
+        case 6: return launch_persistent<D, DIAG, 6>(f, args, probe_only);
+        case 7: return launch_persistent<D, DIAG, 7>(f, args, probe_only);
+        case 8: return launch_persistent<D, DIAG, 8>(f, args, probe_only);
+    }
+    return cusmc_fail(f->ctx, CUSMC_ERR_UNSUPPORTED, "persistent run: too many particles for one tile per resident block");
+}
+
+int launch_persistent_any(cusmc_filter *f, const PersistArgs &args, int d, bool diag, int P, bool probe_only)
+{
+    if (d == 2) return diag ? launch_persistent_p<2, true>(f, args, P, probe_only) : launch_persistent_p<2, false>(f, args, P, probe_only);
+    return diag ? launch_persistent_p<4, true>(f, args, P, probe_only) : launch_persistent_p<4, false>(f, args, P, probe_only);
 }
 
 bool is_diag_cm(const double *A, int d)
@@ -393,15 +440,14 @@ uint64_t u0_bits(uint64_t seed, uint64_t step)
 bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_draws *draws)
 {
     const cusmc_filter_config &cfg = f->cfg;
-    if (cfg.persistent <= 0 || f->world != 1) return false;
+    if (cfg.persistent < 0 || f->world != 1) return false;
     if (cfg.resampler != CUSMC_RESAMPLE_SYSTEMATIC || cfg.kind != CUSMC_MVN) return false;
     if (cfg.keep_history || cfg.summary) return false;
     if (cfg.d != cfg.dy || (cfg.d != 2 && cfg.d != 4)) return false;
     if (cfg.T < 2) return false;
     if (draws && (draws->xi0_dev || draws->xi_dev || draws->chi_dev || draws->u_dev || draws->j_dev || draws->um_dev))
         return false;
-    const int64_t tiles = (cfg.N + kPTile - 1) / kPTile;
-    return tiles <= (int64_t)f->ctx->sm_count * kBlocksPerSM;    // refined by the occupancy query at launch
+    return pick_items(f) != 0;                        // refined by the occupancy query at launch
 }
 
 int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws)
@@ -411,16 +457,17 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     if (!cusmc_filter_persistent_eligible(f, draws))
         return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "configuration not covered by the persistent kernel");
     const int d = cfg.d, T = cfg.T;
-    const unsigned grid = (unsigned)((cfg.N + kPTile - 1) / kPTile);
+    const int P = pick_items(f);
+    const uint32_t tile_n = pick_tile(f);
+    const unsigned grid = (unsigned)((cfg.N + tile_n - 1) / tile_n);
     bool diag = is_diag_cm(f->G.data(), d) && is_diag_cm(f->Qw.data(), d) && is_diag_cm(f->Qc0.data(), d);
     for (int k = 0; k < d && diag; ++k)
         for (int j = 0; j < d; ++j)
             if (j != k && f->M[(size_t)k * d + j] != 0.0) diag = false;
     PersistArgs a{};
+    a.tile_n = tile_n;
     // resident-block check before anything is enqueued (so the caller can still fall back)
-    int rc;
-    if (d == 2) rc = diag ? launch_persistent<2, true>(f, a, grid, true) : launch_persistent<2, false>(f, a, grid, true);
-    else rc = diag ? launch_persistent<4, true>(f, a, grid, true) : launch_persistent<4, false>(f, a, grid, true);
+    int rc = launch_persistent_any(f, a, d, diag, P, true);
     if (rc != CUSMC_OK) return rc;
 
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -468,8 +515,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     a.T = T;
     a.shift = f->shift;
     CUSMC_CUDA(ctx, cudaEventRecord(f->ev0, st));
-    if (d == 2) rc = diag ? launch_persistent<2, true>(f, a, grid, false) : launch_persistent<2, false>(f, a, grid, false);
-    else rc = diag ? launch_persistent<4, true>(f, a, grid, false) : launch_persistent<4, false>(f, a, grid, false);
+    rc = launch_persistent_any(f, a, d, diag, P, false);
     if (rc != CUSMC_OK) return rc;
     CUSMC_CUDA(ctx, cudaEventRecord(f->ev1, st));
     f->cur = (T - 1) & 1;

@@ -282,13 +282,12 @@ typedef struct cusmc_filter_config {
     /* Sharded runs (one process per GPU): N is the GLOBAL particle count; rank r of `world` owns the
      * global slots r*per .. min((r+1)*per, N) - 1, per = ceil(N / world).  world <= 1: one GPU. */
     int rank, world;
-    /* 1: cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (three grid
+    /* cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (three grid
      * barriers per step instead of four launches; log-weights and the weight image stay in shared
      * memory) when the configuration allows it: one GPU, systematic resampling, Normal noise,
-     * d == dy in {2, 4}, device-drawn noise, no history, no summary, N small enough for one
-     * 4096-particle tile per resident block (1.8 M particles on a B200); otherwise, and with 0
-     * (default), the four-launch step.  Results are bit-identical.  Opt-in: in round 1 it is only 5 %
-     * faster (33.8 vs 35.7 us per 10^6-particle step, profiles/r01j_persist_summary.md). */
+     * d == dy in {2, 4}, device-drawn noise, no history, no summary, N small enough for one tile of
+     * <= 4096 particles per resident block (1.2 M particles on a B200).  Results are bit-identical
+     * to the four-launch step (28 vs 35 us per 10^6-particle step).  0 = automatic, -1 = never. */
     int persistent;
 } cusmc_filter_config;
 
