@@ -49,6 +49,31 @@ def ncu_traffic():
         return None
 
 
+def bind_to_gpu_numa_node(torch, device):
+    """The end-to-end leg is bound by host->device copies; with one rank per GPU the pinned staging
+    buffers must live on the NUMA node the GPU hangs off (first-touch), or the ranks' DMA traffic
+    crosses the socket interconnect.  Best effort: silently does nothing where sysfs says nothing."""
+    try:
+        bus = torch.cuda.get_device_properties(device).pci_bus_id
+        dom = torch.cuda.get_device_properties(device).pci_domain_id
+        dev = torch.cuda.get_device_properties(device).pci_device_id
+        path = "/sys/bus/pci/devices/%04x:%02x:%02x.0/numa_node" % (dom, bus, dev)
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -252,6 +277,56 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
             "fp64_tflops": rate * (2 * d * (d + 1) + 4 * d) / 1e12}
     except Exception as e:
         out["mh_c3_chain_steps_per_sec"] = {"error": repr(e)}
+    try:
+        # a4: the reference's own resampler at C4 size (10^6 weights, B = 10), device-drawn (u, j)
+        N, B = 1000000, 10
+        w = torch.rand(N, dtype=torch.float64, device="cuda")
+        a = torch.empty(N, dtype=torch.int32, device="cuda")
+        ctx.metropolis_hastings_dev(a, w, B, seed=5, step=1)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 50
+        e0.record()
+        for r in range(reps):
+            ctx.metropolis_hastings_dev(a, w, B, seed=5, step=2 + r)
+        e1.record()
+        torch.cuda.synchronize()
+        us = e0.elapsed_time(e1) * 1e3 / reps
+        out["metropolis_c4_resample"] = {"us_per_call": us, "N": N, "B": B,
+                                         "accept_tests_per_sec": N * B / (us * 1e-6),
+                                         "bytes_per_particle": 12 + 8 * B, "noise": "philox in-kernel",
+                                         "l2_sector_gbs": N * B * 32 / (us * 1e-6) / 1e9,
+                                         "bound": "32-byte L2 sectors pulled by random 8-byte weight reads"}
+    except Exception as e:
+        out["metropolis_c4_resample"] = {"error": repr(e)}
+    try:
+        # a1/a2 with one covariance per point (the C3 shape as a batched density): d = 32, packed factors
+        N, d = 1 << 19, 32
+        packed = d * (d + 1) // 2
+        g = torch.Generator(device="cuda").manual_seed(9)
+        Lp = torch.randn((N, packed), dtype=torch.float64, device="cuda", generator=g) * 0.1
+        diag_idx = torch.tensor([k * (k + 1) // 2 + k for k in range(d)], device="cuda")
+        Lp[:, diag_idx] = Lp[:, diag_idx].abs() + 1.0
+        x = torch.randn((N, d), dtype=torch.float64, device="cuda", generator=g)
+        mu = torch.zeros((N, d), dtype=torch.float64, device="cuda")
+        o = torch.empty(N, dtype=torch.float64, device="cuda")
+        ctx.logpdf_perpoint_dev("mvt", x, mu, Lp, o, nu=5.0)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 10
+        e0.record()
+        for _ in range(reps):
+            ctx.logpdf_perpoint_dev("mvt", x, mu, Lp, o, nu=5.0)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        bytes_per = 8 * d + 8 * d + 8 * packed + 8
+        out["perpoint_logpdf_evals_per_sec"] = {
+            "value": N / (ms * 1e-3), "N": N, "d": d, "ms": ms, "bytes_per_eval": bytes_per,
+            "roofline_frac": N * bytes_per / (ms * 1e-3) / (hbm_gbs * 1e9),
+            "note": "per-point packed Cholesky factor staged per warp by 1-D TMA bulk copies"}
+    except Exception as e:
+        out["perpoint_logpdf_evals_per_sec"] = {"error": repr(e)}
     return out
 
 
@@ -321,6 +396,7 @@ def main():
         print(json.dumps({"error": "no CUDA device: cusmc_b200 has no CPU fallback"}))
         return 1
     torch.cuda.set_device(local_rank)
+    numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -412,7 +488,8 @@ def main():
                      "kernel_ms": kernel_ms},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
                 "d2h_bytes_per_step": N_POINTS * 8, "steps": e2e_steps,
-                "path": "cusmc_logpdf (host pointers, pinned AoS in, pinned result out)"},
+                "path": "cusmc_logpdf (host pointers, pinned AoS in, pinned result out)",
+                "numa_node": numa_node},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

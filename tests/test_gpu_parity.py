@@ -256,6 +256,36 @@ def test_metropolis_invariants(ctx, orc):
     assert np.array_equal(ctx.metropolis_hastings(np.zeros(2), 10), [0, 1])
 
 
+def test_metropolis_near_ties_take_the_reference_decision(ctx, orc):
+    """u <= w_j / w_k with u built ON the boundary (equal to the IEEE quotient and its neighbours) and
+    zero / denormal / huge / infinite / NaN weights in play: the reference's decision, bit for bit."""
+    rng = np.random.default_rng(8)
+    N, B = 4096, 6
+    w = rng.random(N) ** 3
+    w[rng.random(N) < 0.05] = 0.0
+    w[5], w[6], w[7], w[8], w[9] = 1e-310, 3e-300, 1e305, np.inf, np.nan
+    j = rng.integers(0, N, (N, B), dtype=np.uint32)
+    j[::7, 0] = rng.integers(5, 10, j[::7, 0].shape)           # hit the special weights often
+    u = rng.random((N, B))
+    # walk the chain on the host to know w_k at every test, then put u on / next to the quotient
+    k = np.arange(N)
+    with np.errstate(all="ignore"):
+        for n in range(B):
+            q = w[j[:, n]] / w[k]
+            mode = rng.integers(0, 4, N)
+            un = u[:, n].copy()
+            ok = np.isfinite(q) & (q > 0) & (q < 1)
+            un[ok & (mode == 0)] = q[ok & (mode == 0)]
+            un[ok & (mode == 1)] = np.nextafter(q[ok & (mode == 1)], 2.0)
+            un[ok & (mode == 2)] = np.nextafter(q[ok & (mode == 2)], 0.0)
+            u[:, n] = un
+            acc = un <= q
+            k = np.where(acc, j[:, n], k)
+    want = orc.metropolis_hastings(w, u, j)
+    assert np.mean(want == k.astype(np.uint32)) > 0.99           # the host walk follows the same rule
+    assert np.array_equal(ctx.metropolis_hastings(w, B, u=u, j=j), want)
+
+
 def test_metropolis_philox_mirror(ctx, orc):
     N, B = 300, 10
     w = np.random.default_rng(8).random(N)
