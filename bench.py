@@ -273,8 +273,8 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
         out["mh_c3_chain_steps_per_sec"] = {
             "value": rate, "chains": Cn, "d": d, "steps": steps, "ms": ms, "target": "mvt nu=5 per-chain L",
             "noise": "philox in-kernel", "accept_rate": float(nacc.double().mean().item() / steps),
-            "flops_per_chain_step": 2 * d * (d + 1) + 4 * d,
-            "fp64_tflops": rate * (2 * d * (d + 1) + 4 * d) / 1e12}
+            "formulation": "whitened coordinates: v' = v + s z, q' = |v'|^2 (the proposal uses the target's factor); "
+                           "the factor whitens the start and un-whitens the result"}
     except Exception as e:
         out["mh_c3_chain_steps_per_sec"] = {"error": repr(e)}
     try:

@@ -1,10 +1,10 @@
 // chains.cu -- per-chain / per-point covariance paths (BASELINE.json configs[2]):
 //
 //  * mh_chains_kernel: independent random-walk Metropolis-Hastings chains on an MVN / MVT
-//    target, one warp per chain.  Lane k keeps row k of the chain's Cholesky factor in
-//    registers for the whole run, so a step reads only its d normals (+ threshold) from HBM:
-//    proposal x' = x + s L z is a shuffle-broadcast mat-vec, whitening v = L^-1 (x' - mu) a
-//    column-oriented forward substitution, accept/reject a transcendental-free comparison.
+//    target, one warp per chain, lane k owns component k.  The proposal x' = x + s L z uses the
+//    target's own factor, so the chain runs in whitened coordinates v = L^-1 (x - mu): a step is
+//    v' = v + s z, q' = |v'|^2 (one warp sum) and a transcendental-free accept comparison; the
+//    factor is used to whiten the start and un-whiten the result (and for running sums of x).
 //  * perpoint_kernel: log-density with one covariance per point; each warp pulls its point's
 //    packed factor into shared memory with a 1-D TMA bulk copy (cp.async.bulk + mbarrier,
 //    double buffered) and runs the same forward substitution.
@@ -49,12 +49,28 @@ struct ChainArgs {
     int d, steps, kind, shared;
 };
 
-template <int D, bool PHILOX>
+// Sum over the warp's 32 lanes by xor butterflies (16, 8, 4, 2, 1): every lane ends with the same
+// bits, and a host reproduces them with the same pairing (oracle: butterfly32).
+__device__ __forceinline__ double warp_sum_butterfly(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// The chain runs in WHITENED coordinates.  The proposal x' = x + s L z uses the target's own factor,
+// so with v = L^-1 (x - mu) it is simply v' = v + s z and the target's quadratic form is |v'|^2:
+// a step is one FMA and one warp sum -- no mat-vec, no forward substitution, and the factor is
+// needed only to whiten the start, to un-whiten the result and (MOMENTS) for the running sums of x,
+// so the step loop does not keep it in registers.  Same law as the x-space chain, a fraction of
+// the work; the oracle (orc_mh_chains) restates exactly this arithmetic.
+template <int D, bool PHILOX, bool MOMENTS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mh_chains_kernel(const ChainArgs a)
 {
-    const int lane = threadIdx.x & 31;
-    const int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+    __shared__ __align__(16) double s_v[kWarpsPerBlock][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
     if (c >= a.C) return;
     const int d = a.d;
     const bool live = lane < d;
@@ -63,10 +79,37 @@ mh_chains_kernel(const ChainArgs a)
     double row[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) row[j] = (live && j <= lane) ? __ldg(Lc + (size_t)j * d + lane) : 0.0;
-    const double rinv = live ? 1.0 / __ldg(Lc + (size_t)lane * d + lane) : 0.0;
     const double mu = live ? __ldg(mc + lane) : 0.0;
-    double x = live ? a.x[(size_t)c * d + lane] : 0.0;
-    double q = whiten_q<D>(row, rinv, x - mu);
+
+    // x = mu + L v: v broadcast through shared memory, row k = sum_j L[k][j] v_j, j ascending
+    auto unwhiten = [&](double v) {
+        __syncwarp();
+        s_v[wib][lane] = v;
+        __syncwarp();
+        double acc = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; j += 2) {
+            const double2 vv = *reinterpret_cast<const double2 *>(&s_v[wib][j]);
+            acc = fma(row[j], vv.x, acc);
+            if (j + 1 < D) acc = fma(row[j + 1], vv.y, acc);
+        }
+        return mu + acc;
+    };
+
+    // whiten the start: column-oriented forward substitution, lane k keeps v_k
+    double v = 0.0;
+    const double x_start = live ? a.x[(size_t)c * d + lane] : 0.0;
+    {
+        const double rinv = live ? 1.0 / __ldg(Lc + (size_t)lane * d + lane) : 0.0;
+        double r = live ? x_start - mu : 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, r * rinv, j);
+            if (j == lane) v = vj;
+            r = fma(-row[j], vj, r);   // no-op for lanes k < j (row[j] == 0); lane j is done with r
+        }
+    }
+    double q = warp_sum_butterfly(v * v);
     const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
     double sx = 0.0, sxx = 0.0;
     uint32_t nacc = 0;
@@ -101,8 +144,8 @@ mh_chains_kernel(const ChainArgs a)
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int pick = (lane & 3) ^ r;        // the normal owed to lane ^ r
-                    const float v = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
-                    zq[r] = __shfl_xor_sync(0xffffffffu, v, r);
+                    const float val = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
+                    zq[r] = __shfl_xor_sync(0xffffffffu, val, r);
                 }
             }
             const int r = (lane & 3) ^ (s & 3);
@@ -113,30 +156,33 @@ mh_chains_kernel(const ChainArgs a)
             if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + lane);   // prefetch
             thr = __ldg(a.thr + (size_t)c * a.steps + s);
         }
-        // proposal: x' = x + step * (L z), row k = sum_{j <= k} L[k][j] z_j, j ascending
-        double acc = 0.0;
-#pragma unroll
-        for (int j = 0; j < D; ++j) acc = fma(row[j], __shfl_sync(0xffffffffu, z, j), acc);
-        const double xp = fma(a.step_size, acc, x);
-        const double qp = whiten_q<D>(row, rinv, xp - mu);
+        // proposal and its quadratic form, in whitened coordinates
+        const double vp = fma(a.step_size, z, v);
+        const double qp = warp_sum_butterfly(vp * vp);
         bool accept;
         if (a.kind == CUSMC_MVT)
             accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
         else
             accept = 0.5 * (qp - q) < thr;
         if (accept) {
-            x = xp;
+            v = vp;
             q = qp;
             ++nacc;
         }
-        sx += x;
-        sxx = fma(x, x, sxx);
+        if (MOMENTS) {
+            const double x = nacc ? unwhiten(v) : x_start;
+            sx += x;
+            sxx = fma(x, x, sxx);
+        }
         if (a.accept_bits && lane == 0) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
     }
+    const double x = nacc ? unwhiten(v) : x_start;     // a chain that never moved is left untouched
     if (live) {
         a.x[(size_t)c * d + lane] = x;
-        if (a.sum_x) a.sum_x[(size_t)c * d + lane] = sx;
-        if (a.sum_xx) a.sum_xx[(size_t)c * d + lane] = sxx;
+        if (MOMENTS) {
+            if (a.sum_x) a.sum_x[(size_t)c * d + lane] = sx;
+            if (a.sum_xx) a.sum_xx[(size_t)c * d + lane] = sxx;
+        }
     }
     if (a.n_accept && lane == 0) a.n_accept[c] = nacc;
 }
@@ -266,10 +312,15 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
     a.d = d; a.steps = steps; a.kind = kind; a.shared = shared;
     const unsigned grid = (unsigned)((C + kWarpsPerBlock - 1) / kWarpsPerBlock);
     const bool philox = z_dev == nullptr;
+    const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
+#define CUSMC_CHAIN_LAUNCH(DD, PH, MO) \
+    mh_chains_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a)
 #define CUSMC_CHAIN_CASE(DD)                                                                         \
     case DD:                                                                                         \
-        if (philox) mh_chains_kernel<DD, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);    \
-        else mh_chains_kernel<DD, false><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);          \
+        if (philox && moments) CUSMC_CHAIN_LAUNCH(DD, true, true);                                   \
+        else if (philox) CUSMC_CHAIN_LAUNCH(DD, true, false);                                        \
+        else if (moments) CUSMC_CHAIN_LAUNCH(DD, false, true);                                       \
+        else CUSMC_CHAIN_LAUNCH(DD, false, false);                                                   \
         break;
     switch (cusmc_pad_dim(d)) {
         CUSMC_CHAIN_CASE(2)
@@ -278,6 +329,7 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
         CUSMC_CHAIN_CASE(16)
         CUSMC_CHAIN_CASE(32)
     }
+#undef CUSMC_CHAIN_LAUNCH
 #undef CUSMC_CHAIN_CASE
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;

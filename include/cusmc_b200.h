@@ -241,7 +241,9 @@ int cusmc_normalize_ess(cusmc_ctx *ctx, const double *lw, int64_t N, double *lse
 /*
  * C random-walk MH chains on an MVN / MVT target with per-chain (shared = 0) or
  * single (shared = 1) location mu and lower Cholesky factor L (column-major d x d,
- * strict upper ignored).  Proposal x' = x + step_size * (L z).  Accept rule
+ * strict upper ignored).  Proposal x' = x + step_size * (L z); because it uses the target's own
+ * factor the chain is run in whitened coordinates v = L^-1 (x - mu): v' = v + step_size z,
+ * q' = |v'|^2, x = mu + L v on output (a chain that never accepts keeps its x bit for bit).  Accept rule
  * (transcendental-free so decisions are bit-reproducible on the host):
  *   mvn: 0.5 (q' - q) < thr             thr = -log(u)
  *   mvt: (1 + q'/nu) < thr (1 + q/nu)   thr = exp(2 (-log u) / (nu + d))

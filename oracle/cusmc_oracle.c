@@ -730,6 +730,21 @@ static double whiten_q(const double *L, const double *rinv, const double *r, dou
     return q;
 }
 
+/* Sum of 32 values by xor butterflies (16, 8, 4, 2, 1), the pairing of the kernel's warp sum. */
+static double butterfly32(const double *a32)
+{
+    double a[32], b[32];
+    memcpy(a, a32, sizeof a);
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int l = 0; l < 32; ++l) b[l] = a[l] + a[l ^ o];
+        memcpy(a, b, sizeof a);
+    }
+    return a[0];
+}
+
+/* Random-walk MH with the proposal x' = x + step L z, run in whitened coordinates
+ * v = L^-1 (x - mu):  v' = v + step z,  q' = |v'|^2  (no counterpart in the reference; this
+ * function DEFINES the arithmetic mh_chains_kernel reproduces bit for bit). */
 void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu,
                    int shared, const double *mu, const double *L,
                    const double *x0, const double *z, const double *thr,
@@ -738,28 +753,31 @@ void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu
     double inv_nu = dist == 1 ? 1.0 / nu : 0.0;
 #pragma omp parallel
     {
-        double *x = (double *)malloc(sizeof(double) * d * 5);
-        double *xp = x + d, *r = x + 2 * d, *v = x + 3 * d, *rinv = x + 4 * d;
+        double *r = (double *)malloc(sizeof(double) * d * 3);
+        double *v = r + d, *rinv = r + 2 * d;
+        double vv[32], vp[32], sq[32];
 #pragma omp for schedule(static)
         for (int64_t c = 0; c < C; ++c) {
             const double *Lc = shared ? L : L + (size_t)c * d * d;
             const double *mc = shared ? mu : mu + (size_t)c * d;
             for (int k = 0; k < d; ++k) {
                 rinv[k] = 1.0 / A_(Lc, k, k, d);
-                x[k] = x0[(size_t)c * d + k];
-                r[k] = x[k] - mc[k];
+                r[k] = x0[(size_t)c * d + k] - mc[k];
             }
-            double q = whiten_q(Lc, rinv, r, v, d);
+            (void)whiten_q(Lc, rinv, r, v, d);
+            for (int k = 0; k < 32; ++k) {
+                vv[k] = k < d ? v[k] : 0.0;
+                sq[k] = vv[k] * vv[k];
+            }
+            double q = butterfly32(sq);
             uint32_t nacc = 0;
             for (int s = 0; s < steps; ++s) {
                 const double *zs = z + ((size_t)c * steps + s) * d;
-                for (int k = 0; k < d; ++k) {
-                    double acc = 0.0;
-                    for (int j = 0; j <= k; ++j) acc = fma(A_(Lc, k, j, d), zs[j], acc);
-                    xp[k] = fma(step, acc, x[k]);
-                    r[k] = xp[k] - mc[k];
+                for (int k = 0; k < 32; ++k) {
+                    vp[k] = k < d ? fma(step, zs[k], vv[k]) : 0.0;
+                    sq[k] = vp[k] * vp[k];
                 }
-                double qp = whiten_q(Lc, rinv, r, v, d);
+                double qp = butterfly32(sq);
                 double th = thr[(size_t)c * steps + s];
                 int acc_flag;
                 if (dist == 0) {
@@ -770,16 +788,20 @@ void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu
                     acc_flag = tp < th * tc;
                 }
                 if (acc_flag) {
-                    for (int k = 0; k < d; ++k) x[k] = xp[k];
+                    memcpy(vv, vp, sizeof vv);
                     q = qp;
                     ++nacc;
                 }
                 if (accept_bits) accept_bits[(size_t)c * steps + s] = (uint8_t)acc_flag;
             }
-            for (int k = 0; k < d; ++k) x_final[(size_t)c * d + k] = x[k];
+            for (int k = 0; k < d; ++k) {          /* x = mu + L v, j ascending; untouched if it never moved */
+                double acc = 0.0;
+                for (int j = 0; j <= k; ++j) acc = fma(A_(Lc, k, j, d), vv[j], acc);
+                x_final[(size_t)c * d + k] = nacc ? mc[k] + acc : x0[(size_t)c * d + k];
+            }
             if (n_accept) n_accept[c] = nacc;
         }
-        free(x);
+        free(r);
     }
 }
 
