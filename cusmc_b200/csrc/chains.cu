@@ -76,22 +76,30 @@ mh_chains_kernel(const ChainArgs a)
     const bool live = lane < d;
     const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
     const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
-    double row[D];
-#pragma unroll
-    for (int j = 0; j < D; ++j) row[j] = (live && j <= lane) ? __ldg(Lc + (size_t)j * d + lane) : 0.0;
     const double mu = live ? __ldg(mc + lane) : 0.0;
-
+    // Row k of the factor (column-major storage, so element j of every lane's row is one coalesced
+    // line).  Without MOMENTS the rows are streamed from memory where they are used -- when the start
+    // is whitened and when the result is un-whitened -- in chunks of 8 columns, so neither the step
+    // loop nor those two passes hold 2 D registers of factor; MOMENTS needs x every step and keeps
+    // the row in registers.
+    auto Lkj = [&](const double *Lp, int j) { return (live && j <= lane) ? __ldg(Lp + (size_t)j * d + lane) : 0.0; };
+    double row_m[MOMENTS ? D : 1];
+    if (MOMENTS) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) row_m[j] = Lkj(Lc, j);
+    }
     // x = mu + L v: v broadcast through shared memory, row k = sum_j L[k][j] v_j, j ascending
-    auto unwhiten = [&](double v) {
+    auto unwhiten = [&](const double *Lp, double v) {
         __syncwarp();
         s_v[wib][lane] = v;
         __syncwarp();
         double acc = 0.0;
+        if constexpr (MOMENTS) {
 #pragma unroll
-        for (int j = 0; j < D; j += 2) {
-            const double2 vv = *reinterpret_cast<const double2 *>(&s_v[wib][j]);
-            acc = fma(row[j], vv.x, acc);
-            if (j + 1 < D) acc = fma(row[j + 1], vv.y, acc);
+            for (int j = 0; j < D; ++j) acc = fma(row_m[j], s_v[wib][j], acc);
+        } else {
+#pragma unroll 8
+            for (int j = 0; j < D; ++j) acc = fma(Lkj(Lp, j), s_v[wib][j], acc);
         }
         return mu + acc;
     };
@@ -102,11 +110,11 @@ mh_chains_kernel(const ChainArgs a)
     {
         const double rinv = live ? 1.0 / __ldg(Lc + (size_t)lane * d + lane) : 0.0;
         double r = live ? x_start - mu : 0.0;
-#pragma unroll
+#pragma unroll 8
         for (int j = 0; j < D; ++j) {
             const double vj = __shfl_sync(0xffffffffu, r * rinv, j);
             if (j == lane) v = vj;
-            r = fma(-row[j], vj, r);   // no-op for lanes k < j (row[j] == 0); lane j is done with r
+            r = fma(-Lkj(Lc, j), vj, r);   // no-op for lanes k < j (L[k][j] == 0); lane j is done with r
         }
     }
     double q = warp_sum_butterfly(v * v);
@@ -170,13 +178,13 @@ mh_chains_kernel(const ChainArgs a)
             ++nacc;
         }
         if (MOMENTS) {
-            const double x = nacc ? unwhiten(v) : x_start;
+            const double x = nacc ? unwhiten(Lc, v) : x_start;
             sx += x;
             sxx = fma(x, x, sxx);
         }
         if (a.accept_bits && lane == 0) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
     }
-    const double x = nacc ? unwhiten(v) : x_start;     // a chain that never moved is left untouched
+    const double x = nacc ? unwhiten(Lc, v) : x_start;     // a chain that never moved is left untouched
     if (live) {
         a.x[(size_t)c * d + lane] = x;
         if (MOMENTS) {
