@@ -262,13 +262,27 @@ perpoint_kernel(const PerPointArgs a, const Epilogue ep, const double lognorm_ba
             for (int e = lane; e < packed; e += 32) s_L[wib][buf][e] = ld_stream(src + e);
         }
     };
-    if (w0 < a.N) issue(w0, 0);
+    // the point and its mean are prefetched one iteration ahead as well (registers): without it every
+    // iteration started by waiting a full memory latency on them (the kernel's top stall site)
+    auto load_x = [&](int64_t pt) { return live ? ld_stream(a.x + (size_t)pt * d + lane) : 0.0; };
+    auto load_m = [&](int64_t pt) { return (live && a.mu) ? ld_stream(a.mu + (size_t)pt * d + lane) : 0.0; };
+    double x_next = 0.0, m_next = 0.0;
+    if (w0 < a.N) {
+        issue(w0, 0);
+        x_next = load_x(w0);
+        m_next = load_m(w0);
+    }
     uint32_t phase[2] = {0, 0};
     int buf = 0;
     for (int64_t pt = w0; pt < a.N; pt += n_warps, buf ^= 1) {
         const int64_t nxt = pt + n_warps;
-        if (nxt < a.N) issue(nxt, buf ^ 1);          // prefetch the next factor
-        double r = live ? ld_stream(a.x + (size_t)pt * d + lane) - (a.mu ? ld_stream(a.mu + (size_t)pt * d + lane) : 0.0) : 0.0;
+        const double x_cur = x_next, m_cur = m_next;
+        if (nxt < a.N) {
+            issue(nxt, buf ^ 1);                     // prefetch the next factor
+            x_next = load_x(nxt);
+            m_next = load_m(nxt);
+        }
+        double r = x_cur - m_cur;
         if (a.use_tma) {
             mbar_wait(&s_bar[wib][buf], phase[buf]);
             phase[buf] ^= 1;

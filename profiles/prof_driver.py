@@ -54,3 +54,16 @@ if which in ("all", "mh"):
     ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=3)
     torch.cuda.synchronize()
 print("prof_driver done", ctx.launch_count, "launches")
+
+if which in ("perpoint",):
+    N, d = 1 << 19, 32
+    packed = d * (d + 1) // 2
+    Lp = torch.randn((N, packed), dtype=torch.float64, device="cuda") * 0.1
+    diag_idx = torch.tensor([k * (k + 1) // 2 + k for k in range(d)], device="cuda")
+    Lp[:, diag_idx] = Lp[:, diag_idx].abs() + 1.0
+    x = torch.randn((N, d), dtype=torch.float64, device="cuda")
+    mu = torch.zeros((N, d), dtype=torch.float64, device="cuda")
+    o = torch.empty(N, dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        ctx.logpdf_perpoint_dev("mvt", x, mu, Lp, o, nu=5.0)
+    torch.cuda.synchronize()
