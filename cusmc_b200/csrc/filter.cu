@@ -794,6 +794,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     a.rng_stream = CUSMC_STREAM_NORMAL;
     if (f->world > 1) {
         a.world = f->world;
+        a.rank = f->rank;
         a.per_rank = make_fast_div((uint32_t)f->per);
         a.x_prev_peer = (const double *const *)f->peer_x[f->cur].table_dev;
     }

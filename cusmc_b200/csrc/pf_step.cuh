@@ -26,7 +26,7 @@ struct StepArgs {
     // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.
     const double *const *x_prev_peer;   // device table of the ranks' state buffers
     FastDiv per_rank;
-    int world;
+    int world, rank;             // rank: parents on this rank are read through x_prev directly
 };
 
 // G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no

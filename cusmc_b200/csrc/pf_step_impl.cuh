@@ -110,8 +110,11 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         if (a.has_prev) {
             const double *src = a.x_prev + parent;
             if (a.world > 1) {
+                // ancestors are (nearly) sorted, so almost every parent is local: only a remote one
+                // pays the dependent load of its owner's pointer from the table in device memory
                 const uint32_t g = (uint32_t)parent, r = fast_div(g, a.per_rank);
-                src = a.x_prev_peer[r] + (g - r * a.per_rank.d);   // table in device memory
+                const uint32_t col = g - r * a.per_rank.d;
+                src = (r == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[r]) + col;
             }
 #pragma unroll
             for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;

@@ -336,6 +336,7 @@ struct ScanArgs {
     uint32_t *anc_out;                     // optional systematic ancestors for children
     uint32_t *const *anc_peer;             // PEERS: device table, rank r's ancestor array (child slots r*per_rank ..)
     FastDiv per_rank;
+    uint32_t rank;                         // PEERS: children on this rank go through anc_out directly
     uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
 };
@@ -346,8 +347,11 @@ template <bool PEERS>
 __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, uint32_t parent)
 {
     if (PEERS) {
+        // children of local parents are mostly local: only a remote one pays the load of its
+        // owner's pointer from the table in device memory
         const uint32_t r = fast_div(child, p.per_rank);
-        p.anc_peer[r][child - r * p.per_rank.d] = parent;
+        uint32_t *dst = r == p.rank ? p.anc_out : p.anc_peer[r];
+        dst[child - r * p.per_rank.d] = parent;
     } else {
         p.anc_out[child - p.out_lo] = parent;
     }
@@ -561,6 +565,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     if (peers) {
         p.anc_peer = (uint32_t *const *)peers->table_dev;
         p.per_rank = make_fast_div((uint32_t)peers->per_rank);
+        p.rank = (uint32_t)(j0 / peers->per_rank);          // j0 = this rank's first global slot
         p.out_lo = 0;
         p.out_hi = (uint32_t)N_global;
         scan_resample_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
