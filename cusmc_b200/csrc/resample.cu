@@ -358,8 +358,12 @@ __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, 
 }
 
 // Global CDF from the weight image and, fused in, the systematic offspring scatter: parent j owns
-// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  One thread per parent;
-// indices and offspring counts are 32-bit throughout (N_global < 2^32).
+// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  A thread owns kPar = 4
+// consecutive parents (two 128-bit loads of the tile-local CDF; the block prologue, the per-launch
+// constants and the neighbour exchange are paid once per four parents); indices and offspring counts
+// are 32-bit throughout (N_global < 2^32).
+constexpr int kPar = 4;
+static_assert(kTile % (kThreads * kPar) == 0, "a block of the resampling pass must lie inside one tile");
 template <bool PEERS>
 __global__ void __launch_bounds__(kThreads)
 scan_resample_kernel(const ScanArgs p)
@@ -367,12 +371,26 @@ scan_resample_kernel(const ScanArgs p)
     __shared__ uint32_t s_k[kThreads];
     __shared__ uint64_t s_T, s_r0;
     __shared__ double s_ng_over_t, s_r0_over_t;
-    const uint32_t i = blockIdx.x * kThreads + threadIdx.x;               // local parent
-    const bool active = i < p.N;
-    const uint32_t tile = (blockIdx.x * kThreads) / kTile;                // a block lies inside one tile
+    const uint32_t i0 = (blockIdx.x * kThreads + threadIdx.x) * kPar;    // first local parent of the thread
+    const uint32_t tile = (blockIdx.x * kThreads * kPar) / kTile;         // a block lies inside one tile
     const uint64_t base = p.tile_prefix[tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
-    const uint64_t C = base + (active ? __ldg(p.local + i) : 0ull);
-    if (p.cdf_out && active) p.cdf_out[i] = C;
+    uint64_t C[kPar];
+    if (i0 + kPar <= p.N) {              // the image is padded to whole tiles and 16-byte aligned
+        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(p.local + i0));
+        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(p.local + i0) + 1);
+        C[0] = base + a.x;
+        C[1] = base + a.y;
+        C[2] = base + b.x;
+        C[3] = base + b.y;
+    } else {
+#pragma unroll
+        for (int r = 0; r < kPar; ++r) C[r] = base + (i0 + r < p.N ? __ldg(p.local + i0 + r) : 0ull);
+    }
+    if (p.cdf_out) {
+#pragma unroll
+        for (int r = 0; r < kPar; ++r)
+            if (i0 + r < p.N) p.cdf_out[i0 + r] = C[r];
+    }
     if (!PEERS && !p.anc_out) return;
     // the per-launch constants (two fp64 divisions, 64-bit conversions) once per block, not per thread
     if (threadIdx.x == 0) {
@@ -390,38 +408,53 @@ scan_resample_kernel(const ScanArgs p)
     const uint64_t r0 = s_r0;
     const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
     const uint64_t Ng = p.N_global;
-    // the offspring count is a pure function of the CDF value; the left neighbour's count comes
-    // through shared memory, the block's first thread evaluates its own
-    const uint32_t k_here = active ? (uint32_t)offspring_below(C, Ng, T, r0, ng_over_t, r0_over_t) : 0u;
-    s_k[threadIdx.x] = k_here;
+    // the offspring count is a pure function of the CDF value: a zero weight repeats its left
+    // neighbour's; the thread's left neighbour's last count comes through shared memory, the block's
+    // first thread evaluates its own
+    uint32_t k[kPar];
+#pragma unroll
+    for (int r = 0; r < kPar; ++r) {
+        if (i0 + r >= p.N)
+            k[r] = 0;
+        else if (r > 0 && C[r] == C[r - 1])
+            k[r] = k[r - 1];
+        else
+            k[r] = (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t);
+    }
+    s_k[threadIdx.x] = k[kPar - 1];
     __syncthreads();
     uint32_t k_prev = 0;
     if (threadIdx.x > 0) {
         k_prev = s_k[threadIdx.x - 1];
-    } else if (active) {
-        const uint64_t Cprev = base + ((i % kTile) ? __ldg(p.local + i - 1) : 0ull);
+    } else if (i0 < p.N) {
+        const uint64_t Cprev = base + ((i0 % kTile) ? __ldg(p.local + i0 - 1) : 0ull);
         k_prev = (uint32_t)offspring_below(Cprev, Ng, T, r0, ng_over_t, r0_over_t);
     }
-    // threads past the end own the empty range and stay to help with large families
-    uint32_t a = active ? max(k_prev, p.out_lo) : 0u;
-    const uint32_t b = active ? min(k_here, p.out_hi) : 0u;
-    const uint32_t parent = p.j0 + i;
-    // small families: the owning thread writes them; large ones: the whole warp helps
-    const bool big = b > a && b - a > 8;
-    if (!big) {
-#pragma unroll 1
-        for (; a < b; ++a) put_ancestor<PEERS>(p, a, parent);
-    }
-    unsigned bigmask = __ballot_sync(0xffffffffu, big);
     const uint32_t lane = threadIdx.x & 31;
-    while (bigmask) {
-        const int src = __ffs(bigmask) - 1;
-        bigmask &= bigmask - 1;
-        const uint32_t sa = __shfl_sync(0xffffffffu, a, src);
-        const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
-        const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+#pragma unroll
+    for (int r = 0; r < kPar; ++r) {
+        const bool active = i0 + r < p.N;
+        // parents past the end own the empty range; their threads stay to help with large families
+        uint32_t a = active ? max(k_prev, p.out_lo) : 0u;
+        const uint32_t b = active ? min(k[r], p.out_hi) : 0u;
+        const uint32_t parent = p.j0 + i0 + r;
+        // small families: the owning thread writes them; large ones: the whole warp helps
+        const bool big = b > a && b - a > 8;
+        if (!big) {
 #pragma unroll 1
-        for (uint32_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, sp);
+            for (; a < b; ++a) put_ancestor<PEERS>(p, a, parent);
+        }
+        unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        while (bigmask) {
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const uint32_t sa = __shfl_sync(0xffffffffu, a, src);
+            const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
+            const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+#pragma unroll 1
+            for (uint32_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, sp);
+        }
+        if (active) k_prev = k[r];
     }
 }
 
@@ -561,7 +594,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.out_lo = (uint32_t)out_lo;
     p.out_hi = (uint32_t)(out_lo + out_n);
     p.u0 = u0;
-    const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
+    const unsigned grid = (unsigned)((N + kThreads * kPar - 1) / (kThreads * kPar));
     if (peers) {
         p.anc_peer = (uint32_t *const *)peers->table_dev;
         p.per_rank = make_fast_div((uint32_t)peers->per_rank);
