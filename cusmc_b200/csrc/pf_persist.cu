@@ -22,7 +22,7 @@
 // counters): a persistent run reproduces it bit for bit (tests/test_gpu_parity.py).
 // Same semantics as cusmc_filter_run (src/mcmc.cpp:239-309 of the reference) restricted to:
 // one GPU, systematic resampling, Normal noise, d == dy in {2, 4}, device-drawn noise, no history,
-// no per-step moments, N <= one tile per resident block.
+// N <= one tile per resident block.
 #include "filter_types.cuh"
 #include "pf_step_impl.cuh"
 #include "resample.cuh"
@@ -53,6 +53,7 @@ struct PersistArgs {
     unsigned long long *tile_sums;  // [2][gridDim.x]
     const double *obs;              // [T][D]: L_V^-1 y_t
     const double *u0;               // [T]: systematic offsets (entry t used by step t)
+    double *moments;                // [T][2 + D] or NULL: sum w, -, sum w x_k (summary)
     uint64_t seed;
     int64_t ld;
     uint32_t N;
@@ -146,7 +147,7 @@ __device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long 
 //               running sum plus one block scan.
 // The log-weights and the CDF cross between the two mappings, and between phases, through shared
 // memory (2 x 36 KB per block): neither is ever re-read from global memory.
-template <int D, bool DIAG, int P>
+template <int D, bool DIAG, int P, bool SUMMARY>
 __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                      const __grid_constant__ pfstep::StepOp<D, DIAG> op, const Epilogue ep, const PersistArgs a)
@@ -206,14 +207,18 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         }
     };
 
-    // weigh(t): fixed-point weights against the global max, tile-local CDF into shared memory, tile sum
+    // weigh(t): fixed-point weights against the global max, tile-local CDF into shared memory, tile sum;
+    // with the summary on, also the ESS sum and the weighted first moments of the step
     auto weigh = [&](int t) {
         const double wmax = __ldcg(&a.slots[t].lw_max);
-        unsigned long long c[kItems], run = 0;
+        constexpr bool summary = SUMMARY;
+        unsigned long long c[kItems], run = 0, s2 = 0;
 #pragma unroll
         for (int r = 0; r < kItems; ++r) {
-            run += cusmc_fixed_from_unit(cusmc_unit_from_log(s_lw[pad(kItems * (int)tid + r)], wmax), a.shift);
+            const double wn = cusmc_unit_from_log(s_lw[pad(kItems * (int)tid + r)], wmax);
+            run += cusmc_fixed_from_unit(wn, a.shift);
             c[r] = run;
+            if (summary) s2 += cusmc_fixed_from_unit(wn * wn, a.shift);
         }
         unsigned long long inc = run;
 #pragma unroll
@@ -234,6 +239,44 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
 #pragma unroll
         for (int r = 0; r < kItems; ++r) s_c[pad(kItems * (int)tid + r)] = before + c[r];
         if (tid == 0) a.tile_sums[(size_t)(t & 1) * gridDim.x + blockIdx.x] = tile_total;
+        if constexpr (!SUMMARY) return;
+        // ESS: integer sum of the squared weights (order-independent)
+        unsigned long long dummy = 0;
+        block_sum2(s2, dummy, s_u64);
+        if (tid == 0 && s2) atomicAdd((unsigned long long *)&a.slots[t].sum_q2, s2);
+        // weighted first moments, striped (coalesced reads of the state); the weight of particle j is
+        // the difference of neighbouring CDF entries -- exactly the fixed-point weight resampling uses
+        __syncthreads();
+        const double scale = cusmc_pow2i(-a.shift);
+        const double *xc = a.x[cur];
+        double acc[1 + D];
+#pragma unroll
+        for (int k = 0; k <= D; ++k) acc[k] = 0.0;
+#pragma unroll 2
+        for (int r = 0; r < kItems; ++r) {
+            const int j = r * kThreads + (int)tid;
+            if ((uint32_t)j < tile_n) {
+                const unsigned long long qj = s_c[pad(j)] - (j ? s_c[pad(j - 1)] : 0ull);
+                const double w = (double)qj * scale;
+                acc[0] += w;
+#pragma unroll
+                for (int k = 0; k < D; ++k) acc[1 + k] = fma(w, __ldcg(xc + (int64_t)k * a.ld + tile0 + j), acc[1 + k]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k <= D; ++k) {
+            double v = acc[k];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            __syncthreads();
+            if (lane == 0) s_dbl[warp] = v;
+            __syncthreads();
+            if (tid == 0) {
+                double tsum = 0.0;
+                for (int q = 0; q < kThreads / 32; ++q) tsum += s_dbl[q];
+                atomicAdd(a.moments + (size_t)t * (2 + D) + (k ? 1 + k : 0), tsum);
+            }
+        }
     };
 
     // ---- t = 0: x_0 = m0 + Q_c0 z, constant log-weight 0 (src/mcmc.cpp:63-85) -----------------
@@ -350,12 +393,12 @@ __global__ void persist_init_slots(StepSlot *slots, int T)
     }
 }
 
-template <int D, bool DIAG, int P>
+template <int D, bool DIAG, int P, bool SUMMARY>
 int launch_persistent(cusmc_filter *f, const PersistArgs &args, bool probe_only)
 {
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
-    auto kernel = pf_persistent_kernel<D, DIAG, P>;
+    auto kernel = pf_persistent_kernel<D, DIAG, P, SUMMARY>;
     constexpr size_t kSmem = 2 * sizeof(double) * (size_t)padded_words(P);     // log-weights + CDF of one tile
     const unsigned grid = (unsigned)((cfg.N + args.tile_n - 1) / args.tile_n);
     CUSMC_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
@@ -402,23 +445,30 @@ int pick_items(const cusmc_filter *f)
     return 0;
 }
 
-template <int D, bool DIAG>
+template <int D, bool DIAG, bool SUMMARY>
 int launch_persistent_p(cusmc_filter *f, const PersistArgs &args, int P, bool probe_only)
 {
     switch (P) {
-        case 2: return launch_persistent<D, DIAG, 2>(f, args, probe_only);
-        case 4: return launch_persistent<D, DIAG, 4>(f, args, probe_only);
-        case 6: return launch_persistent<D, DIAG, 6>(f, args, probe_only);
-        case 7: return launch_persistent<D, DIAG, 7>(f, args, probe_only);
-        case 8: return launch_persistent<D, DIAG, 8>(f, args, probe_only);
+        case 2: return launch_persistent<D, DIAG, 2, SUMMARY>(f, args, probe_only);
+        case 4: return launch_persistent<D, DIAG, 4, SUMMARY>(f, args, probe_only);
+        case 6: return launch_persistent<D, DIAG, 6, SUMMARY>(f, args, probe_only);
+        case 7: return launch_persistent<D, DIAG, 7, SUMMARY>(f, args, probe_only);
+        case 8: return launch_persistent<D, DIAG, 8, SUMMARY>(f, args, probe_only);
     }
     return cusmc_fail(f->ctx, CUSMC_ERR_UNSUPPORTED, "persistent run: too many particles for one tile per resident block");
 }
 
+template <int D, bool DIAG>
+int launch_persistent_s(cusmc_filter *f, const PersistArgs &args, int P, bool probe_only)
+{
+    return f->cfg.summary ? launch_persistent_p<D, DIAG, true>(f, args, P, probe_only)
+                          : launch_persistent_p<D, DIAG, false>(f, args, P, probe_only);
+}
+
 int launch_persistent_any(cusmc_filter *f, const PersistArgs &args, int d, bool diag, int P, bool probe_only)
 {
-    if (d == 2) return diag ? launch_persistent_p<2, true>(f, args, P, probe_only) : launch_persistent_p<2, false>(f, args, P, probe_only);
-    return diag ? launch_persistent_p<4, true>(f, args, P, probe_only) : launch_persistent_p<4, false>(f, args, P, probe_only);
+    if (d == 2) return diag ? launch_persistent_s<2, true>(f, args, P, probe_only) : launch_persistent_s<2, false>(f, args, P, probe_only);
+    return diag ? launch_persistent_s<4, true>(f, args, P, probe_only) : launch_persistent_s<4, false>(f, args, P, probe_only);
 }
 
 bool is_diag_cm(const double *A, int d)
@@ -442,7 +492,7 @@ bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_
     const cusmc_filter_config &cfg = f->cfg;
     if (cfg.persistent < 0 || f->world != 1) return false;
     if (cfg.resampler != CUSMC_RESAMPLE_SYSTEMATIC || cfg.kind != CUSMC_MVN) return false;
-    if (cfg.keep_history || cfg.summary) return false;
+    if (cfg.keep_history) return false;
     if (cfg.d != cfg.dy || (cfg.d != 2 && cfg.d != 4)) return false;
     if (cfg.T < 2) return false;
     if (draws && (draws->xi0_dev || draws->xi_dev || draws->chi_dev || draws->u_dev || draws->j_dev || draws->um_dev))
@@ -501,6 +551,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
     persist_init_slots<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
     CUSMC_LAUNCHED(ctx);
+    if (cfg.summary) CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
     a.x[0] = f->x[0];
     a.x[1] = f->x[1];
     a.lw = f->lw;
@@ -509,6 +560,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     a.tile_sums = sums;
     a.obs = obs;
     a.u0 = u0;
+    a.moments = cfg.summary ? f->moments : nullptr;
     a.seed = cfg.seed;
     a.ld = f->per;
     a.N = (uint32_t)cfg.N;

@@ -287,7 +287,7 @@ typedef struct cusmc_filter_config {
     /* cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (three grid
      * barriers per step instead of four launches; log-weights and the weight image stay in shared
      * memory) when the configuration allows it: one GPU, systematic resampling, Normal noise,
-     * d == dy in {2, 4}, device-drawn noise, no history, no summary, N small enough for one tile of
+     * d == dy in {2, 4}, device-drawn noise, no history, N small enough for one tile of
      * <= 4096 particles per resident block (1.2 M particles on a B200).  Results are bit-identical
      * to the four-launch step (28 vs 35 us per 10^6-particle step).  0 = automatic, -1 = never. */
     int persistent;

@@ -493,6 +493,23 @@ def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
     assert np.array_equal(wp, wf)
     assert np.array_equal(lp, lf)
     assert len(np.unique(ap)) > 10 and np.all(np.diff(ap.astype(np.int64)) >= 0)
+    # with the summary on: same states again, ESS from the same integer sums, means to rounding (the
+    # persistent kernel weighs with the fixed-point weights, the four-launch path with exp(lw - max))
+    summ = []
+    for persistent in (True, False):
+        pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=99, summary=True, persistent=persistent, **md)
+        l0 = ctx.launch_count
+        pf.run()
+        x, w, a = pf.state()
+        summ.append((x, a, pf.summary(), ctx.launch_count - l0))
+        pf.close()
+    (xs, as_, sp, n1), (_, _, sf, n2) = summ
+    assert n1 == 2 and n2 > 4 * (T - 1)
+    assert np.array_equal(xs, xp) and np.array_equal(as_, ap)
+    assert np.array_equal(sp["loglik"], sf["loglik"])
+    assert np.allclose(sp["ess"], sf["ess"], rtol=1e-12)
+    # fixed-point weights are truncated at 2^-shift of the largest: |delta mean| <~ N 2^-shift / sum(w)
+    assert np.allclose(sp["mean"], sf["mean"], rtol=1e-7, atol=1e-9)
 
 
 def kalman_means(Y, m0, C0, F, G, V, W):
