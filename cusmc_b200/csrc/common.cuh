@@ -149,6 +149,17 @@ __device__ __forceinline__ double double_from_ordered(unsigned long long o)
     return __longlong_as_double((long long)b);
 }
 
+// atomicMax on a double slot that starts at -inf: non-negative doubles order like signed ints,
+// negative ones like unsigned ints reversed.  NaN is ignored.
+__device__ __forceinline__ void atomic_max_double(double *addr, double v)
+{
+    if (v != v) return;
+    if (v >= 0.0)
+        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
+    else
+        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
+}
+
 // Warp-wide maximum of finite-or--inf doubles (callers map NaN / +inf to -inf first): two
 // REDUX.MAX on the halves of the order-preserving integer image instead of five rounds of
 // 64-bit shuffles + compares.  Every lane gets the result.

@@ -123,15 +123,6 @@ static int build_observation(cusmc_ctx *ctx, int kind, int want_log, int d, int 
     return CUSMC_OK;
 }
 
-static void whiten_observation(const std::vector<double> &Winv, int dy, const double *y, double *c)
-{
-    for (int k = 0; k < dy; ++k) {
-        double s = 0.0;
-        for (int i = 0; i <= k; ++i) s += Winv[(size_t)k * dy + i] * y[i];
-        c[k] = s;
-    }
-}
-
 // ---- extern "C": layout helpers -----------------------------------------------------------------
 extern "C" int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, double *soa_dev, int64_t N,
                                     int64_t ld, int d)
@@ -178,7 +169,7 @@ extern "C" int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_l
     Epilogue ep;
     CUSMC_CHECK(build_observation(ctx, kind, want_log, d, dy, F, V, nu, M, Winv, ep));
     double c[CUSMC_MAX_DIM];
-    whiten_observation(Winv, dy, y, c);
+    cusmc_whiten_observation(Winv, dy, y, c);
     StepArgs a{};
     a.x_new = x_new_dev;
     a.x_prev = x_prev_dev;
@@ -641,16 +632,18 @@ __global__ void init_slots_kernel(StepSlot *slots, int T)
     }
 }
 
-static uint64_t host_u0_bits(uint64_t seed, uint64_t step)
-{
-    const cusmc_u32x4 r = cusmc_rng(seed, 7 /* systematic offset */, step, 0, 0);
-    return ((uint64_t)r.v[0] << 32) | r.v[1];
-}
-
 // ---- the step, phase by phase ------------------------------------------------------------------
 // One GPU: cusmc_filter_run chains them.  Sharded: the binding (cusmc_b200/sharded.py) puts the
 // scalar exchanges between them -- MAX of slot[t].lw_max after propagate, the per-rank sums after
 // weigh, a barrier after resample (ancestors land in peers' memory).
+
+int cusmc_filter_init_slots(cusmc_filter *f)
+{
+    const int T = f->cfg.T;
+    init_slots_kernel<<<(T + 255) / 256, 256, 0, f->ctx->stream>>>(f->slots, T);
+    CUSMC_LAUNCHED(f->ctx);
+    return CUSMC_OK;
+}
 
 extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws)
 {
@@ -662,8 +655,7 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     f->draws = draws ? *draws : cusmc_filter_draws{};
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
-    init_slots_kernel<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
-    CUSMC_LAUNCHED(ctx);
+    CUSMC_CHECK(cusmc_filter_init_slots(f));
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, sizeof(uint64_t), st));   // the arrival counter
     // t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N
@@ -748,7 +740,7 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     StepSlot *prev = &f->slots[t - 1];
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
         const double u0 = dr.u0_host ? dr.u0_host[off]
-                                     : (double)(host_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+                                     : (double)(cusmc_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
         return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
                                  nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr);
     }
@@ -771,7 +763,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     const int64_t n = f->n;
     const size_t off = (size_t)(t - 1);
     double c[CUSMC_MAX_DIM];
-    whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
+    cusmc_whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
     StepArgs a{};
     a.x_new = f->x[f->cur ^ 1];
     a.x_prev = f->x[f->cur];

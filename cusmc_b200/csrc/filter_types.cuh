@@ -4,6 +4,8 @@
 
 #include "density.cuh"
 
+#include "../../include/cusmc_philox.h"
+
 #include <vector>
 
 struct StepSlot {            // one per time step, on the device (64 bytes = 8 words)
@@ -51,6 +53,36 @@ struct cusmc_filter {
     bool ran = false;
 };
 
+
+// ---- host helpers shared by filter.cu and pf_persist.cu --------------------------------------------
+// c = L_V^-1 y (Winv row-major lower triangular)
+inline void cusmc_whiten_observation(const std::vector<double> &Winv, int dy, const double *y, double *c)
+{
+    for (int k = 0; k < dy; ++k) {
+        double s = 0.0;
+        for (int i = 0; i <= k; ++i) s += Winv[(size_t)k * dy + i] * y[i];
+        c[k] = s;
+    }
+}
+
+inline bool cusmc_is_diag_colmajor(const double *A, int d)
+{
+    if (!A) return true;
+    for (int c = 0; c < d; ++c)
+        for (int r = 0; r < d; ++r)
+            if (r != c && A[(size_t)c * d + r] != 0.0) return false;
+    return true;
+}
+
+// The systematic offset of step t when the caller injects none: 64 Philox bits keyed by (seed, step).
+inline uint64_t cusmc_u0_bits(uint64_t seed, uint64_t step)
+{
+    const cusmc_u32x4 r = cusmc_rng(seed, 7 /* systematic offset */, step, 0, 0);
+    return ((uint64_t)r.v[0] << 32) | r.v[1];
+}
+
+// filter.cu: every StepSlot back to { -inf, 0, 0, ... } on the stream
+int cusmc_filter_init_slots(cusmc_filter *f);
 
 // pf_persist.cu: the whole run as ONE cooperative kernel when the configuration allows it
 // (returns CUSMC_ERR_UNSUPPORTED otherwise, without side effects).

@@ -61,15 +61,6 @@ struct PersistArgs {
     int T, shift;
 };
 
-__device__ __forceinline__ void atomic_max_double_p(double *addr, double v)
-{
-    if (v != v) return;
-    if (v >= 0.0)
-        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
-    else
-        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
-}
-
 // x = mu + G xp + Q z and the whitened residual norm, in pf_step_kernel's operation order.
 template <int D, bool DIAG>
 __device__ __forceinline__ void propagate_one(const pfstep::StepOp<D, DIAG> &op, const double (&c)[D], const double (&xp)[D],
@@ -203,7 +194,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         __syncthreads();
         if (tid < 32) {
             m = warp_max_double(tid < kThreads / 32 ? s_dbl[tid] : -INFINITY);
-            if (tid == 0) atomic_max_double_p(&a.slots[t].lw_max, m);
+            if (tid == 0) atomic_max_double(&a.slots[t].lw_max, m);
         }
     };
 
@@ -383,16 +374,6 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
     }
 }
 
-__global__ void persist_init_slots(StepSlot *slots, int T)
-{
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t < T) {
-        StepSlot s{};
-        s.lw_max = -INFINITY;
-        slots[t] = s;
-    }
-}
-
 template <int D, bool DIAG, int P, bool SUMMARY>
 int launch_persistent(cusmc_filter *f, const PersistArgs &args, bool probe_only)
 {
@@ -471,20 +452,6 @@ int launch_persistent_any(cusmc_filter *f, const PersistArgs &args, int d, bool 
     return diag ? launch_persistent_s<4, true>(f, args, P, probe_only) : launch_persistent_s<4, false>(f, args, P, probe_only);
 }
 
-bool is_diag_cm(const double *A, int d)
-{
-    for (int c = 0; c < d; ++c)
-        for (int r = 0; r < d; ++r)
-            if (r != c && A[(size_t)c * d + r] != 0.0) return false;
-    return true;
-}
-
-uint64_t u0_bits(uint64_t seed, uint64_t step)
-{
-    const cusmc_u32x4 r = cusmc_rng(seed, 7 /* systematic offset */, step, 0, 0);
-    return ((uint64_t)r.v[0] << 32) | r.v[1];
-}
-
 }  // namespace
 
 bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_draws *draws)
@@ -510,7 +477,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     const int P = pick_items(f);
     const uint32_t tile_n = pick_tile(f);
     const unsigned grid = (unsigned)((cfg.N + tile_n - 1) / tile_n);
-    bool diag = is_diag_cm(f->G.data(), d) && is_diag_cm(f->Qw.data(), d) && is_diag_cm(f->Qc0.data(), d);
+    bool diag = cusmc_is_diag_colmajor(f->G.data(), d) && cusmc_is_diag_colmajor(f->Qw.data(), d) && cusmc_is_diag_colmajor(f->Qc0.data(), d);
     for (int k = 0; k < d && diag; ++k)
         for (int j = 0; j < d; ++j)
             if (j != k && f->M[(size_t)k * d + j] != 0.0) diag = false;
@@ -535,22 +502,17 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     }
     std::vector<double> host(n_obs + n_u0, 0.0);
     for (int t = 0; t < T; ++t) {
-        for (int k = 0; k < d; ++k) {     // L_V^-1 y_t, as whiten_observation in filter.cu
-            double s = 0.0;
-            for (int i = 0; i <= k; ++i) s += f->Winv[(size_t)k * d + i] * f->Y[(size_t)t * d + i];
-            host[(size_t)t * d + k] = s;
-        }
+        cusmc_whiten_observation(f->Winv, d, f->Y.data() + (size_t)t * d, &host[(size_t)t * d]);
         if (t >= 1)
             host[n_obs + t] = (draws && draws->u0_host) ? draws->u0_host[t - 1]
-                                                        : (double)(u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+                                                        : (double)(cusmc_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
     }
     unsigned long long *sums = (unsigned long long *)f->persist;
     double *obs = (double *)(sums + n_sum), *u0 = obs + n_obs;
     // the host vector dies with this call: a synchronous copy (pageable memory) is what we want
     CUSMC_CUDA(ctx, cudaMemcpyAsync(obs, host.data(), 8 * host.size(), cudaMemcpyHostToDevice, st));
     CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
-    persist_init_slots<<<(T + 255) / 256, 256, 0, st>>>(f->slots, T);
-    CUSMC_LAUNCHED(ctx);
+    CUSMC_CHECK(cusmc_filter_init_slots(f));
     if (cfg.summary) CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
     a.x[0] = f->x[0];
     a.x[1] = f->x[1];

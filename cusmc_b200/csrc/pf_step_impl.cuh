@@ -43,15 +43,6 @@ struct StepOp {
     double mu[D];      // additive location (m0 at t = 0, otherwise 0)
 };
 
-__device__ __forceinline__ void atomic_max_double(double *addr, double v)
-{
-    if (v != v) return;
-    if (v >= 0.0)
-        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
-    else
-        atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));
-}
-
 // chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2): Marsaglia-Tsang with reproducible
 // log/exp (the reference's curand_gamma / curand_chi_square, src/mvt_dist.cu.cpp:20-61).
 static __device__ __noinline__ double chi_factor(uint64_t seed, uint64_t step, uint64_t index, int k, float nu)

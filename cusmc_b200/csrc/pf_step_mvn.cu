@@ -1,4 +1,5 @@
 // pf_step_mvn.cu -- Normal-noise instantiations of the step kernel + the dispatcher.
+#include "filter_types.cuh"
 #include "pf_step_impl.cuh"
 
 namespace pfstep {
@@ -9,15 +10,6 @@ int launch_mvn(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const Ste
 }
 }  // namespace pfstep
 
-static bool is_diag_colmajor(const double *A, int d)
-{
-    if (!A) return true;
-    for (int c = 0; c < d; ++c)
-        for (int r = 0; r < d; ++r)
-            if (r != c && A[(size_t)c * d + r] != 0.0) return false;
-    return true;
-}
-
 int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
                       const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
                       const StepArgs &a, bool philox)
@@ -27,7 +19,7 @@ int cusmc_launch_step(cusmc_ctx *ctx, int d, int dy, const double *G, const doub
         return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "dimension %d not in 1..%d", dm, CUSMC_MAX_DIM);
     if (a.n_out == 0) return CUSMC_OK;
     const bool exact = d == dy && d == cusmc_pad_dim(dm);
-    bool diag = exact && is_diag_colmajor(G, d) && is_diag_colmajor(Q, d);
+    bool diag = exact && cusmc_is_diag_colmajor(G, d) && cusmc_is_diag_colmajor(Q, d);
     if (diag && M)
         for (int k = 0; k < d && diag; ++k)
             for (int j = 0; j < d; ++j)

@@ -77,18 +77,6 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const 
 // ------------------------------------------------------------------------------------------
 // max and fixed-point sums
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void atomic_max_double(double *addr, double v)
-{
-    // slot must start at -inf.  Non-negative doubles order like signed ints, negative ones
-    // like unsigned ints reversed.
-    if (v != v) return;
-    if (v >= 0.0)
-        atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
-    else
-        atomicMin(reinterpret_cast<unsigned long long *>(addr),
-                  (unsigned long long)__double_as_longlong(v));
-}
-
 __global__ void fill_double_kernel(double *p, double v, int n)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
