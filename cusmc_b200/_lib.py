@@ -37,7 +37,7 @@ class FilterConfig(C.Structure):
         ("N", i64), ("d", ci), ("dy", ci), ("T", ci), ("kind", ci), ("resampler", ci), ("B", ci),
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
-        ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci),
+        ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci), ("ess_threshold", dbl),
     ]
 
 
@@ -97,6 +97,7 @@ PROTOTYPES = {
     "cusmc_filter_exchange_status": (ci, [vp, C.POINTER(u64)]),
     "cusmc_filter_get_summary": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_get_history": (ci, [vp, vp, vp, vp]),
+    "cusmc_filter_get_resampled": (ci, [vp, vp]),
     "cusmc_filter_last_ms": (dbl, [vp]),
     "cusmc_filter_state_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "cusmc_run": (ci, [vp, C.POINTER(FilterConfig), vp, vp]),

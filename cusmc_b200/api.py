@@ -386,7 +386,7 @@ class ParticleFilter:
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
                  df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                 persistent=True):
+                 persistent=True, ess_threshold=0.0):
         self.ctx = ctx
         Y = np.asarray(Y, dtype=np.float64)
         F = np.asarray(F, dtype=np.float64)
@@ -411,6 +411,7 @@ class ParticleFilter:
         cfg.summary = int(summary)
         cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
         cfg.persistent = 0 if persistent else -1      # one cooperative kernel per run when eligible
+        cfg.ess_threshold = float(ess_threshold)      # 0: resample every step (the reference's behaviour)
         self.keep_history = bool(keep_history)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
@@ -453,6 +454,12 @@ class ParticleFilter:
         ll = np.empty(self.T)
         self.ctx._check(self.ctx.lib.cusmc_filter_get_summary(self.h, _hp(mean), _hp(ess), _hp(ll)))
         return dict(mean=mean, ess=ess, loglik=ll)
+
+    def resampled(self):
+        """(T,) int array: 1 where the step drew new ancestors (adaptive resampling), else 0."""
+        r = np.zeros(self.T, dtype=np.int32)
+        self.ctx._check(self.ctx.lib.cusmc_filter_get_resampled(self.h, _hp(r)))
+        return r
 
     def state(self):
         """Current device-resident state copied to the host: x (d, n) SoA, weights (n,) (log-weights

@@ -462,6 +462,9 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->kind == CUSMC_MVT, "unknown distribution");
     CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 2, "unknown resampler");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
+    CUSMC_REQUIRE(ctx, cfg->ess_threshold >= 0.0 && cfg->ess_threshold <= 1.0, "ess_threshold must lie in [0, 1]");
+    CUSMC_REQUIRE(ctx, cfg->ess_threshold == 0.0 || cfg->resampler == CUSMC_RESAMPLE_SYSTEMATIC,
+                  "adaptive resampling needs the systematic resampler");
     const int world = cfg->world <= 1 ? 1 : cfg->world;
     CUSMC_REQUIRE(ctx, world <= CUSMC_MAX_PEERS, "world exceeds CUSMC_MAX_PEERS");
     CUSMC_REQUIRE(ctx, world == 1 || (cfg->rank >= 0 && cfg->rank < world), "rank outside 0..world-1");
@@ -627,7 +630,8 @@ __global__ void init_slots_kernel(StepSlot *slots, int T)
         StepSlot s;
         s.lw_max = -INFINITY;
         s.sum_q = s.sum_q2 = s.n_pos = s.cdf_offset = 0;
-        s.reserved[0] = s.reserved[1] = s.reserved[2] = 0.0;
+        s.resampled = t > 0 ? 1 : 0;
+        s.reserved[0] = s.reserved[1] = 0.0;
         slots[t] = s;
     }
 }
@@ -701,7 +705,7 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
     const MailArgs mail = filter_mail(f);
     if (f->is_log)
         CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
-                                             f->scan_state, cfg.summary != 0, &mail, t));
+                                             f->scan_state, cfg.summary != 0 || cfg.ess_threshold > 0.0, &mail, t));
     if (cfg.summary && n > 0) {
         const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
         moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
@@ -741,8 +745,11 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
         const double u0 = dr.u0_host ? dr.u0_host[off]
                                      : (double)(cusmc_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+        const bool adaptive = cfg.ess_threshold > 0.0;
         return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
-                                 nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr);
+                                 nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr,
+                                 adaptive ? &prev->sum_q2 : nullptr, adaptive ? &f->slots[t].resampled : nullptr,
+                                 cfg.ess_threshold * (double)N * std::ldexp(1.0, f->shift));
     }
     CUSMC_CHECK(cusmc_launch_scan(ctx, n, N, &prev->sum_q, nullptr, f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0,
                                   nullptr));
@@ -772,6 +779,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     a.chi = dr.chi_dev ? dr.chi_dev + off * n * d : nullptr;
     a.lw = f->lw;
     a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
+    a.resampled = cfg.ess_threshold > 0.0 ? (const unsigned long long *)&f->slots[t].resampled : nullptr;
     a.n_out = n;
     a.ld_new = a.ld_prev = f->per;
     a.ld_noise = n;
@@ -931,6 +939,19 @@ extern "C" int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *e
             if (loglik) loglik[t] = f->cfg.summary ? std::log(m[0] / (double)f->cfg.N) : NAN;
         }
     }
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_get_resampled(cusmc_filter *f, int *resampled)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, f->ran && resampled, "filter has not run");
+    const int T = f->cfg.T;
+    std::vector<StepSlot> slots(T);
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CUSMC_CUDA(ctx, cudaMemcpy(slots.data(), f->slots, sizeof(StepSlot) * T, cudaMemcpyDeviceToHost));
+    for (int t = 0; t < T; ++t) resampled[t] = (int)slots[t].resampled;
     return CUSMC_OK;
 }
 

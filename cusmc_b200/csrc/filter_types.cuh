@@ -12,7 +12,8 @@ struct StepSlot {            // one per time step, on the device (64 bytes = 8 w
     double lw_max;           // [0] max log-weight (log modes), -inf initialised
     uint64_t sum_q, sum_q2, n_pos;   // [1..3] fixed-point sums (weigh_kernel); global after the exchange
     uint64_t cdf_offset;     // [4] fixed-point mass held by lower-ranked shards (0 on one GPU)
-    double reserved[3];
+    uint64_t resampled;      // [5] 1 if this step drew new ancestors (adaptive resampling), else 0
+    double reserved[2];
 };
 
 struct cusmc_filter {

@@ -459,7 +459,7 @@ bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_
     const cusmc_filter_config &cfg = f->cfg;
     if (cfg.persistent < 0 || f->world != 1) return false;
     if (cfg.resampler != CUSMC_RESAMPLE_SYSTEMATIC || cfg.kind != CUSMC_MVN) return false;
-    if (cfg.keep_history) return false;
+    if (cfg.keep_history || cfg.ess_threshold > 0.0) return false;
     if (cfg.d != cfg.dy || (cfg.d != 2 && cfg.d != 4)) return false;
     if (cfg.T < 2) return false;
     if (draws && (draws->xi0_dev || draws->xi_dev || draws->chi_dev || draws->u_dev || draws->j_dev || draws->um_dev))

@@ -165,6 +165,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
                 q = fma(zk, zk, q);
             }
             lw = density_epilogue(ep, q);
+            if (a.resampled && *a.resampled == 0) lw = *dst_lw + lw;   // no resampling: weights accumulate
         }
         st_stream(dst_lw, lw);
     }

@@ -327,6 +327,11 @@ struct ScanArgs {
     uint32_t rank;                         // PEERS: children on this rank go through anc_out directly
     uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
+    // adaptive resampling: resample only if sum_q^2 < ess_bound * sum_q2 (ess_bound = threshold * N *
+    // 2^shift; 0 = always).  *resampled_out receives the decision (block 0).
+    const unsigned long long *sum_q2;
+    unsigned long long *resampled_out;
+    double ess_bound;
 };
 
 // PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
@@ -359,6 +364,7 @@ scan_resample_kernel(const ScanArgs p)
     __shared__ uint32_t s_k[kThreads];
     __shared__ uint64_t s_T, s_r0;
     __shared__ double s_ng_over_t, s_r0_over_t;
+    __shared__ int s_resample;
     const uint32_t i0 = (blockIdx.x * kThreads + threadIdx.x) * kPar;    // first local parent of the thread
     const uint32_t tile = (blockIdx.x * kThreads * kPar) / kTile;         // a block lies inside one tile
     const uint64_t base = p.tile_prefix[tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
@@ -389,10 +395,21 @@ scan_resample_kernel(const ScanArgs p)
         s_r0 = rr;
         s_ng_over_t = (double)p.N_global / (double)Tt;
         s_r0_over_t = (double)rr / (double)Tt;
+        // ESS = sum_q^2 / (sum_q2 2^shift) < threshold N  <=>  sum_q^2 < ess_bound sum_q2
+        int go = 1;
+        if (p.ess_bound > 0.0) go = (double)Tt * (double)Tt < p.ess_bound * (double)*p.sum_q2;
+        s_resample = go;
+        if (blockIdx.x == 0 && p.resampled_out) *p.resampled_out = (unsigned long long)go;
     }
     __syncthreads();
     const uint64_t T = s_T;
     if (T == 0) return;                               // degenerate: the host reports it
+    if (!s_resample) {                                // keep every particle: a_i = i
+#pragma unroll
+        for (int r = 0; r < kPar; ++r)
+            if (i0 + r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + r, p.j0 + i0 + r);
+        return;
+    }
     const uint64_t r0 = s_r0;
     const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
     const uint64_t Ng = p.N_global;
@@ -564,7 +581,8 @@ size_t cusmc_scan_state_bytes(int64_t N)
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
-                      int64_t out_n, double u0, const CusmcPeers *peers)
+                      int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev,
+                      uint64_t *resampled_dev, double ess_bound)
 {
     if (N == 0) return CUSMC_OK;
     if (N_global > 0xFFFFFFFFll || out_lo < 0 || out_lo + out_n > N_global)
@@ -582,6 +600,9 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.out_lo = (uint32_t)out_lo;
     p.out_hi = (uint32_t)(out_lo + out_n);
     p.u0 = u0;
+    p.sum_q2 = (const unsigned long long *)sum_q2_dev;
+    p.resampled_out = (unsigned long long *)resampled_dev;
+    p.ess_bound = sum_q2_dev ? ess_bound : 0.0;
     const unsigned grid = (unsigned)((N + kThreads * kPar - 1) / (kThreads * kPar));
     if (peers) {
         p.anc_peer = (uint32_t *const *)peers->table_dev;

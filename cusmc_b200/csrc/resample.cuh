@@ -18,7 +18,8 @@ size_t cusmc_scan_state_bytes(int64_t N);
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
-                      int64_t out_n, double u0, const CusmcPeers *peers);
+                      int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev = nullptr,
+                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0);
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
                              int64_t n_out, int64_t j0, uint32_t *a);

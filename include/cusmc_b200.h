@@ -291,6 +291,13 @@ typedef struct cusmc_filter_config {
      * <= 4096 particles per resident block (1.2 M particles on a B200).  Results are bit-identical
      * to the four-launch step (28 vs 35 us per 10^6-particle step).  0 = automatic, -1 = never. */
     int persistent;
+    /* Adaptive resampling (systematic resampler only): 0 (default) = resample at every step, as the
+     * reference does (src/mcmc.cpp:295); in (0, 1] = resample at step t only when the effective
+     * sample size of step t - 1 is below ess_threshold * N.  A step that does not resample keeps
+     * every particle's own ancestor (a_i = i) and ACCUMULATES the log-weights,
+     * lw_t[i] = lw_{t-1}[i] + log p(y_t | x_t[i]).  The decision is taken on the device from the
+     * integer weight sums, so it is identical on every rank of a sharded run and on the CPU oracle. */
+    double ess_threshold;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):
@@ -323,7 +330,7 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
  *                                  state buffer (peer loads).  Ancestors are GLOBAL indices and the
  *                                  noise is keyed by the global slot, so a sharded run reproduces the
  *                                  single-GPU run bit for bit.
- * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset; 3 spare }.
+ * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset, resampled; 2 spare }.
  * Injected draws of a sharded run are this rank's shard (leading dimension = its particle count).
  */
 int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws);
@@ -354,6 +361,8 @@ int cusmc_filter_exchange_status(cusmc_filter *f, uint64_t *status);
 /* Per-step outputs copied to the host (any pointer may be NULL):
  * mean [T][d] weighted posterior mean, ess [T], loglik [T] (log of the mean weight). */
 int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *ess, double *loglik);
+/* resampled[t] = 1 if step t drew new ancestors (always 1 without ess_threshold; resampled[0] = 0). */
+int cusmc_filter_get_resampled(cusmc_filter *f, int *resampled);
 /* History (needs keep_history): x_aos [T][N][d], w [T][N] (densities or normalised
  * weights), a [T][N]. */
 int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a);

@@ -1025,9 +1025,11 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                    const double *G, const double *V, const double *Q_w, float nu, uint64_t seed,
                    const double *xi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
-                   double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik)
+                   double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
+                   double ess_threshold, int *resampled)
 {
     size_t Nd = (size_t)N * d;
+    double *w_old = (double *)malloc(sizeof(double) * N);
     int is_log = resampler != 0;
     double *xa = (double *)malloc(sizeof(double) * Nd), *xb = (double *)malloc(sizeof(double) * Nd);
     double *w = (double *)malloc(sizeof(double) * N), *noise = (double *)malloc(sizeof(double) * Nd);
@@ -1050,6 +1052,7 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
         for (int64_t i = 0; i < N; ++i) w[i] = is_log ? 0.0 : 1.0 / (double)N;
     }
     for (int t = 0; t < T; ++t) {
+        int do_resample = t > 0;
         if (t > 0) {
             size_t off = (size_t)(t - 1);
             if (resampler == 0) {
@@ -1065,15 +1068,23 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                 /* weights of step t-1: max shift, fixed point, integer CDF */
                 double m = -INFINITY;
                 for (int64_t i = 0; i < N; ++i) if (w[i] > m && w[i] < INFINITY) m = w[i];
-                uint64_t run = 0;
+                uint64_t run = 0, run2 = 0;
                 for (int64_t i = 0; i < N; ++i) {
                     double wn = (w[i] <= m) ? orc_det_exp(w[i] - m) : 0.0;
                     run += fixed_from_unit(wn, shift);
+                    run2 += fixed_from_unit(wn * wn, shift);
                     C[i] = run;
                 }
                 uint64_t Tm = run;
                 if (Tm == 0) { rc = -1; goto done; }
-                if (resampler == 1) {
+                /* adaptive resampling: ESS = sum_q^2 / (sum_q2 2^shift) < threshold N, evaluated as
+                 * the kernels do (scan_resample_kernel) */
+                do_resample = 1;
+                if (ess_threshold > 0.0)
+                    do_resample = (double)Tm * (double)Tm < (ess_threshold * (double)N * scale2) * (double)run2;
+                if (!do_resample) {
+                    for (int64_t i = 0; i < N; ++i) a[i] = (uint32_t)i;
+                } else if (resampler == 1) {
                     double uu = u0 ? u0[off] : 0.0;
                     if (!u0) {
                         uint32_t r[4];
@@ -1106,10 +1117,14 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                 for (int i = 0; i <= k; ++i) s += Winv[(size_t)k * dy + i] * Y[(size_t)t * dy + i];
                 c[k] = s;
             }
+            if (!do_resample) memcpy(w_old, w, sizeof(double) * N);
             orc_step_det(dist, is_log, xb, w, xa, a, G, Q_w, NULL, M, c, lognorm, nu, zt,
                          chi ? chi + off * Nd : NULL, N, d, dy);
+            if (!do_resample)            /* no resampling: the log-weights accumulate */
+                for (int64_t i = 0; i < N; ++i) w[i] = w_old[i] + w[i];
             double *tmp = xa; xa = xb; xb = tmp;
         }
+        if (resampled) resampled[t] = do_resample;
         if (x_hist) memcpy(x_hist + (size_t)t * Nd, xa, sizeof(double) * Nd);
         if (w_hist) memcpy(w_hist + (size_t)t * N, w, sizeof(double) * N);
         if (a_hist && t > 0) memcpy(a_hist + (size_t)t * N, a, sizeof(uint32_t) * N);
@@ -1127,6 +1142,7 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
         }
     }
 done:
+    free(w_old);
     free(xa); free(xb); free(w); free(noise); free(a); free(C); free(M); free(Winv); free(c); free(ub); free(jb);
     return rc;
 }

@@ -205,7 +205,8 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                    const double *G, const double *V, const double *Q_w, float nu, uint64_t seed,
                    const double *xi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
-                   double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik);
+                   double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
+                   double ess_threshold, int *resampled);
 
 /* Threads the batched functions will use (OpenMP), for bench reporting. */
 int orc_num_threads(void);

@@ -125,7 +125,7 @@ class Oracle:
         L.orc_filter_det.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_float, C.c_uint64,
                                      _dp, _dp, _dp, _dp, _u32p, _dp, _dp,
-                                     _dp, _dp, _u32p, _dp, _dp]
+                                     _dp, _dp, _u32p, _dp, _dp, C.c_double, C.POINTER(C.c_int)]
 
     # ---- dense helpers ----------------------------------------------------
     def determinant(self, A):
@@ -383,7 +383,7 @@ class Oracle:
         return u, j
 
     def filter_det(self, dist, resampler, Y, m0, Q_c0, F, G, V, Q_w, N, nu=0.0, seed=0, B=10,
-                   xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None):
+                   xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, ess_threshold=0.0):
         """Production-order filter.  resampler: 'metropolis' | 'systematic' | 'multinomial'."""
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
@@ -397,14 +397,16 @@ class Oracle:
         ah[0] = np.arange(N)
         ess = np.full(T, np.nan)
         ll = np.full(T, np.nan)
+        res = np.zeros(T, dtype=np.int32)
         rc = self.lib.orc_filter_det(
             0 if dist == "mvn" else 1, rs, N, d, dy, T, B, _p(colmajor(Y)), _p(f64(m0)),
             _p(colmajor(Q_c0)), _p(colmajor(F)), _p(colmajor(G)), _p(colmajor(V)), _p(colmajor(Q_w)),
             float(nu), int(seed), _p(opt(xi0)), _p(opt(xi)), _p(opt(chi)), _p(opt(u)), _p(j_, _u32p),
-            _p(opt(u0)), _p(opt(um)), _p(xh), _p(wh), _p(ah, _u32p), _p(ess), _p(ll))
+            _p(opt(u0)), _p(opt(um)), _p(xh), _p(wh), _p(ah, _u32p), _p(ess), _p(ll),
+            float(ess_threshold), res.ctypes.data_as(C.POINTER(C.c_int)))
         if rc:
             raise RuntimeError("orc_filter_det failed: %d" % rc)
-        return dict(x=xh, w=wh, a=ah, ess=ess, loglik=ll)
+        return dict(x=xh, w=wh, a=ah, ess=ess, loglik=ll, resampled=res)
 
     def num_threads(self):
         return self.lib.orc_num_threads()

@@ -99,7 +99,8 @@ def gpu_filter_worker(rank, world, port, backend, devices, cfg, out_dir):
     Y = np.random.default_rng(cfg["yseed"]).standard_normal((d, T))
     pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, 0.5 * I, 0.3 * I,
                                           resampler=cfg["resampler"], distribution=cfg.get("dist", "mvn"),
-                                          df=cfg.get("df", 0.0), seed=cfg["seed"], summary=True)
+                                          df=cfg.get("df", 0.0), seed=cfg["seed"], summary=True,
+                                          ess_threshold=cfg.get("ess_threshold", 0.0))
     pf.run(exchange=cfg.get("exchange", "p2p"))
     x, w, a = pf.local_state()
     s = pf.summary()

@@ -512,6 +512,34 @@ def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
     assert np.allclose(sp["mean"], sf["mean"], rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("d,thr", [(2, 0.5), (8, 0.05)])
+def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
+    """ess_threshold: resample only when ESS < threshold N, otherwise keep a_i = i and accumulate the
+    log-weights.  The decision comes from the integer weight sums, so the oracle takes the same one:
+    ancestors, states and (cumulative) log-weights agree bit for bit, and both kinds of step occur."""
+    rng = np.random.default_rng(77 + d)
+    N, T = 4000, 30
+    md = _model(d)
+    Y = rng.standard_normal((d, T)) * 0.5
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=5, keep_history=True, ess_threshold=thr, **md)
+    h, s, res = pf.run().history(), pf.summary(), pf.resampled()
+    pf.close()
+    ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, seed=5, ess_threshold=thr)
+    assert np.array_equal(res, ref["resampled"])
+    assert 0 < res[1:].sum() < T - 1                              # both kinds of step happened
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+    assert np.array_equal(h["w"], ref["w"])
+    assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+    kept = np.where(res[1:] == 0)[0] + 1
+    assert all(np.array_equal(h["a"][t], np.arange(N)) for t in kept)
+    # a resampling step is triggered exactly by the ESS of the step before
+    assert np.array_equal(res[1:], (s["ess"][:-1] < thr * N).astype(np.int32))
+    with pytest.raises(Exception):
+        ctx.filter(N=N, Y=Y, resampler="multinomial", ess_threshold=thr, **md)
+
+
 def kalman_means(Y, m0, C0, F, G, V, W):
     m, P = m0.copy(), C0.copy()
     out = [m.copy()]

@@ -43,7 +43,7 @@ def run_single(ctx, cfg):
     Y = np.random.default_rng(cfg["yseed"]).standard_normal((d, T))
     pf = ctx.filter(N=N, Y=Y, m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=0.5 * I, W=0.3 * I,
                     resampler=cfg["resampler"], distribution=cfg.get("dist", "mvn"), df=cfg.get("df", 0.0),
-                    seed=cfg["seed"], keep_history=True, summary=True)
+                    seed=cfg["seed"], keep_history=True, summary=True, ess_threshold=cfg.get("ess_threshold", 0.0))
     h, s = pf.run().history(), pf.summary()
     pf.close()
     return h, s
@@ -75,6 +75,20 @@ def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d
             assert np.allclose(p["ess"], s["ess"], rtol=1e-12)
             assert np.allclose(p["loglik"], s["loglik"], rtol=1e-12, atol=1e-12)
         assert np.allclose(p["mean"], s["mean"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.timeout(600)
+def test_sharded_adaptive_resampling(ctx, tmp_path):
+    """The resample / keep decision comes from the GLOBAL integer sums: every rank takes the same one
+    and the sharded run still equals the single-GPU run bit for bit."""
+    cfg = dict(d=2, T=25, N=5000, resampler="systematic", seed=12, yseed=33, ess_threshold=0.5)
+    h, _ = run_single(ctx, cfg)
+    parts = run_sharded(tmp_path, 2, cfg)
+    assert np.array_equal(np.concatenate([p["a"] for p in parts]), h["a"][-1])
+    assert np.array_equal(np.concatenate([p["x"] for p in parts], axis=1).T, h["x"][-1])
+    assert np.array_equal(np.concatenate([p["w"] for p in parts]), h["w"][-1])
+    kept = [t for t in range(1, cfg["T"]) if np.array_equal(h["a"][t], np.arange(cfg["N"]))]
+    assert 0 < len(kept) < cfg["T"] - 1
 
 
 @pytest.mark.timeout(600)

@@ -233,6 +233,28 @@ def test_filter_tracks_kalman(orc, resampler):
         assert np.all(r["ess"][8:] > N / 10)
 
 
+def test_adaptive_resampling_oracle(orc):
+    """ess_threshold in the oracle's filter: steps resample exactly when the previous ESS is below the
+    bound, skipped steps keep a_i = i and accumulate the log-weights, and the filter still tracks the
+    Kalman mean."""
+    Y = np.loadtxt(os.path.join(os.path.dirname(__file__), "golden", "y_t.csv"), delimiter=",", skiprows=1).T[:, :40]
+    I2 = np.eye(2)
+    N, thr = 20000, 0.5
+    r = orc.filter_det("mvn", "systematic", Y, np.zeros(2), I2, I2, I2, 0.1 * I2, np.sqrt(0.1) * I2, N, seed=11,
+                       ess_threshold=thr)
+    res = r["resampled"]
+    assert res[0] == 0 and 0 < res[1:].sum() < len(res) - 1
+    assert np.array_equal(res[1:], (r["ess"][:-1] < thr * N).astype(np.int32))
+    for t in np.where(res[1:] == 0)[0] + 1:
+        assert np.array_equal(r["a"][t], np.arange(N))
+    w = np.exp(r["w"] - r["w"].max(axis=1, keepdims=True))
+    mean = (w[:, :, None] * r["x"]).sum(1) / w.sum(1)[:, None]
+    km, _ = kalman_means(Y, np.zeros(2), I2, I2, I2, 0.1 * I2, 0.1 * I2)
+    assert np.max(np.abs(mean[8:] - km[8:])) < 0.05
+    always = orc.filter_det("mvn", "systematic", Y, np.zeros(2), I2, I2, I2, 0.1 * I2, np.sqrt(0.1) * I2, N, seed=11)
+    assert np.all(always["resampled"][1:] == 1)
+
+
 def test_filter_reference_loop_equals_det_loop(orc):
     """orc_filter_metropolis (reference-form arithmetic) and orc_filter_det (production order) are two
     statements of src/mcmc.cpp:292-308: same ancestors, states equal to rounding."""
