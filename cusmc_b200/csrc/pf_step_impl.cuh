@@ -43,35 +43,52 @@ struct StepOp {
     double mu[D];      // additive location (m0 at t = 0, otherwise 0)
 };
 
-// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2): Marsaglia-Tsang with reproducible
-// log/exp (the reference's curand_gamma / curand_chi_square, src/mvt_dist.cu.cpp:20-61).
-static __device__ __noinline__ double chi_factor(uint64_t seed, uint64_t step, uint64_t index, int k, float nu)
+// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2)  (the reference's curand_gamma /
+// curand_chi_square, src/mvt_dist.cu.cpp:20-61): Marsaglia-Tsang in SINGLE precision, like the
+// normals (the draws carry 24 significant bits; every operation on the state stays fp64), built from
+// the reproducible fp32 functions of cusmc_detmath.h.  One Philox block serves TWO components: its
+// Box-Muller pair gives their two normals, its other two words their two uniforms; the squeeze
+// u < 1 - 0.0331 z^4 accepts ~92 % of the proposals without a logarithm and a proposal is rejected
+// ~4 % of the time (the component then redraws from block `attempt + 1`).  A first version drew every
+// component from two blocks with fp64 Box-Muller, log and sincos: 6.5x the cost of the whole Normal
+// step at d = 8.
+static __device__ __noinline__ void chi_pair(uint64_t seed, uint64_t step, uint64_t index, int kpair, float nu,
+                                             float *chi0, float *chi1)
 {
-    const double a0 = 0.5 * (double)nu;
-    const double a = a0 < 1.0 ? a0 + 1.0 : a0;
-    const double dd = a - 1.0 / 3.0;
-    const double cc = 1.0 / sqrt(9.0 * dd);
-    double g = dd;
-    for (uint32_t attempt = 0; attempt < 64; ++attempt) {
-        const uint32_t sub = ((uint32_t)k << 8) | attempt;
-        double z0, z1;
-        cusmc_normal_pair(cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub), &z0, &z1);
-        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, sub | 0x800000u);
-        const double t = fma(cc, z0, 1.0);
-        const double v = t * t * t;
-        if (v > 0.0) {
-            const double lu = cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
-            if (lu < fma(0.5 * z0, z0, dd) - dd * v + dd * cusmc_det_log(v)) {
-                g = dd * v;
-                if (a0 < 1.0) {
-                    const double lb = cusmc_det_log(cusmc_u01_open0(r.v[2], r.v[3]));
-                    g = g * cusmc_det_exp(lb / a0);
-                }
-                break;
+    const float a0 = 0.5f * nu;
+    const float a = a0 < 1.0f ? a0 + 1.0f : a0;
+    const float dd = a - 0.333333343f;
+    const float cc = 1.0f / sqrtf(9.0f * dd);
+    float g[2] = {dd, dd};
+    bool done[2] = {false, false};
+    for (uint32_t attempt = 0; attempt < 32 && !(done[0] && done[1]); ++attempt) {
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, ((uint32_t)kpair << 8) | attempt);
+        float z[2];
+        cusmc_box_muller_f32(r.v[0], r.v[1], &z[0], &z[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (done[e]) continue;
+            const float t = fmaf(cc, z[e], 1.0f);
+            if (!(t > 0.0f)) continue;
+            const float v = t * t * t;
+            const float u = fmaf((float)(r.v[2 + e] >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);  // (0, 1)
+            const float z2 = z[e] * z[e];
+            if (u < fmaf(-0.0331f * z2, z2, 1.0f) ||
+                cusmc_det_logf(u) < fmaf(0.5f, z2, dd * (1.0f - v + cusmc_det_logf(v)))) {
+                g[e] = dd * v;
+                done[e] = true;
             }
         }
     }
-    return sqrt((double)nu / (2.0 * g));
+    if (a0 < 1.0f) {
+        // shape < 1 (nu < 2): Gamma(a0) = Gamma(a0 + 1) U^(1/a0), from a block of its own
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, ((uint32_t)kpair << 8) | 0x800000u);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            g[e] = (float)((double)g[e] * cusmc_det_exp(cusmc_det_log(cusmc_u01_open0(r.v[2 * e], r.v[2 * e + 1])) / (double)a0));
+    }
+    *chi0 = sqrtf(nu / (2.0f * g[0]));
+    *chi1 = sqrtf(nu / (2.0f * g[1]));
 }
 
 constexpr int min_blocks(int D, bool diag) { return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? 3 : 4)); }
@@ -129,6 +146,16 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
 #pragma unroll
             for (int j = 0; j < D; ++j) z[j] = (EXACT || j < d) ? ld_stream(src + (int64_t)j * a.ld_noise) : 0.0;
         }
+        double chi[MVT ? D : 1];
+        if (MVT && !a.chi) {
+#pragma unroll
+            for (int kp = 0; kp < (D + 1) / 2; ++kp) {
+                float c0 = 1.0f, c1 = 1.0f;
+                if (EXACT || 2 * kp < d) chi_pair(a.seed, a.step, (uint64_t)(a.i0 + i), kp, a.nu, &c0, &c1);
+                chi[MVT ? 2 * kp : 0] = (double)c0;
+                if (2 * kp + 1 < D) chi[MVT ? 2 * kp + 1 : 0] = (double)c1;
+            }
+        }
 #pragma unroll
         for (int k = 0; k < D; ++k) {
             double g = op.mu[k], s = 0.0;
@@ -141,11 +168,8 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
 #pragma unroll
                 for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
             }
-            if (MVT && (EXACT || k < d)) {
-                const double chi = a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i)
-                                         : chi_factor(a.seed, a.step, (uint64_t)(a.i0 + i), k, a.nu);
-                s = chi * s;
-            }
+            if (MVT && (EXACT || k < d))
+                s = (a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i) : chi[MVT ? k : 0]) * s;
             xn[k] = s + g;
             if (EXACT || k < d) st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
         }

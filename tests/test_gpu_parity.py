@@ -224,6 +224,16 @@ def test_sample_wrappers(ctx, orc, d):
     got = ctx.mvt_sample(np.zeros((20000, 1)), None, np.zeros((1, 1)), np.ones((1, 1)), 6.0, xi=np.ones((20000, 1)), seed=5)
     inv = 1.0 / got[:, 0] ** 2
     assert abs(inv.mean() - 1.0) < 0.02 and abs(inv.var() - 2.0 / 6.0) < 0.03
+    # ... and the whole law, for a shape above and one below 1 (nu = 1.5 takes the U^(1/a) boost) and
+    # for both components of a pair: Kolmogorov-Smirnov against chi^2_nu
+    from scipy import stats
+    for nu in (6.0, 1.5, 30.0):
+        n = 100000
+        got = ctx.mvt_sample(np.zeros((n, 2)), None, np.zeros((2, 2)), np.eye(2), nu, xi=np.ones((n, 2)), seed=int(nu * 10))
+        for k in range(2):
+            x2 = nu / got[:, k] ** 2
+            assert stats.kstest(x2, "chi2", args=(nu,)).pvalue > 1e-3, (nu, k)
+        assert abs(np.corrcoef(got[:, 0], got[:, 1])[0, 1]) < 0.02      # the pair's factors are independent
 
 
 # ------------------------------------------------------------------------------------------------
