@@ -205,6 +205,7 @@ def run_reference(args, rank):
 # secondary workloads (reported inside the same JSON line; they do not affect `value`)
 # ------------------------------------------------------------------------------------------------
 def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
+    import cusmc_b200
     out = {}
     I2 = np.eye(2)
     try:
@@ -327,6 +328,44 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
             "note": "per-point packed Cholesky factor staged per warp by 1-D TMA bulk copies"}
     except Exception as e:
         out["perpoint_logpdf_evals_per_sec"] = {"error": repr(e)}
+    try:
+        # C1, the reference's own model: run(N = 10 000, d = 2, T = 1000, Y = y_sim, "metropolis", "mvn")
+        # through the R-facing API (host arrays in, weights [T][N] and posterior_x [T][N][d] out),
+        # next to the reference-form CPU loop of the oracle on a bounded sample of the same run
+        # (T = 101; its draws are pre-generated and not timed -- the reference itself spends most of
+        # its time in its 200-draw CLT sampler, src/statistics.cc.cpp:245-258)
+        Y = np.loadtxt(os.path.join(ROOT, "tests", "golden", "y_t.csv"), delimiter=",", skiprows=1).T
+        N, d, T = 10000, 2, 1000
+        kw = dict(m0=np.zeros(2), C0=I2, F=I2, G=I2, V=0.1 * I2, W=0.1 * I2)
+        cusmc_b200.run(N, d, 50, Y, df=0.0, resampler="metropolis", distribution="mvn", seed=1, **kw)   # warm-up
+        t0 = time.perf_counter()
+        res = cusmc_b200.run(N, d, T, Y, df=0.0, resampler="metropolis", distribution="mvn", seed=1, **kw)
+        ours_s = time.perf_counter() - t0
+        entry = {"ours_seconds": ours_s, "N": N, "d": d, "T": T, "resampler": "metropolis (B = 10)",
+                 "particle_steps_per_sec": N * (T - 1) / ours_s,
+                 "path": "cusmc_b200.run -> cusmc_run (host in, full history out: %.0f MB)"
+                         % ((res["weights"].nbytes + res["posterior_x"].nbytes) / 1e6)}
+        try:
+            from oracle_lib import oracle
+            orc = oracle()
+            orc.use_all_cores()
+            Ts, B = 101, 10
+            rng = np.random.default_rng(0)
+            xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((Ts - 1, N, d))
+            u, j = rng.random((Ts - 1, N, B)), rng.integers(0, N, (Ts - 1, N, B), dtype=np.uint32)
+            s10 = np.sqrt(0.1)
+            t0 = time.perf_counter()
+            orc.filter_metropolis("mvn", Y[:, :Ts], kw["m0"], I2, I2, I2, kw["V"], s10 * I2, 0.0, xi0, u, j, xi,
+                                  history=True)
+            cpu_s = time.perf_counter() - t0
+            entry["cpu_port"] = {"seconds": cpu_s, "T_sample": Ts, "cores": orc.num_threads(),
+                                 "particle_steps_per_sec": N * (Ts - 1) / cpu_s,
+                                 "note": "oracle reference-form loop (per-particle LU det + inverse); draws not timed"}
+        except Exception as e:
+            entry["cpu_port"] = {"error": repr(e)}
+        out["run_c1_reference_model"] = entry
+    except Exception as e:
+        out["run_c1_reference_model"] = {"error": repr(e)}
     return out
 
 
