@@ -684,6 +684,10 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     a.skip_weight = 1;
     a.const_weight = f->is_log ? 0.0 : 1.0 / (double)cfg.N;
     a.rng_stream = CUSMC_STREAM_INIT;
+    if (cfg.keep_history) {
+        a.hist_x = f->hist_x;
+        a.hist_w = f->hist_w;
+    }
     CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
                                   f->m0.data(), f->ep, a, f->draws.xi0_dev == nullptr));
     f->next_t = 1;
@@ -711,14 +715,6 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
         moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
                                                       f->moments + (size_t)t * (2 + d));
         CUSMC_LAUNCHED(ctx);
-    }
-    if (cfg.keep_history && n > 0) {
-        CUSMC_CHECK(cusmc_soa_to_aos_dev(ctx, f->x[f->cur], f->hist_x + (size_t)t * n * d, n, P, d));
-        CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_w + (size_t)t * n, f->lw, sizeof(double) * (size_t)n,
-                                        cudaMemcpyDeviceToDevice, st));
-        if (t > 0)
-            CUSMC_CUDA(ctx, cudaMemcpyAsync(f->hist_a + (size_t)t * n, f->anc, sizeof(uint32_t) * (size_t)n,
-                                            cudaMemcpyDeviceToDevice, st));
     }
     return CUSMC_OK;
 }
@@ -792,6 +788,11 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     a.kind = cfg.kind;
     a.has_prev = 1;
     a.rng_stream = CUSMC_STREAM_NORMAL;
+    if (cfg.keep_history) {       // the step's history rows are written by the step kernel itself
+        a.hist_x = f->hist_x + (size_t)t * n * d;
+        a.hist_w = f->hist_w + (size_t)t * n;
+        a.hist_a = f->hist_a + (size_t)t * n;
+    }
     if (f->world > 1) {
         a.world = f->world;
         a.rank = f->rank;

@@ -14,6 +14,10 @@ struct StepArgs {
     const double *chi;
     double *lw;
     double *lw_max;              // optional
+    // optional history rows of this step, written by the same threads (no extra launches):
+    // hist_x [n][d] AoS, hist_w [n], hist_a [n] (global parent ids)
+    double *hist_x, *hist_w;
+    uint32_t *hist_a;
     const unsigned long long *resampled;   // optional: if *resampled == 0 the step did not resample and
                                            // the new log-weight is ADDED to the particle's old one
     int64_t n_out, ld_new, ld_prev, ld_noise;

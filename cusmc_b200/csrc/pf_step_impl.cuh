@@ -192,6 +192,13 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             if (a.resampled && *a.resampled == 0) lw = *dst_lw + lw;   // no resampling: weights accumulate
         }
         st_stream(dst_lw, lw);
+        if (a.hist_x) {
+#pragma unroll
+            for (int k = 0; k < D; ++k)
+                if (EXACT || k < d) st_stream(a.hist_x + i * d + k, xn[k]);
+        }
+        if (a.hist_w) st_stream(a.hist_w + i, lw);
+        if (a.hist_a) a.hist_a[i] = (uint32_t)(parent + a.parent_base);
     }
     if (a.lw_max) {
         double m = (lw == lw && lw < INFINITY) ? lw : -INFINITY;
