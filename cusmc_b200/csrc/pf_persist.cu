@@ -31,9 +31,6 @@
 #include "../../include/cusmc_philox.h"
 
 #include <algorithm>
-#include <cooperative_groups.h>
-
-namespace cg = cooperative_groups;
 
 namespace {
 
@@ -54,6 +51,7 @@ struct PersistArgs {
     const double *obs;              // [T][D]: L_V^-1 y_t
     const double *u0;               // [T]: systematic offsets (entry t used by step t)
     double *moments;                // [T][2 + D] or NULL: sum w, -, sum w x_k (summary)
+    unsigned *barrier;              // grid barrier counter, zero at launch
     uint64_t seed;
     int64_t ld;
     uint32_t N;
@@ -107,6 +105,24 @@ __device__ __forceinline__ void draw_normals(uint64_t seed, int stream, uint64_t
     }
 }
 
+// Grid barrier on a monotonic arrival counter (the kernel is launched cooperatively, so every block
+// is resident).  Everything that crosses a barrier is read with L2 loads (__ldcg), so unlike
+// cooperative_groups' grid.sync() the wait loop does not have to invalidate L1 on every poll.
+__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        target += gridDim.x;
+        __threadfence();                        // release: the block's writes, cumulative through the bar.sync
+        atomicAdd(bar, 1u);
+        unsigned seen;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
+        } while ((int)(seen - target) < 0);
+    }
+    __syncthreads();
+}
+
 // Block-wide sums of two uint64 per thread (every thread gets both totals).
 __device__ __forceinline__ void block_sum2(unsigned long long &a, unsigned long long &b, unsigned long long *sm)
 {
@@ -143,7 +159,7 @@ __global__ void __launch_bounds__(kThreads, kBlocksPerSM)
 pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                      const __grid_constant__ pfstep::StepOp<D, DIAG> op, const Epilogue ep, const PersistArgs a)
 {
-    cg::grid_group grid = cg::this_grid();
+    unsigned bar_target = 0;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kItems = P, kPadded = padded_words(P);
     double *s_lw = reinterpret_cast<double *>(smem_raw);                               // [kPadded]
@@ -278,9 +294,9 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         for (int r = 0; r < kItems; ++r) particle(op_init, zero_c, 0, r, m);
         publish_max(0, m);
     }
-    grid.sync();
+    grid_barrier(a.barrier, bar_target);
     weigh(0);
-    grid.sync();
+    grid_barrier(a.barrier, bar_target);
 
     for (int t = 1; t < a.T; ++t) {
         // ---- scatter(t): ancestors of step t from the weight image of step t - 1 ----------------
@@ -345,7 +361,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                 }
             }
         }
-        grid.sync();
+        grid_barrier(a.barrier, bar_target);
 
         // ---- propagate(t) + reweight(t) (src/mcmc.cpp:298-307), max of the log-weights ----------
         {
@@ -358,11 +374,11 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             publish_max(t, m);
             cur ^= 1;
         }
-        grid.sync();
+        grid_barrier(a.barrier, bar_target);
 
         // ---- weigh(t) ---------------------------------------------------------------------------
         weigh(t);
-        grid.sync();
+        grid_barrier(a.barrier, bar_target);
     }
     // total mass of the last step (log-likelihood of the summary)
     if (blockIdx.x == 0) {
@@ -491,7 +507,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     cudaStream_t st = ctx->stream;
     // per-run scratch: tile sums [2][grid], whitened observations [T][d], systematic offsets [T]
     const size_t n_sum = 2 * (size_t)grid, n_obs = (size_t)T * d, n_u0 = (size_t)T;
-    const size_t bytes = 8 * (n_sum + n_obs + n_u0);
+    const size_t bytes = 8 * (n_sum + n_obs + n_u0 + 1);      // + the grid barrier counter
     if (bytes > f->persist_bytes) {
         CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
         cudaFree(f->persist);
@@ -509,6 +525,8 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     }
     unsigned long long *sums = (unsigned long long *)f->persist;
     double *obs = (double *)(sums + n_sum), *u0 = obs + n_obs;
+    unsigned *barrier = (unsigned *)(u0 + n_u0);
+    CUSMC_CUDA(ctx, cudaMemsetAsync(barrier, 0, 8, st));
     // the host vector dies with this call: a synchronous copy (pageable memory) is what we want
     CUSMC_CUDA(ctx, cudaMemcpyAsync(obs, host.data(), 8 * host.size(), cudaMemcpyHostToDevice, st));
     CUSMC_CUDA(ctx, cudaStreamSynchronize(st));
@@ -523,6 +541,7 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     a.obs = obs;
     a.u0 = u0;
     a.moments = cfg.summary ? f->moments : nullptr;
+    a.barrier = barrier;
     a.seed = cfg.seed;
     a.ld = f->per;
     a.N = (uint32_t)cfg.N;
