@@ -34,6 +34,10 @@
 
 namespace {
 
+#ifndef CUSMC_PERSIST_UNROLL
+#define CUSMC_PERSIST_UNROLL 2
+#endif
+constexpr int kPropagateUnroll = CUSMC_PERSIST_UNROLL;   // particles of a thread in flight in the propagate phase
 constexpr int kThreads = 512;
 // particles per thread: a template parameter P <= 8, picked so that N spreads evenly over the resident blocks
 constexpr int kBlocksPerSM = 2;                 // 2 x 512 threads at <= 64 registers, 2 x 72 KB of shared memory
@@ -369,7 +373,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
 #pragma unroll
             for (int k = 0; k < D; ++k) cobs[k] = __ldg(a.obs + (size_t)t * D + k);
             double m = -INFINITY;
-#pragma unroll 2
+#pragma unroll kPropagateUnroll
             for (int r = 0; r < kItems; ++r) particle(op, cobs, t, r, m);
             publish_max(t, m);
             cur ^= 1;
