@@ -695,6 +695,25 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     return CUSMC_OK;
 }
 
+// The systematic offset of step t: injected, or 53 Philox bits keyed by (seed, t).
+static double filter_u0(const cusmc_filter *f, int t)
+{
+    return f->draws.u0_host ? f->draws.u0_host[t - 1]
+                            : (double)(cusmc_u0_bits(f->cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+}
+
+static double filter_ess_bound(const cusmc_filter *f)
+{
+    return f->cfg.ess_threshold * (double)f->cfg.N * std::ldexp(1.0, f->shift);
+}
+
+// True when slot[t].sum_q is already GLOBAL at the end of weigh(t)'s tile scan (one GPU, or the
+// sums exchange rides in that kernel): the scan then also leaves the constants of resample(t + 1).
+static bool filter_consts_fused(const cusmc_filter *f)
+{
+    return f->cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC && f->is_log && (f->world == 1 || f->fused);
+}
+
 // After step t's weights exist and slot[t].lw_max holds the GLOBAL max: fixed-point sums and tile
 // prefixes (log modes), posterior moments, history.
 extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
@@ -707,9 +726,17 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
     const int64_t n = f->n, P = f->per;
     cudaStream_t st = ctx->stream;
     const MailArgs mail = filter_mail(f);
+    ScatterSetup next{};
+    if (filter_consts_fused(f) && t + 1 < cfg.T) {
+        next.enabled = 1;
+        next.u0 = filter_u0(f, t + 1);
+        next.ess_bound = cfg.ess_threshold > 0.0 ? filter_ess_bound(f) : 0.0;
+        next.N_global = (uint32_t)cfg.N;
+    }
     if (f->is_log)
         CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
-                                             f->scan_state, cfg.summary != 0 || cfg.ess_threshold > 0.0, &mail, t));
+                                             f->scan_state, cfg.summary != 0 || cfg.ess_threshold > 0.0, &mail, t,
+                                             &next));
     if (cfg.summary && n > 0) {
         const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
         moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
@@ -739,13 +766,12 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     }
     StepSlot *prev = &f->slots[t - 1];
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
-        const double u0 = dr.u0_host ? dr.u0_host[off]
-                                     : (double)(cusmc_u0_bits(cfg.seed, (uint64_t)t) >> 11) * 1.1102230246251565e-16;
+        const double u0 = filter_u0(f, t);
         const bool adaptive = cfg.ess_threshold > 0.0;
         return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
                                  nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr,
                                  adaptive ? &prev->sum_q2 : nullptr, adaptive ? &f->slots[t].resampled : nullptr,
-                                 cfg.ess_threshold * (double)N * std::ldexp(1.0, f->shift));
+                                 filter_ess_bound(f), filter_consts_fused(f));
     }
     CUSMC_CHECK(cusmc_launch_scan(ctx, n, N, &prev->sum_q, nullptr, f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0,
                                   nullptr));

@@ -45,6 +45,21 @@ constexpr int kBlocksPerSM = 2;                 // 2 x 512 threads at <= 64 regi
 // and the blocked (j = P*tid + r) access patterns stay (almost) conflict-free
 __device__ __forceinline__ int pad(int j) { return j + (j >> 3); }
 __host__ __device__ constexpr int padded_words(int P) { return kThreads * P + kThreads * P / 8 + 8; }
+// Noise in the barrier shadow: the normals of step t + 1 depend on nothing but (seed, t + 1, slot),
+// so a block generates them -- a third of its tile at each of the three grid barriers that precede
+// propagate(t + 1) -- BETWEEN its arrival at the barrier and the moment the last block arrives, and
+// parks them in shared memory as the single-precision values the generator produces (8 bytes per
+// d = 2 particle).  The 150 of ~400 instructions per particle-step that the Philox block and the
+// Box-Muller transform cost then run while the SM would otherwise spin.  d = 4 would need 2 x 64 KB
+// more shared memory than two resident blocks have: it keeps drawing inside propagate.
+#ifndef CUSMC_PERSIST_PREGEN
+#define CUSMC_PERSIST_PREGEN 1
+#endif
+__host__ __device__ constexpr bool pregen_noise(int D) { return CUSMC_PERSIST_PREGEN && D == 2; }
+__host__ __device__ constexpr size_t persist_smem_bytes(int D, int P)
+{
+    return 2 * sizeof(double) * (size_t)padded_words(P) + (pregen_noise(D) ? sizeof(float2) * (size_t)kThreads * P : 0);
+}
 
 struct PersistArgs {
     double *x[2];                   // SoA [d][ld] double buffer
@@ -112,13 +127,19 @@ __device__ __forceinline__ void draw_normals(uint64_t seed, int stream, uint64_t
 // Grid barrier on a monotonic arrival counter (the kernel is launched cooperatively, so every block
 // is resident).  Everything that crosses a barrier is read with L2 loads (__ldcg), so unlike
 // cooperative_groups' grid.sync() the wait loop does not have to invalidate L1 on every poll.
-__device__ __forceinline__ void grid_barrier(unsigned *bar, unsigned &target)
+// Split in two so that work which needs nothing from the other blocks runs between them.
+__device__ __forceinline__ void grid_barrier_arrive(unsigned *bar, unsigned &target)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
         target += gridDim.x;
         __threadfence();                        // release: the block's writes, cumulative through the bar.sync
         atomicAdd(bar, 1u);
+    }
+}
+__device__ __forceinline__ void grid_barrier_wait(unsigned *bar, unsigned target)
+{
+    if (threadIdx.x == 0) {
         unsigned seen;
         do {
             asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar) : "memory");
@@ -168,6 +189,10 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
     constexpr int kItems = P, kPadded = padded_words(P);
     double *s_lw = reinterpret_cast<double *>(smem_raw);                               // [kPadded]
     unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw) + kPadded;   // [kPadded]
+    constexpr bool kPregen = pregen_noise(D);
+    constexpr int kPregenChunk = (P + 2) / 3;          // rounds generated per barrier: three barriers cover the tile
+    float2 *s_z = reinterpret_cast<float2 *>(smem_raw + 2 * sizeof(double) * kPadded);     // [kThreads * P], striped
+    int z_done = 0;                                    // rounds of the NEXT propagate whose normals sit in s_z
     __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
     __shared__ double s_dbl[kThreads / 32];
     __shared__ uint32_t s_k[kThreads];
@@ -195,7 +220,13 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
 #pragma unroll
                 for (int k = 0; k < D; ++k) xp[k] = 0.0;
             }
-            draw_normals<D>(a.seed, t > 0 ? CUSMC_STREAM_NORMAL : CUSMC_STREAM_INIT, (uint64_t)t, (uint64_t)i, z);
+            if (kPregen && t > 0 && r < z_done) {
+                const float2 zz = s_z[j];
+                z[0] = (double)zz.x;
+                z[D > 1 ? 1 : 0] = (double)zz.y;
+            } else {
+                draw_normals<D>(a.seed, t > 0 ? CUSMC_STREAM_NORMAL : CUSMC_STREAM_INIT, (uint64_t)t, (uint64_t)i, z);
+            }
             propagate_one<D, DIAG>(o, cobs, xp, z, xn, q);
             double *dst = a.x[t > 0 ? cur ^ 1 : 0] + i;
 #pragma unroll
@@ -205,6 +236,27 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             if (lw == lw && lw < INFINITY && lw > m) m = lw;
         }
         s_lw[pad(j)] = lw;
+    };
+
+    // grid barrier; between arrival and release the block draws the next chunk of step t_next's normals
+    auto grid_barrier = [&](int t_next) {
+        grid_barrier_arrive(a.barrier, bar_target);
+        if (kPregen && t_next < a.T && z_done < kItems) {
+            const int hi = min(kItems, z_done + kPregenChunk);
+#pragma unroll 1
+            for (int r = z_done; r < hi; ++r) {
+                const int j = r * kThreads + (int)tid;
+                if ((uint32_t)j < tile_n) {
+                    // the first Box-Muller pair of the particle's block 0 (cusmc_normal4 with D = 2)
+                    const cusmc_u32x4 rb = cusmc_rng(a.seed, CUSMC_STREAM_NORMAL, (uint64_t)t_next, (uint64_t)(tile0 + (uint32_t)j), 0u);
+                    float2 zz;
+                    cusmc_box_muller_f32(rb.v[0], rb.v[1], &zz.x, &zz.y);
+                    s_z[j] = zz;
+                }
+            }
+            z_done = hi;
+        }
+        grid_barrier_wait(a.barrier, bar_target);
     };
 
     // block max -> atomic max into the step's slot
@@ -298,9 +350,9 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         for (int r = 0; r < kItems; ++r) particle(op_init, zero_c, 0, r, m);
         publish_max(0, m);
     }
-    grid_barrier(a.barrier, bar_target);
+    grid_barrier(1);
     weigh(0);
-    grid_barrier(a.barrier, bar_target);
+    grid_barrier(1);
 
     for (int t = 1; t < a.T; ++t) {
         // ---- scatter(t): ancestors of step t from the weight image of step t - 1 ----------------
@@ -365,7 +417,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                 }
             }
         }
-        grid_barrier(a.barrier, bar_target);
+        grid_barrier(t);
 
         // ---- propagate(t) + reweight(t) (src/mcmc.cpp:298-307), max of the log-weights ----------
         {
@@ -377,12 +429,13 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             for (int r = 0; r < kItems; ++r) particle(op, cobs, t, r, m);
             publish_max(t, m);
             cur ^= 1;
+            z_done = 0;                                 // s_z is free: it refills with step t + 1's normals
         }
-        grid_barrier(a.barrier, bar_target);
+        grid_barrier(t + 1);
 
         // ---- weigh(t) ---------------------------------------------------------------------------
         weigh(t);
-        grid_barrier(a.barrier, bar_target);
+        grid_barrier(t + 1);
     }
     // total mass of the last step (log-likelihood of the summary)
     if (blockIdx.x == 0) {
@@ -400,7 +453,7 @@ int launch_persistent(cusmc_filter *f, const PersistArgs &args, bool probe_only)
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     auto kernel = pf_persistent_kernel<D, DIAG, P, SUMMARY>;
-    constexpr size_t kSmem = 2 * sizeof(double) * (size_t)padded_words(P);     // log-weights + CDF of one tile
+    constexpr size_t kSmem = persist_smem_bytes(D, P);     // log-weights + CDF of one tile (+ parked normals)
     const unsigned grid = (unsigned)((cfg.N + args.tile_n - 1) / args.tile_n);
     CUSMC_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmem));
     int per_sm = 0;

@@ -106,11 +106,11 @@ weights_max_kernel(const double *__restrict__ w, int64_t N, double *__restrict__
 //
 // A tile is kTile = 2048 consecutive weights; thread t of the block owns the 8 consecutive weights
 // 8t .. 8t+7 (four 128-bit loads).  Workspace layout, uint64 words (cusmc_scan_state_bytes):
-//     [0]                 reserved
-//     [1 + b]             sum of tile b, turned IN PLACE into the exclusive prefix over tiles by
+//     [0 .. 7]            ScatterConsts: per-launch constants of the resampling pass (resample.cuh)
+//     [8 + b]             sum of tile b, turned IN PLACE into the exclusive prefix over tiles by
 //                         tile_scan_kernel (one block; ~2 us at N = 8 Mi)
-//     [1 + tiles + b]     sum of squared weights of tile b   } FULL only (ESS); reduced by
-//     [1 + 2 tiles + b]   positive weights in tile b         } tile_scan_kernel
+//     [8 + tiles + b]     sum of squared weights of tile b   } FULL only (ESS); reduced by
+//     [8 + 2 tiles + b]   positive weights in tile b         } tile_scan_kernel
 //     [H + i]             inclusive prefix of weight i INSIDE its tile (H = header words, even)
 // exp() is evaluated once per weight, here.  The resampling pass that follows needs neither the
 // weights nor a scan of its own: global CDF_i = offset + prefix[tile(i)] + local_i, one thread per
@@ -122,19 +122,28 @@ weights_max_kernel(const double *__restrict__ w, int64_t N, double *__restrict__
 __host__ __device__ inline int64_t image_tiles(int64_t N) { return (N + kTile - 1) / kTile; }
 __host__ __device__ inline int64_t image_header_words(int64_t N)
 {
-    return (1 + 3 * image_tiles(N) + 1) & ~(int64_t)1;       // rounded up to 16 bytes
+    return (kImageHead + 3 * image_tiles(N) + 3) & ~(int64_t)3;       // rounded up to 32 bytes
+}
+
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): a thread's 8 weights are two loads, its 8
+// prefixes two stores, every request a whole 32-byte sector.
+__device__ __forceinline__ void ldg256(const double *p, double &a, double &b, double &c, double &d)
+{
+    asm volatile("ld.global.nc.v4.f64 {%0, %1, %2, %3}, [%4];" : "=d"(a), "=d"(b), "=d"(c), "=d"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg256(unsigned long long *p, unsigned long long a, unsigned long long b,
+                                       unsigned long long c, unsigned long long d)
+{
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
 }
 
 __device__ __forceinline__ void load_tile_items(const double *__restrict__ w, int64_t base, int64_t N,
                                                 double (&v)[kTileItems])
 {
-    if (base + kTileItems <= N && (((uintptr_t)(w + base)) & 15) == 0) {
+    static_assert(kTileItems % 4 == 0, "tile items come in 256-bit groups");
+    if (base + kTileItems <= N && (((uintptr_t)(w + base)) & 31) == 0) {
 #pragma unroll
-        for (int r = 0; r < kTileItems / 2; ++r) {
-            const double2 t = __ldg(reinterpret_cast<const double2 *>(w + base) + r);
-            v[2 * r] = t.x;
-            v[2 * r + 1] = t.y;
-        }
+        for (int r = 0; r < kTileItems / 4; ++r) ldg256(w + base + 4 * r, v[4 * r], v[4 * r + 1], v[4 * r + 2], v[4 * r + 3]);
     } else {
 #pragma unroll
         for (int r = 0; r < kTileItems; ++r) v[r] = base + r < N ? __ldg(w + base + r) : -INFINITY;
@@ -199,12 +208,13 @@ weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, in
     }
     // tile-local inclusive CDF (the workspace is padded to whole tiles: no bounds checks)
     unsigned long long *local = image + image_header_words(N) + base;
+    if ((((uintptr_t)local) & 31) == 0) {        // always, unless the caller supplied an unaligned image
 #pragma unroll
-    for (int r = 0; r < kTileItems / 2; ++r) {
-        ulonglong2 t;
-        t.x = before + c[2 * r];
-        t.y = before + c[2 * r + 1];
-        reinterpret_cast<ulonglong2 *>(local)[r] = t;
+        for (int r = 0; r < kTileItems / 4; ++r)
+            stg256(local + 4 * r, before + c[4 * r], before + c[4 * r + 1], before + c[4 * r + 2], before + c[4 * r + 3]);
+    } else {
+#pragma unroll
+        for (int r = 0; r < kTileItems; ++r) local[r] = before + c[r];
     }
     if (FULL) {
         s2 = block_sum_u64(s2, sm);
@@ -212,33 +222,45 @@ weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, in
     }
     if (threadIdx.x == 0) {
         const int64_t tiles = gridDim.x;
-        image[1 + blockIdx.x] = tile_total;
+        image[kImageHead + blockIdx.x] = tile_total;
         if (FULL) {
-            image[1 + tiles + blockIdx.x] = s2;
-            image[1 + 2 * tiles + blockIdx.x] = np;
+            image[kImageHead + tiles + blockIdx.x] = s2;
+            image[kImageHead + 2 * tiles + blockIdx.x] = np;
         }
     }
 }
 
 // One block: exclusive prefix of the tile sums, in place, and the totals
-// stats[0..2] = { sum q, sum q2, #positive } (plain stores: nothing to zero beforehand).
+// stats[0..2] = { sum q, sum q2, #positive } (plain stores: nothing to zero beforehand).  A thread
+// owns kScanItems consecutive tiles, all loads of a chunk are issued before the first dependent
+// instruction: 4096 tiles (N = 8 Mi) are one chunk, one block-wide scan.
 constexpr int kScanThreads = 1024;
+constexpr int kScanItems = 4;
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned long long *__restrict__ stats,
-                 int full, const MailArgs mail, size_t cell_sums)
+                 int full, const MailArgs mail, size_t cell_sums, const ScatterSetup next)
 {
     __shared__ unsigned long long sm[kScanThreads / 32];
     __shared__ unsigned long long s_chunk;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *sums = image + kImageHead;
     unsigned long long carry = 0, s2 = 0, np = 0;
-    for (int64_t base = 0; base < tiles; base += kScanThreads) {
-        const int64_t idx = base + threadIdx.x;
-        const unsigned long long v = idx < tiles ? image[1 + idx] : 0ull;
-        if (full && idx < tiles) {
-            s2 += image[1 + tiles + idx];
-            np += image[1 + 2 * tiles + idx];
+    for (int64_t base = 0; base < tiles; base += kScanThreads * kScanItems) {
+        const int64_t i0 = base + (int64_t)threadIdx.x * kScanItems;
+        unsigned long long v[kScanItems], run = 0;
+#pragma unroll
+        for (int r = 0; r < kScanItems; ++r) v[r] = i0 + r < tiles ? sums[i0 + r] : 0ull;
+        if (full) {
+#pragma unroll
+            for (int r = 0; r < kScanItems; ++r)
+                if (i0 + r < tiles) {
+                    s2 += sums[tiles + i0 + r];
+                    np += sums[2 * tiles + i0 + r];
+                }
         }
-        unsigned long long inc = v;
+#pragma unroll
+        for (int r = 0; r < kScanItems; ++r) run += v[r];
+        unsigned long long inc = run;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -258,11 +280,16 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
             if (lane == 31) s_chunk = wi;
         }
         __syncthreads();
-        if (idx < tiles) image[1 + idx] = carry + sm[warp] + inc - v;
+        unsigned long long excl = carry + sm[warp] + inc - run;
+#pragma unroll
+        for (int r = 0; r < kScanItems; ++r) {
+            if (i0 + r < tiles) sums[i0 + r] = excl;
+            excl += v[r];
+        }
         carry += s_chunk;
         __syncthreads();
     }
-    if (!stats) return;
+    if (!stats && !next.enabled) return;
     __shared__ unsigned long long s_tot[3];
     if (full) {
 #pragma unroll
@@ -276,11 +303,13 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
             sm2[warp] = np;
         }
         __syncthreads();
-        if (threadIdx.x == 0) {
-            s2 = np = 0;
-            for (int k = 0; k < kScanThreads / 32; ++k) {
-                s2 += sm[k];
-                np += sm2[k];
+        if (warp == 0) {
+            s2 = sm[lane];
+            np = sm2[lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                np += __shfl_xor_sync(0xffffffffu, np, o);
             }
         }
     }
@@ -306,12 +335,16 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
         }
     }
     if (lane == 0) {
-        stats[0] = w0;
-        if (full) {
-            stats[1] = w1;
-            stats[2] = w2;
+        if (stats) {
+            stats[0] = w0;
+            if (full) {
+                stats[1] = w1;
+                stats[2] = w2;
+            }
+            if (mail.world > 1) stats[3] = below;      // StepSlot::cdf_offset
         }
-        if (mail.world > 1) stats[3] = below;      // StepSlot::cdf_offset
+        if (next.enabled)
+            *reinterpret_cast<ScatterConsts *>(image) = make_scatter_consts(w0, next.u0, next.N_global, next.ess_bound, w1);
     }
 }
 
@@ -320,6 +353,7 @@ struct ScanArgs {
     const unsigned long long *cdf_offset;  // mass on lower shards, or NULL
     const unsigned long long *tile_prefix; // weight image: exclusive prefix of tile b at [b]
     const unsigned long long *local;       // weight image: inclusive prefix of weight i inside its tile
+    ScatterConsts *consts;                 // weight image: the per-launch constants of the scatter
     unsigned long long *cdf_out;           // optional inclusive global CDF
     uint32_t *anc_out;                     // optional systematic ancestors for children
     uint32_t *const *anc_peer;             // PEERS: device table, rank r's ancestor array (child slots r*per_rank ..)
@@ -333,6 +367,15 @@ struct ScanArgs {
     unsigned long long *resampled_out;
     double ess_bound;
 };
+
+// The scatter constants for callers whose totals do not come out of tile_scan_kernel (building-block
+// entry points with a caller-supplied total, sharded runs whose sums travel through torch.distributed).
+__global__ void scatter_consts_kernel(const ScanArgs p)
+{
+    if (threadIdx.x == 0)
+        *p.consts = make_scatter_consts(*p.total, p.u0, p.N_global, p.ess_bound,
+                                        p.ess_bound > 0.0 ? *p.sum_q2 : 0ull);
+}
 
 // PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
 // owning rank's ancestor array through its peer-mapped pointer (4 bytes per child over NVLink).
@@ -351,98 +394,80 @@ __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, 
 }
 
 // Global CDF from the weight image and, fused in, the systematic offspring scatter: parent j owns
-// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  A thread owns kPar = 4
-// consecutive parents (two 128-bit loads of the tile-local CDF; the block prologue, the per-launch
-// constants and the neighbour exchange are paid once per four parents); indices and offspring counts
-// are 32-bit throughout (N_global < 2^32).
+// the child slots [k(C_{j-1}), k(C_j)) and writes its own index into them.  A warp owns 32 kPar
+// consecutive parents, lane l the parents l, l + 32, ... of them: in round r the lanes hold 32
+// CONSECUTIVE parents, so their loads of the tile-local CDF and -- since neighbouring parents own
+// neighbouring child ranges -- their ancestor stores coalesce (a thread owning 4 consecutive parents
+// spread every store instruction of the warp over 16 sectors).  Indices and offspring counts are 32-bit
+// throughout (N_global < 2^32).  Warps are independent: the per-launch constants come precomputed
+// (ScatterConsts), a parent's left neighbour's count arrives by shuffle (lane 31's of the round before
+// for lane 0) and lane 0 evaluates the count below the warp's first parent itself -- no shared
+// memory, no barrier, nothing between a warp's loads and its stores but its own arithmetic.
 constexpr int kPar = 4;
-static_assert(kTile % (kThreads * kPar) == 0, "a block of the resampling pass must lie inside one tile");
+static_assert(kTile % (32 * kPar) == 0, "a warp of the resampling pass must lie inside one tile");
 template <bool PEERS>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 6)
 scan_resample_kernel(const ScanArgs p)
 {
-    __shared__ uint32_t s_k[kThreads];
-    __shared__ uint64_t s_T, s_r0;
-    __shared__ double s_ng_over_t, s_r0_over_t;
-    __shared__ int s_resample;
-    const uint32_t i0 = (blockIdx.x * kThreads + threadIdx.x) * kPar;    // first local parent of the thread
-    const uint32_t tile = (blockIdx.x * kThreads * kPar) / kTile;         // a block lies inside one tile
-    const uint64_t base = p.tile_prefix[tile] + (p.cdf_offset ? *p.cdf_offset : 0ull);
-    uint64_t C[kPar];
-    if (i0 + kPar <= p.N) {              // the image is padded to whole tiles and 16-byte aligned
-        const ulonglong2 a = __ldg(reinterpret_cast<const ulonglong2 *>(p.local + i0));
-        const ulonglong2 b = __ldg(reinterpret_cast<const ulonglong2 *>(p.local + i0) + 1);
-        C[0] = base + a.x;
-        C[1] = base + a.y;
-        C[2] = base + b.x;
-        C[3] = base + b.y;
-    } else {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t w0 = ((blockIdx.x * kThreads + threadIdx.x) >> 5) * (32 * kPar);   // the warp's first local parent
+    if (w0 >= p.N) return;                                                 // whole warp past the end
+    const uint32_t i0 = w0 + lane;                                        // parents i0 + 32 r
+    const uint32_t tile = w0 / kTile;                                     // a warp lies inside one tile
+    const bool scatter = PEERS || p.anc_out;
+    // every load goes out before the first use
+    const uint64_t prefix = __ldg(p.tile_prefix + tile);
+    const uint64_t offset = p.cdf_offset ? __ldg(p.cdf_offset) : 0ull;
+    uint64_t C[kPar], Cprev = 0;
 #pragma unroll
-        for (int r = 0; r < kPar; ++r) C[r] = base + (i0 + r < p.N ? __ldg(p.local + i0 + r) : 0ull);
+    for (int r = 0; r < kPar; ++r) C[r] = i0 + 32 * r < p.N ? __ldg(p.local + i0 + 32 * r) : 0ull;
+    if (scatter && lane == 0 && (w0 % kTile)) Cprev = __ldg(p.local + w0 - 1);
+    ScatterConsts c{};
+    if (scatter) {
+        c.T = __ldg(&p.consts->T);
+        c.r0 = __ldg(&p.consts->r0);
+        c.ng_over_t = __ldg(&p.consts->ng_over_t);
+        c.r0_over_t = __ldg(&p.consts->r0_over_t);
+        c.resample = __ldg(&p.consts->resample);
     }
+    const uint64_t base = prefix + offset;
+#pragma unroll
+    for (int r = 0; r < kPar; ++r) C[r] += base;
     if (p.cdf_out) {
 #pragma unroll
         for (int r = 0; r < kPar; ++r)
-            if (i0 + r < p.N) p.cdf_out[i0 + r] = C[r];
+            if (i0 + 32 * r < p.N) p.cdf_out[i0 + 32 * r] = C[r];
     }
-    if (!PEERS && !p.anc_out) return;
-    // the per-launch constants (two fp64 divisions, 64-bit conversions) once per block, not per thread
-    if (threadIdx.x == 0) {
-        const uint64_t Tt = *p.total;
-        uint64_t rr = (uint64_t)(p.u0 * (double)Tt);
-        if (Tt && rr > Tt - 1) rr = Tt - 1;
-        s_T = Tt;
-        s_r0 = rr;
-        s_ng_over_t = (double)p.N_global / (double)Tt;
-        s_r0_over_t = (double)rr / (double)Tt;
-        // ESS = sum_q^2 / (sum_q2 2^shift) < threshold N  <=>  sum_q^2 < ess_bound sum_q2
-        int go = 1;
-        if (p.ess_bound > 0.0) go = (double)Tt * (double)Tt < p.ess_bound * (double)*p.sum_q2;
-        s_resample = go;
-        if (blockIdx.x == 0 && p.resampled_out) *p.resampled_out = (unsigned long long)go;
-    }
-    __syncthreads();
-    const uint64_t T = s_T;
+    if (!scatter) return;
+    if (w0 == 0 && lane == 0 && p.resampled_out) *p.resampled_out = c.resample;
+    const uint64_t T = c.T;
     if (T == 0) return;                               // degenerate: the host reports it
-    if (!s_resample) {                                // keep every particle: a_i = i
+    if (!c.resample) {                                // keep every particle: a_i = i
 #pragma unroll
         for (int r = 0; r < kPar; ++r)
-            if (i0 + r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + r, p.j0 + i0 + r);
+            if (i0 + 32 * r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + 32 * r, p.j0 + i0 + 32 * r);
         return;
     }
-    const uint64_t r0 = s_r0;
-    const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
+    const uint64_t r0 = c.r0;
+    const double ng_over_t = c.ng_over_t, r0_over_t = c.r0_over_t;
     const uint64_t Ng = p.N_global;
-    // the offspring count is a pure function of the CDF value: a zero weight repeats its left
-    // neighbour's; the thread's left neighbour's last count comes through shared memory, the block's
-    // first thread evaluates its own
+    // the offspring count is a pure function of the CDF value
     uint32_t k[kPar];
 #pragma unroll
-    for (int r = 0; r < kPar; ++r) {
-        if (i0 + r >= p.N)
-            k[r] = 0;
-        else if (r > 0 && C[r] == C[r - 1])
-            k[r] = k[r - 1];
-        else
-            k[r] = (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t);
-    }
-    s_k[threadIdx.x] = k[kPar - 1];
-    __syncthreads();
-    uint32_t k_prev = 0;
-    if (threadIdx.x > 0) {
-        k_prev = s_k[threadIdx.x - 1];
-    } else if (i0 < p.N) {
-        const uint64_t Cprev = base + ((i0 % kTile) ? __ldg(p.local + i0 - 1) : 0ull);
-        k_prev = (uint32_t)offspring_below(Cprev, Ng, T, r0, ng_over_t, r0_over_t);
-    }
-    const uint32_t lane = threadIdx.x & 31;
+    for (int r = 0; r < kPar; ++r)
+        k[r] = i0 + 32 * r < p.N ? (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t) : 0u;
+    uint32_t k_carry = 0;                              // count below the round's first parent (lane 0)
+    if (lane == 0) k_carry = (uint32_t)offspring_below(base + Cprev, Ng, T, r0, ng_over_t, r0_over_t);
 #pragma unroll
     for (int r = 0; r < kPar; ++r) {
-        const bool active = i0 + r < p.N;
+        const bool active = i0 + 32 * r < p.N;
+        uint32_t k_prev = __shfl_up_sync(0xffffffffu, k[r], 1);
+        if (lane == 0) k_prev = k_carry;
+        k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // used by lane 0 only; a full round is all active
         // parents past the end own the empty range; their threads stay to help with large families
         uint32_t a = active ? max(k_prev, p.out_lo) : 0u;
         const uint32_t b = active ? min(k[r], p.out_hi) : 0u;
-        const uint32_t parent = p.j0 + i0 + r;
+        const uint32_t parent = p.j0 + i0 + 32 * r;
         // small families: the owning thread writes them; large ones: the whole warp helps
         const bool big = b > a && b - a > 8;
         if (!big) {
@@ -457,9 +482,8 @@ scan_resample_kernel(const ScanArgs p)
             const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
             const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
 #pragma unroll 1
-            for (uint32_t c = sa + lane; c < sb; c += 32) put_ancestor<PEERS>(p, c, sp);
+            for (uint32_t cc = sa + lane; cc < sb; cc += 32) put_ancestor<PEERS>(p, cc, sp);
         }
-        if (active) k_prev = k[r];
     }
 }
 
@@ -546,10 +570,12 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
 // one block that turns the tile sums into prefixes and totals.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
                              int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
-                             const MailArgs *mail_p, int t)
+                             const MailArgs *mail_p, int t, const ScatterSetup *next_p)
 {
     MailArgs mail{};
     if (mail_p) mail = *mail_p;
+    ScatterSetup next{};
+    if (next_p) next = *next_p;
     const bool exchange = mail.world > 1;
     if (N == 0 && !exchange) return CUSMC_OK;
     // an empty shard still publishes (max = -inf, sums = 0): one block over zero weights
@@ -567,7 +593,7 @@ int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const 
         weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     CUSMC_LAUNCHED(ctx);
     tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(img, (int64_t)tiles, (unsigned long long *)stats_dev,
-                                                          full ? 1 : 0, mail, csum);
+                                                          full ? 1 : 0, mail, csum, next);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -582,7 +608,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev,
-                      uint64_t *resampled_dev, double ess_bound)
+                      uint64_t *resampled_dev, double ess_bound, bool consts_ready)
 {
     if (N == 0) return CUSMC_OK;
     if (N_global > 0xFFFFFFFFll || out_lo < 0 || out_lo + out_n > N_global)
@@ -590,8 +616,9 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     ScanArgs p{};
     p.total = (const unsigned long long *)total_dev;
     p.cdf_offset = (const unsigned long long *)cdf_offset_dev;
-    p.tile_prefix = (const unsigned long long *)image + 1;
+    p.tile_prefix = (const unsigned long long *)image + kImageHead;
     p.local = (const unsigned long long *)image + image_header_words(N);
+    p.consts = (ScatterConsts *)const_cast<void *>(image);
     p.cdf_out = (unsigned long long *)cdf_out;
     p.anc_out = anc_out;
     p.N = (uint32_t)N;
@@ -604,6 +631,10 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.resampled_out = (unsigned long long *)resampled_dev;
     p.ess_bound = sum_q2_dev ? ess_bound : 0.0;
     const unsigned grid = (unsigned)((N + kThreads * kPar - 1) / (kThreads * kPar));
+    if ((anc_out || peers) && !consts_ready) {
+        scatter_consts_kernel<<<1, 32, 0, ctx->stream>>>(p);
+        CUSMC_LAUNCHED(ctx);
+    }
     if (peers) {
         p.anc_peer = (uint32_t *const *)peers->table_dev;
         p.per_rank = make_fast_div((uint32_t)peers->per_rank);

@@ -11,15 +11,24 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
 // image: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the weight image
 // (exclusive tile prefixes + tile-local CDF) the resampling pass consumes.  stats_dev may be NULL.
+// next: when given, the one-block tile scan also leaves the constants of the systematic resampling
+// pass that will consume this image (ScatterConsts, image words 0..7) -- computed from the GLOBAL
+// totals, i.e. after the fused sums exchange of a sharded run.
+struct ScatterSetup {
+    double u0;              // systematic offset of the resampling pass, [0, 1)
+    double ess_bound;       // adaptive resampling bound (0 = always resample), see ScanArgs
+    uint32_t N_global;
+    int enabled;
+};
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
                              int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
-                             const MailArgs *mail = nullptr, int t = 0);
+                             const MailArgs *mail = nullptr, int t = 0, const ScatterSetup *next = nullptr);
 size_t cusmc_scan_state_bytes(int64_t N);
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev = nullptr,
-                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0);
+                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0, bool consts_ready = false);
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
                              int64_t n_out, int64_t j0, uint32_t *a);
@@ -33,7 +42,36 @@ constexpr int kTileItems = CUSMC_TILE_ITEMS;
 constexpr int kTile = kResampleThreads * kTileItems;    // 2048 weights per tile
 
 
+// Per-launch constants of the systematic offspring scatter (64 bytes at the head of the weight
+// image).  Computed ONCE per step by one thread -- the tail of tile_scan_kernel or, for the building-
+// block entry points, scatter_consts_kernel -- instead of once per block of the resampling pass: the
+// dependent chain load(total) -> two fp64 divisions -> barrier was on every block's critical path.
+struct ScatterConsts {
+    unsigned long long T;        // global fixed-point mass
+    unsigned long long r0;       // systematic offset in mass units: min(trunc(u0 T), T - 1)
+    double ng_over_t, r0_over_t; // N_global / T, r0 / T (the floating estimate of offspring_below)
+    unsigned long long resample; // adaptive resampling decision (1 = draw new ancestors)
+    unsigned long long pad[3];
+};
+constexpr int kImageHead = sizeof(ScatterConsts) / 8;   // image words before the tile sums
+
 #ifdef __CUDACC__
+__device__ __forceinline__ ScatterConsts make_scatter_consts(unsigned long long Tt, double u0, uint32_t N_global,
+                                                            double ess_bound, unsigned long long sum_q2)
+{
+    ScatterConsts c{};
+    unsigned long long rr = (unsigned long long)(u0 * (double)Tt);
+    if (Tt && rr > Tt - 1) rr = Tt - 1;
+    c.T = Tt;
+    c.r0 = rr;
+    c.ng_over_t = (double)N_global / (double)Tt;
+    c.r0_over_t = (double)rr / (double)Tt;
+    // ESS = sum_q^2 / (sum_q2 2^shift) < threshold N  <=>  sum_q^2 < ess_bound sum_q2
+    c.resample = 1;
+    if (ess_bound > 0.0) c.resample = (double)Tt * (double)Tt < ess_bound * (double)sum_q2;
+    return c;
+}
+
 // #{ i in [0, Ng) : i*T + r0 < C*Ng }  =  smallest k with k*T + r0 >= C*Ng, clamped to Ng.
 // Floating-point estimate, then (rarely) an exact 128-bit correction.
 __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
