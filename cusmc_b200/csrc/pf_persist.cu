@@ -31,11 +31,12 @@
 #include "../../include/cusmc_philox.h"
 
 #include <algorithm>
+#include <type_traits>
 
 namespace {
 
 #ifndef CUSMC_PERSIST_UNROLL
-#define CUSMC_PERSIST_UNROLL 2
+#define CUSMC_PERSIST_UNROLL 1
 #endif
 constexpr int kPropagateUnroll = CUSMC_PERSIST_UNROLL;   // particles of a thread in flight in the propagate phase
 constexpr int kThreads = 512;
@@ -190,7 +191,11 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
     double *s_lw = reinterpret_cast<double *>(smem_raw);                               // [kPadded]
     unsigned long long *s_c = reinterpret_cast<unsigned long long *>(smem_raw) + kPadded;   // [kPadded]
     constexpr bool kPregen = pregen_noise(D);
-    constexpr int kPregenChunk = (P + 2) / 3;          // rounds generated per barrier: three barriers cover the tile
+#ifndef CUSMC_PERSIST_CHUNK_DIV
+#define CUSMC_PERSIST_CHUNK_DIV 3
+#endif
+    constexpr int kPregenChunk = (P + CUSMC_PERSIST_CHUNK_DIV - 1) / CUSMC_PERSIST_CHUNK_DIV;   // rounds generated per barrier: three barriers cover the tile
+    static_assert(3 * kPregenChunk >= P, "the three barriers before a propagate must cover the tile");
     float2 *s_z = reinterpret_cast<float2 *>(smem_raw + 2 * sizeof(double) * kPadded);     // [kThreads * P], striped
     int z_done = 0;                                    // rounds of the NEXT propagate whose normals sit in s_z
     __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
@@ -205,13 +210,15 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
     int cur = 0;
 
     // one particle: gather (t > 0), noise, propagate, reweight; striped round r
-    auto particle = [&](const pfstep::StepOp<D, DIAG> &o, const double (&cobs)[D], int t, int r, double &m) {
+    auto particle = [&](auto is_init, const pfstep::StepOp<D, DIAG> &o, const double (&cobs)[D], int t_step, int r, double &m) {
+        constexpr bool kInit = decltype(is_init)::value;
+        const int t = kInit ? 0 : t_step;
         const int j = r * kThreads + (int)tid;
         const uint32_t i = tile0 + (uint32_t)j;
         double lw = -INFINITY;
         if ((uint32_t)j < tile_n) {
             double xp[D], z[D], xn[D], q;
-            if (t > 0) {
+            if (!kInit) {
                 const uint32_t par = __ldcg(a.anc + i);
                 const double *src = a.x[cur] + par;
 #pragma unroll
@@ -220,18 +227,20 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
 #pragma unroll
                 for (int k = 0; k < D; ++k) xp[k] = 0.0;
             }
-            if (kPregen && t > 0 && r < z_done) {
+            if (kPregen && !kInit) {
+                // drawn in the shadow of the three barriers since the last propagate (all kItems rounds:
+                // 3 x kPregenChunk >= kItems)
                 const float2 zz = s_z[j];
                 z[0] = (double)zz.x;
                 z[D > 1 ? 1 : 0] = (double)zz.y;
             } else {
-                draw_normals<D>(a.seed, t > 0 ? CUSMC_STREAM_NORMAL : CUSMC_STREAM_INIT, (uint64_t)t, (uint64_t)i, z);
+                draw_normals<D>(a.seed, kInit ? CUSMC_STREAM_INIT : CUSMC_STREAM_NORMAL, (uint64_t)t, (uint64_t)i, z);
             }
             propagate_one<D, DIAG>(o, cobs, xp, z, xn, q);
-            double *dst = a.x[t > 0 ? cur ^ 1 : 0] + i;
+            double *dst = a.x[kInit ? 0 : cur ^ 1] + i;
 #pragma unroll
             for (int k = 0; k < D; ++k) st_stream(dst + (int64_t)k * a.ld, xn[k]);
-            lw = t > 0 ? density_epilogue(ep, q) : 0.0;
+            lw = kInit ? 0.0 : density_epilogue(ep, q);
             st_stream(a.lw + i, lw);
             if (lw == lw && lw < INFINITY && lw > m) m = lw;
         }
@@ -347,7 +356,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
         const double zero_c[D] = {};
         double m = -INFINITY;
 #pragma unroll 1
-        for (int r = 0; r < kItems; ++r) particle(op_init, zero_c, 0, r, m);
+        for (int r = 0; r < kItems; ++r) particle(std::true_type{}, op_init, zero_c, 0, r, m);
         publish_max(0, m);
     }
     grid_barrier(1);
@@ -426,7 +435,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             for (int k = 0; k < D; ++k) cobs[k] = __ldg(a.obs + (size_t)t * D + k);
             double m = -INFINITY;
 #pragma unroll kPropagateUnroll
-            for (int r = 0; r < kItems; ++r) particle(op, cobs, t, r, m);
+            for (int r = 0; r < kItems; ++r) particle(std::false_type{}, op, cobs, t, r, m);
             publish_max(t, m);
             cur ^= 1;
             z_done = 0;                                 // s_z is free: it refills with step t + 1's normals

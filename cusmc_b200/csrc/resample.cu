@@ -405,6 +405,67 @@ __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, 
 // memory, no barrier, nothing between a warp's loads and its stores but its own arithmetic.
 constexpr int kPar = 4;
 static_assert(kTile % (32 * kPar) == 0, "a warp of the resampling pass must lie inside one tile");
+
+// The rounds of one warp.  FAST: all 32 kPar parents exist and the children are not clipped to a
+// sub-range (every filter step but a warp at the end of the cloud): no per-parent predicates.
+template <bool PEERS, bool FAST>
+__device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterConsts &c, const uint64_t (&C)[kPar],
+                                               uint64_t Cbelow, uint32_t i0, uint32_t lane)
+{
+    const uint64_t T = c.T, r0 = c.r0, Ng = p.N_global;
+    const double ng_over_t = c.ng_over_t, r0_over_t = c.r0_over_t;
+    // the offspring count is a pure function of the CDF value
+    uint32_t k[kPar];
+#pragma unroll
+    for (int r = 0; r < kPar; ++r)
+        k[r] = (FAST || i0 + 32 * r < p.N) ? (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t) : 0u;
+    uint32_t k_carry = 0;                              // count below the round's first parent (lane 0)
+    if (lane == 0) k_carry = (uint32_t)offspring_below(Cbelow, Ng, T, r0, ng_over_t, r0_over_t);
+#pragma unroll
+    for (int r = 0; r < kPar; ++r) {
+        const bool active = FAST || i0 + 32 * r < p.N;
+        uint32_t k_prev = __shfl_up_sync(0xffffffffu, k[r], 1);
+        if (lane == 0) k_prev = k_carry;
+        k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // used by lane 0 only; a full round is all active
+        // parents past the end own the empty range; their threads stay to help with large families
+        uint32_t a = FAST ? k_prev : (active ? max(k_prev, p.out_lo) : 0u);
+        const uint32_t b = FAST ? k[r] : (active ? min(k[r], p.out_hi) : 0u);
+        const uint32_t parent = p.j0 + i0 + 32 * r;
+        // small families (<= 8 children): the owning thread writes them, the warp running as many
+        // predicated store slots as its largest small family needs (a uniform trip count: two
+        // instructions per slot instead of a divergent six-instruction loop); large ones: the whole
+        // warp helps
+        const uint32_t n = b > a ? b - a : 0u;
+        const bool big = n > 8;
+        const uint32_t ns = big ? 0u : n;
+        const uint32_t slots = __reduce_max_sync(0xffffffffu, ns);
+        if constexpr (PEERS) {
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                if (q >= slots) break;
+                if (q < ns) put_ancestor<PEERS>(p, a + q, parent);
+            }
+        } else {
+            uint32_t *dst = p.anc_out + (a - p.out_lo);       // slot q: one compare, one store at dst + 4 q
+#pragma unroll
+            for (uint32_t q = 0; q < 8; ++q) {
+                if (q >= slots) break;
+                if (q < ns) dst[q] = parent;
+            }
+        }
+        unsigned bigmask = __ballot_sync(0xffffffffu, big);
+        while (bigmask) {
+            const int src = __ffs(bigmask) - 1;
+            bigmask &= bigmask - 1;
+            const uint32_t sa = __shfl_sync(0xffffffffu, a, src);
+            const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
+            const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
+#pragma unroll 1
+            for (uint32_t cc = sa + lane; cc < sb; cc += 32) put_ancestor<PEERS>(p, cc, sp);
+        }
+    }
+}
+
 template <bool PEERS>
 __global__ void __launch_bounds__(kThreads, 6)
 scan_resample_kernel(const ScanArgs p)
@@ -415,12 +476,13 @@ scan_resample_kernel(const ScanArgs p)
     const uint32_t i0 = w0 + lane;                                        // parents i0 + 32 r
     const uint32_t tile = w0 / kTile;                                     // a warp lies inside one tile
     const bool scatter = PEERS || p.anc_out;
+    const bool full = w0 + 32 * kPar <= p.N;
     // every load goes out before the first use
     const uint64_t prefix = __ldg(p.tile_prefix + tile);
     const uint64_t offset = p.cdf_offset ? __ldg(p.cdf_offset) : 0ull;
     uint64_t C[kPar], Cprev = 0;
 #pragma unroll
-    for (int r = 0; r < kPar; ++r) C[r] = i0 + 32 * r < p.N ? __ldg(p.local + i0 + 32 * r) : 0ull;
+    for (int r = 0; r < kPar; ++r) C[r] = (full || i0 + 32 * r < p.N) ? __ldg(p.local + i0 + 32 * r) : 0ull;
     if (scatter && lane == 0 && (w0 % kTile)) Cprev = __ldg(p.local + w0 - 1);
     ScatterConsts c{};
     if (scatter) {
@@ -440,51 +502,17 @@ scan_resample_kernel(const ScanArgs p)
     }
     if (!scatter) return;
     if (w0 == 0 && lane == 0 && p.resampled_out) *p.resampled_out = c.resample;
-    const uint64_t T = c.T;
-    if (T == 0) return;                               // degenerate: the host reports it
+    if (c.T == 0) return;                             // degenerate: the host reports it
     if (!c.resample) {                                // keep every particle: a_i = i
 #pragma unroll
         for (int r = 0; r < kPar; ++r)
             if (i0 + 32 * r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + 32 * r, p.j0 + i0 + 32 * r);
         return;
     }
-    const uint64_t r0 = c.r0;
-    const double ng_over_t = c.ng_over_t, r0_over_t = c.r0_over_t;
-    const uint64_t Ng = p.N_global;
-    // the offspring count is a pure function of the CDF value
-    uint32_t k[kPar];
-#pragma unroll
-    for (int r = 0; r < kPar; ++r)
-        k[r] = i0 + 32 * r < p.N ? (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t) : 0u;
-    uint32_t k_carry = 0;                              // count below the round's first parent (lane 0)
-    if (lane == 0) k_carry = (uint32_t)offspring_below(base + Cprev, Ng, T, r0, ng_over_t, r0_over_t);
-#pragma unroll
-    for (int r = 0; r < kPar; ++r) {
-        const bool active = i0 + 32 * r < p.N;
-        uint32_t k_prev = __shfl_up_sync(0xffffffffu, k[r], 1);
-        if (lane == 0) k_prev = k_carry;
-        k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // used by lane 0 only; a full round is all active
-        // parents past the end own the empty range; their threads stay to help with large families
-        uint32_t a = active ? max(k_prev, p.out_lo) : 0u;
-        const uint32_t b = active ? min(k[r], p.out_hi) : 0u;
-        const uint32_t parent = p.j0 + i0 + 32 * r;
-        // small families: the owning thread writes them; large ones: the whole warp helps
-        const bool big = b > a && b - a > 8;
-        if (!big) {
-#pragma unroll 1
-            for (; a < b; ++a) put_ancestor<PEERS>(p, a, parent);
-        }
-        unsigned bigmask = __ballot_sync(0xffffffffu, big);
-        while (bigmask) {
-            const int src = __ffs(bigmask) - 1;
-            bigmask &= bigmask - 1;
-            const uint32_t sa = __shfl_sync(0xffffffffu, a, src);
-            const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
-            const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
-#pragma unroll 1
-            for (uint32_t cc = sa + lane; cc < sb; cc += 32) put_ancestor<PEERS>(p, cc, sp);
-        }
-    }
+    if (full && p.out_lo == 0 && p.out_hi >= p.N_global)
+        scatter_rounds<PEERS, true>(p, c, C, base + Cprev, i0, lane);
+    else
+        scatter_rounds<PEERS, false>(p, c, C, base + Cprev, i0, lane);
 }
 
 // Multinomial: a[i] = j0 + #{ j : cdf_j <= p_i },  p_i = min((uint64)(u_i * T), T - 1).

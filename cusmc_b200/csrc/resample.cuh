@@ -77,16 +77,18 @@ __device__ __forceinline__ ScatterConsts make_scatter_consts(unsigned long long 
 __device__ __forceinline__ uint64_t offspring_below(uint64_t C, uint64_t Ng, uint64_t T, uint64_t r0,
                                                     double ng_over_t, double r0_over_t)
 {
-    // p = (C*Ng - r0) / T; the answer is ceil(p) for p > 0.  est is within 2^-19 of p (C, Ng/T and
+    // p = (C*Ng - r0) / T > -1; the answer is max(0, ceil(p)).  est is within 2^-19 of p (C, Ng/T and
     // r0/T each carry one rounding and p <= 2^32), so whenever est sits safely inside an open unit
-    // interval the answer is floor(est) + 1 and no 128-bit arithmetic is needed.  Only boundaries
-    // within 1e-4 of an integer (2e-4 of all cases) take the exact path below.
+    // interval (n, n + 1) the answer is n + 1 -- also for n = -1 -- and no 128-bit arithmetic is
+    // needed.  With t = est - 1/2 that interval test is |t - rint(t)| < 1/2 - 1e-4 and n = rint(t):
+    // one rounding, one subtraction, one compare.  Only boundaries within 1e-4 of an integer (2e-4 of
+    // all cases) take the exact path below.
     const double est = fma((double)C, ng_over_t, -r0_over_t);
-    const double fl = floor(est);
-    const double frac = est - fl;
-    if (est > 1e-4 && frac > 1e-4 && frac < 1.0 - 1e-4) {
-        const uint64_t kf = (uint64_t)fl + 1;
-        return kf > Ng ? Ng : kf;
+    const double t = est - 0.5;
+    const double n = rint(t);
+    if (fabs(t - n) < 0.5 - 1e-4) {
+        const uint32_t kf = __double2uint_rz(n + 1.0);       // saturates at 2^32 - 1 >= Ng
+        return kf > (uint32_t)Ng ? Ng : (uint64_t)kf;
     }
     const uint64_t rhs_lo = C * Ng, rhs_hi = __umul64hi(C, Ng);
     uint64_t k = est <= 0.0 ? 0 : (est >= (double)Ng ? Ng : (uint64_t)est);
