@@ -338,10 +338,13 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
         N, d, T = 10000, 2, 1000
         kw = dict(m0=np.zeros(2), C0=I2, F=I2, G=I2, V=0.1 * I2, W=0.1 * I2)
         cusmc_b200.run(N, d, 50, Y, df=0.0, resampler="metropolis", distribution="mvn", seed=1, **kw)   # warm-up
-        t0 = time.perf_counter()
-        res = cusmc_b200.run(N, d, T, Y, df=0.0, resampler="metropolis", distribution="mvn", seed=1, **kw)
-        ours_s = time.perf_counter() - t0
-        entry = {"ours_seconds": ours_s, "N": N, "d": d, "T": T, "resampler": "metropolis (B = 10)",
+        runs = []
+        for _ in range(3):
+            t0 = time.perf_counter()
+            res = cusmc_b200.run(N, d, T, Y, df=0.0, resampler="metropolis", distribution="mvn", seed=1, **kw)
+            runs.append(time.perf_counter() - t0)
+        ours_s = min(runs)
+        entry = {"ours_seconds": ours_s, "ours_seconds_all": runs, "N": N, "d": d, "T": T, "resampler": "metropolis (B = 10)",
                  "particle_steps_per_sec": N * (T - 1) / ours_s,
                  "path": "cusmc_b200.run -> cusmc_run (host in, full history out: %.0f MB)"
                          % ((res["weights"].nbytes + res["posterior_x"].nbytes) / 1e6)}

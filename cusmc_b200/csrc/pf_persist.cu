@@ -407,10 +407,16 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                     uint32_t lo = k_prev;
                     const uint32_t hi = k[r];
                     const uint32_t parent = tile0 + kItems * tid + r;      // (beyond the tile: zero weight, no children)
-                    const bool big = hi > lo && hi - lo > 8;
-                    if (!big) {
-#pragma unroll 1
-                        for (; lo < hi; ++lo) a.anc[lo] = parent;
+                    const uint32_t n = hi > lo ? hi - lo : 0u;
+                    const bool big = n > 8;
+                    const uint32_t ns = big ? 0u : n;
+                    // small families: predicated store slots, as many as the warp's largest needs
+                    const uint32_t slots = __reduce_max_sync(0xffffffffu, ns);
+                    uint32_t *dst = a.anc + lo;
+#pragma unroll
+                    for (uint32_t q = 0; q < 8; ++q) {
+                        if (q >= slots) break;
+                        if (q < ns) dst[q] = parent;
                     }
                     unsigned bigmask = __ballot_sync(0xffffffffu, big);
                     while (bigmask) {
