@@ -421,12 +421,14 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
         k[r] = (FAST || i0 + 32 * r < p.N) ? (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t) : 0u;
     uint32_t k_carry = 0;                              // count below the round's first parent (lane 0)
     if (lane == 0) k_carry = (uint32_t)offspring_below(Cbelow, Ng, T, r0, ng_over_t, r0_over_t);
+    const uint32_t my_lo = PEERS ? p.rank * p.per_rank.d : 0u, my_hi = my_lo + (PEERS ? p.per_rank.d : 0u);   // this rank's child slots
 #pragma unroll
     for (int r = 0; r < kPar; ++r) {
         const bool active = FAST || i0 + 32 * r < p.N;
         uint32_t k_prev = __shfl_up_sync(0xffffffffu, k[r], 1);
+        const uint32_t round_lo = __shfl_sync(0xffffffffu, k_carry, 0);   // the round's children: [round_lo, k_carry')
         if (lane == 0) k_prev = k_carry;
-        k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // used by lane 0 only; a full round is all active
+        k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // lane 0 uses it as the next round's k_prev; a full round is all active
         // parents past the end own the empty range; their threads stay to help with large families
         uint32_t a = FAST ? k_prev : (active ? max(k_prev, p.out_lo) : 0u);
         const uint32_t b = FAST ? k[r] : (active ? min(k[r], p.out_hi) : 0u);
@@ -439,14 +441,17 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
         const bool big = n > 8;
         const uint32_t ns = big ? 0u : n;
         const uint32_t slots = __reduce_max_sync(0xffffffffu, ns);
-        if constexpr (PEERS) {
+        // (lane 31 may be past the end in the cloud's last warp: the round's upper end is the largest b)
+        if (PEERS && !(round_lo >= my_lo && __reduce_max_sync(0xffffffffu, b) <= my_hi)) {
+            // some child of this round lives on another rank: slot -> rank division per child
 #pragma unroll
             for (uint32_t q = 0; q < 8; ++q) {
                 if (q >= slots) break;
                 if (q < ns) put_ancestor<PEERS>(p, a + q, parent);
             }
         } else {
-            uint32_t *dst = p.anc_out + (a - p.out_lo);       // slot q: one compare, one store at dst + 4 q
+            // all children local (almost every round: shards hold about their share of the mass)
+            uint32_t *dst = p.anc_out + (a - (PEERS ? my_lo : p.out_lo));   // slot q: one compare, one store at dst + 4 q
 #pragma unroll
             for (uint32_t q = 0; q < 8; ++q) {
                 if (q >= slots) break;
