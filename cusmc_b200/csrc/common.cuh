@@ -122,6 +122,9 @@ inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
 int cusmc_scratch(cusmc_ctx *ctx, int slot, size_t bytes, void **out);
 int cusmc_pinned(cusmc_ctx *ctx, size_t bytes, void **out);
 int cusmc_aux_stream(cusmc_ctx *ctx);
+// Large device -> pageable-host copy: pinned double-buffered staging, the host side of every chunk
+// copied (and first-touched) by several threads while the next chunk is in flight.  Synchronous.
+int cusmc_d2h_staged(cusmc_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
 // ---- device helpers ----------------------------------------------------------------
 // Streaming (read-once / write-once) accesses: keep them out of L1 and mark evict-first.

@@ -6,7 +6,10 @@
 // (src/mvn_dist.cu.cpp:231-240,305-314,788) -- none of that survives here.
 #include "common.cuh"
 
+#include <algorithm>
 #include <new>
+#include <thread>
+#include <vector>
 
 extern "C" int cusmc_version(void) { return CUSMC_VERSION; }
 
@@ -118,4 +121,55 @@ int cusmc_pinned(cusmc_ctx *ctx, size_t bytes, void **out)
     }
     *out = ctx->pinned;
     return CUSMC_OK;
+}
+
+// A plain cudaMemcpy into pageable memory runs at ~4 GB/s when the destination has never been
+// touched (the R / numpy result arrays of run(): 240 MB for the C1 model): the driver's staging copy
+// is single-threaded and takes every page fault itself.  Here the device side streams into two
+// pinned 16 MiB slots at PCIe speed and up to 8 host threads copy a finished slot out in parallel.
+int cusmc_d2h_staged(cusmc_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes)
+{
+    constexpr size_t kSlot = (size_t)16 << 20;
+    if (bytes == 0) return CUSMC_OK;
+    if (bytes < kSlot / 4) {
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return CUSMC_OK;
+    }
+    void *pin = nullptr;
+    CUSMC_CHECK(cusmc_pinned(ctx, 2 * kSlot, &pin));
+    cudaEvent_t done[2] = {nullptr, nullptr};
+    for (auto &e : done) CUSMC_CUDA(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int workers = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+    const size_t chunks = (bytes + kSlot - 1) / kSlot;
+    auto issue = [&](size_t c) {
+        const size_t off = c * kSlot, n = std::min(kSlot, bytes - off);
+        cudaMemcpyAsync((char *)pin + (c & 1) * kSlot, (const char *)src_dev + off, n, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaEventRecord(done[c & 1], ctx->stream);
+    };
+    issue(0);
+    int rc = CUSMC_OK;
+    for (size_t c = 0; c < chunks; ++c) {
+        const size_t off = c * kSlot, n = std::min(kSlot, bytes - off);
+        if (cudaEventSynchronize(done[c & 1]) != cudaSuccess) {
+            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "staged device-to-host copy failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (c + 1 < chunks) issue(c + 1);                 // the other slot: drained one iteration ago
+        const char *src = (const char *)pin + (c & 1) * kSlot;
+        char *dst = (char *)dst_host + off;
+        const size_t part = ((n + workers - 1) / workers + 4095) & ~(size_t)4095;
+        std::vector<std::thread> pool;
+        for (int w = 1; w < workers; ++w) {
+            const size_t lo = (size_t)w * part;
+            if (lo >= n) break;
+            pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, std::min(part, n - lo)); });
+        }
+        std::memcpy(dst, src, std::min(part, n));
+        for (auto &t : pool) t.join();
+    }
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &e : done) cudaEventDestroy(e);
+    return rc;
 }

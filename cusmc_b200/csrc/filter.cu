@@ -989,10 +989,10 @@ extern "C" int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *
     CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history, "history was not kept");
     const size_t TN = (size_t)f->cfg.T * (size_t)f->n;   // this rank's shard
     CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (x_aos) CUSMC_CUDA(ctx, cudaMemcpy(x_aos, f->hist_x, sizeof(double) * TN * f->cfg.d, cudaMemcpyDeviceToHost));
-    if (w) CUSMC_CUDA(ctx, cudaMemcpy(w, f->hist_w, sizeof(double) * TN, cudaMemcpyDeviceToHost));
+    if (x_aos) CUSMC_CHECK(cusmc_d2h_staged(ctx, x_aos, f->hist_x, sizeof(double) * TN * f->cfg.d));
+    if (w) CUSMC_CHECK(cusmc_d2h_staged(ctx, w, f->hist_w, sizeof(double) * TN));
     if (a) {
-        CUSMC_CUDA(ctx, cudaMemcpy(a, f->hist_a, sizeof(uint32_t) * TN, cudaMemcpyDeviceToHost));
+        CUSMC_CHECK(cusmc_d2h_staged(ctx, a, f->hist_a, sizeof(uint32_t) * TN));
         for (int64_t i = 0; i < f->n; ++i) a[i] = (uint32_t)(f->lo + i);   // row t = 0: identity
     }
     return CUSMC_OK;
