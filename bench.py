@@ -410,6 +410,40 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
             "value_nccl_exchange": N * (T - 1) / (res["nccl"] * 1e-3)}
     except Exception as e:
         out["pf_c5_sharded_particle_steps_per_sec"] = {"error": repr(e)}
+    try:
+        # C3 over the ranks: the 65 536 chains are independent, each rank advances its contiguous share
+        # (strong scaling, no data-path collective); one all-reduce of the posterior moments at the end
+        Cn_all, d, steps = 65536, 32, (50 if quick else 200)
+        Cn = Cn_all // world
+        rank = dist.get_rank()
+        g = torch.Generator(device="cuda").manual_seed(77 + rank)
+        A = torch.randn((Cn, d, d), dtype=torch.float64, device="cuda", generator=g)
+        L = torch.linalg.cholesky(A @ A.transpose(1, 2) / d + torch.eye(d, dtype=torch.float64, device="cuda"))
+        Lcm = L.transpose(1, 2).contiguous()
+        mu = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+        x = (L @ torch.randn((Cn, d, 1), dtype=torch.float64, device="cuda", generator=g)).squeeze(-1).contiguous()
+        del A, L
+        nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+        ctx.use_torch_stream()
+        ctx.mh_chains_dev("mvt", mu, Lcm, x, 5, 0.3, nu=5.0, seed=3 + rank, n_accept=nacc)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=40 + rank, n_accept=nacc)
+        mom = torch.cat([x.sum(0), (x * x).sum(0)])
+        dist.all_reduce(mom)                                   # the final moment reduction (2 d doubles)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        out["mh_c3_sharded_chain_steps_per_sec"] = {
+            "value": Cn * world * steps / (ms * 1e-3), "chains": Cn * world, "chains_per_gpu": Cn, "n_gpus": world,
+            "d": d, "steps": steps, "ms": ms, "scaling": "strong", "target": "mvt nu=5 per-chain L",
+            "noise": "philox in-kernel", "includes": "all-reduce of the 2 d posterior moment sums"}
+    except Exception as e:
+        out["mh_c3_sharded_chain_steps_per_sec"] = {"error": repr(e)}
     return out
 
 
