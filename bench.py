@@ -426,6 +426,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
         ctx.use_torch_stream()
         ctx.mh_chains_dev("mvt", mu, Lcm, x, 5, 0.3, nu=5.0, seed=3 + rank, n_accept=nacc)
+        dist.all_reduce(torch.cat([x.sum(0), (x * x).sum(0)]))   # warm-up of the reduction too
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
