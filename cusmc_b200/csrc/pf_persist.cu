@@ -5,11 +5,12 @@
 // latency of its dependent ~9 us kernels.  A step has three grid-wide dependencies
 //     max of the log-weights  ->  total fixed-point mass  ->  ancestors scattered to the children
 // and here they are three grid barriers inside a persistent kernel instead of kernel boundaries:
-// one block of 512 threads per tile of 4096 particles, three blocks per SM, and everything a tile
-// carries from one phase to the next (log-weights, tile-local CDF) stays in shared memory --
-// neither the log-weights nor the weight image are ever re-read from global memory.  (A first
-// version kept them in registers, 16 particles per thread: 3.3 resident warps per scheduler,
-// latency-bound, slower than the four launches.)
+// two blocks of 512 threads per SM, the cloud spread evenly over all of them (a tile of <= 4096
+// particles per block), and everything a tile carries from one phase to the next (log-weights,
+// tile-local CDF) stays in shared memory -- neither the log-weights nor the weight image are ever
+// re-read from global memory.  (A first version kept them in registers, 16 particles per thread: 3.3
+// resident warps per scheduler, latency-bound, slower than the four launches.)  Between its arrival
+// at a barrier and the last block's, a block draws the next step's normals (pregen_noise below).
 //
 //   scatter(t) :  C_j = prefix(tile sums of t-1) + c_j  ->  children [k(C_{j-1}), k(C_j)) get ancestor j
 //   ---- grid barrier ----

@@ -1,7 +1,10 @@
-# scratch driver for A/B timing runs on the GPU box (gpurun -- bash profiles/run_ab.sh)
+# A/B timing of kernel-variant builds on the GPU box:
+#   make -C cusmc_b200/csrc VARIANT=x EXTRA=-DSOME_MACRO=1        (builds cusmc_b200/libcusmc_b200_x.so)
+#   gpurun -- 'VARIANTS="_x" WHICH="c4 1000" bash profiles/run_ab.sh'
+# "" is the default build.  Results: gpurun_out/pfb_$TAG.log
 set -x; mkdir -p gpurun_out
-TAG=${TAG:-s4i}
-python -m pytest tests -m gpu -x -q > gpurun_out/pytest_gpu_$TAG.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$TAG.log
-for i in 1 2; do python profiles/pf_breakdown.py c5 41; done > gpurun_out/pfb_$TAG.log 2>&1
-for i in 1 2; do python profiles/pf_breakdown.py c4 1000; done >> gpurun_out/pfb_$TAG.log 2>&1
-tail -3 gpurun_out/pytest_gpu_$TAG.log; cat gpurun_out/pfb_$TAG.log
+TAG=${TAG:-ab}
+for v in "" ${VARIANTS:-}; do
+  for i in 1 2; do echo "variant '$v'"; CUSMC_B200_LIB=$PWD/cusmc_b200/libcusmc_b200$v.so python profiles/pf_breakdown.py ${WHICH:-c5 41}; done
+done > gpurun_out/pfb_$TAG.log 2>&1
+cat gpurun_out/pfb_$TAG.log
