@@ -91,7 +91,10 @@ static __device__ __noinline__ void chi_pair(uint64_t seed, uint64_t step, uint6
     *chi1 = sqrtf(nu / (2.0f * g[1]));
 }
 
-constexpr int min_blocks(int D, bool diag) { return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? 3 : 4)); }
+#ifndef CUSMC_STEP_MINB8
+#define CUSMC_STEP_MINB8 5
+#endif
+constexpr int min_blocks(int D, bool diag) { return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag ? CUSMC_STEP_MINB8 : 3) : 4)); }
 
 // MVT is a template flag so the MVN kernel carries neither the chi branch nor the call to the
 // (rejection-loop) chi-square sampler, whose calling convention alone costs ~30 registers.

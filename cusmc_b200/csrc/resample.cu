@@ -165,8 +165,14 @@ __device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v
 }
 
 // FULL: also sum of squares and positive count (ESS); otherwise only what resampling needs.
+#ifndef CUSMC_WEIGH_MINB
+#define CUSMC_WEIGH_MINB 6
+#endif
+#ifndef CUSMC_SCAN_MINB
+#define CUSMC_SCAN_MINB 8
+#endif
 template <bool FULL, bool LOG>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, LOG ? CUSMC_WEIGH_MINB : 4)
 weigh_kernel(const double *__restrict__ w, const double *__restrict__ wmax_p, int64_t N,
              int shift, unsigned long long *__restrict__ image)
 {
@@ -472,7 +478,7 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
 }
 
 template <bool PEERS>
-__global__ void __launch_bounds__(kThreads, 6)
+__global__ void __launch_bounds__(kThreads, CUSMC_SCAN_MINB)
 scan_resample_kernel(const ScanArgs p)
 {
     const uint32_t lane = threadIdx.x & 31;

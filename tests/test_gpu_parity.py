@@ -348,6 +348,16 @@ def test_systematic_properties_large(ctx):
     assert np.all(np.abs(counts - expect) < 1.0 + 1e-6)   # systematic: floor or ceil of N w / sum w
 
 
+@pytest.mark.parametrize("N", [1 << 20, 1000003])
+def test_systematic_equal_weights_is_the_identity(ctx, N):
+    """Equal weights put EVERY offspring boundary on (or within rounding of) an integer -- the case the
+    floating estimate of the scatter pass must hand to its exact 128-bit path: a_i = i for any offset."""
+    w = np.full(N, 0.125)
+    for u0 in (0.0, 1e-12, 0.5, 1.0 - 1e-12):
+        a = ctx.resample_systematic(w, u0)
+        assert np.array_equal(a, np.arange(N, dtype=np.uint32)), u0
+
+
 def test_resample_degenerate_is_an_error(ctx):
     import cusmc_b200
     with pytest.raises(cusmc_b200.CusmcError) as e:
