@@ -94,12 +94,18 @@ static __device__ __noinline__ void chi_pair(uint64_t seed, uint64_t step, uint6
 #ifndef CUSMC_STEP_MINB8
 #define CUSMC_STEP_MINB8 5
 #endif
-constexpr int min_blocks(int D, bool diag) { return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag ? CUSMC_STEP_MINB8 : 3) : 4)); }
+// d = 8, diagonal model, Normal noise (the C5 configuration): 48 registers hold the kernel without a
+// spill, 5 blocks per SM instead of 4 took the step from 212 to 203 us; at 6 blocks (40 registers) it
+// spills its store addresses and is back at 212 us
+constexpr int min_blocks(int D, bool diag, bool mvt)
+{
+    return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_STEP_MINB8 : 3) : 4));
+}
 
 // MVT is a template flag so the MVN kernel carries neither the chi branch nor the call to the
 // (rejection-loop) chi-square sampler, whose calling convention alone costs ~30 registers.
 template <int D, bool PHILOX, bool MVT, bool EXACT, bool DIAG>
-__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG))
+__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
 pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const StepArgs a)
 {
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
@@ -133,16 +139,27 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
 #pragma unroll
             for (int j = 0; j < D; ++j) xp[j] = 0.0;
         }
+        // DIAG: component k needs only its own normal, so the draws stay in single precision (half the
+        // registers) until the one FMA that consumes them
+        constexpr bool kFloatNoise = PHILOX && DIAG;
+        float zf[kFloatNoise ? D : 1];
         if (PHILOX) {
             // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
 #pragma unroll
             for (int jq = 0; jq < (D + 3) / 4; ++jq) {
-                double zq[4] = {0.0, 0.0, 0.0, 0.0};
-                if (EXACT || 4 * jq < d)
-                    cusmc_normal4(jq == 0 ? r0 : cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq), zq);
+                float zq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+                if (EXACT || 4 * jq < d) {
+                    const cusmc_u32x4 rq = jq == 0 ? r0 : cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq);
+                    cusmc_box_muller_f32(rq.v[0], rq.v[1], &zq[0], &zq[1]);
+                    cusmc_box_muller_f32(rq.v[2], rq.v[3], &zq[2], &zq[3]);
+                }
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
-                    if (4 * jq + e < D) z[4 * jq + e] = (EXACT || 4 * jq + e < d) ? zq[e] : 0.0;
+                    if (4 * jq + e < D) {
+                        const float v = (EXACT || 4 * jq + e < d) ? zq[e] : 0.0f;
+                        if constexpr (kFloatNoise) zf[4 * jq + e] = v;
+                        else z[4 * jq + e] = (double)v;
+                    }
             }
         } else {
             const double *src = a.xi + i;
@@ -164,7 +181,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             double g = op.mu[k], s = 0.0;
             if constexpr (DIAG) {
                 g = fma(op.G[k], xp[k], g);
-                s = fma(op.Q[k], z[k], s);
+                s = fma(op.Q[k], kFloatNoise ? (double)zf[kFloatNoise ? k : 0] : z[k], s);
             } else {
 #pragma unroll
                 for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
@@ -174,7 +191,12 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             if (MVT && (EXACT || k < d))
                 s = (a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i) : chi[MVT ? k : 0]) * s;
             xn[k] = s + g;
-            if (EXACT || k < d) st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
+            if (EXACT || k < d) {
+                st_stream(dst_x + (int64_t)k * dst_ld, xn[k]);
+                // the history row goes out here too: stores keep their order, and one issued after the
+                // weight would pin every xn[k] in a register until the end of the kernel
+                if (a.hist_x) st_stream(a.hist_x + i * d + k, xn[k]);
+            }
         }
         if (a.skip_weight) {
             lw = a.const_weight;
@@ -195,11 +217,6 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             if (a.resampled && *a.resampled == 0) lw = *dst_lw + lw;   // no resampling: weights accumulate
         }
         st_stream(dst_lw, lw);
-        if (a.hist_x) {
-#pragma unroll
-            for (int k = 0; k < D; ++k)
-                if (EXACT || k < d) st_stream(a.hist_x + i * d + k, xn[k]);
-        }
         if (a.hist_w) st_stream(a.hist_w + i, lw);
         if (a.hist_a) a.hist_a[i] = (uint32_t)(parent + a.parent_base);
     }
