@@ -23,21 +23,6 @@ namespace {
 
 constexpr int kWarpsPerBlock = 4;
 
-// Forward substitution, column oriented.  On entry lane k holds r_k; row[j] = L[k][j] (0 for
-// j > k or outside d), rinv = 1 / L[k][k] (0 outside d).  Returns q = sum_k v_k^2 in every lane.
-template <int D>
-__device__ __forceinline__ double whiten_q(const double (&row)[D], double rinv, double r)
-{
-    double q = 0.0;
-#pragma unroll
-    for (int j = 0; j < D; ++j) {
-        const double vj = __shfl_sync(0xffffffffu, r * rinv, j);
-        q = fma(vj, vj, q);
-        r = fma(-row[j], vj, r);   // no-op for lanes k < j (row[j] == 0); lane j is done with r
-    }
-    return q;
-}
-
 struct ChainArgs {
     const double *mu, *L, *z, *thr;
     double *x, *sum_x, *sum_xx;
@@ -230,20 +215,31 @@ struct PerPointArgs {
     int d, use_tma;
 };
 
+// A warp serves G = 32 / D consecutive points per iteration, D lanes each (D = d padded to a power
+// of two): at d = 8 four points, so no lane idles and the warp's loads of x / mu are one contiguous
+// line.  The G packed factors are contiguous too (point-major): ONE 1-D TMA bulk copy per iteration
+// stages them, double buffered, completing on the warp's mbarrier.  d = 32: rows are read from
+// shared memory as the substitution needs them instead of being copied to 64 registers first -- 80
+// registers instead of 108, and shared memory (6 blocks of 4 warps), not the register file, sets the
+// residency: 544 -> 482 us for 2^19 points = 0.79 of the HBM roofline.
 template <int D>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 perpoint_kernel(const PerPointArgs a, const Epilogue ep, const double lognorm_base)
 {
-    constexpr int kPacked = D * (D + 1) / 2;
-    __shared__ __align__(128) double s_L[kWarpsPerBlock][2][kPacked + (kPacked & 1)];
+    constexpr int G = 32 / D;                        // points per warp and iteration
+    constexpr int kPackedMax = D * (D + 1) / 2;
+    constexpr int kBuf = G * kPackedMax + ((G * kPackedMax) & 1);
+    constexpr bool kRowsInSmem = D >= 32;
+    __shared__ __align__(128) double s_L[kWarpsPerBlock][2][kBuf];
     __shared__ __align__(8) uint64_t s_bar[kWarpsPerBlock][2];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / D, sub = lane % D;        // point within the iteration, component
     const int d = a.d;
     const int packed = d * (d + 1) / 2;
-    const uint32_t bytes = (uint32_t)(packed * sizeof(double));
     const int64_t n_warps = (int64_t)gridDim.x * kWarpsPerBlock;
-    const int64_t w0 = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
-    const bool live = lane < d;
+    const int64_t w0 = ((int64_t)blockIdx.x * kWarpsPerBlock + wib) * G;   // first point of the warp's first iteration
+    const int64_t stride = n_warps * G;
+    const bool comp = sub < d;
 
     if (a.use_tma && lane == 0) {
         mbar_init(&s_bar[wib][0], 1);
@@ -251,36 +247,41 @@ perpoint_kernel(const PerPointArgs a, const Epilogue ep, const double lognorm_ba
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncwarp();
-    auto issue = [&](int64_t pt, int buf) {
+    auto issue = [&](int64_t pt0, int buf) {
+        const int64_t left = a.N - pt0;
+        const int n_pts = left < G ? (int)left : G;
         if (a.use_tma) {
             if (lane == 0) {
+                const uint32_t bytes = (uint32_t)(n_pts * packed * sizeof(double));
                 mbar_expect_tx(&s_bar[wib][buf], bytes);
-                tma_load_1d(&s_L[wib][buf][0], a.L + (size_t)pt * packed, bytes, &s_bar[wib][buf]);
+                tma_load_1d(&s_L[wib][buf][0], a.L + (size_t)pt0 * packed, bytes, &s_bar[wib][buf]);
             }
         } else {
-            const double *src = a.L + (size_t)pt * packed;
-            for (int e = lane; e < packed; e += 32) s_L[wib][buf][e] = ld_stream(src + e);
+            const double *src = a.L + (size_t)pt0 * packed;
+            for (int e = lane; e < n_pts * packed; e += 32) s_L[wib][buf][e] = ld_stream(src + e);
         }
     };
     // the point and its mean are prefetched one iteration ahead as well (registers): without it every
     // iteration started by waiting a full memory latency on them (the kernel's top stall site)
-    auto load_x = [&](int64_t pt) { return live ? ld_stream(a.x + (size_t)pt * d + lane) : 0.0; };
-    auto load_m = [&](int64_t pt) { return (live && a.mu) ? ld_stream(a.mu + (size_t)pt * d + lane) : 0.0; };
+    auto load_x = [&](int64_t pt) { return (comp && pt < a.N) ? ld_stream(a.x + (size_t)pt * d + sub) : 0.0; };
+    auto load_m = [&](int64_t pt) { return (comp && pt < a.N && a.mu) ? ld_stream(a.mu + (size_t)pt * d + sub) : 0.0; };
     double x_next = 0.0, m_next = 0.0;
     if (w0 < a.N) {
         issue(w0, 0);
-        x_next = load_x(w0);
-        m_next = load_m(w0);
+        x_next = load_x(w0 + grp);
+        m_next = load_m(w0 + grp);
     }
     uint32_t phase[2] = {0, 0};
     int buf = 0;
-    for (int64_t pt = w0; pt < a.N; pt += n_warps, buf ^= 1) {
-        const int64_t nxt = pt + n_warps;
+    for (int64_t pt0 = w0; pt0 < a.N; pt0 += stride, buf ^= 1) {
+        const int64_t nxt = pt0 + stride;
+        const int64_t pt = pt0 + grp;
+        const bool live = comp && pt < a.N;
         const double x_cur = x_next, m_cur = m_next;
         if (nxt < a.N) {
-            issue(nxt, buf ^ 1);                     // prefetch the next factor
-            x_next = load_x(nxt);
-            m_next = load_m(nxt);
+            issue(nxt, buf ^ 1);                     // prefetch the next factors
+            x_next = load_x(nxt + grp);
+            m_next = load_m(nxt + grp);
         }
         double r = x_cur - m_cur;
         if (a.use_tma) {
@@ -289,19 +290,38 @@ perpoint_kernel(const PerPointArgs a, const Epilogue ep, const double lognorm_ba
         } else {
             __syncwarp();
         }
-        double row[D];
-        const int off = lane * (lane + 1) / 2;
-#pragma unroll
-        for (int j = 0; j < D; ++j) row[j] = (live && j <= lane) ? s_L[wib][buf][off + j] : 0.0;
-        const double diag = live ? s_L[wib][buf][off + lane] : 1.0;
-        __syncwarp();                                 // everyone has read the buffer before it is refilled
+        const double *rowp = &s_L[wib][buf][grp * packed + sub * (sub + 1) / 2];
+        const double diag = live ? rowp[sub] : 1.0;
         const double rinv = live ? 1.0 / diag : 0.0;
-        const double q = whiten_q<D>(row, rinv, r);
+        // forward substitution, column oriented, inside the point's D lanes: lane k holds r_k; step j
+        // broadcasts v_j = r_j / L_jj and every lane k > j subtracts L_kj v_j
+        double q = 0.0;
+        if constexpr (kRowsInSmem) {
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const double vj = __shfl_sync(0xffffffffu, r * rinv, j, D);
+                q = fma(vj, vj, q);
+                const double lkj = (live && j <= sub) ? rowp[j] : 0.0;
+                r = fma(-lkj, vj, r);
+            }
+            __syncwarp();                             // everyone has read the buffer before it is refilled
+        } else {
+            double row[D];
+#pragma unroll
+            for (int j = 0; j < D; ++j) row[j] = (live && j <= sub) ? rowp[j] : 0.0;
+            __syncwarp();                             // everyone has read the buffer before it is refilled
+#pragma unroll
+            for (int j = 0; j < D; ++j) {
+                const double vj = __shfl_sync(0xffffffffu, r * rinv, j, D);
+                q = fma(vj, vj, q);
+                r = fma(-row[j], vj, r);              // no-op for lanes k < j (row[j] == 0); lane j is done with r
+            }
+        }
         // log det Sigma = 2 sum log L_kk
         double ld = live ? log(diag) : 0.0;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
-        if (lane == 0) {
+        for (int o = D / 2; o > 0; o >>= 1) ld += __shfl_xor_sync(0xffffffffu, ld, o);
+        if (sub == 0 && pt < a.N) {
             Epilogue e2 = ep;
             e2.lognorm = lognorm_base - ld;           // lognorm_base excludes -1/2 log det
             e2.scale = exp(e2.lognorm);
@@ -383,8 +403,20 @@ extern "C" int cusmc_logpdf_perpoint_dev(cusmc_ctx *ctx, int kind, int want_log,
     a.x = x_dev; a.mu = mu_dev; a.L = L_dev; a.out = out_dev; a.N = N; a.d = d;
     const size_t bytes = sizeof(double) * (size_t)d * (d + 1) / 2;
     a.use_tma = (bytes % 16 == 0) && ((uintptr_t)L_dev % 16 == 0);
-    int64_t grid = (N + kWarpsPerBlock - 1) / kWarpsPerBlock;
-    const int64_t cap = (int64_t)ctx->sm_count * 8;
+    const int per_warp = 32 / cusmc_pad_dim(d);        // points per warp and iteration
+    int64_t grid = (N + (int64_t)kWarpsPerBlock * per_warp - 1) / ((int64_t)kWarpsPerBlock * per_warp);
+    // one wave of resident blocks (every warp strides over the points)
+    int per_sm = 0;
+    const void *fn = nullptr;
+    switch (cusmc_pad_dim(d)) {
+        case 2: fn = (const void *)perpoint_kernel<2>; break;
+        case 4: fn = (const void *)perpoint_kernel<4>; break;
+        case 8: fn = (const void *)perpoint_kernel<8>; break;
+        case 16: fn = (const void *)perpoint_kernel<16>; break;
+        default: fn = (const void *)perpoint_kernel<32>; break;
+    }
+    CUSMC_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kWarpsPerBlock * 32, 0));
+    const int64_t cap = (int64_t)ctx->sm_count * (per_sm > 0 ? per_sm : 4);
     if (grid > cap) grid = cap;
     switch (cusmc_pad_dim(d)) {
         case 2: perpoint_kernel<2><<<(unsigned)grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a, ep, base); break;
