@@ -161,12 +161,20 @@ int cusmc_d2h_staged(cusmc_ctx *ctx, void *dst_host, const void *src_dev, size_t
         char *dst = (char *)dst_host + off;
         const size_t part = ((n + workers - 1) / workers + 4095) & ~(size_t)4095;
         std::vector<std::thread> pool;
-        for (int w = 1; w < workers; ++w) {
-            const size_t lo = (size_t)w * part;
-            if (lo >= n) break;
-            pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, std::min(part, n - lo)); });
+        size_t done_to = std::min(part, n);              // [0, part) is this thread's; helpers take the rest
+        try {                                            // nothing may unwind across the C ABI
+            pool.reserve(workers);
+            for (int w = 1; w < workers; ++w) {
+                const size_t lo = (size_t)w * part;
+                if (lo >= n) break;
+                pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, std::min(part, n - lo)); });
+                done_to = std::min(lo + part, n);
+            }
+        } catch (...) {
+            // no more threads to be had: this thread copies what has not been handed out
         }
         std::memcpy(dst, src, std::min(part, n));
+        if (done_to < n) std::memcpy(dst + done_to, src + done_to, n - done_to);
         for (auto &t : pool) t.join();
     }
     cudaStreamSynchronize(ctx->stream);
