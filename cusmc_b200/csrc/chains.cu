@@ -34,40 +34,51 @@ struct ChainArgs {
     int d, steps, kind, shared;
 };
 
-// Sum over the warp's 32 lanes by xor butterflies (16, 8, 4, 2, 1): every lane ends with the same
-// bits, and a host reproduces them with the same pairing (oracle: butterfly32).
-__device__ __forceinline__ double warp_sum_butterfly(double v)
+// Sum over the W lanes of a chain by xor butterflies (W/2, ..., 2, 1): every lane of the chain ends
+// with the same bits.  Lanes that hold no component contribute +0, so the value equals the 32-lane
+// butterfly (16, 8, 4, 2, 1) a host reproduces with the same pairing (oracle: butterfly32).
+template <int W>
+__device__ __forceinline__ double chain_sum_butterfly(double v)
 {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
 
 // The chain runs in WHITENED coordinates.  The proposal x' = x + s L z uses the target's own factor,
 // so with v = L^-1 (x - mu) it is simply v' = v + s z and the target's quadratic form is |v'|^2:
-// a step is one FMA and one warp sum -- no mat-vec, no forward substitution, and the factor is
-// needed only to whiten the start, to un-whiten the result and (MOMENTS) for the running sums of x,
-// so the step loop does not keep it in registers.  Same law as the x-space chain, a fraction of
-// the work; the oracle (orc_mh_chains) restates exactly this arithmetic.
+// a step is one FMA and one sum over the chain's lanes -- no mat-vec, no forward substitution, and
+// the factor is needed only to whiten the start, to un-whiten the result and (MOMENTS) for the
+// running sums of x, so the step loop does not keep it in registers.  Same law as the x-space
+// chain, a fraction of the work; the oracle (orc_mh_chains) restates exactly this arithmetic.
+//
+// A chain owns W = max(D, 4) lanes (D = d padded to a power of two; a quad at least, because four
+// lanes share a Philox block of normals), a warp G = 32 / W chains: at d = 8 four chains advance in
+// the instruction stream one used to take, and no lane idles.
 template <int D, bool PHILOX, bool MOMENTS>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mh_chains_kernel(const ChainArgs a)
 {
+    constexpr int W = D < 4 ? 4 : D;                 // lanes per chain
+    constexpr int G = 32 / W;                        // chains per warp
     __shared__ __align__(16) double s_v[kWarpsPerBlock][32];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-    const int64_t c = (int64_t)blockIdx.x * kWarpsPerBlock + wib;
-    if (c >= a.C) return;
+    const int grp = lane / W, sub = lane % W;
+    const int64_t c0 = ((int64_t)blockIdx.x * kWarpsPerBlock + wib) * G;
+    if (c0 >= a.C) return;                           // the whole warp
     const int d = a.d;
-    const bool live = lane < d;
+    const bool active = c0 + grp < a.C;              // chains past the end ride along on zeros
+    const int64_t c = active ? c0 + grp : a.C - 1;   // (a valid address for their guarded loads)
+    const bool live = active && sub < d;
     const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
     const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
-    const double mu = live ? __ldg(mc + lane) : 0.0;
+    const double mu = live ? __ldg(mc + sub) : 0.0;
     // Row k of the factor (column-major storage, so element j of every lane's row is one coalesced
     // line).  Without MOMENTS the rows are streamed from memory where they are used -- when the start
     // is whitened and when the result is un-whitened -- in chunks of 8 columns, so neither the step
     // loop nor those two passes hold 2 D registers of factor; MOMENTS needs x every step and keeps
     // the row in registers.
-    auto Lkj = [&](const double *Lp, int j) { return (live && j <= lane) ? __ldg(Lp + (size_t)j * d + lane) : 0.0; };
+    auto Lkj = [&](const double *Lp, int j) { return (live && j <= sub) ? __ldg(Lp + (size_t)j * d + sub) : 0.0; };
     double row_m[MOMENTS ? D : 1];
     if (MOMENTS) {
 #pragma unroll
@@ -78,59 +89,60 @@ mh_chains_kernel(const ChainArgs a)
         __syncwarp();
         s_v[wib][lane] = v;
         __syncwarp();
+        const double *vc = &s_v[wib][grp * W];
         double acc = 0.0;
         if constexpr (MOMENTS) {
 #pragma unroll
-            for (int j = 0; j < D; ++j) acc = fma(row_m[j], s_v[wib][j], acc);
+            for (int j = 0; j < D; ++j) acc = fma(row_m[j], vc[j], acc);
         } else {
 #pragma unroll 8
-            for (int j = 0; j < D; ++j) acc = fma(Lkj(Lp, j), s_v[wib][j], acc);
+            for (int j = 0; j < D; ++j) acc = fma(Lkj(Lp, j), vc[j], acc);
         }
         return mu + acc;
     };
 
     // whiten the start: column-oriented forward substitution, lane k keeps v_k
     double v = 0.0;
-    const double x_start = live ? a.x[(size_t)c * d + lane] : 0.0;
+    const double x_start = live ? a.x[(size_t)c * d + sub] : 0.0;
     {
-        const double rinv = live ? 1.0 / __ldg(Lc + (size_t)lane * d + lane) : 0.0;
+        const double rinv = live ? 1.0 / __ldg(Lc + (size_t)sub * d + sub) : 0.0;
         double r = live ? x_start - mu : 0.0;
 #pragma unroll 8
         for (int j = 0; j < D; ++j) {
-            const double vj = __shfl_sync(0xffffffffu, r * rinv, j);
-            if (j == lane) v = vj;
+            const double vj = __shfl_sync(0xffffffffu, r * rinv, j, W);
+            if (j == sub) v = vj;
             r = fma(-Lkj(Lc, j), vj, r);   // no-op for lanes k < j (L[k][j] == 0); lane j is done with r
         }
     }
-    double q = warp_sum_butterfly(v * v);
+    double q = chain_sum_butterfly<W>(v * v);
     const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
     double sx = 0.0, sxx = 0.0;
     uint32_t nacc = 0;
 
     const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
-    double z_next = (zc && live) ? ld_stream(zc + lane) : 0.0;
+    double z_next = (zc && live) ? ld_stream(zc + sub) : 0.0;
     // In-kernel randomness is generated in batches so that no Philox block is computed twice and
     // none of its output is thrown away; the (seed, chain, step, component) -> draw mapping is the
     // one of cusmc_philox.h, unchanged:
-    //  * thresholds: every 32 steps lane l computes the threshold of step s + l (one Philox block,
-    //    one log, one exp per lane per 32 steps instead of per step), broadcast per step;
-    //  * normals: lanes 4m .. 4m+3 share the block (step, m).  Every 4 steps lane 4m+k computes the
-    //    block of step s + k -- four normals, one for each lane of its quad -- and a 4 x 4 exchange
-    //    inside the quad hands every lane its own normal of steps s .. s + 3.
+    //  * thresholds: every W steps lane l of the chain computes the threshold of step s + l (one
+    //    Philox block, one log, one exp per lane per W steps instead of per step), broadcast per step;
+    //  * normals: lanes 4m .. 4m+3 of the chain share the block (step, m).  Every 4 steps lane 4m+k
+    //    computes the block of step s + k -- four normals, one for each lane of its quad -- and a
+    //    4 x 4 exchange inside the quad hands every lane its own normal of steps s .. s + 3.
     double thr_batch = 0.0;
     float zq[4] = {0.f, 0.f, 0.f, 0.f};    // zq[r]: this lane's normal of step s0 + ((lane & 3) ^ r)
     for (int s = 0; s < a.steps; ++s) {
         double z, thr;
         if (PHILOX) {
-            if ((s & 31) == 0) {
-                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + lane), (uint64_t)c, 0);
+            if ((s & (W - 1)) == 0) {
+                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + sub), (uint64_t)c, 0);
                 const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
                 thr_batch = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
             }
-            thr = __shfl_sync(0xffffffffu, thr_batch, s & 31);
+            thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
             if ((s & 3) == 0) {
-                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (lane & 3)), (uint64_t)c,
-                                                 (uint32_t)(lane >> 2));
+                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                 (uint32_t)(sub >> 2));
                 float n[4];
                 cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
                 cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
@@ -146,12 +158,12 @@ mh_chains_kernel(const ChainArgs a)
             z = live ? (double)zf : 0.0;
         } else {
             z = z_next;
-            if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + lane);   // prefetch
+            if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + sub);   // prefetch
             thr = __ldg(a.thr + (size_t)c * a.steps + s);
         }
         // proposal and its quadratic form, in whitened coordinates
         const double vp = fma(a.step_size, z, v);
-        const double qp = warp_sum_butterfly(vp * vp);
+        const double qp = chain_sum_butterfly<W>(vp * vp);
         bool accept;
         if (a.kind == CUSMC_MVT)
             accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
@@ -163,21 +175,24 @@ mh_chains_kernel(const ChainArgs a)
             ++nacc;
         }
         if (MOMENTS) {
-            const double x = nacc ? unwhiten(Lc, v) : x_start;
+            // (the un-whitening synchronises the warp: every chain of it takes this path every step)
+            const double xu = unwhiten(Lc, v);
+            const double x = nacc ? xu : x_start;
             sx += x;
             sxx = fma(x, x, sxx);
         }
-        if (a.accept_bits && lane == 0) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
+        if (a.accept_bits && sub == 0 && active) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
     }
-    const double x = nacc ? unwhiten(Lc, v) : x_start;     // a chain that never moved is left untouched
+    const double xu = unwhiten(Lc, v);
+    const double x = nacc ? xu : x_start;                  // a chain that never moved is left untouched
     if (live) {
-        a.x[(size_t)c * d + lane] = x;
+        a.x[(size_t)c * d + sub] = x;
         if (MOMENTS) {
-            if (a.sum_x) a.sum_x[(size_t)c * d + lane] = sx;
-            if (a.sum_xx) a.sum_xx[(size_t)c * d + lane] = sxx;
+            if (a.sum_x) a.sum_x[(size_t)c * d + sub] = sx;
+            if (a.sum_xx) a.sum_xx[(size_t)c * d + sub] = sxx;
         }
     }
-    if (a.n_accept && lane == 0) a.n_accept[c] = nacc;
+    if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
 }
 
 // ---- per-point covariance log-density -------------------------------------------------------
@@ -352,7 +367,9 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
     a.n_accept = n_accept_dev; a.accept_bits = accept_bits_dev;
     a.C = C; a.seed = seed; a.step_size = step_size; a.nu = nu;
     a.d = d; a.steps = steps; a.kind = kind; a.shared = shared;
-    const unsigned grid = (unsigned)((C + kWarpsPerBlock - 1) / kWarpsPerBlock);
+    const int pad = cusmc_pad_dim(d);
+    const int per_block = kWarpsPerBlock * (32 / (pad < 4 ? 4 : pad));    // chains per block
+    const unsigned grid = (unsigned)((C + per_block - 1) / per_block);
     const bool philox = z_dev == nullptr;
     const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
 #define CUSMC_CHAIN_LAUNCH(DD, PH, MO) \
