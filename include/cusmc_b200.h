@@ -289,7 +289,7 @@ typedef struct cusmc_filter_config {
      * memory) when the configuration allows it: one GPU, systematic resampling, Normal noise,
      * d == dy in {2, 4}, device-drawn noise, no history, N small enough for one tile of
      * <= 4096 particles per resident block (1.2 M particles on a B200).  Results are bit-identical
-     * to the four-launch step (28 vs 35 us per 10^6-particle step).  0 = automatic, -1 = never. */
+     * to the four-launch step (25 vs 36 us per 10^6-particle step).  0 = automatic, -1 = never. */
     int persistent;
     /* Adaptive resampling (systematic resampler only): 0 (default) = resample at every step, as the
      * reference does (src/mcmc.cpp:295); in (0, 1] = resample at step t only when the effective
