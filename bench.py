@@ -41,6 +41,16 @@ def workload_inputs():
     return mu, sigma
 
 
+def bench_config():
+    """The workload both arms (ours and --impl reference) are quoted on."""
+    return {"workload": "batched MVN log-density, d=16, N=2^20 points/step/GPU, shared covariance, "
+                        "fp64 (BASELINE configs[1]); SoA device-resident input",
+            "points_per_step_per_gpu": N_POINTS, "dim": DIM,
+            "l2_policy": "inputs rotate through a %d-batch pool (%.0f MiB) larger than the 126 MB L2"
+                         % (POOL_BATCHES, POOL_BATCHES * N_POINTS * DIM * 8 / 2 ** 20),
+            "parallelism": "points sharded across ranks, no data-path collective"}
+
+
 def ncu_traffic():
     """DRAM bytes per launch of the headline kernel from the committed ncu --set full capture."""
     try:
@@ -190,9 +200,10 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "batched MVN pdf d=16 shared covariance fp64 (BASELINE configs[1])",
-                   "points_per_step": n_sample, "dim": DIM,
-                   "note": "CPU restatement of the reference (oracle, faithful per-point LU), bounded sample"},
+        "config": dict(bench_config(),
+                       sample="each step evaluates %d of the workload's 2^20 points (a bounded sample: the "
+                              "whole run has to end within minutes) with the CPU restatement of the reference "
+                              "(oracle, faithful mode: per-point LU determinant + inverse)" % n_sample),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
                          "sample": "%d points per step, faithful mode" % n_sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -553,12 +564,7 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "batched MVN log-density, d=16, N=2^20 points/step/GPU, shared covariance, "
-                               "fp64 (BASELINE configs[1]); SoA device-resident input",
-                   "points_per_step_per_gpu": N_POINTS, "dim": DIM,
-                   "l2_policy": "inputs rotate through a %d-batch pool (%.0f MiB) larger than the 126 MB L2"
-                                % (POOL_BATCHES, POOL_BATCHES * N_POINTS * DIM * 8 / 2 ** 20),
-                   "parallelism": "points sharded across ranks, no data-path collective"},
+        "config": bench_config(),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_gbs, "unit": "GB/s",
                      "frac": achieved / hbm_gbs, "traffic": ncu_traffic(), "peak_source": peak_src,
                      "kernel": "density_soa_kernel<16,true,1,true>", "algorithmic_bytes_per_launch": BYTES_PER_EVAL * N_POINTS,
