@@ -184,8 +184,10 @@ int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_log,
  *                         ESS = stats[0]^2 / (stats[1] 2^shift).  The same pass leaves the WEIGHT
  *                         IMAGE in tile_prefix_dev: the exclusive prefix of the per-tile sums
  *                         (tile = 2048 weights) and every weight's inclusive prefix inside its
- *                         tile -- cusmc_tile_prefix_words(N) uint64 words, 16-byte aligned, word 0
- *                         zero before the first use (the kernel resets it); NULL = context scratch.
+ *                         tile -- cusmc_tile_prefix_words(N) uint64 words (32-byte alignment lets
+ *                         the pass use 256-bit stores; anything else falls back to 8-byte ones);
+ *                         NULL = context scratch.  Words 0..7 are scratch of the resampling pass:
+ *                         cusmc_resample_systematic_dev leaves its per-launch constants there.
  *                         exp() is evaluated once per weight, here.
  * cusmc_weights_scan_dev: cdf_dev[i] = *cdf_offset_dev + inclusive prefix sum of q.  Because the
  *                         total must be known before a single child can be assigned, the sum pass
@@ -215,7 +217,8 @@ int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int is_log, cons
  * (C = global inclusive prefix; 128-bit integer compare).  Every local parent j writes
  *   a_dev[i - out_lo] = j0 + j      for its children i inside [out_lo, out_lo + out_n).
  * j0 = global index of w_dev[0].  One GPU: j0 = out_lo = 0, out_n = N_local = N_global.
- * tile_prefix_dev as for cusmc_weights_scan_dev.
+ * tile_prefix_dev as for cusmc_weights_scan_dev (its words 0..7 are written: the pass keeps its
+ * per-launch constants -- T, r0 and the two quotients of the offspring estimate -- there).
  */
 int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
                                   const double *max_dev, int64_t N_local, int64_t N_global,
