@@ -22,7 +22,7 @@ ci = C.c_int
 dbl = C.c_double
 flt = C.c_float
 
-OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_DEGENERATE, ERR_UNSUPPORTED = range(6)
+OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_DEGENERATE, ERR_UNSUPPORTED, ERR_TIMEOUT = range(7)
 MVN, MVT = 0, 1
 SOA, AOS = 0, 1
 RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1, 2
@@ -38,13 +38,14 @@ class FilterConfig(C.Structure):
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
         ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci), ("ess_threshold", dbl),
+        ("mvt_normal_init", ci),
     ]
 
 
 class FilterDraws(C.Structure):
     _fields_ = [
         ("xi0_dev", vp), ("xi_dev", vp), ("chi_dev", vp), ("u_dev", vp), ("j_dev", vp),
-        ("u0_host", vp), ("um_dev", vp),
+        ("u0_host", vp), ("um_dev", vp), ("chi0_dev", vp),
     ]
 
 
@@ -95,12 +96,16 @@ PROTOTYPES = {
     "cusmc_filter_ipc_attach": (ci, [vp, vp]),
     "cusmc_filter_run_sharded": (ci, [vp, C.POINTER(FilterDraws)]),
     "cusmc_filter_exchange_status": (ci, [vp, C.POINTER(u64)]),
+    "cusmc_filter_set_exchange_timeout": (ci, [vp, dbl]),
+    "cusmc_filter_status": (ci, [vp]),
     "cusmc_filter_get_summary": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_get_history": (ci, [vp, vp, vp, vp]),
     "cusmc_filter_get_resampled": (ci, [vp, vp]),
     "cusmc_filter_last_ms": (dbl, [vp]),
     "cusmc_filter_state_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
+    "cusmc_filter_get_log_weights": (ci, [vp, vp]),
     "cusmc_run": (ci, [vp, C.POINTER(FilterConfig), vp, vp]),
+    "cusmc_run_ancestors": (ci, [vp, C.POINTER(FilterConfig), vp, vp, vp]),
     "cusmc_aos_to_soa_dev": (ci, [vp, vp, vp, i64, i64, ci]),
     "cusmc_soa_to_aos_dev": (ci, [vp, vp, vp, i64, i64, ci]),
 }

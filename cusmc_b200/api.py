@@ -381,38 +381,48 @@ class PreparedDensity:
         self.sigma_p = _hp(self._sigma)
 
 
+def _filter_config(N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10, df=0.0,
+                   noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
+                   persistent=True, ess_threshold=0.0, mvt_normal_init=False):
+    """cusmc_filter_config from numpy inputs; returns (config, arrays to keep alive while it is used)."""
+    Y = np.asarray(Y, dtype=np.float64)
+    if Y.ndim != 2:
+        raise ValueError("Y must be a (dy, T) matrix")
+    keep = [_colmajor(Y), _f64(m0), _colmajor(C0), _colmajor(F), _colmajor(G), _colmajor(V), _colmajor(W)]
+    cfg = FilterConfig()
+    cfg.N, cfg.d, cfg.dy, cfg.T = int(N), np.asarray(G).shape[0], Y.shape[0], Y.shape[1]
+    cfg.kind = _kind(distribution)
+    cfg.resampler = _resampler(resampler)
+    cfg.B = int(B)
+    cfg.nu = float(df)
+    cfg.noise_scale = float(noise_scale)
+    cfg.seed = int(seed)
+    (cfg.Y, cfg.m0, cfg.C0, cfg.F, cfg.G, cfg.V, cfg.W) = [a.ctypes.data for a in keep]
+    cfg.keep_history = int(keep_history)
+    cfg.summary = int(summary)
+    cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
+    cfg.persistent = 0 if persistent else -1      # one cooperative kernel per run when eligible
+    cfg.ess_threshold = float(ess_threshold)      # 0: resample every step (the reference's behaviour)
+    cfg.mvt_normal_init = int(mvt_normal_init)    # "mvt": x_0 = m0 + chi (.) (Q xi) unless set
+    return cfg, keep
+
+
 class ParticleFilter:
     """particle_filter() of the reference (src/particle_filter.cpp:6-39) with device-resident state."""
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
                  df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                 persistent=True, ess_threshold=0.0):
+                 persistent=True, ess_threshold=0.0, mvt_normal_init=False):
         self.ctx = ctx
-        Y = np.asarray(Y, dtype=np.float64)
-        F = np.asarray(F, dtype=np.float64)
-        self.dy, self.T = Y.shape
-        self.d = np.asarray(G).shape[0]
-        self.N = int(N)
+        cfg, self._keep = _filter_config(N, Y, m0, C0, F, G, V, W, distribution, resampler, B, df, noise_scale,
+                                         seed, keep_history, summary, rank, world, persistent, ess_threshold,
+                                         mvt_normal_init)
+        self.dy, self.T, self.d, self.N = cfg.dy, cfg.T, cfg.d, int(N)
         self._world = int(world)
         per = -(-self.N // max(1, int(world)))
         self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
-        self._keep = [_colmajor(Y), _f64(m0), _colmajor(C0), _colmajor(F), _colmajor(G), _colmajor(V),
-                      _colmajor(W)]
-        cfg = FilterConfig()
-        cfg.N, cfg.d, cfg.dy, cfg.T = self.N, self.d, self.dy, self.T
-        cfg.kind = _kind(distribution)
-        cfg.resampler = _resampler(resampler)
-        cfg.B = int(B)
-        cfg.nu = float(df)
-        cfg.noise_scale = float(noise_scale)
-        cfg.seed = int(seed)
-        (cfg.Y, cfg.m0, cfg.C0, cfg.F, cfg.G, cfg.V, cfg.W) = [a.ctypes.data for a in self._keep]
-        cfg.keep_history = int(keep_history)
-        cfg.summary = int(summary)
-        cfg.rank, cfg.world = int(rank), int(world)   # world > 1: see cusmc_b200/sharded.py
-        cfg.persistent = 0 if persistent else -1      # one cooperative kernel per run when eligible
-        cfg.ess_threshold = float(ess_threshold)      # 0: resample every step (the reference's behaviour)
         self.keep_history = bool(keep_history)
+        self.is_log = cfg.resampler != RESAMPLE_METROPOLIS
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
         self.h = h
@@ -428,20 +438,21 @@ class ParticleFilter:
         except Exception:
             pass
 
-    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None):
+    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, chi0=None):
         """Injected draws are torch CUDA tensors (see cusmc_filter_draws), u0 a host array; any
         omitted stream of randomness is drawn on the device from Philox."""
-        dr = self._make_draws(xi0, xi, chi, u, j, u0, um)
+        dr = self._make_draws(xi0, xi, chi, u, j, u0, um, chi0)
         self.ctx._check(self.ctx.lib.cusmc_filter_run(self.h, C.byref(dr)))
         return self
 
-    def _make_draws(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None):
+    def _make_draws(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, chi0=None):
         dr = FilterDraws()
         dr.xi0_dev, dr.xi_dev, dr.chi_dev = _dp(xi0), _dp(xi), _dp(chi)
+        dr.chi0_dev = _dp(chi0)
         dr.u_dev, dr.j_dev, dr.um_dev = _dp(u), _dp(j), _dp(um)
         self._u0 = None if u0 is None else _f64(u0)
         dr.u0_host = _hp(self._u0)
-        self._draws = (xi0, xi, chi, u, j, um)   # keep alive until the stream has consumed them
+        self._draws = (xi0, xi, chi, u, j, um, chi0)   # keep alive until the stream has consumed them
         return dr
 
     @property
@@ -478,12 +489,23 @@ class ParticleFilter:
         return x, w, a
 
     def history(self):
+        """x (T, n, d), a (T, n) and w (T, n): the raw densities in reference mode ("metropolis", w_0 =
+        1/N), NORMALISED weights for the other resamplers -- plus their raw log-weights as "lw"."""
         n = self.n_local            # a sharded filter returns its own shard
         x = np.empty((self.T, n, self.d))
         w = np.empty((self.T, n))
         a = np.empty((self.T, n), dtype=np.uint32)
         self.ctx._check(self.ctx.lib.cusmc_filter_get_history(self.h, _hp(x), _hp(w), _hp(a)))
-        return dict(x=x, w=w, a=a)
+        out = dict(x=x, w=w, a=a)
+        if self.is_log:
+            lw = np.empty((self.T, n))
+            self.ctx._check(self.ctx.lib.cusmc_filter_get_log_weights(self.h, _hp(lw)))
+            out["lw"] = lw
+        return out
+
+    def status(self):
+        """Waits for the last run; raises CusmcError (TIMEOUT / DEGENERATE) if it went wrong inside."""
+        self.ctx._check(self.ctx.lib.cusmc_filter_status(self.h))
 
 
 # ==============================================================================================
@@ -548,17 +570,25 @@ def metropolis_hastings(w, N, B, seed=0):
 
 
 def run(N, d, timeSteps, Y, m0, C0, F, G, V, W, df, resampler, distribution, p=0, seed=0,
-        noise_scale=1.0):
-    """run(...) (src/run.rcpp.cpp:58-126) -> {'weights': (T, N), 'posterior_x': (T, N, d)}.
-    df is passed through correctly (the reference swaps it with `runtime`)."""
+        noise_scale=1.0, ancestors=False, **kw):
+    """run(...) (src/run.rcpp.cpp:58-126) -> {'weights': (T, N), 'posterior_x': (T, N, d)} through
+    cusmc_run: the history streams to the host while the filter runs (bounded device memory).
+    df is passed through correctly (the reference swaps it with `runtime`).
+    ancestors=True adds 'ancestors' (T, N) (cusmc_run_ancestors)."""
     Y = np.asarray(Y, dtype=np.float64)
     if Y.shape[1] < timeSteps:
         raise ValueError("Y has fewer than timeSteps columns")
-    pf = ParticleFilter(default_context(), N, Y[:, :timeSteps], m0, C0, F, G, V, W,
-                        distribution=distribution, resampler=resampler, df=df, seed=seed,
-                        noise_scale=noise_scale, keep_history=True, summary=False)
-    try:
-        h = pf.run().history()
-    finally:
-        pf.close()
-    return {"weights": h["w"], "posterior_x": h["x"]}
+    if np.asarray(G).shape[0] != int(d):
+        raise ValueError("G is not d x d")
+    ctx = default_context()
+    cfg, keep = _filter_config(N, Y[:, :timeSteps], m0, C0, F, G, V, W, distribution, resampler, df=df, seed=seed,
+                               noise_scale=noise_scale, summary=False, **kw)
+    T = int(timeSteps)
+    w = np.empty((T, int(N)))
+    x = np.empty((T, int(N), int(d)))
+    if ancestors:
+        a = np.empty((T, int(N)), dtype=np.uint32)
+        ctx._check(ctx.lib.cusmc_run_ancestors(ctx.h, C.byref(cfg), _hp(w), _hp(x), _hp(a)))
+        return {"weights": w, "posterior_x": x, "ancestors": a}
+    ctx._check(ctx.lib.cusmc_run(ctx.h, C.byref(cfg), _hp(w), _hp(x)))
+    return {"weights": w, "posterior_x": x}

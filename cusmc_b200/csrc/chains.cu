@@ -353,7 +353,7 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
                                    uint32_t *n_accept_dev, uint8_t *accept_bits_dev, double *sum_x_dev,
                                    double *sum_xx_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, C >= 0 && steps >= 0 && d >= 1, "bad sizes");
     CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || kind == CUSMC_MVT, "unknown distribution");
     CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || nu > 0.0, "mvt needs nu > 0");
@@ -398,7 +398,7 @@ extern "C" int cusmc_logpdf_perpoint_dev(cusmc_ctx *ctx, int kind, int want_log,
                                          const double *mu_dev, const double *L_dev, int64_t N, int d,
                                          float nu, double *out_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1, "bad sizes");
     CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || kind == CUSMC_MVT, "unknown distribution");
     CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || nu > 0.0f, "mvt needs nu > 0");

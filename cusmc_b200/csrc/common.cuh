@@ -109,6 +109,14 @@ inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
         if (!(cond)) return cusmc_fail((ctx), CUSMC_ERR_INVALID, "%s: %s", __func__, (msg)); \
     } while (0)
 
+// First statement of every extern "C" entry point that launches, allocates or copies: contexts on
+// different devices may be used from one thread, and per-device state must follow the context.
+#define CUSMC_ENTER(ctx)                                   \
+    do {                                                   \
+        if (!(ctx)) return CUSMC_ERR_INVALID;              \
+        CUSMC_CUDA((ctx), cudaSetDevice((ctx)->device));   \
+    } while (0)
+
 // Checked after every launch; counts the launch for bench.py's gpu_launches.
 #define CUSMC_LAUNCHED(ctx)                                                          \
     do {                                                                             \
@@ -157,7 +165,9 @@ __device__ __forceinline__ double double_from_ordered(unsigned long long o)
 __device__ __forceinline__ void atomic_max_double(double *addr, double v)
 {
     if (v != v) return;
-    if (v >= 0.0)
+    // -0.0 compares >= 0 but its bit pattern is INT64_MIN as a signed integer, which could never
+    // replace the initial -inf: it goes through the negative branch (where it beats every negative)
+    if (v > 0.0 || __double_as_longlong(v) == 0)
         atomicMax(reinterpret_cast<long long *>(addr), __double_as_longlong(v));
     else
         atomicMin(reinterpret_cast<unsigned long long *>(addr), (unsigned long long)__double_as_longlong(v));

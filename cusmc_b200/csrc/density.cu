@@ -126,14 +126,10 @@ int launch_density(cusmc_ctx *ctx, const AffineOp<D, TRI> &op, const Epilogue &e
         const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
         const int64_t grid = (N + kThreads - 1) / kThreads;
         const int vec_ok = (d % 2 == 0) && ((uintptr_t)x % 16 == 0);
-        if (smem > 48 * 1024) {   // d > 23: the tile needs the opt-in shared-memory carve-out
-            static bool raised = false;   // per instantiation
-            if (!raised) {
-                CUSMC_CUDA(ctx, cudaFuncSetAttribute(density_aos_kernel<D, TRI>,
-                                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-                raised = true;
-            }
-        }
+        if (smem > 48 * 1024)     // d > 23: the tile needs the opt-in shared-memory carve-out.  The attribute
+                                  // is per device, so it is set on every such launch (no process-wide cache)
+            CUSMC_CUDA(ctx, cudaFuncSetAttribute(density_aos_kernel<D, TRI>,
+                                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
         density_aos_kernel<D, TRI><<<(unsigned)grid, kThreads, smem, ctx->stream>>>(
             op, ep, x, N, d, vec_ok, out);
     }
@@ -262,7 +258,7 @@ extern "C" int cusmc_logpdf_dev(cusmc_ctx *ctx, int kind, int want_log, const do
                                 int layout, int64_t N, int64_t ld, int d, const double *mu,
                                 const double *sigma, float nu, double *out_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1, "N >= 0 and d >= 1 required");
     CUSMC_REQUIRE(ctx, sigma != nullptr, "sigma is NULL");
     CUSMC_REQUIRE(ctx, N == 0 || (x_dev && out_dev), "x/out is NULL");
@@ -285,7 +281,7 @@ extern "C" int cusmc_logpdf(cusmc_ctx *ctx, int kind, int want_log, const double
                             int layout, int64_t N, int64_t ld, int d, const double *mu,
                             const double *sigma, float nu, double *out_host)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1, "N >= 0 and d >= 1 required");
     CUSMC_REQUIRE(ctx, N == 0 || (x_host && out_host), "x/out is NULL");
     CUSMC_REQUIRE(ctx, layout == CUSMC_SOA || layout == CUSMC_AOS, "bad layout");

@@ -25,6 +25,7 @@
 #include <algorithm>
 #include <cmath>
 #include <new>
+#include <thread>
 #include <vector>
 
 int cusmc_density_launch(cusmc_ctx *ctx, bool tri, int m, int d, const std::vector<double> &M_rowmajor,
@@ -127,7 +128,7 @@ static int build_observation(cusmc_ctx *ctx, int kind, int want_log, int d, int 
 extern "C" int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, double *soa_dev, int64_t N,
                                     int64_t ld, int d)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= 96 && ld >= N, "bad sizes (d must be in 1..96)");
     if (N == 0) return CUSMC_OK;
     const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
@@ -141,7 +142,7 @@ extern "C" int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, doubl
 extern "C" int cusmc_soa_to_aos_dev(cusmc_ctx *ctx, const double *soa_dev, double *aos_dev, int64_t N,
                                     int64_t ld, int d)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= 96 && ld >= N, "bad sizes (d must be in 1..96)");
     if (N == 0) return CUSMC_OK;
     const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
@@ -160,8 +161,10 @@ extern "C" int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_l
                                             const double *xi_dev, const double *chi_dev, uint64_t seed,
                                             uint64_t step, double *lw_dev, double *lw_max_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && dy >= 1 && ld >= N, "bad sizes");
+    if (d > CUSMC_MAX_DIM || dy > CUSMC_MAX_DIM)       // before anything sized CUSMC_MAX_DIM is filled
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d/dy > %d", CUSMC_MAX_DIM);
     CUSMC_REQUIRE(ctx, G && Q && y && F && V, "model matrix is NULL");
     CUSMC_REQUIRE(ctx, N == 0 || (x_new_dev && x_prev_dev && lw_dev), "state pointer is NULL");
     CUSMC_REQUIRE(ctx, x_new_dev != x_prev_dev, "x_new must not alias x_prev (children read arbitrary parents)");
@@ -195,7 +198,7 @@ extern "C" int cusmc_propagate_reweight_dev(cusmc_ctx *ctx, int kind, int want_l
 static int pdf_dropin(cusmc_ctx *ctx, int kind, double *w, const double *y, const double *x_aos, double norm,
                       const double *E_inv, const double *F, int64_t N, int d, int dy, float df)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && dy >= 1, "bad sizes");
     CUSMC_REQUIRE(ctx, y && E_inv && F && (N == 0 || (w && x_aos)), "NULL pointer");
     if (d > CUSMC_MAX_DIM || dy > CUSMC_MAX_DIM)
@@ -261,7 +264,7 @@ static int sample_dropin(cusmc_ctx *ctx, int kind, double *x_new_aos, const doub
                          const double *xi, const double *chi, uint64_t seed, uint64_t step, int stream_id,
                          int64_t N, int d, float df)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && d >= 1 && d <= CUSMC_MAX_DIM, "bad sizes");
     CUSMC_REQUIRE(ctx, Q && (N == 0 || x_new_aos), "NULL pointer");
     CUSMC_REQUIRE(ctx, !G || N == 0 || x_prev_aos, "x_prev is NULL");
@@ -359,6 +362,7 @@ static MailArgs filter_mail(const cusmc_filter *f)
     if (f->world > 1 && f->fused) {
         m.peer = (unsigned long long *const *)f->peer_mail.table_dev;
         m.err = f->mail_err;
+        m.timeout_ns = f->mail_timeout_ns;
         m.epoch = f->epoch;
         m.rank = f->rank;
         m.world = f->world;
@@ -530,9 +534,13 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         if (e == cudaSuccess) e = cudaMemset(f->mail_err, 0, 8);
     }
     if (cfg->keep_history) {
-        alloc((void **)&f->hist_x, sizeof(double) * (size_t)T * P * d);
-        alloc((void **)&f->hist_w, sizeof(double) * (size_t)T * P);
-        alloc((void **)&f->hist_a, sizeof(uint32_t) * (size_t)T * P);
+        // keep_history = 1: all T steps stay on the device (cusmc_filter_get_history);
+        // keep_history < 0: a ring of 2 chunks of -keep_history steps (cusmc_run, world == 1)
+        const size_t rows = cfg->keep_history < 0 ? (size_t)2 * (size_t)(-cfg->keep_history) : (size_t)T;
+        f->ring_K = cfg->keep_history < 0 ? -cfg->keep_history : 0;
+        alloc((void **)&f->hist_x, sizeof(double) * rows * P * d);
+        alloc((void **)&f->hist_w, sizeof(double) * rows * P);
+        alloc((void **)&f->hist_a, sizeof(uint32_t) * rows * P);
     }
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev0);
     if (e == cudaSuccess) e = cudaEventCreate(&f->ev1);
@@ -631,7 +639,8 @@ __global__ void init_slots_kernel(StepSlot *slots, int T)
         s.lw_max = -INFINITY;
         s.sum_q = s.sum_q2 = s.n_pos = s.cdf_offset = 0;
         s.resampled = t > 0 ? 1 : 0;
-        s.reserved[0] = s.reserved[1] = 0.0;
+        s.degenerate = 0;
+        s.reserved = 0.0;
         slots[t] = s;
     }
 }
@@ -679,12 +688,15 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     a.nu = cfg.nu;
     a.d = d;
     a.dy = dy;
-    a.kind = CUSMC_MVN;   // initial chi are 1 (see oracle: orc_filter_metropolis)
+    // "mvt": x_0 = m0 + chi (.) (Q_c0 xi), the reference's initialize() draws from the same distribution
+    // object as the transition noise (src/mcmc.cpp:73-79 -> src/statistics.cc.cpp:379-411)
+    a.kind = (cfg.kind == CUSMC_MVT && !cfg.mvt_normal_init) ? CUSMC_MVT : CUSMC_MVN;
+    a.chi = a.kind == CUSMC_MVT ? f->draws.chi0_dev : nullptr;
     a.has_prev = 0;
     a.skip_weight = 1;
     a.const_weight = f->is_log ? 0.0 : 1.0 / (double)cfg.N;
     a.rng_stream = CUSMC_STREAM_INIT;
-    if (cfg.keep_history) {
+    if (cfg.keep_history) {       // row 0 (of chunk 0 in ring mode)
         a.hist_x = f->hist_x;
         a.hist_w = f->hist_w;
     }
@@ -722,6 +734,7 @@ extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     CUSMC_REQUIRE(ctx, t >= 0 && t < cfg.T && f->next_t == t + 1, "weigh(t) follows begin / propagate(t)");
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     const int d = cfg.d;
     const int64_t n = f->n, P = f->per;
     cudaStream_t st = ctx->stream;
@@ -754,6 +767,7 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     CUSMC_REQUIRE(ctx, t >= 1 && t < cfg.T && f->next_t == t, "resample(t) follows weigh(t - 1)");
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     const cusmc_filter_draws &dr = f->draws;
     const int64_t n = f->n, N = cfg.N;
     const size_t off = (size_t)(t - 1);
@@ -771,12 +785,13 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
         return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
                                  nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr,
                                  adaptive ? &prev->sum_q2 : nullptr, adaptive ? &f->slots[t].resampled : nullptr,
-                                 filter_ess_bound(f), filter_consts_fused(f));
+                                 filter_ess_bound(f), filter_consts_fused(f), &f->slots[t].degenerate);
     }
     CUSMC_CHECK(cusmc_launch_scan(ctx, n, N, &prev->sum_q, nullptr, f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0,
                                   nullptr));
     const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
-    return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc);
+    return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc,
+                                    &f->slots[t].degenerate);
 }
 
 // Propagate and reweight, fused (src/mcmc.cpp:298-307).  Sharded: every rank's ancestors of step t
@@ -787,6 +802,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     CUSMC_REQUIRE(ctx, t >= 1 && t < cfg.T && f->next_t == t, "propagate(t) follows resample(t)");
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     const cusmc_filter_draws &dr = f->draws;
     const int d = cfg.d, dy = cfg.dy;
     const int64_t n = f->n;
@@ -815,9 +831,10 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     a.has_prev = 1;
     a.rng_stream = CUSMC_STREAM_NORMAL;
     if (cfg.keep_history) {       // the step's history rows are written by the step kernel itself
-        a.hist_x = f->hist_x + (size_t)t * n * d;
-        a.hist_w = f->hist_w + (size_t)t * n;
-        a.hist_a = f->hist_a + (size_t)t * n;
+        const size_t row = f->hist_row(t);
+        a.hist_x = f->hist_x + row * n * d;
+        a.hist_w = f->hist_w + row * n;
+        a.hist_a = f->hist_a + row * n;
     }
     if (f->world > 1) {
         a.world = f->world;
@@ -917,6 +934,7 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
 {
     if (!f) return CUSMC_ERR_INVALID;
     CUSMC_REQUIRE(f->ctx, f->world == 1, "a sharded filter is driven phase by phase (cusmc_b200/sharded.py)");
+    CUSMC_CUDA(f->ctx, cudaSetDevice(f->ctx->device));
     if (cusmc_filter_persistent_eligible(f, draws)) {
         const int rc = cusmc_filter_run_persistent(f, draws);
         if (rc != CUSMC_ERR_UNSUPPORTED) return rc;      // unsupported after all (occupancy): fall through
@@ -930,6 +948,46 @@ extern "C" int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws
         CUSMC_CHECK(cusmc_filter_weigh(f, t));
     }
     return cusmc_filter_mark(f, 1);
+}
+
+// What went wrong inside the last run, read back from the device: a scalar exchange that timed out
+// (sharded runs) or a step whose weights had no mass to resample from.  Every getter that hands
+// results to the caller goes through this, so a void run cannot be consumed silently.
+static int filter_run_status(cusmc_filter *f)
+{
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (f->mail_err) {
+        unsigned long long err = 0;
+        CUSMC_CUDA(ctx, cudaMemcpy(&err, f->mail_err, 8, cudaMemcpyDeviceToHost));
+        if (err)
+            return cusmc_fail(ctx, CUSMC_ERR_TIMEOUT, "sharded run: a scalar exchange timed out after %.1f s "
+                              "(a peer never arrived); the results are void", f->mail_timeout_ns * 1e-9);
+    }
+    const int T = f->cfg.T;
+    std::vector<StepSlot> slots(T);
+    CUSMC_CUDA(ctx, cudaMemcpy(slots.data(), f->slots, sizeof(StepSlot) * T, cudaMemcpyDeviceToHost));
+    for (int t = 1; t < T; ++t)
+        if (slots[t].degenerate)
+            return cusmc_fail(ctx, CUSMC_ERR_DEGENERATE, "step %d: every weight of step %d is zero or non-finite "
+                              "(nothing to resample from); ancestors were kept as the identity", t, t - 1);
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_filter_status(cusmc_filter *f)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, f->ran, "filter has not run");
+    return filter_run_status(f);
+}
+
+extern "C" int cusmc_filter_set_exchange_timeout(cusmc_filter *f, double seconds)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    CUSMC_REQUIRE(f->ctx, seconds > 0.0 && seconds < 3600.0, "timeout must lie in (0, 3600) seconds");
+    f->mail_timeout_ns = (unsigned long long)(seconds * 1e9);
+    return CUSMC_OK;
 }
 
 extern "C" double cusmc_filter_last_ms(const cusmc_filter *f)
@@ -946,6 +1004,7 @@ extern "C" int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *e
     if (!f) return CUSMC_ERR_INVALID;
     cusmc_ctx *ctx = f->ctx;
     CUSMC_REQUIRE(ctx, f->ran, "filter has not run");
+    CUSMC_CHECK(filter_run_status(f));
     const int d = f->cfg.d, T = f->cfg.T;
     std::vector<StepSlot> slots(T);
     std::vector<double> mom((size_t)T * (2 + d));
@@ -982,20 +1041,71 @@ extern "C" int cusmc_filter_get_resampled(cusmc_filter *f, int *resampled)
     return CUSMC_OK;
 }
 
+// History weights as the caller sees them (the reference's w_t, src/mcmc.cpp:85,212; R-level
+// `weights`, src/run.rcpp.cpp:110-117): reference mode ("metropolis") keeps the raw densities with
+// w_0 = 1/N exactly as the reference does; the normalised resamplers keep log-weights internally and
+// hand out NORMALISED weights  w_i = exp(lw_i - max) 2^shift / sum_q  (they sum to one over the whole
+// cloud; 1/N at t = 0, and cumulative over steps that did not resample).  Rows [row0, row0 + rows) of
+// `lw` (n columns each) belong to steps t0 .. t0 + rows - 1.
+__global__ void __launch_bounds__(kThreads)
+normalise_rows_kernel(const double *__restrict__ lw, double *__restrict__ out, const StepSlot *__restrict__ slots,
+                      int t0, int64_t n, int64_t total, double two_shift)
+{
+    for (int64_t e = (int64_t)blockIdx.x * kThreads + threadIdx.x; e < total; e += (int64_t)gridDim.x * kThreads) {
+        const int r = (int)(e / n);
+        const StepSlot s = slots[t0 + r];
+        const double v = exp(lw[e] - s.lw_max) * (two_shift / (double)s.sum_q);
+        out[e] = (v == v) ? v : 0.0;
+    }
+}
+
+static int launch_normalise_rows(cusmc_filter *f, const double *lw, double *out, int t0, int rows, cudaStream_t st)
+{
+    const int64_t total = (int64_t)rows * f->n;
+    if (total == 0) return CUSMC_OK;
+    const int grid = (int)std::min<int64_t>((total + kThreads - 1) / kThreads, (int64_t)f->ctx->sm_count * 16);
+    normalise_rows_kernel<<<grid, kThreads, 0, st>>>(lw, out, f->slots, t0, f->n, total, std::ldexp(1.0, f->shift));
+    CUSMC_LAUNCHED(f->ctx);
+    return CUSMC_OK;
+}
+
 extern "C" int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a)
 {
     if (!f) return CUSMC_ERR_INVALID;
     cusmc_ctx *ctx = f->ctx;
-    CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history, "history was not kept");
-    const size_t TN = (size_t)f->cfg.T * (size_t)f->n;   // this rank's shard
-    CUSMC_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history > 0, "history was not kept (keep_history = 1)");
+    CUSMC_CHECK(filter_run_status(f));
+    const int T = f->cfg.T;
+    const size_t TN = (size_t)T * (size_t)f->n;   // this rank's shard
     if (x_aos) CUSMC_CHECK(cusmc_d2h_staged(ctx, x_aos, f->hist_x, sizeof(double) * TN * f->cfg.d));
-    if (w) CUSMC_CHECK(cusmc_d2h_staged(ctx, w, f->hist_w, sizeof(double) * TN));
+    if (w && !f->is_log) CUSMC_CHECK(cusmc_d2h_staged(ctx, w, f->hist_w, sizeof(double) * TN));
+    if (w && f->is_log) {
+        // normalised on the device, a bounded number of rows at a time
+        const int rows_max = (int)std::max<int64_t>(1, std::min<int64_t>(T, ((int64_t)4 << 20) / std::max<int64_t>(1, f->n)));
+        void *tmp = nullptr;
+        CUSMC_CHECK(cusmc_scratch(ctx, 0, sizeof(double) * (size_t)rows_max * (size_t)f->n, &tmp));
+        for (int t0 = 0; t0 < T; t0 += rows_max) {
+            const int rows = std::min(rows_max, T - t0);
+            CUSMC_CHECK(launch_normalise_rows(f, f->hist_w + (size_t)t0 * f->n, (double *)tmp, t0, rows, ctx->stream));
+            CUSMC_CHECK(cusmc_d2h_staged(ctx, w + (size_t)t0 * f->n, tmp, sizeof(double) * (size_t)rows * f->n));
+        }
+    }
     if (a) {
         CUSMC_CHECK(cusmc_d2h_staged(ctx, a, f->hist_a, sizeof(uint32_t) * TN));
         for (int64_t i = 0; i < f->n; ++i) a[i] = (uint32_t)(f->lo + i);   // row t = 0: identity
     }
     return CUSMC_OK;
+}
+
+// The raw per-step log-weights [T][n] of the normalised resamplers (what resampling consumed; row 0 is 0).
+extern "C" int cusmc_filter_get_log_weights(cusmc_filter *f, double *lw)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history > 0 && lw, "history was not kept (keep_history = 1)");
+    CUSMC_REQUIRE(ctx, f->is_log, "the metropolis (reference) mode keeps densities, not log-weights");
+    CUSMC_CHECK(filter_run_status(f));
+    return cusmc_d2h_staged(ctx, lw, f->hist_w, sizeof(double) * (size_t)f->cfg.T * (size_t)f->n);
 }
 
 extern "C" int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa, double **lw, uint32_t **anc)
@@ -1007,17 +1117,171 @@ extern "C" int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa, double **
     return CUSMC_OK;
 }
 
-// R-level run() (src/run.rcpp.cpp:58-126): weights [T][N], posterior_x [T][N][d].
-extern "C" int cusmc_run(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x)
+// R-level run() (src/run.rcpp.cpp:58-126): weights [T][N], posterior_x [T][N][d] (+ optionally the
+// ancestors [T][N]) on HOST pointers.  The reference keeps every step of every particle alive on the
+// host as separately allocated vectors (src/run.rcpp.cpp:82-97) and its GPU build ships the whole
+// cloud both ways every step; here the history STREAMS: the step kernels write their rows into a
+// two-chunk ring on the device, a finished chunk goes device -> pinned host memory on a second
+// stream while the next chunk computes, and this thread (with helpers) copies drained chunks into
+// the caller's arrays.  Device memory is bounded by the ring (2 chunks of ~8 MB of rows), whatever T.
+namespace {
+
+struct RunRing {
+    cusmc_filter *f = nullptr;
+    int K = 1, chunks = 0;
+    size_t n = 0, d = 0;
+    void *pin[2] = {nullptr, nullptr};
+    size_t pin_bytes = 0;
+    cudaEvent_t ready[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
+    double *weights = nullptr, *posterior_x = nullptr;
+    uint32_t *ancestors = nullptr;
+
+    size_t off_w() const { return sizeof(double) * (size_t)K * n * d; }
+    size_t off_a() const { return off_w() + sizeof(double) * (size_t)K * n; }
+    int rows_of(int c) const { return std::min(K, f->cfg.T - c * K); }
+
+    // chunk c is complete on the compute stream: normalise its weights (log modes), ship it
+    int ship(int c)
+    {
+        cusmc_ctx *ctx = f->ctx;
+        const int s = c & 1, rows = rows_of(c);
+        double *dx = f->hist_x + (size_t)s * K * n * d, *dw = f->hist_w + (size_t)s * K * n;
+        uint32_t *da = f->hist_a + (size_t)s * K * n;
+        if (f->is_log && weights) CUSMC_CHECK(launch_normalise_rows(f, dw, dw, c * K, rows, ctx->stream));
+        CUSMC_CUDA(ctx, cudaEventRecord(ready[s], ctx->stream));
+        CUSMC_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ready[s], 0));
+        char *p = (char *)pin[s];
+        if (posterior_x)
+            CUSMC_CUDA(ctx, cudaMemcpyAsync(p, dx, sizeof(double) * (size_t)rows * n * d, cudaMemcpyDeviceToHost, ctx->aux_stream));
+        if (weights)
+            CUSMC_CUDA(ctx, cudaMemcpyAsync(p + off_w(), dw, sizeof(double) * (size_t)rows * n, cudaMemcpyDeviceToHost, ctx->aux_stream));
+        if (ancestors)
+            CUSMC_CUDA(ctx, cudaMemcpyAsync(p + off_a(), da, sizeof(uint32_t) * (size_t)rows * n, cudaMemcpyDeviceToHost, ctx->aux_stream));
+        CUSMC_CUDA(ctx, cudaEventRecord(copied[s], ctx->aux_stream));
+        return CUSMC_OK;
+    }
+
+    static void spread_copy(char *dst, const char *src, size_t bytes)
+    {
+        const unsigned hw = std::thread::hardware_concurrency();
+        const int workers = bytes < ((size_t)1 << 20) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+        const size_t part = ((bytes + workers - 1) / workers + 4095) & ~(size_t)4095;
+        std::vector<std::thread> pool;
+        size_t handed = std::min(part, bytes);
+        try {                                            // nothing may unwind across the C ABI
+            for (int w = 1; w < workers && handed < bytes; ++w) {
+                const size_t lo = handed, len = std::min(part, bytes - lo);
+                pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, len); });
+                handed = lo + len;
+            }
+        } catch (...) {
+        }
+        std::memcpy(dst, src, std::min(part, bytes));
+        if (handed < bytes) std::memcpy(dst + handed, src + handed, bytes - handed);
+        for (auto &t : pool) t.join();
+    }
+
+    // chunk c has landed in pinned memory: copy it into the caller's arrays (frees ring slot c & 1)
+    int drain(int c)
+    {
+        cusmc_ctx *ctx = f->ctx;
+        const int s = c & 1, rows = rows_of(c);
+        CUSMC_CUDA(ctx, cudaEventSynchronize(copied[s]));
+        const char *p = (const char *)pin[s];
+        const size_t t0 = (size_t)c * K;
+        if (posterior_x) spread_copy((char *)(posterior_x + t0 * n * d), p, sizeof(double) * (size_t)rows * n * d);
+        if (weights) spread_copy((char *)(weights + t0 * n), p + off_w(), sizeof(double) * (size_t)rows * n);
+        if (ancestors) {
+            spread_copy((char *)(ancestors + t0 * n), p + off_a(), sizeof(uint32_t) * (size_t)rows * n);
+            if (c == 0)
+                for (size_t i = 0; i < n; ++i) ancestors[i] = (uint32_t)i;      // row t = 0: identity
+        }
+        return CUSMC_OK;
+    }
+
+    void release()
+    {
+        for (int s = 0; s < 2; ++s) {
+            if (pin[s]) cudaFreeHost(pin[s]);
+            if (ready[s]) cudaEventDestroy(ready[s]);
+            if (copied[s]) cudaEventDestroy(copied[s]);
+        }
+    }
+};
+
+int run_streamed(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x,
+                 uint32_t *ancestors)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
-    CUSMC_REQUIRE(ctx, cfg != nullptr, "config is NULL");
     cusmc_filter_config c = *cfg;
-    c.keep_history = 1;
+    CUSMC_REQUIRE(ctx, c.world <= 1, "cusmc_run is single-GPU (a sharded run is driven through cusmc_filter_run_sharded)");
+    CUSMC_REQUIRE(ctx, c.N >= 1 && c.d >= 1 && c.T >= 1, "N, d, T must be positive");
+    const size_t row_bytes = (size_t)c.N * (sizeof(double) * (size_t)c.d + sizeof(double) + sizeof(uint32_t));
+    const int K = (int)std::max<size_t>(1, std::min<size_t>((size_t)c.T, ((size_t)8 << 20) / std::max<size_t>(1, row_bytes)));
+    c.keep_history = -K;
+    c.persistent = -1;            // the history rows are written by the per-step kernels
     cusmc_filter *f = nullptr;
     CUSMC_CHECK(cusmc_filter_create(ctx, &c, &f));
-    int rc = cusmc_filter_run(f, nullptr);
-    if (rc == CUSMC_OK) rc = cusmc_filter_get_history(f, posterior_x, weights, nullptr);
+    RunRing ring;
+    ring.f = f;
+    ring.K = K;
+    ring.chunks = (c.T + K - 1) / K;
+    ring.n = (size_t)c.N;
+    ring.d = (size_t)c.d;
+    ring.weights = weights;
+    ring.posterior_x = posterior_x;
+    ring.ancestors = ancestors;
+    ring.pin_bytes = (size_t)K * row_bytes;
+    int rc = cusmc_aux_stream(ctx);
+    for (int s = 0; s < 2 && rc == CUSMC_OK; ++s) {
+        if (cudaMallocHost(&ring.pin[s], ring.pin_bytes) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ring.ready[s], cudaEventDisableTiming) != cudaSuccess ||
+            cudaEventCreateWithFlags(&ring.copied[s], cudaEventDisableTiming) != cudaSuccess)
+            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_run: pinned staging allocation failed: %s",
+                            cudaGetErrorString(cudaGetLastError()));
+    }
+    const int T = c.T;
+    for (int t = 0; t < T && rc == CUSMC_OK; ++t) {
+        const int ch = t / K;
+        // the ring slot of this chunk was last used by chunk ch - 2: drained (hence copied) first
+        if (t % K == 0 && ch >= 2) rc = ring.drain(ch - 2);
+        if (rc != CUSMC_OK) break;
+        if (t == 0) {
+            rc = cusmc_filter_begin(f, nullptr);
+            if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, 0);
+            if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 0);
+        } else {
+            rc = cusmc_filter_resample(f, t);
+            if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
+            if (rc == CUSMC_OK) rc = cusmc_filter_weigh(f, t);
+        }
+        if (rc == CUSMC_OK && (t % K == K - 1 || t == T - 1)) rc = ring.ship(ch);
+    }
+    if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 1);
+    for (int ch = std::max(0, ring.chunks - 2); ch < ring.chunks && rc == CUSMC_OK; ++ch) rc = ring.drain(ch);
+    if (rc == CUSMC_OK) rc = filter_run_status(f);
+    cudaStreamSynchronize(ctx->aux_stream);
+    cudaStreamSynchronize(ctx->stream);
+    ring.release();
     cusmc_filter_destroy(f);
     return rc;
+}
+
+}  // namespace
+
+extern "C" int cusmc_run(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x)
+{
+    CUSMC_ENTER(ctx);
+    CUSMC_REQUIRE(ctx, cfg != nullptr, "config is NULL");
+    return run_streamed(ctx, cfg, weights, posterior_x, nullptr);
+}
+
+// The same run, also returning the ancestor indices a_t [T][N] (row 0 is the identity): with them the
+// caller can trace any particle's genealogy through posterior_x (the reference keeps a_t as well,
+// src/run.rcpp.cpp:97, but never returns it).
+extern "C" int cusmc_run_ancestors(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights,
+                                   double *posterior_x, uint32_t *ancestors)
+{
+    CUSMC_ENTER(ctx);
+    CUSMC_REQUIRE(ctx, cfg != nullptr, "config is NULL");
+    return run_streamed(ctx, cfg, weights, posterior_x, ancestors);
 }

@@ -13,7 +13,9 @@ struct StepSlot {            // one per time step, on the device (64 bytes = 8 w
     uint64_t sum_q, sum_q2, n_pos;   // [1..3] fixed-point sums (weigh_kernel); global after the exchange
     uint64_t cdf_offset;     // [4] fixed-point mass held by lower-ranked shards (0 on one GPU)
     uint64_t resampled;      // [5] 1 if this step drew new ancestors (adaptive resampling), else 0
-    double reserved[2];
+    uint64_t degenerate;     // [6] 1 if the weights this step resampled FROM had no mass (all -inf / NaN):
+                             //     its ancestors are the identity and the run reports CUSMC_ERR_DEGENERATE
+    double reserved;
 };
 
 struct cusmc_filter {
@@ -33,6 +35,7 @@ struct cusmc_filter {
     CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
     unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
     unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
+    unsigned long long mail_timeout_ns = 2000000000ull;   // bound of every spin-wait (cusmc_filter_set_exchange_timeout)
     void **peer_tables = nullptr;             // device: [5 buffers][CUSMC_MAX_PEERS] peer pointers
     unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
     bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
@@ -47,6 +50,14 @@ struct cusmc_filter {
     size_t persist_bytes = 0;
     double *hist_x = nullptr, *hist_w = nullptr;
     uint32_t *hist_a = nullptr;
+    // ring_K > 0: the history buffers hold a RING of 2 chunks of ring_K steps each instead of all T
+    // steps; the chunk of step t is (t / ring_K) & 1.  cusmc_run streams finished chunks to the host
+    // while the next ones compute, so a run with full history needs bounded device memory.
+    int ring_K = 0;
+    size_t hist_row(int t) const
+    {
+        return ring_K > 0 ? (size_t)((t / ring_K) & 1) * (size_t)ring_K + (size_t)(t % ring_K) : (size_t)t;
+    }
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0;
     int cur = 0;

@@ -10,8 +10,9 @@
 // tried: an extra dependent L2 round trip + system fence per block cost 100 us per step at 32 Ki
 // blocks.)
 //
-// Flags carry the run epoch, so a mailbox is never cleared.  Spins are bounded (2 s): on a timeout
-// the error word is set and the kernel goes on (results void) instead of hanging the GPU.
+// Flags carry the run epoch, so a mailbox is never cleared.  Spins are bounded (2 s by default,
+// cusmc_filter_set_exchange_timeout): on a timeout the error word is set and the kernel goes on instead
+// of hanging the GPU; every getter of the filter then returns CUSMC_ERR_TIMEOUT (results void).
 #pragma once
 
 #include "common.cuh"
@@ -21,6 +22,7 @@ enum { kCellMax = 0, kCellSums = 1, kCellBarrier = 2, kMailCells = 3 };
 struct MailArgs {
     unsigned long long *const *peer;              // device table: every rank's mailbox (own one included)
     unsigned long long *err;
+    unsigned long long timeout_ns;                // bound of a spin-wait (default 2 s)
     unsigned long long epoch;
     int rank, world;                              // world <= 1: no exchange
 };
@@ -64,7 +66,7 @@ __device__ __forceinline__ void mail_wait(const MailArgs &m, size_t cell0, int l
             const unsigned long long t0 = mail_now_ns();
             while (src[3] != m.epoch) {
                 __nanosleep(32);
-                if (mail_now_ns() - t0 > 2000000000ull) {
+                if (mail_now_ns() - t0 > m.timeout_ns) {
                     *m.err = 1;
                     break;
                 }

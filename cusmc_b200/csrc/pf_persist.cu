@@ -386,7 +386,7 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
             }
             __syncthreads();
             const uint64_t T = s_T;
-            if (T != 0) {                                   // T == 0: degenerate weights, ancestors stay
+            if (T != 0) {
                 const uint64_t r0 = s_r0, Ng = a.N;
                 const double ng_over_t = s_ng_over_t, r0_over_t = s_r0_over_t;
                 uint32_t k[kItems];
@@ -431,6 +431,12 @@ pf_persistent_kernel(const __grid_constant__ pfstep::StepOp<D, DIAG> op_init,
                     }
                     k_prev = hi;
                 }
+            } else {
+                // no mass to resample from: identity ancestors, reported by the host getters
+#pragma unroll
+                for (int r = 0; r < kItems; ++r)
+                    if ((uint32_t)(kItems * (int)tid + r) < tile_n) a.anc[tile0 + kItems * tid + r] = tile0 + kItems * tid + r;
+                if (blockIdx.x == 0 && tid == 0) a.slots[t].degenerate = 1;
             }
         }
         grid_barrier(t);
@@ -572,11 +578,11 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
             if (j != k && f->M[(size_t)k * d + j] != 0.0) diag = false;
     PersistArgs a{};
     a.tile_n = tile_n;
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     // resident-block check before anything is enqueued (so the caller can still fall back)
     int rc = launch_persistent_any(f, a, d, diag, P, true);
     if (rc != CUSMC_OK) return rc;
 
-    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     // per-run scratch: tile sums [2][grid], whitened observations [T][d], systematic offsets [T]
     const size_t n_sum = 2 * (size_t)grid, n_obs = (size_t)T * d, n_u0 = (size_t)T;

@@ -371,6 +371,7 @@ struct ScanArgs {
     // 2^shift; 0 = always).  *resampled_out receives the decision (block 0).
     const unsigned long long *sum_q2;
     unsigned long long *resampled_out;
+    unsigned long long *degenerate_out;    // optional: set to 1 when the total mass is zero
     double ess_bound;
 };
 
@@ -513,8 +514,8 @@ scan_resample_kernel(const ScanArgs p)
     }
     if (!scatter) return;
     if (w0 == 0 && lane == 0 && p.resampled_out) *p.resampled_out = c.resample;
-    if (c.T == 0) return;                             // degenerate: the host reports it
-    if (!c.resample) {                                // keep every particle: a_i = i
+    if (c.T == 0 && w0 == 0 && lane == 0 && p.degenerate_out) *p.degenerate_out = 1;   // reported by the host getters
+    if (!c.resample || c.T == 0) {                    // keep every particle: a_i = i (also when there is no mass)
 #pragma unroll
         for (int r = 0; r < kPar; ++r)
             if (i0 + 32 * r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + 32 * r, p.j0 + i0 + 32 * r);
@@ -532,12 +533,16 @@ __global__ void __launch_bounds__(kThreads)
 multinomial_kernel(const unsigned long long *__restrict__ cdf, int64_t N,
                    const unsigned long long *__restrict__ total_p, const double *__restrict__ u,
                    uint64_t seed, uint64_t step, int64_t i0, int64_t n_out, int64_t j0,
-                   uint32_t *__restrict__ a)
+                   uint32_t *__restrict__ a, unsigned long long *degenerate_out)
 {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (t >= n_out) return;
     const uint64_t T = *total_p;
-    if (T == 0) return;
+    if (T == 0) {                                     // no mass: identity ancestors, flagged
+        a[t] = (uint32_t)(j0 + i0 + t);
+        if (t == 0 && degenerate_out) *degenerate_out = 1;
+        return;
+    }
     double ui;
     if (PREDRAWN) {
         ui = __ldg(u + t);
@@ -647,7 +652,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev,
-                      uint64_t *resampled_dev, double ess_bound, bool consts_ready)
+                      uint64_t *resampled_dev, double ess_bound, bool consts_ready, uint64_t *degenerate_dev)
 {
     if (N == 0) return CUSMC_OK;
     if (N_global > 0xFFFFFFFFll || out_lo < 0 || out_lo + out_n > N_global)
@@ -668,6 +673,7 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.u0 = u0;
     p.sum_q2 = (const unsigned long long *)sum_q2_dev;
     p.resampled_out = (unsigned long long *)resampled_dev;
+    p.degenerate_out = (unsigned long long *)degenerate_dev;
     p.ess_bound = sum_q2_dev ? ess_bound : 0.0;
     const unsigned grid = (unsigned)((N + kThreads * kPar - 1) / (kThreads * kPar));
     if ((anc_out || peers) && !consts_ready) {
@@ -690,16 +696,18 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
 
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
-                             int64_t n_out, int64_t j0, uint32_t *a)
+                             int64_t n_out, int64_t j0, uint32_t *a, uint64_t *degenerate_dev)
 {
     if (n_out == 0) return CUSMC_OK;
     const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
     if (u)
         multinomial_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(
-            (const unsigned long long *)cdf, N, (const unsigned long long *)total_dev, u, seed, step, i0, n_out, j0, a);
+            (const unsigned long long *)cdf, N, (const unsigned long long *)total_dev, u, seed, step, i0, n_out, j0, a,
+            (unsigned long long *)degenerate_dev);
     else
         multinomial_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(
-            (const unsigned long long *)cdf, N, (const unsigned long long *)total_dev, u, seed, step, i0, n_out, j0, a);
+            (const unsigned long long *)cdf, N, (const unsigned long long *)total_dev, u, seed, step, i0, n_out, j0, a,
+            (unsigned long long *)degenerate_dev);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -709,7 +717,7 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
                                              const double *u_dev, const uint32_t *j_dev,
                                              uint64_t seed, uint64_t step, int64_t N, int B, int is_log)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && B >= 0, "N, B must be non-negative");
     CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
@@ -719,7 +727,7 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
 
 extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, max_dev && (N == 0 || w_dev), "NULL pointer");
     CUSMC_CHECK(cusmc_fill_double(ctx, max_dev, -INFINITY, 1));
     return cusmc_launch_weights_max(ctx, w_dev, N, max_dev);
@@ -745,7 +753,7 @@ extern "C" int cusmc_weights_sum_dev(cusmc_ctx *ctx, const double *w_dev, int is
                                      const double *max_dev, int64_t N, int64_t N_global,
                                      uint64_t *stats_dev, uint64_t *tile_prefix_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, stats_dev && max_dev && (N == 0 || w_dev), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N && N_global >= 1, "N_global < N");
     if (N == 0) {
@@ -778,7 +786,7 @@ extern "C" int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int i
                                       const uint64_t *cdf_offset_dev, const uint64_t *tile_prefix_dev,
                                       uint64_t *cdf_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, max_dev && (N == 0 || (w_dev && cdf_dev)), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N && N_global >= 1, "N_global < N");
     if (N == 0) return CUSMC_OK;
@@ -794,7 +802,7 @@ extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev
                                              const uint64_t *tile_prefix_dev, int64_t j0, int64_t out_lo,
                                              int64_t out_n, double u0, uint32_t *a_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, max_dev && total_dev && (N_local == 0 || w_dev) && (out_n == 0 || a_dev), "NULL pointer");
     CUSMC_REQUIRE(ctx, N_global >= N_local && N_global >= 1, "N_global < N_local");
     CUSMC_REQUIRE(ctx, N_global <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
@@ -811,7 +819,7 @@ extern "C" int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cd
                                               uint64_t seed, uint64_t step, int64_t i0, int64_t n_out,
                                               int64_t j0, uint32_t *a_dev)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, total_dev && (N == 0 || cdf_dev) && (n_out == 0 || a_dev), "NULL pointer");
     return cusmc_launch_multinomial(ctx, cdf_dev, N, total_dev, u_dev, seed, step, i0, n_out, j0, a_dev);
 }
@@ -851,7 +859,7 @@ int upload_and_reduce(cusmc_ctx *ctx, const double *w, int64_t N, int is_log, Ho
 extern "C" int cusmc_metropolis_hastings(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                                          const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && B >= 0, "N, B must be non-negative");
     CUSMC_REQUIRE(ctx, N == 0 || (a && w), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u == nullptr) == (j == nullptr), "u and j must both be given or both NULL");
@@ -880,7 +888,7 @@ extern "C" int cusmc_metropolis_hastings(cusmc_ctx *ctx, uint32_t *a, const doub
 
 extern "C" int cusmc_resample_systematic(cusmc_ctx *ctx, const double *w, int64_t N, double u0, uint32_t *a)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && (N == 0 || (w && a)), "bad arguments");
     CUSMC_REQUIRE(ctx, u0 >= 0.0 && u0 < 1.0, "u0 must lie in [0, 1)");
     if (N == 0) return CUSMC_OK;
@@ -905,7 +913,7 @@ extern "C" int cusmc_resample_systematic(cusmc_ctx *ctx, const double *w, int64_
 extern "C" int cusmc_resample_multinomial(cusmc_ctx *ctx, const double *w, int64_t N, const double *u,
                                           uint32_t *a)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 0 && (N == 0 || (w && a && u)), "bad arguments");
     if (N == 0) return CUSMC_OK;
     HostWeights hw;
@@ -932,7 +940,7 @@ extern "C" int cusmc_resample_multinomial(cusmc_ctx *ctx, const double *w, int64
 
 extern "C" int cusmc_normalize_ess(cusmc_ctx *ctx, const double *lw, int64_t N, double *lse, double *ess)
 {
-    if (!ctx) return CUSMC_ERR_INVALID;
+    CUSMC_ENTER(ctx);
     CUSMC_REQUIRE(ctx, N >= 1 && lw, "bad arguments");
     HostWeights hw;
     double mx;

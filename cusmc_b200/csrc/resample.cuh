@@ -28,10 +28,11 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
                       int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev = nullptr,
-                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0, bool consts_ready = false);
+                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0, bool consts_ready = false,
+                      uint64_t *degenerate_dev = nullptr);
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
-                             int64_t n_out, int64_t j0, uint32_t *a);
+                             int64_t n_out, int64_t j0, uint32_t *a, uint64_t *degenerate_dev = nullptr);
 
 // ---- shared with the persistent filter kernel (pf_persist.cu) -------------------------------------
 constexpr int kResampleThreads = 256;

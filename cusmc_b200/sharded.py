@@ -140,7 +140,12 @@ class ShardedParticleFilter:
         if kw.get("resampler", "metropolis") == "multinomial" and self.world > 1:
             raise ValueError("the multinomial resampler is single-GPU only")
         ctx.use_torch_stream()
+        exchange_timeout = kw.pop("exchange_timeout", None)
         self.pf = ParticleFilter(ctx, N, Y, m0, C0, F, G, V, W, rank=self.rank, world=self.world, **kw)
+        if exchange_timeout is None:
+            # ranks that time-slice one device (test rigs) wait for each other's kernels to be scheduled
+            exchange_timeout = 2.0 if torch.cuda.device_count() >= self.world else 60.0
+        ctx._check(ctx.lib.cusmc_filter_set_exchange_timeout(self.pf.h, float(exchange_timeout)))
         self.T, self.d, self.N = self.pf.T, self.pf.d, int(N)
         self.is_log = kw.get("resampler", "metropolis") != "metropolis"
         self.summary_on = bool(kw.get("summary", True))
@@ -237,14 +242,20 @@ class ShardedParticleFilter:
     def last_ms(self):
         return self.pf.last_ms
 
+    def status(self):
+        """Waits for the last run; raises CusmcError if an exchange timed out (results void) or a step
+        had no weight mass.  summary() and local_state() check it too."""
+        self.pf.status()
+
     def summary(self):
-        return self.pf.summary()
+        return self.pf.summary()      # cusmc_filter_get_summary reports TIMEOUT / DEGENERATE itself
 
     def local_state(self):
         """(x [d][n] SoA, weights [n], ancestors [n]) of this rank's shard as numpy arrays."""
         import torch
         lib, h = self.ctx.lib, self.pf.h
         px, pw, pa = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.pf.status()
         self.ctx._check(lib.cusmc_filter_state_dev(h, C.byref(px), C.byref(pw), C.byref(pa)))
         torch.cuda.synchronize()
         n, per = self.plan.n, self.plan.per

@@ -44,7 +44,8 @@ enum cusmc_status {
     CUSMC_ERR_CUDA = 2,         /* CUDA runtime / launch failure */
     CUSMC_ERR_NOT_SPD = 3,      /* covariance not symmetric positive definite */
     CUSMC_ERR_DEGENERATE = 4,   /* all weights zero / non-finite: nothing to resample from */
-    CUSMC_ERR_UNSUPPORTED = 5
+    CUSMC_ERR_UNSUPPORTED = 5,
+    CUSMC_ERR_TIMEOUT = 6       /* sharded run: a peer never arrived at a scalar exchange; results void */
 };
 
 enum cusmc_dist_kind { CUSMC_MVN = 0, CUSMC_MVT = 1 };   /* Distributions["mvn"|"mvt"], src/mcmc.cpp:53-58 */
@@ -282,7 +283,8 @@ typedef struct cusmc_filter_config {
     uint64_t seed;        /* Philox key for device-drawn randomness */
     const double *Y;      /* dy x T column-major observations (host) */
     const double *m0, *C0, *F, *G, *V, *W;   /* host, column-major */
-    int keep_history;     /* 1: keep x (T x N x d), w (T x N), a (T x N) on the device */
+    int keep_history;     /* 1: keep x (T x N x d), w (T x N), a (T x N) on the device for cusmc_filter_get_history
+                             (cusmc_run needs no flag: it streams the history through a bounded ring) */
     int summary;          /* 1: per-step weighted posterior mean (one extra pass over the state) */
     /* Sharded runs (one process per GPU): N is the GLOBAL particle count; rank r of `world` owns the
      * global slots r*per .. min((r+1)*per, N) - 1, per = ceil(N / world).  world <= 1: one GPU. */
@@ -301,17 +303,23 @@ typedef struct cusmc_filter_config {
      * lw_t[i] = lw_{t-1}[i] + log p(y_t | x_t[i]).  The decision is taken on the device from the
      * integer weight sums, so it is identical on every rank of a sharded run and on the CPU oracle. */
     double ess_threshold;
+    /* distribution "mvt": the reference draws x_0 from the SAME distribution object as the transition
+     * noise (src/mcmc.cpp:73-79 -> MultiVariateTStudentDistribution::sample, src/statistics.cc.cpp:355-411),
+     * i.e. x_0 = m0 + chi (.) (Q_c0 xi) -- the default here too.  1 = draw a Normal x_0 instead
+     * (round 1's behaviour). */
+    int mvt_normal_init;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):
  *   xi0 [d][N] SoA; per step t = 1..T-1: xi [(T-1)][d][N], chi idem,
  *   u [(T-1)][N][B], j [(T-1)][N][B] (metropolis), u0 [(T-1)] host doubles (systematic),
- *   um [(T-1)][N] (multinomial). */
+ *   um [(T-1)][N] (multinomial), chi0 [d][N] SoA: the factors of the initial draw (mvt). */
 typedef struct cusmc_filter_draws {
     const double *xi0_dev, *xi_dev, *chi_dev, *u_dev;
     const uint32_t *j_dev;
     const double *u0_host;
     const double *um_dev;
+    const double *chi0_dev;
 } cusmc_filter_draws;
 
 int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_filter **out);
@@ -333,7 +341,7 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
  *                                  state buffer (peer loads).  Ancestors are GLOBAL indices and the
  *                                  noise is keyed by the global slot, so a sharded run reproduces the
  *                                  single-GPU run bit for bit.
- * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset, resampled; 2 spare }.
+ * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset, resampled, degenerate; 1 spare }.
  * Injected draws of a sharded run are this rank's shard (leading dimension = its particle count).
  */
 int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws);
@@ -360,23 +368,47 @@ int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all_handles);
  */
 int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws);
 int cusmc_filter_exchange_status(cusmc_filter *f, uint64_t *status);
+/* Bound of every spin-wait of the peer-memory exchanges (default 2 s).  Raise it when ranks share a
+ * device or a peer's stream may still be busy with earlier work when the run is enqueued. */
+int cusmc_filter_set_exchange_timeout(cusmc_filter *f, double seconds);
+/* Waits for the last run and reports what went wrong inside it: CUSMC_ERR_TIMEOUT (a scalar exchange
+ * of a sharded run timed out) or CUSMC_ERR_DEGENERATE (a step had no weight mass to resample from:
+ * its ancestors are the identity).  cusmc_filter_get_summary / _get_history / cusmc_run return the
+ * same status instead of handing out void results. */
+int cusmc_filter_status(cusmc_filter *f);
 
 /* Per-step outputs copied to the host (any pointer may be NULL):
  * mean [T][d] weighted posterior mean, ess [T], loglik [T] (log of the mean weight). */
 int cusmc_filter_get_summary(cusmc_filter *f, double *mean, double *ess, double *loglik);
 /* resampled[t] = 1 if step t drew new ancestors (always 1 without ess_threshold; resampled[0] = 0). */
 int cusmc_filter_get_resampled(cusmc_filter *f, int *resampled);
-/* History (needs keep_history): x_aos [T][N][d], w [T][N] (densities or normalised
- * weights), a [T][N]. */
+/* History (needs keep_history = 1): x_aos [T][n][d], a [T][n] (global parent ids, row 0 = identity)
+ * and w [T][n], the weights as the reference's R-level `weights` (src/run.rcpp.cpp:110-117):
+ *   resampler metropolis (reference mode): the raw densities, w_0 = 1/N (src/mcmc.cpp:85,212);
+ *   systematic / multinomial             : NORMALISED weights exp(lw - max) / sum (summing to one over
+ *                                          the whole cloud; 1/N at t = 0; cumulative over the steps
+ *                                          an ess_threshold run did not resample at).
+ * cusmc_filter_get_log_weights returns the raw log-weights [T][n] of the normalised resamplers
+ * (exactly what resampling consumed; row 0 is 0).  n = this rank's shard (N on one GPU). */
 int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a);
+int cusmc_filter_get_log_weights(cusmc_filter *f, double *lw);
 /* Device time of the last run's step loop (t = 1 .. T-1), ms, from CUDA events on the stream. */
 double cusmc_filter_last_ms(const cusmc_filter *f);
 /* Current device-resident state: x (SoA [d][N]), weights (N), ancestors of the last step (N). */
 int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa_dev, double **w_dev, uint32_t **a_dev);
 
-/* R-level run() (src/run.rcpp.cpp:58-126) on host pointers: allocates a filter, runs it,
- * returns weights [T][N] and posterior_x [T][N][d] exactly as the reference shapes them. */
+/* R-level run() (src/run.rcpp.cpp:58-126) on host pointers: runs the filter and returns weights
+ * [T][N] (semantics as cusmc_filter_get_history) and posterior_x [T][N][d] exactly as the reference
+ * shapes them; either may be NULL.  The history is STREAMED (the reference's io / return path,
+ * src/run.rcpp.cpp:110-125, src/io.cpp:7-43): step kernels write their rows into a two-chunk ring on
+ * the device, finished chunks travel device -> pinned host memory on a second stream while the next
+ * chunk computes, and the calling thread (plus helpers) copies them into the caller's arrays.  Device
+ * memory is bounded by the ring, whatever T.  Returns CUSMC_ERR_DEGENERATE if a step had no weight
+ * mass.  cusmc_run_ancestors also returns the ancestor indices a_t [T][N] (row 0 = identity), the
+ * genealogy needed to trace a particle's path through posterior_x. */
 int cusmc_run(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights, double *posterior_x);
+int cusmc_run_ancestors(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights,
+                        double *posterior_x, uint32_t *ancestors);
 
 /* ---- layout helpers -------------------------------------------------------------- */
 int cusmc_aos_to_soa_dev(cusmc_ctx *ctx, const double *aos_dev, double *soa_dev,

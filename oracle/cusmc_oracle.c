@@ -467,9 +467,9 @@ void orc_filter_metropolis(int dist, int64_t N, int d, int dy, int T, int B,
                            const double *F, const double *G,
                            const double *V, const double *Q_w, float nu,
                            const double *xi0, const double *u, const uint32_t *j,
-                           const double *xi, const double *chi,
+                           const double *xi, const double *chi, const double *chi0,
                            double *x_hist, double *w_hist, uint32_t *a_hist,
-                           double *mean_hist)
+                           double *mean_hist, int faithful)
 {
     size_t Nd = (size_t)N * d;
     double *xa = (double *)malloc(sizeof(double) * Nd);
@@ -477,10 +477,11 @@ void orc_filter_metropolis(int dist, int64_t N, int d, int dy, int T, int B,
     double *w = (double *)malloc(sizeof(double) * N);
     uint32_t *a = (uint32_t *)malloc(sizeof(uint32_t) * N);
 
-    /* initialize (ref: src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N.
-     * The MVT initial draw also multiplies by chi; initial chi are taken as 1
-     * unless the caller folds them into xi0 (the init path is not timed). */
-    orc_propagate(0, xa, NULL, NULL, NULL, m0, Q_c0, xi0, NULL, N, d);
+    /* initialize (ref: src/mcmc.cpp:63-85): the SAME distribution object draws x_0, so for "mvt"
+     * it is MultiVariateTStudentDistribution::sample (ref: src/statistics.cc.cpp:355-411):
+     * x_0 = chi (.) (Q_c0 xi) + m0; for "mvn" x_0 = Q_c0 xi + m0 (:258).  w_0 = 1/N (:85).
+     * chi0 == NULL with dist 1 keeps the Normal start (the library's mvt_normal_init switch). */
+    orc_propagate(dist == 1 && chi0 ? 1 : 0, xa, NULL, NULL, NULL, m0, Q_c0, xi0, chi0, N, d);
     for (int64_t i = 0; i < N; ++i) w[i] = 1 / (double)N;
     if (x_hist) memcpy(x_hist, xa, sizeof(double) * Nd);
     if (w_hist) memcpy(w_hist, w, sizeof(double) * N);
@@ -491,7 +492,8 @@ void orc_filter_metropolis(int dist, int64_t N, int d, int dy, int T, int B,
         orc_metropolis_hastings(a, w, u + off * N * B, j + off * N * B, N, B);
         orc_propagate(dist, xb, xa, a, G, NULL, Q_w, xi + off * Nd,
                       chi ? chi + off * Nd : NULL, N, d);
-        orc_reweight(dist, w, Y + (size_t)t * dy, xb, F, V, nu, N, d, dy, 0, 0);
+        /* faithful: determinant() + inverse() per particle, as ref: src/mcmc.cpp:193-215 does */
+        orc_reweight(dist, w, Y + (size_t)t * dy, xb, F, V, nu, N, d, dy, faithful, 0);
         double *tmp = xa; xa = xb; xb = tmp;
         if (x_hist) memcpy(x_hist + (size_t)t * Nd, xa, sizeof(double) * Nd);
         if (w_hist) memcpy(w_hist + (size_t)t * N, w, sizeof(double) * N);
@@ -1023,7 +1025,7 @@ static uint64_t fixed_from_unit(double wn, int shift)
 int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int B,
                    const double *Y, const double *m0, const double *Q_c0, const double *F,
                    const double *G, const double *V, const double *Q_w, float nu, uint64_t seed,
-                   const double *xi0, const double *xi, const double *chi, const double *u,
+                   const double *xi0, const double *chi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
                    double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
                    double ess_threshold, int *resampled)
@@ -1048,7 +1050,10 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
     {
         const double *z0 = xi0;
         if (!z0) { orc_rng_fill_normals(seed, 6, 0, 0, N, d, noise); z0 = noise; }
-        orc_step_det(0, 0, xa, NULL, NULL, NULL, NULL, Q_c0, m0, NULL, NULL, 0.0, nu, z0, NULL, N, d, dy);
+        /* "mvt": the initial draw is chi (.) (Q_c0 xi) + m0 too (ref: src/mcmc.cpp:73-79 ->
+         * src/statistics.cc.cpp:411); chi0 == NULL keeps the Normal start */
+        orc_step_det(dist == 1 && chi0 ? 1 : 0, 0, xa, NULL, NULL, NULL, NULL, Q_c0, m0, NULL, NULL, 0.0, nu, z0,
+                     chi0, N, d, dy);
         for (int64_t i = 0; i < N; ++i) w[i] = is_log ? 0.0 : 1.0 / (double)N;
     }
     for (int t = 0; t < T; ++t) {

@@ -102,7 +102,9 @@ void orc_reweight(int dist, double *w, const double *y, const double *x_aos,
 /* ---- a7: MCMC loop (ref: src/mcmc.cpp:239-309, src/particle_filter.cpp:6-39)
  * Runs t = 1..T-1: metropolis resample -> propagate -> reweight, keeping only
  * the running state (history optional).  Injected draws: xi0 [N*d] for
- * initialize, u/j [(T-1)*N*B], xi [(T-1)*N*d], chi idem (mvt only).
+ * initialize, u/j [(T-1)*N*B], xi [(T-1)*N*d], chi idem (mvt only), chi0 [N*d] the
+ * initial draw's per-component factors (mvt; NULL = Normal start).  faithful != 0
+ * recomputes determinant() + inverse() per particle in the reweight (ref: src/mcmc.cpp:193-215).
  * Outputs (any may be NULL): x_hist [T*N*d], w_hist [T*N], a_hist [T*N]
  * (row t=0 of a_hist is left untouched, as in the reference), and per-step
  * weighted moments mean_hist [T*d].  Q_c0, Q_w are the eigen factors
@@ -113,9 +115,9 @@ void orc_filter_metropolis(int dist, int64_t N, int d, int dy, int T, int B,
                            const double *F, const double *G,
                            const double *V, const double *Q_w, float nu,
                            const double *xi0, const double *u, const uint32_t *j,
-                           const double *xi, const double *chi,
+                           const double *xi, const double *chi, const double *chi0,
                            double *x_hist, double *w_hist, uint32_t *a_hist,
-                           double *mean_hist);
+                           double *mean_hist, int faithful);
 
 /* ======================= extended (parity unpinned) ======================== */
 
@@ -203,7 +205,7 @@ void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, 
 int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int B,
                    const double *Y, const double *m0, const double *Q_c0, const double *F,
                    const double *G, const double *V, const double *Q_w, float nu, uint64_t seed,
-                   const double *xi0, const double *xi, const double *chi, const double *u,
+                   const double *xi0, const double *chi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
                    double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
                    double ess_threshold, int *resampled);

@@ -82,8 +82,8 @@ class Oracle:
         L.orc_filter_metropolis.restype = None
         L.orc_filter_metropolis.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                             _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_float,
-                                            _dp, _dp, _u32p, _dp, _dp,
-                                            _dp, _dp, _u32p, _dp]
+                                            _dp, _dp, _u32p, _dp, _dp, _dp,
+                                            _dp, _dp, _u32p, _dp, C.c_int]
         L.orc_quadform_fma.restype = C.c_double
         L.orc_quadform_fma.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int, C.c_int]
         L.orc_det_exp.restype = C.c_double
@@ -124,7 +124,7 @@ class Oracle:
         L.orc_filter_det.restype = C.c_int
         L.orc_filter_det.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_float, C.c_uint64,
-                                     _dp, _dp, _dp, _dp, _u32p, _dp, _dp,
+                                     _dp, _dp, _dp, _dp, _dp, _u32p, _dp, _dp,
                                      _dp, _dp, _u32p, _dp, _dp, C.c_double, C.POINTER(C.c_int)]
 
     # ---- dense helpers ----------------------------------------------------
@@ -256,7 +256,7 @@ class Oracle:
         return w
 
     def filter_metropolis(self, dist, Y, m0, Q_c0, F, G, V, Q_w, nu, xi0, u, j, xi, chi=None,
-                          history=True):
+                          history=True, chi0=None, faithful=False):
         """Y: (dy, T).  xi0: (N, d); u, j: (T-1, N, B); xi (chi): (T-1, N, d)."""
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
@@ -267,6 +267,7 @@ class Oracle:
         j = np.ascontiguousarray(j, dtype=np.uint32)
         xi = f64(xi)
         chi_ = None if chi is None else f64(chi)
+        chi0_ = None if chi0 is None else f64(chi0)
         xh = np.zeros((T, N, d)) if history else None
         wh = np.zeros((T, N)) if history else None
         ah = np.zeros((T, N), dtype=np.uint32) if history else None
@@ -274,8 +275,8 @@ class Oracle:
         self.lib.orc_filter_metropolis(
             0 if dist == "mvn" else 1, N, d, dy, T, B, _p(colmajor(Y)), _p(f64(m0)),
             _p(colmajor(Q_c0)), _p(colmajor(F)), _p(colmajor(G)), _p(colmajor(V)),
-            _p(colmajor(Q_w)), float(nu), _p(xi0), _p(u), _p(j, _u32p), _p(xi), _p(chi_),
-            _p(xh), _p(wh), _p(ah, _u32p), _p(mh))
+            _p(colmajor(Q_w)), float(nu), _p(xi0), _p(u), _p(j, _u32p), _p(xi), _p(chi_), _p(chi0_),
+            _p(xh), _p(wh), _p(ah, _u32p), _p(mh), int(faithful))
         return dict(x=xh, w=wh, a=ah, mean=mh)
 
     # ---- extended -------------------------------------------------------------
@@ -383,7 +384,8 @@ class Oracle:
         return u, j
 
     def filter_det(self, dist, resampler, Y, m0, Q_c0, F, G, V, Q_w, N, nu=0.0, seed=0, B=10,
-                   xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, ess_threshold=0.0):
+                   xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, ess_threshold=0.0,
+                   chi0=None):
         """Production-order filter.  resampler: 'metropolis' | 'systematic' | 'multinomial'."""
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
@@ -401,7 +403,7 @@ class Oracle:
         rc = self.lib.orc_filter_det(
             0 if dist == "mvn" else 1, rs, N, d, dy, T, B, _p(colmajor(Y)), _p(f64(m0)),
             _p(colmajor(Q_c0)), _p(colmajor(F)), _p(colmajor(G)), _p(colmajor(V)), _p(colmajor(Q_w)),
-            float(nu), int(seed), _p(opt(xi0)), _p(opt(xi)), _p(opt(chi)), _p(opt(u)), _p(j_, _u32p),
+            float(nu), int(seed), _p(opt(xi0)), _p(opt(chi0)), _p(opt(xi)), _p(opt(chi)), _p(opt(u)), _p(j_, _u32p),
             _p(opt(u0)), _p(opt(um)), _p(xh), _p(wh), _p(ah, _u32p), _p(ess), _p(ll),
             float(ess_threshold), res.ctypes.data_as(C.POINTER(C.c_int)))
         if rc:

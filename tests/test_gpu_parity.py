@@ -434,11 +434,18 @@ def _eig_factor(S):
     return vec * np.sqrt(lam)
 
 
+def _raw_weights(h, resampler):
+    """What resampling consumed: densities in reference mode, log-weights otherwise."""
+    return h["w"] if resampler == "metropolis" else h["lw"]
+
+
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0)])
 @pytest.mark.parametrize("resampler", ["systematic", "multinomial", "metropolis"])
 @pytest.mark.parametrize("d", [2, 8])
-def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d):
-    """Same pre-drawn normals / uniforms on both sides: ancestors and particle states must agree
-    bit for bit at every step; log-weights too (MVN), ESS and log-likelihood to rounding."""
+def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d, kind, nu):
+    """Same pre-drawn normals / uniforms (and, for "mvt", chi factors -- the initial draw's included,
+    ref: src/mcmc.cpp:73-79) on both sides: ancestors and particle states must agree bit for bit at
+    every step; log-weights too (MVN), ESS and log-likelihood to rounding."""
     rng = np.random.default_rng(500 + d)
     N, T, B = 3000, 12, 10
     md = _model(d)
@@ -446,26 +453,94 @@ def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d):
     xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((T - 1, N, d))
     u, j = rng.random((T - 1, N, B)), rng.integers(0, N, (T - 1, N, B), dtype=np.uint32)
     u0, um = rng.random(T - 1), rng.random((T - 1, N))
-    pf = ctx.filter(N=N, Y=Y, resampler=resampler, B=B, keep_history=True, **md)
+    chi0 = chi = None
+    kw = {}
+    if kind == "mvt":
+        chi0 = np.sqrt(nu / rng.chisquare(nu, (N, d)))
+        chi = np.sqrt(nu / rng.chisquare(nu, (T - 1, N, d)))
+        kw = dict(chi0=torch_dev(chi0.T), chi=torch_dev(chi.transpose(0, 2, 1)))
+    pf = ctx.filter(N=N, Y=Y, resampler=resampler, B=B, keep_history=True, distribution=kind, df=nu, **md)
     pf.run(xi0=torch_dev(xi0.T), xi=torch_dev(xi.transpose(0, 2, 1)), u=torch_dev(u), j=torch_dev(j),
-           u0=u0, um=torch_dev(um))
+           u0=u0, um=torch_dev(um), **kw)
     h, s = pf.history(), pf.summary()
     pf.close()
     # the library uses an eigen factor of C0 / W; for scalar covariances it is sqrt(c) I up to
     # sign conventions of the Jacobi sweep (none applied to a diagonal matrix)
-    ref = orc.filter_det("mvn", resampler, Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
-                         _eig_factor(md["W"]), N, B=B, xi0=xi0, xi=xi, u=u, j=j, u0=u0, um=um)
+    ref = orc.filter_det(kind, resampler, Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, nu=nu, B=B, xi0=xi0, xi=xi, u=u, j=j, u0=u0, um=um,
+                         chi0=chi0, chi=chi)
     assert np.array_equal(h["a"], ref["a"])
     assert np.array_equal(h["x"], ref["x"])
+    if kind == "mvt":
+        # x_0 really carries the chi factors: m0 + chi0 (.) (Q_c0 xi0)
+        assert np.array_equal(h["x"][0], md["m0"] + chi0 * (xi0 @ _eig_factor(md["C0"]).T))
+    raw = _raw_weights(h, resampler)
     if resampler == "metropolis":
-        assert relerr(h["w"], ref["w"]) < 1e-13       # densities: CUDA exp vs libm exp
+        assert relerr(raw, ref["w"]) < 1e-13          # densities: CUDA exp / pow vs libm
+        assert np.all(raw[0] == 1.0 / N)              # w_0 = 1/N (src/mcmc.cpp:85)
     else:
-        assert np.array_equal(h["w"], ref["w"])
-        assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+        if kind == "mvn":
+            assert np.array_equal(raw, ref["w"])
+        else:
+            assert np.allclose(raw, ref["w"], rtol=1e-12, atol=1e-12)   # log1p: CUDA vs libm
+        assert np.allclose(s["ess"], ref["ess"], rtol=1e-9 if kind == "mvt" else 1e-12)
         assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
-    wn = np.exp(h["w"] - h["w"].max(axis=1, keepdims=True)) if resampler != "metropolis" else h["w"]
+        # the history hands out NORMALISED weights (1/N at t = 0)
+        wn = np.exp(raw - raw.max(axis=1, keepdims=True))
+        wn /= wn.sum(axis=1, keepdims=True)
+        assert np.allclose(h["w"], wn, rtol=1e-9, atol=1e-300)
+        assert np.allclose(h["w"][0], 1.0 / N, rtol=1e-12)
+    wn = np.exp(raw - raw.max(axis=1, keepdims=True)) if resampler != "metropolis" else raw
     mean = (wn[:, :, None] * h["x"]).sum(1) / wn.sum(1)[:, None]
     assert np.allclose(s["mean"], mean, rtol=1e-10, atol=1e-12)
+
+
+def test_mvt_normal_init_switch(ctx, orc):
+    """mvt_normal_init = 1 keeps round 1's Normal start; the default draws x_0 with chi factors."""
+    rng = np.random.default_rng(3)
+    d, N, T = 2, 512, 3
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    xi0 = rng.standard_normal((N, d))
+    out = {}
+    for flag in (False, True):
+        pf = ctx.filter(N=N, Y=Y, resampler="systematic", keep_history=True, distribution="mvt", df=4.0, seed=8,
+                        mvt_normal_init=flag, **md)
+        out[flag] = pf.run(xi0=torch_dev(xi0.T)).history()["x"][0]
+        pf.close()
+    base = xi0 @ _eig_factor(md["C0"]).T
+    assert np.array_equal(out[True], base)
+    ratio = out[False] / base                       # the device-drawn chi factors: positive, not all one
+    assert np.all(ratio > 0) and np.std(ratio) > 0.1
+    # their law: nu / chi^2 has mean nu / (nu - 2) = 2 at nu = 4 (heavy tailed: loose bound)
+    assert 1.5 < np.mean(ratio ** 2) < 3.5
+
+
+def test_eigen_factor_through_the_abi(ctx):
+    """a8 (ref: src/linear_algebra.cpp:10-23): the factor the library builds from C0 and W must satisfy
+    Q Q^T = Sigma for NON-diagonal covariances.  Q never crosses the ABI, so it is read off the
+    particles: unit-vector draws make x_0[k] - m0 = Q_c0[:, k] and, with G = 0, x_1[k] = Q_w[:, k]."""
+    rng = np.random.default_rng(2024)
+    for d in (2, 3, 5, 8):
+        C0, W = spd(rng, d), spd(rng, d) * 0.7
+        m0 = rng.standard_normal(d)
+        N, T = 64, 2
+        xi = np.zeros((N, d))
+        xi[:d] = np.eye(d)
+        pf = ctx.filter(N=N, Y=np.zeros((d, T)), m0=m0, C0=C0, F=np.eye(d), G=np.zeros((d, d)), V=np.eye(d), W=W,
+                        resampler="systematic", keep_history=True)
+        h = pf.run(xi0=torch_dev(xi.T), xi=torch_dev(xi.T[None]), u0=np.array([0.5])).history()
+        pf.close()
+        Qc0 = (h["x"][0, :d] - m0).T
+        # uniform weights at t = 0 and u0 = 0.5: the ancestors of step 1 are the identity
+        assert np.array_equal(h["a"][1], np.arange(N))
+        Qw = h["x"][1, :d].T
+        assert np.allclose(Qc0 @ Qc0.T, C0, rtol=0, atol=1e-13 * np.abs(C0).max() * d)
+        assert np.allclose(Qw @ Qw.T, W, rtol=0, atol=1e-13 * np.abs(W).max() * d)
+        # the eigen form, not just any factor: columns are orthogonal (Q^T Q = Lambda)
+        G_ = Qc0.T @ Qc0
+        assert np.allclose(G_ - np.diag(np.diag(G_)), 0.0, atol=1e-12)
+        assert np.allclose(np.sort(np.diag(G_)), np.linalg.eigvalsh(C0), rtol=1e-12)
 
 
 @pytest.mark.parametrize("resampler", ["systematic", "metropolis"])
@@ -532,6 +607,32 @@ def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
     assert np.allclose(sp["mean"], sf["mean"], rtol=1e-7, atol=1e-9)
 
 
+@pytest.mark.parametrize("N", [20000, 300000])
+def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, N):
+    """The one-kernel run (the C4 path) against the ORACLE itself, not just against the four-launch
+    path: device-drawn noise on one side, the oracle's Philox mirror on the other, no history --
+    final states, log-weights and ancestors bit for bit, ESS / log-likelihood of every step."""
+    rng = np.random.default_rng(N)
+    d, T = 2, 9
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=1234, summary=True, persistent=True, **md)
+    l0 = ctx.launch_count
+    pf.run()
+    launches = ctx.launch_count - l0
+    x, w, a = pf.state()
+    s = pf.summary()
+    pf.close()
+    assert launches == 2                                  # init_slots + ONE cooperative kernel
+    ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, seed=1234)
+    assert np.array_equal(a, ref["a"][-1])
+    assert np.array_equal(x.T, ref["x"][-1])
+    assert np.array_equal(w, ref["w"][-1])
+    assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+    assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
+
+
 @pytest.mark.parametrize("d,thr", [(2, 0.5), (8, 0.05)])
 def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
     """ess_threshold: resample only when ESS < threshold N, otherwise keep a_i = i and accumulate the
@@ -550,7 +651,7 @@ def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
     assert 0 < res[1:].sum() < T - 1                              # both kinds of step happened
     assert np.array_equal(h["a"], ref["a"])
     assert np.array_equal(h["x"], ref["x"])
-    assert np.array_equal(h["w"], ref["w"])
+    assert np.array_equal(h["lw"], ref["w"])
     assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
     kept = np.where(res[1:] == 0)[0] + 1
     assert all(np.array_equal(h["a"][t], np.arange(N)) for t in kept)
@@ -598,6 +699,85 @@ def test_filter_posterior_moments_vs_kalman(ctx, resampler):
         tol = (12 if resampler == "multinomial" else 6) * sd / np.sqrt(s["ess"][1:, None])
         assert np.all(np.abs(s["mean"][1:] - km[1:]) < tol)
         assert np.all(s["ess"][5:] > N / 10) and np.all(s["ess"] <= N * (1 + 1e-9))
+
+
+def test_filter_posterior_moments_vs_kalman_correlated(ctx):
+    """The same check on a model whose W, C0, V are full and F, G non-diagonal: the dense kernel path
+    and the eigen factors of non-diagonal covariances (a wrong rotation of Q_w would bias the mean)."""
+    rng = np.random.default_rng(12)
+    d, T, N = 3, 40, 400000
+    A = rng.standard_normal((d, d)) * 0.15
+    md = dict(m0=rng.standard_normal(d) * 0.3, C0=spd(rng, d), F=np.eye(d) + A, G=0.85 * np.eye(d) + A.T,
+              V=spd(rng, d) * 0.4, W=spd(rng, d) * 0.3)
+    # data simulated from the model itself, so the filter stays in its typical regime
+    x = md["m0"] + np.linalg.cholesky(md["C0"]) @ rng.standard_normal(d)
+    Y = np.zeros((d, T))
+    for t in range(1, T):
+        x = md["G"] @ x + np.linalg.cholesky(md["W"]) @ rng.standard_normal(d)
+        Y[:, t] = md["F"] @ x + np.linalg.cholesky(md["V"]) @ rng.standard_normal(d)
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=21, **md)
+    s = pf.run().summary()
+    pf.close()
+    km, P = kalman_means(Y, **md)
+    sd = np.sqrt(np.diag(P))
+    tol = 6 * sd[None, :] / np.sqrt(s["ess"][1:, None])
+    assert np.all(np.abs(s["mean"][1:] - km[1:]) < tol)
+    assert np.all(s["ess"][1:] > N / 50)
+
+
+def test_cusmc_run_streams_the_history(ctx):
+    """cusmc_run (the entry the R glue calls) through ctypes: its streamed history -- several ring
+    chunks -- equals the device-resident history of a filter object run with the same seed."""
+    import cusmc_b200
+    Y = np.loadtxt(os.path.join(HERE, "golden", "y_t.csv"), delimiter=",", skiprows=1).T
+    I = np.eye(2)
+    md = dict(m0=np.zeros(2), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
+    N, T = 20000, 61                      # a row is 560 KB: chunks of 14 steps, 5 chunks
+    for resampler in ("metropolis", "systematic"):
+        out = cusmc_b200.run(N, 2, T, Y, md["m0"], I, I, I, md["V"], md["W"], 0.0, resampler, "mvn", seed=77,
+                             ancestors=True)
+        pf = cusmc_b200.ParticleFilter(cusmc_b200.default_context(), N, Y[:, :T], resampler=resampler, seed=77,
+                                       keep_history=True, summary=False, persistent=False, **md)
+        h = pf.run().history()
+        pf.close()
+        assert out["posterior_x"].shape == (T, N, 2) and out["weights"].shape == (T, N)
+        assert np.array_equal(out["posterior_x"], h["x"])
+        assert np.array_equal(out["ancestors"], h["a"])
+        assert np.array_equal(out["weights"], h["w"])
+        if resampler == "systematic":
+            assert np.allclose(out["weights"].sum(axis=1), 1.0, rtol=1e-9)
+    # the plain entry (no ancestors) gives the same arrays
+    out2 = cusmc_b200.run(N, 2, T, Y, md["m0"], I, I, I, md["V"], md["W"], 0.0, "systematic", "mvn", seed=77)
+    assert np.array_equal(out2["posterior_x"], out["posterior_x"]) and np.array_equal(out2["weights"], out["weights"])
+
+
+def test_degenerate_step_is_reported(ctx):
+    """A step whose weights have no mass (NaN observation): identity ancestors, and every getter that
+    hands results out returns CUSMC_ERR_DEGENERATE instead of stale ancestors and CUSMC_OK."""
+    import cusmc_b200
+    from cusmc_b200 import _lib
+    I = np.eye(2)
+    md = dict(m0=np.zeros(2), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
+    Y = np.zeros((2, 6))
+    Y[:, 2] = np.nan                      # every log-weight of step 2 is NaN -> step 3 cannot resample
+    for resampler in ("systematic", "multinomial"):
+        for persistent in ((True, False) if resampler == "systematic" else (False,)):
+            pf = ctx.filter(N=5000, Y=Y, resampler=resampler, seed=3, keep_history=not persistent,
+                            persistent=persistent, **md)
+            pf.run()
+            with pytest.raises(cusmc_b200.CusmcError) as e:
+                pf.summary()
+            assert e.value.code == _lib.ERR_DEGENERATE and "step 3" in str(e.value)
+            with pytest.raises(cusmc_b200.CusmcError):
+                pf.status()
+            pf.close()
+    with pytest.raises(cusmc_b200.CusmcError) as e:
+        cusmc_b200.run(1000, 2, 6, Y, md["m0"], I, I, I, md["V"], md["W"], 0.0, "systematic", "mvn")
+    assert e.value.code == _lib.ERR_DEGENERATE
+    # a healthy run reports nothing
+    pf = ctx.filter(N=5000, Y=np.zeros((2, 6)), resampler="systematic", seed=3, **md)
+    pf.run().status()
+    pf.close()
 
 
 def test_run_r_api(ctx):

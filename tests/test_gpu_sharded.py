@@ -68,7 +68,7 @@ def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d
     a = np.concatenate([p["a"] for p in parts])
     assert np.array_equal(a, h["a"][-1])
     assert np.array_equal(x.T, h["x"][-1])
-    assert np.array_equal(w, h["w"][-1])
+    assert np.array_equal(w, h.get("lw", h["w"])[-1])      # raw weights: log-weights / densities
     assert all(int(p["status"]) == 0 for p in parts)      # no spin-wait timed out
     for p in parts:          # every rank reports the GLOBAL summary
         if resampler != "metropolis":
@@ -86,7 +86,7 @@ def test_sharded_adaptive_resampling(ctx, tmp_path):
     parts = run_sharded(tmp_path, 2, cfg)
     assert np.array_equal(np.concatenate([p["a"] for p in parts]), h["a"][-1])
     assert np.array_equal(np.concatenate([p["x"] for p in parts], axis=1).T, h["x"][-1])
-    assert np.array_equal(np.concatenate([p["w"] for p in parts]), h["w"][-1])
+    assert np.array_equal(np.concatenate([p["w"] for p in parts]), h["lw"][-1])
     kept = [t for t in range(1, cfg["T"]) if np.array_equal(h["a"][t], np.arange(cfg["N"]))]
     assert 0 < len(kept) < cfg["T"] - 1
 

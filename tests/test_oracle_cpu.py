@@ -272,6 +272,37 @@ def test_filter_reference_loop_equals_det_loop(orc):
     assert np.allclose(r1["w"], r2["w"], rtol=1e-11)
 
 
+def test_filter_mvt_initial_draw_carries_chi(orc):
+    """ref: src/mcmc.cpp:73-79 builds ONE distribution object and uses it for the initial draw as well,
+    so an "mvt" run starts from x_0 = m0 + chi (.) (Q_c0 xi) (src/statistics.cc.cpp:411).  Both
+    statements of the loop take the factors of the initial draw and agree; without them the start
+    is the Normal one (the library's mvt_normal_init switch)."""
+    rng = np.random.default_rng(9)
+    N, d, T, B, nu = 300, 3, 6, 10, 4.0
+    I = np.eye(d)
+    Y = rng.standard_normal((d, T))
+    m0 = rng.standard_normal(d)
+    Qc0 = np.linalg.cholesky(spd(rng, d))
+    xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((T - 1, N, d))
+    chi0, chi = np.sqrt(nu / rng.chisquare(nu, (N, d))), np.sqrt(nu / rng.chisquare(nu, (T - 1, N, d)))
+    u, j = rng.random((T - 1, N, B)), rng.integers(0, N, (T - 1, N, B), dtype=np.uint32)
+    G, Qw, V = 0.9 * I, 0.6 * I, 0.5 * I
+    r1 = orc.filter_metropolis("mvt", Y, m0, Qc0, I, G, V, Qw, nu, xi0, u, j, xi, chi=chi, chi0=chi0)
+    r2 = orc.filter_det("mvt", "metropolis", Y, m0, Qc0, I, G, V, Qw, N, nu=nu, B=B, xi0=xi0, xi=xi, u=u, j=j,
+                        chi=chi, chi0=chi0)
+    want0 = m0 + chi0 * (xi0 @ Qc0.T)
+    assert np.allclose(r1["x"][0], want0, rtol=1e-14, atol=1e-14)
+    assert np.allclose(r2["x"][0], want0, rtol=1e-14, atol=1e-14)
+    assert np.array_equal(r1["a"][1:], r2["a"][1:])
+    assert np.allclose(r1["x"], r2["x"], rtol=1e-12, atol=1e-12)
+    assert np.allclose(r1["w"], r2["w"], rtol=1e-11)
+    r3 = orc.filter_det("mvt", "metropolis", Y, m0, Qc0, I, G, V, Qw, N, nu=nu, B=B, xi0=xi0, xi=xi, u=u, j=j, chi=chi)
+    assert np.allclose(r3["x"][0], m0 + xi0 @ Qc0.T, rtol=1e-14, atol=1e-14)
+    # faithful reweight (per-particle determinant + inverse, src/mcmc.cpp:193-215) changes no bit
+    r4 = orc.filter_metropolis("mvt", Y, m0, Qc0, I, G, V, Qw, nu, xi0, u, j, xi, chi=chi, chi0=chi0, faithful=True)
+    assert np.array_equal(r4["w"], r1["w"]) and np.array_equal(r4["a"], r1["a"])
+
+
 # ---- MH chains ------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 6.0)])
 def test_mh_chains_oracle_targets_the_right_law(orc, kind, nu):
