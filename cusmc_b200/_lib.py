@@ -29,7 +29,7 @@ RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1, 2
 MAX_DIM = 32
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
-FILTER_IPC_BUFFERS = 5
+FILTER_IPC_BUFFERS = 7
 
 
 class FilterConfig(C.Structure):
@@ -38,7 +38,7 @@ class FilterConfig(C.Structure):
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
         ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci), ("ess_threshold", dbl),
-        ("mvt_normal_init", ci),
+        ("mvt_normal_init", ci), ("reproducible_rng", ci),
     ]
 
 
@@ -87,6 +87,7 @@ PROTOTYPES = {
     "cusmc_filter_run": (ci, [vp, C.POINTER(FilterDraws)]),
     "cusmc_filter_begin": (ci, [vp, C.POINTER(FilterDraws)]),
     "cusmc_filter_weigh": (ci, [vp, ci]),
+    "cusmc_filter_weigh_phase": (ci, [vp, ci, ci, vp]),
     "cusmc_filter_resample": (ci, [vp, ci]),
     "cusmc_filter_propagate": (ci, [vp, ci]),
     "cusmc_filter_mark": (ci, [vp, ci]),

@@ -381,9 +381,19 @@ class PreparedDensity:
         self.sigma_p = _hp(self._sigma)
 
 
+TILE = 2048     # particles per weight-image tile (csrc/resample.cuh: kTile)
+
+
+def shard_size(N, world):
+    """Slots per rank of a sharded filter (the rule of cusmc_filter_create): ceil(N / world) rounded up to
+    whole weight-image tiles, so a sharded run has the tiles -- hence the bits -- of the single-GPU run."""
+    per = -(-int(N) // max(1, int(world)))
+    return per if world <= 1 else -(-per // TILE) * TILE
+
+
 def _filter_config(N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10, df=0.0,
                    noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                   persistent=True, ess_threshold=0.0, mvt_normal_init=False):
+                   persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False):
     """cusmc_filter_config from numpy inputs; returns (config, arrays to keep alive while it is used)."""
     Y = np.asarray(Y, dtype=np.float64)
     if Y.ndim != 2:
@@ -404,6 +414,7 @@ def _filter_config(N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metr
     cfg.persistent = 0 if persistent else -1      # one cooperative kernel per run when eligible
     cfg.ess_threshold = float(ess_threshold)      # 0: resample every step (the reference's behaviour)
     cfg.mvt_normal_init = int(mvt_normal_init)    # "mvt": x_0 = m0 + chi (.) (Q xi) unless set
+    cfg.reproducible_rng = int(reproducible_rng)  # device-drawn normals a host can regenerate bit for bit
     return cfg, keep
 
 
@@ -412,14 +423,14 @@ class ParticleFilter:
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
                  df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                 persistent=True, ess_threshold=0.0, mvt_normal_init=False):
+                 persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False):
         self.ctx = ctx
         cfg, self._keep = _filter_config(N, Y, m0, C0, F, G, V, W, distribution, resampler, B, df, noise_scale,
                                          seed, keep_history, summary, rank, world, persistent, ess_threshold,
-                                         mvt_normal_init)
+                                         mvt_normal_init, reproducible_rng)
         self.dy, self.T, self.d, self.N = cfg.dy, cfg.T, cfg.d, int(N)
         self._world = int(world)
-        per = -(-self.N // max(1, int(world)))
+        per = shard_size(self.N, int(world))
         self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
         self.keep_history = bool(keep_history)
         self.is_log = cfg.resampler != RESAMPLE_METROPOLIS
@@ -482,7 +493,7 @@ class ParticleFilter:
         self.ctx.synchronize()
         torch.cuda.synchronize()
         n, dev = self.n_local, self.ctx.device
-        per = self.N if self.n_local == self.N else -(-self.N // max(1, self._world))
+        per = self.N if self._world <= 1 else shard_size(self.N, self._world)
         x = _device_view(px.value, (self.d, per), "<f8", dev)[:, :n].cpu().numpy()
         w = _device_view(pw.value, (per,), "<f8", dev)[:n].cpu().numpy()
         a = _device_view(pa.value, (per,), "<i4", dev)[:n].cpu().numpy().view(np.uint32)

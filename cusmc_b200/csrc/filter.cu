@@ -16,8 +16,10 @@
 #include "hostmath.h"
 #include "filter_types.cuh"
 #include "mailbox.cuh"
+#include "pf_fused_impl.cuh"
 #include "pf_step.cuh"
 #include "resample.cuh"
+#include "tile_update.cuh"
 
 #include "../../include/cusmc_detmath.h"
 #include "../../include/cusmc_philox.h"
@@ -417,10 +419,15 @@ static int eigen_factor(cusmc_ctx *ctx, const double *S, int d, std::vector<doub
     return CUSMC_OK;
 }
 
+// Exported buffers, in this order: x[0], x[1], ancestors, weights, mailbox, weight images 0 and 1
+// (a reference-mode filter has no images: it exports its weights twice more, never read).
+enum { kIpcBuffers = CUSMC_FILTER_IPC_BUFFERS };
+
 static void detach_peers(cusmc_filter *f)
 {
     if (!f->attached) return;
-    CusmcPeers *tabs[5] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail};
+    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail,
+                                     &f->peer_img[0], &f->peer_img[1]};
     for (CusmcPeers *t : tabs)
         for (int r = 0; r < f->world; ++r)
             if (r != f->rank && t->ptr[r]) cudaIpcCloseMemHandle(t->ptr[r]);
@@ -440,7 +447,9 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     cudaFree(f->cdf);
     cudaFree(f->slots);
     cudaFree(f->moments);
-    cudaFree(f->scan_state);
+    cudaFree(f->img[0]);
+    cudaFree(f->img[1]);
+    cudaFree(f->rank_sums);
     cudaFree(f->persist);
     cudaFree(f->mail);
     cudaFree(f->mail_err);
@@ -482,8 +491,11 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     const int64_t N = cfg->N;
     f->world = world;
     f->rank = world == 1 ? 0 : cfg->rank;
+    // a shard is a whole number of weight-image tiles, so the tiles of a sharded run are the tiles of the
+    // single-GPU run and both produce the same bits
     f->per = (N + world - 1) / world;
-    f->lo = (int64_t)f->rank * f->per;
+    if (world > 1) f->per = (f->per + kTile - 1) / kTile * kTile;
+    f->lo = std::min<int64_t>((int64_t)f->rank * f->per, N);
     f->n = std::max<int64_t>(0, std::min<int64_t>(f->per, N - f->lo));
     f->Y.assign(cfg->Y, cfg->Y + (size_t)dy * T);
     f->m0.assign(cfg->m0, cfg->m0 + d);
@@ -525,7 +537,15 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     if (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL) alloc((void **)&f->cdf, sizeof(uint64_t) * P);
     alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
     alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
-    alloc(&f->scan_state, cusmc_scan_state_bytes(f->per));
+    if (f->is_log) {
+        // two weight images (step parity): step t reads image t - 1 while it writes image t
+        const size_t img_bytes = sizeof(unsigned long long) * (size_t)fimage_words(f->per);
+        for (int b = 0; b < 2; ++b) {
+            alloc((void **)&f->img[b], img_bytes);
+            if (e == cudaSuccess) e = cudaMemset(f->img[b], 0, sizeof(unsigned long long) * (size_t)fimage_header_words(f->per));
+        }
+        if (world > 1) alloc((void **)&f->rank_sums, sizeof(unsigned long long) * 3 * CUSMC_MAX_PEERS);
+    }
     if (world > 1) {
         const size_t mail_bytes = sizeof(unsigned long long) * 4 * 3 * (size_t)world * (size_t)T;
         alloc((void **)&f->mail, mail_bytes);
@@ -554,8 +574,6 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
 }
 
 // ---- sharded runs: peer mapping of the state ---------------------------------------------------
-// Exported buffers, in this order: x[0], x[1], ancestors, weights, mailbox.
-enum { kIpcBuffers = CUSMC_FILTER_IPC_BUFFERS };
 
 extern "C" int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles)
 {
@@ -564,7 +582,8 @@ extern "C" int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles)
     CUSMC_REQUIRE(ctx, handles != nullptr, "handles is NULL");
     static_assert(sizeof(cudaIpcMemHandle_t) == CUSMC_IPC_HANDLE_BYTES, "IPC handle size");
     CUSMC_REQUIRE(ctx, f->world > 1, "not a sharded filter");
-    void *bufs[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail};
+    void *bufs[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail, f->img[0] ? (void *)f->img[0] : (void *)f->lw,
+                               f->img[1] ? (void *)f->img[1] : (void *)f->lw};
     for (int b = 0; b < kIpcBuffers; ++b) {
         cudaIpcMemHandle_t h;
         CUSMC_CUDA(ctx, cudaIpcGetMemHandle(&h, bufs[b]));
@@ -581,8 +600,10 @@ extern "C" int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all
     CUSMC_REQUIRE(ctx, !f->attached, "peers are already attached");
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
     CUSMC_REQUIRE(ctx, f->world > 1, "not a sharded filter");
-    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail};
-    void *mine[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail};
+    CusmcPeers *tabs[kIpcBuffers] = {&f->peer_x[0], &f->peer_x[1], &f->peer_anc, &f->peer_lw, &f->peer_mail,
+                                     &f->peer_img[0], &f->peer_img[1]};
+    void *mine[kIpcBuffers] = {f->x[0], f->x[1], f->anc, f->lw, f->mail, f->img[0] ? (void *)f->img[0] : (void *)f->lw,
+                               f->img[1] ? (void *)f->img[1] : (void *)f->lw};
     for (int b = 0; b < kIpcBuffers; ++b) {
         *tabs[b] = CusmcPeers{};
         tabs[b]->per_rank = f->per;
@@ -658,6 +679,56 @@ int cusmc_filter_init_slots(cusmc_filter *f)
     return CUSMC_OK;
 }
 
+// Does step t leave its log-weights in f->lw?  Nothing in a fused systematic step reads them (the weight
+// image carries the weights), so they are stored only where somebody needs them: the summary's
+// moment pass, the history, adaptive resampling (weights accumulate), the multinomial search's CDF
+// comes from the image too -- and the LAST step, so that cusmc_filter_state_dev hands out the final
+// log-weights.  Reference mode (metropolis) always keeps its densities: the resampler reads them.
+static bool filter_stores_weights(const cusmc_filter *f, int t)
+{
+    const cusmc_filter_config &cfg = f->cfg;
+    return !f->is_log || cfg.summary || cfg.keep_history || cfg.ess_threshold > 0.0 || t == cfg.T - 1;
+}
+
+// The step arguments common to t = 0 and t >= 1.
+static StepArgs filter_step_args(cusmc_filter *f, int t)
+{
+    const cusmc_filter_config &cfg = f->cfg;
+    StepArgs a{};
+    a.lw = filter_stores_weights(f, t) ? f->lw : nullptr;
+    a.n_out = f->n;
+    a.ld_new = a.ld_prev = f->per;
+    a.ld_noise = f->n;
+    a.i0 = f->lo;
+    a.seed = cfg.seed;
+    a.step = (uint64_t)t;
+    a.nu = cfg.nu;
+    a.d = cfg.d;
+    a.dy = cfg.dy;
+    a.fast_noise = cfg.reproducible_rng ? 0 : 1;
+    if (f->world > 1) {
+        a.world = f->world;
+        a.rank = f->rank;
+        a.per_rank = make_fast_div((uint32_t)f->per);
+    }
+    return a;
+}
+
+static pffused::FusedArgs filter_fused_args(cusmc_filter *f, const StepArgs &a, int t)
+{
+    pffused::FusedArgs fa{};
+    fa.s = a;
+    fa.img_new = f->img[t & 1];
+    fa.img_prev = f->img[(t & 1) ^ 1];
+    fa.img_prev_peer = f->world > 1 ? (const unsigned long long *const *)f->peer_img[(t & 1) ^ 1].table_dev : nullptr;
+    fa.img_hdr_words = fimage_header_words(f->per);
+    fa.tiles_alloc = (uint32_t)fimage_tiles(f->per);
+    fa.N_global = (uint32_t)f->cfg.N;
+    fa.tiles_per_rank = (uint32_t)(f->per / kTile > 0 ? (f->per + kTile - 1) / kTile : 1);
+    fa.shift = f->shift;
+    return fa;
+}
+
 extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws)
 {
     if (!f) return CUSMC_ERR_INVALID;
@@ -670,24 +741,13 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     cudaStream_t st = ctx->stream;
     CUSMC_CHECK(cusmc_filter_init_slots(f));
     CUSMC_CUDA(ctx, cudaMemsetAsync(f->moments, 0, sizeof(double) * (size_t)T * (2 + d), st));
-    CUSMC_CUDA(ctx, cudaMemsetAsync(f->scan_state, 0, sizeof(uint64_t), st));   // the arrival counter
     // t = 0: initialize (src/mcmc.cpp:63-85): x_0 = m0 + Q_c0 xi, w_0 = 1/N
     f->cur = 0;
-    StepArgs a{};
+    StepArgs a = filter_step_args(f, 0);
     a.x_new = f->x[0];
     a.x_prev = f->x[1];
     a.xi = f->draws.xi0_dev;
-    a.lw = f->lw;
-    a.lw_max = f->is_log ? &f->slots[0].lw_max : nullptr;
-    a.n_out = f->n;
-    a.ld_new = a.ld_prev = f->per;
-    a.ld_noise = f->n;
-    a.i0 = f->lo;
-    a.seed = cfg.seed;
-    a.step = 0;
-    a.nu = cfg.nu;
-    a.d = d;
-    a.dy = dy;
+    a.lw_max = nullptr;
     // "mvt": x_0 = m0 + chi (.) (Q_c0 xi), the reference's initialize() draws from the same distribution
     // object as the transition noise (src/mcmc.cpp:73-79 -> src/statistics.cc.cpp:379-411)
     a.kind = (cfg.kind == CUSMC_MVT && !cfg.mvt_normal_init) ? CUSMC_MVT : CUSMC_MVN;
@@ -700,8 +760,16 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
         a.hist_x = f->hist_x;
         a.hist_w = f->hist_w;
     }
-    CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
-                                  f->m0.data(), f->ep, a, f->draws.xi0_dev == nullptr));
+    if (f->is_log) {
+        // the fused kernel also leaves the weight image of step 0 (constant log-weight 0)
+        pffused::FusedArgs fa = filter_fused_args(f, a, 0);
+        fa.mode = pffused::kParentSelf;
+        CUSMC_CHECK(cusmc_launch_fused(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
+                                       f->m0.data(), f->ep, fa, f->draws.xi0_dev == nullptr));
+    } else {
+        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr,
+                                      f->m0.data(), f->ep, a, f->draws.xi0_dev == nullptr));
+    }
     f->next_t = 1;
     f->ran = false;
     return CUSMC_OK;
@@ -719,48 +787,83 @@ static double filter_ess_bound(const cusmc_filter *f)
     return f->cfg.ess_threshold * (double)f->cfg.N * std::ldexp(1.0, f->shift);
 }
 
-// True when slot[t].sum_q is already GLOBAL at the end of weigh(t)'s tile scan (one GPU, or the
-// sums exchange rides in that kernel): the scan then also leaves the constants of resample(t + 1).
-static bool filter_consts_fused(const cusmc_filter *f)
+// The tile update of step t (tile_update.cu), all of it or the phases named: global maximum, rescaled
+// tile prefixes and totals, the constants / start tiles of step t + 1.
+static int filter_tile_update(cusmc_filter *f, int t, int phases)
 {
-    return f->cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC && f->is_log && (f->world == 1 || f->fused);
+    const cusmc_filter_config &cfg = f->cfg;
+    UpdateArgs u{};
+    u.img = f->img[t & 1];
+    u.slot = f->slots + t;
+    u.slot_next = t + 1 < cfg.T ? f->slots + t + 1 : nullptr;
+    u.rank_sums = f->rank_sums;
+    u.tiles = (f->n + kTile - 1) / kTile;
+    u.tiles_alloc = fimage_tiles(f->per);
+    u.lo = (unsigned)f->lo;
+    u.N_global = (unsigned)cfg.N;
+    u.u0_next = (t + 1 < cfg.T && cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) ? filter_u0(f, t + 1) : 0.0;
+    u.ess_bound = cfg.ess_threshold > 0.0 ? filter_ess_bound(f) : 0.0;
+    u.rank = f->rank;
+    u.world = f->world;
+    u.phases = phases;
+    u.mail = filter_mail(f);
+    u.cell_max = mail_cell(t, kCellMax, f->world);
+    u.cell_sums = mail_cell(t, kCellSums, f->world);
+    return cusmc_launch_tile_update(f->ctx, u);
 }
 
-// After step t's weights exist and slot[t].lw_max holds the GLOBAL max: fixed-point sums and tile
-// prefixes (log modes), posterior moments, history.
+static int filter_moments(cusmc_filter *f, int t)
+{
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    if (!cfg.summary || f->n == 0) return CUSMC_OK;
+    const int mom_grid = (int)std::min<int64_t>((f->n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
+    moments_kernel<<<mom_grid, kThreads, 0, ctx->stream>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, f->n,
+                                                           f->per, cfg.d, f->moments + (size_t)t * (2 + cfg.d));
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+// After step t's particles exist: the weight image becomes global (log modes), posterior moments.
 extern "C" int cusmc_filter_weigh(cusmc_filter *f, int t)
 {
     if (!f) return CUSMC_ERR_INVALID;
     cusmc_ctx *ctx = f->ctx;
     const cusmc_filter_config &cfg = f->cfg;
     CUSMC_REQUIRE(ctx, t >= 0 && t < cfg.T && f->next_t == t + 1, "weigh(t) follows begin / propagate(t)");
+    CUSMC_REQUIRE(ctx, f->world == 1 || f->fused || !f->is_log,
+                  "a sharded filter driven phase by phase calls cusmc_filter_weigh_phase (scalar exchanges in between)");
     CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int d = cfg.d;
-    const int64_t n = f->n, P = f->per;
-    cudaStream_t st = ctx->stream;
-    const MailArgs mail = filter_mail(f);
-    ScatterSetup next{};
-    if (filter_consts_fused(f) && t + 1 < cfg.T) {
-        next.enabled = 1;
-        next.u0 = filter_u0(f, t + 1);
-        next.ess_bound = cfg.ess_threshold > 0.0 ? filter_ess_bound(f) : 0.0;
-        next.N_global = (uint32_t)cfg.N;
-    }
-    if (f->is_log)
-        CUSMC_CHECK(cusmc_launch_weights_sum(ctx, f->lw, 1, &f->slots[t].lw_max, n, f->shift, &f->slots[t].sum_q,
-                                             f->scan_state, cfg.summary != 0 || cfg.ess_threshold > 0.0, &mail, t,
-                                             &next));
-    if (cfg.summary && n > 0) {
-        const int mom_grid = (int)std::min<int64_t>((n + kThreads * 4 - 1) / (kThreads * 4), (int64_t)ctx->sm_count * 8);
-        moments_kernel<<<mom_grid, kThreads, 0, st>>>(f->x[f->cur], f->lw, &f->slots[t].lw_max, f->is_log, n, P, d,
-                                                      f->moments + (size_t)t * (2 + d));
-        CUSMC_LAUNCHED(ctx);
-    }
-    return CUSMC_OK;
+    if (f->is_log) CUSMC_CHECK(filter_tile_update(f, t, kUpdAll));
+    return filter_moments(f, t);
 }
 
-// Ancestors of step t (src/mcmc.cpp:295) from the weights of step t - 1.  Sharded systematic runs
-// need slot[t-1].sum_q = the GLOBAL mass and slot[t-1].cdf_offset = the mass on lower ranks.
+// The same in three phases, for callers that carry the scalars themselves (the NCCL formulation,
+// cusmc_b200/sharded.py): phase 0 leaves this rank's maximum in slot[t] word 0 (all-reduce MAX it);
+// phase 1 rescales and scans against that maximum and leaves this rank's sums in words 1..2 (all-gather
+// words 1..3 of every rank into rank_sums_dev, 3 words per rank); phase 2 derives the global totals,
+// rank offsets and the next step's constants from rank_sums_dev, then the moments.
+extern "C" int cusmc_filter_weigh_phase(cusmc_filter *f, int t, int phase, const uint64_t *rank_sums_dev)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    const cusmc_filter_config &cfg = f->cfg;
+    CUSMC_REQUIRE(ctx, t >= 0 && t < cfg.T && f->next_t == t + 1, "weigh(t) follows begin / propagate(t)");
+    CUSMC_REQUIRE(ctx, phase >= 0 && phase <= 2, "phase must be 0, 1 or 2");
+    CUSMC_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!f->is_log) return phase == 2 ? filter_moments(f, t) : CUSMC_OK;
+    if (phase == 2 && f->world > 1) {
+        CUSMC_REQUIRE(ctx, rank_sums_dev != nullptr, "phase 2 needs the all-gathered sums");
+        CUSMC_CUDA(ctx, cudaMemcpyAsync(f->rank_sums, rank_sums_dev, sizeof(uint64_t) * 3 * (size_t)f->world,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    CUSMC_CHECK(filter_tile_update(f, t, phase == 0 ? kUpdMax : phase == 1 ? kUpdScan : kUpdConsts));
+    return phase == 2 ? filter_moments(f, t) : CUSMC_OK;
+}
+
+// Ancestors of step t (src/mcmc.cpp:295) from the weights of step t - 1.  Systematic resampling has no
+// pass of its own any more: every block of the fused step kernel looks its children's parents up in
+// the weight image (pf_fused_impl.cuh), so this is a no-op for it.
 extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
 {
     if (!f) return CUSMC_ERR_INVALID;
@@ -778,24 +881,18 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
         return cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log,
                                        f->lo, n, sharded ? &f->peer_lw : nullptr);
     }
+    if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) return CUSMC_OK;
+    // multinomial: materialise the global CDF from the image, one binary search per child
     StepSlot *prev = &f->slots[t - 1];
-    if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
-        const double u0 = filter_u0(f, t);
-        const bool adaptive = cfg.ess_threshold > 0.0;
-        return cusmc_launch_scan(ctx, n, N, &prev->sum_q, sharded ? &prev->cdf_offset : nullptr, f->scan_state,
-                                 nullptr, f->anc, f->lo, 0, N, u0, sharded ? &f->peer_anc : nullptr,
-                                 adaptive ? &prev->sum_q2 : nullptr, adaptive ? &f->slots[t].resampled : nullptr,
-                                 filter_ess_bound(f), filter_consts_fused(f), &f->slots[t].degenerate);
-    }
-    CUSMC_CHECK(cusmc_launch_scan(ctx, n, N, &prev->sum_q, nullptr, f->scan_state, f->cdf, nullptr, 0, 0, 0, 0.0,
-                                  nullptr));
+    CUSMC_CHECK(cusmc_launch_image_cdf(ctx, f->img[(t - 1) & 1], f->per, n, f->rank, f->cdf));
     const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
     return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc,
                                     &f->slots[t].degenerate);
 }
 
-// Propagate and reweight, fused (src/mcmc.cpp:298-307).  Sharded: every rank's ancestors of step t
-// and state of step t - 1 must be complete (barrier after resample).
+// Propagate and reweight, fused (src/mcmc.cpp:298-307) -- and, for the normalised resamplers, the
+// parent lookup before and the tile's weight image after, in the same kernel.  Sharded: every rank's
+// image and state of step t - 1 must be complete (the exchanges inside weigh(t - 1) guarantee it).
 extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
 {
     if (!f) return CUSMC_ERR_INVALID;
@@ -809,24 +906,12 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
     const size_t off = (size_t)(t - 1);
     double c[CUSMC_MAX_DIM];
     cusmc_whiten_observation(f->Winv, dy, f->Y.data() + (size_t)t * dy, c);
-    StepArgs a{};
+    StepArgs a = filter_step_args(f, t);
     a.x_new = f->x[f->cur ^ 1];
     a.x_prev = f->x[f->cur];
     a.anc = f->anc;
     a.xi = dr.xi_dev ? dr.xi_dev + off * n * d : nullptr;
     a.chi = dr.chi_dev ? dr.chi_dev + off * n * d : nullptr;
-    a.lw = f->lw;
-    a.lw_max = f->is_log ? &f->slots[t].lw_max : nullptr;
-    a.resampled = cfg.ess_threshold > 0.0 ? (const unsigned long long *)&f->slots[t].resampled : nullptr;
-    a.n_out = n;
-    a.ld_new = a.ld_prev = f->per;
-    a.ld_noise = n;
-    a.i0 = f->lo;
-    a.seed = cfg.seed;
-    a.step = (uint64_t)t;
-    a.nu = cfg.nu;
-    a.d = d;
-    a.dy = dy;
     a.kind = cfg.kind;
     a.has_prev = 1;
     a.rng_stream = CUSMC_STREAM_NORMAL;
@@ -836,14 +921,23 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
         a.hist_w = f->hist_w + row * n;
         a.hist_a = f->hist_a + row * n;
     }
-    if (f->world > 1) {
-        a.world = f->world;
-        a.rank = f->rank;
-        a.per_rank = make_fast_div((uint32_t)f->per);
-        a.x_prev_peer = (const double *const *)f->peer_x[f->cur].table_dev;
+    if (f->world > 1) a.x_prev_peer = (const double *const *)f->peer_x[f->cur].table_dev;
+    if (f->is_log) {
+        pffused::FusedArgs fa = filter_fused_args(f, a, t);
+        if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
+            fa.mode = pffused::kParentLookup;
+            fa.anc_out = f->anc;                 // the parents it found (cusmc_filter_state_dev, tests)
+            fa.s.anc = nullptr;
+            fa.accumulate = cfg.ess_threshold > 0.0;
+        } else {
+            fa.mode = pffused::kParentArray;     // multinomial: ancestors from the search kernel
+        }
+        CUSMC_CHECK(cusmc_launch_fused(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
+                                       f->ep, fa, a.xi == nullptr));
+    } else {
+        CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
+                                      f->ep, a, a.xi == nullptr));
     }
-    CUSMC_CHECK(cusmc_launch_step(ctx, d, dy, f->G.data(), f->Qw.data(), cfg.noise_scale, &f->M, c, nullptr,
-                                  f->ep, a, a.xi == nullptr));
     f->cur ^= 1;
     f->next_t = t + 1;
     return CUSMC_OK;
@@ -886,9 +980,15 @@ static int launch_exchange(cusmc_filter *f, bool max, int cell, int t)
     return CUSMC_OK;
 }
 
-// The whole sharded run enqueued from C++: the phases of cusmc_filter_run with the per-step max,
-// sums and barrier travelling through the peer-memory mailboxes.  Every rank calls it the same
-// number of times (the epoch must agree); returns after enqueueing.
+// The whole sharded run enqueued from C++: two launches per step (the fused step kernel, the tile
+// update with its two scalar exchanges over the peer-memory mailboxes inside).  Every rank calls it
+// the same number of times (the epoch must agree); returns after enqueueing.
+//
+// Ordering between ranks: rank A's step kernel of t + 1 reads the peers' images and states of step t
+// and overwrites buffers the peers read during step t.  A's tile update of step t passes its first
+// exchange only when every peer has published its maximum, i.e. finished ITS step kernel of t, and its
+// second only when every peer's tile records of step t are complete -- so both hazards are covered
+// without a barrier of their own.
 extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws)
 {
     if (!f) return CUSMC_ERR_INVALID;
@@ -897,9 +997,8 @@ extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draw
     ++f->epoch;
     f->fused = true;
     auto after_weights = [&](int t) -> int {
-        // slot[t] holds this rank's max: make it global (metropolis: just a barrier, peers read
-        // these weights next); weigh then exchanges the sums inside its tile-scan kernel
-        CUSMC_CHECK(launch_exchange(f, is_log, kCellMax, t));
+        // reference mode: just a barrier (peers read these densities next)
+        if (!is_log) CUSMC_CHECK(launch_exchange(f, false, kCellMax, t));
         return cusmc_filter_weigh(f, t);
     };
     int rc = cudaMemsetAsync(f->mail_err, 0, 8, f->ctx->stream) == cudaSuccess ? CUSMC_OK : CUSMC_ERR_CUDA;
@@ -908,8 +1007,9 @@ extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draw
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 0);
     for (int t = 1; t < f->cfg.T && rc == CUSMC_OK; ++t) {
         rc = cusmc_filter_resample(f, t);
-        // ancestors went into the peers' arrays: after this barrier everyone's stores have landed
-        if (rc == CUSMC_OK) rc = launch_exchange(f, false, kCellBarrier, t);
+        // reference mode: the ancestors are local, but the step kernel overwrites the state buffer the
+        // peers gathered from during the previous step
+        if (rc == CUSMC_OK && !is_log) rc = launch_exchange(f, false, kCellBarrier, t);
         if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
         if (rc == CUSMC_OK) rc = after_weights(t);
     }

@@ -32,11 +32,13 @@ struct cusmc_filter {
     int world = 1, rank = 0;
     int64_t per = 0, lo = 0, n = 0;
     bool attached = false;
-    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{};
+    CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{}, peer_img[2]{};
     unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
     unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out
     unsigned long long mail_timeout_ns = 2000000000ull;   // bound of every spin-wait (cusmc_filter_set_exchange_timeout)
-    void **peer_tables = nullptr;             // device: [5 buffers][CUSMC_MAX_PEERS] peer pointers
+    void **peer_tables = nullptr;             // device: [CUSMC_FILTER_IPC_BUFFERS][CUSMC_MAX_PEERS] peer pointers
+    unsigned long long *img[2] = {nullptr, nullptr};   // weight images by step parity (image.cuh; log modes)
+    unsigned long long *rank_sums = nullptr;  // NCCL formulation: all-gathered per-rank sums of the current step
     unsigned long long epoch = 0;         // flag value of the current run (mail is never cleared)
     bool fused = false;                   // inside cusmc_filter_run_sharded: exchanges ride in the kernels
     double *x[2] = {nullptr, nullptr};
@@ -45,7 +47,6 @@ struct cusmc_filter {
     uint64_t *cdf = nullptr;
     StepSlot *slots = nullptr;
     double *moments = nullptr;        // T x (2 + d)
-    void *scan_state = nullptr;
     void *persist = nullptr;          // scratch of the persistent-kernel run (pf_persist.cu)
     size_t persist_bytes = 0;
     double *hist_x = nullptr, *hist_w = nullptr;

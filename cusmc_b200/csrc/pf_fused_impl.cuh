@@ -1,0 +1,373 @@
+// pf_fused_impl.cuh -- the fused filter step: resample + propagate + reweight + weigh in ONE kernel
+// (included by pf_fused_mvn.cu / pf_fused_mvt.cu, one translation unit per noise family).
+//
+// A block owns one tile of kTile = 2048 consecutive CHILD slots and does, for that tile,
+//
+//   1. lookup    : systematic resampling, child-centric.  The children of a tile descend from a window
+//                  of consecutive parents.  Starting at the parent tile tile_update_kernel left in the
+//                  tile record, the block walks parent tiles: thread t evaluates the offspring counts
+//                  k(C_j) of its 8 parents from the weight image of step t - 1 (C_j = rank_off + P_b +
+//                  (c_j F_b >> 62), 128-bit exact where the floating estimate is not safe) and writes
+//                  j into the shared-memory table for the children [k(C_{j-1}), k(C_j)) that fall in
+//                  the block's tile.  No ancestor array round trip, no scatter pass of its own.
+//   2. propagate : 8 striped rounds of one child per thread (pf_particle.cuh): gather the parent
+//                  (a window of ~2048 consecutive columns: the gather is nearly sequential), noise,
+//                  x_new = G x + noise, lw = log p(y_t | x_new); coalesced stores.
+//   3. weigh     : the tile's log-weights never leave shared memory: block maximum m_b, fixed-point
+//                  weights q_i = trunc(exp(lw_i - m_b) 2^shift), tile-local inclusive prefix c_i
+//                  (256-bit stores, 8 bytes per particle) and the tile record {m_b, sum q, sum q^2}.
+//
+// Replaces scan_resample_kernel + pf_step_kernel + weigh_kernel of round 1 (three passes, 168 bytes
+// per particle-step at d = 8, 274 us per 8 Mi particles) by one pass of 4 + 8 + 8d + 8d + 8 = 148 bytes.
+// The per-step grid-wide dependency (global maximum, tile prefix, total mass) is the one-block
+// tile_update_kernel between two launches of this kernel.
+//
+// Reference: resampler seam inst/include/types.hpp:32 (systematic has no counterpart upstream, SURVEY
+// a11), propagate_K src/mcmc.cpp:90-160, reweight_G src/mcmc.cpp:162-237.  oracle: orc_filter_det.
+#pragma once
+
+#include "image.cuh"
+#include "pf_particle.cuh"
+
+namespace pffused {
+
+using pfstep::StepOp;
+
+constexpr int kThreads = kResampleThreads;                 // 256
+constexpr int kItems = kTileItems;                         // 8 children per thread
+constexpr int kPadded = kTile + kTile / 8;                 // shared-memory words of one padded tile
+static_assert(kThreads * kItems == kTile, "a block owns exactly one tile");
+
+enum ParentMode { kParentSelf = 0, kParentArray = 1, kParentLookup = 2 };
+
+struct FusedArgs {
+    StepArgs s;                                   // x, noise, history rows, lw (optional store), rng keys
+    const unsigned long long *img_prev;           // weight image of step t - 1 (this rank)
+    unsigned long long *img_new;                  // weight image of step t (this rank)
+    const unsigned long long *const *img_prev_peer;   // world > 1: device table of every rank's image t - 1
+    uint32_t *anc_out;                            // optional: the parents this kernel used (global ids)
+    int64_t img_hdr_words;                        // words before c[] in an image (same on every rank)
+    uint32_t tiles_alloc;                         // tiles per rank as laid out: field f of tile b is word 16 + f tiles_alloc + b
+    uint32_t N_global;
+    uint32_t tiles_per_rank;                      // parent tile tau lives on rank tau / tiles_per_rank
+    int mode;                                     // ParentMode
+    int accumulate;                               // adaptive resampling: add the old log-weight when not resampled
+    int shift;
+};
+
+// shared-memory index of tile offset j: one pad word per 8, so both the striped (j = r*256 + tid)
+// and the blocked (j = 8*tid + r) access patterns stay conflict-free
+__device__ __forceinline__ int pad(int j) { return j + (j >> 3); }
+
+__device__ __forceinline__ void ldg256u(const unsigned long long *p, unsigned long long &a, unsigned long long &b,
+                                        unsigned long long &c, unsigned long long &d)
+{
+    asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+__device__ __forceinline__ void stg256u(unsigned long long *p, unsigned long long a, unsigned long long b,
+                                        unsigned long long c, unsigned long long d)
+{
+    asm volatile("st.global.v4.u64 [%0], {%1, %2, %3, %4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+
+// ---- 1. lookup -------------------------------------------------------------------------------------
+// Fills s_anc[pad(j)] = global parent of child i_a + j for j < n_tile.
+//
+// Everything that can be decided in the integer mass domain is: with Q_i = floor((i T + r0) / N)
+// (mass_quotient, two per block) "the CDF value C reaches past child i" is the 64-bit compare C > Q_i,
+// so which parent tiles to walk, when to stop and which threads hold parents of this tile's children
+// cost no offspring count at all.  Only those threads evaluate k(C_j) for their 8 parents, and each
+// parent with children leaves ONE marker -- its index at the slot of its first child inside the tile;
+// a block-wide running maximum then spreads the markers over the slots (parents and slots both
+// ascend), so family sizes never matter: no per-child loops, no divergence on heavy parents.
+template <bool PEERS>
+__device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepConsts &sc, uint32_t i_a, uint32_t n_tile,
+                                               uint32_t *__restrict__ s_anc, unsigned long long *__restrict__ s_q,
+                                               uint32_t *__restrict__ s_warp)
+{
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint64_t T = sc.T, r0 = sc.r0, Ng = fa.N_global;
+    const double ngt = sc.ng_over_t, r0t = sc.r0_over_t;
+    const uint32_t i_b = i_a + n_tile;
+    auto kof = [&](uint64_t C) { return (uint32_t)offspring_below(C, Ng, T, r0, ngt, r0t); };
+
+    if (tid == 0) s_q[0] = mass_quotient(i_a, T, r0, Ng);
+    if (tid == 32) s_q[1] = mass_quotient(i_b - 1, T, r0, Ng);
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) s_anc[pad(r * kThreads + (int)tid)] = 0u;
+    __syncthreads();
+    const uint64_t Qa = s_q[0], Qb = s_q[1];          // C > Qa: reaches past the first child; C > Qb: past the last
+
+    // the parent tile of the first child: largest tile whose exclusive prefix is <= Qa -- first the rank
+    // (block-uniform), then two block-wide rounds over that rank's compact prefix array, every thread
+    // one compare, the block barrier counting the hits
+    uint32_t rk = 0;
+    if (PEERS)
+        for (int r = 1; r < fa.s.world; ++r)
+            if (sc.rank_off[r] <= Qa) rk = (uint32_t)r;
+    uint32_t tau;
+    {
+        const unsigned long long *img = (PEERS && rk != (uint32_t)fa.s.rank) ? fa.img_prev_peer[rk] : fa.img_prev;
+        const unsigned long long *Pc = img + kConstWords + (size_t)kTileP * fa.tiles_alloc;
+        const uint64_t q = Qa - sc.rank_off[rk];
+        const uint32_t tiles = fa.tiles_per_rank, stride = (tiles + kThreads - 1) / kThreads;
+        uint32_t idx = tid * stride;
+        int hit = idx < tiles && __ldg(Pc + idx) <= q;
+        const uint32_t bucket = (uint32_t)__syncthreads_count(hit) - 1u;      // P_0 = 0 always qualifies
+        uint32_t lt = bucket * stride;
+        if (stride > 1) {
+            idx = lt + tid;
+            hit = tid < stride && idx < tiles && __ldg(Pc + idx) <= q;
+            lt += (uint32_t)__syncthreads_count(hit) - 1u;
+        }
+        tau = rk * fa.tiles_per_rank + lt;
+    }
+    for (;; ++tau) {
+        uint32_t lt = tau;
+        const unsigned long long *img = fa.img_prev;
+        rk = 0;
+        if (PEERS) {
+            rk = tau / fa.tiles_per_rank;
+            lt = tau - rk * fa.tiles_per_rank;
+            if (rk != (uint32_t)fa.s.rank) img = fa.img_prev_peer[rk];
+        }
+        const unsigned long long *fld = img + kConstWords + lt;
+        const uint64_t F = __ldg(fld + (size_t)kTileF * fa.tiles_alloc), P = sc.rank_off[rk] + __ldg(fld + (size_t)kTileP * fa.tiles_alloc),
+                       Sp = __ldg(fld + (size_t)kTileSp * fa.tiles_alloc);
+        const uint64_t Chi = P + Sp;                           // CDF at the end of this parent tile
+        if (Sp != 0 && Chi > Qa) {
+            const unsigned long long *cp = img + fa.img_hdr_words + (size_t)lt * kTile + kItems * tid;
+            unsigned long long c[kItems];
+            static_assert(kItems == 8, "two 256-bit loads per thread");
+            ldg256u(cp, c[0], c[1], c[2], c[3]);
+            ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
+            const uint64_t C_last = P + cusmc_mulshift62(c[kItems - 1], F);
+            uint64_t C_prev = __shfl_up_sync(0xffffffffu, C_last, 1);
+            if (lane == 0) C_prev = tid == 0 ? P : P + cusmc_mulshift62(__ldg(cp - 1), F);
+            // my parents matter iff their CDF span (C_prev, C_last] is non-empty, starts at or before the
+            // last child and ends past the first
+            if (C_last != C_prev && C_prev <= Qb && C_last > Qa) {
+                const uint32_t parent0 = tau * (uint32_t)kTile + kItems * tid;
+                uint32_t k_prev = kof(C_prev);
+                uint64_t Cp = C_prev;
+#pragma unroll
+                for (int r = 0; r < kItems; ++r) {
+                    const uint64_t C = r == kItems - 1 ? C_last : P + cusmc_mulshift62(c[r], F);
+                    if (C != Cp) {                              // zero weight: no children, same count
+                        const uint32_t k = kof(C);
+                        if (k > k_prev && k > i_a && k_prev < i_b) s_anc[pad((int)(max(k_prev, i_a) - i_a))] = parent0 + r;
+                        k_prev = k;
+                        Cp = C;
+                    }
+                }
+            }
+        }
+        if (Chi > Qb) break;                                    // the tile reaches past the last child
+    }
+    __syncthreads();
+    // running maximum over the slots: a marker holds until the next one
+    uint32_t v[kItems], run = 0;
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        run = max(run, s_anc[pad(kItems * (int)tid + r)]);
+        v[r] = run;
+    }
+    uint32_t inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc = max(inc, t);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t before = __shfl_up_sync(0xffffffffu, inc, 1);
+    if (lane == 0) before = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k)
+        if (k < (int)warp) before = max(before, s_warp[k]);
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) s_anc[pad(kItems * (int)tid + r)] = max(before, v[r]);
+}
+
+#ifndef CUSMC_FUSED_MINB8
+#define CUSMC_FUSED_MINB8 5
+#endif
+constexpr int min_blocks(int D, bool diag, bool mvt)
+{
+    return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : 3) : 4));
+}
+
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS>
+__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
+pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const FusedArgs fa)
+{
+    __shared__ double s_lw[kPadded];
+    __shared__ uint32_t s_anc[kPadded];
+    __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
+    __shared__ double s_dbl[kThreads / 32];
+    __shared__ StepConsts s_c;
+    __shared__ uint32_t s_warp[kThreads / 32];
+    const StepArgs &a = fa.s;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t j0 = blockIdx.x * (uint32_t)kTile;                 // local column of the tile's first child
+    const uint32_t n_tile = min((uint32_t)kTile, (uint32_t)a.n_out - j0);
+    const uint32_t i_a = (uint32_t)a.i0 + j0;                         // its global slot
+
+    // ---- 1. parents ---------------------------------------------------------------------------------
+    const bool lookup = fa.mode == kParentLookup;
+    bool resample = true;
+    if (lookup) {
+        if (tid < kConstWords) reinterpret_cast<unsigned long long *>(&s_c)[tid] = __ldg(fa.img_prev + tid);
+        __syncthreads();
+        resample = s_c.resample != 0 && s_c.T != 0;                   // no mass: identity (flagged by the update)
+        if (resample) lookup_parents<PEERS>(fa, s_c, i_a, n_tile, s_anc, s_u64, s_warp);
+        __syncthreads();
+    }
+    const bool accumulate = fa.accumulate && lookup && s_c.resample == 0;
+
+    // ---- 2. propagate + reweight, striped ------------------------------------------------------------
+#pragma unroll 1
+    for (int r = 0; r < kItems; ++r) {
+        const uint32_t j = (uint32_t)r * kThreads + tid;
+        double lw = -INFINITY;
+        if (j < n_tile) {
+            const int64_t i = (int64_t)j0 + j;
+            uint32_t parent = i_a + j;                                // global id
+            if (lookup) {
+                if (resample) parent = s_anc[pad((int)j)];
+            } else if (fa.mode == kParentArray) {
+                parent = __ldg(a.anc + i);
+            }
+            cusmc_u32x4 r0{};
+            if (PHILOX) r0 = cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
+            const double *src = a.x_prev + ((int64_t)parent - a.parent_base);
+            if (PEERS && a.has_prev) {
+                const uint32_t rk = fast_div(parent, a.per_rank);
+                const uint32_t col = parent - rk * a.per_rank.d;
+                src = (rk == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[rk]) + col;
+            }
+            lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG>(op, ep, a, i, src, r0);
+            if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
+            if (a.lw) st_stream(a.lw + i, lw);
+            if (a.hist_w) st_stream(a.hist_w + i, lw);
+            if (a.hist_a) a.hist_a[i] = parent;
+            if (fa.anc_out) fa.anc_out[i] = parent;
+        }
+        s_lw[pad((int)j)] = lw;
+    }
+    __syncthreads();
+
+    // ---- 3. weigh: block-relative fixed-point image of the tile ----------------------------------------
+    double v[kItems], m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        v[r] = s_lw[pad(kItems * (int)tid + r)];
+        if (v[r] == v[r] && v[r] < INFINITY && v[r] > m) m = v[r];
+    }
+    m = warp_max_double(m);
+    if (lane == 0) s_dbl[warp] = m;
+    __syncthreads();
+    m = warp_max_double(lane < kThreads / 32 ? s_dbl[lane] : -INFINITY);          // the tile's maximum, every thread
+    unsigned long long c[kItems], run = 0, s2 = 0;
+#pragma unroll
+    for (int r = 0; r < kItems; ++r) {
+        const double wn = cusmc_unit_from_log(v[r], m);                            // -inf padding -> 0
+        run += cusmc_fixed_from_unit(wn, fa.shift);
+        c[r] = run;
+        s2 += cusmc_fixed_from_unit(wn * wn, fa.shift);
+    }
+    unsigned long long inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+    if (lane == 31) s_u64[warp] = inc;
+    if (lane == 0) s_u64[kThreads / 32 + warp] = s2;
+    __syncthreads();
+    unsigned long long before = inc - run, tile_total = 0, s2_total = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        const unsigned long long t = s_u64[k];
+        if (k < (int)warp) before += t;
+        tile_total += t;
+        s2_total += s_u64[kThreads / 32 + k];
+    }
+    unsigned long long *local = fa.img_new + fa.img_hdr_words + j0 + kItems * tid;   // 32-byte aligned
+    stg256u(local, before + c[0], before + c[1], before + c[2], before + c[3]);
+    stg256u(local + 4, before + c[4], before + c[5], before + c[6], before + c[7]);
+    if (tid < 3) {
+        unsigned long long *fld = fa.img_new + kConstWords + blockIdx.x;
+        fld[(size_t)tid * fa.tiles_alloc] = tid == 0 ? (unsigned long long)__double_as_longlong(m) : tid == 1 ? tile_total : s2_total;
+    }
+}
+
+// ---- launch ---------------------------------------------------------------------------------------------
+template <int D, bool MVT, bool EXACT, bool DIAG>
+int launch_one(cusmc_ctx *ctx, const pfstep::StepModel &m, const Epilogue &ep, const FusedArgs &fa, bool philox)
+{
+    StepOp<D, DIAG> op;
+    pfstep::fill_step_op<D, DIAG>(op, m);
+    const unsigned grid = (unsigned)((fa.s.n_out + kTile - 1) / kTile);
+    const bool peers = fa.s.world > 1;
+#define CUSMC_FUSED_GO(PH, FA, PE) \
+    pf_fused_kernel<D, PH, FA, MVT, EXACT, DIAG, PE><<<grid, kThreads, 0, ctx->stream>>>(op, ep, fa)
+    if (philox && fa.s.fast_noise) {
+        if (peers) CUSMC_FUSED_GO(true, true, true); else CUSMC_FUSED_GO(true, true, false);
+    } else if (philox) {
+        if (peers) CUSMC_FUSED_GO(true, false, true); else CUSMC_FUSED_GO(true, false, false);
+    } else {
+        if (peers) CUSMC_FUSED_GO(false, false, true); else CUSMC_FUSED_GO(false, false, false);
+    }
+#undef CUSMC_FUSED_GO
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+// One translation unit per (D, noise family) instantiates its three kernels' worth of launch_one
+// (pf_fused_inst.cu, compiled once per pair by the Makefile so the build parallelises); everybody else
+// sees extern templates.
+#define CUSMC_FUSED_VARIANTS(X, DD, MV)                  \
+    X int launch_one<DD, MV, true, true>(cusmc_ctx *, const pfstep::StepModel &, const Epilogue &, const FusedArgs &, bool);  \
+    X int launch_one<DD, MV, true, false>(cusmc_ctx *, const pfstep::StepModel &, const Epilogue &, const FusedArgs &, bool); \
+    X int launch_one<DD, MV, false, false>(cusmc_ctx *, const pfstep::StepModel &, const Epilogue &, const FusedArgs &, bool);
+#ifndef CUSMC_INST_D
+#define CUSMC_FUSED_EXTERN(DD) CUSMC_FUSED_VARIANTS(extern template, DD, false) CUSMC_FUSED_VARIANTS(extern template, DD, true)
+CUSMC_FUSED_EXTERN(2)
+CUSMC_FUSED_EXTERN(4)
+CUSMC_FUSED_EXTERN(8)
+CUSMC_FUSED_EXTERN(16)
+CUSMC_FUSED_EXTERN(32)
+#undef CUSMC_FUSED_EXTERN
+#endif
+
+template <bool MVT>
+int launch_family(cusmc_ctx *ctx, const pfstep::StepModel &m, const Epilogue &ep, const FusedArgs &fa, bool philox,
+                  bool exact, bool diag)
+{
+    const int dm = m.d > m.dy ? m.d : m.dy;
+#define CUSMC_FUSED_CASE(DD)                                                                         \
+    case DD:                                                                                         \
+        if (exact && diag) return launch_one<DD, MVT, true, true>(ctx, m, ep, fa, philox);           \
+        if (exact) return launch_one<DD, MVT, true, false>(ctx, m, ep, fa, philox);                  \
+        return launch_one<DD, MVT, false, false>(ctx, m, ep, fa, philox);
+    switch (cusmc_pad_dim(dm)) {
+        CUSMC_FUSED_CASE(2)
+        CUSMC_FUSED_CASE(4)
+        CUSMC_FUSED_CASE(8)
+        CUSMC_FUSED_CASE(16)
+        CUSMC_FUSED_CASE(32)
+    }
+#undef CUSMC_FUSED_CASE
+    return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "unreachable");
+}
+
+}  // namespace pffused
+
+// G, Q column-major d x d host (either may be NULL = zero); M row-major dy x d (NULL = no weights);
+// c dy; mu d (NULL = 0).  Picks the EXACT / DIAG specialisations itself (as cusmc_launch_step).
+int cusmc_launch_fused(cusmc_ctx *ctx, int d, int dy, const double *G, const double *Q, double qscale,
+                       const std::vector<double> *M, const double *c, const double *mu, const Epilogue &ep,
+                       const pffused::FusedArgs &fa, bool philox);

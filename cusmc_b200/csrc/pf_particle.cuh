@@ -1,0 +1,219 @@
+// pf_particle.cuh -- what ONE thread does for ONE child particle of a filter step, shared by the
+// one-particle-per-thread step kernel (pf_step_impl.cuh), the fused step kernel (pf_fused_impl.cuh)
+// and the persistent whole-run kernel (pf_persist.cu):
+//
+//     x_new = mu + G x_parent + noise          noise = Q xi | chi (.) (Q xi)
+//     lw    = log pdf_V(y_t - F x_new)         (or the density, reference mode)
+//
+// (propagate_K + sample, src/mcmc.cpp:90-160 and src/statistics.cc.cpp:224-259,355-412; reweight_G,
+// src/mcmc.cpp:162-237.)  G, Q and the whitened observation operator ride in the kernel parameter
+// bank; every operation on the state is fp64 in a fixed order (oracle: orc_step_det).
+#pragma once
+
+#include "pf_step.cuh"
+
+#include "../../include/cusmc_detmath.h"
+#include "../../include/cusmc_philox.h"
+
+namespace pfstep {
+
+template <int D, bool DIAG>
+struct StepOp {
+    static constexpr int NM = DIAG ? D : D * D;
+    double G[NM];      // row-major transition (DIAG: the diagonal)
+    double Q[NM];      // row-major noise factor (already multiplied by noise_scale)
+    double M[NM];      // row-major whitened observation operator  L_V^-1 F
+    double c[D];       // L_V^-1 y_t
+    double mu[D];      // additive location (m0 at t = 0, otherwise 0)
+};
+
+// chi_k = sqrt(nu / X),  X ~ chi^2_nu = 2 Gamma(nu/2)  (the reference's curand_gamma /
+// curand_chi_square, src/mvt_dist.cu.cpp:20-61): Marsaglia-Tsang in SINGLE precision, like the
+// normals (the draws carry 24 significant bits; every operation on the state stays fp64), built from
+// the reproducible fp32 functions of cusmc_detmath.h.  One Philox block serves TWO components: its
+// Box-Muller pair gives their two normals, its other two words their two uniforms; the squeeze
+// u < 1 - 0.0331 z^4 accepts ~92 % of the proposals without a logarithm and a proposal is rejected
+// ~4 % of the time (the component then redraws from block `attempt + 1`).  A first version drew every
+// component from two blocks with fp64 Box-Muller, log and sincos: 6.5x the cost of the whole Normal
+// step at d = 8.
+static __device__ __noinline__ void chi_pair(uint64_t seed, uint64_t step, uint64_t index, int kpair, float nu,
+                                             float *chi0, float *chi1)
+{
+    const float a0 = 0.5f * nu;
+    const float a = a0 < 1.0f ? a0 + 1.0f : a0;
+    const float dd = a - 0.333333343f;
+    const float cc = 1.0f / sqrtf(9.0f * dd);
+    float g[2] = {dd, dd};
+    bool done[2] = {false, false};
+    for (uint32_t attempt = 0; attempt < 32 && !(done[0] && done[1]); ++attempt) {
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, ((uint32_t)kpair << 8) | attempt);
+        float z[2];
+        cusmc_box_muller_f32(r.v[0], r.v[1], &z[0], &z[1]);
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            if (done[e]) continue;
+            const float t = fmaf(cc, z[e], 1.0f);
+            if (!(t > 0.0f)) continue;
+            const float v = t * t * t;
+            const float u = fmaf((float)(r.v[2 + e] >> 8), 5.9604644775390625e-8f, 2.98023223876953125e-8f);  // (0, 1)
+            const float z2 = z[e] * z[e];
+            if (u < fmaf(-0.0331f * z2, z2, 1.0f) ||
+                cusmc_det_logf(u) < fmaf(0.5f, z2, dd * (1.0f - v + cusmc_det_logf(v)))) {
+                g[e] = dd * v;
+                done[e] = true;
+            }
+        }
+    }
+    if (a0 < 1.0f) {
+        // shape < 1 (nu < 2): Gamma(a0) = Gamma(a0 + 1) U^(1/a0), from a block of its own
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_CHI, step, index, ((uint32_t)kpair << 8) | 0x800000u);
+#pragma unroll
+        for (int e = 0; e < 2; ++e)
+            g[e] = (float)((double)g[e] * cusmc_det_exp(cusmc_det_log(cusmc_u01_open0(r.v[2 * e], r.v[2 * e + 1])) / (double)a0));
+    }
+    *chi0 = sqrtf(nu / (2.0f * g[0]));
+    *chi1 = sqrtf(nu / (2.0f * g[1]));
+}
+
+// One Philox block -> two Box-Muller pairs.  FAST: the special-function-unit transform
+// (cusmc_box_muller_fast; the throughput default), otherwise the FFMA-only one a host reproduces.
+template <bool FAST>
+__device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
+{
+    if constexpr (FAST) {
+        cusmc_box_muller_fast(r.v[0], r.v[1], &z[0], &z[1]);
+        cusmc_box_muller_fast(r.v[2], r.v[3], &z[2], &z[3]);
+    } else {
+        cusmc_box_muller_f32(r.v[0], r.v[1], &z[0], &z[1]);
+        cusmc_box_muller_f32(r.v[2], r.v[3], &z[2], &z[3]);
+    }
+}
+
+// The child `i` (local column; global slot a.i0 + i) of parent column `src` (already resolved to the
+// owning rank's buffer; nullptr-free: callers pass has_prev = 0 for the initial draw).  r0 is the
+// child's first Philox block, computed by the caller while the parent index was still in flight.
+// Stores x_new (and the history row) itself; returns the (log-)weight, not yet stored.
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG>
+__device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const Epilogue &ep, const StepArgs &a,
+                                                int64_t i, const double *__restrict__ src, const cusmc_u32x4 &r0)
+{
+    const int d = EXACT ? D : a.d;
+    const uint64_t idx = (uint64_t)(a.i0 + i);
+    double xp[D], z[D], xn[D];
+    if (a.has_prev) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
+    } else {
+#pragma unroll
+        for (int j = 0; j < D; ++j) xp[j] = 0.0;
+    }
+    // DIAG: component k needs only its own normal, so the draws stay in single precision (half the
+    // registers) until the one FMA that consumes them
+    constexpr bool kFloatNoise = PHILOX && DIAG;
+    float zf[kFloatNoise ? D : 1];
+    if (PHILOX) {
+        // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
+#pragma unroll
+        for (int jq = 0; jq < (D + 3) / 4; ++jq) {
+            float zq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+            if (EXACT || 4 * jq < d) {
+                const cusmc_u32x4 rq = jq == 0 ? r0 : cusmc_rng(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq);
+                normals4<FAST>(rq, zq);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * jq + e < D) {
+                    const float v = (EXACT || 4 * jq + e < d) ? zq[e] : 0.0f;
+                    if constexpr (kFloatNoise) zf[4 * jq + e] = v;
+                    else z[4 * jq + e] = (double)v;
+                }
+        }
+    } else {
+        const double *nz = a.xi + i;
+#pragma unroll
+        for (int j = 0; j < D; ++j) z[j] = (EXACT || j < d) ? ld_stream(nz + (int64_t)j * a.ld_noise) : 0.0;
+    }
+    double chi[MVT ? D : 1];
+    if (MVT && !a.chi) {
+#pragma unroll
+        for (int kp = 0; kp < (D + 1) / 2; ++kp) {
+            float c0 = 1.0f, c1 = 1.0f;
+            if (EXACT || 2 * kp < d) chi_pair(a.seed, a.step, idx, kp, a.nu, &c0, &c1);
+            chi[MVT ? 2 * kp : 0] = (double)c0;
+            if (2 * kp + 1 < D) chi[MVT ? 2 * kp + 1 : 0] = (double)c1;
+        }
+    }
+    double *dst_x = a.x_new + i;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double g = op.mu[k], s = 0.0;
+        if constexpr (DIAG) {
+            g = fma(op.G[k], xp[k], g);
+            s = fma(op.Q[k], kFloatNoise ? (double)zf[kFloatNoise ? k : 0] : z[k], s);
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
+#pragma unroll
+            for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
+        }
+        if (MVT && (EXACT || k < d))
+            s = (a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i) : chi[MVT ? k : 0]) * s;
+        xn[k] = s + g;
+        if (EXACT || k < d) {
+            st_stream(dst_x + (int64_t)k * a.ld_new, xn[k]);
+            // the history row goes out here too: stores keep their order, and one issued after the
+            // weight would pin every xn[k] in a register until the end of the kernel
+            if (a.hist_x) st_stream(a.hist_x + i * d + k, xn[k]);
+        }
+    }
+    if (a.skip_weight) return a.const_weight;
+    double q = 0.0;
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+        double zk = op.c[k];
+        if constexpr (DIAG) {
+            zk = fma(-op.M[k], xn[k], zk);
+        } else {
+#pragma unroll
+            for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
+        }
+        q = fma(zk, zk, q);
+    }
+    return density_epilogue(ep, q);
+}
+
+// Host-side view of the model matrices of one step (all optional, column-major like Eigen).
+struct StepModel {
+    int d, dy;
+    const double *G, *Q;
+    double qscale;
+    const std::vector<double> *M;   // row-major dy x d
+    const double *c, *mu;
+};
+
+template <int D, bool DIAG>
+void fill_step_op(StepOp<D, DIAG> &op, const StepModel &m)
+{
+    std::memset(&op, 0, sizeof(op));
+    const int d = m.d, dy = m.dy;
+    if constexpr (DIAG) {
+        for (int k = 0; k < d; ++k) {
+            if (m.G) op.G[k] = m.G[(size_t)k * d + k];
+            if (m.Q) op.Q[k] = m.Q[(size_t)k * d + k] * m.qscale;
+            if (m.M) op.M[k] = (*m.M)[(size_t)k * d + k];
+        }
+    } else {
+        for (int k = 0; k < d; ++k)
+            for (int j = 0; j < d; ++j) {
+                if (m.G) op.G[k * D + j] = m.G[(size_t)j * d + k];
+                if (m.Q) op.Q[k * D + j] = m.Q[(size_t)j * d + k] * m.qscale;
+            }
+        if (m.M)
+            for (int k = 0; k < dy; ++k)
+                for (int j = 0; j < d; ++j) op.M[k * D + j] = (*m.M)[(size_t)k * d + j];
+    }
+    for (int k = 0; k < dy; ++k) op.c[k] = m.c ? m.c[k] : 0.0;
+    for (int k = 0; k < d; ++k) op.mu[k] = m.mu ? m.mu[k] : 0.0;
+}
+
+}  // namespace pfstep

@@ -27,6 +27,7 @@ struct StepArgs {
     double const_weight;         // used when skip_weight
     float nu;
     int d, dy, kind, has_prev, skip_weight, rng_stream;
+    int fast_noise;              // device-drawn normals through the special-function unit (not host-reproducible)
     // peer form (world > 1): anc holds GLOBAL parent ids, parent g lives on rank g / per_rank at
     // column g % per_rank of that rank's state buffer (leading dimension ld_prev on every rank),
     // read through the peer-mapped pointer -- an 8d-byte gather over NVLink when it is remote.

@@ -4,16 +4,18 @@ The reference is single-device; this is the north star's 
 naturally across the 8 GPUs" path.  Rank r owns the global particle slots
 ``[r * per, min((r + 1) * per, N))``, ``per = ceil(N / world)``.  Per step:
 
-    propagate(t)   peer LOADS : a child gathers its parent's state from the owning rank's buffer
-    all-reduce MAX            : 8 bytes  (log-weight max, NCCL)
-    weigh(t)                  : local fixed-point sums + tile prefixes
-    all-gather                : 3 x 8 bytes per rank (NCCL) -> global mass, this rank's CDF offset
-    resample(t+1)  peer STORES: every parent writes its children's ancestor entries into the
-                                owning rank's array (4 bytes per child over NVLink)
-    barrier                   : ancestors have landed
+    step(t)        peer LOADS : ONE fused kernel -- every block looks its children's parents up in the
+                                weight image of step t - 1 (the owning rank's tile records and tile-local
+                                CDF, read over NVLink when the parents are remote), gathers the parent
+                                states from the owning rank's buffer, propagates, reweights and leaves
+                                its tile of the new weight image
+    all-reduce MAX            : 8 bytes  (log-weight max)
+    tile update(t)            : rescale the tiles against the global max, scan, local sums
+    all-gather                : 2 x 8 bytes per rank -> global mass, every rank's CDF offset
 
-``torch.distributed`` carries the scalars and the one-off exchange of IPC handles; the particle
-data never goes through a collective -- it moves by peer loads / stores inside the kernels
+Two launches per step.  By default the scalars travel through peer-memory mailboxes inside the tile
+update kernel (cusmc_filter_run_sharded); ``exchange="nccl"`` carries them with ``torch.distributed``
+collectives between the kernel's three phases.  The particle data never goes through a collective -- it moves by peer loads / stores inside the kernels
 (`cudaIpcOpenMemHandle`-mapped buffers, cusmc_filter_ipc_export / _attach).  Weights are integer
 fixed point and noise is keyed by the global slot, so a sharded run equals the single-GPU run bit
 for bit, whatever the world size.
@@ -26,14 +28,15 @@ import ctypes as C
 import numpy as np
 
 from . import _lib
-from .api import ParticleFilter
+from .api import ParticleFilter, shard_size
 
 SLOT_WORDS = 8          # struct StepSlot (csrc/filter.cu), in 8-byte words
 W_MAX, W_SUM, W_SUM2, W_NPOS, W_OFFSET = 0, 1, 2, 3, 4
 
 
 class ShardPlan:
-    """Contiguous ownership of N global slots by `world` ranks (the rule cusmc_filter_create applies)."""
+    """Contiguous ownership of N global slots by `world` ranks (the rule cusmc_filter_create applies):
+    ceil(N / world) slots per rank, rounded up to whole weight-image tiles of 2048."""
 
     def __init__(self, N, world, rank):
         if not (0 <= rank < world):
@@ -41,7 +44,7 @@ class ShardPlan:
         if world > _lib.MAX_PEERS:
             raise ValueError("world %d exceeds CUSMC_MAX_PEERS = %d" % (world, _lib.MAX_PEERS))
         self.N, self.world, self.rank = int(N), int(world), int(rank)
-        self.per = -(-self.N // self.world)
+        self.per = shard_size(self.N, self.world)
         self.lo = min(self.rank * self.per, self.N)
         self.n = max(0, min(self.per, self.N - self.rank * self.per))
 
@@ -180,16 +183,20 @@ class ShardedParticleFilter:
             self.pf = None
 
     def _after_weights(self, t):
-        """slot[t] holds this rank's max: make it global, weigh, make the sums global."""
+        """NCCL formulation of weigh(t): the three phases of the tile update with the scalars carried by
+        torch.distributed in between -- all-reduce MAX of the log-weight maximum, all-gather of the
+        per-rank fixed-point sums (from which every rank derives the global mass and its CDF offset)."""
         lib, h, ck = self.ctx.lib, self.pf.h, self.ctx._check
-        if self.world > 1:
-            if self.is_log:
-                exchange_max(self.slots_f64[t], self.group)
-            else:
-                rank_barrier(self._token, self.group)     # peers read these weights next
-        ck(lib.cusmc_filter_weigh(h, t))
-        if self.world > 1 and self.is_log:
-            exchange_sums(self.slots_i64[t], self.rank, self.world, self._scratch, self.group)
+        if self.world == 1 or not self.is_log:
+            if self.world > 1:
+                rank_barrier(self._token, self.group)     # reference mode: peers read these densities next
+            ck(lib.cusmc_filter_weigh(h, t))
+            return
+        ck(lib.cusmc_filter_weigh_phase(h, t, 0, None))
+        exchange_max(self.slots_f64[t], self.group)
+        ck(lib.cusmc_filter_weigh_phase(h, t, 1, None))
+        gathered = exchange_sums(self.slots_i64[t], self.rank, self.world, self._scratch, self.group)
+        ck(lib.cusmc_filter_weigh_phase(h, t, 2, gathered.data_ptr()))
 
     def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, exchange="p2p"):
         """Injected draws (optional) are this rank's shard; omitted ones come from Philox keyed by
@@ -213,8 +220,8 @@ class ShardedParticleFilter:
         ck(lib.cusmc_filter_mark(h, 0))
         for t in range(1, self.T):
             ck(lib.cusmc_filter_resample(h, t))
-            if self.world > 1:
-                rank_barrier(self._token, self.group)
+            if self.world > 1 and not self.is_log:
+                rank_barrier(self._token, self.group)     # the state buffer about to be overwritten was read by peers
             ck(lib.cusmc_filter_propagate(h, t))
             self._after_weights(t)
         ck(lib.cusmc_filter_mark(h, 1))

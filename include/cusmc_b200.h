@@ -59,7 +59,7 @@ enum cusmc_resampler {                                    /* Resamplers[...], sr
 #define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
 #define CUSMC_MAX_PEERS 8           /* ranks (GPUs of one NVLink domain) of a sharded filter */
 #define CUSMC_IPC_HANDLE_BYTES 64   /* sizeof(cudaIpcMemHandle_t) */
-#define CUSMC_FILTER_IPC_BUFFERS 5   /* state x 2, ancestors, weights, mailbox */
+#define CUSMC_FILTER_IPC_BUFFERS 7   /* state x 2, ancestors, weights, mailbox, weight image x 2 */
 
 typedef struct cusmc_ctx cusmc_ctx;
 
@@ -308,6 +308,12 @@ typedef struct cusmc_filter_config {
      * i.e. x_0 = m0 + chi (.) (Q_c0 xi) -- the default here too.  1 = draw a Normal x_0 instead
      * (round 1's behaviour). */
     int mvt_normal_init;
+    /* Device-drawn normals: 0 (default) = the throughput generator, Philox words through the special-
+     * function unit (MUFU lg2 / sqrt / sin / cos, ~12 instructions per pair); 1 = the reproducible one
+     * (FFMA-only polynomials, ~67 per pair) whose every bit a host can regenerate -- the oracle mirrors
+     * it, so device-drawn runs can be checked bit for bit on a CPU.  Same law and resolution either way;
+     * injected draws are unaffected. */
+    int reproducible_rng;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):
@@ -346,6 +352,13 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
  */
 int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *draws);
 int cusmc_filter_weigh(cusmc_filter *f, int t);
+/* weigh(t) in three phases for callers that carry the scalars themselves (NCCL formulation):
+ *   phase 0: this rank's maximum log-weight -> slot[t] word 0            (then all-reduce MAX it)
+ *   phase 1: rescale + scan against that maximum, this rank's sums -> slot[t] words 1..2
+ *                                                                     (then all-gather words 1..3)
+ *   phase 2: global totals, rank offsets, next step's constants from rank_sums_dev (3 words per rank,
+ *            rank-major: what the all-gather produced), then the posterior moments. */
+int cusmc_filter_weigh_phase(cusmc_filter *f, int t, int phase, const uint64_t *rank_sums_dev);
 int cusmc_filter_resample(cusmc_filter *f, int t);
 int cusmc_filter_propagate(cusmc_filter *f, int t);
 /* Records the start (which = 0) / end (1) event cusmc_filter_last_ms measures between. */

@@ -291,4 +291,24 @@ CUSMC_HD double cusmc_unit_from_log(double lw, double lmax)
     return (lw <= lmax) ? v : 0.0; /* NaN or above the max -> 0 */
 }
 
+/* ---- block-relative weight image (the filter's resampling image; oracle: orc_tile_image) ----------
+ * A tile of particles is weighed against ITS OWN maximum m_b, so the pass that produces the log-weights
+ * can finish the tile without a grid-wide dependency; once the global maximum M is known the tile is
+ * rescaled by the 62-bit fixed-point factor F_b = trunc(exp(m_b - M) 2^62):  c -> (c F_b) >> 62. */
+CUSMC_HD uint64_t cusmc_rescale_factor(double m_b, double M)
+{
+    const double v = cusmc_unit_from_log(m_b, M);          /* in [0, 1]; -inf / NaN -> 0 */
+    return (uint64_t)(v * 4611686018427387904.0);          /* 2^62 */
+}
+
+/* floor(c F / 2^62) for c < 2^62, F <= 2^62 (128-bit product). */
+CUSMC_HD uint64_t cusmc_mulshift62(uint64_t c, uint64_t F)
+{
+#if defined(__CUDA_ARCH__)
+    return (__umul64hi(c, F) << 2) | ((c * F) >> 62);
+#else
+    return (uint64_t)(((unsigned __int128)c * F) >> 62);
+#endif
+}
+
 #endif /* CUSMC_DETMATH_H */

@@ -1022,14 +1022,71 @@ static uint64_t fixed_from_unit(double wn, int shift)
     return (uint64_t)(wn * bits_to_double((uint64_t)(shift + 1023) << 52));
 }
 
+/* ---- block-relative weight image (extended; no reference counterpart) -----------------------
+ * The filter's normalised resamplers take their weights from this image.  Particles are cut into
+ * tiles of `tile` consecutive slots (global index space).  Inside tile b
+ *     m_b = max finite lw,   q_i = trunc(exp(lw_i - m_b) 2^shift),   c_i = inclusive prefix of q,
+ *     S_b = c_last,          S2_b = sum trunc(exp(lw_i - m_b)^2 2^shift),
+ * so a tile is complete without knowing anything about the others.  With M = max_b m_b the tile is
+ * rescaled by the 62-bit fixed-point factor F_b = trunc(exp(m_b - M) 2^62):
+ *     C_i = P_b + (c_i F_b >> 62),   P_b = sum_{b' < b} (S_b' F_b' >> 62),   T = sum_b (S_b F_b >> 62),
+ *     T2  = sum_b ((S2_b F_b >> 62) F_b >> 62)
+ * (128-bit products).  C is the integer CDF systematic / multinomial resampling read; ESS =
+ * T^2 / (T2 2^shift), log-likelihood = M + log(T / 2^shift / N).  exp is orc_det_exp, flushed to 0
+ * below -43.5 (anything that small truncates to 0 anyway).  The kernels (pf_fused_kernel epilogue,
+ * tile_update_kernel) reproduce every one of these integers. */
+static uint64_t mulshift62(uint64_t c, uint64_t F) { return (uint64_t)(((unsigned __int128)c * F) >> 62); }
+
+static double exp_unit(double x) { return (x >= -43.5) ? orc_det_exp(x) : 0.0; }   /* NaN -> 0 */
+
+uint64_t orc_tile_image(const double *lw, int64_t N, int64_t tile, int shift, uint64_t *C,
+                        uint64_t *T2_out, double *M_out)
+{
+    int64_t nt = (N + tile - 1) / tile;
+    double *m = (double *)malloc(sizeof(double) * (nt > 0 ? nt : 1));
+    uint64_t *S = (uint64_t *)malloc(sizeof(uint64_t) * (nt > 0 ? nt : 1));
+    uint64_t *S2 = (uint64_t *)malloc(sizeof(uint64_t) * (nt > 0 ? nt : 1));
+    double M = -INFINITY;
+#pragma omp parallel for schedule(static) reduction(max : M)
+    for (int64_t b = 0; b < nt; ++b) {
+        int64_t lo = b * tile, hi = lo + tile < N ? lo + tile : N;
+        double mb = -INFINITY;
+        for (int64_t i = lo; i < hi; ++i) if (lw[i] > mb && lw[i] < INFINITY) mb = lw[i];
+        uint64_t run = 0, s2 = 0;
+        for (int64_t i = lo; i < hi; ++i) {
+            double wn = (lw[i] <= mb) ? exp_unit(lw[i] - mb) : 0.0;
+            run += fixed_from_unit(wn, shift);
+            s2 += fixed_from_unit(wn * wn, shift);
+            C[i] = run;                          /* tile-local for now */
+        }
+        m[b] = mb; S[b] = run; S2[b] = s2;
+        if (mb > M) M = mb;
+    }
+    uint64_t P = 0, T2 = 0;
+    const double two62 = 4611686018427387904.0;
+    for (int64_t b = 0; b < nt; ++b) {
+        int64_t lo = b * tile, hi = lo + tile < N ? lo + tile : N;
+        double f = (m[b] <= M) ? exp_unit(m[b] - M) : 0.0;
+        uint64_t F = (uint64_t)(f * two62);
+        for (int64_t i = lo; i < hi; ++i) C[i] = P + mulshift62(C[i], F);
+        P += mulshift62(S[b], F);
+        T2 += mulshift62(mulshift62(S2[b], F), F);
+    }
+    free(m); free(S); free(S2);
+    if (T2_out) *T2_out = T2;
+    if (M_out) *M_out = M;
+    return P;
+}
+
 int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int B,
                    const double *Y, const double *m0, const double *Q_c0, const double *F,
                    const double *G, const double *V, const double *Q_w, float nu, uint64_t seed,
                    const double *xi0, const double *chi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
                    double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
-                   double ess_threshold, int *resampled)
+                   double ess_threshold, int *resampled, int64_t tile)
 {
+    if (tile <= 0) tile = 2048;       /* the library's tile (kTile); the persistent kernel passes its own */
     size_t Nd = (size_t)N * d;
     double *w_old = (double *)malloc(sizeof(double) * N);
     int is_log = resampler != 0;
@@ -1070,17 +1127,9 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                                                &ub[(size_t)i * B + n], &jb[(size_t)i * B + n]);
                 orc_metropolis_hastings(a, w, ut, jt, N, B);
             } else {
-                /* weights of step t-1: max shift, fixed point, integer CDF */
-                double m = -INFINITY;
-                for (int64_t i = 0; i < N; ++i) if (w[i] > m && w[i] < INFINITY) m = w[i];
-                uint64_t run = 0, run2 = 0;
-                for (int64_t i = 0; i < N; ++i) {
-                    double wn = (w[i] <= m) ? orc_det_exp(w[i] - m) : 0.0;
-                    run += fixed_from_unit(wn, shift);
-                    run2 += fixed_from_unit(wn * wn, shift);
-                    C[i] = run;
-                }
-                uint64_t Tm = run;
+                /* weights of step t-1: the block-relative fixed-point image, integer CDF */
+                uint64_t run2 = 0;
+                uint64_t Tm = orc_tile_image(w, N, tile, shift, C, &run2, NULL);
                 if (Tm == 0) { rc = -1; goto done; }
                 /* adaptive resampling: ESS = sum_q^2 / (sum_q2 2^shift) < threshold N, evaluated as
                  * the kernels do (scan_resample_kernel) */
@@ -1134,14 +1183,9 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
         if (w_hist) memcpy(w_hist + (size_t)t * N, w, sizeof(double) * N);
         if (a_hist && t > 0) memcpy(a_hist + (size_t)t * N, a, sizeof(uint32_t) * N);
         if (is_log && (ess || loglik)) {
-            double m = -INFINITY;
-            for (int64_t i = 0; i < N; ++i) if (w[i] > m && w[i] < INFINITY) m = w[i];
-            uint64_t s1 = 0, s2 = 0;
-            for (int64_t i = 0; i < N; ++i) {
-                double wn = (w[i] <= m) ? orc_det_exp(w[i] - m) : 0.0;
-                s1 += fixed_from_unit(wn, shift);
-                s2 += fixed_from_unit(wn * wn, shift);
-            }
+            double m;
+            uint64_t s2 = 0;
+            uint64_t s1 = orc_tile_image(w, N, tile, shift, C, &s2, &m);
             if (ess) ess[t] = ((double)s1 * (double)s1) / ((double)s2 * scale2);
             if (loglik) loglik[t] = m + log((double)s1 / scale2 / (double)N);
         }

@@ -201,6 +201,7 @@ void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, 
 /* Whole filter in production order.  resampler: 0 metropolis (linear weights, as the
  * reference), 1 systematic, 2 multinomial (log weights, max-shifted fixed point).  Draw arrays may
  * be NULL -> Philox mirror with `seed`.  Layouts as orc_filter_metropolis; u0 [(T-1)], um [(T-1)*N].
+ * tile: tile size of the weight image (<= 0: 2048, the library's; the persistent kernel uses its own).
  * Outputs optional: x_hist [T*N*d], w_hist [T*N], a_hist [T*N], ess [T], loglik [T]. */
 int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int B,
                    const double *Y, const double *m0, const double *Q_c0, const double *F,
@@ -208,7 +209,11 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                    const double *xi0, const double *chi0, const double *xi, const double *chi, const double *u,
                    const uint32_t *j, const double *u0, const double *um,
                    double *x_hist, double *w_hist, uint32_t *a_hist, double *ess, double *loglik,
-                   double ess_threshold, int *resampled);
+                   double ess_threshold, int *resampled, int64_t tile);
+/* The block-relative weight image the filter's normalised resamplers read (definition in the .c):
+ * C[i] = global inclusive integer CDF; returns the total T; optional T2 (sum of squares), M (max). */
+uint64_t orc_tile_image(const double *lw, int64_t N, int64_t tile, int shift, uint64_t *C,
+                        uint64_t *T2_out, double *M_out);
 
 /* Threads the batched functions will use (OpenMP), for bench reporting. */
 int orc_num_threads(void);

@@ -125,7 +125,9 @@ class Oracle:
         L.orc_filter_det.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int,
                                      _dp, _dp, _dp, _dp, _dp, _dp, _dp, C.c_float, C.c_uint64,
                                      _dp, _dp, _dp, _dp, _dp, _u32p, _dp, _dp,
-                                     _dp, _dp, _u32p, _dp, _dp, C.c_double, C.POINTER(C.c_int)]
+                                     _dp, _dp, _u32p, _dp, _dp, C.c_double, C.POINTER(C.c_int), C.c_int64]
+        L.orc_tile_image.restype = C.c_uint64
+        L.orc_tile_image.argtypes = [_dp, C.c_int64, C.c_int64, C.c_int, _u64p, _u64p, _dp]
 
     # ---- dense helpers ----------------------------------------------------
     def determinant(self, A):
@@ -224,6 +226,15 @@ class Oracle:
         q = np.empty(w.size, dtype=np.uint64)
         tot = self.lib.orc_fixed_weights(_p(w), w.size, float(wmax), int(shift), _p(q, _u64p))
         return q, tot
+
+    def tile_image(self, lw, tile, shift=None):
+        """Block-relative weight image: (C, T, T2, M)."""
+        lw = f64(lw)
+        shift = self.fixed_shift(lw.size) if shift is None else shift
+        Cd = np.empty(lw.size, dtype=np.uint64)
+        T2, M = C.c_uint64(), C.c_double()
+        T = self.lib.orc_tile_image(_p(lw), lw.size, int(tile), int(shift), _p(Cd, _u64p), C.byref(T2), C.byref(M))
+        return Cd, int(T), int(T2.value), M.value
 
     def logsumexp_ess(self, lw):
         lw = f64(lw)
@@ -385,7 +396,7 @@ class Oracle:
 
     def filter_det(self, dist, resampler, Y, m0, Q_c0, F, G, V, Q_w, N, nu=0.0, seed=0, B=10,
                    xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, ess_threshold=0.0,
-                   chi0=None):
+                   chi0=None, tile=0):
         """Production-order filter.  resampler: 'metropolis' | 'systematic' | 'multinomial'."""
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
@@ -405,7 +416,7 @@ class Oracle:
             _p(colmajor(Q_c0)), _p(colmajor(F)), _p(colmajor(G)), _p(colmajor(V)), _p(colmajor(Q_w)),
             float(nu), int(seed), _p(opt(xi0)), _p(opt(chi0)), _p(opt(xi)), _p(opt(chi)), _p(opt(u)), _p(j_, _u32p),
             _p(opt(u0)), _p(opt(um)), _p(xh), _p(wh), _p(ah, _u32p), _p(ess), _p(ll),
-            float(ess_threshold), res.ctypes.data_as(C.POINTER(C.c_int)))
+            float(ess_threshold), res.ctypes.data_as(C.POINTER(C.c_int)), int(tile))
         if rc:
             raise RuntimeError("orc_filter_det failed: %d" % rc)
         return dict(x=xh, w=wh, a=ah, ess=ess, loglik=ll, resampled=res)

@@ -549,7 +549,7 @@ def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
     d, N, T = 2, 2048, 8
     md = _model(d)
     Y = rng.standard_normal((d, T))
-    pf = ctx.filter(N=N, Y=Y, resampler=resampler, seed=4242, keep_history=True, **md)
+    pf = ctx.filter(N=N, Y=Y, resampler=resampler, seed=4242, keep_history=True, reproducible_rng=True, **md)
     h = pf.run().history()
     pf.close()
     ref = orc.filter_det("mvn", resampler, Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
@@ -642,7 +642,8 @@ def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
     N, T = 4000, 30
     md = _model(d)
     Y = rng.standard_normal((d, T)) * 0.5
-    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=5, keep_history=True, ess_threshold=thr, **md)
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=5, keep_history=True, ess_threshold=thr,
+                    reproducible_rng=True, **md)
     h, s, res = pf.run().history(), pf.summary(), pf.resampled()
     pf.close()
     ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
