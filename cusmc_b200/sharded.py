@@ -147,7 +147,7 @@ class ShardedParticleFilter:
         self.pf = ParticleFilter(ctx, N, Y, m0, C0, F, G, V, W, rank=self.rank, world=self.world, **kw)
         if exchange_timeout is None:
             # ranks that time-slice one device (test rigs) wait for each other's kernels to be scheduled
-            exchange_timeout = 2.0 if torch.cuda.device_count() >= self.world else 60.0
+            exchange_timeout = 2.0 if torch.cuda.device_count() >= self.world else 10.0
         ctx._check(ctx.lib.cusmc_filter_set_exchange_timeout(self.pf.h, float(exchange_timeout)))
         self.T, self.d, self.N = self.pf.T, self.pf.d, int(N)
         self.is_log = kw.get("resampler", "metropolis") != "metropolis"

