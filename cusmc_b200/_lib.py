@@ -84,6 +84,7 @@ PROTOTYPES = {
                                  vp, vp]),
     "cusmc_filter_create": (ci, [vp, C.POINTER(FilterConfig), C.POINTER(vp)]),
     "cusmc_filter_destroy": (ci, [vp]),
+    "cusmc_filter_tile_size": (i64, [vp]),
     "cusmc_filter_run": (ci, [vp, C.POINTER(FilterDraws)]),
     "cusmc_filter_begin": (ci, [vp, C.POINTER(FilterDraws)]),
     "cusmc_filter_weigh": (ci, [vp, ci]),

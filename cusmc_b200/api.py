@@ -470,6 +470,11 @@ class ParticleFilter:
     def last_ms(self):
         return float(self.ctx.lib.cusmc_filter_last_ms(self.h))
 
+    @property
+    def tile_size(self):
+        """Particles per weight-image tile of the path run() takes (2048, or the persistent kernel's)."""
+        return int(self.ctx.lib.cusmc_filter_tile_size(self.h))
+
     def summary(self):
         mean = np.empty((self.T, self.d))
         ess = np.empty(self.T)

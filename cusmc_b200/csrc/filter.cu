@@ -538,11 +538,15 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
     alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
     if (f->is_log) {
-        // two weight images (step parity): step t reads image t - 1 while it writes image t
-        const size_t img_bytes = sizeof(unsigned long long) * (size_t)fimage_words(f->per);
+        // two weight images (step parity): step t reads image t - 1 while it writes image t.  A persistent
+        // run spreads the cloud over more, smaller tiles (one per resident block): the layout holds both.
+        f->persist_tile = cusmc_filter_persistent_tile(f);
+        f->img_n = f->per;
+        if (f->persist_tile) f->img_n = std::max<int64_t>(f->img_n, (N + f->persist_tile - 1) / f->persist_tile * (int64_t)kTile);
+        const size_t img_bytes = sizeof(unsigned long long) * (size_t)fimage_words(f->img_n);
         for (int b = 0; b < 2; ++b) {
             alloc((void **)&f->img[b], img_bytes);
-            if (e == cudaSuccess) e = cudaMemset(f->img[b], 0, sizeof(unsigned long long) * (size_t)fimage_header_words(f->per));
+            if (e == cudaSuccess) e = cudaMemset(f->img[b], 0, sizeof(unsigned long long) * (size_t)fimage_header_words(f->img_n));
         }
         if (world > 1) alloc((void **)&f->rank_sums, sizeof(unsigned long long) * 3 * CUSMC_MAX_PEERS);
     }
@@ -636,6 +640,13 @@ extern "C" int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all
     return CUSMC_OK;
 }
 
+extern "C" int64_t cusmc_filter_tile_size(cusmc_filter *f)
+{
+    if (!f) return 0;
+    // what cusmc_filter_run (without injected per-particle draws) will use
+    return cusmc_filter_persistent_eligible(f, nullptr) ? (int64_t)f->persist_tile : (int64_t)kTile;
+}
+
 extern "C" int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev)
 {
     if (!f) return CUSMC_ERR_INVALID;
@@ -721,10 +732,11 @@ static pffused::FusedArgs filter_fused_args(cusmc_filter *f, const StepArgs &a, 
     fa.img_new = f->img[t & 1];
     fa.img_prev = f->img[(t & 1) ^ 1];
     fa.img_prev_peer = f->world > 1 ? (const unsigned long long *const *)f->peer_img[(t & 1) ^ 1].table_dev : nullptr;
-    fa.img_hdr_words = fimage_header_words(f->per);
-    fa.tiles_alloc = (uint32_t)fimage_tiles(f->per);
+    fa.img_hdr_words = fimage_header_words(f->img_n);
+    fa.tiles_alloc = (uint32_t)fimage_tiles(f->img_n);
     fa.N_global = (uint32_t)f->cfg.N;
     fa.tiles_per_rank = (uint32_t)(f->per / kTile > 0 ? (f->per + kTile - 1) / kTile : 1);
+    fa.tile_n = (uint32_t)kTile;
     fa.shift = f->shift;
     return fa;
 }
@@ -798,7 +810,7 @@ static int filter_tile_update(cusmc_filter *f, int t, int phases)
     u.slot_next = t + 1 < cfg.T ? f->slots + t + 1 : nullptr;
     u.rank_sums = f->rank_sums;
     u.tiles = (f->n + kTile - 1) / kTile;
-    u.tiles_alloc = fimage_tiles(f->per);
+    u.tiles_alloc = fimage_tiles(f->img_n);
     u.lo = (unsigned)f->lo;
     u.N_global = (unsigned)cfg.N;
     u.u0_next = (t + 1 < cfg.T && cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) ? filter_u0(f, t + 1) : 0.0;
@@ -884,7 +896,7 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) return CUSMC_OK;
     // multinomial: materialise the global CDF from the image, one binary search per child
     StepSlot *prev = &f->slots[t - 1];
-    CUSMC_CHECK(cusmc_launch_image_cdf(ctx, f->img[(t - 1) & 1], f->per, n, f->rank, f->cdf));
+    CUSMC_CHECK(cusmc_launch_image_cdf(ctx, f->img[(t - 1) & 1], f->img_n, n, f->rank, f->cdf));
     const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
     return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc,
                                     &f->slots[t].degenerate);

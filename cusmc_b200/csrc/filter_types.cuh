@@ -49,6 +49,8 @@ struct cusmc_filter {
     double *moments = nullptr;        // T x (2 + d)
     void *persist = nullptr;          // scratch of the persistent-kernel run (pf_persist.cu)
     size_t persist_bytes = 0;
+    uint32_t persist_tile = 0;        // particles per block of a persistent run (0: not covered / does not fit)
+    int64_t img_n = 0;                // particle count the weight images are laid out for (image.cuh)
     double *hist_x = nullptr, *hist_w = nullptr;
     uint32_t *hist_a = nullptr;
     // ring_K > 0: the history buffers hold a RING of 2 chunks of ring_K steps each instead of all T
@@ -101,3 +103,4 @@ int cusmc_filter_init_slots(cusmc_filter *f);
 // (returns CUSMC_ERR_UNSUPPORTED otherwise, without side effects).
 int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws);
 bool cusmc_filter_persistent_eligible(const cusmc_filter *f, const cusmc_filter_draws *draws);
+uint32_t cusmc_filter_persistent_tile(cusmc_filter *f);

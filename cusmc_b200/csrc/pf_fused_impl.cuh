@@ -50,6 +50,8 @@ struct FusedArgs {
     uint32_t tiles_alloc;                         // tiles per rank as laid out: field f of tile b is word 16 + f tiles_alloc + b
     uint32_t N_global;
     uint32_t tiles_per_rank;                      // parent tile tau lives on rank tau / tiles_per_rank
+    uint32_t tile_n;                              // particles per tile (kTile; the persistent kernel spreads N
+                                                  // evenly over its resident blocks: tile_n <= kTile, c stride kTile)
     int mode;                                     // ParentMode
     int accumulate;                               // adaptive resampling: add the old log-weight when not resampled
     int shift;
@@ -63,6 +65,17 @@ __device__ __forceinline__ void ldg256u(const unsigned long long *p, unsigned lo
                                         unsigned long long &c, unsigned long long &d)
 {
     asm volatile("ld.global.nc.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p));
+}
+// the same through L2 only: data other blocks wrote earlier in the SAME launch (persistent kernel)
+__device__ __forceinline__ void ldcg256u(const unsigned long long *p, unsigned long long &a, unsigned long long &b,
+                                         unsigned long long &c, unsigned long long &d)
+{
+    asm volatile("ld.global.cg.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(p) : "memory");
+}
+template <bool COH>
+__device__ __forceinline__ unsigned long long ld_word(const unsigned long long *p)
+{
+    return COH ? __ldcg(p) : __ldg(p);
 }
 __device__ __forceinline__ void stg256u(unsigned long long *p, unsigned long long a, unsigned long long b,
                                         unsigned long long c, unsigned long long d)
@@ -80,7 +93,7 @@ __device__ __forceinline__ void stg256u(unsigned long long *p, unsigned long lon
 // parent with children leaves ONE marker -- its index at the slot of its first child inside the tile;
 // a block-wide running maximum then spreads the markers over the slots (parents and slots both
 // ascend), so family sizes never matter: no per-child loops, no divergence on heavy parents.
-template <bool PEERS>
+template <bool PEERS, bool COH>
 __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepConsts &sc, uint32_t i_a, uint32_t n_tile,
                                                uint32_t *__restrict__ s_anc, unsigned long long *__restrict__ s_q,
                                                uint32_t *__restrict__ s_warp)
@@ -112,12 +125,12 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
         const uint64_t q = Qa - sc.rank_off[rk];
         const uint32_t tiles = fa.tiles_per_rank, stride = (tiles + kThreads - 1) / kThreads;
         uint32_t idx = tid * stride;
-        int hit = idx < tiles && __ldg(Pc + idx) <= q;
+        int hit = idx < tiles && ld_word<COH>(Pc + idx) <= q;
         const uint32_t bucket = (uint32_t)__syncthreads_count(hit) - 1u;      // P_0 = 0 always qualifies
         uint32_t lt = bucket * stride;
         if (stride > 1) {
             idx = lt + tid;
-            hit = tid < stride && idx < tiles && __ldg(Pc + idx) <= q;
+            hit = tid < stride && idx < tiles && ld_word<COH>(Pc + idx) <= q;
             lt += (uint32_t)__syncthreads_count(hit) - 1u;
         }
         tau = rk * fa.tiles_per_rank + lt;
@@ -132,22 +145,28 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
             if (rk != (uint32_t)fa.s.rank) img = fa.img_prev_peer[rk];
         }
         const unsigned long long *fld = img + kConstWords + lt;
-        const uint64_t F = __ldg(fld + (size_t)kTileF * fa.tiles_alloc), P = sc.rank_off[rk] + __ldg(fld + (size_t)kTileP * fa.tiles_alloc),
-                       Sp = __ldg(fld + (size_t)kTileSp * fa.tiles_alloc);
+        const uint64_t F = ld_word<COH>(fld + (size_t)kTileF * fa.tiles_alloc),
+                       P = sc.rank_off[rk] + ld_word<COH>(fld + (size_t)kTileP * fa.tiles_alloc),
+                       Sp = ld_word<COH>(fld + (size_t)kTileSp * fa.tiles_alloc);
         const uint64_t Chi = P + Sp;                           // CDF at the end of this parent tile
         if (Sp != 0 && Chi > Qa) {
             const unsigned long long *cp = img + fa.img_hdr_words + (size_t)lt * kTile + kItems * tid;
             unsigned long long c[kItems];
             static_assert(kItems == 8, "two 256-bit loads per thread");
-            ldg256u(cp, c[0], c[1], c[2], c[3]);
-            ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
+            if (COH) {
+                ldcg256u(cp, c[0], c[1], c[2], c[3]);
+                ldcg256u(cp + 4, c[4], c[5], c[6], c[7]);
+            } else {
+                ldg256u(cp, c[0], c[1], c[2], c[3]);
+                ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
+            }
             const uint64_t C_last = P + cusmc_mulshift62(c[kItems - 1], F);
             uint64_t C_prev = __shfl_up_sync(0xffffffffu, C_last, 1);
-            if (lane == 0) C_prev = tid == 0 ? P : P + cusmc_mulshift62(__ldg(cp - 1), F);
+            if (lane == 0) C_prev = tid == 0 ? P : P + cusmc_mulshift62(ld_word<COH>(cp - 1), F);
             // my parents matter iff their CDF span (C_prev, C_last] is non-empty, starts at or before the
             // last child and ends past the first
             if (C_last != C_prev && C_prev <= Qb && C_last > Qa) {
-                const uint32_t parent0 = tau * (uint32_t)kTile + kItems * tid;
+                const uint32_t parent0 = tau * fa.tile_n + kItems * tid;
                 uint32_t k_prev = kof(C_prev);
                 uint64_t Cp = C_prev;
 #pragma unroll
@@ -197,33 +216,37 @@ constexpr int min_blocks(int D, bool diag, bool mvt)
     return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : 3) : 4));
 }
 
-template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS>
-__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
-pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const FusedArgs fa)
+struct FusedSmem {
+    double lw[kPadded];
+    uint32_t anc[kPadded];
+    unsigned long long u64[2 * (kThreads / 32)];
+    double dbl[kThreads / 32];
+    StepConsts c;
+    uint32_t warp[kThreads / 32];
+};
+
+// One tile of children through the three phases.  `tile` = the block's tile on this rank.
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS, bool COH>
+__device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
+                                                 const FusedArgs &fa, uint32_t tile, FusedSmem &sm)
 {
-    __shared__ double s_lw[kPadded];
-    __shared__ uint32_t s_anc[kPadded];
-    __shared__ unsigned long long s_u64[2 * (kThreads / 32)];
-    __shared__ double s_dbl[kThreads / 32];
-    __shared__ StepConsts s_c;
-    __shared__ uint32_t s_warp[kThreads / 32];
     const StepArgs &a = fa.s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t j0 = blockIdx.x * (uint32_t)kTile;                 // local column of the tile's first child
-    const uint32_t n_tile = min((uint32_t)kTile, (uint32_t)a.n_out - j0);
+    const uint32_t j0 = tile * fa.tile_n;                             // local column of the tile's first child
+    const uint32_t n_tile = min(fa.tile_n, (uint32_t)a.n_out - j0);
     const uint32_t i_a = (uint32_t)a.i0 + j0;                         // its global slot
 
     // ---- 1. parents ---------------------------------------------------------------------------------
     const bool lookup = fa.mode == kParentLookup;
     bool resample = true;
     if (lookup) {
-        if (tid < kConstWords) reinterpret_cast<unsigned long long *>(&s_c)[tid] = __ldg(fa.img_prev + tid);
+        if (tid < kConstWords) reinterpret_cast<unsigned long long *>(&sm.c)[tid] = ld_word<COH>(fa.img_prev + tid);
         __syncthreads();
-        resample = s_c.resample != 0 && s_c.T != 0;                   // no mass: identity (flagged by the update)
-        if (resample) lookup_parents<PEERS>(fa, s_c, i_a, n_tile, s_anc, s_u64, s_warp);
+        resample = sm.c.resample != 0 && sm.c.T != 0;                 // no mass: identity (flagged by the update)
+        if (resample) lookup_parents<PEERS, COH>(fa, sm.c, i_a, n_tile, sm.anc, sm.u64, sm.warp);
         __syncthreads();
     }
-    const bool accumulate = fa.accumulate && lookup && s_c.resample == 0;
+    const bool accumulate = fa.accumulate && lookup && sm.c.resample == 0;
 
     // ---- 2. propagate + reweight, striped ------------------------------------------------------------
 #pragma unroll 1
@@ -234,7 +257,7 @@ pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, c
             const int64_t i = (int64_t)j0 + j;
             uint32_t parent = i_a + j;                                // global id
             if (lookup) {
-                if (resample) parent = s_anc[pad((int)j)];
+                if (resample) parent = sm.anc[pad((int)j)];
             } else if (fa.mode == kParentArray) {
                 parent = __ldg(a.anc + i);
             }
@@ -246,14 +269,14 @@ pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, c
                 const uint32_t col = parent - rk * a.per_rank.d;
                 src = (rk == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[rk]) + col;
             }
-            lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG>(op, ep, a, i, src, r0);
+            lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0);
             if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
             if (a.lw) st_stream(a.lw + i, lw);
             if (a.hist_w) st_stream(a.hist_w + i, lw);
             if (a.hist_a) a.hist_a[i] = parent;
             if (fa.anc_out) fa.anc_out[i] = parent;
         }
-        s_lw[pad((int)j)] = lw;
+        sm.lw[pad((int)j)] = lw;
     }
     __syncthreads();
 
@@ -261,13 +284,13 @@ pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, c
     double v[kItems], m = -INFINITY;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
-        v[r] = s_lw[pad(kItems * (int)tid + r)];
+        v[r] = sm.lw[pad(kItems * (int)tid + r)];
         if (v[r] == v[r] && v[r] < INFINITY && v[r] > m) m = v[r];
     }
     m = warp_max_double(m);
-    if (lane == 0) s_dbl[warp] = m;
+    if (lane == 0) sm.dbl[warp] = m;
     __syncthreads();
-    m = warp_max_double(lane < kThreads / 32 ? s_dbl[lane] : -INFINITY);          // the tile's maximum, every thread
+    m = warp_max_double(lane < kThreads / 32 ? sm.dbl[lane] : -INFINITY);          // the tile's maximum, every thread
     unsigned long long c[kItems], run = 0, s2 = 0;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
@@ -284,24 +307,32 @@ pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, c
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-    if (lane == 31) s_u64[warp] = inc;
-    if (lane == 0) s_u64[kThreads / 32 + warp] = s2;
+    if (lane == 31) sm.u64[warp] = inc;
+    if (lane == 0) sm.u64[kThreads / 32 + warp] = s2;
     __syncthreads();
     unsigned long long before = inc - run, tile_total = 0, s2_total = 0;
 #pragma unroll
     for (int k = 0; k < kThreads / 32; ++k) {
-        const unsigned long long t = s_u64[k];
+        const unsigned long long t = sm.u64[k];
         if (k < (int)warp) before += t;
         tile_total += t;
-        s2_total += s_u64[kThreads / 32 + k];
+        s2_total += sm.u64[kThreads / 32 + k];
     }
-    unsigned long long *local = fa.img_new + fa.img_hdr_words + j0 + kItems * tid;   // 32-byte aligned
+    unsigned long long *local = fa.img_new + fa.img_hdr_words + (size_t)tile * kTile + kItems * tid;   // 32-byte aligned
     stg256u(local, before + c[0], before + c[1], before + c[2], before + c[3]);
     stg256u(local + 4, before + c[4], before + c[5], before + c[6], before + c[7]);
     if (tid < 3) {
-        unsigned long long *fld = fa.img_new + kConstWords + blockIdx.x;
+        unsigned long long *fld = fa.img_new + kConstWords + tile;
         fld[(size_t)tid * fa.tiles_alloc] = tid == 0 ? (unsigned long long)__double_as_longlong(m) : tid == 1 ? tile_total : s2_total;
     }
+}
+
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS>
+__global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
+pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const FusedArgs fa)
+{
+    __shared__ FusedSmem sm;
+    fused_block_step<D, PHILOX, FAST, MVT, EXACT, DIAG, PEERS, false>(op, op.c, ep, fa, blockIdx.x, sm);
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------

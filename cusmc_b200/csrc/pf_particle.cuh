@@ -93,16 +93,22 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 // owning rank's buffer; nullptr-free: callers pass has_prev = 0 for the initial draw).  r0 is the
 // child's first Philox block, computed by the caller while the parent index was still in flight.
 // Stores x_new (and the history row) itself; returns the (log-)weight, not yet stored.
-template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG>
-__device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const Epilogue &ep, const StepArgs &a,
-                                                int64_t i, const double *__restrict__ src, const cusmc_u32x4 &r0)
+// cobs: the whitened observation L_V^-1 y_t -- op.c in the per-step kernels (a parameter-bank operand),
+// a register array in the persistent kernel, whose observation changes inside the launch.  COH: the
+// parent state was written earlier in the SAME launch by other blocks (persistent kernel): read it
+// through L2, never through the non-coherent path.
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false>
+__device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
+                                                const StepArgs &a, int64_t i, const double *__restrict__ src,
+                                                const cusmc_u32x4 &r0)
 {
     const int d = EXACT ? D : a.d;
     const uint64_t idx = (uint64_t)(a.i0 + i);
     double xp[D], z[D], xn[D];
     if (a.has_prev) {
 #pragma unroll
-        for (int j = 0; j < D; ++j) xp[j] = (EXACT || j < d) ? __ldg(src + (int64_t)j * a.ld_prev) : 0.0;
+        for (int j = 0; j < D; ++j)
+            xp[j] = (EXACT || j < d) ? (COH ? __ldcg(src + (int64_t)j * a.ld_prev) : __ldg(src + (int64_t)j * a.ld_prev)) : 0.0;
     } else {
 #pragma unroll
         for (int j = 0; j < D; ++j) xp[j] = 0.0;
@@ -170,7 +176,7 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
     double q = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
-        double zk = op.c[k];
+        double zk = cobs[k];
         if constexpr (DIAG) {
             zk = fma(-op.M[k], xn[k], zk);
         } else {

@@ -66,7 +66,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
             const uint32_t col = g - r * a.per_rank.d;
             src = (r == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[r]) + col;
         }
-        lw = particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG>(op, ep, a, i, src, r0);
+        lw = particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG>(op, op.c, ep, a, i, src, r0);
         double *dst_lw = a.lw + i;
         if (!a.skip_weight && a.resampled && *a.resampled == 0) lw = *dst_lw + lw;   // no resampling: weights accumulate
         st_stream(dst_lw, lw);

@@ -330,6 +330,10 @@ typedef struct cusmc_filter_draws {
 
 int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_filter **out);
 int cusmc_filter_destroy(cusmc_filter *f);
+/* Particles per tile of the weight image cusmc_filter_run will use: 2048 for the per-step path, the
+ * evenly spread tile of the persistent kernel when the run takes that path.  The resampling image is
+ * defined per tile, so a CPU restatement needs this number to reproduce a run bit for bit. */
+int64_t cusmc_filter_tile_size(cusmc_filter *f);
 /* Runs t = 0 (initialize) then steps 1 .. T-1 on the stream; returns after enqueueing. */
 int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
 /*

@@ -559,80 +559,48 @@ def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
 
 
 @pytest.mark.parametrize("d,diag,N", [(2, True, 20000), (2, False, 8192), (4, True, 12346), (4, False, 4100),
-                                      (2, True, 300000)])
-def test_persistent_kernel_equals_four_launch_path(ctx, d, diag, N):
-    """cusmc_filter_run as ONE cooperative kernel (pf_persist.cu) against the four-launch path:
-    final particles, log-weights and ancestors bit for bit, and the per-step log-likelihood."""
-    pytest.skip("persistent kernel: being rewritten on the block-relative weight image")
+                                      (8, True, 50000), (2, True, 300000), (2, True, 1000000)])
+def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, d, diag, N):
+    """cusmc_filter_run as ONE cooperative kernel (pf_persist.cu; the C4 path) against the ORACLE: device-
+    drawn noise on one side, the oracle's Philox mirror on the other, no history.  The weight image is
+    defined per tile and the persistent kernel spreads the cloud evenly over its resident blocks, so
+    the oracle is told the run's tile size: final states, log-weights and ancestors bit for bit, ESS and
+    log-likelihood of every step.  The per-step path of the same filter (tile 2048) is checked too."""
     rng = np.random.default_rng(31 * d + N)
-    T = 14
+    T = 9 if N >= 300000 else 14
     I = np.eye(d)
     if diag:
         md = dict(m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=0.5 * I, W=0.3 * I)
     else:
         A = rng.standard_normal((d, d)) * 0.2
-        md = dict(m0=rng.standard_normal(d), C0=spd(rng, d), F=I + A, G=0.8 * I + A.T, V=spd(rng, d), W=spd(rng, d))
+        # dense F, G, V (the general kernel path); C0 and W stay scalar so that the library's Jacobi factor
+        # and numpy's eigh factor are the same matrix (eigenvector signs are not unique otherwise)
+        md = dict(m0=rng.standard_normal(d), C0=1.3 * I, F=I + A, G=0.8 * I + A.T, V=spd(rng, d), W=0.4 * I)
     Y = rng.standard_normal((d, T))
-    out = []
+    tiles = []
     for persistent in (True, False):
-        pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=99, summary=False, persistent=persistent, **md)
+        pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=99, summary=False, persistent=persistent,
+                        reproducible_rng=True, **md)
+        tile = pf.tile_size
         l0 = ctx.launch_count
         pf.run()
         x, w, a = pf.state()
         launches = ctx.launch_count - l0
-        out.append((x, w, a, pf.summary()["loglik"], launches))
+        s = pf.summary()
         pf.close()
-    (xp, wp, ap, lp, np_), (xf, wf, af, lf, nf) = out
-    assert np_ == 2 and nf == 4 * (T - 1) + 4          # the persistent run really took the one-kernel path
-    assert np.array_equal(ap, af)
-    assert np.array_equal(xp, xf)
-    assert np.array_equal(wp, wf)
-    assert np.array_equal(lp, lf)
-    assert len(np.unique(ap)) > 10 and np.all(np.diff(ap.astype(np.int64)) >= 0)
-    # with the summary on: same states again, ESS from the same integer sums, means to rounding (the
-    # persistent kernel weighs with the fixed-point weights, the four-launch path with exp(lw - max))
-    summ = []
-    for persistent in (True, False):
-        pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=99, summary=True, persistent=persistent, **md)
-        l0 = ctx.launch_count
-        pf.run()
-        x, w, a = pf.state()
-        summ.append((x, a, pf.summary(), ctx.launch_count - l0))
-        pf.close()
-    (xs, as_, sp, n1), (_, _, sf, n2) = summ
-    assert n1 == 2 and n2 > 4 * (T - 1)
-    assert np.array_equal(xs, xp) and np.array_equal(as_, ap)
-    assert np.array_equal(sp["loglik"], sf["loglik"])
-    assert np.allclose(sp["ess"], sf["ess"], rtol=1e-12)
-    # fixed-point weights are truncated at 2^-shift of the largest: |delta mean| <~ N 2^-shift / sum(w)
-    assert np.allclose(sp["mean"], sf["mean"], rtol=1e-7, atol=1e-9)
-
-
-@pytest.mark.parametrize("N", [20000, 300000])
-def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, N):
-    """The one-kernel run (the C4 path) against the ORACLE itself, not just against the four-launch
-    path: device-drawn noise on one side, the oracle's Philox mirror on the other, no history --
-    final states, log-weights and ancestors bit for bit, ESS / log-likelihood of every step."""
-    pytest.skip("persistent kernel: being rewritten on the block-relative weight image")
-    rng = np.random.default_rng(N)
-    d, T = 2, 9
-    md = _model(d)
-    Y = rng.standard_normal((d, T))
-    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=1234, summary=True, persistent=True, **md)
-    l0 = ctx.launch_count
-    pf.run()
-    launches = ctx.launch_count - l0
-    x, w, a = pf.state()
-    s = pf.summary()
-    pf.close()
-    assert launches == 2                                  # init_slots + ONE cooperative kernel
-    ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
-                         _eig_factor(md["W"]), N, seed=1234)
-    assert np.array_equal(a, ref["a"][-1])
-    assert np.array_equal(x.T, ref["x"][-1])
-    assert np.array_equal(w, ref["w"][-1])
-    assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
-    assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
+        # the persistent run really took the one-kernel path: init_slots + ONE cooperative kernel
+        assert launches == (2 if persistent else 1 + 2 * T)
+        assert (tile != 2048 or N > 500000) if persistent else tile == 2048
+        tiles.append(tile)
+        ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                             _eig_factor(md["W"]), N, seed=99, tile=tile)
+        assert np.array_equal(a, ref["a"][-1])
+        assert np.array_equal(x.T, ref["x"][-1])
+        assert np.array_equal(w, ref["w"][-1])
+        assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+        assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
+        assert len(np.unique(a)) > 10 and np.all(np.diff(a.astype(np.int64)) >= 0)
+    assert tiles[0] % 32 == 0 and tiles[0] <= 2048
 
 
 @pytest.mark.parametrize("d,thr", [(2, 0.5), (8, 0.05)])
