@@ -55,6 +55,7 @@ struct FusedArgs {
     int mode;                                     // ParentMode
     int accumulate;                               // adaptive resampling: add the old log-weight when not resampled
     int shift;
+    double *trace;                                // profiling builds: 8 time stamps per step (else NULL)
 };
 
 // shared-memory index of tile offset j: one pad word per 8, so both the striped (j = r*256 + tid)
@@ -135,6 +136,9 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
         }
         tau = rk * fa.tiles_per_rank + lt;
     }
+    // (Software-pipelining this walk -- the loads of tile tau + 1 in flight while tile tau is processed --
+    // was tried: the speculative tile per block and the registers it pins cost more than the shorter
+    // dependency chain gains: 241 -> 272 us per C5 step, 27.3 -> 30.1 us per C4 step.)
     for (;; ++tau) {
         uint32_t lt = tau;
         const unsigned long long *img = fa.img_prev;
@@ -216,6 +220,21 @@ constexpr int min_blocks(int D, bool diag, bool mvt)
     return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : 3) : 4));
 }
 
+// Phase trace (profiling builds only, -DCUSMC_TRACE): block 0 / thread 0 stamps the global timer.
+#ifdef CUSMC_TRACE
+__device__ __forceinline__ void trace_stamp(double *buf, int slot)
+{
+    if (buf && (blockIdx.x == 0 || buf[-1] == 1.0) && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        buf[slot] = (double)t;
+    }
+}
+#define CUSMC_STAMP(buf, slot) pffused::trace_stamp(buf, slot)
+#else
+#define CUSMC_STAMP(buf, slot) ((void)0)
+#endif
+
 struct FusedSmem {
     double lw[kPadded];
     uint32_t anc[kPadded];
@@ -246,39 +265,79 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
         if (resample) lookup_parents<PEERS, COH>(fa, sm.c, i_a, n_tile, sm.anc, sm.u64, sm.warp);
         __syncthreads();
     }
+    CUSMC_STAMP(fa.trace, 1);
     const bool accumulate = fa.accumulate && lookup && sm.c.resample == 0;
 
     // ---- 2. propagate + reweight, striped ------------------------------------------------------------
-#pragma unroll 1
-    for (int r = 0; r < kItems; ++r) {
-        const uint32_t j = (uint32_t)r * kThreads + tid;
-        double lw = -INFINITY;
-        if (j < n_tile) {
-            const int64_t i = (int64_t)j0 + j;
-            uint32_t parent = i_a + j;                                // global id
-            if (lookup) {
-                if (resample) parent = sm.anc[pad((int)j)];
-            } else if (fa.mode == kParentArray) {
-                parent = __ldg(a.anc + i);
-            }
-            cusmc_u32x4 r0{};
-            if (PHILOX) r0 = cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
-            const double *src = a.x_prev + ((int64_t)parent - a.parent_base);
-            if (PEERS && a.has_prev) {
-                const uint32_t rk = fast_div(parent, a.per_rank);
-                const uint32_t col = parent - rk * a.per_rank.d;
-                src = (rk == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[rk]) + col;
-            }
-            lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0);
-            if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
-            if (a.lw) st_stream(a.lw + i, lw);
-            if (a.hist_w) st_stream(a.hist_w + i, lw);
-            if (a.hist_a) a.hist_a[i] = parent;
-            if (fa.anc_out) fa.anc_out[i] = parent;
+    // one child: everything after the parent's state is known
+    auto child = [&](uint32_t j, uint32_t parent, const double *src, const double *xp_in) {
+        const int64_t i = (int64_t)j0 + j;
+        cusmc_u32x4 r0{};
+        if (PHILOX) r0 = cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
+        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0, xp_in);
+        if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
+        if (a.lw) st_stream(a.lw + i, lw);
+        if (a.hist_w) st_stream(a.hist_w + i, lw);
+        if (a.hist_a) a.hist_a[i] = parent;
+        if (fa.anc_out) fa.anc_out[i] = parent;
+        return lw;
+    };
+    auto parent_of = [&](uint32_t j) {
+        uint32_t parent = i_a + j;                                // global id
+        if (lookup) {
+            if (resample) parent = sm.anc[pad((int)j)];
+        } else if (fa.mode == kParentArray) {
+            parent = __ldg(a.anc + (int64_t)j0 + j);
         }
-        sm.lw[pad((int)j)] = lw;
+        return parent;
+    };
+    auto column_of = [&](uint32_t parent) {
+        const double *src = a.x_prev + ((int64_t)parent - a.parent_base);
+        if (PEERS && a.has_prev) {
+            const uint32_t rk = fast_div(parent, a.per_rank);
+            const uint32_t col = parent - rk * a.per_rank.d;
+            src = (rk == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[rk]) + col;
+        }
+        return src;
+    };
+    if constexpr (COH && D <= 4) {
+        // persistent kernel: the cloud lives in L2 and a round is one dependent gather -- bound by its
+        // latency, not by bandwidth.  A batch of rounds issues all its gathers first, then computes.
+        constexpr int kBatch = 4;
+#pragma unroll 1
+        for (int rb = 0; rb < kItems; rb += kBatch) {
+            double xpre[kBatch][D];
+            uint32_t par[kBatch];
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t j = (uint32_t)(rb + b) * kThreads + tid;
+                par[b] = j < n_tile ? parent_of(j) : 0u;
+                const double *src = column_of(par[b]);
+#pragma unroll
+                for (int k = 0; k < D; ++k) xpre[b][k] = (j < n_tile && a.has_prev) ? __ldcg(src + (int64_t)k * a.ld_prev) : 0.0;
+            }
+#pragma unroll
+            for (int b = 0; b < kBatch; ++b) {
+                const uint32_t j = (uint32_t)(rb + b) * kThreads + tid;
+                double lw = -INFINITY;
+                if (j < n_tile) lw = child(j, par[b], nullptr, xpre[b]);
+                sm.lw[pad((int)j)] = lw;
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int r = 0; r < kItems; ++r) {
+            const uint32_t j = (uint32_t)r * kThreads + tid;
+            double lw = -INFINITY;
+            if (j < n_tile) {
+                const uint32_t parent = parent_of(j);
+                lw = child(j, parent, column_of(parent), nullptr);
+            }
+            sm.lw[pad((int)j)] = lw;
+        }
     }
     __syncthreads();
+    CUSMC_STAMP(fa.trace, 2);
 
     // ---- 3. weigh: block-relative fixed-point image of the tile ----------------------------------------
     double v[kItems], m = -INFINITY;

@@ -97,15 +97,20 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 // a register array in the persistent kernel, whose observation changes inside the launch.  COH: the
 // parent state was written earlier in the SAME launch by other blocks (persistent kernel): read it
 // through L2, never through the non-coherent path.
+// xp_in (optional): the parent state already gathered into registers by the caller (the persistent
+// kernel issues a batch of gathers before it computes the batch: its rounds are latency-bound).
 template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false>
 __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                 const StepArgs &a, int64_t i, const double *__restrict__ src,
-                                                const cusmc_u32x4 &r0)
+                                                const cusmc_u32x4 &r0, const double *xp_in = nullptr)
 {
     const int d = EXACT ? D : a.d;
     const uint64_t idx = (uint64_t)(a.i0 + i);
     double xp[D], z[D], xn[D];
-    if (a.has_prev) {
+    if (xp_in) {
+#pragma unroll
+        for (int j = 0; j < D; ++j) xp[j] = xp_in[j];
+    } else if (a.has_prev) {
 #pragma unroll
         for (int j = 0; j < D; ++j)
             xp[j] = (EXACT || j < d) ? (COH ? __ldcg(src + (int64_t)j * a.ld_prev) : __ldg(src + (int64_t)j * a.ld_prev)) : 0.0;

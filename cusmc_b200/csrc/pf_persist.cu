@@ -25,6 +25,7 @@
 #include "tile_update_impl.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 
 namespace {
 
@@ -45,6 +46,7 @@ struct PersistArgs {
     unsigned *barrier;              // [0] arrival counter, [1] release generation; zero at launch
     int64_t tiles_alloc;
     int T;
+    double *trace;                  // profiling builds (-DCUSMC_TRACE): [T][8] time stamps of block 0
 };
 
 // Grid barrier whose last arriver runs the tile update of step t before releasing the others.
@@ -59,6 +61,15 @@ __device__ __forceinline__ void barrier_with_update(const PersistArgs &pa, int t
         const unsigned old = atomicAdd(pa.barrier, 1u);
         __threadfence();                                    // acquire the others' (if this is the last arrival)
         *s_last = old == (gen + 1u) * gridDim.x - 1u;
+#ifdef CUSMC_TRACE
+        if (pa.trace && t > 0) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (blockIdx.x == 0) pa.trace[1 + (size_t)t * 9 + 7] = (double)now;       // block 0 has arrived
+            if (*s_last) pa.trace[1 + (size_t)t * 9 + 5] = (double)now;               // the last arrival
+            if (t == 50) pa.trace[1 + ((size_t)pa.T + blockIdx.x) * 9 + 7] = (double)now;
+        }
+#endif
     }
     __syncthreads();
     if (*s_last) {
@@ -75,6 +86,13 @@ __device__ __forceinline__ void barrier_with_update(const PersistArgs &pa, int t
         tile_update_block<kThreads>(u, us);
         __syncthreads();
         if (threadIdx.x == 0) {
+#ifdef CUSMC_TRACE
+            if (pa.trace && t > 0) {
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                pa.trace[1 + (size_t)t * 9 + 6] = (double)now;                          // update done
+            }
+#endif
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pa.barrier + 1), "r"(gen + 1u) : "memory");
         }
@@ -139,8 +157,17 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
             fa.s.lw = pa.lw;
             fa.anc_out = pa.anc;
         }
+#ifdef CUSMC_TRACE
+        // block 0 stamps every step; at step 50 EVERY block stamps its own row (after the T rows of block 0;
+        // the word before a row says "everybody": rows are 9 words apart)
+        fa.trace = pa.trace ? pa.trace + 1 + (size_t)t * 9 : nullptr;
+        if (pa.trace && t == 50) fa.trace = pa.trace + 1 + ((size_t)pa.T + blockIdx.x) * 9;
+#endif
+        CUSMC_STAMP(fa.trace, 0);
         pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op, cobs, ep, fa, blockIdx.x, sm);
+        CUSMC_STAMP(fa.trace, 3);
         barrier_with_update(pa, t, gen, &s_last, us);
+        CUSMC_STAMP(fa.trace, 4);
     }
 }
 
@@ -314,6 +341,10 @@ int cusmc_filter_run_persistent(cusmc_filter *f, const cusmc_filter_draws *draws
     pa.barrier = barrier;
     pa.tiles_alloc = fimage_tiles(f->img_n);
     pa.T = T;
+#ifdef CUSMC_TRACE
+    pa.trace = nullptr;      // a device buffer of T x 8 doubles, handed in by the profiling script
+    if (getenv("CUSMC_TRACE_BUF")) pa.trace = (double *)strtoull(getenv("CUSMC_TRACE_BUF"), nullptr, 0);
+#endif
     CUSMC_CUDA(ctx, cudaEventRecord(f->ev0, st));
     uint32_t tile_n = 0;
     const int rc = launch_persistent_any(f, pa, !cfg.reproducible_rng, model_is_diag(f), false, &tile_n);
