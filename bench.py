@@ -55,7 +55,11 @@ def bench_config():
 def ncu_traffic():
     """DRAM bytes per launch of the headline kernel from the committed ncu --set full capture."""
     try:
-        return float(json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))["traffic_bytes_per_launch"])
+        for name in ("r02_traffic.json", "r01_traffic.json"):      # regenerated from the final build each round
+            path = os.path.join(ROOT, "profiles", name)
+            if os.path.exists(path):
+                return float(json.load(open(path))["traffic_bytes_per_launch"])
+        return None
     except Exception:
         return None
 
@@ -493,50 +497,111 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
     return out
 
 
+def _sharded_run(pf, torch, dist, exchange):
+    pf.run(exchange=exchange)
+    torch.cuda.synchronize()
+    dist.barrier()
+    pf.run(exchange=exchange)
+    torch.cuda.synchronize()
+    t = torch.tensor([pf.last_ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
-    """C5: synthetic state-space SMC, d = 8, 8 Mi particles per GPU (64 Mi on 8), systematic
-    resampling every step; scalars over NCCL, particle data by peer loads / stores."""
+    """C5: synthetic state-space SMC, d = 8, 8 Mi particles per GPU (64 Mi on 8), systematic resampling
+    every step: two launches per step and rank; scalars through peer-memory mailboxes (or NCCL), parents'
+    weight images and states by peer loads over NVLink."""
     import cusmc_b200
     out = {}
+    rank = dist.get_rank()
+    d, per = 8, 8 << 20
+    N = per * world
+    I = np.eye(d)
     try:
-        d, per, T = 8, 8 << 20, (11 if quick else 41)
-        N = per * world
-        I = np.eye(d)
+        T = 11 if quick else 41
         Y = np.random.default_rng(5000).standard_normal((d, T))
         pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, I, I,
                                               resampler="systematic", seed=2, summary=False)
-        res = {}
-        for exchange in ("p2p", "nccl"):
-            pf.run(exchange=exchange)
-            torch.cuda.synchronize()
-            dist.barrier()
-            pf.run(exchange=exchange)
-            torch.cuda.synchronize()
-            t = torch.tensor([pf.last_ms], dtype=torch.float64, device="cuda")
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            res[exchange] = float(t.item())
+        res = {ex: _sharded_run(pf, torch, dist, ex) for ex in ("p2p", "nccl")}
+        ess = pf.summary()["ess"]
         status = pf.exchange_status()
         pf.close()
         ms = res["p2p"]
         rate = N * (T - 1) / (ms * 1e-3)
         out["pf_c5_sharded_particle_steps_per_sec"] = {
             "value": rate, "N_global": N, "n_gpus": world, "d": d, "T": T, "ms_per_step": ms / (T - 1),
-            "resampler": "systematic", "noise": "philox in-kernel", "bytes_per_particle_step": 160,
-            "roofline_frac_per_gpu": rate / world * 160 / (hbm_gbs * 1e9),
-            "exchange": "p2p: per-step max / sums / barrier through peer-memory mailboxes (one-warp kernels, "
-                        "CUDA IPC over NVLink), whole run enqueued by the library; ancestors by peer stores, "
-                        "parent states by peer loads",
+            "resampler": "systematic, every step", "noise": NOISE_NOTE, "ess": True,
+            "ess_mean_over_N": float(np.mean(ess[1:]) / N), "bytes_per_particle_step": 160,
+            "roofline_frac_per_gpu": rate / world * 160 / (hbm_gbs * 1e9), "launches_per_step_per_rank": 2,
+            "exchange": "p2p: the per-step maximum and sums travel through peer-memory mailboxes INSIDE the one-block "
+                        "tile-update kernel (CUDA IPC over NVLink), whole run enqueued by the library; parents' weight "
+                        "images and states read by peer loads in the fused step kernel",
             "exchange_status": status,
             "ms_per_step_nccl_exchange": res["nccl"] / (T - 1),
             "value_nccl_exchange": N * (T - 1) / (res["nccl"] * 1e-3)}
     except Exception as e:
         out["pf_c5_sharded_particle_steps_per_sec"] = {"error": repr(e)}
     try:
+        # the same model with informative observations (V = 0.05 I): the weights are uneven enough for the mass
+        # to move BETWEEN shards, so children really descend from parents on other GPUs
+        T = 11 if quick else 21
+        rng = np.random.default_rng(5002)
+        xs, Y = np.zeros(d), np.zeros((d, T))
+        for t in range(1, T):
+            xs = 0.9 * xs + rng.standard_normal(d)
+            Y[:, t] = xs + np.sqrt(0.05) * rng.standard_normal(d)
+        pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, 0.05 * I, I,
+                                              resampler="systematic", seed=3, summary=False)
+        ms = _sharded_run(pf, torch, dist, "p2p")
+        ess = pf.summary()["ess"]
+        _, _, a = pf.local_state()
+        remote = torch.tensor([float(np.count_nonzero(a // pf.plan.per != rank)), float(a.size)], dtype=torch.float64,
+                              device="cuda")
+        dist.all_reduce(remote)
+        frac = float(remote[0] / remote[1])
+        pf.close()
+        out["pf_c5_sharded_skewed_weights"] = {
+            "value": N * (T - 1) / (ms * 1e-3), "N_global": N, "n_gpus": world, "d": d, "T": T, "ms_per_step": ms / (T - 1),
+            "model": "V = 0.05 I (informative observations), data simulated from the model",
+            "ess_mean_over_N": float(np.mean(ess[1:]) / N), "remote_parent_fraction_last_step": frac,
+            "nvlink_gather_bytes_per_step_estimate": frac * N * 8 * d,
+            "note": "remote parents are read over NVLink by the fused step kernel (8 d bytes per child whose parent "
+                    "lives on another GPU, plus the parents' tile-local CDF words during the lookup)"}
+    except Exception as e:
+        out["pf_c5_sharded_skewed_weights"] = {"error": repr(e)}
+    try:
+        # real-NVLink bit-exactness: a 2^20 x world particle filter sharded over the ranks against the SAME
+        # filter on rank 0 alone (final states, log-weights and ancestors must be identical bit for bit)
+        n1, T = (1 << 20) * world, 6
+        Y = np.random.default_rng(5003).standard_normal((d, T))
+        md = (np.zeros(d), I, I, 0.9 * I, 0.5 * I, 0.3 * I)
+        pf = cusmc_b200.ShardedParticleFilter(ctx, n1, Y, *md, resampler="systematic", seed=77, summary=False)
+        pf.run(exchange="p2p")
+        xs_, ws_, as_ = pf.local_state()
+        st = pf.exchange_status()
+        pf.close()
+        parts = [None] * world
+        dist.gather_object((xs_, ws_, as_, st), parts if rank == 0 else None, dst=0)
+        if rank == 0:
+            single = ctx.filter(N=n1, Y=Y, m0=md[0], C0=md[1], F=md[2], G=md[3], V=md[4], W=md[5], resampler="systematic",
+                                seed=77, summary=False, persistent=False)
+            single.run()
+            x1, w1, a1 = single.state()
+            single.close()
+            same = (np.array_equal(np.concatenate([p[0] for p in parts], axis=1), x1) and
+                    np.array_equal(np.concatenate([p[1] for p in parts]), w1) and
+                    np.array_equal(np.concatenate([p[2] for p in parts]), a1))
+            out["sharded_equals_single"] = bool(same) and all(p[3] == 0 for p in parts)
+            out["sharded_equals_single_config"] = {"N_global": n1, "d": d, "T": T, "compared": "final x, log-weights, ancestors"}
+        dist.barrier()
+    except Exception as e:
+        out["sharded_equals_single"] = {"error": repr(e)}
+    try:
         # C3 over the ranks: the 65 536 chains are independent, each rank advances its contiguous share
         # (strong scaling, no data-path collective); one all-reduce of the posterior moments at the end
         Cn_all, d, steps = 65536, 32, (50 if quick else 200)
         Cn = Cn_all // world
-        rank = dist.get_rank()
         g = torch.Generator(device="cuda").manual_seed(77 + rank)
         A = torch.randn((Cn, d, d), dtype=torch.float64, device="cuda", generator=g)
         L = torch.linalg.cholesky(A @ A.transpose(1, 2) / d + torch.eye(d, dtype=torch.float64, device="cuda"))
@@ -563,7 +628,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         out["mh_c3_sharded_chain_steps_per_sec"] = {
             "value": Cn * world * steps / (ms * 1e-3), "chains": Cn * world, "chains_per_gpu": Cn, "n_gpus": world,
             "d": d, "steps": steps, "ms": ms, "scaling": "strong", "target": "mvt nu=5 per-chain L",
-            "noise": "philox in-kernel", "includes": "all-reduce of the 2 d posterior moment sums"}
+            "noise": NOISE_NOTE, "includes": "all-reduce of the 2 d posterior moment sums"}
     except Exception as e:
         out["mh_c3_sharded_chain_steps_per_sec"] = {"error": repr(e)}
     return out
@@ -670,6 +735,25 @@ def main():
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
     e2e_value = world * N_POINTS * e2e_steps / float(te.item())
 
+    # the ceiling of that leg: every rank copying one step's input from pinned host memory at the same
+    # time, nothing else (what the box's PCIe links give N concurrent host->device streams)
+    dev_buf = torch.empty((N_POINTS, DIM), dtype=torch.float64, device="cuda")
+    for _ in range(2):
+        dev_buf.copy_(host_x[0], non_blocking=True)
+    barrier()
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    c0.record()
+    for i in range(5):
+        dev_buf.copy_(host_x[i % 2], non_blocking=True)
+    c1.record()
+    barrier()
+    tc = torch.tensor([c0.elapsed_time(c1) / 5.0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+    h2d_gbs_per_rank = N_POINTS * DIM * 8 / (float(tc.item()) * 1e-3) / 1e9
+    h2d_ceiling_evals = world * N_POINTS / (float(tc.item()) * 1e-3)
+    del dev_buf
+
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True,
@@ -682,7 +766,10 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
                 "d2h_bytes_per_step": N_POINTS * 8, "steps": e2e_steps,
                 "path": "cusmc_logpdf (host pointers, pinned AoS in, pinned result out)",
-                "numa_node": numa_node},
+                "numa_node": numa_node,
+                "h2d_ceiling": {"gbs_per_rank_all_ranks_concurrent": h2d_gbs_per_rank, "evals_per_sec": h2d_ceiling_evals,
+                                "how": "all ranks copy one step's 128 MiB input from pinned host memory at once, 5 times"},
+                "frac_of_h2d_ceiling": e2e_value / h2d_ceiling_evals},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -32,6 +32,14 @@ extern "C" int cusmc_ctx_create(cusmc_ctx **out, int device)
         return CUSMC_ERR_CUDA;
     }
     ctx->stream = ctx->own_stream;
+    // single-GPU filters take their device buffers from the device's stream-ordered pool: keep what they
+    // free, so that a filter per call (cusmc_run) costs microseconds of allocation, not ~15 ms of
+    // cudaMalloc / cudaFree
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t keep = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     *out = ctx;
     return CUSMC_OK;
 }

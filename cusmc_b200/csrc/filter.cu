@@ -25,6 +25,9 @@
 #include "../../include/cusmc_philox.h"
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <new>
 #include <thread>
@@ -440,23 +443,30 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     cudaSetDevice(f->ctx->device);
     cudaStreamSynchronize(f->ctx->stream);
     detach_peers(f);
-    cudaFree(f->x[0]);
-    cudaFree(f->x[1]);
-    cudaFree(f->lw);
-    cudaFree(f->anc);
-    cudaFree(f->cdf);
-    cudaFree(f->slots);
-    cudaFree(f->moments);
-    cudaFree(f->img[0]);
-    cudaFree(f->img[1]);
-    cudaFree(f->rank_sums);
+    // pooled (single-GPU) filters hand their buffers back to the stream-ordered pool; sharded ones own
+    // cudaMalloc memory (CUDA IPC cannot export pool allocations)
+    cudaStream_t st = f->ctx->stream;
+    auto release = [&](void *p) {
+        if (!p) return;
+        if (f->pooled) cudaFreeAsync(p, st); else cudaFree(p);
+    };
+    release(f->x[0]);
+    release(f->x[1]);
+    release(f->lw);
+    release(f->anc);
+    release(f->cdf);
+    release(f->slots);
+    release(f->moments);
+    release(f->img[0]);
+    release(f->img[1]);
+    release(f->rank_sums);
     cudaFree(f->persist);
-    cudaFree(f->mail);
-    cudaFree(f->mail_err);
+    release(f->mail);
+    release(f->mail_err);
     cudaFree(f->peer_tables);
-    cudaFree(f->hist_x);
-    cudaFree(f->hist_w);
-    cudaFree(f->hist_a);
+    release(f->hist_x);
+    release(f->hist_w);
+    release(f->hist_a);
     if (f->ev0) cudaEventDestroy(f->ev0);
     if (f->ev1) cudaEventDestroy(f->ev1);
     delete f;
@@ -526,8 +536,10 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         return rc;
     }
     cudaError_t e = cudaSetDevice(ctx->device);
+    f->pooled = world == 1;
     auto alloc = [&](void **p, size_t bytes) {
-        if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 8);
+        if (e != cudaSuccess) return;
+        e = f->pooled ? cudaMallocAsync(p, bytes ? bytes : 8, ctx->stream) : cudaMalloc(p, bytes ? bytes : 8);
     };
     const size_t P = (size_t)f->per;          // columns allocated on every rank
     alloc((void **)&f->x[0], sizeof(double) * P * d);
@@ -546,7 +558,8 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         const size_t img_bytes = sizeof(unsigned long long) * (size_t)fimage_words(f->img_n);
         for (int b = 0; b < 2; ++b) {
             alloc((void **)&f->img[b], img_bytes);
-            if (e == cudaSuccess) e = cudaMemset(f->img[b], 0, sizeof(unsigned long long) * (size_t)fimage_header_words(f->img_n));
+            if (e == cudaSuccess)
+                e = cudaMemsetAsync(f->img[b], 0, sizeof(unsigned long long) * (size_t)fimage_header_words(f->img_n), ctx->stream);
         }
         if (world > 1) alloc((void **)&f->rank_sums, sizeof(unsigned long long) * 3 * CUSMC_MAX_PEERS);
     }
@@ -554,8 +567,9 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         const size_t mail_bytes = sizeof(unsigned long long) * 4 * 3 * (size_t)world * (size_t)T;
         alloc((void **)&f->mail, mail_bytes);
         alloc((void **)&f->mail_err, 8);
-        if (e == cudaSuccess) e = cudaMemset(f->mail, 0, mail_bytes);
-        if (e == cudaSuccess) e = cudaMemset(f->mail_err, 0, 8);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->mail, 0, mail_bytes, ctx->stream);
+        if (e == cudaSuccess) e = cudaMemsetAsync(f->mail_err, 0, 8, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);     // peers may map these buffers right away
     }
     if (cfg->keep_history) {
         // keep_history = 1: all T steps stay on the device (cusmc_filter_get_history);
@@ -1247,6 +1261,16 @@ struct RunRing {
     cudaEvent_t ready[2] = {nullptr, nullptr}, copied[2] = {nullptr, nullptr};
     double *weights = nullptr, *posterior_x = nullptr;
     uint32_t *ancestors = nullptr;
+    // the drain crew: `workers` host threads, alive for the whole run, each copying ITS slice of every
+    // landed chunk into the caller's arrays while the calling thread keeps enqueueing steps.  (Spawning
+    // helpers per chunk and draining from the enqueueing thread made the host side the critical path:
+    // 51 ms for the C1 run, of which the GPU needed 12.)
+    int workers = 1;
+    std::atomic<int> shipped{0};      // chunks whose device -> pinned copy has been ENQUEUED (by the caller's thread)
+    std::atomic<int> landed{0};       // chunks whose copy has COMPLETED (worker 0 waits on the event)
+    std::atomic<long long> drained{0};   // worker-chunks finished: chunk c is out of its slot when drained >= workers (c + 1)
+    std::atomic<int> abort{0};
+    std::vector<std::thread> crew;
 
     size_t off_w() const { return sizeof(double) * (size_t)K * n * d; }
     size_t off_a() const { return off_w() + sizeof(double) * (size_t)K * n; }
@@ -1270,51 +1294,73 @@ struct RunRing {
         if (ancestors)
             CUSMC_CUDA(ctx, cudaMemcpyAsync(p + off_a(), da, sizeof(uint32_t) * (size_t)rows * n, cudaMemcpyDeviceToHost, ctx->aux_stream));
         CUSMC_CUDA(ctx, cudaEventRecord(copied[s], ctx->aux_stream));
+        shipped.store(c + 1, std::memory_order_release);
         return CUSMC_OK;
     }
 
-    static void spread_copy(char *dst, const char *src, size_t bytes)
+    static void slice_copy(char *dst, const char *src, size_t bytes, int w, int W)
+    {
+        const size_t part = ((bytes + W - 1) / W + 4095) & ~(size_t)4095;      // whole pages per worker
+        const size_t lo = (size_t)w * part;
+        if (lo < bytes) std::memcpy(dst + lo, src + lo, std::min(part, bytes - lo));
+    }
+
+    void work(int w)
+    {
+        for (int c = 0; c < chunks; ++c) {
+            if (w == 0) {
+                while (shipped.load(std::memory_order_acquire) <= c && !abort.load()) std::this_thread::yield();
+                if (abort.load()) return;
+                if (cudaEventSynchronize(copied[c & 1]) != cudaSuccess) abort.store(1);
+                landed.store(c + 1, std::memory_order_release);
+            } else {
+                while (landed.load(std::memory_order_acquire) <= c && !abort.load()) std::this_thread::yield();
+            }
+            if (abort.load()) return;
+            const int rows = rows_of(c);
+            const char *p = (const char *)pin[c & 1];
+            const size_t t0 = (size_t)c * K;
+            if (posterior_x) slice_copy((char *)(posterior_x + t0 * n * d), p, sizeof(double) * (size_t)rows * n * d, w, workers);
+            if (weights) slice_copy((char *)(weights + t0 * n), p + off_w(), sizeof(double) * (size_t)rows * n, w, workers);
+            if (ancestors) slice_copy((char *)(ancestors + t0 * n), p + off_a(), sizeof(uint32_t) * (size_t)rows * n, w, workers);
+            drained.fetch_add(1, std::memory_order_release);
+        }
+    }
+
+    // blocks the caller's thread until chunk c has left its ring slot (every worker is done with it)
+    bool wait_drained(int c)
+    {
+        while (drained.load(std::memory_order_acquire) < (long long)workers * (c + 1)) {
+            if (abort.load()) return false;
+            std::this_thread::yield();
+        }
+        return true;
+    }
+
+    void start()
     {
         const unsigned hw = std::thread::hardware_concurrency();
-        const int workers = bytes < ((size_t)1 << 20) ? 1 : (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
-        const size_t part = ((bytes + workers - 1) / workers + 4095) & ~(size_t)4095;
-        std::vector<std::thread> pool;
-        size_t handed = std::min(part, bytes);
+        workers = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
         try {                                            // nothing may unwind across the C ABI
-            for (int w = 1; w < workers && handed < bytes; ++w) {
-                const size_t lo = handed, len = std::min(part, bytes - lo);
-                pool.emplace_back([=] { std::memcpy(dst + lo, src + lo, len); });
-                handed = lo + len;
-            }
+            for (int w = 0; w < workers; ++w) crew.emplace_back([this, w] { work(w); });
         } catch (...) {
+            // fewer threads than hoped for: the slices are fixed, so finish what exists and fall back to one
+            abort.store(1);
+            for (auto &t : crew) t.join();
+            crew.clear();
+            abort.store(0);
+            shipped.store(0);
+            landed.store(0);
+            drained.store(0);
+            workers = 1;
+            crew.emplace_back([this] { work(0); });
         }
-        std::memcpy(dst, src, std::min(part, bytes));
-        if (handed < bytes) std::memcpy(dst + handed, src + handed, bytes - handed);
-        for (auto &t : pool) t.join();
-    }
-
-    // chunk c has landed in pinned memory: copy it into the caller's arrays (frees ring slot c & 1)
-    int drain(int c)
-    {
-        cusmc_ctx *ctx = f->ctx;
-        const int s = c & 1, rows = rows_of(c);
-        CUSMC_CUDA(ctx, cudaEventSynchronize(copied[s]));
-        const char *p = (const char *)pin[s];
-        const size_t t0 = (size_t)c * K;
-        if (posterior_x) spread_copy((char *)(posterior_x + t0 * n * d), p, sizeof(double) * (size_t)rows * n * d);
-        if (weights) spread_copy((char *)(weights + t0 * n), p + off_w(), sizeof(double) * (size_t)rows * n);
-        if (ancestors) {
-            spread_copy((char *)(ancestors + t0 * n), p + off_a(), sizeof(uint32_t) * (size_t)rows * n);
-            if (c == 0)
-                for (size_t i = 0; i < n; ++i) ancestors[i] = (uint32_t)i;      // row t = 0: identity
-        }
-        return CUSMC_OK;
     }
 
     void release()
     {
-        for (int s = 0; s < 2; ++s) {
-            if (pin[s]) cudaFreeHost(pin[s]);
+        for (auto &t : crew) t.join();
+        for (int s = 0; s < 2; ++s) {          // (the pinned slots are the context's)
             if (ready[s]) cudaEventDestroy(ready[s]);
             if (copied[s]) cudaEventDestroy(copied[s]);
         }
@@ -1325,6 +1371,14 @@ int run_streamed(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights
                  uint32_t *ancestors)
 {
     cusmc_filter_config c = *cfg;
+    // CUSMC_RUN_TRACE=1: wall-clock of the phases of this call on stderr (profiles/c1_breakdown.py)
+    const bool trace = std::getenv("CUSMC_RUN_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto lap = [&](const char *what) {
+        if (trace)
+            std::fprintf(stderr, "cusmc_run %-28s %8.2f ms\n", what,
+                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     CUSMC_REQUIRE(ctx, c.world <= 1, "cusmc_run is single-GPU (a sharded run is driven through cusmc_filter_run_sharded)");
     CUSMC_REQUIRE(ctx, c.N >= 1 && c.d >= 1 && c.T >= 1, "N, d, T must be positive");
     const size_t row_bytes = (size_t)c.N * (sizeof(double) * (size_t)c.d + sizeof(double) + sizeof(uint32_t));
@@ -1333,6 +1387,7 @@ int run_streamed(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights
     c.persistent = -1;            // the history rows are written by the per-step kernels
     cusmc_filter *f = nullptr;
     CUSMC_CHECK(cusmc_filter_create(ctx, &c, &f));
+    lap("filter created");
     RunRing ring;
     ring.f = f;
     ring.K = K;
@@ -1344,18 +1399,25 @@ int run_streamed(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights
     ring.ancestors = ancestors;
     ring.pin_bytes = (size_t)K * row_bytes;
     int rc = cusmc_aux_stream(ctx);
+    // the two pinned slots belong to the CONTEXT (grow-only): page-locking 2 x 8 MB costs ~20 ms, more than
+    // the whole C1 run, so only the first call on a context pays for it
+    void *pin_base = nullptr;
+    const size_t slot_bytes = (ring.pin_bytes + 4095) & ~(size_t)4095;
+    if (rc == CUSMC_OK) rc = cusmc_pinned(ctx, 2 * slot_bytes, &pin_base);
     for (int s = 0; s < 2 && rc == CUSMC_OK; ++s) {
-        if (cudaMallocHost(&ring.pin[s], ring.pin_bytes) != cudaSuccess ||
-            cudaEventCreateWithFlags(&ring.ready[s], cudaEventDisableTiming) != cudaSuccess ||
+        ring.pin[s] = (char *)pin_base + (size_t)s * slot_bytes;
+        if (cudaEventCreateWithFlags(&ring.ready[s], cudaEventDisableTiming) != cudaSuccess ||
             cudaEventCreateWithFlags(&ring.copied[s], cudaEventDisableTiming) != cudaSuccess)
-            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_run: pinned staging allocation failed: %s",
-                            cudaGetErrorString(cudaGetLastError()));
+            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_run: event creation failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
+    lap("pinned ring allocated");
+    if (rc == CUSMC_OK) ring.start();
     const int T = c.T;
     for (int t = 0; t < T && rc == CUSMC_OK; ++t) {
         const int ch = t / K;
-        // the ring slot of this chunk was last used by chunk ch - 2: drained (hence copied) first
-        if (t % K == 0 && ch >= 2) rc = ring.drain(ch - 2);
+        // the ring slot of this chunk was last used by chunk ch - 2: it must have been drained
+        if (t % K == 0 && ch >= 2 && !ring.wait_drained(ch - 2))
+            rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_run: the device -> host copy of the history failed");
         if (rc != CUSMC_OK) break;
         if (t == 0) {
             rc = cusmc_filter_begin(f, nullptr);
@@ -1369,12 +1431,20 @@ int run_streamed(cusmc_ctx *ctx, const cusmc_filter_config *cfg, double *weights
         if (rc == CUSMC_OK && (t % K == K - 1 || t == T - 1)) rc = ring.ship(ch);
     }
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 1);
-    for (int ch = std::max(0, ring.chunks - 2); ch < ring.chunks && rc == CUSMC_OK; ++ch) rc = ring.drain(ch);
+    lap("all steps enqueued");
+    if (rc == CUSMC_OK && !ring.wait_drained(ring.chunks - 1))
+        rc = cusmc_fail(ctx, CUSMC_ERR_CUDA, "cusmc_run: the device -> host copy of the history failed");
+    if (rc != CUSMC_OK) ring.abort.store(1);
+    if (rc == CUSMC_OK && ancestors)
+        for (size_t i = 0; i < ring.n; ++i) ancestors[i] = (uint32_t)i;      // row t = 0: identity
+    lap("history drained");
     if (rc == CUSMC_OK) rc = filter_run_status(f);
     cudaStreamSynchronize(ctx->aux_stream);
     cudaStreamSynchronize(ctx->stream);
     ring.release();
+    lap("ring released");
     cusmc_filter_destroy(f);
+    lap("filter destroyed");
     return rc;
 }
 

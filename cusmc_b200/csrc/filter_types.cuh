@@ -32,6 +32,7 @@ struct cusmc_filter {
     int world = 1, rank = 0;
     int64_t per = 0, lo = 0, n = 0;
     bool attached = false;
+    bool pooled = false;                  // device buffers come from the stream-ordered pool (single-GPU filters)
     CusmcPeers peer_x[2]{}, peer_anc{}, peer_lw{}, peer_mail{}, peer_img[2]{};
     unsigned long long *mail = nullptr;   // [T][3 phases][world] x 4 words, written by the peers
     unsigned long long *mail_err = nullptr;   // 1 word: a spin-wait timed out

@@ -30,6 +30,10 @@ for rs in ("metropolis", "systematic"):
         t5 = time.perf_counter()
         print(rs, "create %.1f ms, enqueue %.1f ms, sync %.1f ms (device loop %.1f ms), history D2H %.1f ms, close %.1f ms"
               % ((t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3, pf.last_ms if False else 0.0, (t4 - t3) * 1e3, (t5 - t4) * 1e3))
-    t0 = time.perf_counter()
-    cusmc_b200.run(N, 2, T, Y, np.zeros(2), I2, I2, I2, 0.1 * I2, 0.1 * I2, 0.0, rs, "mvn", seed=1)
-    print(rs, "run() end to end %.1f ms" % ((time.perf_counter() - t0) * 1e3))
+    for rep in range(3):
+        os.environ["CUSMC_RUN_TRACE"] = "1" if rep == 2 else ""
+        if rep < 2:
+            os.environ.pop("CUSMC_RUN_TRACE")
+        t0 = time.perf_counter()
+        cusmc_b200.run(N, 2, T, Y, np.zeros(2), I2, I2, I2, 0.1 * I2, 0.1 * I2, 0.0, rs, "mvn", seed=1)
+        print(rs, "run() end to end %.1f ms" % ((time.perf_counter() - t0) * 1e3))
