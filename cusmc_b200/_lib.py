@@ -25,7 +25,7 @@ flt = C.c_float
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_DEGENERATE, ERR_UNSUPPORTED, ERR_TIMEOUT = range(7)
 MVN, MVT = 0, 1
 SOA, AOS = 0, 1
-RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL = 0, 1, 2
+RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL, RESAMPLE_REJECTION = 0, 1, 2, 3
 MAX_DIM = 32
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
@@ -69,6 +69,7 @@ PROTOTYPES = {
     "cusmc_mvt_sample": (ci, [vp, vp, vp, vp, vp, vp, vp, vp, u64, u64, i64, ci, flt]),
     "cusmc_metropolis_hastings": (ci, [vp, vp, vp, vp, vp, u64, u64, i64, ci]),
     "cusmc_metropolis_hastings_dev": (ci, [vp, vp, vp, vp, vp, u64, u64, i64, ci, ci]),
+    "cusmc_rejection_resample_dev": (ci, [vp, vp, vp, vp, u64, u64, i64, ci]),
     "cusmc_propagate_reweight_dev": (ci, [vp, ci, ci, vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp,
                                           vp, flt, vp, vp, u64, u64, vp, vp]),
     "cusmc_weights_max_dev": (ci, [vp, vp, i64, vp]),
@@ -82,6 +83,8 @@ PROTOTYPES = {
     "cusmc_normalize_ess": (ci, [vp, vp, i64, c_double_p, c_double_p]),
     "cusmc_mh_chains_dev": (ci, [vp, ci, i64, ci, ci, dbl, dbl, ci, vp, vp, vp, vp, vp, u64, vp, vp,
                                  vp, vp]),
+    "cusmc_mh_chains_general_dev": (ci, [vp, ci, i64, ci, ci, dbl, vp, dbl, ci, vp, vp, vp, vp, vp, u64, vp, vp,
+                                         vp, vp]),
     "cusmc_filter_create": (ci, [vp, C.POINTER(FilterConfig), C.POINTER(vp)]),
     "cusmc_filter_destroy": (ci, [vp]),
     "cusmc_filter_tile_size": (i64, [vp]),
@@ -106,6 +109,7 @@ PROTOTYPES = {
     "cusmc_filter_last_ms": (dbl, [vp]),
     "cusmc_filter_state_dev": (ci, [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]),
     "cusmc_filter_get_log_weights": (ci, [vp, vp]),
+    "cusmc_filter_get_lineage": (ci, [vp, vp, vp]),
     "cusmc_run": (ci, [vp, C.POINTER(FilterConfig), vp, vp]),
     "cusmc_run_ancestors": (ci, [vp, C.POINTER(FilterConfig), vp, vp, vp]),
     "cusmc_aos_to_soa_dev": (ci, [vp, vp, vp, i64, i64, ci]),

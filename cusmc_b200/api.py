@@ -20,12 +20,12 @@ import numpy as np
 
 from . import _lib
 from ._lib import (AOS, MVN as KIND_MVN, MVT as KIND_MVT, RESAMPLE_METROPOLIS,
-                   RESAMPLE_MULTINOMIAL, RESAMPLE_SYSTEMATIC, SOA, CusmcError, FilterConfig,
-                   FilterDraws)
+                   RESAMPLE_MULTINOMIAL, RESAMPLE_REJECTION, RESAMPLE_SYSTEMATIC, SOA, CusmcError,
+                   FilterConfig, FilterDraws)
 
 _KINDS = {"mvn": KIND_MVN, "mvt": KIND_MVT}
 _RESAMPLERS = {"metropolis": RESAMPLE_METROPOLIS, "systematic": RESAMPLE_SYSTEMATIC,
-               "multinomial": RESAMPLE_MULTINOMIAL}
+               "multinomial": RESAMPLE_MULTINOMIAL, "rejection": RESAMPLE_REJECTION}
 
 
 def _kind(name):
@@ -295,6 +295,10 @@ class Context:
         self._check(self.lib.cusmc_metropolis_hastings_dev(self.h, _dp(a), _dp(w), _dp(u), _dp(j),
                                                            int(seed), int(step), N, int(B), int(is_log)))
 
+    def rejection_resample_dev(self, a, w, w_max, seed=0, step=1, cap=4096, N=None):
+        self._check(self.lib.cusmc_rejection_resample_dev(self.h, _dp(a), _dp(w), _dp(w_max), int(seed), int(step),
+                                                          w.numel() if N is None else N, int(cap)))
+
     def weights_max_dev(self, w, max_out, N=None):
         self._check(self.lib.cusmc_weights_max_dev(self.h, _dp(w), w.numel() if N is None else N,
                                                    _dp(max_out)))
@@ -351,6 +355,16 @@ class Context:
             self.h, _kind(dist), Cn, d, int(steps), float(step_size), float(nu), int(shared), _dp(mu),
             _dp(L), _dp(x), _dp(z), _dp(thr), int(seed), _dp(n_accept), _dp(accept_bits), _dp(sum_x),
             _dp(sum_xx)))
+
+    def mh_chains_general_dev(self, dist, mu, L, x, steps, step_size, nu=0.0, shared=False, scale=None, z=None,
+                              thr=None, seed=0, n_accept=None, accept_bits=None, sum_x=None, sum_xx=None):
+        """Random-walk chains whose proposal x' = x + step_size * scale (.) z does not use the target's
+        factor: every step evaluates the target density in the kernel (forward substitution with the
+        chain's factor resident in registers).  Arguments as mh_chains_dev; scale: (d,) or None."""
+        Cn, d = x.shape
+        self._check(self.lib.cusmc_mh_chains_general_dev(
+            self.h, _kind(dist), Cn, d, int(steps), float(step_size), _dp(scale), float(nu), int(shared), _dp(mu),
+            _dp(L), _dp(x), _dp(z), _dp(thr), int(seed), _dp(n_accept), _dp(accept_bits), _dp(sum_x), _dp(sum_xx)))
 
     def aos_to_soa_dev(self, aos, soa):
         N, d = aos.shape
@@ -433,7 +447,7 @@ class ParticleFilter:
         per = shard_size(self.N, int(world))
         self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
         self.keep_history = bool(keep_history)
-        self.is_log = cfg.resampler != RESAMPLE_METROPOLIS
+        self.is_log = cfg.resampler not in (RESAMPLE_METROPOLIS, RESAMPLE_REJECTION)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
         self.h = h
@@ -518,6 +532,14 @@ class ParticleFilter:
             self.ctx._check(self.ctx.lib.cusmc_filter_get_log_weights(self.h, _hp(lw)))
             out["lw"] = lw
         return out
+
+    def lineage(self):
+        """The ancestor tree as paths: (lineage (T, n), n_unique (T,)) -- lineage[t, i] is the index at step t
+        of the ancestor of final particle i, n_unique[t] the distinct ancestors alive at step t."""
+        lin = np.empty((self.T, self.n_local), dtype=np.uint32)
+        nu = np.empty(self.T, dtype=np.int32)
+        self.ctx._check(self.ctx.lib.cusmc_filter_get_lineage(self.h, _hp(lin), _hp(nu)))
+        return lin, nu
 
     def status(self):
         """Waits for the last run; raises CusmcError (TIMEOUT / DEGENERATE) if it went wrong inside."""

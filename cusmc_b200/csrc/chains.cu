@@ -195,6 +195,131 @@ mh_chains_kernel(const ChainArgs a)
     if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
 }
 
+// ---- general random walk: the proposal does NOT use the target's factor ---------------------------
+// x' = x + s (.) z  (isotropic step, optionally a per-component scale): nothing cancels any more, so
+// EVERY step evaluates the target density -- the north star's "proposal, log-acceptance ratio and
+// accept / reject fused into the same kernel as the density evaluation" (a2's arithmetic,
+// src/statistics.cc.cpp:295-311, under the accept rule of src/samplers.cpp:30):
+//
+//     r = x' - mu,   v = L_c^-1 r  (forward substitution),   q' = |v|^2,   accept on (q', q)
+//
+// Row k of the chain's factor stays in lane k's REGISTERS for the whole run (d doubles per lane; the
+// factor is read from memory once per chain, not once per step: 264 B instead of 4.4 KB per step at
+// d = 32).  The substitution is column oriented inside the chain's W lanes: step j broadcasts
+// v_j = r_j / L_jj by shuffle, every lane k > j subtracts L_kj v_j; every lane accumulates the same
+// q' = sum_j v_j^2 in the same order, so no reduction follows.  oracle: orc_mh_chains_general (same
+// operation order: bit-exact decisions and states).
+struct GeneralArgs {
+    ChainArgs c;
+    const double *scale;          // optional per-component proposal scale (d doubles, shared)
+};
+
+template <int D, bool PHILOX, bool MOMENTS>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32)
+mh_general_kernel(const GeneralArgs ga)
+{
+    const ChainArgs &a = ga.c;
+    constexpr int W = D < 4 ? 4 : D;                 // lanes per chain
+    constexpr int G = 32 / W;                        // chains per warp
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / W, sub = lane % W;
+    const int64_t c0 = ((int64_t)blockIdx.x * kWarpsPerBlock + wib) * G;
+    if (c0 >= a.C) return;                           // the whole warp
+    const int d = a.d;
+    const bool active = c0 + grp < a.C;              // chains past the end ride along on zeros
+    const int64_t c = active ? c0 + grp : a.C - 1;
+    const bool live = active && sub < d;
+    const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
+    const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
+    const double mu = live ? __ldg(mc + sub) : 0.0;
+    // row k of the factor (column-major storage: element j of every lane's row is one coalesced line)
+    double row[D];
+#pragma unroll
+    for (int j = 0; j < D; ++j) row[j] = (live && j < sub) ? __ldg(Lc + (size_t)j * d + sub) : 0.0;
+    const double rinv = live ? 1.0 / __ldg(Lc + (size_t)sub * d + sub) : 0.0;
+    const double s_k = a.step_size * ((ga.scale && live) ? __ldg(ga.scale + sub) : 1.0);
+
+    // q = |L^-1 (x - mu)|^2, identical in every lane of the chain
+    auto quadform = [&](double xk) {
+        double r = live ? xk - mu : 0.0, q = 0.0;
+#pragma unroll
+        for (int j = 0; j < D; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, r * rinv, j, W);
+            q = fma(vj, vj, q);
+            r = fma(-row[j], vj, r);          // no-op for lanes k <= j (row[j] == 0); lane j is done with r
+        }
+        return q;
+    };
+    double x = live ? a.x[(size_t)c * d + sub] : 0.0;
+    double q = quadform(x);
+    const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
+    double sx = 0.0, sxx = 0.0;
+    uint32_t nacc = 0;
+
+    const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
+    double z_next = (zc && live) ? ld_stream(zc + sub) : 0.0;
+    // in-kernel randomness: batched exactly as in mh_chains_kernel (same (seed, chain, step, component)
+    // -> draw mapping of cusmc_philox.h)
+    double thr_batch = 0.0;
+    float zq[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int s = 0; s < a.steps; ++s) {
+        double z, thr;
+        if (PHILOX) {
+            if ((s & (W - 1)) == 0) {
+                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + sub), (uint64_t)c, 0);
+                const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+                thr_batch = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+            }
+            thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
+            if ((s & 3) == 0) {
+                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                 (uint32_t)(sub >> 2));
+                float n[4];
+                cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+                cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+#pragma unroll
+                for (int r = 0; r < 4; ++r) {
+                    const int pick = (lane & 3) ^ r;
+                    const float val = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
+                    zq[r] = __shfl_xor_sync(0xffffffffu, val, r);
+                }
+            }
+            const int r = (lane & 3) ^ (s & 3);
+            const float zf = r == 0 ? zq[0] : r == 1 ? zq[1] : r == 2 ? zq[2] : zq[3];
+            z = live ? (double)zf : 0.0;
+        } else {
+            z = z_next;
+            if (s + 1 < a.steps && live) z_next = ld_stream(zc + (size_t)(s + 1) * d + sub);   // prefetch
+            thr = __ldg(a.thr + (size_t)c * a.steps + s);
+        }
+        const double xp = fma(s_k, z, x);
+        const double qp = quadform(xp);
+        bool accept;
+        if (a.kind == CUSMC_MVT)
+            accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
+        else
+            accept = 0.5 * (qp - q) < thr;
+        if (accept) {
+            x = xp;
+            q = qp;
+            ++nacc;
+        }
+        if (MOMENTS) {
+            sx += x;
+            sxx = fma(x, x, sxx);
+        }
+        if (a.accept_bits && sub == 0 && active) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
+    }
+    if (live) {
+        a.x[(size_t)c * d + sub] = x;
+        if (MOMENTS) {
+            if (a.sum_x) a.sum_x[(size_t)c * d + sub] = sx;
+            if (a.sum_xx) a.sum_xx[(size_t)c * d + sub] = sxx;
+        }
+    }
+    if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
+}
+
 // ---- per-point covariance log-density -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -390,6 +515,55 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
     }
 #undef CUSMC_CHAIN_LAUNCH
 #undef CUSMC_CHAIN_CASE
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
+extern "C" int cusmc_mh_chains_general_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps, double step_size,
+                                           const double *scale_dev, double nu, int shared, const double *mu_dev,
+                                           const double *L_dev, double *x_dev, const double *z_dev,
+                                           const double *thr_dev, uint64_t seed, uint32_t *n_accept_dev,
+                                           uint8_t *accept_bits_dev, double *sum_x_dev, double *sum_xx_dev)
+{
+    CUSMC_ENTER(ctx);
+    CUSMC_REQUIRE(ctx, C >= 0 && steps >= 0 && d >= 1, "bad sizes");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || kind == CUSMC_MVT, "unknown distribution");
+    CUSMC_REQUIRE(ctx, kind == CUSMC_MVN || nu > 0.0, "mvt needs nu > 0");
+    CUSMC_REQUIRE(ctx, (z_dev == nullptr) == (thr_dev == nullptr), "z and thr must both be given or both NULL");
+    CUSMC_REQUIRE(ctx, C == 0 || (mu_dev && L_dev && x_dev), "NULL pointer");
+    if (d > 32) return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "d = %d > 32", d);
+    if (C == 0) return CUSMC_OK;
+    GeneralArgs ga;
+    ChainArgs &a = ga.c;
+    a.mu = mu_dev; a.L = L_dev; a.z = z_dev; a.thr = thr_dev;
+    a.x = x_dev; a.sum_x = sum_x_dev; a.sum_xx = sum_xx_dev;
+    a.n_accept = n_accept_dev; a.accept_bits = accept_bits_dev;
+    a.C = C; a.seed = seed; a.step_size = step_size; a.nu = nu;
+    a.d = d; a.steps = steps; a.kind = kind; a.shared = shared;
+    ga.scale = scale_dev;
+    const int pad = cusmc_pad_dim(d);
+    const int per_block = kWarpsPerBlock * (32 / (pad < 4 ? 4 : pad));    // chains per block
+    const unsigned grid = (unsigned)((C + per_block - 1) / per_block);
+    const bool philox = z_dev == nullptr;
+    const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
+#define CUSMC_GEN_LAUNCH(DD, PH, MO) \
+    mh_general_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga)
+#define CUSMC_GEN_CASE(DD)                                                                           \
+    case DD:                                                                                         \
+        if (philox && moments) CUSMC_GEN_LAUNCH(DD, true, true);                                     \
+        else if (philox) CUSMC_GEN_LAUNCH(DD, true, false);                                          \
+        else if (moments) CUSMC_GEN_LAUNCH(DD, false, true);                                         \
+        else CUSMC_GEN_LAUNCH(DD, false, false);                                                     \
+        break;
+    switch (pad) {
+        CUSMC_GEN_CASE(2)
+        CUSMC_GEN_CASE(4)
+        CUSMC_GEN_CASE(8)
+        CUSMC_GEN_CASE(16)
+        CUSMC_GEN_CASE(32)
+    }
+#undef CUSMC_GEN_LAUNCH
+#undef CUSMC_GEN_CASE
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }

@@ -483,7 +483,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     CUSMC_REQUIRE(ctx, cfg->d <= CUSMC_MAX_DIM && cfg->dy <= CUSMC_MAX_DIM, "d/dy exceed CUSMC_MAX_DIM");
     CUSMC_REQUIRE(ctx, cfg->Y && cfg->m0 && cfg->C0 && cfg->F && cfg->G && cfg->V && cfg->W, "model pointer is NULL");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->kind == CUSMC_MVT, "unknown distribution");
-    CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 2, "unknown resampler");
+    CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 3, "unknown resampler");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold >= 0.0 && cfg->ess_threshold <= 1.0, "ess_threshold must lie in [0, 1]");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold == 0.0 || cfg->resampler == CUSMC_RESAMPLE_SYSTEMATIC,
@@ -491,8 +491,8 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     const int world = cfg->world <= 1 ? 1 : cfg->world;
     CUSMC_REQUIRE(ctx, world <= CUSMC_MAX_PEERS, "world exceeds CUSMC_MAX_PEERS");
     CUSMC_REQUIRE(ctx, world == 1 || (cfg->rank >= 0 && cfg->rank < world), "rank outside 0..world-1");
-    if (world > 1 && cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL)
-        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "the multinomial resampler is single-GPU only");
+    if (world > 1 && (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL || cfg->resampler == CUSMC_RESAMPLE_REJECTION))
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "the multinomial and rejection resamplers are single-GPU only");
     cusmc_filter *f = new (std::nothrow) cusmc_filter();
     if (!f) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "out of host memory");
     f->ctx = ctx;
@@ -525,7 +525,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     if (f->cfg.B <= 0) f->cfg.B = 10;   // the reference hard-codes B = 10 (src/mcmc.cpp:291)
     // Reference mode (metropolis) keeps raw densities as weights like src/mcmc.cpp:212; the
     // normalised resamplers work on log-weights.
-    f->is_log = cfg->resampler == CUSMC_RESAMPLE_METROPOLIS ? 0 : 1;
+    f->is_log = (cfg->resampler == CUSMC_RESAMPLE_METROPOLIS || cfg->resampler == CUSMC_RESAMPLE_REJECTION) ? 0 : 1;
     f->shift = cusmc_fixed_shift(N);
     int rc = eigen_factor(ctx, f->C0.data(), d, f->Qc0);
     if (rc == CUSMC_OK) rc = eigen_factor(ctx, f->W.data(), d, f->Qw);
@@ -704,6 +704,8 @@ int cusmc_filter_init_slots(cusmc_filter *f)
     return CUSMC_OK;
 }
 
+constexpr int kRejectionCap = 4096;      // attempts per particle of the rejection resampler
+
 // Does step t leave its log-weights in f->lw?  Nothing in a fused systematic step reads them (the weight
 // image carries the weights), so they are stored only where somebody needs them: the summary's
 // moment pass, the history, adaptive resampling (weights accumulate), the multinomial search's CDF
@@ -773,7 +775,7 @@ extern "C" int cusmc_filter_begin(cusmc_filter *f, const cusmc_filter_draws *dra
     a.x_new = f->x[0];
     a.x_prev = f->x[1];
     a.xi = f->draws.xi0_dev;
-    a.lw_max = nullptr;
+    a.lw_max = cfg.resampler == CUSMC_RESAMPLE_REJECTION ? &f->slots[0].lw_max : nullptr;   // the largest density
     // "mvt": x_0 = m0 + chi (.) (Q_c0 xi), the reference's initialize() draws from the same distribution
     // object as the transition noise (src/mcmc.cpp:73-79 -> src/statistics.cc.cpp:379-411)
     a.kind = (cfg.kind == CUSMC_MVT && !cfg.mvt_normal_init) ? CUSMC_MVT : CUSMC_MVN;
@@ -908,6 +910,9 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
                                        f->lo, n, sharded ? &f->peer_lw : nullptr);
     }
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) return CUSMC_OK;
+    if (cfg.resampler == CUSMC_RESAMPLE_REJECTION)
+        return cusmc_launch_rejection(ctx, f->anc, f->lw, &f->slots[t - 1].lw_max, cfg.seed, (uint64_t)t, N,
+                                      kRejectionCap);
     // multinomial: materialise the global CDF from the image, one binary search per child
     StepSlot *prev = &f->slots[t - 1];
     CUSMC_CHECK(cusmc_launch_image_cdf(ctx, f->img[(t - 1) & 1], f->img_n, n, f->rank, f->cdf));
@@ -948,6 +953,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
         a.hist_a = f->hist_a + row * n;
     }
     if (f->world > 1) a.x_prev_peer = (const double *const *)f->peer_x[f->cur].table_dev;
+    if (cfg.resampler == CUSMC_RESAMPLE_REJECTION) a.lw_max = &f->slots[t].lw_max;     // the next step's w_max
     if (f->is_log) {
         pffused::FusedArgs fa = filter_fused_args(f, a, t);
         if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
@@ -1232,6 +1238,53 @@ extern "C" int cusmc_filter_get_log_weights(cusmc_filter *f, double *lw)
     CUSMC_REQUIRE(ctx, f->is_log, "the metropolis (reference) mode keeps densities, not log-weights");
     CUSMC_CHECK(filter_run_status(f));
     return cusmc_d2h_staged(ctx, lw, f->hist_w, sizeof(double) * (size_t)f->cfg.T * (size_t)f->n);
+}
+
+// Genealogy: thread i walks the ancestor rows back from the final step.
+__global__ void __launch_bounds__(kThreads)
+lineage_kernel(const uint32_t *__restrict__ hist_a, int T, int64_t n, uint32_t *__restrict__ lineage)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= n) return;
+    uint32_t k = (uint32_t)i;
+    lineage[(size_t)(T - 1) * n + i] = k;
+    for (int t = T - 1; t >= 1; --t) {
+        k = __ldg(hist_a + (size_t)t * n + k);
+        lineage[(size_t)(t - 1) * n + i] = k;
+    }
+}
+
+extern "C" int cusmc_filter_get_lineage(cusmc_filter *f, uint32_t *lineage, int *n_unique)
+{
+    if (!f) return CUSMC_ERR_INVALID;
+    cusmc_ctx *ctx = f->ctx;
+    CUSMC_REQUIRE(ctx, f->ran && f->cfg.keep_history > 0 && lineage, "history was not kept (keep_history = 1)");
+    CUSMC_REQUIRE(ctx, f->world == 1, "the lineage is traced on one GPU");
+    CUSMC_CHECK(filter_run_status(f));
+    const int T = f->cfg.T;
+    const int64_t n = f->n;
+    void *tmp = nullptr;
+    CUSMC_CHECK(cusmc_scratch(ctx, 0, sizeof(uint32_t) * (size_t)T * (size_t)n, &tmp));
+    lineage_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(f->hist_a, T, n, (uint32_t *)tmp);
+    CUSMC_LAUNCHED(ctx);
+    CUSMC_CHECK(cusmc_d2h_staged(ctx, lineage, tmp, sizeof(uint32_t) * (size_t)T * (size_t)n));
+    if (n_unique)                       // rows are non-decreasing in i (ancestors are monotone): count the steps
+        for (int t = 0; t < T; ++t) {
+            const uint32_t *row = lineage + (size_t)t * n;
+            int u = n > 0 ? 1 : 0;
+            bool sorted = true;
+            for (int64_t i = 1; i < n; ++i) {
+                u += row[i] != row[i - 1];
+                sorted = sorted && row[i] >= row[i - 1];
+            }
+            if (!sorted) {              // resamplers without monotone ancestors (metropolis, rejection, multinomial)
+                std::vector<uint32_t> v(row, row + n);
+                std::sort(v.begin(), v.end());
+                u = (int)(std::unique(v.begin(), v.end()) - v.begin());
+            }
+            n_unique[t] = u;
+        }
+    return CUSMC_OK;
 }
 
 extern "C" int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa, double **lw, uint32_t **anc)

@@ -74,6 +74,27 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const 
     a[t] = k;
 }
 
+// Rejection resampler: the unbiased relative of the rule above (no counterpart in the reference; the
+// resampler_f seam of inst/include/types.hpp:32 would register it).  Attempt n consumes the Philox block
+// the Metropolis resampler uses for (seed, step, i, n): its uniform decides, its index is the next proposal.
+__global__ void __launch_bounds__(kThreads)
+rejection_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const double *__restrict__ wmax_p,
+                 uint64_t seed, uint64_t step, int64_t N, int cap)
+{
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= N) return;
+    const double wmax = *wmax_p;
+    uint32_t k = (uint32_t)i;
+    double wk = __ldg(w + i);
+    for (int n = 0; n < cap; ++n) {
+        const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_METROPOLIS, step, (uint64_t)i, (uint32_t)n);
+        if (cusmc_u01(r.v[0], r.v[1]) <= wk / wmax) break;          // NaN (0 / 0) never accepts, as in the reference's rule
+        k = (uint32_t)cusmc_uint_below(r.v[2], r.v[3], (uint64_t)N);
+        wk = __ldg(w + k);
+    }
+    a[i] = k;
+}
+
 // ------------------------------------------------------------------------------------------
 // max and fixed-point sums
 // ------------------------------------------------------------------------------------------
@@ -601,6 +622,15 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
     return CUSMC_OK;
 }
 
+int cusmc_launch_rejection(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *wmax_dev, uint64_t seed,
+                           uint64_t step, int64_t N, int cap)
+{
+    if (N == 0) return CUSMC_OK;
+    rejection_kernel<<<(unsigned)((N + kThreads - 1) / kThreads), kThreads, 0, ctx->stream>>>(a, w, wmax_dev, seed, step, N, cap);
+    CUSMC_LAUNCHED(ctx);
+    return CUSMC_OK;
+}
+
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev)
 {
     if (N == 0) return CUSMC_OK;
@@ -723,6 +753,16 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
     CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
     return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr);
+}
+
+extern "C" int cusmc_rejection_resample_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev,
+                                            const double *w_max_dev, uint64_t seed, uint64_t step, int64_t N, int cap)
+{
+    CUSMC_ENTER(ctx);
+    CUSMC_REQUIRE(ctx, N >= 0 && cap >= 1, "N >= 0 and cap >= 1 required");
+    CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev && w_max_dev), "NULL pointer");
+    CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
+    return cusmc_launch_rejection(ctx, a_dev, w_dev, w_max_dev, seed, step, N, cap);
 }
 
 extern "C" int cusmc_weights_max_dev(cusmc_ctx *ctx, const double *w_dev, int64_t N, double *max_dev)

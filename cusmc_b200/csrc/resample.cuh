@@ -9,6 +9,8 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
                             int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers);
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
+int cusmc_launch_rejection(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *wmax_dev, uint64_t seed,
+                           uint64_t step, int64_t N, int cap);
 // image: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the weight image
 // (exclusive tile prefixes + tile-local CDF) the resampling pass consumes.  stats_dev may be NULL.
 // next: when given, the one-block tile scan also leaves the constants of the systematic resampling

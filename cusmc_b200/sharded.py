@@ -140,8 +140,8 @@ class ShardedParticleFilter:
         self.ctx, self.group = ctx, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.plan = ShardPlan(N, self.world, self.rank)
-        if kw.get("resampler", "metropolis") == "multinomial" and self.world > 1:
-            raise ValueError("the multinomial resampler is single-GPU only")
+        if kw.get("resampler", "metropolis") in ("multinomial", "rejection") and self.world > 1:
+            raise ValueError("the multinomial and rejection resamplers are single-GPU only")
         ctx.use_torch_stream()
         exchange_timeout = kw.pop("exchange_timeout", None)
         self.pf = ParticleFilter(ctx, N, Y, m0, C0, F, G, V, W, rank=self.rank, world=self.world, **kw)
@@ -150,7 +150,7 @@ class ShardedParticleFilter:
             exchange_timeout = 2.0 if torch.cuda.device_count() >= self.world else 10.0
         ctx._check(ctx.lib.cusmc_filter_set_exchange_timeout(self.pf.h, float(exchange_timeout)))
         self.T, self.d, self.N = self.pf.T, self.pf.d, int(N)
-        self.is_log = kw.get("resampler", "metropolis") != "metropolis"
+        self.is_log = kw.get("resampler", "metropolis") not in ("metropolis", "rejection")
         self.summary_on = bool(kw.get("summary", True))
         lib, h = ctx.lib, self.pf.h
         if self.world > 1:

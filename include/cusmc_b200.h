@@ -53,7 +53,8 @@ enum cusmc_layout { CUSMC_SOA = 0, CUSMC_AOS = 1 };
 enum cusmc_resampler {                                    /* Resamplers[...], src/mcmc.cpp:252-255 */
     CUSMC_RESAMPLE_METROPOLIS = 0,   /* the reference's only resampler */
     CUSMC_RESAMPLE_SYSTEMATIC = 1,
-    CUSMC_RESAMPLE_MULTINOMIAL = 2
+    CUSMC_RESAMPLE_MULTINOMIAL = 2,
+    CUSMC_RESAMPLE_REJECTION = 3     /* unbiased relative of the reference's resampler: see cusmc_rejection_resample_dev */
 };
 
 #define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
@@ -154,6 +155,16 @@ int cusmc_metropolis_hastings(cusmc_ctx *ctx, uint32_t *a, const double *w,
 int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev,
                                   const double *u_dev, const uint32_t *j_dev,
                                   uint64_t seed, uint64_t step, int64_t N, int B, int is_log);
+/*
+ * Rejection resampler (Murray, Lee & Jacob 2016, the unbiased relative of the reference's B-step
+ * Metropolis rule, same `resampler_f` seam, inst/include/types.hpp:32): for each i, k = i; attempt n =
+ * 0, 1, ...: accept k if u_n <= w[k] / w_max, else k = j_n.  (u_n, j_n) is the Philox draw the Metropolis
+ * resampler would use for (seed, step, i, n), so a host reproduces every ancestor.  w_max_dev: the
+ * largest weight (device).  Attempts are capped at `cap` (the current k is kept: a bias of at most
+ * (1 - mean w / w_max)^cap).  a_dev receives N ancestors.
+ */
+int cusmc_rejection_resample_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev, const double *w_max_dev,
+                                 uint64_t seed, uint64_t step, int64_t N, int cap);
 /*
  * Fused propagate + reweight (src/mcmc.cpp:90-160 + :162-237), SoA in and out:
  *   x_new[:, i] = G x_prev[:, a[i]] + noise_i,   noise = Q xi (mvn) | chi (.) (Q xi) (mvt)
@@ -262,6 +273,21 @@ int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps,
                         const double *z_dev, const double *thr_dev, uint64_t seed,
                         uint32_t *n_accept_dev, uint8_t *accept_bits_dev,
                         double *sum_x_dev, double *sum_xx_dev);
+
+/*
+ * The same chains with a proposal that does NOT use the target's factor:  x' = x + step_size * scale (.) z
+ * (scale_dev: d per-component factors shared by all chains, or NULL = isotropic).  Nothing cancels, so
+ * every step evaluates the target density in the kernel: r = x' - mu, v = L^-1 r by forward substitution
+ * (the chain's factor stays in registers for the whole run), q' = |v|^2, and the accept rule above on
+ * (q', q) -- proposal, acceptance ratio and accept / reject fused with the density evaluation
+ * (src/statistics.cc.cpp:295-311 under the rule of src/samplers.cpp:30).  Other arguments as above.
+ */
+int cusmc_mh_chains_general_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps,
+                                double step_size, const double *scale_dev, double nu, int shared,
+                                const double *mu_dev, const double *L_dev, double *x_dev,
+                                const double *z_dev, const double *thr_dev, uint64_t seed,
+                                uint32_t *n_accept_dev, uint8_t *accept_bits_dev,
+                                double *sum_x_dev, double *sum_xx_dev);
 
 /* ---- the filter (a7): particle_filter() / MCMC() -------------------------------- */
 /*
@@ -409,6 +435,11 @@ int cusmc_filter_get_resampled(cusmc_filter *f, int *resampled);
  * (exactly what resampling consumed; row 0 is 0).  n = this rank's shard (N on one GPU). */
 int cusmc_filter_get_history(cusmc_filter *f, double *x_aos, double *w, uint32_t *a);
 int cusmc_filter_get_log_weights(cusmc_filter *f, double *lw);
+/* The ancestor tree as paths (needs keep_history = 1, one GPU): lineage[t][i] = index at step t of the
+ * ancestor of FINAL particle i (lineage[T-1][i] = i, lineage[t-1][i] = a_t[lineage[t][i]]), traced on
+ * the device; n_unique[t] (optional, T ints) = distinct ancestors alive at step t -- the coalescence
+ * profile of the genealogy.  x_aos[t][lineage[t][i]] is then the trajectory of particle i. */
+int cusmc_filter_get_lineage(cusmc_filter *f, uint32_t *lineage, int *n_unique);
 /* Device time of the last run's step loop (t = 1 .. T-1), ms, from CUDA events on the stream. */
 double cusmc_filter_last_ms(const cusmc_filter *f);
 /* Current device-resident state: x (SoA [d][N]), weights (N), ancestors of the last step (N). */

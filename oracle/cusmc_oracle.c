@@ -719,6 +719,12 @@ int orc_resample_multinomial(const double *w, int64_t N, const double *u, uint32
     return 0;
 }
 
+/* Rejection resampler (extended; the unbiased relative of ref: src/samplers.cpp:21-35): k = i; attempt
+ * n = 0, 1, ...: accept k if u_n <= w[k] / wmax, else k = j_n, with (u_n, j_n) the counter-based draw
+ * the Metropolis resampler uses for (seed, step, i, n).  Capped at `cap` attempts. */
+void orc_resample_rejection(uint32_t *a, const double *w, double wmax, int64_t N, uint64_t seed,
+                            uint64_t step, int cap);
+
 /* ---- independent MH chains -------------------------------------------------- */
 static double whiten_q(const double *L, const double *rinv, const double *r, double *v, int d)
 {
@@ -804,6 +810,63 @@ void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu
             if (n_accept) n_accept[c] = nacc;
         }
         free(r);
+    }
+}
+
+/* Random-walk MH whose proposal does not use the target's factor: x' = x + step * scale (.) z.  Every
+ * step evaluates the target's quadratic form q' = |L^-1 (x' - mu)|^2 by forward substitution (whiten_q:
+ * row k accumulates j ascending with fma, v_k = acc * (1 / L_kk), q accumulates k ascending) -- the
+ * density arithmetic of ref: src/statistics.cc.cpp:295-311 in whitened form -- and applies the accept
+ * rule of orc_mh_chains (ref: src/samplers.cpp:30 on the density ratio).  No counterpart in the
+ * reference; defines what mh_general_kernel reproduces bit for bit. */
+void orc_mh_chains_general(int dist, int64_t C, int d, int steps, double step, const double *scale, double nu,
+                           int shared, const double *mu, const double *L, const double *x0, const double *z,
+                           const double *thr, double *x_final, uint32_t *n_accept, uint8_t *accept_bits)
+{
+    double inv_nu = dist == 1 ? 1.0 / nu : 0.0;
+#pragma omp parallel
+    {
+        double *buf = (double *)malloc(sizeof(double) * d * 5);
+        double *r = buf, *v = buf + d, *rinv = buf + 2 * d, *x = buf + 3 * d, *xp = buf + 4 * d;
+#pragma omp for schedule(static)
+        for (int64_t c = 0; c < C; ++c) {
+            const double *Lc = shared ? L : L + (size_t)c * d * d;
+            const double *mc = shared ? mu : mu + (size_t)c * d;
+            for (int k = 0; k < d; ++k) {
+                rinv[k] = 1.0 / A_(Lc, k, k, d);
+                x[k] = x0[(size_t)c * d + k];
+                r[k] = x[k] - mc[k];
+            }
+            double q = whiten_q(Lc, rinv, r, v, d);
+            uint32_t nacc = 0;
+            for (int s = 0; s < steps; ++s) {
+                const double *zs = z + ((size_t)c * steps + s) * d;
+                for (int k = 0; k < d; ++k) {
+                    double sk = step * (scale ? scale[k] : 1.0);
+                    xp[k] = fma(sk, zs[k], x[k]);
+                    r[k] = xp[k] - mc[k];
+                }
+                double qp = whiten_q(Lc, rinv, r, v, d);
+                double th = thr[(size_t)c * steps + s];
+                int acc_flag;
+                if (dist == 0) {
+                    acc_flag = 0.5 * (qp - q) < th;
+                } else {
+                    double tp = fma(qp, inv_nu, 1.0);
+                    double tc = fma(q, inv_nu, 1.0);
+                    acc_flag = tp < th * tc;
+                }
+                if (acc_flag) {
+                    memcpy(x, xp, sizeof(double) * d);
+                    q = qp;
+                    ++nacc;
+                }
+                if (accept_bits) accept_bits[(size_t)c * steps + s] = (uint8_t)acc_flag;
+            }
+            memcpy(x_final + (size_t)c * d, x, sizeof(double) * d);
+            if (n_accept) n_accept[c] = nacc;
+        }
+        free(buf);
     }
 }
 
@@ -1015,6 +1078,25 @@ void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, 
         }
 }
 
+void orc_resample_rejection(uint32_t *a, const double *w, double wmax, int64_t N, uint64_t seed,
+                            uint64_t step, int cap)
+{
+#pragma omp parallel for schedule(dynamic, 256)
+    for (int64_t i = 0; i < N; ++i) {
+        uint32_t k = (uint32_t)i;
+        double wk = w[i];
+        for (int n = 0; n < cap; ++n) {
+            double u;
+            uint32_t j;
+            orc_rng_metropolis(seed, step, (uint64_t)i, (uint32_t)n, (uint64_t)N, &u, &j);
+            if (u <= wk / wmax) break;
+            k = j;
+            wk = w[k];
+        }
+        a[i] = k;
+    }
+}
+
 static uint64_t fixed_from_unit(double wn, int shift)
 {
     if (!(wn > 0.0)) return 0;
@@ -1089,7 +1171,7 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
     if (tile <= 0) tile = 2048;       /* the library's tile (kTile); the persistent kernel passes its own */
     size_t Nd = (size_t)N * d;
     double *w_old = (double *)malloc(sizeof(double) * N);
-    int is_log = resampler != 0;
+    int is_log = resampler != 0 && resampler != 3;
     double *xa = (double *)malloc(sizeof(double) * Nd), *xb = (double *)malloc(sizeof(double) * Nd);
     double *w = (double *)malloc(sizeof(double) * N), *noise = (double *)malloc(sizeof(double) * Nd);
     uint32_t *a = (uint32_t *)malloc(sizeof(uint32_t) * N);
@@ -1126,6 +1208,10 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
                             orc_rng_metropolis(seed, (uint64_t)t, (uint64_t)i, (uint32_t)n, (uint64_t)N,
                                                &ub[(size_t)i * B + n], &jb[(size_t)i * B + n]);
                 orc_metropolis_hastings(a, w, ut, jt, N, B);
+            } else if (resampler == 3) {
+                double m = -INFINITY;           /* the kernels' atomic max over finite weights */
+                for (int64_t i = 0; i < N; ++i) if (w[i] == w[i] && w[i] < INFINITY && w[i] > m) m = w[i];
+                orc_resample_rejection(a, w, m, N, seed, (uint64_t)t, 4096);
             } else {
                 /* weights of step t-1: the block-relative fixed-point image, integer CDF */
                 uint64_t run2 = 0;

@@ -155,6 +155,11 @@ int orc_resample_systematic(const double *w, int64_t N, double u0, uint32_t *a);
 /* Multinomial: p_i = min((uint64)(u[i] * (double)T), T-1), a[i] = #{ j : C_j <= p_i }. */
 int orc_resample_multinomial(const double *w, int64_t N, const double *u, uint32_t *a);
 
+/* Rejection resampler: k = i; attempt n: accept k if u_n <= w[k] / wmax, else k = j_n; (u_n, j_n) = the
+ * counter-based draw of (seed, step, i, n) (orc_rng_metropolis); at most `cap` attempts. */
+void orc_resample_rejection(uint32_t *a, const double *w, double wmax, int64_t N, uint64_t seed,
+                            uint64_t step, int cap);
+
 /* Independent random-walk Metropolis-Hastings chains.
  * Chain c (AoS): state x_c (d), target dist (0 mvn / 1 mvt) with location mu_c
  * and lower Cholesky factor L_c (column-major d x d; strict upper ignored),
@@ -171,6 +176,12 @@ void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu
                    const double *x0, const double *z, const double *thr,
                    double *x_final, uint32_t *n_accept, uint8_t *accept_bits);
 
+
+/* The same chains with the proposal x' = x + step * scale (.) z (scale: d factors or NULL): every step
+ * evaluates q' = |L^-1 (x' - mu)|^2 by forward substitution (definition in the .c). */
+void orc_mh_chains_general(int dist, int64_t C, int d, int steps, double step, const double *scale, double nu,
+                           int shared, const double *mu, const double *L, const double *x0, const double *z,
+                           const double *thr, double *x_final, uint32_t *n_accept, uint8_t *accept_bits);
 
 /* ---- production-order ("det") restatements: same operation order as the kernels, so the
  * comparison is bit-for-bit (MVN; the MVT epilogue uses libm log1p and is compared to 1e-12). */
@@ -199,7 +210,8 @@ void orc_rng_metropolis(uint64_t seed, uint64_t step, uint64_t index, uint32_t n
 /* Fills xi (AoS N x d) with the normals the step kernel draws for (seed, stream, step). */
 void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, int64_t N, int d, double *xi);
 /* Whole filter in production order.  resampler: 0 metropolis (linear weights, as the
- * reference), 1 systematic, 2 multinomial (log weights, max-shifted fixed point).  Draw arrays may
+ * reference), 1 systematic, 2 multinomial (log weights, block-relative fixed point), 3 rejection (linear
+ * weights, device-drawn only).  Draw arrays may
  * be NULL -> Philox mirror with `seed`.  Layouts as orc_filter_metropolis; u0 [(T-1)], um [(T-1)*N].
  * tile: tile size of the weight image (<= 0: 2048, the library's; the persistent kernel uses its own).
  * Outputs optional: x_hist [T*N*d], w_hist [T*N], a_hist [T*N], ess [T], loglik [T]. */

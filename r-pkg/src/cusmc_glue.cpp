@@ -203,6 +203,7 @@ Rcpp::List run(unsigned N, unsigned d, unsigned timeSteps, Rcpp::NumericMatrix Y
     if (resampler == "metropolis") cfg.resampler = CUSMC_RESAMPLE_METROPOLIS;
     else if (resampler == "systematic") cfg.resampler = CUSMC_RESAMPLE_SYSTEMATIC;
     else if (resampler == "multinomial") cfg.resampler = CUSMC_RESAMPLE_MULTINOMIAL;
+    else if (resampler == "rejection") cfg.resampler = CUSMC_RESAMPLE_REJECTION;
     else Rcpp::stop("CuSMC: unknown resampler '%s'", resampler.c_str());
     cfg.B = 10;                                   // ref: src/mcmc.cpp:252-255
     cfg.nu = df;

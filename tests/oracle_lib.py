@@ -105,6 +105,11 @@ class Oracle:
         L.orc_mh_chains.restype = None
         L.orc_mh_chains.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, C.c_double,
                                     C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _u32p, _u8p]
+        L.orc_resample_rejection.restype = None
+        L.orc_resample_rejection.argtypes = [_u32p, _dp, C.c_double, C.c_int64, C.c_uint64, C.c_uint64, C.c_int]
+        L.orc_mh_chains_general.restype = None
+        L.orc_mh_chains_general.argtypes = [C.c_int, C.c_int64, C.c_int, C.c_int, C.c_double, _dp, C.c_double,
+                                            C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _u32p, _u8p]
         L.orc_num_threads.restype = C.c_int
         L.orc_observation_operator.restype = C.c_int
         L.orc_observation_operator.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _dp, C.c_float, _dp, _dp, _dp]
@@ -218,6 +223,12 @@ class Oracle:
         rc = self.lib.orc_resample_multinomial(_p(w), w.size, _p(u), _p(a, _u32p))
         return a, rc
 
+    def resample_rejection(self, w, wmax, seed, step, cap=4096):
+        w = f64(w)
+        a = np.empty(w.size, dtype=np.uint32)
+        self.lib.orc_resample_rejection(_p(a, _u32p), _p(w), float(wmax), w.size, int(seed), int(step), int(cap))
+        return a
+
     def fixed_shift(self, n_global):
         return self.lib.orc_fixed_shift(int(n_global))
 
@@ -327,6 +338,21 @@ class Oracle:
                                _p(xf), _p(nacc, _u32p), _p(bits, _u8p))
         return xf, nacc, bits
 
+    def mh_chains_general(self, dist, mu, L, x0, z, thr, step, nu=0.0, shared=False, scale=None, want_bits=True):
+        """Isotropic / per-component-scaled random walk: every step evaluates the target density."""
+        x0, z, thr = f64(x0), f64(z), f64(thr)
+        Cn, d = x0.shape
+        steps = z.shape[1]
+        Lf = colmajor(L) if shared else f64(np.transpose(np.asarray(L), (0, 2, 1)))
+        sc = None if scale is None else f64(scale)
+        xf = np.empty((Cn, d))
+        nacc = np.empty(Cn, dtype=np.uint32)
+        bits = np.empty((Cn, steps), dtype=np.uint8) if want_bits else None
+        self.lib.orc_mh_chains_general(0 if dist == "mvn" else 1, Cn, d, steps, float(step), _p(sc), float(nu),
+                                       int(shared), _p(f64(mu)), _p(Lf), _p(x0), _p(z), _p(thr), _p(xf),
+                                       _p(nacc, _u32p), _p(bits, _u8p))
+        return xf, nacc, bits
+
     # ---- production-order restatements --------------------------------------------
     def observation_operator(self, dist, F, V, nu=0.0):
         F = np.asarray(F, dtype=np.float64)
@@ -401,7 +427,7 @@ class Oracle:
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
         d = np.asarray(G).shape[0]
-        rs = {"metropolis": 0, "systematic": 1, "multinomial": 2}[resampler]
+        rs = {"metropolis": 0, "systematic": 1, "multinomial": 2, "rejection": 3}[resampler]
         opt = lambda a: None if a is None else f64(a)
         j_ = None if j is None else np.ascontiguousarray(j, dtype=np.uint32)
         xh = np.zeros((T, N, d))

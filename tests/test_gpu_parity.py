@@ -632,6 +632,68 @@ def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
         ctx.filter(N=N, Y=Y, resampler="multinomial", ess_threshold=thr, **md)
 
 
+def test_rejection_resampler(ctx, orc):
+    """The rejection resampler (N4): bit-exact against the oracle's mirror of the same counter-based
+    draws, unbiased offspring counts (its point over the B-step Metropolis rule), and a whole filter run
+    bit for bit."""
+    import torch
+    rng = np.random.default_rng(606)
+    N = 50000
+    w = rng.random(N) ** 4
+    w[rng.random(N) < 0.05] = 0.0
+    wd = torch_dev(w)
+    wmax = torch_dev(np.array([w.max()]))
+    a = torch.empty(N, dtype=torch.int32, device="cuda")
+    ctx.rejection_resample_dev(a, wd, wmax, seed=11, step=3)
+    ctx.synchronize()
+    got = a.cpu().numpy().view(np.uint32)
+    assert np.array_equal(got, orc.resample_rejection(w, w.max(), 11, 3))
+    # offspring counts: E[#children of j] = N w_j / sum(w), checked on coarse bins (exact in law)
+    bins = np.add.reduceat(np.bincount(got, minlength=N), np.arange(0, N, 500))
+    want = N * np.add.reduceat(w, np.arange(0, N, 500)) / w.sum()
+    assert np.all(np.abs(bins - want) < 6 * np.sqrt(want + 1) + 3)
+    assert np.all(w[got] > 0)                              # nobody descends from a zero-weight particle
+    # inside the filter (reference-mode densities, device-drawn everything)
+    d, Nf, T = 2, 4000, 8
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=Nf, Y=Y, resampler="rejection", seed=21, keep_history=True, reproducible_rng=True, **md)
+    h = pf.run().history()
+    lin, nuq = pf.lineage()
+    pf.close()
+    ref = orc.filter_det("mvn", "rejection", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), Nf, seed=21)
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+    assert relerr(h["w"], ref["w"]) < 1e-13
+    # the ancestor tree as paths: lineage[t - 1] = a_t[lineage[t]], and the genealogy coalesces backwards
+    want_lin = np.empty((T, Nf), dtype=np.uint32)
+    want_lin[T - 1] = np.arange(Nf)
+    for t in range(T - 1, 0, -1):
+        want_lin[t - 1] = h["a"][t][want_lin[t]]
+    assert np.array_equal(lin, want_lin)
+    assert np.array_equal(nuq, [len(np.unique(r)) for r in want_lin])
+    assert np.all(np.diff(nuq) >= 0) and nuq[-1] == Nf and nuq[0] < Nf
+
+
+def test_lineage_of_a_systematic_run(ctx):
+    d, N, T = 2, 20000, 12
+    rng = np.random.default_rng(5)
+    md = _model(d)
+    pf = ctx.filter(N=N, Y=rng.standard_normal((d, T)), resampler="systematic", seed=4, keep_history=True, **md)
+    h = pf.run().history()
+    lin, nuq = pf.lineage()
+    pf.close()
+    k = np.arange(N)
+    for t in range(T - 1, 0, -1):
+        assert np.array_equal(lin[t], k)
+        k = h["a"][t][k]
+    assert np.array_equal(lin[0], k)
+    assert nuq[-1] == N and np.all(np.diff(nuq) >= 0) and nuq[0] < N // 2
+    traj = h["x"][np.arange(T)[:, None], lin]             # (T, N, d): the path of every final particle
+    assert traj.shape == (T, N, d) and np.array_equal(traj[-1], h["x"][-1])
+
+
 def kalman_means(Y, m0, C0, F, G, V, W):
     m, P = m0.copy(), C0.copy()
     out = [m.copy()]
@@ -829,6 +891,85 @@ def test_mh_chains_device_rng_matches_oracle_mirror(ctx, orc, kind, nu, d):
     assert np.array_equal(bits.cpu().numpy(), want_bits)
     assert np.array_equal(x.cpu().numpy(), want_x)
     assert 0.05 < want_bits.mean() < 0.99
+
+
+@pytest.mark.parametrize("kind,nu,d,shared,Cn,steps", [("mvn", 0.0, 2, False, 257, 40), ("mvt", 5.0, 8, True, 257, 40),
+                                                       ("mvn", 0.0, 17, False, 100, 40),
+                                                       ("mvt", 5.0, 32, False, 1024, 100)])     # C3's shape, 1024 x 100
+def test_mh_chains_general_proposal_bit_exact(ctx, orc, kind, nu, d, shared, Cn, steps):
+    """The random walk whose proposal does not use the target's factor (x' = x + s z, optionally scaled per
+    component): every step evaluates the target density in the kernel.  Same pre-drawn normals and
+    thresholds on both sides: accept / reject decisions and final states bit for bit."""
+    import torch
+    rng = np.random.default_rng(1900 + d)
+    step = 0.9 / math.sqrt(d)
+    if shared:
+        L, mu = np.linalg.cholesky(spd(rng, d)), rng.standard_normal(d)
+        Ldev, mudev = torch_dev(L.T), torch_dev(mu)              # column-major
+    else:
+        L = np.stack([np.linalg.cholesky(spd(rng, d)) for _ in range(Cn)])
+        mu = rng.standard_normal((Cn, d))
+        Ldev, mudev = torch_dev(L.transpose(0, 2, 1)), torch_dev(mu)
+    scale = None if d == 32 else 0.5 + rng.random(d)
+    x0 = mu + rng.standard_normal((Cn, d))
+    z = rng.standard_normal((Cn, steps, d))
+    e = -np.log(rng.random((Cn, steps)))
+    thr = e if kind == "mvn" else np.exp(2 * e / (nu + d))
+    want_x, want_n, want_bits = orc.mh_chains_general(kind, mu, L, x0, z, thr, step, nu=nu, shared=shared, scale=scale)
+    x = torch_dev(x0)
+    nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+    bits = torch.zeros((Cn, steps), dtype=torch.uint8, device="cuda")
+    ctx.mh_chains_general_dev(kind, mudev, Ldev, x, steps, step, nu=nu, shared=shared,
+                              scale=None if scale is None else torch_dev(scale), z=torch_dev(z), thr=torch_dev(thr),
+                              n_accept=nacc, accept_bits=bits)
+    ctx.synchronize()
+    assert np.array_equal(bits.cpu().numpy(), want_bits)          # accept / reject decisions
+    assert np.array_equal(nacc.cpu().numpy().astype(np.uint32), want_n)
+    assert np.array_equal(x.cpu().numpy(), want_x)
+    assert 0.05 < want_bits.mean() < 0.95
+
+
+def test_mh_chains_general_device_rng(ctx, orc):
+    """Device-drawn general chains: the oracle regenerates the kernel's Philox draws (bit-exact decisions),
+    and the chains' time-averaged moments match the MVN target's."""
+    import torch
+    rng = np.random.default_rng(4242)
+    d, Cn, steps, seed = 5, 48, 70, 313
+    L = np.stack([np.linalg.cholesky(spd(rng, d)) for _ in range(Cn)])
+    mu = rng.standard_normal((Cn, d))
+    x0 = mu + rng.standard_normal((Cn, d))
+    z = np.stack([orc.rng_fill_normals(seed, 4, s, 0, Cn, d) for s in range(steps)], axis=1)   # CHAIN_Z
+    thr = np.empty((Cn, steps))
+    for c in range(Cn):
+        for s in range(steps):
+            thr[c, s] = -float(orc.det_log(orc.rng_u01(seed, 5, s, c) + 2.0 ** -53)[0])       # CHAIN_U, (0, 1]
+    want_x, _, want_bits = orc.mh_chains_general("mvn", mu, L, x0, z, thr, 0.5, shared=False)
+    x = torch_dev(x0)
+    bits = torch.zeros((Cn, steps), dtype=torch.uint8, device="cuda")
+    ctx.mh_chains_general_dev("mvn", torch_dev(mu), torch_dev(L.transpose(0, 2, 1)), x, steps, 0.5, seed=seed,
+                              accept_bits=bits)
+    ctx.synchronize()
+    assert np.array_equal(bits.cpu().numpy(), want_bits)
+    assert np.array_equal(x.cpu().numpy(), want_x)
+    # the law: many chains on one MVN target, running sums of x and x^2
+    d, Cn, steps = 4, 4096, 3000
+    S = spd(rng, d)
+    Ls, mus = np.linalg.cholesky(S), rng.standard_normal(d)
+    x = torch_dev(np.tile(mus, (Cn, 1)))
+    sx = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+    sxx = torch.zeros_like(sx)
+    nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+    ctx.mh_chains_general_dev("mvn", torch_dev(mus), torch_dev(Ls.T), x, steps, 1.1, shared=True, seed=78, n_accept=nacc,
+                              sum_x=sx, sum_xx=sxx)
+    ctx.synchronize()
+    mean = sx.cpu().numpy().mean(0) / steps
+    var = sxx.cpu().numpy().mean(0) / steps - mean ** 2
+    acc = nacc.cpu().numpy().mean() / steps
+    assert 0.15 < acc < 0.6
+    # ~Cn * steps / (integrated autocorrelation ~ 40) effective draws; the start at the mode adds O(1 / steps) bias
+    tol = 6 * np.sqrt(np.diag(S) * 40 / (Cn * steps))
+    assert np.all(np.abs(mean - mus) < tol)
+    assert np.all(np.abs(var / np.diag(S) - 1.0) < 0.05)
 
 
 def test_mh_chains_device_rng_moments(ctx):

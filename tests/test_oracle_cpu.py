@@ -324,3 +324,26 @@ def test_mh_chains_oracle_targets_the_right_law(orc, kind, nu):
     xa, na, _ = orc.mh_chains(kind, mu, L, x0, z[:, :5], np.full((Cn, 5), np.inf), 1.0, nu=nu, shared=True)
     xn, nn, _ = orc.mh_chains(kind, mu, L, x0, z[:, :5], np.full((Cn, 5), -np.inf), 1.0, nu=nu, shared=True)
     assert np.all(na == 5) and np.all(nn == 0) and np.array_equal(xn, x0)
+
+
+def test_mh_chains_general_oracle_targets_the_right_law(orc):
+    """The general random walk (proposal independent of the target's factor) keeps the MVT target
+    invariant: the q of draws from the chains follows d * F(d, nu)."""
+    import scipy.stats as st
+    rng = np.random.default_rng(14)
+    d, Cn, steps, nu = 3, 600, 1500, 6.0
+    S = spd(rng, d)
+    L, mu = np.linalg.cholesky(S), rng.standard_normal(d)
+    x0 = mu + rng.standard_normal((Cn, d)) @ L.T
+    z = rng.standard_normal((Cn, steps, d))
+    e = -np.log(rng.random((Cn, steps)))
+    thr = np.exp(2 * e / (nu + d))
+    xf, nacc, bits = orc.mh_chains_general("mvt", mu, L, x0, z, thr, 0.9, nu=nu, shared=True)
+    assert 0.2 < bits.mean() < 0.7
+    v = np.linalg.solve(L, (xf - mu).T).T
+    q = (v * v).sum(1)
+    assert st.kstest(q / d, st.f(d, nu).cdf).pvalue > 1e-3
+    # scaled proposal: same law
+    xf2, _, _ = orc.mh_chains_general("mvt", mu, L, x0, z, thr, 0.9, nu=nu, shared=True, scale=np.array([0.5, 1.0, 1.5]))
+    v = np.linalg.solve(L, (xf2 - mu).T).T
+    assert st.kstest((v * v).sum(1) / d, st.f(d, nu).cdf).pvalue > 1e-3
