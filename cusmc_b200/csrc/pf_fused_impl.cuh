@@ -149,24 +149,28 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
             if (rk != (uint32_t)fa.s.rank) img = fa.img_prev_peer[rk];
         }
         const unsigned long long *fld = img + kConstWords + lt;
+        // the tile's three fields AND this thread's CDF words go out together: the words' address does not
+        // depend on the fields, and a tile on the walk is (almost) always needed -- one round trip per tile
+        // instead of two dependent ones
+        const unsigned long long *cp = img + fa.img_hdr_words + (size_t)lt * kTile + kItems * tid;
+        unsigned long long c[kItems];
+        static_assert(kItems == 8, "two 256-bit loads per thread");
+        if (COH) {
+            ldcg256u(cp, c[0], c[1], c[2], c[3]);
+            ldcg256u(cp + 4, c[4], c[5], c[6], c[7]);
+        } else {
+            ldg256u(cp, c[0], c[1], c[2], c[3]);
+            ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
+        }
+        const unsigned long long c_left = (lane == 0 && tid != 0) ? ld_word<COH>(cp - 1) : 0ull;
         const uint64_t F = ld_word<COH>(fld + (size_t)kTileF * fa.tiles_alloc),
                        P = sc.rank_off[rk] + ld_word<COH>(fld + (size_t)kTileP * fa.tiles_alloc),
                        Sp = ld_word<COH>(fld + (size_t)kTileSp * fa.tiles_alloc);
         const uint64_t Chi = P + Sp;                           // CDF at the end of this parent tile
         if (Sp != 0 && Chi > Qa) {
-            const unsigned long long *cp = img + fa.img_hdr_words + (size_t)lt * kTile + kItems * tid;
-            unsigned long long c[kItems];
-            static_assert(kItems == 8, "two 256-bit loads per thread");
-            if (COH) {
-                ldcg256u(cp, c[0], c[1], c[2], c[3]);
-                ldcg256u(cp + 4, c[4], c[5], c[6], c[7]);
-            } else {
-                ldg256u(cp, c[0], c[1], c[2], c[3]);
-                ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
-            }
             const uint64_t C_last = P + cusmc_mulshift62(c[kItems - 1], F);
             uint64_t C_prev = __shfl_up_sync(0xffffffffu, C_last, 1);
-            if (lane == 0) C_prev = tid == 0 ? P : P + cusmc_mulshift62(ld_word<COH>(cp - 1), F);
+            if (lane == 0) C_prev = tid == 0 ? P : P + cusmc_mulshift62(c_left, F);
             // my parents matter iff their CDF span (C_prev, C_last] is non-empty, starts at or before the
             // last child and ends past the first
             if (C_last != C_prev && C_prev <= Qb && C_last > Qa) {
@@ -273,7 +277,7 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
     auto child = [&](uint32_t j, uint32_t parent, const double *src, const double *xp_in) {
         const int64_t i = (int64_t)j0 + j;
         cusmc_u32x4 r0{};
-        if (PHILOX) r0 = cusmc_rng(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
+        if (PHILOX) r0 = pfstep::step_rng<FAST>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
         double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0, xp_in);
         if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
         if (a.lw) st_stream(a.lw + i, lw);

@@ -31,13 +31,13 @@ typedef struct cusmc_u32x4 {
     uint32_t v[4];
 } cusmc_u32x4;
 
-CUSMC_HD cusmc_u32x4 cusmc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                         uint32_t k0, uint32_t k1)
+CUSMC_HD cusmc_u32x4 cusmc_philox4x32_rounds(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                             uint32_t k0, uint32_t k1, int rounds)
 {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-    for (int round = 0; round < 10; ++round) {
+    for (int round = 0; round < rounds; ++round) {
         const uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         const uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -57,10 +57,26 @@ CUSMC_HD cusmc_u32x4 cusmc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, 
     return out;
 }
 
+CUSMC_HD cusmc_u32x4 cusmc_philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                         uint32_t k0, uint32_t k1)
+{
+    return cusmc_philox4x32_rounds(c0, c1, c2, c3, k0, k1, 10);
+}
+
 CUSMC_HD cusmc_u32x4 cusmc_rng(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub)
 {
     return cusmc_philox4x32_10((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)step,
                                (uint32_t)stream | (sub << 8), (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+
+/* The same counter / key layout with 7 rounds: Philox4x32-7, the shortest variant Salmon et al. report
+ * as passing BigCrush (10 rounds is their recommended safety margin, used everywhere a host may have
+ * to reproduce the draws).  Only the throughput noise path uses it (cusmc_filter_config.reproducible_rng
+ * = 0), where the 3 rounds are 22 of a d = 8 particle-step's ~440 instructions per block. */
+CUSMC_HD cusmc_u32x4 cusmc_rng7(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub)
+{
+    return cusmc_philox4x32_rounds((uint32_t)index, (uint32_t)(index >> 32), (uint32_t)step,
+                                   (uint32_t)stream | (sub << 8), (uint32_t)seed, (uint32_t)(seed >> 32), 7);
 }
 
 /* 53-bit uniform in [0, 1). */
