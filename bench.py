@@ -311,7 +311,7 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
                 continue
             x0 = x.clone()
             run = (lambda st, sd: ctx.mh_chains_dev("mvt", mu, Lcm, x0, st, 0.3, nu=5.0, seed=sd, n_accept=nacc)) if not kw \
-                else (lambda st, sd: ctx.mh_chains_general_dev("mvt", mu, Lcm, x0, st, 0.3 / math.sqrt(d), nu=5.0, seed=sd,
+                else (lambda st, sd: ctx.mh_chains_general_dev("mvt", mu, Lcm, x0, st, 1.2 / math.sqrt(d), nu=5.0, seed=sd,
                                                                n_accept=nacc))
             run(5, 3)
             torch.cuda.synchronize()
@@ -543,15 +543,15 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
     except Exception as e:
         out["pf_c5_sharded_particle_steps_per_sec"] = {"error": repr(e)}
     try:
-        # the same model with informative observations (V = 0.05 I): the weights are uneven enough for the mass
+        # the same model with informative observations (V = 0.5 I): the weights are uneven enough for the mass
         # to move BETWEEN shards, so children really descend from parents on other GPUs
         T = 11 if quick else 21
         rng = np.random.default_rng(5002)
         xs, Y = np.zeros(d), np.zeros((d, T))
         for t in range(1, T):
             xs = 0.9 * xs + rng.standard_normal(d)
-            Y[:, t] = xs + np.sqrt(0.05) * rng.standard_normal(d)
-        pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, 0.05 * I, I,
+            Y[:, t] = xs + np.sqrt(0.5) * rng.standard_normal(d)
+        pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, 0.5 * I, I,
                                               resampler="systematic", seed=3, summary=False)
         ms = _sharded_run(pf, torch, dist, "p2p")
         ess = pf.summary()["ess"]
@@ -563,7 +563,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         pf.close()
         out["pf_c5_sharded_skewed_weights"] = {
             "value": N * (T - 1) / (ms * 1e-3), "N_global": N, "n_gpus": world, "d": d, "T": T, "ms_per_step": ms / (T - 1),
-            "model": "V = 0.05 I (informative observations), data simulated from the model",
+            "model": "V = 0.5 I (informative observations), data simulated from the model",
             "ess_mean_over_N": float(np.mean(ess[1:]) / N), "remote_parent_fraction_last_step": frac,
             "nvlink_gather_bytes_per_step_estimate": frac * N * 8 * d,
             "note": "remote parents are read over NVLink by the fused step kernel (8 d bytes per child whose parent "

@@ -959,9 +959,9 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
         if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
             fa.mode = pffused::kParentLookup;
             // the parents it found: an OUTPUT only (nothing downstream reads them), so they are stored where
-            // somebody can ask for them -- the last step (cusmc_filter_state_dev), phase-by-phase drivers
-            // (sharded runs, which may stop anywhere) and history rows (written through hist_a)
-            fa.anc_out = (t == cfg.T - 1 || f->world > 1) ? f->anc : nullptr;
+            // somebody can ask for them -- the last step (cusmc_filter_state_dev) and the history rows
+            // (written through hist_a)
+            fa.anc_out = t == cfg.T - 1 ? f->anc : nullptr;
             fa.s.anc = nullptr;
             fa.accumulate = cfg.ess_threshold > 0.0;
         } else {

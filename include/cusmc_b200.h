@@ -442,7 +442,10 @@ int cusmc_filter_get_log_weights(cusmc_filter *f, double *lw);
 int cusmc_filter_get_lineage(cusmc_filter *f, uint32_t *lineage, int *n_unique);
 /* Device time of the last run's step loop (t = 1 .. T-1), ms, from CUDA events on the stream. */
 double cusmc_filter_last_ms(const cusmc_filter *f);
-/* Current device-resident state: x (SoA [d][N]), weights (N), ancestors of the last step (N). */
+/* Current device-resident state: x (SoA [d][N]), weights (N), ancestors of the last step (N).  The
+ * normalised resamplers carry their weights in the weight image, so w and a are filled in by the LAST
+ * step of a run (t = T - 1) -- and w by every step when the summary, the history or ess_threshold need
+ * the log-weights anyway; in reference mode ("metropolis", "rejection") both are current after every step. */
 int cusmc_filter_state_dev(cusmc_filter *f, double **x_soa_dev, double **w_dev, uint32_t **a_dev);
 
 /* R-level run() (src/run.rcpp.cpp:58-126) on host pointers: runs the filter and returns weights

@@ -52,10 +52,18 @@ if which in ("all", "mh"):
     mu = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
     x = (L @ torch.randn((Cn, d, 1), dtype=torch.float64, device="cuda")).squeeze(-1).contiguous()
     ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=3)
+    ctx.mh_chains_general_dev("mvt", mu, Lcm, x, steps, 1.2 / np.sqrt(d), nu=5.0, seed=4)
     torch.cuda.synchronize()
-print("prof_driver done", ctx.launch_count, "launches")
 
-if which in ("perpoint",):
+if which in ("all", "metropolis"):
+    N, B = 1000000, 10
+    w = torch.rand(N, dtype=torch.float64, device="cuda")
+    a = torch.empty(N, dtype=torch.int32, device="cuda")
+    for r in range(2):
+        ctx.metropolis_hastings_dev(a, w, B, seed=5, step=1 + r)
+    torch.cuda.synchronize()
+
+if which in ("all", "perpoint"):
     N, d = 1 << 19, 32
     packed = d * (d + 1) // 2
     Lp = torch.randn((N, packed), dtype=torch.float64, device="cuda") * 0.1
@@ -67,3 +75,4 @@ if which in ("perpoint",):
     for _ in range(2):
         ctx.logpdf_perpoint_dev("mvt", x, mu, Lp, o, nu=5.0)
     torch.cuda.synchronize()
+print("prof_driver done", ctx.launch_count, "launches")

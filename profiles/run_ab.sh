@@ -5,6 +5,6 @@
 set -x; mkdir -p gpurun_out
 TAG=${TAG:-ab}
 for v in "" ${VARIANTS:-}; do
-  for i in 1 2; do echo "variant '$v'"; CUSMC_B200_LIB=$PWD/cusmc_b200/libcusmc_b200$v.so python profiles/pf_breakdown.py ${WHICH:-c5 41}; done
+  for i in 1 2; do echo "variant '$v'"; CUSMC_B200_LIB=$PWD/cusmc_b200/libcusmc_b200$v.so python profiles/prof_c5.py ${WHICH:-c5 41}; done
 done > gpurun_out/pfb_$TAG.log 2>&1
 cat gpurun_out/pfb_$TAG.log
