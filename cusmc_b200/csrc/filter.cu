@@ -564,7 +564,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         if (world > 1) alloc((void **)&f->rank_sums, sizeof(unsigned long long) * 3 * CUSMC_MAX_PEERS);
     }
     if (world > 1) {
-        const size_t mail_bytes = sizeof(unsigned long long) * 4 * 3 * (size_t)world * (size_t)T;
+        const size_t mail_bytes = sizeof(unsigned long long) * kMailWords * kMailCells * (size_t)world * (size_t)T;
         alloc((void **)&f->mail, mail_bytes);
         alloc((void **)&f->mail_err, 8);
         if (e == cudaSuccess) e = cudaMemsetAsync(f->mail, 0, mail_bytes, ctx->stream);
@@ -1040,15 +1040,39 @@ extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draw
     if (rc == CUSMC_OK) rc = cusmc_filter_begin(f, draws);
     if (rc == CUSMC_OK) rc = after_weights(0);
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 0);
+    // CUSMC_SHARD_TRACE=1: device time of the step kernel and of the update (exchanges included) of steps
+    // 5 .. 14 of this rank, on stderr (profiling aid; events on the stream, read after the run)
+    const bool trace = std::getenv("CUSMC_SHARD_TRACE") != nullptr && f->cfg.T > 16;
+    cudaEvent_t tev[10][3] = {};
+    if (trace)
+        for (auto &row : tev)
+            for (auto &e : row) cudaEventCreate(&e);
     for (int t = 1; t < f->cfg.T && rc == CUSMC_OK; ++t) {
+        const bool stamp = trace && t >= 5 && t < 15;
         rc = cusmc_filter_resample(f, t);
         // reference mode: the ancestors are local, but the step kernel overwrites the state buffer the
         // peers gathered from during the previous step
         if (rc == CUSMC_OK && !is_log) rc = launch_exchange(f, false, kCellBarrier, t);
+        if (stamp) cudaEventRecord(tev[t - 5][0], f->ctx->stream);
         if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
+        if (stamp) cudaEventRecord(tev[t - 5][1], f->ctx->stream);
         if (rc == CUSMC_OK) rc = after_weights(t);
+        if (stamp) cudaEventRecord(tev[t - 5][2], f->ctx->stream);
     }
     if (rc == CUSMC_OK) rc = cusmc_filter_mark(f, 1);
+    if (trace) {
+        cudaStreamSynchronize(f->ctx->stream);
+        float k1 = 0.f, k2 = 0.f, ms = 0.f;
+        for (auto &row : tev) {
+            cudaEventElapsedTime(&ms, row[0], row[1]);
+            k1 += ms;
+            cudaEventElapsedTime(&ms, row[1], row[2]);
+            k2 += ms;
+            for (auto &e : row) cudaEventDestroy(e);
+        }
+        std::fprintf(stderr, "rank %d: step kernel %.1f us, update + exchanges %.1f us (mean of steps 5..14)\n", f->rank,
+                     k1 * 100.0, k2 * 100.0);
+    }
     f->fused = false;
     return rc;
 }

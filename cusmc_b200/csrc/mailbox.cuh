@@ -1,16 +1,19 @@
 // mailbox.cuh -- scalar exchange between the ranks of a sharded filter through PEER MEMORY.
 //
-// Every rank owns a mailbox [T][3 cells][world] of 4-word entries (words 0..2 payload, word 3 flag)
-// that its peers map with CUDA IPC.  Publishing = lane r of one warp stores this rank's payload
-// into entry [cell][rank] of rank r's mailbox (a peer store over NVLink), fences at system scope,
-// then stores the flag; waiting = lane r spins on entry [cell][r] of the rank's OWN mailbox (local
-// memory the peers write).  No collective library and no host round trip inside the time loop.
-// The sums exchange is fused into the tail of the (single-block) tile-scan kernel; the max exchange
-// and the barrier are one-warp kernels.  (Gating every block of the big kernels on the flags was
-// tried: an extra dependent L2 round trip + system fence per block cost 100 us per step at 32 Ki
-// blocks.)
+// Every rank owns a mailbox [T][3 cells][world] of 64-byte entries that its peers map with CUDA IPC.
+// An entry carries three 64-bit payload words as SIX 8-byte units, each unit = 32 bits of data + the
+// 32-bit run epoch (the flag travels INSIDE every store, the scheme of NCCL's low-latency protocol):
+// publishing = lane r of one warp stores the six units into entry [cell][rank] of rank r's mailbox (peer
+// stores over NVLink); waiting = lane r polls entry [cell][r] of the rank's OWN mailbox until all six
+// epochs match.  8-byte stores are single-copy atomic, so there is no payload / flag ordering to
+// enforce and no fence between them; a device-scope fence BEFORE the stores puts the publisher's earlier
+// writes (its tile fields) into L2, where the peers' NVLink loads are served from.  Measured on 2 GPUs
+// (profiles/shard_trace.py): update + both exchanges 28 us with payload / system fence / flag, 26 with
+// flag-in-data units, 19 without the two system-scope fences, against 8 us for the update alone.
+// No collective library and no host round trip inside the time loop.  The exchanges ride inside the
+// one-block tile-update kernel; reference-mode runs use one-warp exchange kernels as barriers.
 //
-// Flags carry the run epoch, so a mailbox is never cleared.  Spins are bounded (2 s by default,
+// Epochs make clearing unnecessary.  Spins are bounded (2 s by default,
 // cusmc_filter_set_exchange_timeout): on a timeout the error word is set and the kernel goes on instead
 // of hanging the GPU; every getter of the filter then returns CUSMC_ERR_TIMEOUT (results void).
 #pragma once
@@ -40,42 +43,64 @@ __device__ __forceinline__ unsigned long long mail_now_ns()
     return t;
 }
 
-// Lanes 0 .. world-1 of ONE warp: store (w0, w1, w2) + flag into every rank's mailbox.
+constexpr int kMailWords = 8;     // uint64 words per mailbox entry (six used)
+
+__device__ __forceinline__ unsigned long long mail_unit(unsigned int data, unsigned long long epoch)
+{
+    return (unsigned long long)data | (epoch << 32);
+}
+
+// Lanes 0 .. world-1 of ONE warp: store (w0, w1, w2), flag included, into every rank's mailbox.
 __device__ __forceinline__ void mail_publish(const MailArgs &m, size_t cell0, int lane, unsigned long long w0,
                                              unsigned long long w1, unsigned long long w2)
 {
     if (lane < m.world) {
-        volatile unsigned long long *dst = m.peer[lane] + (cell0 + m.rank) * 4;
-        dst[0] = w0;
-        dst[1] = w1;
-        dst[2] = w2;
-        __threadfence_system();
-        dst[3] = m.epoch;
+        // This rank's earlier writes (its tile fields) must be in L2 -- where the peers' NVLink loads are
+        // served from -- before a unit is even issued: a DEVICE-scope fence.  (A system-scope one costs
+        // 1.8 us per exchange here and buys nothing: the only remote stores are the units themselves.)
+        __threadfence();
+        volatile unsigned long long *dst = m.peer[lane] + (cell0 + m.rank) * kMailWords;
+        const unsigned long long w[3] = {w0, w1, w2};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            dst[2 * k] = mail_unit((unsigned int)w[k], m.epoch);
+            dst[2 * k + 1] = mail_unit((unsigned int)(w[k] >> 32), m.epoch);
+        }
     }
 }
 
-// Lanes 0 .. world-1 of a warp: lane r returns rank r's payload once its flag is up (0 for the
-// other lanes).
+// Lanes 0 .. world-1 of a warp: lane r returns rank r's payload once all its units carry the epoch (0
+// for the other lanes).
 __device__ __forceinline__ void mail_wait(const MailArgs &m, size_t cell0, int lane, unsigned long long &w0,
                                           unsigned long long &w1, unsigned long long &w2)
 {
     w0 = w1 = w2 = 0;
     if (lane < m.world) {
-        volatile unsigned long long *src = m.peer[m.rank] + (cell0 + lane) * 4;
-        if (src[3] != m.epoch) {
-            const unsigned long long t0 = mail_now_ns();
-            while (src[3] != m.epoch) {
-                __nanosleep(32);
-                if (mail_now_ns() - t0 > m.timeout_ns) {
-                    *m.err = 1;
-                    break;
-                }
+        volatile unsigned long long *src = m.peer[m.rank] + (cell0 + lane) * kMailWords;
+        const unsigned long long want = m.epoch & 0xffffffffull;
+        unsigned long long u[6];
+        unsigned long long t0 = 0;
+        unsigned spins = 0;
+        for (;;) {
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                u[k] = src[k];
+                ok = ok && (u[k] >> 32) == want;
+            }
+            if (ok) break;
+            if ((++spins & 15u) != 0) continue;          // the global timer is slow to read: every 16th poll
+            if (t0 == 0) t0 = mail_now_ns();
+            if (mail_now_ns() - t0 > m.timeout_ns) {
+                *m.err = 1;
+                break;
             }
         }
-        __threadfence_system();
-        w0 = src[0];
-        w1 = src[1];
-        w2 = src[2];
+        // no acquire fence: the waiting warp only consumes the payload it has just read; the peers' bulk
+        // data is read by the NEXT kernel, which the kernel boundary orders after this one
+        w0 = (u[0] & 0xffffffffull) | (u[1] << 32);
+        w1 = (u[2] & 0xffffffffull) | (u[3] << 32);
+        w2 = (u[4] & 0xffffffffull) | (u[5] << 32);
     }
 }
 
