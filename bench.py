@@ -221,7 +221,10 @@ def run_reference(args, rank):
 # ------------------------------------------------------------------------------------------------
 # secondary workloads (reported inside the same JSON line; they do not affect `value`)
 # ------------------------------------------------------------------------------------------------
-NOISE_NOTE = "philox4x32-10 in-kernel, single-precision Box-Muller (24-bit normals, +-6.7 sigma)"
+NOISE_NOTE = ("in-kernel, counter-based: philox4x32-7 + single-precision Box-Muller on the special-function unit "
+              "(24-bit normals, +-6.7 sigma; the throughput generator -- reproducible_rng=1 selects philox4x32-10 + "
+              "FFMA-only polynomials, which the oracle mirrors bit for bit)")
+CHAIN_NOISE_NOTE = "in-kernel philox4x32-10 + reproducible single-precision Box-Muller (mirrored bit for bit by the oracle)"
 
 
 def _timed(torch, fn, reps):
@@ -325,7 +328,7 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
                          "accept_rate": float(nacc.double().mean().item() / steps)}
         first = res["target_factor_proposal"]
         line = {"value": first["value"], "chains": Cn, "d": d, "steps": steps, "ms": first["ms"],
-                "target": "mvt nu=5 per-chain L", "noise": NOISE_NOTE, "accept_rate": first["accept_rate"],
+                "target": "mvt nu=5 per-chain L", "noise": CHAIN_NOISE_NOTE, "accept_rate": first["accept_rate"],
                 "formulation": "proposal x' = x + s L_c z: whitened coordinates v' = v + s z, q' = |v'|^2; the factor "
                                "whitens the start and un-whitens the result"}
         if "isotropic_proposal" in res:
@@ -628,7 +631,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         out["mh_c3_sharded_chain_steps_per_sec"] = {
             "value": Cn * world * steps / (ms * 1e-3), "chains": Cn * world, "chains_per_gpu": Cn, "n_gpus": world,
             "d": d, "steps": steps, "ms": ms, "scaling": "strong", "target": "mvt nu=5 per-chain L",
-            "noise": NOISE_NOTE, "includes": "all-reduce of the 2 d posterior moment sums"}
+            "noise": CHAIN_NOISE_NOTE, "includes": "all-reduce of the 2 d posterior moment sums"}
     except Exception as e:
         out["mh_c3_sharded_chain_steps_per_sec"] = {"error": repr(e)}
     return out

@@ -295,9 +295,20 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
         }
         return parent;
     };
+    // Sharded: a tile whose parents all live on this rank (ancestors are monotone: look at the first and
+    // the last) skips the per-child slot -> rank division -- almost every tile of a shard.
+    bool all_local = !PEERS;
+    const int64_t local_base = PEERS ? (int64_t)a.rank * (int64_t)a.per_rank.d : a.parent_base;
+    if (PEERS && lookup) {
+        all_local = true;
+        if (resample) {
+            const uint32_t lo = (uint32_t)local_base, first = sm.anc[pad(0)], last = sm.anc[pad((int)n_tile - 1)];
+            all_local = first >= lo && last - lo < a.per_rank.d;
+        }
+    }
     auto column_of = [&](uint32_t parent) {
-        const double *src = a.x_prev + ((int64_t)parent - a.parent_base);
-        if (PEERS && a.has_prev) {
+        const double *src = a.x_prev + ((int64_t)parent - local_base);
+        if (PEERS && a.has_prev && !all_local) {
             const uint32_t rk = fast_div(parent, a.per_rank);
             const uint32_t col = parent - rk * a.per_rank.d;
             src = (rk == (uint32_t)a.rank ? a.x_prev : a.x_prev_peer[rk]) + col;

@@ -694,6 +694,32 @@ def test_lineage_of_a_systematic_run(ctx):
     assert traj.shape == (T, N, d) and np.array_equal(traj[-1], h["x"][-1])
 
 
+def test_filter_c5_size_properties(ctx):
+    """BASELINE configs[4] at its per-GPU size (d = 8, 8 Mi particles), checked through size-independent
+    properties of systematic resampling on the library's own fixed-point weights: ancestors are sorted,
+    every parent's offspring count is floor or ceil of N w_j (never off by more), zero-weight parents
+    have no children, the normalised weights sum to one, ESS agrees with the weights."""
+    d, N, T = 8, 8 << 20, 3
+    I = np.eye(d)
+    Y = np.random.default_rng(5000).standard_normal((d, T))
+    pf = ctx.filter(N=N, Y=Y, m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=I, W=I, resampler="systematic", seed=2,
+                    keep_history=True, summary=False)
+    pf.run()
+    h, s = pf.history(), pf.summary()
+    pf.close()
+    for t in (1, 2):
+        a = h["a"][t].astype(np.int64)
+        assert np.all(np.diff(a) >= 0) and a[0] >= 0 and a[-1] < N
+        w = h["w"][t - 1]                                   # normalised weights of the parents
+        assert abs(w.sum() - 1.0) < 1e-9
+        counts = np.bincount(a, minlength=N)
+        expect = N * w
+        assert np.all(counts >= np.floor(expect - 1e-6)) and np.all(counts <= np.ceil(expect + 1e-6))
+        assert np.all(counts[w == 0.0] == 0)
+        assert np.isclose(s["ess"][t - 1], 1.0 / np.sum(w * w), rtol=1e-6)
+    assert np.all(np.isfinite(h["x"][2]))
+
+
 def kalman_means(Y, m0, C0, F, G, V, W):
     m, P = m0.copy(), C0.copy()
     out = [m.copy()]
