@@ -814,11 +814,25 @@ void orc_mh_chains(int dist, int64_t C, int d, int steps, double step, double nu
 }
 
 /* Random-walk MH whose proposal does not use the target's factor: x' = x + step * scale (.) z.  Every
- * step evaluates the target's quadratic form q' = |L^-1 (x' - mu)|^2 by forward substitution (whiten_q:
- * row k accumulates j ascending with fma, v_k = acc * (1 / L_kk), q accumulates k ascending) -- the
+ * step evaluates the target's quadratic form q' = |L^-1 (x' - mu)|^2 by forward substitution
+ * (whiten_q_scaled: rows pre-scaled by 1 / L_kk, row k accumulates j ascending with fma, q k ascending) -- the
  * density arithmetic of ref: src/statistics.cc.cpp:295-311 in whitened form -- and applies the accept
  * rule of orc_mh_chains (ref: src/samplers.cpp:30 on the density ratio).  No counterpart in the
  * reference; defines what mh_general_kernel reproduces bit for bit. */
+/* forward substitution with rows pre-scaled by 1 / L_kk: Ls[k][j] = L[k][j] * rinv[k], r~_k = r_k * rinv[k];
+ * v_k = r~_k - sum_{j<k} Ls[k][j] v_j (fma, j ascending), q = sum v_k^2 (fma, k ascending). */
+static double whiten_q_scaled(const double *Ls, const double *rs, double *v, int d)
+{
+    double q = 0.0;
+    for (int k = 0; k < d; ++k) {
+        double acc = rs[k];
+        for (int j = 0; j < k; ++j) acc = fma(-Ls[(size_t)k * d + j], v[j], acc);
+        v[k] = acc;
+        q = fma(v[k], v[k], q);
+    }
+    return q;
+}
+
 void orc_mh_chains_general(int dist, int64_t C, int d, int steps, double step, const double *scale, double nu,
                            int shared, const double *mu, const double *L, const double *x0, const double *z,
                            const double *thr, double *x_final, uint32_t *n_accept, uint8_t *accept_bits)
@@ -826,27 +840,28 @@ void orc_mh_chains_general(int dist, int64_t C, int d, int steps, double step, c
     double inv_nu = dist == 1 ? 1.0 / nu : 0.0;
 #pragma omp parallel
     {
-        double *buf = (double *)malloc(sizeof(double) * d * 5);
-        double *r = buf, *v = buf + d, *rinv = buf + 2 * d, *x = buf + 3 * d, *xp = buf + 4 * d;
+        double *buf = (double *)malloc(sizeof(double) * ((size_t)d * 5 + (size_t)d * d));
+        double *r = buf, *v = buf + d, *rinv = buf + 2 * d, *x = buf + 3 * d, *xp = buf + 4 * d, *Ls = buf + 5 * d;
 #pragma omp for schedule(static)
         for (int64_t c = 0; c < C; ++c) {
             const double *Lc = shared ? L : L + (size_t)c * d * d;
             const double *mc = shared ? mu : mu + (size_t)c * d;
             for (int k = 0; k < d; ++k) {
                 rinv[k] = 1.0 / A_(Lc, k, k, d);
+                for (int j = 0; j < k; ++j) Ls[(size_t)k * d + j] = A_(Lc, k, j, d) * rinv[k];
                 x[k] = x0[(size_t)c * d + k];
-                r[k] = x[k] - mc[k];
+                r[k] = (x[k] - mc[k]) * rinv[k];
             }
-            double q = whiten_q(Lc, rinv, r, v, d);
+            double q = whiten_q_scaled(Ls, r, v, d);
             uint32_t nacc = 0;
             for (int s = 0; s < steps; ++s) {
                 const double *zs = z + ((size_t)c * steps + s) * d;
                 for (int k = 0; k < d; ++k) {
                     double sk = step * (scale ? scale[k] : 1.0);
                     xp[k] = fma(sk, zs[k], x[k]);
-                    r[k] = xp[k] - mc[k];
+                    r[k] = (xp[k] - mc[k]) * rinv[k];
                 }
-                double qp = whiten_q(Lc, rinv, r, v, d);
+                double qp = whiten_q_scaled(Ls, r, v, d);
                 double th = thr[(size_t)c * steps + s];
                 int acc_flag;
                 if (dist == 0) {
