@@ -987,30 +987,20 @@ extern "C" int cusmc_filter_mark(cusmc_filter *f, int which)
 }
 
 // ---- the sharded run ------------------------------------------------------------------------------
-// One-warp exchange kernels (mailbox.cuh): all-reduce(MAX) of the step's log-weight max, or a plain
-// barrier.  (The third exchange, the sums, rides in the tail of tile_scan_kernel.)
-template <bool MAX>
-__global__ void __launch_bounds__(32) exchange_kernel(const MailArgs m, size_t cell0, StepSlot *slot)
+// One-warp barrier over the mailboxes (reference-mode runs: the peers read each other's densities and
+// state buffers between launches; the normalised resamplers exchange inside tile_update_kernel).
+__global__ void __launch_bounds__(32) barrier_kernel(const MailArgs m, size_t cell0)
 {
     const int lane = threadIdx.x;
-    mail_publish(m, cell0, lane, MAX ? (unsigned long long)__double_as_longlong(slot->lw_max) : 0ull, 0, 0);
+    mail_publish(m, cell0, lane, 0ull, 0ull, 0ull);
     unsigned long long w0, w1, w2;
     mail_wait(m, cell0, lane, w0, w1, w2);
-    if (MAX) {
-        double v = lane < m.world ? __longlong_as_double((long long)w0) : -INFINITY;
-        if (!(v == v)) v = -INFINITY;
-        v = warp_max_double(v);
-        if (lane == 0) slot->lw_max = v;       // the slot now holds the GLOBAL max
-    }
 }
 
-static int launch_exchange(cusmc_filter *f, bool max, int cell, int t)
+static int launch_barrier(cusmc_filter *f, int cell, int t)
 {
     cusmc_ctx *ctx = f->ctx;
-    const MailArgs m = filter_mail(f);
-    const size_t cell0 = mail_cell(t, cell, f->world);
-    if (max) exchange_kernel<true><<<1, 32, 0, ctx->stream>>>(m, cell0, f->slots + t);
-    else exchange_kernel<false><<<1, 32, 0, ctx->stream>>>(m, cell0, f->slots + t);
+    barrier_kernel<<<1, 32, 0, ctx->stream>>>(filter_mail(f), mail_cell(t, cell, f->world));
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -1033,7 +1023,7 @@ extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draw
     f->fused = true;
     auto after_weights = [&](int t) -> int {
         // reference mode: just a barrier (peers read these densities next)
-        if (!is_log) CUSMC_CHECK(launch_exchange(f, false, kCellMax, t));
+        if (!is_log) CUSMC_CHECK(launch_barrier(f, kCellMax, t));
         return cusmc_filter_weigh(f, t);
     };
     int rc = cudaMemsetAsync(f->mail_err, 0, 8, f->ctx->stream) == cudaSuccess ? CUSMC_OK : CUSMC_ERR_CUDA;
@@ -1052,7 +1042,7 @@ extern "C" int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draw
         rc = cusmc_filter_resample(f, t);
         // reference mode: the ancestors are local, but the step kernel overwrites the state buffer the
         // peers gathered from during the previous step
-        if (rc == CUSMC_OK && !is_log) rc = launch_exchange(f, false, kCellBarrier, t);
+        if (rc == CUSMC_OK && !is_log) rc = launch_barrier(f, kCellBarrier, t);
         if (stamp) cudaEventRecord(tev[t - 5][0], f->ctx->stream);
         if (rc == CUSMC_OK) rc = cusmc_filter_propagate(f, t);
         if (stamp) cudaEventRecord(tev[t - 5][1], f->ctx->stream);

@@ -18,8 +18,6 @@ struct StepArgs {
     // hist_x [n][d] AoS, hist_w [n], hist_a [n] (global parent ids)
     double *hist_x, *hist_w;
     uint32_t *hist_a;
-    const unsigned long long *resampled;   // optional: if *resampled == 0 the step did not resample and
-                                           // the new log-weight is ADDED to the particle's old one
     int64_t n_out, ld_new, ld_prev, ld_noise;
     int64_t i0;                  // global index of child 0 (keys the counter-based draws)
     int64_t parent_base;         // global index of x_prev column 0

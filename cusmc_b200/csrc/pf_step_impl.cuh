@@ -68,7 +68,6 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         }
         lw = particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG>(op, op.c, ep, a, i, src, r0);
         double *dst_lw = a.lw + i;
-        if (!a.skip_weight && a.resampled && *a.resampled == 0) lw = *dst_lw + lw;   // no resampling: weights accumulate
         st_stream(dst_lw, lw);
         if (a.hist_w) st_stream(a.hist_w + i, lw);
         if (a.hist_a) a.hist_a[i] = (uint32_t)(parent + a.parent_base);

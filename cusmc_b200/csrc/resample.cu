@@ -265,7 +265,7 @@ constexpr int kScanThreads = 1024;
 constexpr int kScanItems = 4;
 __global__ void __launch_bounds__(kScanThreads)
 tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned long long *__restrict__ stats,
-                 int full, const MailArgs mail, size_t cell_sums, const ScatterSetup next)
+                 int full)
 {
     __shared__ unsigned long long sm[kScanThreads / 32];
     __shared__ unsigned long long s_chunk;
@@ -316,8 +316,7 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
         carry += s_chunk;
         __syncthreads();
     }
-    if (!stats && !next.enabled) return;
-    __shared__ unsigned long long s_tot[3];
+    if (!stats) return;
     if (full) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -340,38 +339,12 @@ tile_scan_kernel(unsigned long long *__restrict__ image, int64_t tiles, unsigned
             }
         }
     }
-    if (threadIdx.x == 0) {
-        s_tot[0] = carry;
-        s_tot[1] = full ? s2 : 0ull;
-        s_tot[2] = full ? np : 0ull;
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    unsigned long long w0 = s_tot[0], w1 = s_tot[1], w2 = s_tot[2], below = 0;
-    if (mail.world > 1) {
-        // fused all-gather of the per-rank sums: totals over ranks, and the mass on lower ranks
-        mail_publish(mail, cell_sums, lane, w0, w1, w2);
-        mail_wait(mail, cell_sums, lane, w0, w1, w2);
-        below = lane < mail.rank ? w0 : 0ull;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            w0 += __shfl_xor_sync(0xffffffffu, w0, o);
-            w1 += __shfl_xor_sync(0xffffffffu, w1, o);
-            w2 += __shfl_xor_sync(0xffffffffu, w2, o);
-            below += __shfl_xor_sync(0xffffffffu, below, o);
+    if (threadIdx.x == 0) {                 // thread 0 holds the running total and warp 0's reductions
+        stats[0] = carry;
+        if (full) {
+            stats[1] = s2;
+            stats[2] = np;
         }
-    }
-    if (lane == 0) {
-        if (stats) {
-            stats[0] = w0;
-            if (full) {
-                stats[1] = w1;
-                stats[2] = w2;
-            }
-            if (mail.world > 1) stats[3] = below;      // StepSlot::cdf_offset
-        }
-        if (next.enabled)
-            *reinterpret_cast<ScatterConsts *>(image) = make_scatter_consts(w0, next.u0, next.N_global, next.ess_bound, w1);
     }
 }
 
@@ -382,43 +355,20 @@ struct ScanArgs {
     const unsigned long long *local;       // weight image: inclusive prefix of weight i inside its tile
     ScatterConsts *consts;                 // weight image: the per-launch constants of the scatter
     unsigned long long *cdf_out;           // optional inclusive global CDF
-    uint32_t *anc_out;                     // optional systematic ancestors for children
-    uint32_t *const *anc_peer;             // PEERS: device table, rank r's ancestor array (child slots r*per_rank ..)
-    FastDiv per_rank;
-    uint32_t rank;                         // PEERS: children on this rank go through anc_out directly
+    uint32_t *anc_out;                     // optional systematic ancestors for the children out_lo .. out_hi - 1
     uint32_t N, N_global, j0, out_lo, out_hi;   // all < 2^32 (ancestors are 32-bit)
     double u0;
-    // adaptive resampling: resample only if sum_q^2 < ess_bound * sum_q2 (ess_bound = threshold * N *
-    // 2^shift; 0 = always).  *resampled_out receives the decision (block 0).
-    const unsigned long long *sum_q2;
-    unsigned long long *resampled_out;
-    unsigned long long *degenerate_out;    // optional: set to 1 when the total mass is zero
-    double ess_bound;
 };
 
-// The scatter constants for callers whose totals do not come out of tile_scan_kernel (building-block
-// entry points with a caller-supplied total, sharded runs whose sums travel through torch.distributed).
+// The per-launch constants of the scatter, computed once by one thread (the caller supplies the total).
 __global__ void scatter_consts_kernel(const ScanArgs p)
 {
-    if (threadIdx.x == 0)
-        *p.consts = make_scatter_consts(*p.total, p.u0, p.N_global, p.ess_bound,
-                                        p.ess_bound > 0.0 ? *p.sum_q2 : 0ull);
+    if (threadIdx.x == 0) *p.consts = make_scatter_consts(*p.total, p.u0, p.N_global, 0.0, 0ull);
 }
 
-// PEERS: every child of a local parent is written, wherever its slot lives -- a store into the
-// owning rank's ancestor array through its peer-mapped pointer (4 bytes per child over NVLink).
-template <bool PEERS>
 __device__ __forceinline__ void put_ancestor(const ScanArgs &p, uint32_t child, uint32_t parent)
 {
-    if (PEERS) {
-        // children of local parents are mostly local: only a remote one pays the load of its
-        // owner's pointer from the table in device memory
-        const uint32_t r = fast_div(child, p.per_rank);
-        uint32_t *dst = r == p.rank ? p.anc_out : p.anc_peer[r];
-        dst[child - r * p.per_rank.d] = parent;
-    } else {
-        p.anc_out[child - p.out_lo] = parent;
-    }
+    p.anc_out[child - p.out_lo] = parent;
 }
 
 // Global CDF from the weight image and, fused in, the systematic offspring scatter: parent j owns
@@ -436,7 +386,7 @@ static_assert(kTile % (32 * kPar) == 0, "a warp of the resampling pass must lie 
 
 // The rounds of one warp.  FAST: all 32 kPar parents exist and the children are not clipped to a
 // sub-range (every filter step but a warp at the end of the cloud): no per-parent predicates.
-template <bool PEERS, bool FAST>
+template <bool FAST>
 __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterConsts &c, const uint64_t (&C)[kPar],
                                                uint64_t Cbelow, uint32_t i0, uint32_t lane)
 {
@@ -449,12 +399,10 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
         k[r] = (FAST || i0 + 32 * r < p.N) ? (uint32_t)offspring_below(C[r], Ng, T, r0, ng_over_t, r0_over_t) : 0u;
     uint32_t k_carry = 0;                              // count below the round's first parent (lane 0)
     if (lane == 0) k_carry = (uint32_t)offspring_below(Cbelow, Ng, T, r0, ng_over_t, r0_over_t);
-    const uint32_t my_lo = PEERS ? p.rank * p.per_rank.d : 0u, my_hi = my_lo + (PEERS ? p.per_rank.d : 0u);   // this rank's child slots
 #pragma unroll
     for (int r = 0; r < kPar; ++r) {
         const bool active = FAST || i0 + 32 * r < p.N;
         uint32_t k_prev = __shfl_up_sync(0xffffffffu, k[r], 1);
-        const uint32_t round_lo = __shfl_sync(0xffffffffu, k_carry, 0);   // the round's children: [round_lo, k_carry')
         if (lane == 0) k_prev = k_carry;
         k_carry = __shfl_sync(0xffffffffu, k[r], 31);  // lane 0 uses it as the next round's k_prev; a full round is all active
         // parents past the end own the empty range; their threads stay to help with large families
@@ -469,17 +417,8 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
         const bool big = n > 8;
         const uint32_t ns = big ? 0u : n;
         const uint32_t slots = __reduce_max_sync(0xffffffffu, ns);
-        // (lane 31 may be past the end in the cloud's last warp: the round's upper end is the largest b)
-        if (PEERS && !(round_lo >= my_lo && __reduce_max_sync(0xffffffffu, b) <= my_hi)) {
-            // some child of this round lives on another rank: slot -> rank division per child
-#pragma unroll
-            for (uint32_t q = 0; q < 8; ++q) {
-                if (q >= slots) break;
-                if (q < ns) put_ancestor<PEERS>(p, a + q, parent);
-            }
-        } else {
-            // all children local (almost every round: shards hold about their share of the mass)
-            uint32_t *dst = p.anc_out + (a - (PEERS ? my_lo : p.out_lo));   // slot q: one compare, one store at dst + 4 q
+        {
+            uint32_t *dst = p.anc_out + (a - p.out_lo);       // slot q: one compare, one store at dst + 4 q
 #pragma unroll
             for (uint32_t q = 0; q < 8; ++q) {
                 if (q >= slots) break;
@@ -494,12 +433,11 @@ __device__ __forceinline__ void scatter_rounds(const ScanArgs &p, const ScatterC
             const uint32_t sb = __shfl_sync(0xffffffffu, b, src);
             const uint32_t sp = __shfl_sync(0xffffffffu, parent, src);
 #pragma unroll 1
-            for (uint32_t cc = sa + lane; cc < sb; cc += 32) put_ancestor<PEERS>(p, cc, sp);
+            for (uint32_t cc = sa + lane; cc < sb; cc += 32) put_ancestor(p, cc, sp);
         }
     }
 }
 
-template <bool PEERS>
 __global__ void __launch_bounds__(kThreads, CUSMC_SCAN_MINB)
 scan_resample_kernel(const ScanArgs p)
 {
@@ -508,7 +446,7 @@ scan_resample_kernel(const ScanArgs p)
     if (w0 >= p.N) return;                                                 // whole warp past the end
     const uint32_t i0 = w0 + lane;                                        // parents i0 + 32 r
     const uint32_t tile = w0 / kTile;                                     // a warp lies inside one tile
-    const bool scatter = PEERS || p.anc_out;
+    const bool scatter = p.anc_out != nullptr;
     const bool full = w0 + 32 * kPar <= p.N;
     // every load goes out before the first use
     const uint64_t prefix = __ldg(p.tile_prefix + tile);
@@ -523,7 +461,6 @@ scan_resample_kernel(const ScanArgs p)
         c.r0 = __ldg(&p.consts->r0);
         c.ng_over_t = __ldg(&p.consts->ng_over_t);
         c.r0_over_t = __ldg(&p.consts->r0_over_t);
-        c.resample = __ldg(&p.consts->resample);
     }
     const uint64_t base = prefix + offset;
 #pragma unroll
@@ -534,18 +471,19 @@ scan_resample_kernel(const ScanArgs p)
             if (i0 + 32 * r < p.N) p.cdf_out[i0 + 32 * r] = C[r];
     }
     if (!scatter) return;
-    if (w0 == 0 && lane == 0 && p.resampled_out) *p.resampled_out = c.resample;
-    if (c.T == 0 && w0 == 0 && lane == 0 && p.degenerate_out) *p.degenerate_out = 1;   // reported by the host getters
-    if (!c.resample || c.T == 0) {                    // keep every particle: a_i = i (also when there is no mass)
+    if (c.T == 0) {                                   // no mass: identity ancestors (the host entry points report it)
 #pragma unroll
         for (int r = 0; r < kPar; ++r)
-            if (i0 + 32 * r < p.N) put_ancestor<PEERS>(p, p.j0 + i0 + 32 * r, p.j0 + i0 + 32 * r);
+            if (i0 + 32 * r < p.N) {
+                const uint32_t g = p.j0 + i0 + 32 * r;
+                if (g >= p.out_lo && g < p.out_hi) put_ancestor(p, g, g);
+            }
         return;
     }
     if (full && p.out_lo == 0 && p.out_hi >= p.N_global)
-        scatter_rounds<PEERS, true>(p, c, C, base + Cprev, i0, lane);
+        scatter_rounds<true>(p, c, C, base + Cprev, i0, lane);
     else
-        scatter_rounds<PEERS, false>(p, c, C, base + Cprev, i0, lane);
+        scatter_rounds<false>(p, c, C, base + Cprev, i0, lane);
 }
 
 // Multinomial: a[i] = j0 + #{ j : cdf_j <= p_i },  p_i = min((uint64)(u_i * T), T - 1).
@@ -643,19 +581,11 @@ int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double 
 // full_stats adds the sum of squares and the positive count (ESS).  Two launches: the tiles, then
 // one block that turns the tile sums into prefixes and totals.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
-                             const MailArgs *mail_p, int t, const ScatterSetup *next_p)
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats)
 {
-    MailArgs mail{};
-    if (mail_p) mail = *mail_p;
-    ScatterSetup next{};
-    if (next_p) next = *next_p;
-    const bool exchange = mail.world > 1;
-    if (N == 0 && !exchange) return CUSMC_OK;
-    // an empty shard still publishes (max = -inf, sums = 0): one block over zero weights
-    const unsigned tiles = N == 0 ? 1u : (unsigned)image_tiles(N);
+    if (N == 0) return CUSMC_OK;
+    const unsigned tiles = (unsigned)image_tiles(N);
     const bool full = full_stats && stats_dev;
-    const size_t csum = mail_cell(t, kCellSums, mail.world);
     unsigned long long *img = (unsigned long long *)image;
     if (full && is_log)
         weigh_kernel<true, true><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
@@ -666,8 +596,7 @@ int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const 
     else
         weigh_kernel<false, false><<<tiles, kThreads, 0, ctx->stream>>>(w, max_dev, N, shift, img);
     CUSMC_LAUNCHED(ctx);
-    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(img, (int64_t)tiles, (unsigned long long *)stats_dev,
-                                                          full ? 1 : 0, mail, csum, next);
+    tile_scan_kernel<<<1, kScanThreads, 0, ctx->stream>>>(img, (int64_t)tiles, (unsigned long long *)stats_dev, full ? 1 : 0);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -681,8 +610,7 @@ size_t cusmc_scan_state_bytes(int64_t N)
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
-                      int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev,
-                      uint64_t *resampled_dev, double ess_bound, bool consts_ready, uint64_t *degenerate_dev)
+                      int64_t out_n, double u0)
 {
     if (N == 0) return CUSMC_OK;
     if (N_global > 0xFFFFFFFFll || out_lo < 0 || out_lo + out_n > N_global)
@@ -701,25 +629,12 @@ int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_
     p.out_lo = (uint32_t)out_lo;
     p.out_hi = (uint32_t)(out_lo + out_n);
     p.u0 = u0;
-    p.sum_q2 = (const unsigned long long *)sum_q2_dev;
-    p.resampled_out = (unsigned long long *)resampled_dev;
-    p.degenerate_out = (unsigned long long *)degenerate_dev;
-    p.ess_bound = sum_q2_dev ? ess_bound : 0.0;
     const unsigned grid = (unsigned)((N + kThreads * kPar - 1) / (kThreads * kPar));
-    if ((anc_out || peers) && !consts_ready) {
+    if (anc_out) {
         scatter_consts_kernel<<<1, 32, 0, ctx->stream>>>(p);
         CUSMC_LAUNCHED(ctx);
     }
-    if (peers) {
-        p.anc_peer = (uint32_t *const *)peers->table_dev;
-        p.per_rank = make_fast_div((uint32_t)peers->per_rank);
-        p.rank = (uint32_t)(j0 / peers->per_rank);          // j0 = this rank's first global slot
-        p.out_lo = 0;
-        p.out_hi = (uint32_t)N_global;
-        scan_resample_kernel<true><<<grid, kThreads, 0, ctx->stream>>>(p);
-    } else {
-        scan_resample_kernel<false><<<grid, kThreads, 0, ctx->stream>>>(p);
-    }
+    scan_resample_kernel<<<grid, kThreads, 0, ctx->stream>>>(p);
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -832,8 +747,7 @@ extern "C" int cusmc_weights_scan_dev(cusmc_ctx *ctx, const double *w_dev, int i
     if (N == 0) return CUSMC_OK;
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N, N_global, tile_prefix_dev, &state));
-    return cusmc_launch_scan(ctx, N, N_global, nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0,
-                             nullptr);
+    return cusmc_launch_scan(ctx, N, N_global, nullptr, cdf_offset_dev, state, cdf_dev, nullptr, 0, 0, 0, 0.0);
 }
 
 extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev, int is_log,
@@ -851,7 +765,7 @@ extern "C" int cusmc_resample_systematic_dev(cusmc_ctx *ctx, const double *w_dev
     const void *state = nullptr;
     CUSMC_CHECK(scan_prefixes(ctx, w_dev, is_log, max_dev, N_local, N_global, tile_prefix_dev, &state));
     return cusmc_launch_scan(ctx, N_local, N_global, total_dev, cdf_offset_dev, state, nullptr, a_dev, j0, out_lo,
-                             out_n, u0, nullptr);
+                             out_n, u0);
 }
 
 extern "C" int cusmc_resample_multinomial_dev(cusmc_ctx *ctx, const uint64_t *cdf_dev, int64_t N,

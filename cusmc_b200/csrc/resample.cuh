@@ -2,7 +2,6 @@
 #pragma once
 
 #include "common.cuh"
-#include "mailbox.cuh"
 
 int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n);
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
@@ -11,27 +10,16 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
 int cusmc_launch_rejection(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *wmax_dev, uint64_t seed,
                            uint64_t step, int64_t N, int cap);
-// image: cusmc_scan_state_bytes(N) bytes whose first word is zero; receives the weight image
-// (exclusive tile prefixes + tile-local CDF) the resampling pass consumes.  stats_dev may be NULL.
-// next: when given, the one-block tile scan also leaves the constants of the systematic resampling
-// pass that will consume this image (ScatterConsts, image words 0..7) -- computed from the GLOBAL
-// totals, i.e. after the fused sums exchange of a sharded run.
-struct ScatterSetup {
-    double u0;              // systematic offset of the resampling pass, [0, 1)
-    double ess_bound;       // adaptive resampling bound (0 = always resample), see ScanArgs
-    uint32_t N_global;
-    int enabled;
-};
+// Building-block weight image (global-max form; the filter itself lives on the block-relative image of
+// image.cuh): cusmc_scan_state_bytes(N) bytes; receives the exclusive tile prefixes + tile-local CDF the
+// scan / scatter pass consumes.  stats_dev may be NULL.
 int cusmc_launch_weights_sum(cusmc_ctx *ctx, const double *w, int is_log, const double *max_dev,
-                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats,
-                             const MailArgs *mail = nullptr, int t = 0, const ScatterSetup *next = nullptr);
+                             int64_t N, int shift, uint64_t *stats_dev, void *image, bool full_stats);
 size_t cusmc_scan_state_bytes(int64_t N);
 int cusmc_launch_scan(cusmc_ctx *ctx, int64_t N, int64_t N_global, const uint64_t *total_dev,
                       const uint64_t *cdf_offset_dev, const void *image,
                       uint64_t *cdf_out, uint32_t *anc_out, int64_t j0, int64_t out_lo,
-                      int64_t out_n, double u0, const CusmcPeers *peers, const uint64_t *sum_q2_dev = nullptr,
-                      uint64_t *resampled_dev = nullptr, double ess_bound = 0.0, bool consts_ready = false,
-                      uint64_t *degenerate_dev = nullptr);
+                      int64_t out_n, double u0);
 int cusmc_launch_multinomial(cusmc_ctx *ctx, const uint64_t *cdf, int64_t N, const uint64_t *total_dev,
                              const double *u, uint64_t seed, uint64_t step, int64_t i0,
                              int64_t n_out, int64_t j0, uint32_t *a, uint64_t *degenerate_dev = nullptr);

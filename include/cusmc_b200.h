@@ -365,18 +365,19 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
 /*
  * The same run, phase by phase -- what cusmc_filter_run chains on one GPU:
  *     begin;  weigh(0);  for t = 1 .. T-1:  resample(t);  propagate(t);  weigh(t)
- * A sharded filter (cfg.world > 1) is driven through these by the binding, which puts the scalar
- * exchanges between the phases (cusmc_b200/sharded.py; NCCL on the slot words below):
- *     after begin / propagate(t) : all-reduce MAX of slot[t] word 0 (the log-weight max)
- *     after weigh(t)             : all-gather of slot[t] words 1..3 (this rank's fixed-point sums);
- *                                  then words 1..3 := sums over ranks, word 4 := sum of word 1 over
- *                                  lower ranks (this rank's offset in the global CDF)
- *     after resample(t)          : barrier -- parents wrote their children's ancestor entries
- *                                  straight into the owning rank's array (peer stores over NVLink);
- *                                  propagate(t) then gathers parent states from the owning rank's
- *                                  state buffer (peer loads).  Ancestors are GLOBAL indices and the
- *                                  noise is keyed by the global slot, so a sharded run reproduces the
- *                                  single-GPU run bit for bit.
+ * For the normalised resamplers propagate(t) is the FUSED step kernel (every block finds the parents of
+ * its tile of children in the weight image of step t - 1, propagates, reweights and leaves its tile of
+ * the new image; systematic resample(t) is a no-op, multinomial materialises the CDF and searches it) and
+ * weigh(t) is the one-block tile update (global maximum, rescaled tile prefixes, total mass, constants of
+ * step t + 1), followed by the moment pass when cfg.summary is set.  Reference mode ("metropolis",
+ * "rejection") keeps densities: resample(t) runs the resampler, propagate(t) the one-particle-per-thread
+ * step kernel.
+ * A sharded filter (cfg.world > 1) is either run by cusmc_filter_run_sharded (scalar exchanges inside the
+ * update kernel) or driven through these phases by a binding that carries the scalars itself
+ * (cusmc_filter_weigh_phase below; cusmc_b200/sharded.py with NCCL).  Peers' weight images and states
+ * are read by peer loads inside the step kernel; ancestors are GLOBAL indices, noise is keyed by the
+ * global slot and a shard is a whole number of 2048-particle tiles, so a sharded run reproduces the
+ * single-GPU run bit for bit.
  * Slot layout (8 x 8 bytes): { double lw_max; uint64 sum_q, sum_q2, n_pos, cdf_offset, resampled, degenerate; 1 spare }.
  * Injected draws of a sharded run are this rank's shard (leading dimension = its particle count).
  */
@@ -398,16 +399,17 @@ int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev);
  * a sharded run all-reduces them (SUM) before cusmc_filter_get_summary. */
 int cusmc_filter_moments_dev(cusmc_filter *f, double **moments_dev);
 /* Peer mapping: export this rank's CUSMC_FILTER_IPC_BUFFERS buffers (state x 2, ancestors, weights,
- * mailbox) as that many x CUSMC_IPC_HANDLE_BYTES bytes; after an all-gather of those, attach maps
+ * mailbox, weight image x 2) as that many x CUSMC_IPC_HANDLE_BYTES bytes; after an all-gather of those, attach maps
  * every other rank's buffers (cudaIpcOpenMemHandle; all_handles is rank-major). */
 int cusmc_filter_ipc_export(cusmc_filter *f, unsigned char *handles);
 int cusmc_filter_ipc_attach(cusmc_filter *f, const unsigned char *all_handles);
 /*
- * The whole sharded run enqueued by the library: the phases above, with the three scalar exchanges
- * done by a one-warp kernel over PEER MEMORY (each rank stores its scalars and a flag into every
- * peer's mailbox and spins, bounded, on its own) -- no collective library and no host round trip
- * inside the time loop.  Every rank calls it collectively.  cusmc_filter_exchange_status returns
- * non-zero if a bounded spin timed out (a peer never arrived); the run's results are then void.
+ * The whole sharded run enqueued by the library: two launches per step and rank, the two scalar
+ * exchanges (maximum; per-rank sums) done INSIDE the tile-update kernel over PEER MEMORY (each rank
+ * stores its scalars, flag included, into every peer's mailbox and spins, bounded, on its own) -- no
+ * collective library and no host round trip inside the time loop.  Every rank calls it collectively.
+ * cusmc_filter_exchange_status returns non-zero if a bounded spin timed out (a peer never arrived); the
+ * run's results are then void and every getter returns CUSMC_ERR_TIMEOUT.
  */
 int cusmc_filter_run_sharded(cusmc_filter *f, const cusmc_filter_draws *draws);
 int cusmc_filter_exchange_status(cusmc_filter *f, uint64_t *status);
