@@ -251,7 +251,8 @@ struct FusedSmem {
 // One tile of children through the three phases.  `tile` = the block's tile on this rank.
 template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS, bool COH>
 __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
-                                                 const FusedArgs &fa, uint32_t tile, FusedSmem &sm)
+                                                 const FusedArgs &fa, uint32_t tile, FusedSmem &sm,
+                                                 const float *z_ready = nullptr)
 {
     const StepArgs &a = fa.s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -277,8 +278,9 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
     auto child = [&](uint32_t j, uint32_t parent, const double *src, const double *xp_in) {
         const int64_t i = (int64_t)j0 + j;
         cusmc_u32x4 r0{};
-        if (PHILOX) r0 = pfstep::step_rng<FAST>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
-        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0, xp_in);
+        const float *zin = z_ready ? z_ready + (size_t)j * D : nullptr;       // drawn in the barrier shadow
+        if (PHILOX && !zin) r0 = pfstep::step_rng<FAST>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
+        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0, xp_in, zin);
         if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
         if (a.lw) st_stream(a.lw + i, lw);
         if (a.hist_w) st_stream(a.hist_w + i, lw);

@@ -108,10 +108,13 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 // through L2, never through the non-coherent path.
 // xp_in (optional): the parent state already gathered into registers by the caller (the persistent
 // kernel issues a batch of gathers before it computes the batch: its rounds are latency-bound).
+// zf_in (optional, PHILOX): the child's D normals already drawn (the persistent kernel draws the next
+// step's normals while its block waits at the grid barrier).
 template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false>
 __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                 const StepArgs &a, int64_t i, const double *__restrict__ src,
-                                                const cusmc_u32x4 &r0, const double *xp_in = nullptr)
+                                                const cusmc_u32x4 &r0, const double *xp_in = nullptr,
+                                                const float *zf_in = nullptr)
 {
     const int d = EXACT ? D : a.d;
     const uint64_t idx = (uint64_t)(a.i0 + i);
@@ -131,7 +134,13 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
     // registers) until the one FMA that consumes them
     constexpr bool kFloatNoise = PHILOX && DIAG;
     float zf[kFloatNoise ? D : 1];
-    if (PHILOX) {
+    if (PHILOX && zf_in) {
+#pragma unroll
+        for (int k = 0; k < D; ++k) {
+            if constexpr (kFloatNoise) zf[k] = zf_in[k];
+            else z[k] = (double)zf_in[k];
+        }
+    } else if (PHILOX) {
         // one Philox block -> four single-precision Box-Muller normals (cusmc_philox.h)
 #pragma unroll
         for (int jq = 0; jq < (D + 3) / 4; ++jq) {

@@ -52,8 +52,12 @@ struct PersistArgs {
 // Grid barrier whose last arriver runs the tile update of step t before releasing the others.
 // Monotonic arrival counter + release generation (the kernel is launched cooperatively, so every block
 // is resident); everything that crosses it is read through L2 (ld.global.cg / ld.acquire).
-__device__ __forceinline__ void barrier_with_update(const PersistArgs &pa, int t, unsigned &gen, int *s_last,
-                                                    UpdateSmem<kThreads> &us)
+// While a block waits -- between its arrival and the release -- it draws the NEXT step's normals for its
+// own tile into shared memory (`shadow`, called by every block but the last to arrive, which has the
+// update to run and draws its normals inside its rounds instead).  Returns whether the shadow ran.
+template <typename Shadow>
+__device__ __forceinline__ bool barrier_with_update(const PersistArgs &pa, int t, unsigned &gen, int *s_last,
+                                                    UpdateSmem<kThreads> &us, Shadow shadow)
 {
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -96,14 +100,19 @@ __device__ __forceinline__ void barrier_with_update(const PersistArgs &pa, int t
             __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pa.barrier + 1), "r"(gen + 1u) : "memory");
         }
-    } else if (threadIdx.x == 0) {
-        unsigned seen;
-        do {
-            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(pa.barrier + 1) : "memory");
-        } while ((int)(seen - (gen + 1u)) < 0);
+    } else {
+        shadow();
+        if (threadIdx.x == 0) {
+            unsigned seen;
+            do {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(pa.barrier + 1) : "memory");
+            } while ((int)(seen - (gen + 1u)) < 0);
+        }
     }
+    const bool ran = !*s_last;
     __syncthreads();
     ++gen;
+    return ran;
 }
 
 #ifndef CUSMC_PERSIST_MINB
@@ -119,8 +128,28 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
     __shared__ FusedSmem sm;
     __shared__ UpdateSmem<kThreads> us;
     __shared__ int s_last;
+    // normals of the next step, drawn in the barrier shadow (d = 2: 16 KB; wider states would cost a
+    // resident block per SM, they draw inside their rounds)
+    constexpr bool kShadowNoise = D == 2;
+    __shared__ float s_z[kShadowNoise ? kTile * D : 1];
     unsigned gen = 0;
     FusedArgs fa = pa.fa;
+    const uint32_t tile_lo = blockIdx.x * fa.tile_n;
+    const uint32_t tile_cnt = min(fa.tile_n, (uint32_t)fa.s.n_out - tile_lo);
+    // the normals the step kernel would draw for (step, slot): same counters, same transform
+    auto draw_next = [&](int t_next) {
+        if constexpr (kShadowNoise) {
+            if (t_next >= pa.T) return;
+            for (uint32_t j = threadIdx.x; j < tile_cnt; j += kThreads) {
+                const cusmc_u32x4 r = pfstep::step_rng<FAST>(fa.s.seed, CUSMC_STREAM_NORMAL, (uint64_t)t_next,
+                                                             (uint64_t)(fa.s.i0 + tile_lo + j), 0u);
+                float zq[4];
+                pfstep::normals4<FAST>(r, zq);
+#pragma unroll
+                for (int k = 0; k < D; ++k) s_z[(size_t)j * D + k] = zq[k];
+            }
+        }
+    };
 
     // ---- t = 0: x_0 = m0 + Q_c0 z, constant log-weight 0 (src/mcmc.cpp:63-85) -----------------------
     {
@@ -137,7 +166,7 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         fa.s.step = 0;
         pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op_init, zero_c, ep, fa, blockIdx.x, sm);
     }
-    barrier_with_update(pa, 0, gen, &s_last, us);
+    bool z_ready = barrier_with_update(pa, 0, gen, &s_last, us, [&] { draw_next(1); }) && kShadowNoise;
 
     fa.mode = pffused::kParentLookup;
     fa.s.has_prev = 1;
@@ -164,9 +193,10 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         if (pa.trace && t == 50) fa.trace = pa.trace + 1 + ((size_t)pa.T + blockIdx.x) * 9;
 #endif
         CUSMC_STAMP(fa.trace, 0);
-        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op, cobs, ep, fa, blockIdx.x, sm);
+        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op, cobs, ep, fa, blockIdx.x, sm,
+                                                                                 z_ready ? s_z : nullptr);
         CUSMC_STAMP(fa.trace, 3);
-        barrier_with_update(pa, t, gen, &s_last, us);
+        z_ready = barrier_with_update(pa, t, gen, &s_last, us, [&] { draw_next(t + 1); }) && kShadowNoise;
         CUSMC_STAMP(fa.trace, 4);
     }
 }

@@ -347,3 +347,46 @@ def test_mh_chains_general_oracle_targets_the_right_law(orc):
     xf2, _, _ = orc.mh_chains_general("mvt", mu, L, x0, z, thr, 0.9, nu=nu, shared=True, scale=np.array([0.5, 1.0, 1.5]))
     v = np.linalg.solve(L, (xf2 - mu).T).T
     assert st.kstest((v * v).sum(1) / d, st.f(d, nu).cdf).pvalue > 1e-3
+
+
+def test_tile_image_definition(orc):
+    """orc_tile_image DEFINES the block-relative weight image the fused step and the tile update produce.
+    Checked here against what it must mean: a monotone integer CDF whose increments are the max-shifted
+    weights in fixed point (to one unit of the rescale), the same mass whatever the tile size (to
+    rounding), ESS from its integer sums = textbook ESS, exactness on constant weights, zero mass for
+    -inf / NaN weights and for tiles far below the global maximum."""
+    rng = np.random.default_rng(77)
+    N = 10000
+    lw = rng.standard_normal(N) * 3.0 - 7.0
+    lw[rng.random(N) < 0.02] = -np.inf
+    lw[5] = np.nan
+    shift = orc.fixed_shift(N)
+    lse, ess, lmax = orc.logsumexp_ess(np.where(np.isfinite(lw), lw, -np.inf))
+    totals = []
+    for tile in (64, 2048, 1 << 20):
+        C, T, T2, M = orc.tile_image(lw, tile)
+        assert M == lmax
+        Ci = C.astype(object)
+        assert all(Ci[i] <= Ci[i + 1] for i in range(N - 1)) and int(C[-1]) == T
+        q = np.diff(np.concatenate([[0], C.astype(np.float64)]))
+        want = np.where(np.isfinite(lw), np.exp(lw - M), 0.0) * 2.0 ** shift
+        # one unit from truncating q, one from each of the two rescales of a prefix difference
+        assert np.all(np.abs(q - want) <= 3.0 + 1e-12 * want)
+        assert q[5] == 0.0 and np.all(q[~np.isfinite(lw)] == 0.0)
+        assert np.isclose(T / 2.0 ** shift, np.exp(lse - M), rtol=1e-9)
+        assert np.isclose(T * T / (T2 * 2.0 ** shift), ess, rtol=1e-6)
+        totals.append(T)
+    assert max(totals) - min(totals) <= 2 * N                  # tile sizes differ by rounding only
+    # one tile = the global-max image: no rescale at all, increments are trunc(exp(lw - M) 2^shift) exactly
+    C, T, _, M = orc.tile_image(lw, 1 << 20)
+    q = np.diff(np.concatenate([[0], C.astype(np.float64)]))
+    exact = np.array([int(orc.det_exp(v - M)[0] * 2.0 ** shift) if np.isfinite(v) and v - M >= -43.5 else 0 for v in lw[:200]])
+    assert np.array_equal(q[:200], exact)
+    # constant weights: exact whatever the tile
+    for tile in (7, 100, 4096):
+        C, T, T2, _ = orc.tile_image(np.full(1000, -3.25), tile)
+        assert np.array_equal(C, (np.arange(1000, dtype=np.uint64) + 1) << np.uint64(orc.fixed_shift(1000)))
+    # a tile 60 nats below the maximum carries no mass
+    lw2 = np.concatenate([np.full(64, -60.0), np.zeros(64)])
+    C, T, _, _ = orc.tile_image(lw2, 64)
+    assert int(C[63]) == 0 and T == 64 << orc.fixed_shift(128)
