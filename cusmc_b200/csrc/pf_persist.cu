@@ -61,9 +61,10 @@ __device__ __forceinline__ bool barrier_with_update(const PersistArgs &pa, int t
 {
     __syncthreads();
     if (threadIdx.x == 0) {
-        __threadfence();                                    // release this block's tile
-        const unsigned old = atomicAdd(pa.barrier, 1u);
-        __threadfence();                                    // acquire the others' (if this is the last arrival)
+        // one acq_rel atomic: releases this block's tile (the bar.sync above makes the release cumulative
+        // over the whole block's writes) and, for the last arrival, acquires everybody else's
+        unsigned old;
+        asm volatile("atom.add.acq_rel.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(pa.barrier) : "memory");
         *s_last = old == (gen + 1u) * gridDim.x - 1u;
 #ifdef CUSMC_TRACE
         if (pa.trace && t > 0) {
@@ -97,7 +98,6 @@ __device__ __forceinline__ bool barrier_with_update(const PersistArgs &pa, int t
                 pa.trace[1 + (size_t)t * 9 + 6] = (double)now;                          // update done
             }
 #endif
-            __threadfence();
             asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(pa.barrier + 1), "r"(gen + 1u) : "memory");
         }
     } else {
