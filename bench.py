@@ -293,6 +293,19 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
     guarded("pf_c5_shard_particle_steps_per_sec", lambda: c5(False))
     guarded("pf_c5_shard_dense_G_particle_steps_per_sec", lambda: c5(True))
 
+    def c5_mvt():
+        # the same shard with Student-t noise and observation density (the reference's "mvt": per-component chi
+        # factors, src/statistics.cc.cpp:381-411), nu = 5
+        d, N, T = 8, 8 << 20, (11 if quick else 41)
+        I = np.eye(d)
+        Y = np.random.default_rng(5000).standard_normal((d, T))
+        line = _pf_line(ctx, N, d, T, dict(m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=I, W=I), Y, 160, hbm_gbs, seed=2,
+                        summary=False, distribution="mvt", df=5.0)
+        line["noise"] = ("normals as above; chi factors sqrt(nu / chi2_nu): Marsaglia-Tsang gammas in single precision, one "
+                         "philox4x32-10 block per pair of components")
+        return line
+    guarded("pf_c5_shard_mvt_particle_steps_per_sec", c5_mvt)
+
     def c3():
         # C3: 65 536 independent MH chains, MVT target d = 32, per-chain covariance, 1k steps
         Cn, d, steps = 65536, 32, (100 if quick else 1000)

@@ -958,6 +958,7 @@ extern "C" int cusmc_filter_propagate(cusmc_filter *f, int t)
         pffused::FusedArgs fa = filter_fused_args(f, a, t);
         if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) {
             fa.mode = pffused::kParentLookup;
+            fa.pdl = cfg.summary ? 0 : 1;        // the kernel right before it on the stream is the tile update
             // the parents it found: an OUTPUT only (nothing downstream reads them), so they are stored where
             // somebody can ask for them -- the last step (cusmc_filter_state_dev) and the history rows
             // (written through hist_a)

@@ -55,6 +55,7 @@ struct FusedArgs {
     int mode;                                     // ParentMode
     int accumulate;                               // adaptive resampling: add the old log-weight when not resampled
     int shift;
+    int pdl;                                      // launch as a programmatic dependent of the preceding tile update
     double *trace;                                // profiling builds: 8 time stamps per step (else NULL)
 };
 
@@ -412,6 +413,13 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
 pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const FusedArgs fa)
 {
     __shared__ FusedSmem sm;
+    // Programmatic dependent launch: this grid is launched while the tile update of the previous step is
+    // still running (its blocks become resident, its launch latency is hidden) and waits HERE until that
+    // grid has completed and its writes are visible.  A no-op when launched the ordinary way.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    // ... and the tile update that follows THIS grid may be made resident as soon as every block here has
+    // started (it waits the same way), which hides its launch latency behind the last wave.
+    asm volatile("griddepcontrol.launch_dependents;");
     fused_block_step<D, PHILOX, FAST, MVT, EXACT, DIAG, PEERS, false>(op, op.c, ep, fa, blockIdx.x, sm);
 }
 
@@ -423,8 +431,20 @@ int launch_one(cusmc_ctx *ctx, const pfstep::StepModel &m, const Epilogue &ep, c
     pfstep::fill_step_op<D, DIAG>(op, m);
     const unsigned grid = (unsigned)((fa.s.n_out + kTile - 1) / kTile);
     const bool peers = fa.s.world > 1;
+    // launched as a programmatic dependent of the kernel before it on the stream (the tile update, which
+    // releases its dependents as soon as it starts): see pf_fused_kernel
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = fa.pdl ? 1 : 0;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.dynamicSmemBytes = 0;
+    lc.stream = ctx->stream;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
 #define CUSMC_FUSED_GO(PH, FA, PE) \
-    pf_fused_kernel<D, PH, FA, MVT, EXACT, DIAG, PE><<<grid, kThreads, 0, ctx->stream>>>(op, ep, fa)
+    CUSMC_CUDA(ctx, cudaLaunchKernelEx(&lc, pf_fused_kernel<D, PH, FA, MVT, EXACT, DIAG, PE>, op, ep, fa))
     if (philox && fa.s.fast_noise) {
         if (peers) CUSMC_FUSED_GO(true, true, true); else CUSMC_FUSED_GO(true, true, false);
     } else if (philox) {

@@ -28,6 +28,12 @@ __global__ void __launch_bounds__(kUpdThreads)
 tile_update_kernel(const UpdateArgs u)
 {
     __shared__ UpdateSmem<kUpdThreads> us;
+    // let the next step kernel (a programmatic dependent, pf_fused_kernel) be launched now: its blocks wait
+    // at their griddepcontrol.wait until this grid has completed
+    asm volatile("griddepcontrol.launch_dependents;");
+    // launched itself as a programmatic dependent of the step kernel: resident during that kernel's last
+    // wave, it starts the moment the grid has completed (a no-op after any other kernel)
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     tile_update_block<kUpdThreads>(u, us);
 }
 
@@ -48,7 +54,16 @@ image_cdf_kernel(const unsigned long long *__restrict__ img, int64_t hdr_words, 
 
 int cusmc_launch_tile_update(cusmc_ctx *ctx, const UpdateArgs &u)
 {
-    tile_update_kernel<<<1, kUpdThreads, 0, ctx->stream>>>(u);
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(1);
+    lc.blockDim = dim3(kUpdThreads);
+    lc.stream = ctx->stream;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    CUSMC_CUDA(ctx, cudaLaunchKernelEx(&lc, tile_update_kernel, u));
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
