@@ -454,7 +454,6 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     release(f->x[1]);
     release(f->lw);
     release(f->anc);
-    release(f->cdf);
     release(f->slots);
     release(f->moments);
     release(f->img[0]);
@@ -491,8 +490,8 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     const int world = cfg->world <= 1 ? 1 : cfg->world;
     CUSMC_REQUIRE(ctx, world <= CUSMC_MAX_PEERS, "world exceeds CUSMC_MAX_PEERS");
     CUSMC_REQUIRE(ctx, world == 1 || (cfg->rank >= 0 && cfg->rank < world), "rank outside 0..world-1");
-    if (world > 1 && (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL || cfg->resampler == CUSMC_RESAMPLE_REJECTION))
-        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "the multinomial and rejection resamplers are single-GPU only");
+    if (world > 1 && cfg->resampler == CUSMC_RESAMPLE_REJECTION)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "the rejection resampler is single-GPU only");
     cusmc_filter *f = new (std::nothrow) cusmc_filter();
     if (!f) return cusmc_fail(ctx, CUSMC_ERR_CUDA, "out of host memory");
     f->ctx = ctx;
@@ -546,7 +545,6 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     alloc((void **)&f->x[1], sizeof(double) * P * d);
     alloc((void **)&f->lw, sizeof(double) * P);
     alloc((void **)&f->anc, sizeof(uint32_t) * P);
-    if (cfg->resampler == CUSMC_RESAMPLE_MULTINOMIAL) alloc((void **)&f->cdf, sizeof(uint64_t) * P);
     alloc((void **)&f->slots, sizeof(StepSlot) * (size_t)T);
     alloc((void **)&f->moments, sizeof(double) * (size_t)T * (2 + d));
     if (f->is_log) {
@@ -913,12 +911,14 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     if (cfg.resampler == CUSMC_RESAMPLE_REJECTION)
         return cusmc_launch_rejection(ctx, f->anc, f->lw, &f->slots[t - 1].lw_max, cfg.seed, (uint64_t)t, N,
                                       kRejectionCap);
-    // multinomial: materialise the global CDF from the image, one binary search per child
-    StepSlot *prev = &f->slots[t - 1];
-    CUSMC_CHECK(cusmc_launch_image_cdf(ctx, f->img[(t - 1) & 1], f->img_n, n, f->rank, f->cdf));
+    // multinomial: every child searches the global integer CDF on the weight images themselves (its own
+    // rank's or a peer's), tile_update.cu
     const double *um = dr.um_dev ? dr.um_dev + off * n : nullptr;
-    return cusmc_launch_multinomial(ctx, f->cdf, n, &prev->sum_q, um, cfg.seed, (uint64_t)t, 0, n, 0, f->anc,
-                                    &f->slots[t].degenerate);
+    const unsigned long long *const *peers =
+        sharded ? (const unsigned long long *const *)f->peer_img[(t - 1) & 1].table_dev : nullptr;
+    return cusmc_launch_multinomial_image(ctx, f->img[(t - 1) & 1], peers, f->img_n, n, f->lo, N, f->per, f->rank,
+                                          f->world, um, cfg.seed, (uint64_t)t, f->anc,
+                                          (unsigned long long *)&f->slots[t].degenerate);
 }
 
 // Propagate and reweight, fused (src/mcmc.cpp:298-307) -- and, for the normalised resamplers, the

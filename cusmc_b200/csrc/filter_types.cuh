@@ -45,7 +45,6 @@ struct cusmc_filter {
     double *x[2] = {nullptr, nullptr};
     double *lw = nullptr;
     uint32_t *anc = nullptr;
-    uint64_t *cdf = nullptr;
     StepSlot *slots = nullptr;
     double *moments = nullptr;        // T x (2 + d)
     void *persist = nullptr;          // scratch of the persistent-kernel run (pf_persist.cu)

@@ -26,6 +26,9 @@ struct UpdateArgs {
 };
 
 int cusmc_launch_tile_update(cusmc_ctx *ctx, const UpdateArgs &u);
-// cdf[i] = global inclusive fixed-point CDF of local particle i (n_alloc: the particle count the image was sized for)
-int cusmc_launch_image_cdf(cusmc_ctx *ctx, const unsigned long long *img, int64_t n_alloc, int64_t n, int rank,
-                           uint64_t *cdf);
+// multinomial ancestors of n local children (global slots i0 ..) searched on the weight images themselves, peers' included
+// (img_peer: device table of every rank's image, NULL on one GPU; n_alloc: the particle count the images were sized for)
+int cusmc_launch_multinomial_image(cusmc_ctx *ctx, const unsigned long long *img, const unsigned long long *const *img_peer,
+                                   int64_t n_alloc, int64_t n, int64_t i0, int64_t N_global, int64_t per_rank, int rank,
+                                   int world, const double *u, uint64_t seed, uint64_t step, uint32_t *a,
+                                   unsigned long long *degenerate_out);

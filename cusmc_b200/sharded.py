@@ -140,8 +140,8 @@ class ShardedParticleFilter:
         self.ctx, self.group = ctx, group
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
         self.plan = ShardPlan(N, self.world, self.rank)
-        if kw.get("resampler", "metropolis") in ("multinomial", "rejection") and self.world > 1:
-            raise ValueError("the multinomial and rejection resamplers are single-GPU only")
+        if kw.get("resampler", "metropolis") == "rejection" and self.world > 1:
+            raise ValueError("the rejection resampler is single-GPU only")
         ctx.use_torch_stream()
         exchange_timeout = kw.pop("exchange_timeout", None)
         self.pf = ParticleFilter(ctx, N, Y, m0, C0, F, G, V, W, rank=self.rank, world=self.world, **kw)
@@ -198,7 +198,7 @@ class ShardedParticleFilter:
         gathered = exchange_sums(self.slots_i64[t], self.rank, self.world, self._scratch, self.group)
         ck(lib.cusmc_filter_weigh_phase(h, t, 2, gathered.data_ptr()))
 
-    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, exchange="p2p"):
+    def run(self, xi0=None, xi=None, chi=None, u=None, j=None, u0=None, um=None, exchange="p2p"):
         """Injected draws (optional) are this rank's shard; omitted ones come from Philox keyed by
         the global slot.  Returns self; everything is enqueued on the stream.
 
@@ -208,7 +208,7 @@ class ShardedParticleFilter:
         torch.distributed collectives in between (the reference formulation of the exchange)."""
         import torch.distributed as dist
         lib, h, ck = self.ctx.lib, self.pf.h, self.ctx._check
-        dr = self.pf._make_draws(xi0=xi0, xi=xi, chi=chi, u=u, j=j, u0=u0, um=None)
+        dr = self.pf._make_draws(xi0=xi0, xi=xi, chi=chi, u=u, j=j, u0=u0, um=um)
         if exchange not in ("p2p", "nccl"):
             raise ValueError("exchange must be 'p2p' or 'nccl'")
         if exchange == "p2p" and self.world > 1:

@@ -367,7 +367,8 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
  *     begin;  weigh(0);  for t = 1 .. T-1:  resample(t);  propagate(t);  weigh(t)
  * For the normalised resamplers propagate(t) is the FUSED step kernel (every block finds the parents of
  * its tile of children in the weight image of step t - 1, propagates, reweights and leaves its tile of
- * the new image; systematic resample(t) is a no-op, multinomial materialises the CDF and searches it) and
+ * the new image; systematic resample(t) is a no-op, multinomial searches the images of step t - 1 -- its own
+ * rank's or a peer's -- rank, then tile, then particle, the global CDF never materialised) and
  * weigh(t) is the one-block tile update (global maximum, rescaled tile prefixes, total mass, constants of
  * step t + 1), followed by the moment pass when cfg.summary is set.  Reference mode ("metropolis",
  * "rejection") keeps densities: resample(t) runs the resampler, propagate(t) the one-particle-per-thread

@@ -56,6 +56,8 @@ def run_single(ctx, cfg):
     ("systematic", 2, 5001, 8),      # ragged: the last rank owns one slot fewer
     ("systematic", 3, 4097, 4),
     ("metropolis", 2, 4096, 2),
+    ("multinomial", 2, 6000, 2),     # every child searches the global CDF on its own or a peer's weight image
+    ("multinomial", 3, 4097, 4),
 ])
 def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d, exchange):
     """exchange = p2p: scalars through peer-memory mailboxes, whole run enqueued by the library;
