@@ -377,6 +377,20 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
             line["bound"] = "32-byte L2 sectors pulled by random 8-byte weight reads (peak: profiles/micro/l2_random.cu)"
         except Exception:
             line["bound"] = "32-byte L2 sectors pulled by random 8-byte weight reads (no measured peak committed)"
+
+        # N4: Metropolis-C2, the same rule with a warp's proposals confined to one 256-byte segment per iteration
+        def call_c2():
+            step[0] += 1
+            ctx.metropolis_c2_dev(a, w, B, seed=5, step=step[0])
+        us2 = _timed(torch, call_c2, 50) * 1e3
+        line["metropolis_c2"] = {"us_per_call": us2, "accept_tests_per_sec": N * B / (us2 * 1e-6),
+                                 "speedup_over_scattered_proposals": us / us2,
+                                 "note": "8 contiguous sectors per warp and iteration instead of 32 scattered ones (the "
+                                         "warp's segments are drawn by its lanes for each other, one Philox block per lane "
+                                         "and 32 iterations).  On B200 the whole weight vector sits in the 126 MB L2 and the "
+                                         "scattered kernel is issue-bound (Philox-10, 64-bit Lemire, fp64 division: ~190 "
+                                         "issue slots per warp-iteration), not sector-bound, so coalescing the proposals "
+                                         "does not pay here; the variant is kept for parity with the registry (SURVEY N4)"}
         return line
     guarded("metropolis_c4_resample", metropolis)
 

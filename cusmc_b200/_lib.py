@@ -25,7 +25,7 @@ flt = C.c_float
 OK, ERR_INVALID, ERR_CUDA, ERR_NOT_SPD, ERR_DEGENERATE, ERR_UNSUPPORTED, ERR_TIMEOUT = range(7)
 MVN, MVT = 0, 1
 SOA, AOS = 0, 1
-RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL, RESAMPLE_REJECTION = 0, 1, 2, 3
+RESAMPLE_METROPOLIS, RESAMPLE_SYSTEMATIC, RESAMPLE_MULTINOMIAL, RESAMPLE_REJECTION, RESAMPLE_METROPOLIS_C2 = 0, 1, 2, 3, 4
 MAX_DIM = 32
 MAX_PEERS = 8
 IPC_HANDLE_BYTES = 64
@@ -70,6 +70,7 @@ PROTOTYPES = {
     "cusmc_metropolis_hastings": (ci, [vp, vp, vp, vp, vp, u64, u64, i64, ci]),
     "cusmc_metropolis_hastings_dev": (ci, [vp, vp, vp, vp, vp, u64, u64, i64, ci, ci]),
     "cusmc_rejection_resample_dev": (ci, [vp, vp, vp, vp, u64, u64, i64, ci]),
+    "cusmc_metropolis_c2_dev": (ci, [vp, vp, vp, u64, u64, i64, ci, ci]),
     "cusmc_propagate_reweight_dev": (ci, [vp, ci, ci, vp, vp, vp, i64, i64, ci, ci, vp, vp, vp, vp,
                                           vp, flt, vp, vp, u64, u64, vp, vp]),
     "cusmc_weights_max_dev": (ci, [vp, vp, i64, vp]),

@@ -19,13 +19,14 @@ import math
 import numpy as np
 
 from . import _lib
-from ._lib import (AOS, MVN as KIND_MVN, MVT as KIND_MVT, RESAMPLE_METROPOLIS,
+from ._lib import (AOS, MVN as KIND_MVN, MVT as KIND_MVT, RESAMPLE_METROPOLIS, RESAMPLE_METROPOLIS_C2,
                    RESAMPLE_MULTINOMIAL, RESAMPLE_REJECTION, RESAMPLE_SYSTEMATIC, SOA, CusmcError,
                    FilterConfig, FilterDraws)
 
 _KINDS = {"mvn": KIND_MVN, "mvt": KIND_MVT}
 _RESAMPLERS = {"metropolis": RESAMPLE_METROPOLIS, "systematic": RESAMPLE_SYSTEMATIC,
-               "multinomial": RESAMPLE_MULTINOMIAL, "rejection": RESAMPLE_REJECTION}
+               "multinomial": RESAMPLE_MULTINOMIAL, "rejection": RESAMPLE_REJECTION,
+               "metropolis_c2": RESAMPLE_METROPOLIS_C2}
 
 
 def _kind(name):
@@ -295,6 +296,11 @@ class Context:
         self._check(self.lib.cusmc_metropolis_hastings_dev(self.h, _dp(a), _dp(w), _dp(u), _dp(j),
                                                            int(seed), int(step), N, int(B), int(is_log)))
 
+    def metropolis_c2_dev(self, a, w, B, seed=0, step=1, is_log=False, N=None):
+        """Metropolis-C2: the same rule, a warp's proposals confined to one 32-particle segment per iteration."""
+        self._check(self.lib.cusmc_metropolis_c2_dev(self.h, _dp(a), _dp(w), int(seed), int(step),
+                                                     w.numel() if N is None else N, int(B), int(is_log)))
+
     def rejection_resample_dev(self, a, w, w_max, seed=0, step=1, cap=4096, N=None):
         self._check(self.lib.cusmc_rejection_resample_dev(self.h, _dp(a), _dp(w), _dp(w_max), int(seed), int(step),
                                                           w.numel() if N is None else N, int(cap)))
@@ -447,7 +453,7 @@ class ParticleFilter:
         per = shard_size(self.N, int(world))
         self.n_local = self.N if world <= 1 else max(0, min(per, self.N - int(rank) * per))
         self.keep_history = bool(keep_history)
-        self.is_log = cfg.resampler not in (RESAMPLE_METROPOLIS, RESAMPLE_REJECTION)
+        self.is_log = cfg.resampler not in (RESAMPLE_METROPOLIS, RESAMPLE_REJECTION, RESAMPLE_METROPOLIS_C2)
         h = C.c_void_p()
         ctx._check(ctx.lib.cusmc_filter_create(ctx.h, C.byref(cfg), C.byref(h)))
         self.h = h

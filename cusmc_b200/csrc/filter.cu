@@ -482,7 +482,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     CUSMC_REQUIRE(ctx, cfg->d <= CUSMC_MAX_DIM && cfg->dy <= CUSMC_MAX_DIM, "d/dy exceed CUSMC_MAX_DIM");
     CUSMC_REQUIRE(ctx, cfg->Y && cfg->m0 && cfg->C0 && cfg->F && cfg->G && cfg->V && cfg->W, "model pointer is NULL");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->kind == CUSMC_MVT, "unknown distribution");
-    CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 3, "unknown resampler");
+    CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 4, "unknown resampler");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold >= 0.0 && cfg->ess_threshold <= 1.0, "ess_threshold must lie in [0, 1]");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold == 0.0 || cfg->resampler == CUSMC_RESAMPLE_SYSTEMATIC,
@@ -524,7 +524,8 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     if (f->cfg.B <= 0) f->cfg.B = 10;   // the reference hard-codes B = 10 (src/mcmc.cpp:291)
     // Reference mode (metropolis) keeps raw densities as weights like src/mcmc.cpp:212; the
     // normalised resamplers work on log-weights.
-    f->is_log = (cfg->resampler == CUSMC_RESAMPLE_METROPOLIS || cfg->resampler == CUSMC_RESAMPLE_REJECTION) ? 0 : 1;
+    f->is_log = (cfg->resampler == CUSMC_RESAMPLE_METROPOLIS || cfg->resampler == CUSMC_RESAMPLE_REJECTION ||
+                 cfg->resampler == CUSMC_RESAMPLE_METROPOLIS_C2) ? 0 : 1;
     f->shift = cusmc_fixed_shift(N);
     int rc = eigen_factor(ctx, f->C0.data(), d, f->Qc0);
     if (rc == CUSMC_OK) rc = eigen_factor(ctx, f->W.data(), d, f->Qw);
@@ -901,11 +902,12 @@ extern "C" int cusmc_filter_resample(cusmc_filter *f, int t)
     const int64_t n = f->n, N = cfg.N;
     const size_t off = (size_t)(t - 1);
     const bool sharded = f->world > 1;
-    if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS) {
+    if (cfg.resampler == CUSMC_RESAMPLE_METROPOLIS || cfg.resampler == CUSMC_RESAMPLE_METROPOLIS_C2) {
         const double *u = dr.u_dev ? dr.u_dev + off * n * cfg.B : nullptr;
         const uint32_t *j = dr.j_dev ? dr.j_dev + off * n * cfg.B : nullptr;
         return cusmc_launch_metropolis(ctx, f->anc, f->lw, u, j, cfg.seed, (uint64_t)t, N, cfg.B, f->is_log,
-                                       f->lo, n, sharded ? &f->peer_lw : nullptr);
+                                       f->lo, n, sharded ? &f->peer_lw : nullptr,
+                                       cfg.resampler == CUSMC_RESAMPLE_METROPOLIS_C2);
     }
     if (cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC) return CUSMC_OK;
     if (cfg.resampler == CUSMC_RESAMPLE_REJECTION)

@@ -38,28 +38,61 @@ __device__ __forceinline__ double weight_at(const double *__restrict__ w, const 
     return __ldg(w + idx);
 }
 
-template <bool PREDRAWN, bool PEERS>
+// C2 = true: the Metropolis-C2 variant (Dulger et al., "Memory coalescing for parallelised Metropolis
+// resampling"): at every iteration the 32 particles of a warp draw their proposals from ONE
+// common 32-particle segment of the weight vector (256 bytes: 8 sectors instead of 32 scattered ones), a
+// fresh segment per iteration.  The segment is the one holding a uniform index drawn from a counter keyed
+// by (i / 32, n) -- so it is picked with probability proportional to its length and every proposal is
+// still uniform over 0 .. N-1 -- and the lane's own draw picks the slot inside it.  oracle:
+// orc_rng_metropolis_c2.
+template <bool PREDRAWN, bool PEERS, bool C2>
 __global__ void __launch_bounds__(kThreads)
 metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const PeerWeights pw,
                   const double *__restrict__ u, const uint32_t *__restrict__ j, uint64_t seed,
                   uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out)
 {
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-    if (t >= n_out) return;
+    const bool live = t < n_out;
+    if (!C2 && !live) return;              // (C2 keeps whole warps alive: lanes draw segments for each other)
     const int64_t i = i0 + t;              // global particle index (i0 = 0 on one GPU)
     uint32_t k = (uint32_t)i;
-    double wk = weight_at<PEERS>(w, pw, (uint32_t)i);
+    double wk = live ? weight_at<PEERS>(w, pw, (uint32_t)i) : 0.0;
+    // C2: the segment of (group, n) is the same for the 32 particles of a group.  When the warp IS the
+    // group (i0 a multiple of 32), lane l draws the segments of iterations nb + l for everybody, 32
+    // iterations per Philox block per lane, handed round by shuffles; otherwise every lane draws its own.
+    const uint32_t lane = threadIdx.x & 31;
+    const bool shared_draw = C2 && (i0 & 31) == 0;
+    uint32_t seg_mine = 0;
+    auto segment_of = [&](int n) {
+        const cusmc_u32x4 rs = cusmc_rng(seed, CUSMC_STREAM_SEGMENT, step, (uint64_t)i >> 5, (uint32_t)n);
+        return (uint32_t)cusmc_uint_below(rs.v[0], rs.v[1], (uint64_t)N) & ~31u;
+    };
     for (int n = 0; n < B; ++n) {
-        double un;
-        uint32_t jn;
+        double un = 0.0;
+        uint32_t jn = 0;
         if (PREDRAWN) {
             un = __ldg(u + t * B + n);
             jn = __ldg(j + t * B + n);
         } else {
+            uint32_t first = 0;
+            if (C2) {
+                if (shared_draw) {
+                    if ((n & 31) == 0 && n + (int)lane < B) seg_mine = segment_of(n + (int)lane);
+                    first = __shfl_sync(0xffffffffu, seg_mine, n & 31);
+                } else {
+                    first = segment_of(n);
+                }
+            }
             const cusmc_u32x4 r = cusmc_rng(seed, CUSMC_STREAM_METROPOLIS, step, (uint64_t)i, (uint32_t)n);
             un = cusmc_u01(r.v[0], r.v[1]);
-            jn = (uint32_t)cusmc_uint_below(r.v[2], r.v[3], (uint64_t)N);
+            if (C2) {
+                const uint64_t len = (uint64_t)N - first < 32u ? (uint64_t)N - first : 32u;
+                jn = first + (uint32_t)cusmc_uint_below(r.v[2], r.v[3], len);
+            } else {
+                jn = (uint32_t)cusmc_uint_below(r.v[2], r.v[3], (uint64_t)N);
+            }
         }
+        if (C2 && !live) continue;
         const double wj = weight_at<PEERS>(w, pw, jn);
         // linear: u <= w_j / w_k (0/0 = NaN rejects, x/0 = inf accepts, as on the CPU);
         // log   : u <= exp(lw_j - lw_k) with the reproducible exp.
@@ -71,7 +104,7 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const 
             wk = wj;
         }
     }
-    a[t] = k;
+    if (live) a[t] = k;
 }
 
 // Rejection resampler: the unbiased relative of the rule above (no counterpart in the reference; the
@@ -540,22 +573,25 @@ int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n)
 
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers)
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers, bool c2)
 {
     if (n_out == 0) return CUSMC_OK;
     const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
     PeerWeights pw{};
+#define CUSMC_METRO_GO(PR, PE, C2) \
+    metropolis_kernel<PR, PE, C2><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out)
     if (peers) {
         pw.w = (const double *const *)peers->table_dev;
         pw.per_rank = make_fast_div((uint32_t)peers->per_rank);
-        if (u)
-            metropolis_kernel<true, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
-        else
-            metropolis_kernel<false, true><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
-    } else if (u)
-        metropolis_kernel<true, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
-    else
-        metropolis_kernel<false, false><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out);
+        if (u) CUSMC_METRO_GO(true, true, false);          // injected proposals are the caller's, whatever the variant
+        else if (c2) CUSMC_METRO_GO(false, true, true);
+        else CUSMC_METRO_GO(false, true, false);
+    } else {
+        if (u) CUSMC_METRO_GO(true, false, false);
+        else if (c2) CUSMC_METRO_GO(false, false, true);
+        else CUSMC_METRO_GO(false, false, false);
+    }
+#undef CUSMC_METRO_GO
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }
@@ -667,7 +703,17 @@ extern "C" int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, co
     CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
     CUSMC_REQUIRE(ctx, (u_dev == nullptr) == (j_dev == nullptr), "u and j must both be given or both NULL");
     CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
-    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr);
+    return cusmc_launch_metropolis(ctx, a_dev, w_dev, u_dev, j_dev, seed, step, N, B, is_log, 0, N, nullptr, false);
+}
+
+extern "C" int cusmc_metropolis_c2_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev, uint64_t seed, uint64_t step,
+                                       int64_t N, int B, int is_log)
+{
+    CUSMC_ENTER(ctx);
+    CUSMC_REQUIRE(ctx, N >= 0 && B >= 0, "N, B must be non-negative");
+    CUSMC_REQUIRE(ctx, N == 0 || (a_dev && w_dev), "a/w is NULL");
+    CUSMC_REQUIRE(ctx, N <= 0xFFFFFFFFll, "N exceeds the 32-bit ancestor range");
+    return cusmc_launch_metropolis(ctx, a_dev, w_dev, nullptr, nullptr, seed, step, N, B, is_log, 0, N, nullptr, true);
 }
 
 extern "C" int cusmc_rejection_resample_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev,

@@ -6,7 +6,7 @@
 int cusmc_fill_double(cusmc_ctx *ctx, double *p, double v, int n);
 int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *u,
                             const uint32_t *j, uint64_t seed, uint64_t step, int64_t N, int B,
-                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers);
+                            int is_log, int64_t i0, int64_t n_out, const CusmcPeers *peers, bool c2 = false);
 int cusmc_launch_weights_max(cusmc_ctx *ctx, const double *w, int64_t N, double *max_dev);
 int cusmc_launch_rejection(cusmc_ctx *ctx, uint32_t *a, const double *w, const double *wmax_dev, uint64_t seed,
                            uint64_t step, int64_t N, int cap);

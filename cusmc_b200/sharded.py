@@ -150,7 +150,7 @@ class ShardedParticleFilter:
             exchange_timeout = 2.0 if torch.cuda.device_count() >= self.world else 10.0
         ctx._check(ctx.lib.cusmc_filter_set_exchange_timeout(self.pf.h, float(exchange_timeout)))
         self.T, self.d, self.N = self.pf.T, self.pf.d, int(N)
-        self.is_log = kw.get("resampler", "metropolis") not in ("metropolis", "rejection")
+        self.is_log = kw.get("resampler", "metropolis") not in ("metropolis", "rejection", "metropolis_c2")
         self.summary_on = bool(kw.get("summary", True))
         lib, h = ctx.lib, self.pf.h
         if self.world > 1:

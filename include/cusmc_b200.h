@@ -54,7 +54,8 @@ enum cusmc_resampler {                                    /* Resamplers[...], sr
     CUSMC_RESAMPLE_METROPOLIS = 0,   /* the reference's only resampler */
     CUSMC_RESAMPLE_SYSTEMATIC = 1,
     CUSMC_RESAMPLE_MULTINOMIAL = 2,
-    CUSMC_RESAMPLE_REJECTION = 3     /* unbiased relative of the reference's resampler: see cusmc_rejection_resample_dev */
+    CUSMC_RESAMPLE_REJECTION = 3,    /* unbiased relative of the reference's resampler: see cusmc_rejection_resample_dev */
+    CUSMC_RESAMPLE_METROPOLIS_C2 = 4 /* the reference's rule with warp-coalesced proposals: see cusmc_metropolis_c2_dev */
 };
 
 #define CUSMC_MAX_DIM 32            /* largest d with an unrolled kernel */
@@ -155,6 +156,19 @@ int cusmc_metropolis_hastings(cusmc_ctx *ctx, uint32_t *a, const double *w,
 int cusmc_metropolis_hastings_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev,
                                   const double *u_dev, const uint32_t *j_dev,
                                   uint64_t seed, uint64_t step, int64_t N, int B, int is_log);
+/*
+ * Metropolis-C2 (Dulger et al., "Memory coalescing for parallelised Metropolis resampling"; the same
+ * `resampler_f` seam, inst/include/types.hpp:32): the rule of Sampler::metropolis_hastings
+ * (src/samplers.cpp:21-35) with the proposals of the 32 particles i0 .. i0 + 31 of a warp confined, at each
+ * iteration n, to ONE 32-particle segment of the weight vector -- the segment [first, first + len) holding a
+ * uniform index drawn from Philox (seed, CUSMC_STREAM_SEGMENT, step, i / 32, n), so segments are picked in
+ * proportion to their length and each proposal is still uniform over 0 .. N-1; j_n = first + (the lane's
+ * own 64 Metropolis bits scaled to len), u_n the lane's own uniform.  A warp's 32 scattered 32-byte sectors
+ * per iteration become 8 contiguous ones.  Draws are device-side only (a host reproduces them from the
+ * counters; oracle: orc_rng_metropolis_c2).
+ */
+int cusmc_metropolis_c2_dev(cusmc_ctx *ctx, uint32_t *a_dev, const double *w_dev, uint64_t seed, uint64_t step,
+                            int64_t N, int B, int is_log);
 /*
  * Rejection resampler (Murray, Lee & Jacob 2016, the unbiased relative of the reference's B-step
  * Metropolis rule, same `resampler_f` seam, inst/include/types.hpp:32): for each i, k = i; attempt n =
@@ -371,7 +385,7 @@ int cusmc_filter_run(cusmc_filter *f, const cusmc_filter_draws *draws);
  * rank's or a peer's -- rank, then tile, then particle, the global CDF never materialised) and
  * weigh(t) is the one-block tile update (global maximum, rescaled tile prefixes, total mass, constants of
  * step t + 1), followed by the moment pass when cfg.summary is set.  Reference mode ("metropolis",
- * "rejection") keeps densities: resample(t) runs the resampler, propagate(t) the one-particle-per-thread
+ * "metropolis_c2", "rejection") keeps densities: resample(t) runs the resampler, propagate(t) the one-particle-per-thread
  * step kernel.
  * A sharded filter (cfg.world > 1) is either run by cusmc_filter_run_sharded (scalar exchanges inside the
  * update kernel) or driven through these phases by a binding that carries the scalars itself

@@ -24,7 +24,9 @@ enum cusmc_rng_stream {
     CUSMC_STREAM_MULTINOMIAL = 3,
     CUSMC_STREAM_CHAIN_Z = 4,    /* index = chain, step = MH step, sub = component quad */
     CUSMC_STREAM_CHAIN_U = 5,
-    CUSMC_STREAM_INIT = 6
+    CUSMC_STREAM_INIT = 6,
+    CUSMC_STREAM_OFFSET = 7,     /* the systematic offset u0 of a step: index = sub = 0 */
+    CUSMC_STREAM_SEGMENT = 8     /* Metropolis-C2: index = i / 32 (the warp), sub = n: out[0..1] -> the proposal segment */
 };
 
 typedef struct cusmc_u32x4 {

@@ -1019,6 +1019,22 @@ void orc_rng_metropolis(uint64_t seed, uint64_t step, uint64_t index, uint32_t n
     *j = (uint32_t)(((unsigned __int128)bits * N) >> 64);
 }
 
+/* Metropolis-C2 proposals (include/cusmc_b200.h, cusmc_metropolis_c2_dev): the segment comes from the
+ * counter of the particle's group of 32, the slot inside it and the uniform from the particle's own. */
+void orc_rng_metropolis_c2(uint64_t seed, uint64_t step, uint64_t index, uint32_t n, uint64_t N,
+                           double *u, uint32_t *j)
+{
+    uint32_t r[4], rs[4];
+    rng_block(seed, 0, step, index, n, r);
+    rng_block(seed, 8, step, index >> 5, n, rs);
+    *u = u01_from(r[0], r[1], 0);
+    uint64_t sbits = ((uint64_t)rs[0] << 32) | rs[1];
+    uint32_t first = (uint32_t)(((unsigned __int128)sbits * N) >> 64) & ~31u;
+    uint64_t len = N - first < 32 ? N - first : 32;
+    uint64_t bits = ((uint64_t)r[2] << 32) | r[3];
+    *j = first + (uint32_t)(((unsigned __int128)bits * len) >> 64);
+}
+
 /* Single-precision deterministic log / sincospi / Box-Muller: mirror of the kernels' default
  * normal generator (include/cusmc_detmath.h, cusmc_philox.h). */
 static float bits_to_float(uint32_t b) { float f; memcpy(&f, &b, 4); return f; }
@@ -1186,7 +1202,7 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
     if (tile <= 0) tile = 2048;       /* the library's tile (kTile); the persistent kernel passes its own */
     size_t Nd = (size_t)N * d;
     double *w_old = (double *)malloc(sizeof(double) * N);
-    int is_log = resampler != 0 && resampler != 3;
+    int is_log = resampler != 0 && resampler != 3 && resampler != 4;
     double *xa = (double *)malloc(sizeof(double) * Nd), *xb = (double *)malloc(sizeof(double) * Nd);
     double *w = (double *)malloc(sizeof(double) * N), *noise = (double *)malloc(sizeof(double) * Nd);
     uint32_t *a = (uint32_t *)malloc(sizeof(uint32_t) * N);
@@ -1214,14 +1230,15 @@ int orc_filter_det(int dist, int resampler, int64_t N, int d, int dy, int T, int
         int do_resample = t > 0;
         if (t > 0) {
             size_t off = (size_t)(t - 1);
-            if (resampler == 0) {
+            if (resampler == 0 || resampler == 4) {
                 const double *ut = u ? u + off * N * B : ub;
                 const uint32_t *jt = j ? j + off * N * B : jb;
                 if (!u)
                     for (int64_t i = 0; i < N; ++i)
                         for (int n = 0; n < B; ++n)
-                            orc_rng_metropolis(seed, (uint64_t)t, (uint64_t)i, (uint32_t)n, (uint64_t)N,
-                                               &ub[(size_t)i * B + n], &jb[(size_t)i * B + n]);
+                            (resampler == 4 ? orc_rng_metropolis_c2 : orc_rng_metropolis)(
+                                seed, (uint64_t)t, (uint64_t)i, (uint32_t)n, (uint64_t)N,
+                                &ub[(size_t)i * B + n], &jb[(size_t)i * B + n]);
                 orc_metropolis_hastings(a, w, ut, jt, N, B);
             } else if (resampler == 3) {
                 double m = -INFINITY;           /* the kernels' atomic max over finite weights */

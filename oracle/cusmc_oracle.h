@@ -207,10 +207,14 @@ void orc_rng_normal4(uint64_t seed, int stream, uint64_t step, uint64_t index, u
 double orc_rng_u01(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub);
 void orc_rng_metropolis(uint64_t seed, uint64_t step, uint64_t index, uint32_t n, uint64_t N,
                         double *u, uint32_t *j);
+/* Metropolis-C2: the proposal of particle `index` at iteration n lies in the 32-particle segment its group
+ * index / 32 drew for that iteration (extended; mirrors cusmc_metropolis_c2_dev). */
+void orc_rng_metropolis_c2(uint64_t seed, uint64_t step, uint64_t index, uint32_t n, uint64_t N,
+                           double *u, uint32_t *j);
 /* Fills xi (AoS N x d) with the normals the step kernel draws for (seed, stream, step). */
 void orc_rng_fill_normals(uint64_t seed, int stream, uint64_t step, int64_t i0, int64_t N, int d, double *xi);
 /* Whole filter in production order.  resampler: 0 metropolis (linear weights, as the
- * reference), 1 systematic, 2 multinomial (log weights, block-relative fixed point), 3 rejection (linear
+ * reference), 1 systematic, 2 multinomial (log weights, block-relative fixed point), 3 rejection / 4 Metropolis-C2 (linear
  * weights, device-drawn only).  Draw arrays may
  * be NULL -> Philox mirror with `seed`.  Layouts as orc_filter_metropolis; u0 [(T-1)], um [(T-1)*N].
  * tile: tile size of the weight image (<= 0: 2048, the library's; the persistent kernel uses its own).

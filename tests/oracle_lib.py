@@ -124,6 +124,8 @@ class Oracle:
         L.orc_rng_u01.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_uint64, C.c_uint32]
         L.orc_rng_metropolis.restype = None
         L.orc_rng_metropolis.argtypes = [C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint64, _dp, _u32p]
+        L.orc_rng_metropolis_c2.restype = None
+        L.orc_rng_metropolis_c2.argtypes = L.orc_rng_metropolis.argtypes
         L.orc_rng_fill_normals.restype = None
         L.orc_rng_fill_normals.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_int64, C.c_int64, C.c_int, _dp]
         L.orc_filter_det.restype = C.c_int
@@ -410,13 +412,15 @@ class Oracle:
     def rng_u01(self, seed, stream, step, index, sub=0):
         return self.lib.orc_rng_u01(int(seed), int(stream), int(step), int(index), int(sub))
 
-    def rng_metropolis(self, seed, step, N, B):
+    def rng_metropolis(self, seed, step, N, B, c2=False):
+        """(u, j) [N][B] the Metropolis resampler draws on the device; c2: the Metropolis-C2 proposals."""
         u = np.empty((N, B))
         j = np.empty((N, B), dtype=np.uint32)
         uu, jj = C.c_double(), C.c_uint32()
+        draw = self.lib.orc_rng_metropolis_c2 if c2 else self.lib.orc_rng_metropolis
         for i in range(N):
             for n in range(B):
-                self.lib.orc_rng_metropolis(int(seed), int(step), i, n, N, C.byref(uu), C.byref(jj))
+                draw(int(seed), int(step), i, n, N, C.byref(uu), C.byref(jj))
                 u[i, n], j[i, n] = uu.value, jj.value
         return u, j
 
@@ -427,7 +431,7 @@ class Oracle:
         Y = np.asarray(Y, dtype=np.float64)
         dy, T = Y.shape
         d = np.asarray(G).shape[0]
-        rs = {"metropolis": 0, "systematic": 1, "multinomial": 2, "rejection": 3}[resampler]
+        rs = {"metropolis": 0, "systematic": 1, "multinomial": 2, "rejection": 3, "metropolis_c2": 4}[resampler]
         opt = lambda a: None if a is None else f64(a)
         j_ = None if j is None else np.ascontiguousarray(j, dtype=np.uint32)
         xh = np.zeros((T, N, d))

@@ -676,6 +676,50 @@ def test_rejection_resampler(ctx, orc):
     assert np.all(np.diff(nuq) >= 0) and nuq[-1] == Nf and nuq[0] < Nf
 
 
+def test_metropolis_c2_resampler(ctx, orc):
+    """Metropolis-C2 (N4): the reference's accept rule with a warp's proposals confined to one 32-particle
+    segment per iteration.  Bit-exact against the oracle's mirror of the counters (ragged N: the last
+    segment is short), proposals uniform over 0 .. N-1, and a whole filter run bit for bit."""
+    import torch
+    rng = np.random.default_rng(707)
+    for N, B in ((5000, 10), (4099, 7), (33, 4)):
+        w = rng.random(N) ** 4
+        w[rng.random(N) < 0.05] = 0.0
+        u, j = orc.rng_metropolis(13, 2, N, B, c2=True)
+        # the structure: the 32 particles of a group share their segment at every iteration
+        seg = j // 32
+        for g0 in range(0, N, 32):
+            assert np.all(seg[g0:g0 + 32] == seg[g0]), (N, g0)
+        assert j.max() < N
+        a = torch.empty(N, dtype=torch.int32, device="cuda")
+        ctx.metropolis_c2_dev(a, torch_dev(w), B, seed=13, step=2)
+        ctx.synchronize()
+        assert np.array_equal(a.cpu().numpy().view(np.uint32), orc.metropolis_hastings(w, u, j)), (N, B)
+    # in law: ancestors follow the weights as well as the plain B-step rule's do (same bias allowance)
+    N, B = 200000, 30
+    w = rng.random(N)
+    a = torch.empty(N, dtype=torch.int32, device="cuda")
+    ctx.metropolis_c2_dev(a, torch_dev(w), B, seed=5, step=1)
+    ctx.synchronize()
+    got = a.cpu().numpy().view(np.uint32)
+    bins = np.add.reduceat(np.bincount(got, minlength=N), np.arange(0, N, 2000))
+    want = N * np.add.reduceat(w, np.arange(0, N, 2000)) / w.sum()
+    # (the 32 particles of a group propose from common segments: bin counts up to 32 x Poisson)
+    assert np.all(np.abs(bins - want) < 6 * np.sqrt(32 * want) + 0.02 * want)
+    # inside the filter (reference-mode densities)
+    d, Nf, T = 2, 4000, 8
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=Nf, Y=Y, resampler="metropolis_c2", seed=22, keep_history=True, reproducible_rng=True, **md)
+    h = pf.run().history()
+    pf.close()
+    ref = orc.filter_det("mvn", "metropolis_c2", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), Nf, seed=22)
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+    assert relerr(h["w"], ref["w"]) < 1e-13
+
+
 def test_lineage_of_a_systematic_run(ctx):
     d, N, T = 2, 20000, 12
     rng = np.random.default_rng(5)

@@ -56,6 +56,7 @@ def run_single(ctx, cfg):
     ("systematic", 2, 5001, 8),      # ragged: the last rank owns one slot fewer
     ("systematic", 3, 4097, 4),
     ("metropolis", 2, 4096, 2),
+    ("metropolis_c2", 2, 4096, 2),
     ("multinomial", 2, 6000, 2),     # every child searches the global CDF on its own or a peer's weight image
     ("multinomial", 3, 4097, 4),
 ])
@@ -73,7 +74,7 @@ def test_sharded_equals_single_gpu_bitwise(ctx, tmp_path, resampler, world, N, d
     assert np.array_equal(w, h.get("lw", h["w"])[-1])      # raw weights: log-weights / densities
     assert all(int(p["status"]) == 0 for p in parts)      # no spin-wait timed out
     for p in parts:          # every rank reports the GLOBAL summary
-        if resampler != "metropolis":
+        if not resampler.startswith("metropolis"):
             assert np.allclose(p["ess"], s["ess"], rtol=1e-12)
             assert np.allclose(p["loglik"], s["loglik"], rtol=1e-12, atol=1e-12)
         assert np.allclose(p["mean"], s["mean"], rtol=1e-9, atol=1e-12)

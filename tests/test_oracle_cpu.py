@@ -390,3 +390,22 @@ def test_tile_image_definition(orc):
     lw2 = np.concatenate([np.full(64, -60.0), np.zeros(64)])
     C, T, _, _ = orc.tile_image(lw2, 64)
     assert int(C[63]) == 0 and T == 64 << orc.fixed_shift(128)
+
+
+def test_metropolis_c2_proposals(orc):
+    """Metropolis-C2 (include/cusmc_b200.h): a group of 32 particles shares its proposal segment at every
+    iteration, segments are picked in proportion to their length, so proposals are uniform over 0 .. N-1."""
+    N, B = 4099, 40                       # ragged: the last segment holds 3 particles
+    u, j = orc.rng_metropolis(3, 1, N, B, c2=True)
+    assert j.max() < N and u.min() >= 0.0 and u.max() < 1.0
+    seg = j // 32
+    for g0 in range(0, N, 32):
+        assert np.all(seg[g0:g0 + 32] == seg[g0])
+    assert len(np.unique(seg[::32])) > 100                 # a fresh segment per (group, iteration)
+    counts = np.bincount(j.ravel(), minlength=N)
+    bins = np.add.reduceat(counts, np.arange(0, N, 128))
+    want = np.diff(np.append(np.arange(0, N, 128), N)) * (B * N / N)
+    # proposals inside a group are correlated (common segment): the bin variance is up to 32 x Poisson
+    assert np.all(np.abs(bins - want) < 6 * np.sqrt(32 * want))
+    u1, j1 = orc.rng_metropolis(3, 1, N, B)
+    assert np.array_equal(u, u1) and not np.array_equal(j, j1)      # the lane's own uniform is the plain rule's
