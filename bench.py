@@ -549,7 +549,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
     N = per * world
     I = np.eye(d)
     try:
-        T = 11 if quick else 41
+        T = 11 if quick else 100
         Y = np.random.default_rng(5000).standard_normal((d, T))
         pf = cusmc_b200.ShardedParticleFilter(ctx, N, Y, np.zeros(d), I, I, 0.9 * I, I, I,
                                               resampler="systematic", seed=2, summary=False)

@@ -495,6 +495,31 @@ def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d, kind, nu):
     assert np.allclose(s["mean"], mean, rtol=1e-10, atol=1e-12)
 
 
+@pytest.mark.parametrize("reproducible", [False, True])
+@pytest.mark.parametrize("nu,d", [(5.0, 8), (2.5, 3), (1.5, 2)])
+def test_mvt_device_noise_is_student_t(ctx, reproducible, nu, d):
+    """Device-drawn "mvt" noise inside the filter, both generators (the throughput one draws its chi factors
+    with chi_fast for nu >= 2): with G = 0 and W = C0 = I every component of x_0 and x_1 is chi z ~ t_nu.
+    Kolmogorov-Smirnov per component, and the chi factors of different components are independent."""
+    from scipy import stats
+    N, T = 120000, 2
+    I = np.eye(d)
+    Y = np.zeros((d, T))
+    pf = ctx.filter(N=N, Y=Y, m0=np.zeros(d), C0=I, F=I, G=np.zeros((d, d)), V=100.0 * I, W=I, resampler="systematic",
+                    distribution="mvt", df=nu, seed=77, keep_history=True, reproducible_rng=reproducible)
+    h = pf.run().history()
+    pf.close()
+    for t in range(T):
+        x = h["x"][t]
+        assert np.all(np.isfinite(x))
+        for k in range(d):
+            assert stats.kstest(x[:, k], "t", args=(nu,)).pvalue > 1e-3, (t, k)
+        # |x_k| of two components would correlate if they shared a chi factor
+        r = np.corrcoef(np.log(np.abs(x) + 1e-300).T)
+        assert np.all(np.abs(r - np.eye(d)) < 0.02), (t, r)
+    assert not np.array_equal(h["x"][0], h["x"][1])
+
+
 def test_mvt_normal_init_switch(ctx, orc):
     """mvt_normal_init = 1 keeps round 1's Normal start; the default draws x_0 with chi factors."""
     rng = np.random.default_rng(3)
