@@ -44,6 +44,19 @@ if which in ("all", "pf"):
     ctx.synchronize()
     pf.close()
 
+if which in ("all", "pfmore"):
+    # the same shard with Student-t noise / a dense transition / the multinomial search (T = 3: two steps each)
+    d = 8
+    I = np.eye(d)
+    Y = np.random.default_rng(5000).standard_normal((d, 3))
+    Gd = 0.9 * np.linalg.qr(np.random.default_rng(11).standard_normal((d, d)))[0]
+    for kw in (dict(G=0.9 * I, distribution="mvt", df=5.0), dict(G=Gd), dict(G=0.9 * I, resampler="multinomial")):
+        kw.setdefault("resampler", "systematic")
+        pf = ctx.filter(N=8 << 20, Y=Y, m0=np.zeros(d), C0=I, F=I, V=I, W=I, seed=2, summary=False, **kw)
+        pf.run()
+        ctx.synchronize()
+        pf.close()
+
 if which in ("all", "mh"):
     Cn, d, steps = 65536, 32, 20
     A = torch.randn((Cn, d, d), dtype=torch.float64, device="cuda")
@@ -61,6 +74,7 @@ if which in ("all", "metropolis"):
     a = torch.empty(N, dtype=torch.int32, device="cuda")
     for r in range(2):
         ctx.metropolis_hastings_dev(a, w, B, seed=5, step=1 + r)
+    ctx.metropolis_c2_dev(a, w, B, seed=5, step=3)
     torch.cuda.synchronize()
 
 if which in ("all", "perpoint"):

@@ -5,7 +5,7 @@
 set -x; mkdir -p gpurun_out
 python profiles/prof_driver.py all > gpurun_out/r02_prof_plain.log 2>&1 &&
 ncu --set full --clock-control none --import-source on \
-    -k regex:"density_soa|pf_fused|tile_update|pf_persistent|mh_chains|mh_general|perpoint|metropolis" -c 24 \
+    -k regex:"density_soa|pf_fused|tile_update|pf_persistent|mh_chains|mh_general|perpoint|metropolis|multinomial" -c 56 \
     -o gpurun_out/r02_final python profiles/prof_driver.py all > gpurun_out/r02_prof_ncu.log 2>&1
 python bench.py --steps 3 --warmup 3 --quick > gpurun_out/r02_bench_quick.json 2> gpurun_out/r02_bench_quick.err &&
 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/r02_launches.csv \
