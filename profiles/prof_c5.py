@@ -1,5 +1,5 @@
 """One short C5-shard (d = 8, 8 Mi particles) or C4 (d = 2, 10^6) filter run for ncu captures.
-usage: python profiles/prof_c5.py [c5|c4|c5dense] [T]"""
+usage: python profiles/prof_c5.py [c5|c4|c5dense] [T] [N]"""
 import os
 import sys
 
@@ -25,10 +25,12 @@ else:
     I = np.eye(d)
     Y = np.loadtxt(os.path.join(ROOT, "tests", "golden", "y_t.csv"), delimiter=",", skiprows=1).T[:, :T]
     md = dict(m0=np.zeros(d), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
+if len(sys.argv) > 3:
+    N = int(sys.argv[3])
 pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=2, summary=False, **md)
 pf.run()
 ctx.synchronize()
 pf.run()
 ms = pf.last_ms
-print("%s: %.1f us/step" % (which, ms / (T - 1) * 1e3))
+print("%s N=%d: %.1f us/step, %.3f ns/particle-step" % (which, N, ms / (T - 1) * 1e3, ms / (T - 1) * 1e6 / N))
 pf.close()
