@@ -14,8 +14,11 @@ import sys
 
 rep, kre = sys.argv[1], sys.argv[2]
 skip = int(sys.argv[3]) if len(sys.argv) > 3 else 0
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
-                     capture_output=True, text=True).stdout
+if rep.endswith(".csv"):        # a source page exported on the GPU box (run_r02_profiles.sh); the regex was applied there
+    out = open(rep).read()
+else:
+    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--kernel-name", "regex:" + kre],
+                         capture_output=True, text=True).stdout
 blocks = []
 for r in csv.reader(io.StringIO(out)):
     if r and r[0] == "Kernel Name":
