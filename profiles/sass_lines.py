@@ -31,7 +31,7 @@ for line in sass.splitlines():
     if m:
         cur = (os.path.basename(m.group(1)), int(m.group(2)))
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m:
         per_line[cur] += 1
         ops[cur][m.group(2)] += 1

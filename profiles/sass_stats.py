@@ -25,7 +25,7 @@ for line in sass.splitlines():
         cur = m.group(1)
         stats[cur] = collections.Counter()
         continue
-    m = re.match(r"\s+/\*[0-9a-f]{4}\*/\s+(@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", line)
+    m = re.match(r"\s+/\*[0-9a-f]{4,}\*/\s+(@!?U?P\w+\s+)?([A-Z][A-Z0-9_]*)", line)
     if m and cur:
         stats[cur][m.group(2)] += 1
 names = list(stats)
