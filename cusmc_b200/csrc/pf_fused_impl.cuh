@@ -95,22 +95,33 @@ __device__ __forceinline__ void stg256u(unsigned long long *p, unsigned long lon
 // parent with children leaves ONE marker -- its index at the slot of its first child inside the tile;
 // a block-wide running maximum then spreads the markers over the slots (parents and slots both
 // ascend), so family sizes never matter: no per-child loops, no divergence on heavy parents.
-template <bool PEERS, bool COH>
+//
+// TAB: the tile fields F / P / Sp of the parents' image sit in SHARED memory (the persistent kernel, where
+// every block runs the tile update itself after the grid barrier): the prefix search and the fields of a
+// walked tile cost no L2 round trip; only the CDF words of the walked tiles are fetched.
+struct TileTab {
+    const unsigned long long *F, *P, *Sp;
+};
+
+template <bool PEERS, bool COH, bool TAB = false>
 __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepConsts &sc, uint32_t i_a, uint32_t n_tile,
                                                uint32_t *__restrict__ s_anc, unsigned long long *__restrict__ s_q,
-                                               uint32_t *__restrict__ s_warp)
+                                               uint32_t *__restrict__ s_warp, const TileTab &tab = TileTab{})
 {
+    static_assert(!(TAB && PEERS), "tile tables in shared memory: one rank");
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint64_t T = sc.T, r0 = sc.r0, Ng = fa.N_global;
     const double ngt = sc.ng_over_t, r0t = sc.r0_over_t;
     const uint32_t i_b = i_a + n_tile;
     auto kof = [&](uint64_t C) { return (uint32_t)offspring_below(C, Ng, T, r0, ngt, r0t); };
 
-    if (tid == 0) s_q[0] = mass_quotient(i_a, T, r0, Ng);
-    if (tid == 32) s_q[1] = mass_quotient(i_b - 1, T, r0, Ng);
+    if constexpr (!TAB) {         // (TAB: the block's own tile update left the quotients and the zeroed table)
+        if (tid == 0) s_q[0] = mass_quotient(i_a, T, r0, Ng);
+        if (tid == 32) s_q[1] = mass_quotient(i_b - 1, T, r0, Ng);
 #pragma unroll
-    for (int r = 0; r < kItems; ++r) s_anc[pad(r * kThreads + (int)tid)] = 0u;
-    __syncthreads();
+        for (int r = 0; r < kItems; ++r) s_anc[pad(r * kThreads + (int)tid)] = 0u;
+        __syncthreads();
+    }
     const uint64_t Qa = s_q[0], Qb = s_q[1];          // C > Qa: reaches past the first child; C > Qb: past the last
 
     // the parent tile of the first child: largest tile whose exclusive prefix is <= Qa -- first the rank
@@ -126,14 +137,34 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
         const unsigned long long *Pc = img + kConstWords + (size_t)kTileP * fa.tiles_alloc;
         const uint64_t q = Qa - sc.rank_off[rk];
         const uint32_t tiles = fa.tiles_per_rank, stride = (tiles + kThreads - 1) / kThreads;
-        uint32_t idx = tid * stride;
-        int hit = idx < tiles && ld_word<COH>(Pc + idx) <= q;
-        const uint32_t bucket = (uint32_t)__syncthreads_count(hit) - 1u;      // P_0 = 0 always qualifies
-        uint32_t lt = bucket * stride;
-        if (stride > 1) {
-            idx = lt + tid;
-            hit = tid < stride && idx < tiles && ld_word<COH>(Pc + idx) <= q;
-            lt += (uint32_t)__syncthreads_count(hit) - 1u;
+        uint32_t lt;
+        if (TAB) {
+            // prefixes in shared memory (at most 4 per thread): every thread counts the hits h among its
+            // `stride` consecutive prefixes; they ascend, so the total is the sum over k of #{threads with
+            // h >= k}: `stride` barrier counts.  (With the prefixes in L2 this single-round form was slower
+            // than the two dependent rounds below: 25.7 vs 24.4 us per C4 step.)
+            uint32_t h = 0;
+            unsigned long long pv[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t idx = tid * stride + k;
+                pv[k] = (k < (int)stride && idx < tiles) ? tab.P[idx] : ~0ull;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) h += pv[k] <= q;
+            uint32_t total = 0;
+            for (uint32_t k = 1; k <= stride; ++k) total += (uint32_t)__syncthreads_count(h >= k);
+            lt = total - 1u;                                                  // P_0 = 0 always qualifies
+        } else {
+            uint32_t idx = tid * stride;
+            int hit = idx < tiles && ld_word<COH>(Pc + idx) <= q;
+            const uint32_t bucket = (uint32_t)__syncthreads_count(hit) - 1u;  // P_0 = 0 always qualifies
+            lt = bucket * stride;
+            if (stride > 1) {
+                idx = lt + tid;
+                hit = tid < stride && idx < tiles && ld_word<COH>(Pc + idx) <= q;
+                lt += (uint32_t)__syncthreads_count(hit) - 1u;
+            }
         }
         tau = rk * fa.tiles_per_rank + lt;
     }
@@ -164,9 +195,9 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
             ldg256u(cp + 4, c[4], c[5], c[6], c[7]);
         }
         const unsigned long long c_left = (lane == 0 && tid != 0) ? ld_word<COH>(cp - 1) : 0ull;
-        const uint64_t F = ld_word<COH>(fld + (size_t)kTileF * fa.tiles_alloc),
-                       P = sc.rank_off[rk] + ld_word<COH>(fld + (size_t)kTileP * fa.tiles_alloc),
-                       Sp = ld_word<COH>(fld + (size_t)kTileSp * fa.tiles_alloc);
+        const uint64_t F = TAB ? tab.F[lt] : ld_word<COH>(fld + (size_t)kTileF * fa.tiles_alloc),
+                       P = TAB ? tab.P[lt] : sc.rank_off[rk] + ld_word<COH>(fld + (size_t)kTileP * fa.tiles_alloc),
+                       Sp = TAB ? tab.Sp[lt] : ld_word<COH>(fld + (size_t)kTileSp * fa.tiles_alloc);
         const uint64_t Chi = P + Sp;                           // CDF at the end of this parent tile
         if (Sp != 0 && Chi > Qa) {
             const uint64_t C_last = P + cusmc_mulshift62(c[kItems - 1], F);
@@ -250,11 +281,16 @@ struct FusedSmem {
 };
 
 // One tile of children through the three phases.  `tile` = the block's tile on this rank.
-template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS, bool COH>
+// LEAN (the persistent kernel's main loop: systematic lookup every step, Normal log-weights, no history,
+// no accumulation): the run-time switches of the general step are compiled out.  TAB (with LEAN): the
+// step constants are already in sm.c and the parents' tile fields in shared memory (`tab`).
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS, bool COH, bool LEAN = false,
+          bool TAB = false>
 __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                  const FusedArgs &fa, uint32_t tile, FusedSmem &sm,
-                                                 const float *z_ready = nullptr)
+                                                 const float *z_ready = nullptr, const TileTab &tab = TileTab{})
 {
+    static_assert(!TAB || LEAN, "tile tables: the persistent main loop");
     const StepArgs &a = fa.s;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t j0 = tile * fa.tile_n;                             // local column of the tile's first child
@@ -262,17 +298,19 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
     const uint32_t i_a = (uint32_t)a.i0 + j0;                         // its global slot
 
     // ---- 1. parents ---------------------------------------------------------------------------------
-    const bool lookup = fa.mode == kParentLookup;
+    const bool lookup = LEAN || fa.mode == kParentLookup;
     bool resample = true;
     if (lookup) {
-        if (tid < kConstWords) reinterpret_cast<unsigned long long *>(&sm.c)[tid] = ld_word<COH>(fa.img_prev + tid);
-        __syncthreads();
+        if constexpr (!TAB) {
+            if (tid < kConstWords) reinterpret_cast<unsigned long long *>(&sm.c)[tid] = ld_word<COH>(fa.img_prev + tid);
+            __syncthreads();
+        }
         resample = sm.c.resample != 0 && sm.c.T != 0;                 // no mass: identity (flagged by the update)
-        if (resample) lookup_parents<PEERS, COH>(fa, sm.c, i_a, n_tile, sm.anc, sm.u64, sm.warp);
+        if (resample) lookup_parents<PEERS, COH, TAB>(fa, sm.c, i_a, n_tile, sm.anc, sm.u64, sm.warp, tab);
         __syncthreads();
     }
     CUSMC_STAMP(fa.trace, 1);
-    const bool accumulate = fa.accumulate && lookup && sm.c.resample == 0;
+    const bool accumulate = !LEAN && fa.accumulate && lookup && sm.c.resample == 0;
 
     // ---- 2. propagate + reweight, striped ------------------------------------------------------------
     // one child: everything after the parent's state is known
@@ -280,12 +318,12 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
         const int64_t i = (int64_t)j0 + j;
         cusmc_u32x4 r0{};
         const float *zin = z_ready ? z_ready + (size_t)j * D : nullptr;       // drawn in the barrier shadow
-        if (PHILOX && !zin) r0 = pfstep::step_rng<FAST>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
-        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH>(op, cobs, ep, a, i, src, r0, xp_in, zin);
+        if (PHILOX && !zin) r0 = pfstep::first_block<FAST, D>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i));
+        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH, LEAN>(op, cobs, ep, a, i, src, r0, xp_in, zin);
         if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
         if (a.lw) st_stream(a.lw + i, lw);
-        if (a.hist_w) st_stream(a.hist_w + i, lw);
-        if (a.hist_a) a.hist_a[i] = parent;
+        if (!LEAN && a.hist_w) st_stream(a.hist_w + i, lw);
+        if (!LEAN && a.hist_a) a.hist_a[i] = parent;
         if (fa.anc_out) fa.anc_out[i] = parent;
         return lw;
     };
@@ -332,7 +370,8 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
                 par[b] = j < n_tile ? parent_of(j) : 0u;
                 const double *src = column_of(par[b]);
 #pragma unroll
-                for (int k = 0; k < D; ++k) xpre[b][k] = (j < n_tile && a.has_prev) ? __ldcg(src + (int64_t)k * a.ld_prev) : 0.0;
+                for (int k = 0; k < D; ++k)
+                    xpre[b][k] = (j < n_tile && (LEAN || a.has_prev)) ? __ldcg(src + (int64_t)k * a.ld_prev) : 0.0;
             }
 #pragma unroll
             for (int b = 0; b < kBatch; ++b) {
@@ -372,6 +411,8 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
     if (lane == 0) sm.dbl[warp] = m;
     __syncthreads();
     m = warp_max_double(lane < kThreads / 32 ? sm.dbl[lane] : -INFINITY);          // the tile's maximum, every thread
+    // (Letting the persistent kernel's all-padding warps -- its tiles are shorter than kTile -- skip the
+    // exponentials was tried: 20.2 -> 21.2 us per C4 step.)
     unsigned long long c[kItems], run = 0, s2 = 0;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {

@@ -138,6 +138,24 @@ __device__ __forceinline__ cusmc_u32x4 step_rng(uint64_t seed, int stream, uint6
     return cusmc_rng(seed, stream, step, index, sub);
 }
 
+// Throughput noise at D <= 2: a Philox block makes four normals and a particle needs two, so the
+// neighbours 2p and 2p + 1 share the block of p (first pair | second pair): half the generator work of a
+// d = 2 step.  Keyed by the GLOBAL slot, so shards and the persistent kernel draw the same normals.
+#ifndef CUSMC_PAIR_D2
+#define CUSMC_PAIR_D2 1
+#endif
+template <bool FAST, int D>
+struct PairBlocks {
+    static constexpr bool value = FAST && D <= 2 && CUSMC_PAIR_D2 != 0;
+};
+// the child's first block (what callers compute while the parent index is still in flight)
+template <bool FAST, int D>
+__device__ __forceinline__ cusmc_u32x4 first_block(uint64_t seed, int stream, uint64_t step, uint64_t index)
+{
+    if constexpr (PairBlocks<FAST, D>::value) return cusmc_rng7(seed, stream, step, index >> 1, 0u);
+    return step_rng<FAST>(seed, stream, step, index, 0u);
+}
+
 // One Philox block -> two Box-Muller pairs.  FAST: the special-function-unit transform
 // (cusmc_box_muller_fast; the throughput default), otherwise the FFMA-only one a host reproduces.
 template <bool FAST>
@@ -154,7 +172,7 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 
 // The child `i` (local column; global slot a.i0 + i) of parent column `src` (already resolved to the
 // owning rank's buffer; nullptr-free: callers pass has_prev = 0 for the initial draw).  r0 is the
-// child's first Philox block, computed by the caller while the parent index was still in flight.
+// child's first Philox block (first_block()), computed by the caller while the parent index was still in flight.
 // Stores x_new (and the history row) itself; returns the (log-)weight, not yet stored.
 // cobs: the whitened observation L_V^-1 y_t -- op.c in the per-step kernels (a parameter-bank operand),
 // a register array in the persistent kernel, whose observation changes inside the launch.  COH: the
@@ -164,7 +182,10 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 // kernel issues a batch of gathers before it computes the batch: its rounds are latency-bound).
 // zf_in (optional, PHILOX): the child's D normals already drawn (the persistent kernel draws the next
 // step's normals while its block waits at the grid barrier).
-template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false>
+// LEAN: the persistent kernel's main loop -- there is a parent, there is no history row, the weight is
+// the Normal log-density: the run-time switches of the general step (has_prev, hist_x, skip_weight, the
+// epilogue's kind / log branches) are compiled out.  Same arithmetic.
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false, bool LEAN = false>
 __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                 const StepArgs &a, int64_t i, const double *__restrict__ src,
                                                 const cusmc_u32x4 &r0, const double *xp_in = nullptr,
@@ -173,10 +194,11 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
     const int d = EXACT ? D : a.d;
     const uint64_t idx = (uint64_t)(a.i0 + i);
     double xp[D], z[D], xn[D];
-    if (xp_in) {
+    constexpr bool kGathered = LEAN && COH && D <= 4;      // the persistent kernel's batched gathers: always
+    if (kGathered || xp_in) {
 #pragma unroll
         for (int j = 0; j < D; ++j) xp[j] = xp_in[j];
-    } else if (a.has_prev) {
+    } else if (LEAN || a.has_prev) {
 #pragma unroll
         for (int j = 0; j < D; ++j)
             xp[j] = (EXACT || j < d) ? (COH ? __ldcg(src + (int64_t)j * a.ld_prev) : __ldg(src + (int64_t)j * a.ld_prev)) : 0.0;
@@ -199,7 +221,10 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
 #pragma unroll
         for (int jq = 0; jq < (D + 3) / 4; ++jq) {
             float zq[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-            if (EXACT || 4 * jq < d) {
+            if constexpr (PairBlocks<FAST, D>::value) {
+                const bool odd = (idx & 1u) != 0;             // r0 = first_block(): the block of the pair idx >> 1
+                cusmc_box_muller_fast(odd ? r0.v[2] : r0.v[0], odd ? r0.v[3] : r0.v[1], &zq[0], &zq[1]);
+            } else if (EXACT || 4 * jq < d) {
                 const cusmc_u32x4 rq = jq == 0 ? r0 : step_rng<FAST>(a.seed, a.rng_stream, a.step, idx, (uint32_t)jq);
                 normals4<FAST>(rq, zq);
             }
@@ -256,10 +281,10 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
             st_stream(dst_x + (int64_t)k * a.ld_new, xn[k]);
             // the history row goes out here too: stores keep their order, and one issued after the
             // weight would pin every xn[k] in a register until the end of the kernel
-            if (a.hist_x) st_stream(a.hist_x + i * d + k, xn[k]);
+            if (!LEAN && a.hist_x) st_stream(a.hist_x + i * d + k, xn[k]);
         }
     }
-    if (a.skip_weight) return a.const_weight;
+    if (!LEAN && a.skip_weight) return a.const_weight;
     double q = 0.0;
 #pragma unroll
     for (int k = 0; k < D; ++k) {
@@ -272,6 +297,7 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
         }
         q = fma(zk, zk, q);
     }
+    if constexpr (LEAN) return fma(-0.5, q, ep.lognorm);      // density_epilogue's MVN / log branch
     return density_epilogue(ep, q);
 }
 

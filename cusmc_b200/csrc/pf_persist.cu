@@ -11,7 +11,16 @@
 //
 // inside one cooperative launch: one barrier per step (round 1's persistent kernel needed three: max,
 // total, scatter), no launch gaps, and the cloud is spread EVENLY over all resident blocks (tile_n
-// particles per block instead of a fixed 2048).  The code is the per-step path's, instantiated with
+// particles per block instead of a fixed 2048).
+//
+// CUSMC_PERSIST_SELFUPD (default): nobody runs the update FOR the others.  Once every block has arrived,
+// EVERY block runs the (tiny: <= 768 tiles) update itself, redundantly, from the tile fields in L2 into its
+// own shared memory: the serial update + release hop behind the barrier disappears, and the next step's
+// lookup finds the step constants, the tile prefix array and the fields of every parent tile in shared
+// memory instead of two dependent L2 round trips.  Same integers in every block (the update is integer /
+// IEEE arithmetic in a fixed order); ONE block per step (the first to arrive -- the one with the most
+// slack) also writes the step record, the image header and the tile fields to global memory, so the
+// filter's state after the run is what the per-step path leaves.  The code is the per-step path's, instantiated with
 // L2-coherent loads for everything another block wrote earlier in the same launch.
 //
 // Same arithmetic as the per-step path operation for operation (same device functions, same Philox
@@ -115,6 +124,177 @@ __device__ __forceinline__ bool barrier_with_update(const PersistArgs &pa, int t
     return ran;
 }
 
+// ---- the self-served update -------------------------------------------------------------------------
+#ifndef CUSMC_PERSIST_SELFUPD
+#define CUSMC_PERSIST_SELFUPD 1
+#endif
+#ifndef CUSMC_PERSIST_LEAN
+#define CUSMC_PERSIST_LEAN 1
+#endif
+// the three tile tables alias FusedSmem::lw (dead between the weigh phase and the next step's rounds)
+constexpr int kSelfMaxTiles = 768;
+static_assert(3 * kSelfMaxTiles * sizeof(unsigned long long) <= sizeof(FusedSmem::lw), "tile tables alias the log-weight tile");
+static_assert(kSelfMaxTiles <= kThreads * kUpdItems, "one chunk: a thread owns four consecutive tiles");
+
+// tile_update_block (tile_update_impl.cuh) for one rank, no adaptive decision, at most kThreads * 4 tiles,
+// results into shared memory: tables F / P / Sp and the step constants sm.c.  `writer`: this block also
+// computes the sum of squares and writes what tile_update_block writes to global memory.
+// It also leaves what the next step's lookup starts from: the marker table zeroed and the mass quotients of
+// the block's first and last child in sm.u64[0..1] (lookup_parents with TAB).  The serial tail is spread
+// over four threads (constants and Q_a | Q_b | the two quotients N / T, r0 / T | the step record), and
+// u0_next was fetched before the barrier wait.
+__device__ __forceinline__ void self_update(const PersistArgs &pa, int t, bool writer, FusedSmem &sm,
+                                            UpdateSmem<kThreads> &us, unsigned long long *tabF,
+                                            unsigned long long *tabP, unsigned long long *tabSp, double u0_next,
+                                            uint32_t i_a, uint32_t n_tile)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tiles = gridDim.x, tiles_all = pa.tiles_alloc;
+    unsigned long long *img = pa.img[t & 1];
+    unsigned long long *fld[kTileFields];
+#pragma unroll
+    for (int f = 0; f < kTileFields; ++f) fld[f] = img + kConstWords + (int64_t)f * tiles_all;
+    const int64_t b0 = (int64_t)tid * kUpdItems;
+    unsigned long long mv[kUpdItems] = {0, 0, 0, 0}, S[kUpdItems] = {0, 0, 0, 0}, S2[kUpdItems] = {0, 0, 0, 0};
+    if (b0 < tiles) {
+        ld4(fld[kTileM] + b0, mv);
+        ld4(fld[kTileS] + b0, S);
+        if (writer) ld4(fld[kTileS2] + b0, S2);
+    }
+#pragma unroll
+    for (int r = 0; r < pffused::kItems; ++r) sm.anc[pffused::pad(r * kThreads + tid)] = 0u;      // the lookup's marker table
+    double m = -INFINITY;
+#pragma unroll
+    for (int r = 0; r < kUpdItems; ++r) {
+        const double v = __longlong_as_double((long long)mv[r]);
+        if (b0 + r < tiles && v > m) m = v;                        // records hold finite values or -inf
+    }
+    m = warp_max_double(m);
+    if (lane == 0) us.dbl[warp] = m;
+    __syncthreads();
+    const double M = warp_max_double(lane < kThreads / 32 ? us.dbl[lane] : -INFINITY);
+    unsigned long long F[kUpdItems] = {0, 0, 0, 0}, sp[kUpdItems] = {0, 0, 0, 0}, run = 0, t2 = 0;
+#pragma unroll
+    for (int r = 0; r < kUpdItems; ++r)
+        if (b0 + r < tiles) {
+            F[r] = cusmc_rescale_factor(__longlong_as_double((long long)mv[r]), M);
+            sp[r] = cusmc_mulshift62(S[r], F[r]);
+            if (writer) t2 += cusmc_mulshift62(cusmc_mulshift62(S2[r], F[r]), F[r]);
+            run += sp[r];
+        }
+    unsigned long long inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += v;
+    }
+    if (lane == 31) us.sm[warp] = inc;
+    if (writer) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t2 += __shfl_xor_sync(0xffffffffu, t2, o);
+        if (lane == 0) us.sm2[warp] = t2;
+    }
+    __syncthreads();
+    unsigned long long excl = inc - run, T = 0, T2 = 0;
+#pragma unroll
+    for (int k = 0; k < kThreads / 32; ++k) {
+        const unsigned long long w = us.sm[k];
+        if (k < warp) excl += w;
+        T += w;
+        if (writer) T2 += us.sm2[k];
+    }
+    unsigned long long P[kUpdItems];
+#pragma unroll
+    for (int r = 0; r < kUpdItems; ++r) {
+        P[r] = excl;
+        excl += sp[r];
+    }
+    if (b0 < tiles_all) {                                          // tiles past the end of the cloud are empty
+#pragma unroll
+        for (int r = 0; r < kUpdItems; ++r) {
+            tabF[b0 + r] = F[r];
+            tabP[b0 + r] = P[r];
+            tabSp[b0 + r] = sp[r];
+        }
+        if (writer) {
+            st4(fld[kTileF] + b0, F);
+            st4(fld[kTileP] + b0, P);
+            st4(fld[kTileSp] + b0, sp);
+        }
+    }
+    if ((tid & 31) == 0 && tid < 128) {
+        unsigned long long rr = (unsigned long long)(u0_next * (double)T);
+        if (T && rr > T - 1) rr = T - 1;
+        StepConsts &c = sm.c;
+        const unsigned long long Ng = pa.fa.N_global;
+        if (tid == 0) {
+            c.T = T;
+            c.r0 = rr;
+            c.resample = 1;
+            c.T2 = T2;
+            c.M = M;
+            c.reserved = 0;
+            c.rank_off[0] = 0;
+#pragma unroll
+            for (int k = 1; k < CUSMC_MAX_PEERS; ++k) c.rank_off[k] = T;
+            sm.u64[0] = mass_quotient(i_a, T, rr, Ng);
+        } else if (tid == 32) {
+            sm.u64[1] = mass_quotient(i_a + n_tile - 1, T, rr, Ng);
+        } else if (tid == 64) {
+            c.ng_over_t = (double)pa.fa.N_global / (double)T;
+            c.r0_over_t = (double)rr / (double)T;
+        } else if (writer) {
+            StepSlot *slot = pa.slots + t;
+            slot->lw_max = M;
+            slot->sum_q = T;
+            slot->sum_q2 = T2;
+            slot->n_pos = 0;
+            slot->cdf_offset = 0;
+            if (t + 1 < pa.T) {
+                pa.slots[t + 1].resampled = 1;
+                pa.slots[t + 1].degenerate = T == 0 ? 1 : 0;
+            }
+        }
+    }
+    __syncthreads();
+    if (writer && tid < kConstWords) img[tid] = reinterpret_cast<const unsigned long long *>(&sm.c)[tid];
+}
+
+// The grid barrier of the self-served update: arrive, draw the next step's normals (`shadow`), wait until
+// everybody has arrived, update.
+template <typename Shadow>
+__device__ __forceinline__ void barrier_self_update(const PersistArgs &pa, int t, unsigned &gen, int *s_first, FusedSmem &sm,
+                                                    UpdateSmem<kThreads> &us, unsigned long long *tabF,
+                                                    unsigned long long *tabP, unsigned long long *tabSp, double *trace,
+                                                    Shadow shadow)
+{
+    const double u0_next = t + 1 < pa.T ? __ldg(pa.u0 + t + 1) : 0.0;      // in flight while the block waits
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        // releases this block's tile (the bar.sync above makes the release cumulative over the block's writes)
+        unsigned old;
+        asm volatile("atom.add.release.gpu.global.u32 %0, [%1], 1;" : "=r"(old) : "l"(pa.barrier) : "memory");
+        *s_first = old == gen * gridDim.x;
+    }
+    CUSMC_STAMP(trace, 7);                                         // arrived
+    shadow();
+    if (threadIdx.x == 0) {
+        const unsigned want = (gen + 1u) * gridDim.x;
+        unsigned seen;
+        // (relaxed polls + one acquire fence at the end measured no faster: 20.4 vs 20.2 us per C4 step)
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(pa.barrier) : "memory");
+        } while ((int)(seen - want) < 0);
+    }
+    CUSMC_STAMP(trace, 5);                                         // everybody has arrived
+    __syncthreads();
+    const uint32_t tile_lo = blockIdx.x * pa.fa.tile_n;
+    self_update(pa, t, *s_first != 0, sm, us, tabF, tabP, tabSp, u0_next, (uint32_t)pa.fa.s.i0 + tile_lo,
+                min(pa.fa.tile_n, (uint32_t)pa.fa.s.n_out - tile_lo));
+    CUSMC_STAMP(trace, 6);                                         // update done
+    ++gen;
+}
+
 #ifndef CUSMC_PERSIST_MINB
 #define CUSMC_PERSIST_MINB 4
 #endif
@@ -131,7 +311,7 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
     // normals of the next step, drawn in the barrier shadow (d = 2: 16 KB; wider states would cost a
     // resident block per SM, they draw inside their rounds)
     constexpr bool kShadowNoise = D == 2;
-    __shared__ float s_z[kShadowNoise ? kTile * D : 1];
+    __shared__ __align__(16) float s_z[kShadowNoise ? kTile * D : 1];
     unsigned gen = 0;
     FusedArgs fa = pa.fa;
     const uint32_t tile_lo = blockIdx.x * fa.tile_n;
@@ -140,6 +320,17 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
     auto draw_next = [&](int t_next) {
         if constexpr (kShadowNoise) {
             if (t_next >= pa.T) return;
+            if constexpr (pfstep::PairBlocks<FAST, D>::value) {
+                // one block per PAIR of neighbours (i0 = 0 and tile_lo is a multiple of 32: pairs never straddle tiles)
+                for (uint32_t p = threadIdx.x; 2 * p < tile_cnt; p += kThreads) {
+                    const cusmc_u32x4 r = pfstep::first_block<FAST, D>(fa.s.seed, CUSMC_STREAM_NORMAL, (uint64_t)t_next,
+                                                                       (uint64_t)(fa.s.i0 + tile_lo + 2 * p));
+                    float zq[4];
+                    pfstep::normals4<FAST>(r, zq);
+                    *reinterpret_cast<float4 *>(s_z + 4 * (size_t)p) = make_float4(zq[0], zq[1], zq[2], zq[3]);
+                }
+                return;
+            }
             for (uint32_t j = threadIdx.x; j < tile_cnt; j += kThreads) {
                 const cusmc_u32x4 r = pfstep::step_rng<FAST>(fa.s.seed, CUSMC_STREAM_NORMAL, (uint64_t)t_next,
                                                              (uint64_t)(fa.s.i0 + tile_lo + j), 0u);
@@ -166,7 +357,17 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         fa.s.step = 0;
         pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op_init, zero_c, ep, fa, blockIdx.x, sm);
     }
-    bool z_ready = barrier_with_update(pa, 0, gen, &s_last, us, [&] { draw_next(1); }) && kShadowNoise;
+    constexpr bool kLean = CUSMC_PERSIST_LEAN != 0, kSelf = kLean && CUSMC_PERSIST_SELFUPD != 0;
+    unsigned long long *tabF = reinterpret_cast<unsigned long long *>(sm.lw), *tabP = tabF + kSelfMaxTiles,
+                       *tabSp = tabP + kSelfMaxTiles;
+    const pffused::TileTab tab{tabF, tabP, tabSp};
+    bool z_ready;
+    if constexpr (kSelf) {
+        barrier_self_update(pa, 0, gen, &s_last, sm, us, tabF, tabP, tabSp, nullptr, [&] { draw_next(1); });
+        z_ready = kShadowNoise;
+    } else {
+        z_ready = barrier_with_update(pa, 0, gen, &s_last, us, [&] { draw_next(1); }) && kShadowNoise;
+    }
 
     fa.mode = pffused::kParentLookup;
     fa.s.has_prev = 1;
@@ -193,10 +394,13 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         if (pa.trace && t == 50) fa.trace = pa.trace + 1 + ((size_t)pa.T + blockIdx.x) * 9;
 #endif
         CUSMC_STAMP(fa.trace, 0);
-        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op, cobs, ep, fa, blockIdx.x, sm,
-                                                                                 z_ready ? s_z : nullptr);
+        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true, kLean, kSelf>(
+            op, cobs, ep, fa, blockIdx.x, sm, z_ready ? s_z : nullptr, tab);
         CUSMC_STAMP(fa.trace, 3);
-        z_ready = barrier_with_update(pa, t, gen, &s_last, us, [&] { draw_next(t + 1); }) && kShadowNoise;
+        if constexpr (kSelf)
+            barrier_self_update(pa, t, gen, &s_last, sm, us, tabF, tabP, tabSp, fa.trace, [&] { draw_next(t + 1); });
+        else
+            z_ready = barrier_with_update(pa, t, gen, &s_last, us, [&] { draw_next(t + 1); }) && kShadowNoise;
         CUSMC_STAMP(fa.trace, 4);
     }
 }
@@ -205,7 +409,8 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
 // whole warps; 0 if such a tile exceeds what one block holds.
 uint32_t pick_tile(const cusmc_filter *f, int per_sm)
 {
-    const int64_t slots = (int64_t)f->ctx->sm_count * per_sm;
+    int64_t slots = (int64_t)f->ctx->sm_count * per_sm;
+    if (CUSMC_PERSIST_LEAN && CUSMC_PERSIST_SELFUPD) slots = std::min<int64_t>(slots, kSelfMaxTiles);   // tables in shared memory
     int64_t n = (f->cfg.N + slots - 1) / slots;
     n = std::max<int64_t>((n + 31) & ~(int64_t)31, 32);
     return n <= kTile ? (uint32_t)n : 0u;
@@ -227,6 +432,9 @@ int launch_persistent(cusmc_filter *f, PersistArgs &pa, bool probe_only, uint32_
     *tile_out = tile_n;
     if (probe_only) return CUSMC_OK;
     const unsigned grid = (unsigned)((cfg.N + tile_n - 1) / tile_n);
+    if (CUSMC_PERSIST_SELFUPD && pa.tiles_alloc > kSelfMaxTiles)
+        return cusmc_fail(ctx, CUSMC_ERR_UNSUPPORTED, "persistent run: %lld tiles exceed the %d the blocks keep in shared memory",
+                          (long long)pa.tiles_alloc, kSelfMaxTiles);
     pa.fa.tile_n = tile_n;
     StepOp<D, DIAG> op0, op;
     const pfstep::StepModel m0{cfg.d, cfg.dy, nullptr, f->Qc0.data(), cfg.noise_scale, nullptr, nullptr, f->m0.data()};
@@ -280,7 +488,8 @@ bool config_allows(const cusmc_filter *f)
     const cusmc_filter_config &cfg = f->cfg;
     return cfg.persistent >= 0 && f->world == 1 && cfg.resampler == CUSMC_RESAMPLE_SYSTEMATIC && cfg.kind == CUSMC_MVN &&
            !cfg.keep_history && !cfg.summary && cfg.ess_threshold == 0.0 && cfg.d == cfg.dy &&
-           (cfg.d == 2 || cfg.d == 4 || cfg.d == 8) && cfg.T >= 2;
+           (cfg.d == 2 || cfg.d == 4 || cfg.d == 8) && cfg.T >= 2 &&
+           f->is_log && f->ep.kind == CUSMC_MVN && f->ep.want_log;      // the lean main loop's epilogue
 }
 
 }  // namespace

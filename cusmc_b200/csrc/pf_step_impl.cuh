@@ -57,7 +57,7 @@ pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, co
         int64_t parent = i;
         if (a.anc) parent = (int64_t)a.anc[i] - a.parent_base;
         cusmc_u32x4 r0{};
-        if (PHILOX) r0 = pfstep::step_rng<FAST>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i), 0u);
+        if (PHILOX) r0 = pfstep::first_block<FAST, D>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i));
         const double *src = a.x_prev + parent;
         if (a.has_prev && a.world > 1) {
             // ancestors are (nearly) sorted, so almost every parent is local: only a remote one

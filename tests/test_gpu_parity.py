@@ -520,6 +520,35 @@ def test_mvt_device_noise_is_student_t(ctx, reproducible, nu, d):
     assert not np.array_equal(h["x"][0], h["x"][1])
 
 
+@pytest.mark.parametrize("persistent", [False, True])
+def test_fast_normal_noise_d2_pairs(ctx, persistent):
+    """Throughput noise at d = 2: the neighbours 2p, 2p + 1 share one Philox block (first_block(), pf_particle.cuh).
+    With G = 0, W = C0 = I every x_t is the raw noise: standard Normal per component (KS), components and
+    NEIGHBOURS uncorrelated (also in squares), steps differ, and the one-kernel run draws the same normals
+    as the per-step path."""
+    from scipy import stats
+    N, T, d = 200000, 3, 2
+    I = np.eye(d)
+    Y = np.zeros((d, T))
+    pf = ctx.filter(N=N, Y=Y, m0=np.zeros(d), C0=I, F=I, G=np.zeros((d, d)), V=1e6 * I, W=I, resampler="systematic",
+                    seed=123, summary=False, persistent=persistent)
+    pf.run()
+    x, _, _ = pf.state()
+    pf.close()
+    x = x.T                                                        # [N, d], the last step's cloud
+    assert np.all(np.isfinite(x))
+    for k in range(d):
+        assert stats.kstest(x[:, k], "norm").pvalue > 1e-3, k
+    cols = np.stack([x[0::2, 0], x[0::2, 1], x[1::2, 0], x[1::2, 1]])
+    for v in (cols, cols ** 2):
+        r = np.corrcoef(v)
+        assert np.all(np.abs(r - np.eye(4)) < 0.015), r
+    test_fast_normal_noise_d2_pairs.seen = getattr(test_fast_normal_noise_d2_pairs, "seen", {})
+    test_fast_normal_noise_d2_pairs.seen[persistent] = x
+    if len(test_fast_normal_noise_d2_pairs.seen) == 2:
+        assert np.array_equal(test_fast_normal_noise_d2_pairs.seen[False], test_fast_normal_noise_d2_pairs.seen[True])
+
+
 def test_mvt_normal_init_switch(ctx, orc):
     """mvt_normal_init = 1 keeps round 1's Normal start; the default draws x_0 with chi factors."""
     rng = np.random.default_rng(3)
