@@ -31,6 +31,8 @@
 #include "common.cuh"
 #include "resample.cuh"
 
+#include "../../include/cusmc_detmath.h"
+
 struct StepConsts {
     unsigned long long T;            // global fixed-point mass of the step this image belongs to
     unsigned long long r0;           // systematic offset of the NEXT step in mass units
@@ -58,6 +60,25 @@ __device__ __forceinline__ const StepConsts *fimage_consts(const unsigned long l
     return reinterpret_cast<const StepConsts *>(img);
 }
 
+// The fixed-point weight of a log-weight against its tile's maximum m and the image of its square:
+//     q = cusmc_fixed_from_unit(w, shift),  q2 = cusmc_fixed_from_unit(w w, shift),  w = cusmc_unit_from_log(lw, m)
+// bit for bit, with the selects those three calls repeat folded into two: w is exp of a number in [-43.5, 0]
+// or nothing, so it lies in (0, 1] (the last Horner step of cusmc_det_exp_core is fma(p, r, 1) with r <= 0
+// when k = 0, and p 2^k <= 0.71 when k < 0) and the clamps of cusmc_fixed_from_unit never act; "nothing" (NaN,
+// +inf, below 2^-62, above the maximum) zeroes the SCALE 2^shift -- a power of two, whose low word is zero
+// either way: one 32-bit select.
+__device__ __forceinline__ void weigh_fixed(double lw, double m, int shift, unsigned long long &q, unsigned long long &q2)
+{
+    const double x = lw - m;
+    const bool ok = x >= -43.5 && x <= 0.0;
+    int k;
+    const double p = cusmc_det_exp_core(ok ? x : 0.0, &k);
+    const double w = p * cusmc_pow2i(k);
+    const double scale = __hiloint2double(ok ? (shift + 1023) << 20 : 0, 0);
+    q = (unsigned long long)(w * scale);
+    q2 = (unsigned long long)((w * w) * scale);
+}
+
 // Q_i = floor((i T + r0) / N): the largest CDF value NOT above child i, i.e. for any integer C
 //     offspring_below(C) <= i   <=>   C N <= i T + r0   <=>   C <= Q_i.
 // Every "does this parent / tile / rank reach child i" question of the lookup becomes one 64-bit
@@ -69,9 +90,26 @@ __device__ __forceinline__ unsigned long long mass_quotient(unsigned long long i
     unsigned long long lo = i * T, hi = __umul64hi(i, T);
     const unsigned long long lo2 = lo + r0;
     hi += lo2 < lo;
-    unsigned long long cur = (hi << 32) | (lo2 >> 32);        // hi < N < 2^32
-    const unsigned long long q1 = cur / Ng;
-    cur = ((cur - q1 * Ng) << 32) | (lo2 & 0xffffffffull);
-    return (q1 << 32) | (cur / Ng);
+    // Each step divides a number below N 2^32 by N < 2^32 (the quotient fits 32 bits): an fp64 quotient is
+    // within one of it (both roundings are relative 2^-53, the quotient is below 2^32), one exact
+    // remainder in wrap-around 64-bit arithmetic corrects it.  A third of the generic 64-bit division's
+    // instructions, on the serial path between the tile update and the lookup.
+    auto div_step = [&](unsigned long long cur, unsigned long long &rem) {
+        unsigned long long q = (unsigned long long)((double)cur / (double)Ng);
+        long long r = (long long)(cur - q * Ng);
+        if (r < 0) {
+            q -= 1;
+            r += (long long)Ng;
+        } else if (r >= (long long)Ng) {
+            q += 1;
+            r -= (long long)Ng;
+        }
+        rem = (unsigned long long)r;
+        return q;
+    };
+    unsigned long long rem;
+    const unsigned long long q1 = div_step((hi << 32) | (lo2 >> 32), rem);      // hi < N < 2^32
+    const unsigned long long q0 = div_step((rem << 32) | (lo2 & 0xffffffffull), rem);
+    return (q1 << 32) | q0;
 }
 #endif

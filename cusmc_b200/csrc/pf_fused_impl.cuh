@@ -416,10 +416,11 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
     unsigned long long c[kItems], run = 0, s2 = 0;
 #pragma unroll
     for (int r = 0; r < kItems; ++r) {
-        const double wn = cusmc_unit_from_log(v[r], m);                            // -inf padding -> 0
-        run += cusmc_fixed_from_unit(wn, fa.shift);
+        unsigned long long q, q2;
+        weigh_fixed(v[r], m, fa.shift, q, q2);                                     // -inf padding -> 0
+        run += q;
         c[r] = run;
-        s2 += cusmc_fixed_from_unit(wn * wn, fa.shift);
+        s2 += q2;
     }
     unsigned long long inc = run;
 #pragma unroll

@@ -173,20 +173,23 @@ __device__ __forceinline__ void self_update(const PersistArgs &pa, int t, bool w
     if (lane == 0) us.dbl[warp] = m;
     __syncthreads();
     const double M = warp_max_double(lane < kThreads / 32 ? us.dbl[lane] : -INFINITY);
-    unsigned long long F[kUpdItems] = {0, 0, 0, 0}, sp[kUpdItems] = {0, 0, 0, 0}, run = 0, t2 = 0;
+    unsigned long long F[kUpdItems] = {0, 0, 0, 0}, sp[kUpdItems] = {0, 0, 0, 0}, run = 0, t2 = 0, inc = 0;
+    const bool warp_live = (int64_t)(warp * 32) * kUpdItems < tiles;       // (a warp past the last tile has nothing to scan)
+    if (warp_live) {
 #pragma unroll
-    for (int r = 0; r < kUpdItems; ++r)
-        if (b0 + r < tiles) {
-            F[r] = cusmc_rescale_factor(__longlong_as_double((long long)mv[r]), M);
-            sp[r] = cusmc_mulshift62(S[r], F[r]);
-            if (writer) t2 += cusmc_mulshift62(cusmc_mulshift62(S2[r], F[r]), F[r]);
-            run += sp[r];
+        for (int r = 0; r < kUpdItems; ++r)
+            if (b0 + r < tiles) {
+                F[r] = cusmc_rescale_factor(__longlong_as_double((long long)mv[r]), M);
+                sp[r] = cusmc_mulshift62(S[r], F[r]);
+                if (writer) t2 += cusmc_mulshift62(cusmc_mulshift62(S2[r], F[r]), F[r]);
+                run += sp[r];
+            }
+        inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += v;
         }
-    unsigned long long inc = run;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
-        if (lane >= o) inc += v;
     }
     if (lane == 31) us.sm[warp] = inc;
     if (writer) {
