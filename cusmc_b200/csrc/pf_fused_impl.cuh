@@ -251,9 +251,17 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
 #ifndef CUSMC_FUSED_MINB8
 #define CUSMC_FUSED_MINB8 5
 #endif
+#ifndef CUSMC_DENSE_SMOP
+#define CUSMC_DENSE_SMOP 1
+#endif
+#ifndef CUSMC_DENSE_MINB8
+#define CUSMC_DENSE_MINB8 3
+#endif
+// dense operators up to d = 16 are staged in shared memory (3 d^2 doubles: 6 KB at d = 16)
+__host__ __device__ constexpr bool dense_smop(int D, bool diag) { return !diag && D <= 16 && CUSMC_DENSE_SMOP != 0; }
 constexpr int min_blocks(int D, bool diag, bool mvt)
 {
-    return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : 3) : 4));
+    return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : (diag ? 3 : CUSMC_DENSE_MINB8)) : 4));
 }
 
 // Phase trace (profiling builds only, -DCUSMC_TRACE): block 0 / thread 0 stamps the global timer.
@@ -284,11 +292,14 @@ struct FusedSmem {
 // LEAN (the persistent kernel's main loop: systematic lookup every step, Normal log-weights, no history,
 // no accumulation): the run-time switches of the general step are compiled out.  TAB (with LEAN): the
 // step constants are already in sm.c and the parents' tile fields in shared memory (`tab`).
+// SMOP (dense operators, per-step kernel): the matrices are read from the shared-memory copy `smop`
+// (pf_particle.cuh).
 template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool PEERS, bool COH, bool LEAN = false,
-          bool TAB = false>
+          bool TAB = false, bool SMOP = false>
 __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                  const FusedArgs &fa, uint32_t tile, FusedSmem &sm,
-                                                 const float *z_ready = nullptr, const TileTab &tab = TileTab{})
+                                                 const float *z_ready = nullptr, const TileTab &tab = TileTab{},
+                                                 const double *smop = nullptr)
 {
     static_assert(!TAB || LEAN, "tile tables: the persistent main loop");
     const StepArgs &a = fa.s;
@@ -319,7 +330,8 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
         cusmc_u32x4 r0{};
         const float *zin = z_ready ? z_ready + (size_t)j * D : nullptr;       // drawn in the barrier shadow
         if (PHILOX && !zin) r0 = pfstep::first_block<FAST, D>(a.seed, a.rng_stream, a.step, (uint64_t)(a.i0 + i));
-        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH, LEAN>(op, cobs, ep, a, i, src, r0, xp_in, zin);
+        double lw = pfstep::particle_step<D, PHILOX, FAST, MVT, EXACT, DIAG, COH, LEAN, SMOP>(op, cobs, ep, a, i, src, r0, xp_in,
+                                                                                              zin, smop);
         if (accumulate) lw = a.lw[i] + lw;                        // no resampling: the log-weights accumulate
         if (a.lw) st_stream(a.lw + i, lw);
         if (!LEAN && a.hist_w) st_stream(a.hist_w + i, lw);
@@ -382,10 +394,11 @@ __device__ __forceinline__ void fused_block_step(const StepOp<D, DIAG> &op, cons
             }
         }
     } else {
-        // (Dense operators: the compiler hoists the loop-invariant parameter-bank operands of a rolled
-        // loop into registers and spills some (d = 8: 80 registers + 304 bytes of stack).  Unrolling the
-        // eight rounds removes the spills and changes nothing: 458 vs 464 us per dense C5 step -- that
-        // kernel is bound by its 3 d^2 LDCU + DFMA pairs at 24 warps per SM, not by the spills.)
+        // Dense operators (SMOP): 3 blocks per SM.  What was tried against the latency of the parent gather
+        // there (17 % of the stall samples on its first use): a register-held prefetch of the next round
+        // (spills: 358 -> 401 us per dense C5 step), prefetch.global.L1 / .L2 hints (362 us), cp.async into a
+        // double-buffered per-thread slot of shared memory (long-scoreboard stalls 2.2 -> 0.8 per issue, but
+        // the LDGSTS traffic delays the operator LDS: short-scoreboard 1.7 -> 2.7, kernel time unchanged).
 #pragma unroll 1
         for (int r = 0; r < kItems; ++r) {
             const uint32_t j = (uint32_t)r * kThreads + tid;
@@ -455,6 +468,17 @@ __global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
 pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const FusedArgs fa)
 {
     __shared__ FusedSmem sm;
+    constexpr bool SMOP = dense_smop(D, DIAG);
+    __shared__ alignas(16) double s_op[SMOP ? 3 * D * D : 2];
+    if constexpr (SMOP) {
+        // the operators are launch parameters: staged before the wait on the previous grid
+        for (int e = threadIdx.x; e < D * D; e += kThreads) {
+            s_op[e] = op.G[DIAG ? 0 : e];
+            s_op[D * D + e] = op.Q[DIAG ? 0 : e];
+            s_op[2 * D * D + e] = op.M[DIAG ? 0 : e];
+        }
+        __syncthreads();
+    }
     // Programmatic dependent launch: this grid is launched while the tile update of the previous step is
     // still running (its blocks become resident, its launch latency is hidden) and waits HERE until that
     // grid has completed and its writes are visible.  A no-op when launched the ordinary way.
@@ -462,7 +486,8 @@ pf_fused_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, c
     // ... and the tile update that follows THIS grid may be made resident as soon as every block here has
     // started (it waits the same way), which hides its launch latency behind the last wave.
     asm volatile("griddepcontrol.launch_dependents;");
-    fused_block_step<D, PHILOX, FAST, MVT, EXACT, DIAG, PEERS, false>(op, op.c, ep, fa, blockIdx.x, sm);
+    fused_block_step<D, PHILOX, FAST, MVT, EXACT, DIAG, PEERS, false, false, false, SMOP>(op, op.c, ep, fa, blockIdx.x, sm, nullptr,
+                                                                                          TileTab{}, s_op);
 }
 
 // ---- launch ---------------------------------------------------------------------------------------------

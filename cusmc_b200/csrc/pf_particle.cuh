@@ -185,12 +185,28 @@ __device__ __forceinline__ void normals4(const cusmc_u32x4 &r, float (&z)[4])
 // LEAN: the persistent kernel's main loop -- there is a parent, there is no history row, the weight is
 // the Normal log-density: the run-time switches of the general step (has_prev, hist_x, skip_weight, the
 // epilogue's kind / log branches) are compiled out.  Same arithmetic.
-template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false, bool LEAN = false>
+// SMOP (dense operators only): G, Q and M are read from a shared-memory copy `smop` = [G | Q | M], row-major
+// D x D each, 16-byte aligned -- one broadcast LDS.128 per two DFMAs.  As parameter-bank operands the
+// compiler hoists them out of the caller's loop over rounds into registers, spills those (d = 8: 344 bytes
+// of stack per thread = 230 MB of extra DRAM writes per C5 step) and moves them back with R2UR before every
+// use: 17 % of the dense kernel's stall samples sat on those reloads.  Same values, same order of operations.
+template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG, bool COH = false, bool LEAN = false,
+          bool SMOP = false>
 __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const double (&cobs)[D], const Epilogue &ep,
                                                 const StepArgs &a, int64_t i, const double *__restrict__ src,
                                                 const cusmc_u32x4 &r0, const double *xp_in = nullptr,
-                                                const float *zf_in = nullptr)
+                                                const float *zf_in = nullptr, const double *smop = nullptr)
 {
+    static_assert(!SMOP || (!DIAG && D % 2 == 0), "shared-memory operators: the dense step");
+    // element `idx` of matrix `which` (0 = G, 1 = Q, 2 = M), two at a time from shared memory
+    auto mat2 = [&](int which, int idx) {
+        if constexpr (SMOP) {
+            return reinterpret_cast<const double2 *>(smop)[(which * D * D + idx) >> 1];
+        } else {
+            const double *m = which == 0 ? op.G : which == 1 ? op.Q : op.M;
+            return make_double2(m[DIAG ? 0 : idx], m[DIAG ? 0 : idx + 1]);
+        }
+    };
     const int d = EXACT ? D : a.d;
     const uint64_t idx = (uint64_t)(a.i0 + i);
     double xp[D], z[D], xn[D];
@@ -270,9 +286,17 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
             s = fma(op.Q[k], kFloatNoise ? (double)zf[kFloatNoise ? k : 0] : z[k], s);
         } else {
 #pragma unroll
-            for (int j = 0; j < D; ++j) g = fma(op.G[k * D + j], xp[j], g);
+            for (int j = 0; j < D; j += 2) {
+                const double2 m2 = mat2(0, k * D + j);
+                g = fma(m2.x, xp[j], g);
+                g = fma(m2.y, xp[j + 1], g);
+            }
 #pragma unroll
-            for (int j = 0; j < D; ++j) s = fma(op.Q[k * D + j], z[j], s);
+            for (int j = 0; j < D; j += 2) {
+                const double2 m2 = mat2(1, k * D + j);
+                s = fma(m2.x, z[j], s);
+                s = fma(m2.y, z[j + 1], s);
+            }
         }
         if (MVT && (EXACT || k < d))
             s = (a.chi ? ld_stream(a.chi + (int64_t)k * a.ld_noise + i) : chi[MVT ? k : 0]) * s;
@@ -293,7 +317,11 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
             zk = fma(-op.M[k], xn[k], zk);
         } else {
 #pragma unroll
-            for (int j = 0; j < D; ++j) zk = fma(-op.M[k * D + j], xn[j], zk);
+            for (int j = 0; j < D; j += 2) {
+                const double2 m2 = mat2(2, k * D + j);
+                zk = fma(-m2.x, xn[j], zk);
+                zk = fma(-m2.y, xn[j + 1], zk);
+            }
         }
         q = fma(zk, zk, q);
     }

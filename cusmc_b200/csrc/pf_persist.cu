@@ -360,6 +360,18 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         fa.s.step = 0;
         pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true>(op_init, zero_c, ep, fa, blockIdx.x, sm);
     }
+    // dense operators of the main loop: read from shared memory (pf_particle.cuh, SMOP) -- as parameter-bank
+    // operands they are hoisted out of the step loop and spilled (272-352 bytes of stack at d = 4, 8)
+    constexpr bool kSmop = pffused::dense_smop(D, DIAG);
+    __shared__ alignas(16) double s_op[kSmop ? 3 * D * D : 2];
+    if constexpr (kSmop) {
+        for (int e = threadIdx.x; e < D * D; e += kThreads) {
+            s_op[e] = op.G[DIAG ? 0 : e];
+            s_op[D * D + e] = op.Q[DIAG ? 0 : e];
+            s_op[2 * D * D + e] = op.M[DIAG ? 0 : e];
+        }
+        __syncthreads();
+    }
     constexpr bool kLean = CUSMC_PERSIST_LEAN != 0, kSelf = kLean && CUSMC_PERSIST_SELFUPD != 0;
     unsigned long long *tabF = reinterpret_cast<unsigned long long *>(sm.lw), *tabP = tabF + kSelfMaxTiles,
                        *tabSp = tabP + kSelfMaxTiles;
@@ -397,8 +409,8 @@ pf_persistent_kernel(const __grid_constant__ StepOp<D, DIAG> op_init, const __gr
         if (pa.trace && t == 50) fa.trace = pa.trace + 1 + ((size_t)pa.T + blockIdx.x) * 9;
 #endif
         CUSMC_STAMP(fa.trace, 0);
-        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true, kLean, kSelf>(
-            op, cobs, ep, fa, blockIdx.x, sm, z_ready ? s_z : nullptr, tab);
+        pffused::fused_block_step<D, true, FAST, false, true, DIAG, false, true, kLean, kSelf, kSmop>(
+            op, cobs, ep, fa, blockIdx.x, sm, z_ready ? s_z : nullptr, tab, s_op);
         CUSMC_STAMP(fa.trace, 3);
         if constexpr (kSelf)
             barrier_self_update(pa, t, gen, &s_last, sm, us, tabF, tabP, tabSp, fa.trace, [&] { draw_next(t + 1); });

@@ -613,7 +613,7 @@ def test_filter_device_rng_matches_oracle_mirror(ctx, orc, resampler):
 
 
 @pytest.mark.parametrize("d,diag,N", [(2, True, 20000), (2, False, 8192), (4, True, 12346), (4, False, 4100),
-                                      (8, True, 50000), (2, True, 300000), (2, True, 1000000)])
+                                      (8, True, 50000), (8, False, 9001), (2, True, 300000), (2, True, 1000000)])
 def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, d, diag, N):
     """cusmc_filter_run as ONE cooperative kernel (pf_persist.cu; the C4 path) against the ORACLE: device-
     drawn noise on one side, the oracle's Philox mirror on the other, no history.  The weight image is
@@ -655,6 +655,81 @@ def test_persistent_kernel_bit_exact_vs_oracle(ctx, orc, d, diag, N):
         assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
         assert len(np.unique(a)) > 10 and np.all(np.diff(a.astype(np.int64)) >= 0)
     assert tiles[0] % 32 == 0 and tiles[0] <= 2048
+
+
+def _library_factors(ctx, C0, W):
+    """The eigen factors the library builds from C0 and W, bit for bit, read off the particles as in
+    test_eigen_factor_through_the_abi (m0 = 0, G = 0 and unit-vector draws: x_0[k] = Q_c0[:, k], x_1[k] = Q_w[:, k])."""
+    d = C0.shape[0]
+    N = 64
+    xi = np.zeros((N, d))
+    xi[:d] = np.eye(d)
+    pf = ctx.filter(N=N, Y=np.zeros((d, 2)), m0=np.zeros(d), C0=C0, F=np.eye(d), G=np.zeros((d, d)), V=np.eye(d), W=W,
+                    resampler="systematic", keep_history=True)
+    h = pf.run(xi0=torch_dev(xi.T), xi=torch_dev(xi.T[None]), u0=np.array([0.5])).history()
+    pf.close()
+    assert np.array_equal(h["a"][1], np.arange(N))
+    return h["x"][0, :d].T.copy(), h["x"][1, :d].T.copy()
+
+
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0)])
+@pytest.mark.parametrize("d", [3, 4, 8, 16])
+def test_filter_dense_model_bit_exact_vs_oracle(ctx, orc, d, kind, nu):
+    """The GENERAL kernel path (every operator dense: F, G, V, W, C0 full; d = 3 is the padded, non-EXACT
+    instantiation) of the per-step fused kernel -- operators staged in shared memory, parent gathers
+    issued one round ahead -- against the oracle on the same pre-drawn normals / uniforms / chi factors:
+    ancestors, states and log-weights bit for bit at every step.  N spans several tiles, the last ragged."""
+    rng = np.random.default_rng(900 + d)
+    N, T = 2048 * 3 + 517, 7
+    A = rng.standard_normal((d, d)) * (0.4 / np.sqrt(d))
+    C0, W, V = spd(rng, d), spd(rng, d) * 0.6, spd(rng, d)
+    md = dict(m0=rng.standard_normal(d), C0=C0, F=np.eye(d) + A, G=0.8 * np.eye(d) + A.T, V=V, W=W)
+    Qc0, Qw = _library_factors(ctx, C0, W)
+    assert np.abs(Qw - np.diag(np.diag(Qw))).max() > 1e-3            # really dense
+    Y = rng.standard_normal((d, T))
+    xi0, xi = rng.standard_normal((N, d)), rng.standard_normal((T - 1, N, d))
+    u0 = rng.random(T - 1)
+    chi0 = chi = None
+    kw = {}
+    if kind == "mvt":
+        chi0 = np.sqrt(nu / rng.chisquare(nu, (N, d)))
+        chi = np.sqrt(nu / rng.chisquare(nu, (T - 1, N, d)))
+        kw = dict(chi0=torch_dev(chi0.T), chi=torch_dev(chi.transpose(0, 2, 1)))
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", keep_history=True, distribution=kind, df=nu, **md)
+    pf.run(xi0=torch_dev(xi0.T), xi=torch_dev(xi.transpose(0, 2, 1)), u0=u0, **kw)
+    h = pf.history()
+    pf.close()
+    ref = orc.filter_det(kind, "systematic", Y, md["m0"], Qc0, md["F"], md["G"], md["V"], Qw, N, nu=nu,
+                         xi0=xi0, xi=xi, u0=u0, chi0=chi0, chi=chi)
+    assert np.array_equal(h["a"], ref["a"])
+    assert np.array_equal(h["x"], ref["x"])
+    if kind == "mvn":
+        assert np.array_equal(h["lw"], ref["w"])
+    else:
+        assert np.allclose(h["lw"], ref["w"], rtol=1e-12, atol=1e-12)
+    assert len(np.unique(h["a"][-1])) > 100
+
+
+@pytest.mark.parametrize("d", [8, 16])
+def test_filter_dense_model_device_rng_vs_oracle_mirror(ctx, orc, d):
+    """Same path with device-drawn (reproducible) noise and no history -- the configuration the dense
+    bench line runs, minus the throughput generator: final state against the oracle's Philox mirror."""
+    rng = np.random.default_rng(950 + d)
+    N, T = 2048 * 5 + 33, 6
+    A = rng.standard_normal((d, d)) * (0.4 / np.sqrt(d))
+    C0, W = spd(rng, d), spd(rng, d) * 0.6
+    md = dict(m0=rng.standard_normal(d), C0=C0, F=np.eye(d) + A, G=0.8 * np.eye(d) + A.T, V=spd(rng, d), W=W)
+    Qc0, Qw = _library_factors(ctx, C0, W)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=31, summary=False, persistent=False,
+                    reproducible_rng=True, **md)
+    pf.run()
+    x, w, a = pf.state()
+    pf.close()
+    ref = orc.filter_det("mvn", "systematic", Y, md["m0"], Qc0, md["F"], md["G"], md["V"], Qw, N, seed=31)
+    assert np.array_equal(a, ref["a"][-1])
+    assert np.array_equal(x.T, ref["x"][-1])
+    assert np.array_equal(w, ref["w"][-1])
 
 
 @pytest.mark.parametrize("d,thr", [(2, 0.5), (8, 0.05)])
