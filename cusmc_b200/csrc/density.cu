@@ -15,6 +15,9 @@
 namespace {
 
 constexpr int kThreads = 256;
+#ifndef CUSMC_DENSITY_PDL
+#define CUSMC_DENSITY_PDL 1
+#endif
 
 // ---- SoA: x[j*ld + i].  VEC = 2 -> 128-bit loads, a thread owns points 2u and 2u+1. ----
 // One unit per thread and no grid-stride loop ON PURPOSE: with a loop (grid-stride or a
@@ -31,6 +34,12 @@ density_soa_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue e
                    const double *__restrict__ x, int64_t n_units, int64_t ld, int d,
                    double *__restrict__ out)
 {
+#if CUSMC_DENSITY_PDL
+    // Programmatic dependent launch (see launch_soa): the NEXT kernel on the stream may become resident
+    // while this grid drains; this grid touches memory only after the one before it has completed.
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
     const int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (u >= n_units) return;
     if constexpr (VEC == 2) {
@@ -98,6 +107,29 @@ density_aos_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue e
     }
 }
 
+// SoA launch.  CUSMC_DENSITY_PDL: launched as a programmatic dependent of whatever precedes it on the
+// stream -- back-to-back density calls overlap the block dispatch of call n + 1 with the tail of call n.
+template <int D, bool TRI, int VEC, bool EXACT>
+cudaError_t launch_soa(cusmc_ctx *ctx, unsigned grid, const AffineOp<D, TRI> &op, const Epilogue &ep, const double *x,
+                       int64_t units, int64_t ld, int d, double *out)
+{
+#if CUSMC_DENSITY_PDL
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(kThreads);
+    lc.stream = ctx->stream;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, density_soa_kernel<D, TRI, VEC, EXACT>, op, ep, x, units, ld, d, out);
+#else
+    density_soa_kernel<D, TRI, VEC, EXACT><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
+    return cudaSuccess;
+#endif
+}
+
 template <int D, bool TRI>
 int launch_density(cusmc_ctx *ctx, const AffineOp<D, TRI> &op, const Epilogue &ep,
                    const double *x, int layout, int64_t N, int64_t ld, int d, double *out)
@@ -111,17 +143,17 @@ int launch_density(cusmc_ctx *ctx, const AffineOp<D, TRI> &op, const Epilogue &e
             const int64_t units = N / 2;
             const unsigned grid = (unsigned)((units + kThreads - 1) / kThreads);
             if (exact)
-                density_soa_kernel<D, TRI, 2, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
+                CUSMC_CUDA(ctx, (launch_soa<D, TRI, 2, true>(ctx, grid, op, ep, x, units, ld, d, out)));
             else
-                density_soa_kernel<D, TRI, 2, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
+                CUSMC_CUDA(ctx, (launch_soa<D, TRI, 2, false>(ctx, grid, op, ep, x, units, ld, d, out)));
             CUSMC_LAUNCHED(ctx);
             return CUSMC_OK;
         }
         const unsigned grid = (unsigned)((N + kThreads - 1) / kThreads);
         if (exact)
-            density_soa_kernel<D, TRI, 1, true><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, N, ld, d, out);
+            CUSMC_CUDA(ctx, (launch_soa<D, TRI, 1, true>(ctx, grid, op, ep, x, N, ld, d, out)));
         else
-            density_soa_kernel<D, TRI, 1, false><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, N, ld, d, out);
+            CUSMC_CUDA(ctx, (launch_soa<D, TRI, 1, false>(ctx, grid, op, ep, x, N, ld, d, out)));
     } else {
         const size_t smem = sizeof(double) * kThreads * (size_t)(d | 1);
         const int64_t grid = (N + kThreads - 1) / kThreads;
