@@ -98,6 +98,36 @@ inline int cusmc_fail(cusmc_ctx *ctx, int code, const char *fmt, ...)
                               __LINE__, #call, cudaGetErrorString(e__));                \
     } while (0)
 
+// Programmatic dependent launch for the short kernels that follow each other on a stream (step /
+// resample pairs of the reference-mode filter, back-to-back density calls): the grid may become resident
+// while its predecessor drains, which hides its launch latency and block dispatch.  A kernel launched
+// this way executes cusmc_pdl_enter() BEFORE its first access to memory: it lets ITS successor do the same
+// and then waits until the predecessor has completed and its writes are visible (a no-op after an
+// ordinary launch or a copy).
+#ifdef __CUDACC__
+__device__ __forceinline__ void cusmc_pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... P, typename... A>
+inline cudaError_t cusmc_launch_pdl(void (*kernel)(P...), unsigned grid, unsigned block, size_t smem, cudaStream_t st,
+                                    A &&...args)
+{
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cudaLaunchConfig_t lc{};
+    lc.gridDim = dim3(grid);
+    lc.blockDim = dim3(block);
+    lc.dynamicSmemBytes = smem;
+    lc.stream = st;
+    lc.attrs = attr;
+    lc.numAttrs = 1;
+    return cudaLaunchKernelEx(&lc, kernel, P(args)...);
+}
+#endif
+
 #define CUSMC_CHECK(expr)                 \
     do {                                  \
         int rc__ = (expr);                \

@@ -35,10 +35,7 @@ density_soa_kernel(const __grid_constant__ AffineOp<D, TRI> op, const Epilogue e
                    double *__restrict__ out)
 {
 #if CUSMC_DENSITY_PDL
-    // Programmatic dependent launch (see launch_soa): the NEXT kernel on the stream may become resident
-    // while this grid drains; this grid touches memory only after the one before it has completed.
-    asm volatile("griddepcontrol.launch_dependents;");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
+    cusmc_pdl_enter();      // back-to-back density calls: the block dispatch of call n + 1 overlaps the tail of call n
 #endif
     const int64_t u = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     if (u >= n_units) return;
@@ -114,16 +111,7 @@ cudaError_t launch_soa(cusmc_ctx *ctx, unsigned grid, const AffineOp<D, TRI> &op
                        int64_t units, int64_t ld, int d, double *out)
 {
 #if CUSMC_DENSITY_PDL
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cudaLaunchConfig_t lc{};
-    lc.gridDim = dim3(grid);
-    lc.blockDim = dim3(kThreads);
-    lc.stream = ctx->stream;
-    lc.attrs = attr;
-    lc.numAttrs = 1;
-    return cudaLaunchKernelEx(&lc, density_soa_kernel<D, TRI, VEC, EXACT>, op, ep, x, units, ld, d, out);
+    return cusmc_launch_pdl(density_soa_kernel<D, TRI, VEC, EXACT>, grid, kThreads, 0, ctx->stream, op, ep, x, units, ld, d, out);
 #else
     density_soa_kernel<D, TRI, VEC, EXACT><<<grid, kThreads, 0, ctx->stream>>>(op, ep, x, units, ld, d, out);
     return cudaSuccess;

@@ -47,6 +47,7 @@ template <int D, bool PHILOX, bool FAST, bool MVT, bool EXACT, bool DIAG>
 __global__ void __launch_bounds__(kThreads, min_blocks(D, DIAG, MVT))
 pf_step_kernel(const __grid_constant__ StepOp<D, DIAG> op, const Epilogue ep, const StepArgs a)
 {
+    cusmc_pdl_enter();
     const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool active = i < a.n_out;
     double lw = -INFINITY;
@@ -92,11 +93,11 @@ int launch_one(cusmc_ctx *ctx, const StepModel &m, const Epilogue &ep, const Ste
     fill_step_op<D, DIAG>(op, m);
     const unsigned grid = (unsigned)((a.n_out + kThreads - 1) / kThreads);
     if (philox && a.fast_noise)
-        pf_step_kernel<D, true, true, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+        CUSMC_CUDA(ctx, cusmc_launch_pdl(pf_step_kernel<D, true, true, MVT, EXACT, DIAG>, grid, kThreads, 0, ctx->stream, op, ep, a));
     else if (philox)
-        pf_step_kernel<D, true, false, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+        CUSMC_CUDA(ctx, cusmc_launch_pdl(pf_step_kernel<D, true, false, MVT, EXACT, DIAG>, grid, kThreads, 0, ctx->stream, op, ep, a));
     else
-        pf_step_kernel<D, false, false, MVT, EXACT, DIAG><<<grid, kThreads, 0, ctx->stream>>>(op, ep, a);
+        CUSMC_CUDA(ctx, cusmc_launch_pdl(pf_step_kernel<D, false, false, MVT, EXACT, DIAG>, grid, kThreads, 0, ctx->stream, op, ep, a));
     CUSMC_LAUNCHED(ctx);
     return CUSMC_OK;
 }

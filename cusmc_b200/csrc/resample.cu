@@ -51,6 +51,7 @@ metropolis_kernel(uint32_t *__restrict__ a, const double *__restrict__ w, const 
                   const double *__restrict__ u, const uint32_t *__restrict__ j, uint64_t seed,
                   uint64_t step, int64_t N, int B, int is_log, int64_t i0, int64_t n_out)
 {
+    cusmc_pdl_enter();
     const int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x;
     const bool live = t < n_out;
     if (!C2 && !live) return;              // (C2 keeps whole warps alive: lanes draw segments for each other)
@@ -578,8 +579,9 @@ int cusmc_launch_metropolis(cusmc_ctx *ctx, uint32_t *a, const double *w, const 
     if (n_out == 0) return CUSMC_OK;
     const unsigned grid = (unsigned)((n_out + kThreads - 1) / kThreads);
     PeerWeights pw{};
-#define CUSMC_METRO_GO(PR, PE, C2) \
-    metropolis_kernel<PR, PE, C2><<<grid, kThreads, 0, ctx->stream>>>(a, w, pw, u, j, seed, step, N, B, is_log, i0, n_out)
+#define CUSMC_METRO_GO(PR, PE, C2)                                                                                       \
+    CUSMC_CUDA(ctx, cusmc_launch_pdl(metropolis_kernel<PR, PE, C2>, grid, kThreads, 0, ctx->stream, a, w, pw, u, j, seed, step, \
+                                     N, B, is_log, i0, n_out))
     if (peers) {
         pw.w = (const double *const *)peers->table_dev;
         pw.per_rank = make_fast_div((uint32_t)peers->per_rank);
