@@ -225,6 +225,10 @@ NOISE_NOTE = ("in-kernel, counter-based: philox4x32-7 + single-precision Box-Mul
               "(24-bit normals, +-6.7 sigma; the throughput generator -- reproducible_rng=1 selects philox4x32-10 + "
               "FFMA-only polynomials, which the oracle mirrors bit for bit)")
 CHAIN_NOISE_NOTE = "in-kernel philox4x32-10 + reproducible single-precision Box-Muller (mirrored bit for bit by the oracle)"
+CHAIN_FAST_NOISE_NOTE = ("in-kernel, counter-based: proposal normals from philox4x32-7 + single-precision Box-Muller on the "
+                         "special-function unit (cusmc_ctx_set_chain_noise(0), the throughput generator of the filter "
+                         "kernels); thresholds -log u with the exact fp64 logarithm; 'reproducible_noise' = the same run with "
+                         "the default generator the oracle mirrors bit for bit")
 
 
 def _timed(torch, fn, reps):
@@ -322,9 +326,12 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
         nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
         ctx.use_torch_stream()
         res = {}
-        for name, kw in (("target_factor_proposal", {}), ("isotropic_proposal", {"proposal": "isotropic"})):
+        for name, kw, fast in (("target_factor_proposal", {}, True), ("isotropic_proposal", {"proposal": "isotropic"}, True),
+                               ("target_factor_proposal_reproducible_noise", {}, False),
+                               ("isotropic_proposal_reproducible_noise", {"proposal": "isotropic"}, False)):
             if kw and not hasattr(ctx, "mh_chains_general_dev"):
                 continue
+            ctx.set_chain_noise(reproducible=not fast)
             x0 = x.clone()
             run = (lambda st, sd: ctx.mh_chains_dev("mvt", mu, Lcm, x0, st, 0.3, nu=5.0, seed=sd, n_accept=nacc)) if not kw \
                 else (lambda st, sd: ctx.mh_chains_general_dev("mvt", mu, Lcm, x0, st, 1.2 / math.sqrt(d), nu=5.0, seed=sd,
@@ -339,9 +346,11 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
             ms = e0.elapsed_time(e1)
             res[name] = {"value": Cn * steps / (ms * 1e-3), "ms": ms,
                          "accept_rate": float(nacc.double().mean().item() / steps)}
+        ctx.set_chain_noise(reproducible=True)
         first = res["target_factor_proposal"]
         line = {"value": first["value"], "chains": Cn, "d": d, "steps": steps, "ms": first["ms"],
-                "target": "mvt nu=5 per-chain L", "noise": CHAIN_NOISE_NOTE, "accept_rate": first["accept_rate"],
+                "target": "mvt nu=5 per-chain L", "noise": CHAIN_FAST_NOISE_NOTE, "accept_rate": first["accept_rate"],
+                "reproducible_noise": dict(res["target_factor_proposal_reproducible_noise"], noise=CHAIN_NOISE_NOTE),
                 "formulation": "proposal x' = x + s L_c z: whitened coordinates v' = v + s z, q' = |v'|^2; the factor "
                                "whitens the start and un-whitens the result"}
         if "isotropic_proposal" in res:
@@ -349,6 +358,7 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
             flops = 2 * d * (d + 1) / 2 + 4 * d          # forward substitution + residual + sum of squares
             line["general_proposal"] = {
                 "value": g_["value"], "ms": g_["ms"], "accept_rate": g_["accept_rate"],
+                "reproducible_noise_value": res["isotropic_proposal_reproducible_noise"]["value"],
                 "formulation": "proposal x' = x + s z (isotropic random walk): every step evaluates the target "
                                "density, q' = |L_c^-1 (x' - mu_c)|^2 by forward substitution with L_c resident on chip",
                 "fp64_flop_per_step": flops, "fp64_tflops": g_["value"] * flops / 1e12,
@@ -615,7 +625,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         dist.gather_object((xs_, ws_, as_, st), parts if rank == 0 else None, dst=0)
         if rank == 0:
             single = ctx.filter(N=n1, Y=Y, m0=md[0], C0=md[1], F=md[2], G=md[3], V=md[4], W=md[5], resampler="systematic",
-                                seed=77, summary=False, persistent=False)
+                                seed=77, summary=False, persistent=False, tile_size=2048)   # the shards' tiles
             single.run()
             x1, w1, a1 = single.state()
             single.close()
@@ -641,6 +651,7 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         del A, L
         nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
         ctx.use_torch_stream()
+        ctx.set_chain_noise(reproducible=False)                  # the throughput generator, as in the 1-GPU line
         ctx.mh_chains_dev("mvt", mu, Lcm, x, 5, 0.3, nu=5.0, seed=3 + rank, n_accept=nacc)
         dist.all_reduce(torch.cat([x.sum(0), (x * x).sum(0)]))   # warm-up of the reduction too
         torch.cuda.synchronize()
@@ -655,10 +666,11 @@ def sharded_filter_benchmark(ctx, torch, dist, world, hbm_gbs, quick):
         t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        ctx.set_chain_noise(reproducible=True)
         out["mh_c3_sharded_chain_steps_per_sec"] = {
             "value": Cn * world * steps / (ms * 1e-3), "chains": Cn * world, "chains_per_gpu": Cn, "n_gpus": world,
             "d": d, "steps": steps, "ms": ms, "scaling": "strong", "target": "mvt nu=5 per-chain L",
-            "noise": CHAIN_NOISE_NOTE, "includes": "all-reduce of the 2 d posterior moment sums"}
+            "noise": CHAIN_FAST_NOISE_NOTE, "includes": "all-reduce of the 2 d posterior moment sums"}
     except Exception as e:
         out["mh_c3_sharded_chain_steps_per_sec"] = {"error": repr(e)}
     return out

@@ -38,7 +38,7 @@ class FilterConfig(C.Structure):
         ("nu", flt), ("noise_scale", dbl), ("seed", u64),
         ("Y", vp), ("m0", vp), ("C0", vp), ("F", vp), ("G", vp), ("V", vp), ("W", vp),
         ("keep_history", ci), ("summary", ci), ("rank", ci), ("world", ci), ("persistent", ci), ("ess_threshold", dbl),
-        ("mvt_normal_init", ci), ("reproducible_rng", ci),
+        ("mvt_normal_init", ci), ("reproducible_rng", ci), ("tile_size", ci),
     ]
 
 
@@ -56,6 +56,7 @@ PROTOTYPES = {
     "cusmc_ctx_destroy": (ci, [vp]),
     "cusmc_last_error": (C.c_char_p, [vp]),
     "cusmc_ctx_set_stream": (ci, [vp, vp]),
+    "cusmc_ctx_set_chain_noise": (ci, [vp, ci]),
     "cusmc_ctx_synchronize": (ci, [vp]),
     "cusmc_ctx_launch_count": (u64, [vp]),
     "cusmc_ctx_last_kernel_ms": (dbl, [vp]),

@@ -123,6 +123,11 @@ class Context:
             raise CusmcError(rc, self.lib.cusmc_last_error(self.h).decode())
 
     # ---- stream / bookkeeping --------------------------------------------------------------
+    def set_chain_noise(self, reproducible=True):
+        """Device-drawn proposal normals of mh_chains*_dev: the host-reproducible generator (default) or the
+        throughput one (Philox4x32-7 + special-function-unit Box-Muller); see cusmc_ctx_set_chain_noise."""
+        self._check(self.lib.cusmc_ctx_set_chain_noise(self.h, int(bool(reproducible))))
+
     def set_stream(self, stream):
         """stream: a raw cudaStream_t integer, a torch.cuda.Stream, or None (context's own)."""
         ptr = None
@@ -413,7 +418,7 @@ def shard_size(N, world):
 
 def _filter_config(N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10, df=0.0,
                    noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                   persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False):
+                   persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False, tile_size=0):
     """cusmc_filter_config from numpy inputs; returns (config, arrays to keep alive while it is used)."""
     Y = np.asarray(Y, dtype=np.float64)
     if Y.ndim != 2:
@@ -435,6 +440,7 @@ def _filter_config(N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metr
     cfg.ess_threshold = float(ess_threshold)      # 0: resample every step (the reference's behaviour)
     cfg.mvt_normal_init = int(mvt_normal_init)    # "mvt": x_0 = m0 + chi (.) (Q xi) unless set
     cfg.reproducible_rng = int(reproducible_rng)  # device-drawn normals a host can regenerate bit for bit
+    cfg.tile_size = int(tile_size)                # 0: automatic (see cusmc_filter_config.tile_size)
     return cfg, keep
 
 
@@ -443,11 +449,11 @@ class ParticleFilter:
 
     def __init__(self, ctx, N, Y, m0, C0, F, G, V, W, distribution="mvn", resampler="metropolis", B=10,
                  df=0.0, noise_scale=1.0, seed=0, keep_history=False, summary=True, rank=0, world=1,
-                 persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False):
+                 persistent=True, ess_threshold=0.0, mvt_normal_init=False, reproducible_rng=False, tile_size=0):
         self.ctx = ctx
         cfg, self._keep = _filter_config(N, Y, m0, C0, F, G, V, W, distribution, resampler, B, df, noise_scale,
                                          seed, keep_history, summary, rank, world, persistent, ess_threshold,
-                                         mvt_normal_init, reproducible_rng)
+                                         mvt_normal_init, reproducible_rng, tile_size)
         self.dy, self.T, self.d, self.N = cfg.dy, cfg.T, cfg.d, int(N)
         self._world = int(world)
         per = shard_size(self.N, int(world))

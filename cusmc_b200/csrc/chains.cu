@@ -55,7 +55,10 @@ __device__ __forceinline__ double chain_sum_butterfly(double v)
 // A chain owns W = max(D, 4) lanes (D = d padded to a power of two; a quad at least, because four
 // lanes share a Philox block of normals), a warp G = 32 / W chains: at d = 8 four chains advance in
 // the instruction stream one used to take, and no lane idles.
-template <int D, bool PHILOX, bool MOMENTS>
+// FAST (with PHILOX): the throughput generator of the filter kernels for the proposal normals -- Philox4x32-7 and
+// the special-function-unit Box-Muller (cusmc_box_muller_fast: ~12 instead of ~67 instructions per pair); the
+// thresholds keep the exact logarithm.  Same law; a host cannot mirror its last bits (cusmc_ctx_set_chain_noise).
+template <int D, bool PHILOX, bool MOMENTS, bool FAST = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mh_chains_kernel(const ChainArgs a)
 {
@@ -141,11 +144,18 @@ mh_chains_kernel(const ChainArgs a)
             }
             thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
             if ((s & 3) == 0) {
-                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
-                                                 (uint32_t)(sub >> 2));
                 float n[4];
-                cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
-                cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+                if constexpr (FAST) {
+                    const cusmc_u32x4 rz = cusmc_rng7(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                      (uint32_t)(sub >> 2));
+                    cusmc_box_muller_fast(rz.v[0], rz.v[1], &n[0], &n[1]);
+                    cusmc_box_muller_fast(rz.v[2], rz.v[3], &n[2], &n[3]);
+                } else {
+                    const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                     (uint32_t)(sub >> 2));
+                    cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+                    cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int pick = (lane & 3) ^ r;        // the normal owed to lane ^ r
@@ -214,7 +224,7 @@ struct GeneralArgs {
     const double *scale;          // optional per-component proposal scale (d doubles, shared)
 };
 
-template <int D, bool PHILOX, bool MOMENTS>
+template <int D, bool PHILOX, bool MOMENTS, bool FAST = false>
 __global__ void __launch_bounds__(kWarpsPerBlock * 32)
 mh_general_kernel(const GeneralArgs ga)
 {
@@ -274,11 +284,18 @@ mh_general_kernel(const GeneralArgs ga)
             }
             thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
             if ((s & 3) == 0) {
-                const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
-                                                 (uint32_t)(sub >> 2));
                 float n[4];
-                cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
-                cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+                if constexpr (FAST) {
+                    const cusmc_u32x4 rz = cusmc_rng7(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                      (uint32_t)(sub >> 2));
+                    cusmc_box_muller_fast(rz.v[0], rz.v[1], &n[0], &n[1]);
+                    cusmc_box_muller_fast(rz.v[2], rz.v[3], &n[2], &n[3]);
+                } else {
+                    const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c,
+                                                     (uint32_t)(sub >> 2));
+                    cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+                    cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+                }
 #pragma unroll
                 for (int r = 0; r < 4; ++r) {
                     const int pick = (lane & 3) ^ r;
@@ -499,11 +516,14 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
     const unsigned grid = (unsigned)((C + per_block - 1) / per_block);
     const bool philox = z_dev == nullptr;
     const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
+    const bool fast = philox && ctx->chain_fast_noise;
 #define CUSMC_CHAIN_LAUNCH(DD, PH, MO) \
     mh_chains_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a)
 #define CUSMC_CHAIN_CASE(DD)                                                                         \
     case DD:                                                                                         \
-        if (philox && moments) CUSMC_CHAIN_LAUNCH(DD, true, true);                                   \
+        if (fast && moments) mh_chains_kernel<DD, true, true, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a); \
+        else if (fast) mh_chains_kernel<DD, true, false, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);      \
+        else if (philox && moments) CUSMC_CHAIN_LAUNCH(DD, true, true);                              \
         else if (philox) CUSMC_CHAIN_LAUNCH(DD, true, false);                                        \
         else if (moments) CUSMC_CHAIN_LAUNCH(DD, false, true);                                       \
         else CUSMC_CHAIN_LAUNCH(DD, false, false);                                                   \
@@ -548,11 +568,14 @@ extern "C" int cusmc_mh_chains_general_dev(cusmc_ctx *ctx, int kind, int64_t C, 
     const unsigned grid = (unsigned)((C + per_block - 1) / per_block);
     const bool philox = z_dev == nullptr;
     const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
+    const bool fast = philox && ctx->chain_fast_noise;
 #define CUSMC_GEN_LAUNCH(DD, PH, MO) \
     mh_general_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga)
 #define CUSMC_GEN_CASE(DD)                                                                           \
     case DD:                                                                                         \
-        if (philox && moments) CUSMC_GEN_LAUNCH(DD, true, true);                                     \
+        if (fast && moments) mh_general_kernel<DD, true, true, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga); \
+        else if (fast) mh_general_kernel<DD, true, false, true><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga);      \
+        else if (philox && moments) CUSMC_GEN_LAUNCH(DD, true, true);                                \
         else if (philox) CUSMC_GEN_LAUNCH(DD, true, false);                                          \
         else if (moments) CUSMC_GEN_LAUNCH(DD, false, true);                                         \
         else CUSMC_GEN_LAUNCH(DD, false, false);                                                     \

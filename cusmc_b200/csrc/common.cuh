@@ -73,6 +73,9 @@ struct cusmc_ctx {
     // batch after batch under one distribution -- the reference builds its distribution object once
     // and calls pdf() many times, src/mcmc.cpp:53-58 -- pays for it once, not per 25 us kernel
     cusmc_density_cache *dcache = nullptr;
+    // cusmc_ctx_set_chain_noise: 1 = the MH chain kernels draw their proposal normals with the throughput
+    // generator (Philox4x32-7, special-function-unit Box-Muller) instead of the host-reproducible one
+    int chain_fast_noise = 0;
 };
 
 void cusmc_density_cache_free(cusmc_ctx *ctx);

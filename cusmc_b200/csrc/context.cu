@@ -76,6 +76,13 @@ extern "C" int cusmc_ctx_set_stream(cusmc_ctx *ctx, void *cuda_stream)
     return CUSMC_OK;
 }
 
+extern "C" int cusmc_ctx_set_chain_noise(cusmc_ctx *ctx, int reproducible)
+{
+    if (!ctx) return CUSMC_ERR_INVALID;
+    ctx->chain_fast_noise = reproducible ? 0 : 1;
+    return CUSMC_OK;
+}
+
 extern "C" int cusmc_ctx_synchronize(cusmc_ctx *ctx)
 {
     if (!ctx) return CUSMC_ERR_INVALID;

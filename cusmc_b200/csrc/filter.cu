@@ -472,6 +472,16 @@ extern "C" int cusmc_filter_destroy(cusmc_filter *f)
     return CUSMC_OK;
 }
 
+// Particles per tile of the per-step path: kTile unless the caller fixes it (cfg.tile_size).  An automatic
+// "whole waves of resident blocks" choice was measured and dropped: a C5 shard as 4370 tiles of 1920 (5.9 waves
+// of 740 blocks) instead of 4096 tiles of 2048 (5.5 waves) runs at 240 us per step instead of 233 (1792: 243;
+// dense model 370 vs 357; 16 Mi particles 460 vs 447) -- blocks finish staggered, so the last wave costs less
+// than its emptiness suggests, and every extra tile pays its own lookup, scans and a half-empty last round.
+static uint32_t pick_step_tile(const cusmc_filter *f)
+{
+    return f->cfg.tile_size ? (uint32_t)f->cfg.tile_size : (uint32_t)kTile;
+}
+
 extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cfg, cusmc_filter **out)
 {
     if (!ctx || !out) return CUSMC_ERR_INVALID;
@@ -485,6 +495,11 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
     CUSMC_REQUIRE(ctx, cfg->resampler >= 0 && cfg->resampler <= 4, "unknown resampler");
     CUSMC_REQUIRE(ctx, cfg->kind == CUSMC_MVN || cfg->nu > 0.0f, "mvt needs nu > 0");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold >= 0.0 && cfg->ess_threshold <= 1.0, "ess_threshold must lie in [0, 1]");
+    CUSMC_REQUIRE(ctx, cfg->tile_size == 0 || (cfg->tile_size >= 32 && cfg->tile_size <= kTile && cfg->tile_size % 32 == 0),
+                  "tile_size must be 0 or a multiple of 32 in [32, 2048]");
+    CUSMC_REQUIRE(ctx, cfg->tile_size == 0 || cfg->tile_size == kTile ||
+                           (cfg->world <= 1 && cfg->resampler == CUSMC_RESAMPLE_SYSTEMATIC),
+                  "tile_size other than 2048: single-GPU systematic resampling only");
     CUSMC_REQUIRE(ctx, cfg->ess_threshold == 0.0 || cfg->resampler == CUSMC_RESAMPLE_SYSTEMATIC,
                   "adaptive resampling needs the systematic resampler");
     const int world = cfg->world <= 1 ? 1 : cfg->world;
@@ -535,6 +550,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         delete f;
         return rc;
     }
+    f->tile = pick_step_tile(f);
     cudaError_t e = cudaSetDevice(ctx->device);
     f->pooled = world == 1;
     auto alloc = [&](void **p, size_t bytes) {
@@ -554,6 +570,7 @@ extern "C" int cusmc_filter_create(cusmc_ctx *ctx, const cusmc_filter_config *cf
         f->persist_tile = cusmc_filter_persistent_tile(f);
         f->img_n = f->per;
         if (f->persist_tile) f->img_n = std::max<int64_t>(f->img_n, (N + f->persist_tile - 1) / f->persist_tile * (int64_t)kTile);
+        if (f->tile != (uint32_t)kTile) f->img_n = std::max<int64_t>(f->img_n, (N + f->tile - 1) / f->tile * (int64_t)kTile);
         const size_t img_bytes = sizeof(unsigned long long) * (size_t)fimage_words(f->img_n);
         for (int b = 0; b < 2; ++b) {
             alloc((void **)&f->img[b], img_bytes);
@@ -657,7 +674,7 @@ extern "C" int64_t cusmc_filter_tile_size(cusmc_filter *f)
 {
     if (!f) return 0;
     // what cusmc_filter_run (without injected per-particle draws) will use
-    return cusmc_filter_persistent_eligible(f, nullptr) ? (int64_t)f->persist_tile : (int64_t)kTile;
+    return cusmc_filter_persistent_eligible(f, nullptr) ? (int64_t)f->persist_tile : (int64_t)f->tile;
 }
 
 extern "C" int cusmc_filter_slot_dev(cusmc_filter *f, int t, void **slot_dev)
@@ -750,8 +767,8 @@ static pffused::FusedArgs filter_fused_args(cusmc_filter *f, const StepArgs &a, 
     fa.img_hdr_words = fimage_header_words(f->img_n);
     fa.tiles_alloc = (uint32_t)fimage_tiles(f->img_n);
     fa.N_global = (uint32_t)f->cfg.N;
-    fa.tiles_per_rank = (uint32_t)(f->per / kTile > 0 ? (f->per + kTile - 1) / kTile : 1);
-    fa.tile_n = (uint32_t)kTile;
+    fa.tiles_per_rank = (uint32_t)(f->per / f->tile > 0 ? (f->per + f->tile - 1) / f->tile : 1);
+    fa.tile_n = f->tile;
     fa.shift = f->shift;
     return fa;
 }
@@ -824,7 +841,7 @@ static int filter_tile_update(cusmc_filter *f, int t, int phases)
     u.slot = f->slots + t;
     u.slot_next = t + 1 < cfg.T ? f->slots + t + 1 : nullptr;
     u.rank_sums = f->rank_sums;
-    u.tiles = (f->n + kTile - 1) / kTile;
+    u.tiles = (f->n + f->tile - 1) / f->tile;
     u.tiles_alloc = fimage_tiles(f->img_n);
     u.lo = (unsigned)f->lo;
     u.N_global = (unsigned)cfg.N;

@@ -50,6 +50,7 @@ struct cusmc_filter {
     void *persist = nullptr;          // scratch of the persistent-kernel run (pf_persist.cu)
     size_t persist_bytes = 0;
     uint32_t persist_tile = 0;        // particles per block of a persistent run (0: not covered / does not fit)
+    uint32_t tile = 2048;             // particles per tile of the per-step path (cfg.tile_size; kTile unless balanced)
     int64_t img_n = 0;                // particle count the weight images are laid out for (image.cuh)
     double *hist_x = nullptr, *hist_w = nullptr;
     uint32_t *hist_a = nullptr;

@@ -259,7 +259,7 @@ __device__ __forceinline__ void lookup_parents(const FusedArgs &fa, const StepCo
 #endif
 // dense operators up to d = 16 are staged in shared memory (3 d^2 doubles: 6 KB at d = 16)
 __host__ __device__ constexpr bool dense_smop(int D, bool diag) { return !diag && D <= 16 && CUSMC_DENSE_SMOP != 0; }
-constexpr int min_blocks(int D, bool diag, bool mvt)
+__host__ __device__ constexpr int min_blocks(int D, bool diag, bool mvt)
 {
     return D >= 32 ? (diag ? 2 : 1) : (D >= 16 ? 2 : (D >= 8 ? (diag && !mvt ? CUSMC_FUSED_MINB8 : (diag ? 3 : CUSMC_DENSE_MINB8)) : 4));
 }
@@ -496,7 +496,7 @@ int launch_one(cusmc_ctx *ctx, const pfstep::StepModel &m, const Epilogue &ep, c
 {
     StepOp<D, DIAG> op;
     pfstep::fill_step_op<D, DIAG>(op, m);
-    const unsigned grid = (unsigned)((fa.s.n_out + kTile - 1) / kTile);
+    const unsigned grid = (unsigned)((fa.s.n_out + fa.tile_n - 1) / fa.tile_n);
     const bool peers = fa.s.world > 1;
     // launched as a programmatic dependent of the kernel before it on the stream (the tile update, which
     // releases its dependents as soon as it starts): see pf_fused_kernel

@@ -281,6 +281,14 @@ int cusmc_normalize_ess(cusmc_ctx *ctx, const double *lw, int64_t N, double *lse
  * n_accept_dev (C), accept_bits_dev (C x steps bytes), sum_x_dev / sum_xx_dev (C x d running
  * sums over steps) are optional.
  */
+/* Device-drawn proposal normals of both chain entry points (z_dev == NULL): reproducible = 1 (the default)
+ * draws them with Philox4x32-10 and the FFMA-only Box-Muller a host regenerates bit for bit (the oracle's
+ * mirror; what the bit-exact tests use); 0 = the throughput generator of the filter kernels (Philox4x32-7,
+ * Box-Muller on the special-function unit): same law and resolution, ~1/4 of the instructions per normal,
+ * last bits not reproducible on a CPU.  Thresholds keep the exact logarithm either way; pre-drawn z / thr
+ * are unaffected.  (The filter's switch is cusmc_filter_config.reproducible_rng.) */
+int cusmc_ctx_set_chain_noise(cusmc_ctx *ctx, int reproducible);
+
 int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, int steps,
                         double step_size, double nu, int shared,
                         const double *mu_dev, const double *L_dev, double *x_dev,
@@ -354,6 +362,11 @@ typedef struct cusmc_filter_config {
      * it, so device-drawn runs can be checked bit for bit on a CPU.  Same law and resolution either way;
      * injected draws are unaffected. */
     int reproducible_rng;
+    /* Particles per weight-image tile of the per-step path (a tile = the children one thread block finishes;
+     * the weight image, hence every bit of a run, is defined per tile).  0 = 2048.  A multiple of 32 in
+     * [32, 2048] (single GPU, systematic resampling) reproduces a run whose tile was something else -- the
+     * persistent kernel's evenly spread tile, as reported by cusmc_filter_tile_size(). */
+    int tile_size;
 } cusmc_filter_config;
 
 /* Injected randomness for one run (all DEVICE pointers, any may be NULL -> Philox):

@@ -27,10 +27,12 @@ else:
     md = dict(m0=np.zeros(d), C0=I, F=I, G=I, V=0.1 * I, W=0.1 * I)
 if len(sys.argv) > 3:
     N = int(sys.argv[3])
-pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=2, summary=False, **md)
+tile = int(os.environ.get("TILE", "0"))           # 0: the library's automatic tile
+pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=2, summary=False, tile_size=tile, **md)
 pf.run()
 ctx.synchronize()
 pf.run()
 ms = pf.last_ms
+print("tile %d " % pf.tile_size, end="")
 print("%s N=%d: %.1f us/step, %.3f ns/particle-step" % (which, N, ms / (T - 1) * 1e3, ms / (T - 1) * 1e6 / N))
 pf.close()

@@ -732,6 +732,48 @@ def test_filter_dense_model_device_rng_vs_oracle_mirror(ctx, orc, d):
     assert np.array_equal(w, ref["w"][-1])
 
 
+@pytest.mark.parametrize("d,tile,N", [(8, 1920, 2 * 1920 + 777), (8, 96, 5000), (2, 1696, 9000), (4, 2048, 7000)])
+def test_filter_tile_size_bit_exact_vs_oracle(ctx, orc, d, tile, N):
+    """cfg.tile_size: the per-step path with a caller-chosen tile (e.g. to reproduce a persistent run's evenly
+    spread tile on the per-step path).  The weight image is defined per tile, so the oracle is told the tile:
+    final states, log-weights and ancestors bit for bit, for tiles that are not a multiple of the block size,
+    with a ragged last tile."""
+    rng = np.random.default_rng(17 * d + tile)
+    T = 9
+    md = _model(d)
+    Y = rng.standard_normal((d, T))
+    pf = ctx.filter(N=N, Y=Y, resampler="systematic", seed=123, summary=False, persistent=False, reproducible_rng=True,
+                    tile_size=tile, **md)
+    assert pf.tile_size == tile
+    pf.run()
+    x, w, a = pf.state()
+    s = pf.summary()
+    pf.close()
+    ref = orc.filter_det("mvn", "systematic", Y, md["m0"], _eig_factor(md["C0"]), md["F"], md["G"], md["V"],
+                         _eig_factor(md["W"]), N, seed=123, tile=tile)
+    assert np.array_equal(a, ref["a"][-1])
+    assert np.array_equal(x.T, ref["x"][-1])
+    assert np.array_equal(w, ref["w"][-1])
+    assert np.allclose(s["ess"], ref["ess"], rtol=1e-12)
+    assert np.allclose(s["loglik"], ref["loglik"], rtol=1e-12, atol=1e-12)
+
+
+def test_filter_tile_size_default_and_validation(ctx):
+    """The tile is 2048 unless the caller fixes it; bad values are refused."""
+    import cusmc_b200
+    d = 8
+    md = _model(d)
+    Y = np.random.default_rng(3).standard_normal((d, 4))
+    for N, resampler in ((100000, "systematic"), (8 << 20, "systematic"), (50000, "multinomial")):
+        pf = ctx.filter(N=N, Y=Y, resampler=resampler, summary=False, persistent=False, **md)
+        assert pf.tile_size == 2048
+        pf.close()
+    with pytest.raises(cusmc_b200.CusmcError):
+        ctx.filter(N=5000, Y=Y, resampler="systematic", tile_size=100, **md)          # not a multiple of 32
+    with pytest.raises(cusmc_b200.CusmcError):
+        ctx.filter(N=5000, Y=Y, resampler="multinomial", tile_size=1024, **md)        # systematic only
+
+
 @pytest.mark.parametrize("d,thr", [(2, 0.5), (8, 0.05)])
 def test_adaptive_resampling_bit_exact_vs_oracle(ctx, orc, d, thr):
     """ess_threshold: resample only when ESS < threshold N, otherwise keep a_i = i and accumulate the
@@ -1126,6 +1168,49 @@ def test_mh_chains_general_proposal_bit_exact(ctx, orc, kind, nu, d, shared, Cn,
     assert np.array_equal(nacc.cpu().numpy().astype(np.uint32), want_n)
     assert np.array_equal(x.cpu().numpy(), want_x)
     assert 0.05 < want_bits.mean() < 0.95
+
+
+@pytest.mark.parametrize("general", [False, True])
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 7.0)])
+def test_mh_chains_throughput_noise_law(ctx, general, kind, nu):
+    """cusmc_ctx_set_chain_noise(0): proposal normals from Philox4x32-7 + the special-function-unit Box-Muller.
+    Not reproducible on a host, so the check is the law: many chains on one target, time-averaged mean and
+    variance against the target's (MVT: covariance nu / (nu - 2) Sigma), both kernels; and the switch really
+    changes the draws while the default stays the mirrored generator."""
+    import torch
+    rng = np.random.default_rng(555)
+    d, Cn, steps = 4, 4096, 3000
+    S = spd(rng, d)
+    Ls, mus = np.linalg.cholesky(S), rng.standard_normal(d)
+    run = ctx.mh_chains_general_dev if general else ctx.mh_chains_dev
+    step = 1.1 if general else 0.9
+
+    def chains(seed, n_steps):
+        x = torch_dev(np.tile(mus, (Cn, 1)))
+        sx = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
+        sxx = torch.zeros_like(sx)
+        nacc = torch.zeros(Cn, dtype=torch.int32, device="cuda")
+        run(kind, torch_dev(mus), torch_dev(Ls.T), x, n_steps, step, nu=nu, shared=True, seed=seed, n_accept=nacc,
+            sum_x=sx, sum_xx=sxx)
+        ctx.synchronize()
+        return x.cpu().numpy(), sx.cpu().numpy(), sxx.cpu().numpy(), nacc.cpu().numpy()
+
+    x_rep, _, _, _ = chains(78, 20)
+    ctx.set_chain_noise(reproducible=False)
+    try:
+        x_fast, _, _, _ = chains(78, 20)
+        _, sx, sxx, nacc = chains(79, steps)
+    finally:
+        ctx.set_chain_noise(reproducible=True)
+    x_rep2, _, _, _ = chains(78, 20)
+    assert np.array_equal(x_rep, x_rep2) and not np.array_equal(x_rep, x_fast)
+    mean = sx.mean(0) / steps
+    var = sxx.mean(0) / steps - mean ** 2
+    target_var = np.diag(S) * (nu / (nu - 2.0) if kind == "mvt" else 1.0)
+    assert 0.1 < nacc.mean() / steps < 0.7
+    tol = 6 * np.sqrt(target_var * 60 / (Cn * steps))
+    assert np.all(np.abs(mean - mus) < tol)
+    assert np.all(np.abs(var / target_var - 1.0) < (0.1 if kind == "mvt" else 0.05))
 
 
 def test_mh_chains_general_device_rng(ctx, orc):
