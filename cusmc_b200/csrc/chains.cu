@@ -246,6 +246,10 @@ mh_general_kernel(const GeneralArgs ga)
     // one coalesced line).  With r~_k = r_k / L_kk carried instead of r_k the substitution's dependent
     // chain is shuffle -> FMA per column, the division's multiply is off it (1.9e9 -> 2.1e9 chain-steps/s).
     const double rinv = live ? 1.0 / __ldg(Lc + (size_t)sub * d + sub) : 0.0;
+    // (Rows in shared memory instead -- column j of all lanes contiguous, 72 registers, 24 instead of 16 warps per
+    // SM -- were measured: 2.05e9 against 2.22e9 chain-steps/s.  The step is not short of warps: its 64 SHFL per
+    // step (two per broadcast double) keep the shuffle / shared-memory pipe half busy by themselves, and the
+    // extra LDS go through the same pipe.)
     double row[D];
 #pragma unroll
     for (int j = 0; j < D; ++j) row[j] = (live && j < sub) ? __ldg(Lc + (size_t)j * d + sub) * rinv : 0.0;
