@@ -704,10 +704,9 @@ def main():
     numa_node = bind_to_gpu_numa_node(torch, local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        # stdout carries ONE JSON line: NCCL's version banner (NCCL_DEBUG=VERSION prints it there) is dropped,
-        # any louder setting the caller chose (INFO, TRACE) is kept
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # stdout carries ONE JSON line: whatever NCCL logs (its version banner at NCCL_DEBUG=VERSION / WARN, more at
+        # INFO) goes to stderr unless the caller chose a file
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     import cusmc_b200
     ctx = cusmc_b200.Context(local_rank)
