@@ -129,6 +129,53 @@ __device__ __forceinline__ void chi_fast(uint64_t seed, uint64_t step, uint64_t 
     for (int k = 0; k < D; ++k) chi[k] = rsqrtf(scale * g[k]);
 }
 
+// Integer nu (throughput generator): chi^2_nu = 2 Gamma(nu / 2) without rejection.  Gamma(k + odd / 2) is the sum
+// of k unit exponentials and, for odd nu, half a squared normal:  g = -ln(U_1 ... U_k) + odd Z^2 / 2.  Straight-line
+// code, no retries and therefore no divergence (chi_fast pays ~1.8 retry rounds per particle because a warp almost
+// always holds a rejected lane, and runs the squeeze's logarithms for the same reason): nu = 5 costs 6 Philox
+// blocks and 16 logarithms per d = 8 particle -- ~58 instead of ~112 instructions per factor.  One block serves
+// four components; k is uniform over the grid.  Used for integer nu <= kHalfIntMaxNu: its cost grows with nu and
+// Marsaglia-Tsang's does not -- measured per d = 8 C5 step (chi_fast: 470-495 us at every nu): nu = 3: 374 us,
+// 5: 412, 8: 450, 12: 536.  Same law as chi_fast / chi_pair (KS against t_nu, 10^6 draws x 6 seeds: p-values
+// uniform, profiles/mvt_ks.py), other draws.
+constexpr int kHalfIntMaxNu = 8;
+template <int D>
+__device__ __forceinline__ void chi_halfint(uint64_t seed, uint64_t step, uint64_t index, int nu_int, float (&chi)[D])
+{
+    const int k = nu_int >> 1;
+    float acc[D];                       // sum of log2 U
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = 0.0f;
+    for (int i = 0; i < k; ++i) {
+#pragma unroll
+        for (int q = 0; q < (D + 3) / 4; ++q) {
+            const cusmc_u32x4 r = cusmc_rng7(seed, CUSMC_STREAM_CHI, step, index, 0x4000u | ((uint32_t)q << 8) | (uint32_t)i);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < D)      // U = (word + 1/2) 2^-32 in (0, 1]
+                    acc[4 * q + e] += __log2f(fmaf((float)r.v[e], 2.3283064365386963e-10f, 1.16415321826934814e-10f));
+        }
+    }
+    float g[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) g[c] = -0.6931471805599453f * acc[c];
+    if (nu_int & 1) {
+#pragma unroll
+        for (int q = 0; q < (D + 3) / 4; ++q) {
+            const cusmc_u32x4 r = cusmc_rng7(seed, CUSMC_STREAM_CHI, step, index, 0x6000u | ((uint32_t)q << 8));
+            float z[4];
+            cusmc_box_muller_fast(r.v[0], r.v[1], &z[0], &z[1]);
+            cusmc_box_muller_fast(r.v[2], r.v[3], &z[2], &z[3]);
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+                if (4 * q + e < D) g[4 * q + e] = fmaf(0.5f * z[e], z[e], g[4 * q + e]);
+        }
+    }
+    const float scale = 2.0f / (float)nu_int;
+#pragma unroll
+    for (int c = 0; c < D; ++c) chi[c] = rsqrtf(fmaxf(scale * g[c], 1e-37f));      // g = 0 has probability ~2^-32 per draw
+}
+
 // The block of (seed, stream, step, particle, quad): Philox4x32-10, or -7 on the throughput path.
 template <bool FAST>
 __device__ __forceinline__ cusmc_u32x4 step_rng(uint64_t seed, int stream, uint64_t step, uint64_t index, uint32_t sub)
@@ -141,6 +188,9 @@ __device__ __forceinline__ cusmc_u32x4 step_rng(uint64_t seed, int stream, uint6
 // Throughput noise at D <= 2: a Philox block makes four normals and a particle needs two, so the
 // neighbours 2p and 2p + 1 share the block of p (first pair | second pair): half the generator work of a
 // d = 2 step.  Keyed by the GLOBAL slot, so shards and the persistent kernel draw the same normals.
+#ifndef CUSMC_CHI_HALFINT
+#define CUSMC_CHI_HALFINT 1
+#endif
 #ifndef CUSMC_PAIR_D2
 #define CUSMC_PAIR_D2 1
 #endif
@@ -260,7 +310,14 @@ __device__ __forceinline__ double particle_step(const StepOp<D, DIAG> &op, const
     double chi[MVT ? D : 1];
     bool chi_drawn = false;
     if constexpr (MVT && FAST) {
-        if (!a.chi && a.nu >= 2.0f) {
+        const int nu_int = (int)a.nu;
+        if (!a.chi && CUSMC_CHI_HALFINT != 0 && (float)nu_int == a.nu && nu_int >= 1 && nu_int <= kHalfIntMaxNu) {
+            float cf[D];
+            chi_halfint<D>(a.seed, a.step, idx, nu_int, cf);
+#pragma unroll
+            for (int k = 0; k < D; ++k) chi[MVT ? k : 0] = (double)cf[k];
+            chi_drawn = true;
+        } else if (!a.chi && a.nu >= 2.0f) {
             float cf[D];
             chi_fast<D>(a.seed, a.step, idx, a.nu, cf);
 #pragma unroll

@@ -496,10 +496,11 @@ def test_filter_bit_exact_vs_oracle(ctx, orc, resampler, d, kind, nu):
 
 
 @pytest.mark.parametrize("reproducible", [False, True])
-@pytest.mark.parametrize("nu,d", [(5.0, 8), (2.5, 3), (1.5, 2)])
+@pytest.mark.parametrize("nu,d", [(5.0, 8), (2.5, 3), (1.5, 2), (1.0, 4), (2.0, 2), (4.0, 8), (8.0, 3), (13.0, 4), (7.5, 8)])
 def test_mvt_device_noise_is_student_t(ctx, reproducible, nu, d):
     """Device-drawn "mvt" noise inside the filter, both generators (the throughput one draws its chi factors
-    with chi_fast for nu >= 2): with G = 0 and W = C0 = I every component of x_0 and x_1 is chi z ~ t_nu.
+    without rejection for integer nu <= 8 -- sums of exponentials and half a squared normal, chi_halfint -- and
+    with chi_fast for the other nu >= 2): with G = 0 and W = C0 = I every component of x_0 and x_1 is chi z ~ t_nu.
     Kolmogorov-Smirnov per component, and the chi factors of different components are independent."""
     from scipy import stats
     N, T = 120000, 2
@@ -513,7 +514,8 @@ def test_mvt_device_noise_is_student_t(ctx, reproducible, nu, d):
         x = h["x"][t]
         assert np.all(np.isfinite(x))
         for k in range(d):
-            assert stats.kstest(x[:, k], "t", args=(nu,)).pvalue > 1e-3, (t, k)
+            # ~170 KS tests over the parametrisation: 1e-4 keeps the family-wise false-alarm rate below 2 %
+            assert stats.kstest(x[:, k], "t", args=(nu,)).pvalue > 1e-4, (t, k)
         # |x_k| of two components would correlate if they shared a chi factor
         r = np.corrcoef(np.log(np.abs(x) + 1e-300).T)
         assert np.all(np.abs(r - np.eye(d)) < 0.02), (t, r)
