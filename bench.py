@@ -305,8 +305,9 @@ def secondary_benchmarks(ctx, torch, hbm_gbs, quick):
         Y = np.random.default_rng(5000).standard_normal((d, T))
         line = _pf_line(ctx, N, d, T, dict(m0=np.zeros(d), C0=I, F=I, G=0.9 * I, V=I, W=I), Y, 160, hbm_gbs, seed=2,
                         summary=False, distribution="mvt", df=5.0)
-        line["noise"] = ("normals as above; chi factors sqrt(nu / chi2_nu): Marsaglia-Tsang gammas in single precision, one "
-                         "philox4x32-10 block per pair of components")
+        line["noise"] = ("normals as above; chi factors sqrt(nu / chi2_nu), nu = 5: chi2_nu = 2 Gamma(nu / 2) as a sum of two unit "
+                         "exponentials plus half a squared normal (the rejection-free path of integer nu <= 8, philox4x32-7; "
+                         "other nu: Marsaglia-Tsang gammas), single precision")
         return line
     guarded("pf_c5_shard_mvt_particle_steps_per_sec", c5_mvt)
 
