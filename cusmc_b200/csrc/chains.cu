@@ -22,6 +22,9 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef CUSMC_GENERAL_DUAL
+#define CUSMC_GENERAL_DUAL 1
+#endif
 
 struct ChainArgs {
     const double *mu, *L, *z, *thr;
@@ -343,6 +346,155 @@ mh_general_kernel(const GeneralArgs ga)
     if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
 }
 
+// ---- the same chains at 16 < d <= 32: TWO rows per lane, two chains per warp ---------------------------------
+// mh_general_kernel<32> gives a chain a whole warp: 32 broadcast rounds of two SHFL and two DFMA in which, on
+// average, half the lanes multiply by a zero of the triangle -- its shuffle pipe is half busy with 16 warps per SM
+// and more warps do not help (see the note there).  Here lane l of a 16-lane group owns components l and l + 16:
+// rounds 0..15 broadcast the first residual (both rows updated), rounds 16..31 the second (only the second row has
+// entries there), and ONE warp-wide shuffle serves two chains: half the shuffles and 5/8 of the FMAs per
+// chain-step.  Same operations on the same values in the same order for every component (the skipped updates
+// multiplied by an exact zero), same (seed, chain, step, component) -> draw mapping: bit-identical to the one-row
+// kernel and to the oracle (orc_mh_chains_general).
+template <bool PHILOX, bool MOMENTS, bool FAST>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 3)
+mh_general_dual_kernel(const GeneralArgs ga)
+{
+    const ChainArgs &a = ga.c;
+    constexpr int W = 16, H = 16;                    // lanes per chain; lane l: components l and l + H
+    constexpr int G = 32 / W;
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / W, sub = lane % W;
+    const int64_t c0 = ((int64_t)blockIdx.x * kWarpsPerBlock + wib) * G;
+    if (c0 >= a.C) return;
+    const int d = a.d;                               // 16 < d <= 32
+    const bool active = c0 + grp < a.C;
+    const int64_t c = active ? c0 + grp : a.C - 1;
+    const bool live0 = active, live1 = active && sub + H < d;
+    const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
+    const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
+    const double mu0 = live0 ? __ldg(mc + sub) : 0.0, mu1 = live1 ? __ldg(mc + sub + H) : 0.0;
+    const double rinv0 = live0 ? 1.0 / __ldg(Lc + (size_t)sub * d + sub) : 0.0;
+    const double rinv1 = live1 ? 1.0 / __ldg(Lc + (size_t)(sub + H) * d + sub + H) : 0.0;
+    double rowA[H], rowB[2 * H];                     // rows sub and sub + H, pre-scaled by 1 / L_kk (column-major L)
+#pragma unroll
+    for (int j = 0; j < H; ++j) rowA[j] = (live0 && j < sub) ? __ldg(Lc + (size_t)j * d + sub) * rinv0 : 0.0;
+#pragma unroll
+    for (int j = 0; j < 2 * H; ++j) rowB[j] = (live1 && j < sub + H) ? __ldg(Lc + (size_t)j * d + sub + H) * rinv1 : 0.0;
+    const double s0 = a.step_size * ((ga.scale && live0) ? __ldg(ga.scale + sub) : 1.0);
+    const double s1 = a.step_size * ((ga.scale && live1) ? __ldg(ga.scale + sub + H) : 1.0);
+
+    auto quadform = [&](double xa, double xb) {
+        double ra = live0 ? (xa - mu0) * rinv0 : 0.0, rb = live1 ? (xb - mu1) * rinv1 : 0.0, q = 0.0;
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, ra, j, W);
+            q = fma(vj, vj, q);
+            ra = fma(-rowA[j], vj, ra);
+            rb = fma(-rowB[j], vj, rb);
+        }
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, rb, j, W);
+            q = fma(vj, vj, q);
+            rb = fma(-rowB[H + j], vj, rb);
+        }
+        return q;
+    };
+    double x0 = live0 ? a.x[(size_t)c * d + sub] : 0.0, x1 = live1 ? a.x[(size_t)c * d + sub + H] : 0.0;
+    double q = quadform(x0, x1);
+    const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
+    double sx0 = 0.0, sxx0 = 0.0, sx1 = 0.0, sxx1 = 0.0;
+    uint32_t nacc = 0;
+
+    const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
+    double zn0 = (zc && live0) ? ld_stream(zc + sub) : 0.0, zn1 = (zc && live1) ? ld_stream(zc + sub + H) : 0.0;
+    // randomness batched as in mh_general_kernel; the block (step, m) holds the normals of components 4m .. 4m + 3,
+    // so this lane's quad computes blocks m = sub / 4 and m + 4
+    double thr_batch = 0.0;
+    float zq0[4] = {0.f, 0.f, 0.f, 0.f}, zq1[4] = {0.f, 0.f, 0.f, 0.f};
+    auto quad_normals = [&](int s, uint32_t m, float (&zq)[4]) {
+        float n[4];
+        if constexpr (FAST) {
+            const cusmc_u32x4 rz = cusmc_rng7(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c, m);
+            cusmc_box_muller_fast(rz.v[0], rz.v[1], &n[0], &n[1]);
+            cusmc_box_muller_fast(rz.v[2], rz.v[3], &n[2], &n[3]);
+        } else {
+            const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c, m);
+            cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+            cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int pick = (lane & 3) ^ r;
+            const float val = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
+            zq[r] = __shfl_xor_sync(0xffffffffu, val, r);
+        }
+    };
+    for (int s = 0; s < a.steps; ++s) {
+        double z0, z1, thr;
+        if (PHILOX) {
+            if ((s & (W - 1)) == 0) {
+                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + sub), (uint64_t)c, 0);
+                const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+                thr_batch = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+            }
+            thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
+            if ((s & 3) == 0) {
+                quad_normals(s, (uint32_t)(sub >> 2), zq0);
+                quad_normals(s, (uint32_t)(sub >> 2) + (uint32_t)(H / 4), zq1);
+            }
+            const int r = (lane & 3) ^ (s & 3);
+            const float f0 = r == 0 ? zq0[0] : r == 1 ? zq0[1] : r == 2 ? zq0[2] : zq0[3];
+            const float f1 = r == 0 ? zq1[0] : r == 1 ? zq1[1] : r == 2 ? zq1[2] : zq1[3];
+            z0 = live0 ? (double)f0 : 0.0;
+            z1 = live1 ? (double)f1 : 0.0;
+        } else {
+            z0 = zn0;
+            z1 = zn1;
+            if (s + 1 < a.steps) {
+                if (live0) zn0 = ld_stream(zc + (size_t)(s + 1) * d + sub);
+                if (live1) zn1 = ld_stream(zc + (size_t)(s + 1) * d + sub + H);
+            }
+            thr = __ldg(a.thr + (size_t)c * a.steps + s);
+        }
+        const double xp0 = fma(s0, z0, x0), xp1 = fma(s1, z1, x1);
+        const double qp = quadform(xp0, xp1);
+        bool accept;
+        if (a.kind == CUSMC_MVT)
+            accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
+        else
+            accept = 0.5 * (qp - q) < thr;
+        if (accept) {
+            x0 = xp0;
+            x1 = xp1;
+            q = qp;
+            ++nacc;
+        }
+        if (MOMENTS) {
+            sx0 += x0;
+            sxx0 = fma(x0, x0, sxx0);
+            sx1 += x1;
+            sxx1 = fma(x1, x1, sxx1);
+        }
+        if (a.accept_bits && sub == 0 && active) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
+    }
+    if (live0) {
+        a.x[(size_t)c * d + sub] = x0;
+        if (MOMENTS) {
+            if (a.sum_x) a.sum_x[(size_t)c * d + sub] = sx0;
+            if (a.sum_xx) a.sum_xx[(size_t)c * d + sub] = sxx0;
+        }
+    }
+    if (live1) {
+        a.x[(size_t)c * d + sub + H] = x1;
+        if (MOMENTS) {
+            if (a.sum_x) a.sum_x[(size_t)c * d + sub + H] = sx1;
+            if (a.sum_xx) a.sum_xx[(size_t)c * d + sub + H] = sxx1;
+        }
+    }
+    if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
+}
+
 // ---- per-point covariance log-density -------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -573,6 +725,20 @@ extern "C" int cusmc_mh_chains_general_dev(cusmc_ctx *ctx, int kind, int64_t C, 
     const bool philox = z_dev == nullptr;
     const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
     const bool fast = philox && ctx->chain_fast_noise;
+    if (pad == 32 && CUSMC_GENERAL_DUAL != 0) {
+        // two chains per warp (mh_general_dual_kernel)
+        const unsigned grid2 = (unsigned)((C + kWarpsPerBlock * 2 - 1) / (kWarpsPerBlock * 2));
+#define CUSMC_DUAL_GO(PH, MO, FA) mh_general_dual_kernel<PH, MO, FA><<<grid2, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga)
+        if (fast && moments) CUSMC_DUAL_GO(true, true, true);
+        else if (fast) CUSMC_DUAL_GO(true, false, true);
+        else if (philox && moments) CUSMC_DUAL_GO(true, true, false);
+        else if (philox) CUSMC_DUAL_GO(true, false, false);
+        else if (moments) CUSMC_DUAL_GO(false, true, false);
+        else CUSMC_DUAL_GO(false, false, false);
+#undef CUSMC_DUAL_GO
+        CUSMC_LAUNCHED(ctx);
+        return CUSMC_OK;
+    }
 #define CUSMC_GEN_LAUNCH(DD, PH, MO) \
     mh_general_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(ga)
 #define CUSMC_GEN_CASE(DD)                                                                           \

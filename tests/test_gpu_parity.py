@@ -1138,6 +1138,8 @@ def test_mh_chains_device_rng_matches_oracle_mirror(ctx, orc, kind, nu, d):
 
 @pytest.mark.parametrize("kind,nu,d,shared,Cn,steps", [("mvn", 0.0, 2, False, 257, 40), ("mvt", 5.0, 8, True, 257, 40),
                                                        ("mvn", 0.0, 17, False, 100, 40),
+                                                       ("mvn", 0.0, 25, True, 101, 30),         # two-rows-per-lane kernel,
+                                                       ("mvt", 5.0, 16, False, 65, 30),         # odd chain counts
                                                        ("mvt", 5.0, 32, False, 1024, 100)])     # C3's shape, 1024 x 100
 def test_mh_chains_general_proposal_bit_exact(ctx, orc, kind, nu, d, shared, Cn, steps):
     """The random walk whose proposal does not use the target's factor (x' = x + s z, optionally scaled per
@@ -1215,12 +1217,14 @@ def test_mh_chains_throughput_noise_law(ctx, general, kind, nu):
     assert np.all(np.abs(var / target_var - 1.0) < (0.1 if kind == "mvt" else 0.05))
 
 
-def test_mh_chains_general_device_rng(ctx, orc):
-    """Device-drawn general chains: the oracle regenerates the kernel's Philox draws (bit-exact decisions),
-    and the chains' time-averaged moments match the MVN target's."""
+@pytest.mark.parametrize("d", [5, 21, 32])
+def test_mh_chains_general_device_rng(ctx, orc, d):
+    """Device-drawn general chains: the oracle regenerates the kernel's Philox draws (bit-exact decisions; d > 16
+    runs the two-rows-per-lane kernel, whose lanes draw the blocks of two components), and the chains'
+    time-averaged moments match the MVN target's."""
     import torch
-    rng = np.random.default_rng(4242)
-    d, Cn, steps, seed = 5, 48, 70, 313
+    rng = np.random.default_rng(4242 + d)
+    Cn, steps, seed = 47, 70, 313
     L = np.stack([np.linalg.cholesky(spd(rng, d)) for _ in range(Cn)])
     mu = rng.standard_normal((Cn, d))
     x0 = mu + rng.standard_normal((Cn, d))
@@ -1229,14 +1233,18 @@ def test_mh_chains_general_device_rng(ctx, orc):
     for c in range(Cn):
         for s in range(steps):
             thr[c, s] = -float(orc.det_log(orc.rng_u01(seed, 5, s, c) + 2.0 ** -53)[0])       # CHAIN_U, (0, 1]
-    want_x, _, want_bits = orc.mh_chains_general("mvn", mu, L, x0, z, thr, 0.5, shared=False)
+    step = 1.1 / math.sqrt(d)
+    want_x, _, want_bits = orc.mh_chains_general("mvn", mu, L, x0, z, thr, step, shared=False)
     x = torch_dev(x0)
     bits = torch.zeros((Cn, steps), dtype=torch.uint8, device="cuda")
-    ctx.mh_chains_general_dev("mvn", torch_dev(mu), torch_dev(L.transpose(0, 2, 1)), x, steps, 0.5, seed=seed,
+    ctx.mh_chains_general_dev("mvn", torch_dev(mu), torch_dev(L.transpose(0, 2, 1)), x, steps, step, seed=seed,
                               accept_bits=bits)
     ctx.synchronize()
     assert np.array_equal(bits.cpu().numpy(), want_bits)
     assert np.array_equal(x.cpu().numpy(), want_x)
+    assert 0.05 < want_bits.mean() < 0.95
+    if d != 5:
+        return
     # the law: many chains on one MVN target, running sums of x and x^2
     d, Cn, steps = 4, 4096, 3000
     S = spd(rng, d)
