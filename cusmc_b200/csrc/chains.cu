@@ -22,6 +22,9 @@
 namespace {
 
 constexpr int kWarpsPerBlock = 4;
+#ifndef CUSMC_CHAINS_DUAL
+#define CUSMC_CHAINS_DUAL 1
+#endif
 #ifndef CUSMC_GENERAL_DUAL
 #define CUSMC_GENERAL_DUAL 1
 #endif
@@ -205,6 +208,152 @@ mh_chains_kernel(const ChainArgs a)
             if (a.sum_xx) a.sum_xx[(size_t)c * d + sub] = sxx;
         }
     }
+    if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
+}
+
+// ---- the whitened chains at 16 < d <= 32: two components per lane, two chains per warp ----------------------
+// mh_chains_kernel<32> spends a warp on one chain and most of a step on the 32-lane butterfly of the quadratic
+// form (five double shuffles) and the accept logic -- work per WARP, not per component.  With components l and
+// l + 16 in lane l of a 16-lane group the butterfly's first stage (lanes l and l ^ 16) becomes a local addition
+// of the same two squares, four shuffle stages remain, and every warp-wide instruction of the step serves two
+// chains.  Same pairing, same (seed, chain, step, component) -> draw mapping: bit-identical to the one-row kernel
+// and to the oracle (butterfly32).  Running moments need the factor's rows in registers every step and stay on
+// the one-row kernel.
+template <bool PHILOX, bool FAST>
+__global__ void __launch_bounds__(kWarpsPerBlock * 32, 8)
+mh_chains_dual_kernel(const ChainArgs a)
+{
+    constexpr int W = 16, H = 16, G = 2;
+    __shared__ __align__(16) double s_v[kWarpsPerBlock][G][2 * H];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int grp = lane / W, sub = lane % W;
+    const int64_t c0 = ((int64_t)blockIdx.x * kWarpsPerBlock + wib) * G;
+    if (c0 >= a.C) return;
+    const int d = a.d;                               // 16 < d <= 32
+    const bool active = c0 + grp < a.C;
+    const int64_t c = active ? c0 + grp : a.C - 1;
+    const bool live0 = active, live1 = active && sub + H < d;
+    const double *Lc = a.shared ? a.L : a.L + (size_t)c * d * d;
+    const double *mc = a.shared ? a.mu : a.mu + (size_t)c * d;
+    const double mu0 = live0 ? __ldg(mc + sub) : 0.0, mu1 = live1 ? __ldg(mc + sub + H) : 0.0;
+    // L[k][j], j <= k, of this lane's two rows (column-major storage), streamed where they are used
+    auto LA = [&](int j) { return (live0 && j <= sub) ? __ldg(Lc + (size_t)j * d + sub) : 0.0; };
+    auto LB = [&](int j) { return (live1 && j <= sub + H) ? __ldg(Lc + (size_t)j * d + sub + H) : 0.0; };
+    // x = mu + L v, row k = sum_j L[k][j] v_j with j ascending (the rows' zeros beyond the diagonal are skipped:
+    // they add exact zeros in the one-row kernel)
+    auto unwhiten = [&](double va, double vb, double &xa, double &xb) {
+        __syncwarp();
+        s_v[wib][grp][sub] = va;
+        s_v[wib][grp][sub + H] = vb;
+        __syncwarp();
+        const double *vc = s_v[wib][grp];
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 8
+        for (int j = 0; j < H; ++j) {
+            acc0 = fma(LA(j), vc[j], acc0);
+            acc1 = fma(LB(j), vc[j], acc1);
+        }
+#pragma unroll 8
+        for (int j = H; j < 2 * H; ++j) acc1 = fma(LB(j), vc[j], acc1);
+        xa = mu0 + acc0;
+        xb = mu1 + acc1;
+    };
+
+    // whiten the start: column-oriented forward substitution over the 32 columns
+    double v0 = 0.0, v1 = 0.0;
+    const double xs0 = live0 ? a.x[(size_t)c * d + sub] : 0.0, xs1 = live1 ? a.x[(size_t)c * d + sub + H] : 0.0;
+    {
+        const double rinv0 = live0 ? 1.0 / __ldg(Lc + (size_t)sub * d + sub) : 0.0;
+        const double rinv1 = live1 ? 1.0 / __ldg(Lc + (size_t)(sub + H) * d + sub + H) : 0.0;
+        double ra = live0 ? xs0 - mu0 : 0.0, rb = live1 ? xs1 - mu1 : 0.0;
+#pragma unroll 8
+        for (int j = 0; j < H; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, ra * rinv0, j, W);
+            if (j == sub) v0 = vj;
+            ra = fma(-LA(j), vj, ra);
+            rb = fma(-LB(j), vj, rb);
+        }
+#pragma unroll 8
+        for (int j = 0; j < H; ++j) {
+            const double vj = __shfl_sync(0xffffffffu, rb * rinv1, j, W);
+            if (j == sub) v1 = vj;
+            rb = fma(-LB(H + j), vj, rb);
+        }
+    }
+    // the 32-lane butterfly (16, 8, 4, 2, 1) of the one-row kernel: stage 16 pairs components l and l + 16
+    auto sumsq = [&](double a0, double a1) { return chain_sum_butterfly<W>(a0 * a0 + a1 * a1); };
+    double q = sumsq(v0, v1);
+    const double inv_nu = a.kind == CUSMC_MVT ? 1.0 / a.nu : 0.0;
+    uint32_t nacc = 0;
+
+    const double *zc = a.z ? a.z + (size_t)c * a.steps * d : nullptr;
+    double zn0 = (zc && live0) ? ld_stream(zc + sub) : 0.0, zn1 = (zc && live1) ? ld_stream(zc + sub + H) : 0.0;
+    double thr_batch = 0.0;
+    float zq0[4] = {0.f, 0.f, 0.f, 0.f}, zq1[4] = {0.f, 0.f, 0.f, 0.f};
+    auto quad_normals = [&](int s, uint32_t m, float (&zq)[4]) {
+        float n[4];
+        if constexpr (FAST) {
+            const cusmc_u32x4 rz = cusmc_rng7(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c, m);
+            cusmc_box_muller_fast(rz.v[0], rz.v[1], &n[0], &n[1]);
+            cusmc_box_muller_fast(rz.v[2], rz.v[3], &n[2], &n[3]);
+        } else {
+            const cusmc_u32x4 rz = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_Z, (uint64_t)(s + (sub & 3)), (uint64_t)c, m);
+            cusmc_box_muller_f32(rz.v[0], rz.v[1], &n[0], &n[1]);
+            cusmc_box_muller_f32(rz.v[2], rz.v[3], &n[2], &n[3]);
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int pick = (lane & 3) ^ r;
+            const float val = pick == 0 ? n[0] : pick == 1 ? n[1] : pick == 2 ? n[2] : n[3];
+            zq[r] = __shfl_xor_sync(0xffffffffu, val, r);
+        }
+    };
+    for (int s = 0; s < a.steps; ++s) {
+        double z0, z1, thr;
+        if (PHILOX) {
+            if ((s & (W - 1)) == 0) {
+                const cusmc_u32x4 r = cusmc_rng(a.seed, CUSMC_STREAM_CHAIN_U, (uint64_t)(s + sub), (uint64_t)c, 0);
+                const double e = -cusmc_det_log(cusmc_u01_open0(r.v[0], r.v[1]));
+                thr_batch = a.kind == CUSMC_MVT ? cusmc_det_exp((e + e) / (a.nu + (double)d)) : e;
+            }
+            thr = __shfl_sync(0xffffffffu, thr_batch, s & (W - 1), W);
+            if ((s & 3) == 0) {
+                quad_normals(s, (uint32_t)(sub >> 2), zq0);
+                quad_normals(s, (uint32_t)(sub >> 2) + (uint32_t)(H / 4), zq1);
+            }
+            const int r = (lane & 3) ^ (s & 3);
+            const float f0 = r == 0 ? zq0[0] : r == 1 ? zq0[1] : r == 2 ? zq0[2] : zq0[3];
+            const float f1 = r == 0 ? zq1[0] : r == 1 ? zq1[1] : r == 2 ? zq1[2] : zq1[3];
+            z0 = live0 ? (double)f0 : 0.0;
+            z1 = live1 ? (double)f1 : 0.0;
+        } else {
+            z0 = zn0;
+            z1 = zn1;
+            if (s + 1 < a.steps) {
+                if (live0) zn0 = ld_stream(zc + (size_t)(s + 1) * d + sub);
+                if (live1) zn1 = ld_stream(zc + (size_t)(s + 1) * d + sub + H);
+            }
+            thr = __ldg(a.thr + (size_t)c * a.steps + s);
+        }
+        const double vp0 = fma(a.step_size, z0, v0), vp1 = fma(a.step_size, z1, v1);
+        const double qp = sumsq(vp0, vp1);
+        bool accept;
+        if (a.kind == CUSMC_MVT)
+            accept = fma(qp, inv_nu, 1.0) < thr * fma(q, inv_nu, 1.0);
+        else
+            accept = 0.5 * (qp - q) < thr;
+        if (accept) {
+            v0 = vp0;
+            v1 = vp1;
+            q = qp;
+            ++nacc;
+        }
+        if (a.accept_bits && sub == 0 && active) a.accept_bits[(size_t)c * a.steps + s] = (uint8_t)accept;
+    }
+    double xu0, xu1;
+    unwhiten(v0, v1, xu0, xu1);
+    if (live0) a.x[(size_t)c * d + sub] = nacc ? xu0 : xs0;            // a chain that never moved is left untouched
+    if (live1) a.x[(size_t)c * d + sub + H] = nacc ? xu1 : xs1;
     if (a.n_accept && sub == 0 && active) a.n_accept[c] = nacc;
 }
 
@@ -673,6 +822,15 @@ extern "C" int cusmc_mh_chains_dev(cusmc_ctx *ctx, int kind, int64_t C, int d, i
     const bool philox = z_dev == nullptr;
     const bool moments = sum_x_dev != nullptr || sum_xx_dev != nullptr;
     const bool fast = philox && ctx->chain_fast_noise;
+    if (pad == 32 && !moments && CUSMC_CHAINS_DUAL != 0) {
+        // two chains per warp (mh_chains_dual_kernel)
+        const unsigned grid2 = (unsigned)((C + kWarpsPerBlock * 2 - 1) / (kWarpsPerBlock * 2));
+        if (fast) mh_chains_dual_kernel<true, true><<<grid2, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        else if (philox) mh_chains_dual_kernel<true, false><<<grid2, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        else mh_chains_dual_kernel<false, false><<<grid2, kWarpsPerBlock * 32, 0, ctx->stream>>>(a);
+        CUSMC_LAUNCHED(ctx);
+        return CUSMC_OK;
+    }
 #define CUSMC_CHAIN_LAUNCH(DD, PH, MO) \
     mh_chains_kernel<DD, PH, MO><<<grid, kWarpsPerBlock * 32, 0, ctx->stream>>>(a)
 #define CUSMC_CHAIN_CASE(DD)                                                                         \
