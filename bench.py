@@ -812,7 +812,7 @@ def main():
                      "launch": "each call is launched as a programmatic dependent of the one before it on the stream "
                                "(griddepcontrol): its blocks are dispatched while the predecessor drains and touch memory "
                                "only after it has completed; kernel_ms = timed region / launches in that stream of calls. "
-                               "One launch alone (ncu launch list, profiles/r02k_launches_summary.md): 22.4 us = 0.97; the "
+                               "One launch alone (ncu launch list, profiles/r02m_launches_summary.md): 22.4 us = 0.97; the "
                                "same stream launched the ordinary way: 23.8 us = 0.92. The peak is a COPY bandwidth "
                                "(read + write); this kernel reads 16 words per word it writes"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": N_POINTS * DIM * 8,
