@@ -58,14 +58,17 @@ if which in ("all", "pfmore"):
         pf.close()
 
 if which in ("all", "mh"):
-    Cn, d, steps = 65536, 32, 20
+    Cn, d, steps = 65536, 32, 200
     A = torch.randn((Cn, d, d), dtype=torch.float64, device="cuda")
     L = torch.linalg.cholesky(A @ A.transpose(1, 2) / d + torch.eye(d, dtype=torch.float64, device="cuda"))
     Lcm = L.transpose(1, 2).contiguous()
     mu = torch.zeros((Cn, d), dtype=torch.float64, device="cuda")
     x = (L @ torch.randn((Cn, d, 1), dtype=torch.float64, device="cuda")).squeeze(-1).contiguous()
-    ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=3)
-    ctx.mh_chains_general_dev("mvt", mu, Lcm, x, steps, 1.2 / np.sqrt(d), nu=5.0, seed=4)
+    for rep in (True, False):        # the host-reproducible generator, then the throughput one
+        ctx.set_chain_noise(reproducible=rep)
+        ctx.mh_chains_dev("mvt", mu, Lcm, x, steps, 0.3, nu=5.0, seed=3)
+        ctx.mh_chains_general_dev("mvt", mu, Lcm, x, steps, 1.2 / np.sqrt(d), nu=5.0, seed=4)
+    ctx.set_chain_noise(reproducible=True)
     torch.cuda.synchronize()
 
 if which in ("all", "metropolis"):
