@@ -409,3 +409,74 @@ def test_metropolis_c2_proposals(orc):
     assert np.all(np.abs(bins - want) < 6 * np.sqrt(32 * want))
     u1, j1 = orc.rng_metropolis(3, 1, N, B)
     assert np.array_equal(u, u1) and not np.array_equal(j, j1)      # the lane's own uniform is the plain rule's
+
+
+def test_rejection_resampler_law(orc):
+    """Rejection resampler (include/cusmc_b200.h; the unbiased relative of ref: src/samplers.cpp:21-35):
+    a particle keeps itself with probability w_i / wmax, otherwise the accepted proposal is a draw from
+    w / sum(w), so E[#children of k] = w_k / wmax + (N - sum(w) / wmax) w_k / sum(w)."""
+    rng = np.random.default_rng(11)
+    N = 1 << 15
+    w = rng.random(N) ** 2 + 1e-3
+    w[::97] = 0.0                                                 # dead particles never survive
+    wmax = float(w.max())
+    a = orc.resample_rejection(w, wmax, seed=5, step=3)
+    assert a.dtype == np.uint32 and a.max() < N
+    assert np.all(w[a] > 0.0)
+    assert np.array_equal(a, orc.resample_rejection(w, wmax, seed=5, step=3))     # counter-based: reproducible
+    assert not np.array_equal(a, orc.resample_rejection(w, wmax, seed=5, step=4))
+    keep = a == np.arange(N)
+    p_keep = w / wmax
+    # #self-survivors vs its expectation (proposals that land on i itself add at most 1/N each)
+    assert abs(keep.sum() - p_keep.sum()) < 6 * np.sqrt((p_keep * (1 - p_keep)).sum()) + 4
+    counts = np.bincount(a, minlength=N).astype(float)
+    want = p_keep + (N - p_keep.sum()) * w / w.sum()
+    order = np.argsort(w)
+    bins = np.add.reduceat(counts[order], np.arange(0, N, 1024))
+    wbin = np.add.reduceat(want[order], np.arange(0, N, 1024))
+    assert np.all(np.abs(bins - wbin) < 6 * np.sqrt(wbin) + 6)
+    # equal weights: everybody is accepted at the first attempt
+    assert np.array_equal(orc.resample_rejection(np.full(257, 0.25), 0.25, 1, 0), np.arange(257))
+    # cap = 1: one attempt, then the particle holds the first proposal
+    a1 = orc.resample_rejection(w, wmax, seed=5, step=3, cap=1)
+    u, j = orc.rng_metropolis(5, 3, N, 1)
+    assert np.array_equal(a1, np.where(u[:, 0] <= w / wmax, np.arange(N), j[:, 0]))
+
+
+@pytest.mark.parametrize("kind,nu", [("mvn", 0.0), ("mvt", 5.0)])
+def test_perpoint_batch_equals_shared_batch(orc, kind, nu):
+    """Per-point parameters (C3's per-chain covariance): the per-point form with every point carrying the
+    same (mu, Sigma) is the shared form; with its own Sigma a point equals a one-point shared call."""
+    rng = np.random.default_rng(12)
+    N, d = 64, 5
+    x, mu, S = rng.standard_normal((N, d)), rng.standard_normal(d), spd(rng, d)
+    shared = orc.pdf_batch(kind, x, mu, S, nu, log=True)
+    pp = orc.pdf_batch_perpoint(kind, x, np.tile(mu, (N, 1)), np.tile(S, (N, 1, 1)), nu, log=True)
+    assert np.max(np.abs(pp - shared)) <= 1e-12 * np.max(np.abs(shared))
+    S_all = np.stack([spd(rng, d) for _ in range(N)])
+    mu_all = rng.standard_normal((N, d))
+    pp = orc.pdf_batch_perpoint(kind, x, mu_all, S_all, nu, log=True)
+    for i in (0, 17, N - 1):
+        one = orc.pdf_batch(kind, x[i:i + 1], mu_all[i], S_all[i], nu, log=True)[0]
+        assert abs(pp[i] - one) <= 1e-12 * abs(one)
+    lin = orc.pdf_batch_perpoint(kind, x, mu_all, S_all, nu)
+    assert np.max(np.abs(np.log(lin) - pp)) < 1e-12 * np.max(np.abs(pp))
+
+
+def test_normalising_constants(orc):
+    """getNorm (ref: src/statistics.cc.cpp:205-211 MVN, :332-340 MVT incl. the float nu + n of Q9)
+    against the closed forms; the density at the mean IS the constant."""
+    rng = np.random.default_rng(13)
+    for d in (1, 2, 3, 8, 16):
+        S = spd(rng, d)
+        det = np.linalg.det(S)
+        want = (2 * math.pi) ** (-d / 2) / math.sqrt(det)
+        assert abs(orc.mvn_norm(S) - want) <= 1e-13 * want
+        assert abs(orc.pdf_batch("mvn", np.zeros((1, d)), None, S, faithful=True)[0] - want) <= 1e-13 * want
+        for nu in (1.0, 3.0, 5.0, 7.5):
+            lg = math.lgamma((nu + d) / 2) - math.lgamma(nu / 2) - d / 2 * math.log(math.pi * nu) - 0.5 * math.log(det)
+            got = orc.mvt_norm(S, nu)
+            assert abs(got - math.exp(lg)) <= 1e-12 * got
+            assert abs(orc.pdf_batch("mvt", np.zeros((1, d)), None, S, nu, faithful=True)[0] - got) <= 1e-13 * got
+    assert round(orc.mvn_norm(np.eye(2)), 7) == 0.1591549          # CuSMC/CuSMC.tex:104
+    assert round(orc.mvt_norm(np.eye(3), 3.0), 8) == 0.07799708    # CuSMC/CuSMC.tex:141
