@@ -39,6 +39,15 @@ def test_exchange_protocol_world2_gloo(tmp_path, N):
     assert (tmp_path / "ok0").exists() and (tmp_path / "ok1").exists()
 
 
+@pytest.mark.parametrize("N,world", [(5003, 3), (5, 4)])
+def test_exchange_protocol_ragged_worlds_gloo(tmp_path, N, world):
+    """Three ranks with a ragged last shard, and more ranks than a tiny cloud fills (one rank empty)."""
+    import torch.multiprocessing as mp
+    from sharded_workers import exchange_protocol_worker
+    mp.spawn(exchange_protocol_worker, args=(world, free_port(), N, str(tmp_path)), nprocs=world, join=True)
+    assert all((tmp_path / ("ok%d" % r)).exists() for r in range(world))
+
+
 def test_sharded_filter_needs_a_process_group():
     with pytest.raises(RuntimeError):
         sharded.ShardedParticleFilter(None, 8, np.zeros((2, 3)), None, None, None, None, None, None)
