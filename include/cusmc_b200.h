@@ -337,12 +337,14 @@ typedef struct cusmc_filter_config {
     /* Sharded runs (one process per GPU): N is the GLOBAL particle count; rank r of `world` owns the
      * global slots r*per .. min((r+1)*per, N) - 1, per = ceil(N / world).  world <= 1: one GPU. */
     int rank, world;
-    /* cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (three grid
-     * barriers per step instead of four launches; log-weights and the weight image stay in shared
-     * memory) when the configuration allows it: one GPU, systematic resampling, Normal noise,
-     * d == dy in {2, 4}, device-drawn noise, no history, N small enough for one tile of
-     * <= 4096 particles per resident block (1.2 M particles on a B200).  Results are bit-identical
-     * to the four-launch step (25 vs 36 us per 10^6-particle step).  0 = automatic, -1 = never. */
+    /* cusmc_filter_run executes the whole run as ONE persistent cooperative kernel (one grid barrier
+     * per step instead of two launches; every block keeps its tile of the weight image and runs the
+     * tile update itself) when the configuration allows it: one GPU, systematic resampling at every
+     * step, Normal noise, d == dy in {2, 4, 8}, device-drawn noise, no history, no posterior-mean
+     * summary (the ESS and likelihood sums of every step are recorded either way), and a cloud that
+     * fits one tile per resident block (cusmc_filter_tile_size() reports the tile).
+     * Results are bit-identical to the per-step path run with that tile_size (19.6 vs 36 us per
+     * 10^6-particle step).  0 = automatic, -1 = never. */
     int persistent;
     /* Adaptive resampling (systematic resampler only): 0 (default) = resample at every step, as the
      * reference does (src/mcmc.cpp:295); in (0, 1] = resample at step t only when the effective

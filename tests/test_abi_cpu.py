@@ -133,3 +133,35 @@ def test_bench_reference_arm_runs_on_cpu():
     line = json.loads(out)
     assert line["impl"] == "reference" and line["metric"] == "mvn_logpdf_evals_per_sec" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_struct_layouts_match_the_binding(tmp_path):
+    """cusmc_filter_config / cusmc_filter_draws cross the ABI by pointer: the ctypes mirrors must have the
+    C compiler's size and field offsets (a drifted field would silently shift every later argument)."""
+    import cusmc_b200._lib as L
+    structs = {"cusmc_filter_config": L.FilterConfig, "cusmc_filter_draws": L.FilterDraws}
+    lines = []
+    for cname, cls in structs.items():
+        lines.append('printf("%s %%zu\\n", sizeof(%s));' % (cname, cname))
+        for f, _ in cls._fields_:
+            lines.append('printf("%s.%s %%zu\\n", offsetof(%s, %s));' % (cname, f, cname, f))
+    src = tmp_path / "layout.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "cusmc_b200.h"\nint main(void){\n'
+                   + "\n".join(lines) + "\nreturn 0;}\n")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["/usr/bin/gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    got = dict(l.split() for l in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in structs.items():
+        assert int(got[cname]) == C.sizeof(cls), cname
+        for f, _ in cls._fields_:
+            assert int(got["%s.%s" % (cname, f)]) == getattr(cls, f).offset, "%s.%s" % (cname, f)
+    # and the header has no field the binding lacks
+    hdr = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for cname, cls in structs.items():
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (cname, cname), hdr, flags=re.S).group(1)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if decl:
+                names += [re.sub(r"[\s\*]", "", n).split(" ")[-1] for n in re.sub(r"^(const\s+)?\w+\s+", "", decl).split(",")]
+        assert names == [f for f, _ in cls._fields_], (cname, names)
