@@ -480,3 +480,22 @@ def test_normalising_constants(orc):
             assert abs(orc.pdf_batch("mvt", np.zeros((1, d)), None, S, nu, faithful=True)[0] - got) <= 1e-13 * got
     assert round(orc.mvn_norm(np.eye(2)), 7) == 0.1591549          # CuSMC/CuSMC.tex:104
     assert round(orc.mvt_norm(np.eye(3), 3.0), 8) == 0.07799708    # CuSMC/CuSMC.tex:141
+
+
+def test_reference_clt_sampler_is_a_scaled_normal():
+    """Quirk Q1 (ref: src/statistics.cc.cpp:245-256): the CPU sampler sums n = 200 draws of (z + 1) / 2 with
+    z ~ N(0, 1), subtracts n / 2 and divides by sqrt(n / 12).  Algebraically that is sqrt(3) * (sum z / sqrt n):
+    a N(0, 3) draw -- what cfg.noise_scale = sqrt(3) reproduces with one standard normal per component
+    (and why injected `xi` are "effective standard draws", oracle/cusmc_oracle.h)."""
+    rng = np.random.default_rng(14)
+    n_iter, d, reps = 200, 3, 20000
+    z = rng.standard_normal((reps, n_iter, d))
+    s = np.zeros((reps, d))
+    for i in range(n_iter):                                       # the reference's loop, line by line
+        x = 0.5 * (z[:, i, :] + 1.0)
+        s += x
+    s = s - n_iter / 2
+    x = s / math.sqrt(n_iter / 12)
+    xi = z.sum(axis=1) / math.sqrt(n_iter)                        # one N(0, 1) draw per component
+    assert np.max(np.abs(x - math.sqrt(3.0) * xi)) < 1e-11
+    assert abs(x.var() - 3.0) < 0.06 and abs(x.mean()) < 0.03
